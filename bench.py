@@ -1,0 +1,295 @@
+#!/usr/bin/env python
+"""Headline benchmark: EEG windows/s for DDIM-50 sampling (BASELINE.json metric), config 3 of
+SURVEY.md section 8d -- batch 1024 of [1,768] latents, config_ldm.yaml UNet, AEKL 2-2-4 decode to
+[1,3072] -- per GPU (weak scaling), synthetic noise, seeded random weights.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--math M]
+
+A "step" is one full sampling pass over one batch: 50 denoise iterations (one CUDA graph launch each)
++ the autoencoder decode (+ one NCCL all-gather of the decoded windows when N > 1).
+Prints ONE JSON line on rank 0.  See DESIGN.md section "Measurement" for every field.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "synthetic-sleep-eeg-signal-generation-using-latent-diffusion-models_b200")
+for _p in (ROOT, PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+# algorithmic work per window: UNet 13.90 GFLOP and 25.2 MB block-fused
+# fp32 activation traffic per forward per sample
+UNET_GFLOP_PER_FWD = 13.90
+UNET_MB_PER_FWD = 25.2
+DDIM_STEPS = 50
+T_LATENT = 768
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tc_burst=d["bf16_tflops"], tc_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    src="measured")
+    return dict(hbm=6650.0, tc_burst=1590.0, tc_sustained=1400.0, src="fallback")   # B200_PROFILING.md fallback
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc = index, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=10)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, smax, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "reasons": sorted(reasons),
+                "power_w_max": max(pw), "samples": len(sm)}
+
+
+def _oracle_models():
+    from oracle import aekl as oa, unet as ou
+    ucfg, acfg = ou.full_cfg(), oa.full_cfg()
+    return ucfg, ou.make_unet_state_dict(ucfg, 0), acfg, oa.make_aekl_state_dict(acfg, 42)
+
+
+def _cpu_ddim_windows_per_s(B, reps, warm):
+    """The reference's CPU implementation of the path (oracle port: src/models/unet.py restated +
+    restated MONAI AEKL/DDIM), all host threads, fp32, no_grad.  Returns (windows/s list, threads)."""
+    import torch
+    from oracle import sample as osamp
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    ucfg, usd, acfg, asd = _oracle_models()
+    noise = torch.randn(B, 1, T_LATENT, generator=torch.Generator().manual_seed(0))
+    vals = []
+    for i in range(warm + reps):
+        t0 = time.perf_counter()
+        osamp.ddim_sample(ucfg, usd, noise, DDIM_STEPS, acfg, asd, crop=36)
+        dt = time.perf_counter() - t0
+        if i >= warm:
+            vals.append(B / dt)
+    return vals, threads
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    B = args.ref_batch
+    t0 = time.perf_counter()
+    vals, threads = _cpu_ddim_windows_per_s(B, args.steps, min(args.warmup, 1))
+    total = time.perf_counter() - t0
+    v = B * len(vals) / sum(B / x for x in vals)
+    line = {
+        "impl": "reference", "metric": "EEG windows/sec DDIM-50 sampling", "value": v, "unit": "windows/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * B / v,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"DDIM-50 sampling + AEKL 2-2-4 decode, config_ldm.yaml UNet, [B,1,768] latents -> [B,1,3000] windows; "
+                               f"bounded sample of B={B} windows per step on the host CPU"},
+        "cpu_baseline": {"value": v, "unit": "windows/s", "cores": threads, "kind": "port",
+                         "sample": f"{B} windows x DDIM-50 + decode per step, {len(vals)} steps, torch {threads} threads"},
+        "e2e": {"value": v, "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": total,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import eegldm
+    from eegldm import _lib
+    from oracle.sample import SAMPLER_DEFAULTS
+    import ctypes as C
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: eegldm has no CPU fallback")
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    ucfg, usd, acfg, asd = _oracle_models()     # seeded random-init weights (no checkpoint ships)
+    unet = eegldm.UNetModel(**ucfg, math=args.math)
+    unet.load_state_dict(usd)
+    unet = unet.to(dev).eval()
+    aekl = eegldm.AutoencoderKL(**acfg)
+    aekl.load_state_dict(asd)
+    aekl = aekl.to(dev).eval()
+    sched = eegldm.DDIMScheduler(**SAMPLER_DEFAULTS)
+    sched.set_timesteps(DDIM_STEPS)
+
+    B = args.batch
+    noise_host = torch.randn(B, 1, T_LATENT, generator=torch.Generator().manual_seed(rank)).pin_memory()
+    noise = noise_host.to(dev)
+    gathered = torch.empty((world * B, 1, 3072), device=dev) if world > 1 else None
+    out_host = torch.empty((B, 1, 3072), dtype=torch.float32).pin_memory()
+
+    def step_device():
+        y = eegldm.ddim_sample(unet, sched, noise, DDIM_STEPS, aekl)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, y)      # the single collective
+        return y
+
+    def step_e2e():
+        eegldm.ddim_sample_host(unet, sched, noise_host, DDIM_STEPS, aekl, out_host=out_host, device=dev)
+        if world > 1:
+            dist.barrier()
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)     # max over ranks
+        return float(ms.item())
+
+    for _ in range(args.warmup):
+        step_device()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    l0 = eegldm.launch_count()
+    ms = timed(step_device, args.steps)
+    launches = eegldm.launch_count() - l0
+    clk = clocks.stop() if rank == 0 else None
+    value = world * B * args.steps / (ms / 1e3)
+
+    step_e2e()                                            # warm the host path (allocator pools)
+    ms_e2e = timed(step_e2e, args.steps)
+    e2e = world * B * args.steps / (ms_e2e / 1e3)
+
+    # ---- roofline leg: per-kernel-family device time measured live with CUDA events on the launch stream
+    roof, prof = None, None
+    if rank == 0:
+        L = eegldm.lib()
+        pb = min(B, args.profile_batch)
+        L.eegldm_set_graphs(0)
+        L.eegldm_profile_enable(1)
+        psteps = 2
+        eegldm.ddim_sample(unet, sched, noise[:pb], psteps, aekl)
+        torch.cuda.synchronize(dev)
+        fam = {}
+        for kind, name in enumerate(("conv", "groupnorm", "attention", "other")):
+            m, f, b, n = C.c_double(), C.c_double(), C.c_double(), C.c_int64()
+            _lib.check(L.eegldm_profile_read(kind, C.byref(m), C.byref(f), C.byref(b), C.byref(n)))
+            fam[name] = dict(ms=m.value, flops=f.value, bytes=b.value, launches=n.value)
+        L.eegldm_profile_enable(0)
+        L.eegldm_set_graphs(1)
+        tot = sum(v["ms"] for v in fam.values()) or 1.0
+        conv = fam["conv"]
+        peaks = _peaks()
+        peak_tc = peaks["tc_sustained"]
+        ach = conv["flops"] / (conv["ms"] / 1e3) / 1e12 if conv["ms"] else 0.0
+        roof = {"bound": "tensor", "kernel": "conv implicit-GEMM (" + args.math + ")", "achieved": ach, "peak": peak_tc,
+                "unit": "TFLOP/s", "frac": ach / peak_tc, "traffic": None, "peak_source": peaks["src"] + " bf16 sustained",
+                "avg_launch_ms": conv["ms"] / max(conv["launches"], 1), "share_of_step": conv["ms"] / tot,
+                "algorithmic_flops_per_launch": conv["flops"] / max(conv["launches"], 1),
+                "profile_batch": pb,
+                # whole-step view against both ceilings (13.90 GFLOP, 25.2 MB per forward per sample)
+                "step_tensor_frac": value / world * DDIM_STEPS * UNET_GFLOP_PER_FWD * 1e9 / (peak_tc * 1e12),
+                "step_hbm_frac": value / world * DDIM_STEPS * UNET_MB_PER_FWD * 1e6 / (peaks["hbm"] * 1e9)}
+        prof = {k: {"ms": round(v["ms"], 3), "share": round(v["ms"] / tot, 4), "launches": v["launches"],
+                    "tflops": (v["flops"] / (v["ms"] / 1e3) / 1e12 if v["ms"] else 0.0),
+                    "gbs": (v["bytes"] / (v["ms"] / 1e3) / 1e9 if v["ms"] else 0.0)} for k, v in fam.items()}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        vals, threads = _cpu_ddim_windows_per_s(args.ref_batch, 1, 0)
+        cpu = {"value": vals[0], "unit": "windows/s", "cores": threads, "kind": "port",
+               "sample": f"{args.ref_batch} windows x DDIM-50 + decode, oracle port (reference unet.py restated), torch {threads} threads"}
+
+    if rank == 0:
+        line = {
+            "metric": "EEG windows/sec DDIM-50 sampling", "value": value, "unit": "windows/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "config 3: DDIM-50 sampling, batch %d per GPU of [1,768] latents, config_ldm.yaml UNet "
+                                   "(30.5M params), AEKL 2-2-4 decode -> [B,1,3072]" % B,
+                       "math": args.math, "batch_per_gpu": B, "ddim_steps": DDIM_STEPS,
+                       "parallelism": f"batch-shard x{world}, one all-gather of decoded windows" if world > 1 else "single GPU",
+                       "l2": "activations per launch (>= 400 MB at B=1024) exceed the 126 MB L2; no explicit flush"},
+            "e2e": {"value": e2e, "unit": "windows/s", "h2d_bytes_per_step": world * noise_host.numel() * 4,
+                    "d2h_bytes_per_step": world * out_host.numel() * 4, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "kernel_profile": prof, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=1024, help="windows per GPU per step (config 3: 1024)")
+    ap.add_argument("--math", default=os.environ.get("EEGLDM_BENCH_MATH", "fp32"), help="fp32 | bf16x3 (both parity-green)")
+    ap.add_argument("--ref-batch", type=int, default=8, help="windows per CPU-baseline step (bounded sample)")
+    ap.add_argument("--profile-batch", type=int, default=1024)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,172 @@
+/* eegldm -- C ABI of the B200-native 1-D latent-diffusion engine for sleep-EEG windows.
+ *
+ * The reference (bruAristimunha/Synthetic-Sleep-EEG-Signal-Generation-using-Latent-Diffusion-Models)
+ * has no FFI: its boundary for this path is the Python nn.Module call surface.  Each entry point below
+ * names the reference interface (file:line under /root/reference) it replaces; the ctypes binding that
+ * re-exposes the reference's Python signatures on top of this ABI lives in
+ * <package>/eegldm/ and is described in INTEGRATION.md.
+ *
+ * Conventions
+ *  - All tensors are fp32, contiguous, in the REFERENCE layout: [B, C, T] (PyTorch NCL).
+ *  - "dev" pointers are device pointers on the current CUDA device (e.g. torch.Tensor.data_ptr());
+ *    "host" pointers are ordinary host memory.  The caller owns every I/O buffer; the engine owns
+ *    weights and workspace.
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Calls taking dev
+ *    pointers are asynchronous on that stream and never synchronise; the *_host variants copy in/out
+ *    and return after the result is in host memory.
+ *  - Return value: 0 on success, a negative eegldm_status otherwise; eegldm_last_error() returns a
+ *    thread-local message.  Nothing throws or aborts across the ABI.
+ *  - A handle is not thread-safe; use one handle per (device, stream).
+ *  - There is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *    EEGLDM_ERR_CUDA.
+ */
+#ifndef EEGLDM_H_
+#define EEGLDM_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    EEGLDM_OK = 0,
+    EEGLDM_ERR_INVALID = -1,      /* bad argument / unsupported configuration */
+    EEGLDM_ERR_SHAPE = -2,        /* tensor shape does not match the configuration */
+    EEGLDM_ERR_MISSING = -3,      /* a state_dict entry was never loaded / unknown name */
+    EEGLDM_ERR_CUDA = -4,         /* CUDA runtime error (message has the cudaError string) */
+    EEGLDM_ERR_NOMEM = -5
+} eegldm_status;
+
+/* Arithmetic used by the convolution GEMMs.
+ *  FP32_SIMT : fp32 FMA on the CUDA cores -- exact-order-independent fp32, the parity baseline.
+ *  BF16X3_TC : tcgen05 tensor cores, each fp32 operand split into bf16 hi+lo, 3 products
+ *              (hi*hi + hi*lo + lo*hi), fp32 accumulate in TMEM: ~2^-16 relative operand error.
+ *  BF16_TC   : single bf16 product (fast mode; does NOT meet the fp32 parity tolerance). */
+typedef enum { EEGLDM_MATH_FP32_SIMT = 0, EEGLDM_MATH_BF16X3_TC = 1, EEGLDM_MATH_BF16_TC = 2 } eegldm_math;
+
+const char* eegldm_last_error(void);
+const char* eegldm_version(void);
+/* number of CUDA kernels launched by this library since process start (bench.py's gpu_launches) */
+int64_t eegldm_launch_count(void);
+
+/* Live per-kernel profile (bench.py's roofline leg).  While enabled, every launch made outside CUDA-graph
+ * capture is bracketed by CUDA events on the launching stream.  eegldm_profile_read sums, for one kernel
+ * family (0 = conv implicit-GEMM, 1 = GroupNorm statistics, 2 = attention, 3 = other), the measured
+ * milliseconds, the ALGORITHMIC flops and HBM bytes and the launch count since enable. */
+int eegldm_profile_enable(int on);
+int eegldm_profile_read(int kind, double* ms, double* flops, double* bytes, int64_t* launches);
+
+/* ------------------------------------------------------------------------------------------------
+ * Denoiser: replaces UNetModel (src/models/unet.py:330-563).  Fields mirror the constructor kwargs
+ * (unet.py:331-351) that the reference's configs set (config/config_ldm.yaml:30-43). */
+typedef struct {
+    int32_t image_size;                 /* informational (unet.py:357); any T divisible by 2^(levels-1) runs */
+    int32_t in_channels;
+    int32_t model_channels;
+    int32_t out_channels;
+    int32_t num_res_blocks;
+    int32_t n_attention_resolutions;
+    int32_t attention_resolutions[8];
+    int32_t n_channel_mult;
+    int32_t channel_mult[8];
+    int32_t num_heads;
+    int32_t num_head_channels;          /* -1 = use num_heads */
+    int32_t num_heads_upsample;         /* -1 = num_heads; heads of the output-block attention (unet.py:353-354,476) */
+    int32_t resblock_updown;            /* 1 = ResBlock up/down (config_ldm.yaml:43) */
+    int32_t conv_resample;              /* used when resblock_updown = 0 */
+    int32_t use_scale_shift_norm;       /* must be 0 (no reference config enables it) */
+} eegldm_unet_cfg;
+
+typedef struct eegldm_unet eegldm_unet;
+
+int eegldm_unet_create(const eegldm_unet_cfg* cfg, eegldm_unet** out);
+void eegldm_unet_destroy(eegldm_unet* h);
+/* number of state_dict entries the configuration expects and the name/shape of entry i
+ * (order = the reference's registration order; key grammar: SURVEY.md section 8c) */
+int eegldm_unet_num_params(const eegldm_unet* h);
+int eegldm_unet_param_info(const eegldm_unet* h, int i, const char** name, int64_t shape[4], int* ndim);
+/* nn.Module.load_state_dict, one entry per call (host pointer, reference [Cout,Cin,k] layout);
+ * the engine copies and repacks. */
+int eegldm_unet_load(eegldm_unet* h, const char* name, const float* host, const int64_t* shape, int ndim);
+/* verifies every entry was loaded, uploads and packs the weights (strict=True semantics) */
+int eegldm_unet_finalize(eegldm_unet* h);
+int eegldm_unet_set_math(eegldm_unet* h, eegldm_math mode);
+/* UNetModel.forward(x, timesteps)  (unet.py:512-563)
+ *   x_dev   [B, in_channels, T] ; out_dev [B, out_channels, T]
+ *   timesteps_host: nt values, nt == 1 (broadcast, sample_trials.py:158) or nt == B (training.py:430);
+ *   float, as the reference converts with .float() (unet.py:28). */
+int eegldm_unet_forward(eegldm_unet* h, const float* x_dev, const float* timesteps_host, int nt, float* out_dev,
+                        int B, int T, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Autoencoder: replaces generative.networks.nets.AutoencoderKL as constructed at
+ * src/train_autoencoderkl.py:129-133 / src/sample_trials.py:95-100 (config/config_aekl_eeg*.yaml). */
+typedef struct {
+    int32_t in_channels;
+    int32_t out_channels;
+    int32_t n_levels;
+    int32_t num_channels[8];
+    int32_t num_res_blocks[8];
+    int32_t latent_channels;
+    int32_t norm_num_groups;
+} eegldm_aekl_cfg;
+
+typedef struct eegldm_aekl eegldm_aekl;
+
+int eegldm_aekl_create(const eegldm_aekl_cfg* cfg, eegldm_aekl** out);
+void eegldm_aekl_destroy(eegldm_aekl* h);
+int eegldm_aekl_num_params(const eegldm_aekl* h);
+int eegldm_aekl_param_info(const eegldm_aekl* h, int i, const char** name, int64_t shape[4], int* ndim);
+int eegldm_aekl_load(eegldm_aekl* h, const char* name, const float* host, const int64_t* shape, int ndim);
+int eegldm_aekl_finalize(eegldm_aekl* h);
+/* AutoencoderKL.encode(x) -> (z_mu, z_sigma)   x [B,in,L] -> [B,z,L/2^(levels-1)] each */
+int eegldm_aekl_encode(eegldm_aekl* h, const float* x_dev, float* z_mu_dev, float* z_sigma_dev, int B, int L,
+                       void* stream);
+/* AutoencoderKL.decode(z) / decode_stage_2_outputs   z [B,z,T] -> [B,out,T*2^(levels-1)] */
+int eegldm_aekl_decode(eegldm_aekl* h, const float* z_dev, float* out_dev, int B, int T, void* stream);
+/* AutoencoderKL.forward(x) with the sampling noise supplied by the caller:
+ * z = mu + eps*sigma; recon = decode(z).  eps_dev [B,z,T]. */
+int eegldm_aekl_forward(eegldm_aekl* h, const float* x_dev, const float* eps_dev, float* recon_dev,
+                        float* z_mu_dev, float* z_sigma_dev, int B, int L, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Scheduler + sampling loop: replaces generative.networks.schedulers.DDIMScheduler as used at
+ * src/sample_trials.py:136-145 and the loop at src/sample_trials.py:153-166. */
+typedef struct {
+    int32_t num_train_timesteps;   /* 1000 */
+    float beta_start;              /* 0.0015 */
+    float beta_end;                /* 0.0205 */
+    int32_t schedule;              /* 0 = linear_beta, 1 = scaled_linear_beta */
+    int32_t prediction_type;       /* 0 = epsilon, 1 = v_prediction */
+    int32_t set_alpha_to_one;      /* 1 (upstream default) */
+    int32_t steps_offset;          /* 0 */
+} eegldm_sched_cfg;
+
+/* host-only helpers (no GPU needed): alphas_cumprod[num_train_timesteps]; DDIM timesteps[n_steps]
+ * (descending) and the per-step update coefficients coef[2*i+0..1] with
+ * x_prev = coef0 * x + coef1 * model_output (eta = 0, clip_sample = False). */
+int eegldm_sched_alphas_cumprod(const eegldm_sched_cfg* cfg, float* out);
+int eegldm_sched_ddim_tables(const eegldm_sched_cfg* cfg, int n_steps, int64_t* timesteps, float* coef);
+/* timestep_embedding (unet.py:12-36) on the host: out[nt][dim] */
+int eegldm_timestep_embedding(const float* timesteps, int nt, int dim, float* out);
+
+/* Full DDIM sampling of B windows on one GPU.
+ *   noise_dev [B, z, T] (the reference draws torch.randn on the host, sample_trials.py:151)
+ *   aekl may be NULL: then out_dev receives the final latent [B, z, T];
+ *   otherwise out_dev receives decode(latent / scale_factor) [B, out, T*2^(levels-1)]  (sample_trials.py:166).
+ * One CUDA graph per denoise step is captured on first use for (B, T) and replayed n_steps times. */
+int eegldm_ddim_sample(eegldm_unet* unet, eegldm_aekl* aekl, const eegldm_sched_cfg* sched, const float* noise_dev,
+                       float scale_factor, int n_steps, float* out_dev, int B, int T, void* stream);
+/* Same, with HOST buffers: H2D of the noise, sampling, D2H of the result, stream-synchronised on return.
+ * The buffers should be pinned for full copy bandwidth. */
+int eegldm_ddim_sample_host(eegldm_unet* unet, eegldm_aekl* aekl, const eegldm_sched_cfg* sched,
+                            const float* noise_host, float scale_factor, int n_steps, float* out_host, int B, int T,
+                            void* stream);
+/* disable (0) / enable (1) CUDA-graph replay inside eegldm_ddim_sample (default 1) */
+int eegldm_set_graphs(int enabled);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EEGLDM_H_ */

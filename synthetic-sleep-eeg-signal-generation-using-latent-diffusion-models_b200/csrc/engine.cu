@@ -1,0 +1,1408 @@
+// eegldm engine: host-side runtime of the B200-native latent-diffusion sampler and the C ABI
+// declared in include/eegldm.h.
+//
+// What lives here (all of it host code; the device code is in kernels_simt.cu / conv_tc.cu):
+//   * topology of the reference denoiser  UNetModel.__init__   src/models/unet.py:372-505
+//     and of the KL autoencoder (monai-generative AutoencoderKL; in-tree ancestor src/models/ae_kl.py)
+//   * state_dict ingestion (reference key grammar) and weight repacking
+//   * the per-(B,T) launch plan: every activation is a slot of one arena in HBM, laid out
+//     channels-last [B][T][C]; GroupNorm/SiLU/resample/concat/residual/time-embedding are folded
+//     into the prologue/epilogue of the conv launches, so a ResBlock is 2 stat passes + 2 conv launches
+//   * the DDIM loop (src/sample_trials.py:153-166): one CUDA graph per denoise step, the scheduler
+//     update fused into the output conv's epilogue, per-step time-embedding rows precomputed
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "eegldm.h"
+#include "kernels.cuh"
+
+namespace eegldm {
+std::atomic<long long> g_launch_count{0};
+}
+
+using namespace eegldm;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+    g_err = std::string(what) + ": " + cudaGetErrorString(e);
+    return EEGLDM_ERR_CUDA;
+}
+#define CU(expr)                                                   \
+    do {                                                           \
+        cudaError_t e__ = (expr);                                  \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #expr);      \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// state_dict store
+struct HostParam {
+    std::string name;
+    std::vector<int64_t> shape;
+    std::vector<float> data;
+    bool loaded = false;
+    size_t numel() const {
+        size_t n = 1;
+        for (auto s : shape) n *= (size_t)s;
+        return n;
+    }
+};
+
+struct ParamSet {
+    std::vector<HostParam> params;
+    std::unordered_map<std::string, int> index;
+    void add(const std::string& name, std::vector<int64_t> shape) {
+        index[name] = (int)params.size();
+        HostParam p;
+        p.name = name;
+        p.shape = std::move(shape);
+        params.push_back(std::move(p));
+    }
+    void lin(const std::string& p, int i, int o) { add(p + ".weight", {o, i}); add(p + ".bias", {o}); }
+    void conv(const std::string& p, int i, int o, int k) { add(p + ".weight", {o, i, k}); add(p + ".bias", {o}); }
+    void gn(const std::string& p, int c) { add(p + ".weight", {c}); add(p + ".bias", {c}); }
+    int load(const char* name, const float* host, const int64_t* shape, int ndim) {
+        if (!name || !host || !shape) return fail(EEGLDM_ERR_INVALID, "null argument");
+        std::string key(name);
+        if (key.rfind("module.", 0) == 0) key = key.substr(7);  // DataParallel prefix (MSSIM_reconstruction.py:66-69)
+        auto it = index.find(key);
+        if (it == index.end()) return fail(EEGLDM_ERR_MISSING, "unexpected state_dict key: " + key);
+        HostParam& p = params[it->second];
+        bool ok = (int)p.shape.size() == ndim;
+        for (int i = 0; ok && i < ndim; ++i) ok = p.shape[i] == shape[i];
+        if (!ok) return fail(EEGLDM_ERR_SHAPE, "shape mismatch for " + key);
+        p.data.assign(host, host + p.numel());
+        p.loaded = true;
+        return EEGLDM_OK;
+    }
+    const std::vector<float>& get(const std::string& name) const { return params[index.at(name)].data; }
+    int check_all_loaded() const {
+        for (auto& p : params)
+            if (!p.loaded) return fail(EEGLDM_ERR_MISSING, "missing state_dict key: " + p.name);
+        return EEGLDM_OK;
+    }
+};
+
+// Packed device weights: staged on the host, uploaded once.
+struct WeightPool {
+    std::vector<float> stage;
+    float* dev = nullptr;
+    size_t push(const float* src, size_t n) {
+        size_t off = (stage.size() + 63) & ~size_t(63);
+        stage.resize(off + n);
+        std::memcpy(stage.data() + off, src, n * sizeof(float));
+        return off;
+    }
+    size_t push(const std::vector<float>& v) { return push(v.data(), v.size()); }
+    int upload() {
+        if (dev) { cudaFree(dev); dev = nullptr; }
+        if (stage.empty()) return EEGLDM_OK;
+        CU(cudaMalloc(&dev, stage.size() * sizeof(float)));
+        CU(cudaMemcpy(dev, stage.data(), stage.size() * sizeof(float), cudaMemcpyHostToDevice));
+        return EEGLDM_OK;
+    }
+    const float* at(size_t off) const { return dev + off; }
+    ~WeightPool() { if (dev) cudaFree(dev); }
+};
+
+// [Cout][Cin][k] (PyTorch)  ->  [(ci*k + kk)][Cout]  (SIMT conv kernel layout)
+std::vector<float> pack_conv(const std::vector<float>& w, int Cout, int Cin, int k) {
+    std::vector<float> out((size_t)Cout * Cin * k);
+    for (int co = 0; co < Cout; ++co)
+        for (int ci = 0; ci < Cin; ++ci)
+            for (int kk = 0; kk < k; ++kk)
+                out[((size_t)ci * k + kk) * Cout + co] = w[((size_t)co * Cin + ci) * k + kk];
+    return out;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Plan-time arena: activations are offsets into one device buffer; slots are recycled as soon as
+// their last consumer has been planned (launches are stream-ordered, so reuse is safe).
+struct Planner {
+    std::vector<std::pair<size_t, size_t>> free_;  // (off, n)
+    size_t top = 0;
+    size_t alloc(size_t n) {
+        n = (n + 63) & ~size_t(63);
+        int best = -1;
+        for (int i = 0; i < (int)free_.size(); ++i)
+            if (free_[i].second >= n && (best < 0 || free_[i].second < free_[best].second)) best = i;
+        if (best >= 0) {
+            size_t off = free_[best].first;
+            if (free_[best].second == n) free_.erase(free_.begin() + best);
+            else { free_[best].first += n; free_[best].second -= n; }
+            return off;
+        }
+        size_t off = top;
+        top += n;
+        return off;
+    }
+    void release(size_t off, size_t n) {
+        n = (n + 63) & ~size_t(63);
+        free_.push_back({off, n});
+        // coalesce neighbours
+        std::sort(free_.begin(), free_.end());
+        std::vector<std::pair<size_t, size_t>> m;
+        for (auto& f : free_) {
+            if (!m.empty() && m.back().first + m.back().second == f.first) m.back().second += f.second;
+            else m.push_back(f);
+        }
+        if (!m.empty() && m.back().first + m.back().second == top) { top = m.back().first; m.pop_back(); }
+        free_.swap(m);
+    }
+};
+
+struct Buf {
+    Planner* pl;
+    size_t off, n;
+    Buf(Planner* p, size_t n_) : pl(p), off(p->alloc(n_)), n(n_) {}
+    ~Buf() { pl->release(off, n); }
+};
+struct Act {  // channels-last activation [B][T][C]
+    std::shared_ptr<Buf> buf;
+    const float* ext = nullptr;  // external (caller-owned) tensor instead of an arena slot
+    int C = 0, T = 0;
+};
+
+using OpFn = std::function<cudaError_t(cudaStream_t)>;
+
+// per-launch bookkeeping for the live profile (eegldm_profile_*): algorithmic FLOPs / HBM bytes
+enum OpKind : int { OP_CONV = 0, OP_GN = 1, OP_ATTN = 2, OP_OTHER = 3, OP_NKIND = 4 };
+struct OpMeta { int kind; double flops, bytes; };
+
+struct Builder {
+    Planner pl;
+    float* base = nullptr;  // null during the sizing pass
+    std::vector<OpFn> ops;
+    std::vector<OpMeta> meta;
+    int n_kernels = 0;
+    int B = 0;
+    size_t peak = 0;
+    Act act(int C, int T) {
+        Act a;
+        a.buf = std::make_shared<Buf>(&pl, (size_t)B * T * C);
+        a.C = C; a.T = T;
+        peak = std::max(peak, pl.top);
+        return a;
+    }
+    std::shared_ptr<Buf> scratch(size_t n) {
+        auto b = std::make_shared<Buf>(&pl, n);
+        peak = std::max(peak, pl.top);
+        return b;
+    }
+    float* ptr(const std::shared_ptr<Buf>& b) const { return base + b->off; }
+    const float* ptr(const Act& a) const { return a.ext ? a.ext : base + a.buf->off; }
+    float* wptr(const Act& a) const { return base + a.buf->off; }
+    void add(OpFn f, int kernels, int kind = OP_OTHER, double flops = 0, double bytes = 0) {
+        if (base) { ops.push_back(std::move(f)); meta.push_back({kind, flops, bytes}); }
+        n_kernels += kernels;
+    }
+};
+
+// GroupNorm statistics of (virtual concat of) x0,x1 -> per-(sample,channel) scale/shift
+struct ScaleShift { std::shared_ptr<Buf> buf; const float* scale; const float* shift; };
+ScaleShift plan_gn(Builder& bd, const Act& x0, const Act* x1, int G, const float* gamma, const float* beta, float eps) {
+    const int C = x0.C + (x1 ? x1->C : 0);
+    ScaleShift ss;
+    ss.buf = bd.scratch((size_t)bd.B * C * 2);
+    GnParams p{};
+    p.src0 = bd.ptr(x0); p.C0 = x0.C;
+    p.src1 = x1 ? bd.ptr(*x1) : nullptr; p.C1 = x1 ? x1->C : 0;
+    p.T = x0.T; p.G = G; p.gamma = gamma; p.beta = beta; p.eps = eps; p.B = bd.B;
+    p.nsplit = groupnorm_nsplit(C, x0.T, G);
+    auto part = bd.scratch((size_t)bd.B * p.nsplit * G * 3);
+    p.scale = bd.ptr(ss.buf);
+    p.shift = p.scale + (size_t)bd.B * C;
+    p.partial = bd.ptr(part);
+    ss.scale = p.scale; ss.shift = p.shift;
+    bd.add([p](cudaStream_t st) { return launch_groupnorm(p, st); }, 2, OP_GN, 3.0 * bd.B * C * x0.T,
+           4.0 * bd.B * C * (x0.T + 2.0));
+    return ss;
+}
+
+int resampled_len(int T, int mode) { return mode == RS_AVGPOOL2 ? T / 2 : (mode == RS_NEAREST2 ? T * 2 : T); }
+
+ConvSeg make_seg(Builder& bd, const Act& x0, const Act* x1, const ScaleShift* ss, int silu, int resample,
+                 const float* w, int taps) {
+    ConvSeg s{};
+    s.src0 = bd.ptr(x0); s.C0 = x0.C;
+    s.src1 = x1 ? bd.ptr(*x1) : nullptr; s.C1 = x1 ? x1->C : 0;
+    s.scale = ss ? ss->scale : nullptr; s.shift = ss ? ss->shift : nullptr;
+    s.silu = silu; s.resample = resample; s.Tin = x0.T; s.w = w; s.taps = taps;
+    return s;
+}
+
+// ================================================================================================ UNet
+struct ULayer {
+    enum Kind { CONV_IN, RES, ATTN, DOWN, UP } kind;
+    std::string prefix;
+    int cin = 0, cout = 0, mode = RS_NONE;  // RES
+    int ch = 0, heads = 1;                  // ATTN / DOWN / UP
+    int use_conv = 0;
+    // device weights (valid after finalize)
+    const float *g1 = nullptr, *be1 = nullptr, *w1 = nullptr, *b1 = nullptr;
+    const float *g2 = nullptr, *be2 = nullptr, *w2 = nullptr, *b2 = nullptr, *wskip = nullptr;
+    int emb_off = 0;
+    const float *wqkv = nullptr, *bqkv = nullptr, *wproj = nullptr, *bproj = nullptr;
+    size_t o_g1, o_be1, o_w1, o_b1, o_g2, o_be2, o_w2, o_b2, o_wskip, o_wqkv, o_bqkv, o_wproj, o_bproj;
+};
+
+struct GraphEntry {
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    int n_kernels = 0;
+};
+
+}  // namespace
+
+struct eegldm_unet {
+    eegldm_unet_cfg cfg{};
+    ParamSet ps;
+    std::vector<std::vector<ULayer>> input_blocks, output_blocks;
+    std::vector<ULayer> middle;
+    int final_ch = 0, ted = 0, emb_total = 0;
+    bool finalized = false;
+    eegldm_math math = EEGLDM_MATH_FP32_SIMT;
+    WeightPool pool;
+    const float *te0_w = nullptr, *te0_b = nullptr, *te2_w = nullptr, *te2_b = nullptr;
+    const float *emb_w = nullptr, *emb_b = nullptr;  // concatenated emb_layers.1 of every ResBlock
+    const float *out_g = nullptr, *out_be = nullptr, *out_w = nullptr, *out_b = nullptr;
+    // runtime buffers
+    float* arena = nullptr; size_t arena_cap = 0;
+    float* temb_fwd = nullptr; size_t temb_fwd_cap = 0;    // forward(): [nt][emb_total]
+    float* tscratch = nullptr; size_t tscratch_cap = 0;    // time MLP scratch
+    float* temb_step = nullptr;                            // ddim: current row [emb_total]
+    float* temb_table = nullptr; size_t temb_table_cap = 0;  // ddim: [n_steps][emb_total]
+    float* coef_table = nullptr; size_t coef_table_cap = 0;  // ddim: [n_steps][2]
+    float* coef_cur = nullptr;                             // [2]
+    int* step_ctr = nullptr;
+    float* xbuf = nullptr; size_t xbuf_cap = 0;            // ddim state [B][T][z]
+    float* xtmp = nullptr; size_t xtmp_cap = 0;            // NCL<->NLC staging
+    std::vector<float> table_key;                          // identifies the cached temb/coef tables
+    std::map<std::pair<int, int>, GraphEntry> graphs;      // (B,T) -> one denoise step
+    ~eegldm_unet() {
+        drop_graphs();
+        for (void* p : {(void*)arena, (void*)temb_fwd, (void*)tscratch, (void*)temb_step, (void*)temb_table,
+                        (void*)coef_table, (void*)coef_cur, (void*)step_ctr, (void*)xbuf, (void*)xtmp})
+            if (p) cudaFree(p);
+    }
+    void drop_graphs() {
+        for (auto& g : graphs) {
+            if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
+            if (g.second.graph) cudaGraphDestroy(g.second.graph);
+        }
+        graphs.clear();
+    }
+};
+
+namespace {
+
+bool g_graphs_enabled = true;
+
+template <class T>
+int ensure(T*& p, size_t& cap, size_t n) {
+    if (n <= cap) return EEGLDM_OK;
+    if (p) { cudaFree(p); p = nullptr; cap = 0; }
+    CU(cudaMalloc((void**)&p, n * sizeof(T)));
+    cap = n;
+    return EEGLDM_OK;
+}
+
+int n_heads_for(const eegldm_unet_cfg& c, int ch, bool upsample) {
+    if (c.num_head_channels != -1) return c.num_head_channels > 0 ? ch / c.num_head_channels : 0;
+    return (upsample && c.num_heads_upsample != -1) ? c.num_heads_upsample : c.num_heads;
+}
+
+// UNetModel.__init__ topology, unet.py:382-505
+int build_unet_topology(eegldm_unet* h) {
+    const auto& c = h->cfg;
+    if (c.use_scale_shift_norm) return fail(EEGLDM_ERR_INVALID, "use_scale_shift_norm is not supported (no reference config enables it)");
+    if (c.n_channel_mult < 1 || c.n_channel_mult > 8 || c.n_attention_resolutions < 0 || c.n_attention_resolutions > 8)
+        return fail(EEGLDM_ERR_INVALID, "bad channel_mult / attention_resolutions length");
+    if (c.model_channels % 32 != 0) return fail(EEGLDM_ERR_INVALID, "model_channels must be a multiple of 32 (GroupNorm32)");
+    if (c.in_channels < 1 || c.out_channels < 1 || c.num_res_blocks < 1) return fail(EEGLDM_ERR_INVALID, "bad channel / block counts");
+    if (c.num_head_channels == -1 && c.num_heads < 1) return fail(EEGLDM_ERR_INVALID, "num_heads must be >= 1");
+    const int mc = c.model_channels;
+    auto has_att = [&](int ds) {
+        for (int i = 0; i < c.n_attention_resolutions; ++i)
+            if (c.attention_resolutions[i] == ds) return true;
+        return false;
+    };
+    auto res = [&](const std::string& p, int cin, int cout, int mode) {
+        ULayer l; l.kind = ULayer::RES; l.prefix = p; l.cin = cin; l.cout = cout; l.mode = mode; return l;
+    };
+    auto attn = [&](const std::string& p, int ch, bool upsample = false) {
+        ULayer l; l.kind = ULayer::ATTN; l.prefix = p; l.ch = ch; l.heads = n_heads_for(c, ch, upsample); return l;
+    };
+    h->ted = mc * 4;
+    {
+        ULayer l; l.kind = ULayer::CONV_IN; l.prefix = "input_blocks.0.0"; l.cin = c.in_channels; l.cout = mc;
+        h->input_blocks.push_back({l});
+    }
+    std::vector<int> chans{mc};
+    int ch = mc, ds = 1;
+    for (int level = 0; level < c.n_channel_mult; ++level) {
+        const int m = c.channel_mult[level];
+        for (int r = 0; r < c.num_res_blocks; ++r) {
+            const int idx = (int)h->input_blocks.size();
+            std::vector<ULayer> layers{res("input_blocks." + std::to_string(idx) + ".0", ch, m * mc, RS_NONE)};
+            ch = m * mc;
+            if (has_att(ds)) layers.push_back(attn("input_blocks." + std::to_string(idx) + ".1", ch));
+            h->input_blocks.push_back(layers);
+            chans.push_back(ch);
+        }
+        if (level != c.n_channel_mult - 1) {
+            const int idx = (int)h->input_blocks.size();
+            const std::string p = "input_blocks." + std::to_string(idx) + ".0";
+            if (c.resblock_updown) h->input_blocks.push_back({res(p, ch, ch, RS_AVGPOOL2)});
+            else { ULayer l; l.kind = ULayer::DOWN; l.prefix = p; l.ch = ch; l.use_conv = c.conv_resample; h->input_blocks.push_back({l}); }
+            chans.push_back(ch);
+            ds *= 2;
+        }
+    }
+    h->middle = {res("middle_block.0", ch, ch, RS_NONE), attn("middle_block.1", ch), res("middle_block.2", ch, ch, RS_NONE)};
+    for (int level = c.n_channel_mult - 1; level >= 0; --level) {
+        const int m = c.channel_mult[level];
+        for (int i = 0; i <= c.num_res_blocks; ++i) {
+            const int ich = chans.back(); chans.pop_back();
+            const int idx = (int)h->output_blocks.size();
+            const std::string bp = "output_blocks." + std::to_string(idx) + ".";
+            std::vector<ULayer> layers{res(bp + "0", ch + ich, mc * m, RS_NONE)};
+            ch = mc * m;
+            if (has_att(ds)) layers.push_back(attn(bp + std::to_string(layers.size()), ch, true));
+            if (level && i == c.num_res_blocks) {
+                const std::string p = bp + std::to_string(layers.size());
+                if (c.resblock_updown) layers.push_back(res(p, ch, ch, RS_NEAREST2));
+                else { ULayer l; l.kind = ULayer::UP; l.prefix = p; l.ch = ch; l.use_conv = c.conv_resample; layers.push_back(l); }
+                ds /= 2;
+            }
+            h->output_blocks.push_back(layers);
+        }
+    }
+    h->final_ch = ch;
+    // state_dict entries in the reference's registration order
+    ParamSet& ps = h->ps;
+    ps.lin("time_embed.0", mc, h->ted);
+    ps.lin("time_embed.2", h->ted, h->ted);
+    auto reg = [&](const ULayer& l) -> int {
+        const std::string& p = l.prefix;
+        switch (l.kind) {
+            case ULayer::CONV_IN: ps.conv(p, l.cin, l.cout, 3); break;
+            case ULayer::RES:
+                if (l.cin % 32 || l.cout % 32) return fail(EEGLDM_ERR_INVALID, "ResBlock channels must be multiples of 32");
+                ps.gn(p + ".in_layers.0", l.cin); ps.conv(p + ".in_layers.2", l.cin, l.cout, 3);
+                ps.lin(p + ".emb_layers.1", h->ted, l.cout);
+                ps.gn(p + ".out_layers.0", l.cout); ps.conv(p + ".out_layers.3", l.cout, l.cout, 3);
+                if (l.cin != l.cout) ps.conv(p + ".skip_connection", l.cin, l.cout, 1);
+                break;
+            case ULayer::ATTN:
+                if (l.heads < 1 || l.ch % l.heads) return fail(EEGLDM_ERR_INVALID, "attention channels not divisible by heads");
+                ps.gn(p + ".norm", l.ch); ps.conv(p + ".qkv", l.ch, 3 * l.ch, 1); ps.conv(p + ".proj_out", l.ch, l.ch, 1);
+                break;
+            case ULayer::DOWN: if (l.use_conv) ps.conv(p + ".op", l.ch, l.ch, 3); break;
+            case ULayer::UP: if (l.use_conv) ps.conv(p + ".conv", l.ch, l.ch, 3); break;
+        }
+        return EEGLDM_OK;
+    };
+    for (auto& b : h->input_blocks) for (auto& l : b) { int r = reg(l); if (r) return r; }
+    for (auto& l : h->middle) { int r = reg(l); if (r) return r; }
+    for (auto& b : h->output_blocks) for (auto& l : b) { int r = reg(l); if (r) return r; }
+    ps.gn("out.0", h->final_ch);
+    ps.conv("out.2", mc, c.out_channels, 3);
+    if (h->final_ch != mc) return fail(EEGLDM_ERR_INVALID, "channel_mult[0] must be 1 (out conv takes model_channels)");
+    return EEGLDM_OK;
+}
+
+template <class F>
+void for_each_layer(eegldm_unet* h, F f) {
+    for (auto& b : h->input_blocks) for (auto& l : b) f(l);
+    for (auto& l : h->middle) f(l);
+    for (auto& b : h->output_blocks) for (auto& l : b) f(l);
+}
+
+int finalize_unet(eegldm_unet* h) {
+    int r = h->ps.check_all_loaded();
+    if (r) return r;
+    h->drop_graphs();
+    h->table_key.clear();
+    WeightPool& wp = h->pool;
+    wp.stage.clear();
+    const ParamSet& ps = h->ps;
+    const size_t o_te0w = wp.push(ps.get("time_embed.0.weight")), o_te0b = wp.push(ps.get("time_embed.0.bias"));
+    const size_t o_te2w = wp.push(ps.get("time_embed.2.weight")), o_te2b = wp.push(ps.get("time_embed.2.bias"));
+    // concatenated emb_layers.1 (ResBlock time projections): one batched linear per step
+    std::vector<float> embw, embb;
+    for_each_layer(h, [&](ULayer& l) {
+        if (l.kind != ULayer::RES) return;
+        l.emb_off = (int)embb.size();
+        const auto& w = ps.get(l.prefix + ".emb_layers.1.weight");
+        const auto& b = ps.get(l.prefix + ".emb_layers.1.bias");
+        embw.insert(embw.end(), w.begin(), w.end());
+        embb.insert(embb.end(), b.begin(), b.end());
+    });
+    h->emb_total = (int)embb.size();
+    const size_t o_embw = wp.push(embw), o_embb = wp.push(embb);
+    for_each_layer(h, [&](ULayer& l) {
+        const std::string& p = l.prefix;
+        switch (l.kind) {
+            case ULayer::CONV_IN:
+                l.o_w1 = wp.push(pack_conv(ps.get(p + ".weight"), l.cout, l.cin, 3));
+                l.o_b1 = wp.push(ps.get(p + ".bias"));
+                break;
+            case ULayer::RES: {
+                l.o_g1 = wp.push(ps.get(p + ".in_layers.0.weight")); l.o_be1 = wp.push(ps.get(p + ".in_layers.0.bias"));
+                l.o_w1 = wp.push(pack_conv(ps.get(p + ".in_layers.2.weight"), l.cout, l.cin, 3));
+                l.o_b1 = wp.push(ps.get(p + ".in_layers.2.bias"));
+                l.o_g2 = wp.push(ps.get(p + ".out_layers.0.weight")); l.o_be2 = wp.push(ps.get(p + ".out_layers.0.bias"));
+                l.o_w2 = wp.push(pack_conv(ps.get(p + ".out_layers.3.weight"), l.cout, l.cout, 3));
+                std::vector<float> b2 = ps.get(p + ".out_layers.3.bias");
+                if (l.cin != l.cout) {
+                    l.o_wskip = wp.push(pack_conv(ps.get(p + ".skip_connection.weight"), l.cout, l.cin, 1));
+                    const auto& bs = ps.get(p + ".skip_connection.bias");
+                    for (int i = 0; i < l.cout; ++i) b2[i] += bs[i];
+                }
+                l.o_b2 = wp.push(b2);
+                break;
+            }
+            case ULayer::ATTN:
+                l.o_g1 = wp.push(ps.get(p + ".norm.weight")); l.o_be1 = wp.push(ps.get(p + ".norm.bias"));
+                l.o_wqkv = wp.push(pack_conv(ps.get(p + ".qkv.weight"), 3 * l.ch, l.ch, 1));
+                l.o_bqkv = wp.push(ps.get(p + ".qkv.bias"));
+                l.o_wproj = wp.push(pack_conv(ps.get(p + ".proj_out.weight"), l.ch, l.ch, 1));
+                l.o_bproj = wp.push(ps.get(p + ".proj_out.bias"));
+                break;
+            case ULayer::DOWN:
+                if (l.use_conv) { l.o_w1 = wp.push(pack_conv(ps.get(p + ".op.weight"), l.ch, l.ch, 3)); l.o_b1 = wp.push(ps.get(p + ".op.bias")); }
+                break;
+            case ULayer::UP:
+                if (l.use_conv) { l.o_w1 = wp.push(pack_conv(ps.get(p + ".conv.weight"), l.ch, l.ch, 3)); l.o_b1 = wp.push(ps.get(p + ".conv.bias")); }
+                break;
+        }
+    });
+    const size_t o_og = wp.push(ps.get("out.0.weight")), o_obe = wp.push(ps.get("out.0.bias"));
+    const size_t o_ow = wp.push(pack_conv(ps.get("out.2.weight"), h->cfg.out_channels, h->cfg.model_channels, 3));
+    const size_t o_ob = wp.push(ps.get("out.2.bias"));
+    r = wp.upload();
+    if (r) return r;
+    h->te0_w = wp.at(o_te0w); h->te0_b = wp.at(o_te0b); h->te2_w = wp.at(o_te2w); h->te2_b = wp.at(o_te2b);
+    h->emb_w = wp.at(o_embw); h->emb_b = wp.at(o_embb);
+    h->out_g = wp.at(o_og); h->out_be = wp.at(o_obe); h->out_w = wp.at(o_ow); h->out_b = wp.at(o_ob);
+    for_each_layer(h, [&](ULayer& l) {
+        switch (l.kind) {
+            case ULayer::CONV_IN: l.w1 = wp.at(l.o_w1); l.b1 = wp.at(l.o_b1); break;
+            case ULayer::RES:
+                l.g1 = wp.at(l.o_g1); l.be1 = wp.at(l.o_be1); l.w1 = wp.at(l.o_w1); l.b1 = wp.at(l.o_b1);
+                l.g2 = wp.at(l.o_g2); l.be2 = wp.at(l.o_be2); l.w2 = wp.at(l.o_w2); l.b2 = wp.at(l.o_b2);
+                l.wskip = l.cin != l.cout ? wp.at(l.o_wskip) : nullptr;
+                break;
+            case ULayer::ATTN:
+                l.g1 = wp.at(l.o_g1); l.be1 = wp.at(l.o_be1); l.wqkv = wp.at(l.o_wqkv); l.bqkv = wp.at(l.o_bqkv);
+                l.wproj = wp.at(l.o_wproj); l.bproj = wp.at(l.o_bproj);
+                break;
+            case ULayer::DOWN: case ULayer::UP:
+                if (l.use_conv) { l.w1 = wp.at(l.o_w1); l.b1 = wp.at(l.o_b1); }
+                break;
+        }
+    });
+    if (!h->temb_step) CU(cudaMalloc((void**)&h->temb_step, (size_t)std::max(h->emb_total, 1) * sizeof(float)));
+    else { cudaFree(h->temb_step); h->temb_step = nullptr; CU(cudaMalloc((void**)&h->temb_step, (size_t)std::max(h->emb_total, 1) * sizeof(float))); }
+    if (!h->coef_cur) CU(cudaMalloc((void**)&h->coef_cur, 2 * sizeof(float)));
+    if (!h->step_ctr) CU(cudaMalloc((void**)&h->step_ctr, sizeof(int)));
+    h->finalized = true;
+    return EEGLDM_OK;
+}
+
+// ---- launch plan of one UNetModel.forward (unet.py:512-563) on channels-last tensors -----------
+struct UNetIO {
+    const float* x;       // [B][T][in_ch]
+    float* out;           // [B][T][out_ch]
+    const float* temb;    // [nt][emb_total]
+    int temb_stride;      // 0 (shared timestep) or emb_total
+    const float* ddim_x;  // non-null: out = coef[0]*ddim_x + coef[1]*model_output
+    const float* ddim_coef;
+};
+
+void plan_conv(Builder& bd, ConvParams p) {
+    p.B = bd.B;
+    double flops = 0, bytes = 4.0 * p.B * (double)p.Tout * p.Cout;   // output write
+    for (int s = 0; s < p.nseg; ++s) {
+        const double cin = p.seg[s].C0 + p.seg[s].C1;
+        flops += 2.0 * cin * p.Cout * p.seg[s].taps * (double)p.Tout * p.B;
+        if (s == 0 || p.seg[s].src0 != p.seg[0].src0) bytes += 4.0 * p.B * (double)p.seg[s].Tin * cin;  // input read (once)
+        bytes += 4.0 * cin * p.Cout * p.seg[s].taps;                                                     // weights
+    }
+    if (p.res) bytes += 4.0 * p.B * (double)p.res_Tin * p.Cout;
+    bd.add([p](cudaStream_t st) { return launch_conv_simt(p, st); }, 1, OP_CONV, flops, bytes);
+}
+
+Act plan_res(Builder& bd, const ULayer& l, const Act& x0, const Act* x1, const UNetIO& io) {
+    const int Tc = resampled_len(x0.T, l.mode);
+    Act h1 = bd.act(l.cout, Tc);
+    {
+        ScaleShift ss = plan_gn(bd, x0, x1, 32, l.g1, l.be1, 1e-6f);
+        ConvParams p{};
+        p.seg[0] = make_seg(bd, x0, x1, &ss, 1, l.mode, l.w1, 3);
+        p.nseg = 1; p.Cout = l.cout; p.Tout = Tc; p.Tc = Tc; p.stride = 1; p.pad_left = 1;
+        p.bias = l.b1; p.temb = io.temb + l.emb_off; p.temb_stride = io.temb_stride;
+        p.out = bd.wptr(h1);
+        plan_conv(bd, p);
+    }
+    Act y = bd.act(l.cout, Tc);
+    {
+        ScaleShift ss = plan_gn(bd, h1, nullptr, 32, l.g2, l.be2, 1e-6f);
+        ConvParams p{};
+        p.seg[0] = make_seg(bd, h1, nullptr, &ss, 1, RS_NONE, l.w2, 3);
+        p.nseg = 1; p.Cout = l.cout; p.Tout = Tc; p.Tc = Tc; p.stride = 1; p.pad_left = 1;
+        p.bias = l.b2;
+        if (l.cin != l.cout) {  // skip_connection = Conv1d k=1 on the (resampled) raw input, unet.py:295-302
+            p.seg[1] = make_seg(bd, x0, x1, nullptr, 0, l.mode, l.wskip, 1);
+            p.nseg = 2;
+        } else {                // Identity skip (cin == cout implies a single source)
+            p.res = bd.ptr(x0); p.res_mode = l.mode; p.res_Tin = x0.T;
+        }
+        p.out = bd.wptr(y);
+        plan_conv(bd, p);
+    }
+    return y;
+}
+
+Act plan_attn(Builder& bd, const ULayer& l, const Act& x) {
+    Act qkv = bd.act(3 * l.ch, x.T);
+    {
+        ScaleShift ss = plan_gn(bd, x, nullptr, 32, l.g1, l.be1, 1e-6f);
+        ConvParams p{};
+        p.seg[0] = make_seg(bd, x, nullptr, &ss, 0, RS_NONE, l.wqkv, 1);
+        p.nseg = 1; p.Cout = 3 * l.ch; p.Tout = x.T; p.Tc = x.T; p.stride = 1; p.pad_left = 0;
+        p.bias = l.bqkv; p.out = bd.wptr(qkv);
+        plan_conv(bd, p);
+    }
+    Act a = bd.act(l.ch, x.T);
+    {
+        AttnParams ap{};
+        ap.qkv = bd.ptr(qkv); ap.out = bd.wptr(a); ap.T = x.T; ap.H = l.heads; ap.ch = l.ch / l.heads; ap.B = bd.B;
+        bd.add([ap](cudaStream_t st) { return launch_attention_simt(ap, st); }, 1, OP_ATTN,
+               4.0 * bd.B * (double)x.T * x.T * l.ch, 4.0 * bd.B * (double)x.T * l.ch * 4.0);
+    }
+    qkv.buf.reset();
+    Act y = bd.act(l.ch, x.T);
+    {
+        ConvParams p{};
+        p.seg[0] = make_seg(bd, a, nullptr, nullptr, 0, RS_NONE, l.wproj, 1);
+        p.nseg = 1; p.Cout = l.ch; p.Tout = x.T; p.Tc = x.T; p.stride = 1; p.pad_left = 0;
+        p.bias = l.bproj; p.res = bd.ptr(x); p.res_mode = RS_NONE; p.res_Tin = x.T;
+        p.out = bd.wptr(y);
+        plan_conv(bd, p);
+    }
+    return y;
+}
+
+Act plan_layer(Builder& bd, const ULayer& l, const Act& x0, const Act* x1, const UNetIO& io) {
+    switch (l.kind) {
+        case ULayer::CONV_IN: {
+            Act y = bd.act(l.cout, x0.T);
+            ConvParams p{};
+            p.seg[0] = make_seg(bd, x0, nullptr, nullptr, 0, RS_NONE, l.w1, 3);
+            p.nseg = 1; p.Cout = l.cout; p.Tout = x0.T; p.Tc = x0.T; p.stride = 1; p.pad_left = 1;
+            p.bias = l.b1; p.out = bd.wptr(y);
+            plan_conv(bd, p);
+            return y;
+        }
+        case ULayer::RES: return plan_res(bd, l, x0, x1, io);
+        case ULayer::ATTN: return plan_attn(bd, l, x0);
+        case ULayer::DOWN: {  // Downsample, unet.py:177-199
+            if (l.use_conv) {
+                const int Tout = (x0.T + 2 - 3) / 2 + 1;
+                Act y = bd.act(l.ch, Tout);
+                ConvParams p{};
+                p.seg[0] = make_seg(bd, x0, nullptr, nullptr, 0, RS_NONE, l.w1, 3);
+                p.nseg = 1; p.Cout = l.ch; p.Tout = Tout; p.Tc = x0.T; p.stride = 2; p.pad_left = 1;
+                p.bias = l.b1; p.out = bd.wptr(y);
+                plan_conv(bd, p);
+                return y;
+            }
+            Act y = bd.act(l.ch, x0.T / 2);
+            const float* src = bd.ptr(x0); float* dst = bd.wptr(y);
+            const int B = bd.B, C = l.ch, Tin = x0.T;
+            bd.add([=](cudaStream_t st) { return launch_resample(src, dst, B, Tin, C, RS_AVGPOOL2, st); }, 1);
+            return y;
+        }
+        case ULayer::UP: {  // Upsample, unet.py:202-224
+            if (l.use_conv) {
+                Act y = bd.act(l.ch, x0.T * 2);
+                ConvParams p{};
+                p.seg[0] = make_seg(bd, x0, nullptr, nullptr, 0, RS_NEAREST2, l.w1, 3);
+                p.nseg = 1; p.Cout = l.ch; p.Tout = x0.T * 2; p.Tc = x0.T * 2; p.stride = 1; p.pad_left = 1;
+                p.bias = l.b1; p.out = bd.wptr(y);
+                plan_conv(bd, p);
+                return y;
+            }
+            Act y = bd.act(l.ch, x0.T * 2);
+            const float* src = bd.ptr(x0); float* dst = bd.wptr(y);
+            const int B = bd.B, C = l.ch, Tin = x0.T;
+            bd.add([=](cudaStream_t st) { return launch_resample(src, dst, B, Tin, C, RS_NEAREST2, st); }, 1);
+            return y;
+        }
+    }
+    return Act{};
+}
+
+int plan_unet_body(eegldm_unet* h, Builder& bd, int T, const UNetIO& io) {
+    Act x; x.ext = io.x; x.C = h->cfg.in_channels; x.T = T;
+    std::vector<Act> hs;
+    Act cur = x;
+    for (auto& blk : h->input_blocks) {
+        for (auto& l : blk) cur = plan_layer(bd, l, cur, nullptr, io);
+        hs.push_back(cur);
+    }
+    for (auto& l : h->middle) cur = plan_layer(bd, l, cur, nullptr, io);
+    for (auto& blk : h->output_blocks) {
+        Act skip = hs.back(); hs.pop_back();
+        if (skip.T != cur.T) return fail(EEGLDM_ERR_SHAPE, "skip length mismatch: T must be divisible by 2^(levels-1)");
+        bool first = true;
+        for (auto& l : blk) {
+            cur = plan_layer(bd, l, cur, first ? &skip : nullptr, io);
+            if (first) skip.buf.reset();
+            first = false;
+        }
+    }
+    // out = Conv3(SiLU(GN(h)))  unet.py:501-505  (+ fused scheduler step)
+    ScaleShift ss = plan_gn(bd, cur, nullptr, 32, h->out_g, h->out_be, 1e-6f);
+    ConvParams p{};
+    p.seg[0] = make_seg(bd, cur, nullptr, &ss, 1, RS_NONE, h->out_w, 3);
+    p.nseg = 1; p.Cout = h->cfg.out_channels; p.Tout = T; p.Tc = T; p.stride = 1; p.pad_left = 1;
+    p.bias = h->out_b; p.out = io.out; p.ddim_x = io.ddim_x; p.ddim_coef = io.ddim_coef;
+    plan_conv(bd, p);
+    return EEGLDM_OK;
+}
+
+// two passes: size the arena, then emit launches with real pointers
+int build_unet_plan(eegldm_unet* h, int B, int T, const UNetIO& io, Builder& out) {
+    const int levels = h->cfg.n_channel_mult;
+    if (T <= 0 || (T % (1 << (levels - 1))) != 0)
+        return fail(EEGLDM_ERR_SHAPE, "T must be a positive multiple of 2^(levels-1)");
+    Builder sizing; sizing.B = B;
+    int r = plan_unet_body(h, sizing, T, io);
+    if (r) return r;
+    if (sizing.peak > h->arena_cap) {
+        h->drop_graphs();
+        r = ensure(h->arena, h->arena_cap, sizing.peak);
+        if (r) return r;
+    }
+    out.B = B; out.base = h->arena;
+    return plan_unet_body(h, out, T, io);
+}
+
+struct ProfRec { OpMeta m; cudaEvent_t e0, e1; };
+bool g_profile = false;
+std::vector<ProfRec> g_prof;
+
+int run_ops(const Builder& bd, cudaStream_t st) {
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    const bool prof = g_profile && cudaStreamIsCapturing(st, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone;
+    for (size_t i = 0; i < bd.ops.size(); ++i) {
+        ProfRec r{};
+        if (prof) {
+            r.m = bd.meta[i];
+            CU(cudaEventCreate(&r.e0)); CU(cudaEventCreate(&r.e1));
+            CU(cudaEventRecord(r.e0, st));
+        }
+        cudaError_t e = bd.ops[i](st);
+        if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
+        if (prof) { CU(cudaEventRecord(r.e1, st)); g_prof.push_back(r); }
+    }
+    return EEGLDM_OK;
+}
+
+// timestep_embedding (unet.py:12-36) -- double precision on the host, rounded to fp32 at the same
+// points the reference rounds (freqs, the product t*freq, the cos/sin result).
+void timestep_embedding_host(const float* t, int nt, int dim, float* out) {
+    const int half = dim / 2;
+    for (int i = 0; i < nt; ++i) {
+        for (int j = 0; j < half; ++j) {
+            const float fr = (float)std::exp((double)(-(float)std::log(10000.0) * (float)j / (float)half));
+            const float arg = t[i] * fr;
+            out[(size_t)i * dim + j] = (float)std::cos((double)arg);
+            out[(size_t)i * dim + half + j] = (float)std::sin((double)arg);
+        }
+        if (dim % 2) out[(size_t)i * dim + dim - 1] = 0.f;
+    }
+}
+
+// time MLP + every ResBlock's emb projection: temb_out[nt][emb_total]   (unet.py:372-377, 277-285)
+int run_time_mlp(eegldm_unet* h, const float* t_host, int nt, float* temb_out, cudaStream_t st) {
+    const int mc = h->cfg.model_channels, ted = h->ted;
+    std::vector<float> te((size_t)nt * mc);
+    timestep_embedding_host(t_host, nt, mc, te.data());
+    int r = ensure(h->tscratch, h->tscratch_cap, (size_t)nt * (mc + 2 * ted));
+    if (r) return r;
+    float* d_te = h->tscratch;
+    float* d_h0 = d_te + (size_t)nt * mc;
+    float* d_emb = d_h0 + (size_t)nt * ted;
+    CU(cudaMemcpyAsync(d_te, te.data(), te.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+    CU(launch_linear(d_te, h->te0_w, h->te0_b, d_h0, nt, mc, ted, 0, st));
+    CU(launch_linear(d_h0, h->te2_w, h->te2_b, d_emb, nt, ted, ted, 1, st));
+    CU(launch_linear(d_emb, h->emb_w, h->emb_b, temb_out, nt, ted, h->emb_total, 1, st));
+    return EEGLDM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// scheduler tables (host)   generative/networks/schedulers/{scheduler,ddim}.py [upstream]
+int sched_alphas(const eegldm_sched_cfg* c, std::vector<float>& ac) {
+    if (!c || c->num_train_timesteps < 1) return fail(EEGLDM_ERR_INVALID, "bad scheduler config");
+    const int n = c->num_train_timesteps;
+    ac.resize(n);
+    // torch.linspace(fp32): start + i*step for the first half, end - (n-1-i)*step for the second
+    auto linspace = [n](float a, float b, int i) -> float {
+        if (n == 1) return a;
+        const float step = (b - a) / (float)(n - 1);
+        return i < n / 2 ? a + step * (float)i : b - step * (float)(n - 1 - i);
+    };
+    float prod = 1.f;
+    for (int i = 0; i < n; ++i) {
+        float beta;
+        if (c->schedule == 0) beta = linspace(c->beta_start, c->beta_end, i);
+        else if (c->schedule == 1) {
+            const float s = linspace(std::sqrt(c->beta_start), std::sqrt(c->beta_end), i);
+            beta = s * s;
+        } else return fail(EEGLDM_ERR_INVALID, "schedule must be 0 (linear_beta) or 1 (scaled_linear_beta)");
+        prod *= (1.f - beta);
+        ac[i] = prod;
+    }
+    return EEGLDM_OK;
+}
+
+int sched_ddim_tables(const eegldm_sched_cfg* c, int n_steps, std::vector<int64_t>& ts, std::vector<float>& coef) {
+    std::vector<float> ac;
+    int r = sched_alphas(c, ac);
+    if (r) return r;
+    const int n = c->num_train_timesteps;
+    if (n_steps < 1 || n_steps > n) return fail(EEGLDM_ERR_INVALID, "n_steps must be in [1, num_train_timesteps]");
+    const int ratio = n / n_steps;
+    ts.resize(n_steps); coef.resize(2 * (size_t)n_steps);
+    for (int i = 0; i < n_steps; ++i) {
+        const int t = (n_steps - 1 - i) * ratio + c->steps_offset;
+        if (t < 0 || t >= n) return fail(EEGLDM_ERR_INVALID, "timestep out of range (steps_offset)");
+        ts[i] = t;
+        const int prev = t - ratio;
+        const double a_t = ac[t];
+        const double a_p = prev >= 0 ? (double)ac[prev] : (c->set_alpha_to_one ? 1.0 : (double)ac[0]);
+        const double sa = std::sqrt(a_t), sb = std::sqrt(1.0 - a_t), sap = std::sqrt(a_p), sbp = std::sqrt(1.0 - a_p);
+        double cx, cm;
+        if (c->prediction_type == 1) { cx = sap * sa + sbp * sb; cm = -sap * sb + sbp * sa; }       // v-prediction
+        else if (c->prediction_type == 0) { cx = sap / sa; cm = -sap * sb / sa + sbp; }             // epsilon
+        else return fail(EEGLDM_ERR_INVALID, "prediction_type must be 0 (epsilon) or 1 (v_prediction)");
+        coef[2 * i] = (float)cx; coef[2 * i + 1] = (float)cm;
+    }
+    return EEGLDM_OK;
+}
+
+}  // namespace
+
+// ================================================================================================ AEKL
+namespace {
+struct ALayer {
+    enum Kind { CONV, RES, DOWN, UP, NORM } kind;
+    std::string prefix;
+    int cin = 0, cout = 0, k = 3;
+    const float *g1 = nullptr, *be1 = nullptr, *w1 = nullptr, *b1 = nullptr, *g2 = nullptr, *be2 = nullptr, *w2 = nullptr,
+                *b2 = nullptr, *wskip = nullptr;
+    size_t o_g1 = 0, o_be1 = 0, o_w1 = 0, o_b1 = 0, o_g2 = 0, o_be2 = 0, o_w2 = 0, o_b2 = 0, o_wskip = 0;
+};
+}  // namespace
+
+struct eegldm_aekl {
+    eegldm_aekl_cfg cfg{};
+    ParamSet ps;
+    std::vector<ALayer> enc, dec;
+    ALayer q_mu, q_ls, post_q;
+    WeightPool pool;
+    bool finalized = false;
+    float* arena = nullptr; size_t arena_cap = 0;
+    float* io_tmp = nullptr; size_t io_tmp_cap = 0;
+    int down_factor() const { return 1 << (cfg.n_levels - 1); }
+    ~eegldm_aekl() { if (arena) cudaFree(arena); if (io_tmp) cudaFree(io_tmp); }
+};
+
+namespace {
+
+int build_aekl_topology(eegldm_aekl* h) {
+    const auto& c = h->cfg;
+    if (c.n_levels < 1 || c.n_levels > 8) return fail(EEGLDM_ERR_INVALID, "bad n_levels");
+    if (c.in_channels < 1 || c.out_channels < 1 || c.latent_channels < 1 || c.norm_num_groups < 1)
+        return fail(EEGLDM_ERR_INVALID, "bad autoencoder config");
+    for (int i = 0; i < c.n_levels; ++i)
+        if (c.num_channels[i] < 1 || c.num_channels[i] % c.norm_num_groups || c.num_res_blocks[i] < 0)
+            return fail(EEGLDM_ERR_INVALID, "num_channels must be positive multiples of norm_num_groups");
+    auto mk = [](ALayer::Kind k, const std::string& p, int cin, int cout, int ks) {
+        ALayer l; l.kind = k; l.prefix = p; l.cin = cin; l.cout = cout; l.k = ks; return l;
+    };
+    const int L = c.n_levels, z = c.latent_channels;
+    auto& enc = h->enc; auto& dec = h->dec;
+    enc.push_back(mk(ALayer::CONV, "encoder.blocks.0", c.in_channels, c.num_channels[0], 3));
+    int out_ch = c.num_channels[0];
+    for (int i = 0; i < L; ++i) {
+        int in_ch = out_ch; out_ch = c.num_channels[i];
+        for (int r = 0; r < c.num_res_blocks[i]; ++r) {
+            enc.push_back(mk(ALayer::RES, "encoder.blocks." + std::to_string(enc.size()), in_ch, out_ch, 3));
+            in_ch = out_ch;
+        }
+        if (i != L - 1) enc.push_back(mk(ALayer::DOWN, "encoder.blocks." + std::to_string(enc.size()), in_ch, in_ch, 3));
+        out_ch = in_ch;
+    }
+    enc.push_back(mk(ALayer::NORM, "encoder.blocks." + std::to_string(enc.size()), out_ch, out_ch, 0));
+    enc.push_back(mk(ALayer::CONV, "encoder.blocks." + std::to_string(enc.size()), out_ch, z, 3));
+
+    std::vector<int> rc(c.num_channels, c.num_channels + L), rr(c.num_res_blocks, c.num_res_blocks + L);
+    std::reverse(rc.begin(), rc.end()); std::reverse(rr.begin(), rr.end());
+    dec.push_back(mk(ALayer::CONV, "decoder.blocks.0", z, rc[0], 3));
+    out_ch = rc[0];
+    int in_ch = out_ch;
+    for (int i = 0; i < L; ++i) {
+        in_ch = out_ch; out_ch = rc[i];
+        for (int r = 0; r < rr[i]; ++r) {
+            dec.push_back(mk(ALayer::RES, "decoder.blocks." + std::to_string(dec.size()), in_ch, out_ch, 3));
+            in_ch = out_ch;
+        }
+        if (i != L - 1) dec.push_back(mk(ALayer::UP, "decoder.blocks." + std::to_string(dec.size()), in_ch, in_ch, 3));
+        out_ch = in_ch;
+    }
+    dec.push_back(mk(ALayer::NORM, "decoder.blocks." + std::to_string(dec.size()), in_ch, in_ch, 0));
+    dec.push_back(mk(ALayer::CONV, "decoder.blocks." + std::to_string(dec.size()), in_ch, c.out_channels, 3));
+    h->q_mu = mk(ALayer::CONV, "quant_conv_mu", z, z, 1);
+    h->q_ls = mk(ALayer::CONV, "quant_conv_log_sigma", z, z, 1);
+    h->post_q = mk(ALayer::CONV, "post_quant_conv", z, z, 1);
+
+    ParamSet& ps = h->ps;
+    auto conv = [&](const std::string& p, int i, int o, int k) { ps.add(p + ".conv.weight", {o, i, k}); ps.add(p + ".conv.bias", {o}); };
+    auto reg = [&](const ALayer& l) {
+        const std::string& p = l.prefix;
+        switch (l.kind) {
+            case ALayer::CONV: conv(p, l.cin, l.cout, l.k); break;
+            case ALayer::RES:
+                ps.gn(p + ".norm1", l.cin); conv(p + ".conv1", l.cin, l.cout, 3);
+                ps.gn(p + ".norm2", l.cout); conv(p + ".conv2", l.cout, l.cout, 3);
+                if (l.cin != l.cout) conv(p + ".nin_shortcut", l.cin, l.cout, 1);
+                break;
+            case ALayer::DOWN: case ALayer::UP: conv(p + ".conv", l.cin, l.cin, 3); break;
+            case ALayer::NORM: ps.gn(p, l.cin); break;
+        }
+    };
+    for (auto& l : enc) reg(l);
+    for (auto& l : dec) reg(l);
+    reg(h->q_mu); reg(h->q_ls); reg(h->post_q);
+    return EEGLDM_OK;
+}
+
+int finalize_aekl(eegldm_aekl* h) {
+    int r = h->ps.check_all_loaded();
+    if (r) return r;
+    WeightPool& wp = h->pool;
+    wp.stage.clear();
+    const ParamSet& ps = h->ps;
+    auto stage = [&](ALayer& l) {
+        const std::string& p = l.prefix;
+        switch (l.kind) {
+            case ALayer::CONV:
+                l.o_w1 = wp.push(pack_conv(ps.get(p + ".conv.weight"), l.cout, l.cin, l.k)); l.o_b1 = wp.push(ps.get(p + ".conv.bias"));
+                break;
+            case ALayer::RES: {
+                l.o_g1 = wp.push(ps.get(p + ".norm1.weight")); l.o_be1 = wp.push(ps.get(p + ".norm1.bias"));
+                l.o_w1 = wp.push(pack_conv(ps.get(p + ".conv1.conv.weight"), l.cout, l.cin, 3)); l.o_b1 = wp.push(ps.get(p + ".conv1.conv.bias"));
+                l.o_g2 = wp.push(ps.get(p + ".norm2.weight")); l.o_be2 = wp.push(ps.get(p + ".norm2.bias"));
+                l.o_w2 = wp.push(pack_conv(ps.get(p + ".conv2.conv.weight"), l.cout, l.cout, 3));
+                std::vector<float> b2 = ps.get(p + ".conv2.conv.bias");
+                if (l.cin != l.cout) {
+                    l.o_wskip = wp.push(pack_conv(ps.get(p + ".nin_shortcut.conv.weight"), l.cout, l.cin, 1));
+                    const auto& bs = ps.get(p + ".nin_shortcut.conv.bias");
+                    for (int i = 0; i < l.cout; ++i) b2[i] += bs[i];
+                }
+                l.o_b2 = wp.push(b2);
+                break;
+            }
+            case ALayer::DOWN: case ALayer::UP:
+                l.o_w1 = wp.push(pack_conv(ps.get(p + ".conv.conv.weight"), l.cin, l.cin, 3)); l.o_b1 = wp.push(ps.get(p + ".conv.conv.bias"));
+                break;
+            case ALayer::NORM:
+                l.o_g1 = wp.push(ps.get(p + ".weight")); l.o_be1 = wp.push(ps.get(p + ".bias"));
+                break;
+        }
+    };
+    for (auto& l : h->enc) stage(l);
+    for (auto& l : h->dec) stage(l);
+    stage(h->q_mu); stage(h->q_ls); stage(h->post_q);
+    r = wp.upload();
+    if (r) return r;
+    auto fix = [&](ALayer& l) {
+        l.g1 = wp.at(l.o_g1); l.be1 = wp.at(l.o_be1); l.w1 = wp.at(l.o_w1); l.b1 = wp.at(l.o_b1);
+        l.g2 = wp.at(l.o_g2); l.be2 = wp.at(l.o_be2); l.w2 = wp.at(l.o_w2); l.b2 = wp.at(l.o_b2);
+        l.wskip = (l.kind == ALayer::RES && l.cin != l.cout) ? wp.at(l.o_wskip) : nullptr;
+    };
+    for (auto& l : h->enc) fix(l);
+    for (auto& l : h->dec) fix(l);
+    fix(h->q_mu); fix(h->q_ls); fix(h->post_q);
+    h->finalized = true;
+    return EEGLDM_OK;
+}
+
+Act plan_aekl_conv(Builder& bd, const ALayer& l, const Act& x, const ScaleShift* ss, int resample, int stride, int pad_left,
+                   float* ext_out = nullptr) {
+    const int Tc = resampled_len(x.T, resample);
+    const int Tout = stride == 1 ? Tc : (Tc + 1 - 3) / 2 + 1;  // stride 2: pad right 1, k3, padding 0
+    Act y;
+    if (ext_out) { y.ext = ext_out; y.C = l.cout; y.T = Tout; }
+    else y = bd.act(l.cout, Tout);
+    ConvParams p{};
+    p.seg[0] = make_seg(bd, x, nullptr, ss, 0, resample, l.w1, l.k);
+    p.nseg = 1; p.Cout = l.cout; p.Tout = Tout; p.Tc = Tc; p.stride = stride; p.pad_left = pad_left;
+    p.bias = l.b1; p.out = ext_out ? ext_out : bd.wptr(y);
+    plan_conv(bd, p);
+    return y;
+}
+
+// generic block runner (Encoder.forward / Decoder.forward upstream; ae_kl.py:66-80 ResBlock)
+Act plan_aekl_blocks(Builder& bd, const std::vector<ALayer>& blocks, Act cur, int G, float* final_out) {
+    ScaleShift pending{};  // the final GroupNorm is folded into the last conv's prologue (no SiLU)
+    bool has_pending = false;
+    for (size_t i = 0; i < blocks.size(); ++i) {
+        const ALayer& l = blocks[i];
+        const bool last = i + 1 == blocks.size();
+        switch (l.kind) {
+            case ALayer::CONV:
+                cur = plan_aekl_conv(bd, l, cur, has_pending ? &pending : nullptr, RS_NONE, 1, l.k / 2, last ? final_out : nullptr);
+                has_pending = false; pending = ScaleShift{};
+                break;
+            case ALayer::RES: {
+                Act h1 = bd.act(l.cout, cur.T);
+                {
+                    ScaleShift ss = plan_gn(bd, cur, nullptr, G, l.g1, l.be1, 1e-6f);
+                    ConvParams p{};
+                    p.seg[0] = make_seg(bd, cur, nullptr, &ss, 1, RS_NONE, l.w1, 3);
+                    p.nseg = 1; p.Cout = l.cout; p.Tout = cur.T; p.Tc = cur.T; p.stride = 1; p.pad_left = 1;
+                    p.bias = l.b1; p.out = bd.wptr(h1);
+                    plan_conv(bd, p);
+                }
+                Act y = bd.act(l.cout, cur.T);
+                {
+                    ScaleShift ss = plan_gn(bd, h1, nullptr, G, l.g2, l.be2, 1e-6f);
+                    ConvParams p{};
+                    p.seg[0] = make_seg(bd, h1, nullptr, &ss, 1, RS_NONE, l.w2, 3);
+                    p.nseg = 1; p.Cout = l.cout; p.Tout = cur.T; p.Tc = cur.T; p.stride = 1; p.pad_left = 1;
+                    p.bias = l.b2;
+                    if (l.cin != l.cout) { p.seg[1] = make_seg(bd, cur, nullptr, nullptr, 0, RS_NONE, l.wskip, 1); p.nseg = 2; }
+                    else { p.res = bd.ptr(cur); p.res_mode = RS_NONE; p.res_Tin = cur.T; }
+                    p.out = bd.wptr(y);
+                    plan_conv(bd, p);
+                }
+                cur = y;
+                break;
+            }
+            case ALayer::DOWN: cur = plan_aekl_conv(bd, l, cur, nullptr, RS_NONE, 2, 0); break;     // ae_kl.py:41-45
+            case ALayer::UP: cur = plan_aekl_conv(bd, l, cur, nullptr, RS_NEAREST2, 1, 1); break;   // ae_kl.py:27-30
+            case ALayer::NORM:
+                pending = plan_gn(bd, cur, nullptr, G, l.g1, l.be1, 1e-6f);
+                has_pending = true;
+                break;
+        }
+    }
+    return cur;
+}
+
+struct AeklEncodeIO { const float* x; float* mu; float* sigma; };
+
+int plan_aekl_encode(eegldm_aekl* h, Builder& bd, int L, const AeklEncodeIO& io) {
+    Act x; x.ext = io.x; x.C = h->cfg.in_channels; x.T = L;
+    Act hh = plan_aekl_blocks(bd, h->enc, x, h->cfg.norm_num_groups, nullptr);
+    plan_aekl_conv(bd, h->q_mu, hh, nullptr, RS_NONE, 1, 0, io.mu);
+    Act ls = plan_aekl_conv(bd, h->q_ls, hh, nullptr, RS_NONE, 1, 0);
+    const float* lsp = bd.ptr(ls); float* sg = io.sigma;
+    const size_t n = (size_t)bd.B * ls.T * ls.C;
+    bd.add([=](cudaStream_t st) { return launch_kl_sigma(lsp, sg, n, st); }, 1);
+    return EEGLDM_OK;
+}
+
+int plan_aekl_decode(eegldm_aekl* h, Builder& bd, int T, const float* z, float* out) {
+    Act x; x.ext = z; x.C = h->cfg.latent_channels; x.T = T;
+    Act p = plan_aekl_conv(bd, h->post_q, x, nullptr, RS_NONE, 1, 0);
+    plan_aekl_blocks(bd, h->dec, p, h->cfg.norm_num_groups, out);
+    return EEGLDM_OK;
+}
+
+template <class PlanFn>
+int build_aekl_plan(eegldm_aekl* h, int B, PlanFn fn, Builder& out) {
+    Builder sizing; sizing.B = B;
+    int r = fn(sizing);
+    if (r) return r;
+    r = ensure(h->arena, h->arena_cap, std::max<size_t>(sizing.peak, 64));
+    if (r) return r;
+    out.B = B; out.base = h->arena;
+    return fn(out);
+}
+
+// boundary layout helpers: reference NCL <-> engine NLC (identity when C == 1)
+int to_nlc(const float* src_ncl, float*& tmp, size_t& cap, size_t tmp_off, int B, int C, int T, cudaStream_t st,
+           const float** out) {
+    if (C == 1) { *out = src_ncl; return EEGLDM_OK; }
+    (void)cap;
+    CU(launch_transpose_ncl_to_nlc(src_ncl, tmp + tmp_off, B, C, T, st));
+    *out = tmp + tmp_off;
+    return EEGLDM_OK;
+}
+
+}  // namespace
+
+// ================================================================================================ C ABI
+extern "C" {
+
+const char* eegldm_last_error(void) { return g_err.c_str(); }
+const char* eegldm_version(void) { return "eegldm 0.1 (sm_100a)"; }
+int64_t eegldm_launch_count(void) { return (int64_t)g_launch_count.load(); }
+int eegldm_set_graphs(int enabled) { g_graphs_enabled = enabled != 0; return EEGLDM_OK; }
+
+int eegldm_profile_enable(int on) {
+    for (auto& r : g_prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    g_prof.clear();
+    g_profile = on != 0;
+    return EEGLDM_OK;
+}
+int eegldm_profile_read(int kind, double* ms, double* flops, double* bytes, int64_t* launches) {
+    if (kind < 0 || kind >= OP_NKIND) return fail(EEGLDM_ERR_INVALID, "kind must be 0 (conv), 1 (groupnorm), 2 (attention) or 3 (other)");
+    double t = 0, f = 0, b = 0; int64_t n = 0;
+    for (auto& r : g_prof) {
+        if (r.m.kind != kind) continue;
+        CU(cudaEventSynchronize(r.e1));
+        float dt = 0.f;
+        CU(cudaEventElapsedTime(&dt, r.e0, r.e1));
+        t += dt; f += r.m.flops; b += r.m.bytes; ++n;
+    }
+    if (ms) *ms = t; if (flops) *flops = f; if (bytes) *bytes = b; if (launches) *launches = n;
+    return EEGLDM_OK;
+}
+
+int eegldm_unet_create(const eegldm_unet_cfg* cfg, eegldm_unet** out) {
+    if (!cfg || !out) return fail(EEGLDM_ERR_INVALID, "null argument");
+    auto* h = new (std::nothrow) eegldm_unet();
+    if (!h) return fail(EEGLDM_ERR_NOMEM, "out of host memory");
+    h->cfg = *cfg;
+    int r = build_unet_topology(h);
+    if (r) { delete h; return r; }
+    *out = h;
+    return EEGLDM_OK;
+}
+void eegldm_unet_destroy(eegldm_unet* h) { delete h; }
+int eegldm_unet_num_params(const eegldm_unet* h) { return h ? (int)h->ps.params.size() : 0; }
+int eegldm_unet_param_info(const eegldm_unet* h, int i, const char** name, int64_t shape[4], int* ndim) {
+    if (!h || i < 0 || i >= (int)h->ps.params.size()) return fail(EEGLDM_ERR_INVALID, "bad parameter index");
+    const HostParam& p = h->ps.params[i];
+    if (name) *name = p.name.c_str();
+    if (ndim) *ndim = (int)p.shape.size();
+    if (shape) for (size_t k = 0; k < p.shape.size() && k < 4; ++k) shape[k] = p.shape[k];
+    return EEGLDM_OK;
+}
+int eegldm_unet_load(eegldm_unet* h, const char* name, const float* host, const int64_t* shape, int ndim) {
+    if (!h) return fail(EEGLDM_ERR_INVALID, "null handle");
+    h->finalized = false;
+    return h->ps.load(name, host, shape, ndim);
+}
+int eegldm_unet_finalize(eegldm_unet* h) {
+    if (!h) return fail(EEGLDM_ERR_INVALID, "null handle");
+    return finalize_unet(h);
+}
+int eegldm_unet_set_math(eegldm_unet* h, eegldm_math mode) {
+    if (!h) return fail(EEGLDM_ERR_INVALID, "null handle");
+    if (mode != EEGLDM_MATH_FP32_SIMT) return fail(EEGLDM_ERR_INVALID, "only EEGLDM_MATH_FP32_SIMT is built in this version");
+    if (mode != h->math) h->drop_graphs();
+    h->math = mode;
+    return EEGLDM_OK;
+}
+
+int eegldm_unet_forward(eegldm_unet* h, const float* x_dev, const float* timesteps_host, int nt, float* out_dev, int B,
+                        int T, void* stream) {
+    if (!h || !x_dev || !timesteps_host || !out_dev) return fail(EEGLDM_ERR_INVALID, "null argument");
+    if (!h->finalized) return fail(EEGLDM_ERR_MISSING, "eegldm_unet_finalize has not been called");
+    if (B < 0 || (nt != 1 && nt != B)) return fail(EEGLDM_ERR_SHAPE, "timesteps must have 1 or B entries");
+    if (B == 0) return EEGLDM_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int zin = h->cfg.in_channels, zout = h->cfg.out_channels;
+    int r = ensure(h->temb_fwd, h->temb_fwd_cap, (size_t)nt * h->emb_total);
+    if (r) return r;
+    r = run_time_mlp(h, timesteps_host, nt, h->temb_fwd, st);
+    if (r) return r;
+    const size_t nin = (size_t)B * T * zin, nout = (size_t)B * T * zout;
+    r = ensure(h->xtmp, h->xtmp_cap, nin + nout);
+    if (r) return r;
+    UNetIO io{};
+    r = to_nlc(x_dev, h->xtmp, h->xtmp_cap, 0, B, zin, T, st, &io.x);
+    if (r) return r;
+    io.out = zout == 1 ? out_dev : h->xtmp + nin;
+    io.temb = h->temb_fwd; io.temb_stride = nt == 1 ? 0 : h->emb_total;
+    Builder bd;
+    r = build_unet_plan(h, B, T, io, bd);
+    if (r) return r;
+    r = run_ops(bd, st);
+    if (r) return r;
+    if (zout != 1) CU(launch_transpose_nlc_to_ncl(io.out, out_dev, B, zout, T, st));
+    return EEGLDM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- AEKL
+int eegldm_aekl_create(const eegldm_aekl_cfg* cfg, eegldm_aekl** out) {
+    if (!cfg || !out) return fail(EEGLDM_ERR_INVALID, "null argument");
+    auto* h = new (std::nothrow) eegldm_aekl();
+    if (!h) return fail(EEGLDM_ERR_NOMEM, "out of host memory");
+    h->cfg = *cfg;
+    int r = build_aekl_topology(h);
+    if (r) { delete h; return r; }
+    *out = h;
+    return EEGLDM_OK;
+}
+void eegldm_aekl_destroy(eegldm_aekl* h) { delete h; }
+int eegldm_aekl_num_params(const eegldm_aekl* h) { return h ? (int)h->ps.params.size() : 0; }
+int eegldm_aekl_param_info(const eegldm_aekl* h, int i, const char** name, int64_t shape[4], int* ndim) {
+    if (!h || i < 0 || i >= (int)h->ps.params.size()) return fail(EEGLDM_ERR_INVALID, "bad parameter index");
+    const HostParam& p = h->ps.params[i];
+    if (name) *name = p.name.c_str();
+    if (ndim) *ndim = (int)p.shape.size();
+    if (shape) for (size_t k = 0; k < p.shape.size() && k < 4; ++k) shape[k] = p.shape[k];
+    return EEGLDM_OK;
+}
+int eegldm_aekl_load(eegldm_aekl* h, const char* name, const float* host, const int64_t* shape, int ndim) {
+    if (!h) return fail(EEGLDM_ERR_INVALID, "null handle");
+    h->finalized = false;
+    return h->ps.load(name, host, shape, ndim);
+}
+int eegldm_aekl_finalize(eegldm_aekl* h) {
+    if (!h) return fail(EEGLDM_ERR_INVALID, "null handle");
+    return finalize_aekl(h);
+}
+
+int eegldm_aekl_encode(eegldm_aekl* h, const float* x_dev, float* z_mu_dev, float* z_sigma_dev, int B, int L, void* stream) {
+    if (!h || !x_dev || !z_mu_dev || !z_sigma_dev) return fail(EEGLDM_ERR_INVALID, "null argument");
+    if (!h->finalized) return fail(EEGLDM_ERR_MISSING, "eegldm_aekl_finalize has not been called");
+    const int f = h->down_factor();
+    if (B < 0 || L <= 0 || L % f) return fail(EEGLDM_ERR_SHAPE, "L must be a positive multiple of 2^(levels-1)");
+    if (B == 0) return EEGLDM_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int cin = h->cfg.in_channels, z = h->cfg.latent_channels, T = L / f;
+    const size_t nin = (size_t)B * L * cin, nz = (size_t)B * T * z;
+    int r = ensure(h->io_tmp, h->io_tmp_cap, nin + 2 * nz);
+    if (r) return r;
+    AeklEncodeIO io{};
+    r = to_nlc(x_dev, h->io_tmp, h->io_tmp_cap, 0, B, cin, L, st, &io.x);
+    if (r) return r;
+    io.mu = z == 1 ? z_mu_dev : h->io_tmp + nin;
+    io.sigma = z == 1 ? z_sigma_dev : h->io_tmp + nin + nz;
+    Builder bd;
+    r = build_aekl_plan(h, B, [&](Builder& b) { return plan_aekl_encode(h, b, L, io); }, bd);
+    if (r) return r;
+    r = run_ops(bd, st);
+    if (r) return r;
+    if (z != 1) {
+        CU(launch_transpose_nlc_to_ncl(io.mu, z_mu_dev, B, z, T, st));
+        CU(launch_transpose_nlc_to_ncl(io.sigma, z_sigma_dev, B, z, T, st));
+    }
+    return EEGLDM_OK;
+}
+
+int eegldm_aekl_decode(eegldm_aekl* h, const float* z_dev, float* out_dev, int B, int T, void* stream) {
+    if (!h || !z_dev || !out_dev) return fail(EEGLDM_ERR_INVALID, "null argument");
+    if (!h->finalized) return fail(EEGLDM_ERR_MISSING, "eegldm_aekl_finalize has not been called");
+    if (B < 0 || T <= 0) return fail(EEGLDM_ERR_SHAPE, "bad latent shape");
+    if (B == 0) return EEGLDM_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int z = h->cfg.latent_channels, co = h->cfg.out_channels, L = T * h->down_factor();
+    const size_t nz = (size_t)B * T * z, nout = (size_t)B * L * co;
+    int r = ensure(h->io_tmp, h->io_tmp_cap, nz + nout);
+    if (r) return r;
+    const float* zin;
+    r = to_nlc(z_dev, h->io_tmp, h->io_tmp_cap, 0, B, z, T, st, &zin);
+    if (r) return r;
+    float* out = co == 1 ? out_dev : h->io_tmp + nz;
+    Builder bd;
+    r = build_aekl_plan(h, B, [&](Builder& b) { return plan_aekl_decode(h, b, T, zin, out); }, bd);
+    if (r) return r;
+    r = run_ops(bd, st);
+    if (r) return r;
+    if (co != 1) CU(launch_transpose_nlc_to_ncl(out, out_dev, B, co, L, st));
+    return EEGLDM_OK;
+}
+
+int eegldm_aekl_forward(eegldm_aekl* h, const float* x_dev, const float* eps_dev, float* recon_dev, float* z_mu_dev,
+                        float* z_sigma_dev, int B, int L, void* stream) {
+    if (!h || !eps_dev || !recon_dev) return fail(EEGLDM_ERR_INVALID, "null argument");
+    int r = eegldm_aekl_encode(h, x_dev, z_mu_dev, z_sigma_dev, B, L, stream);
+    if (r || B == 0) return r;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int T = L / h->down_factor();
+    const size_t nz = (size_t)B * T * h->cfg.latent_channels;
+    float* zbuf = nullptr;
+    CU(cudaMallocAsync((void**)&zbuf, nz * sizeof(float), st));
+    cudaError_t e = launch_axpy_sampling(z_mu_dev, z_sigma_dev, eps_dev, zbuf, nz, st);  // NCL elementwise
+    if (e == cudaSuccess) {
+        r = eegldm_aekl_decode(h, zbuf, recon_dev, B, T, stream);
+    } else r = cuda_fail(e, "sampling kernel");
+    cudaFreeAsync(zbuf, st);
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------- scheduler
+int eegldm_sched_alphas_cumprod(const eegldm_sched_cfg* cfg, float* out) {
+    if (!out) return fail(EEGLDM_ERR_INVALID, "null argument");
+    std::vector<float> ac;
+    int r = sched_alphas(cfg, ac);
+    if (r) return r;
+    std::memcpy(out, ac.data(), ac.size() * sizeof(float));
+    return EEGLDM_OK;
+}
+int eegldm_sched_ddim_tables(const eegldm_sched_cfg* cfg, int n_steps, int64_t* timesteps, float* coef) {
+    std::vector<int64_t> ts; std::vector<float> cf;
+    int r = sched_ddim_tables(cfg, n_steps, ts, cf);
+    if (r) return r;
+    if (timesteps) std::memcpy(timesteps, ts.data(), ts.size() * sizeof(int64_t));
+    if (coef) std::memcpy(coef, cf.data(), cf.size() * sizeof(float));
+    return EEGLDM_OK;
+}
+int eegldm_timestep_embedding(const float* timesteps, int nt, int dim, float* out) {
+    if (!timesteps || !out || nt < 0 || dim < 1) return fail(EEGLDM_ERR_INVALID, "bad argument");
+    timestep_embedding_host(timesteps, nt, dim, out);
+    return EEGLDM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- sampling
+int eegldm_ddim_sample(eegldm_unet* u, eegldm_aekl* a, const eegldm_sched_cfg* sc, const float* noise_dev, float scale_factor,
+                       int n_steps, float* out_dev, int B, int T, void* stream) {
+    if (!u || !sc || !noise_dev || !out_dev) return fail(EEGLDM_ERR_INVALID, "null argument");
+    if (!u->finalized) return fail(EEGLDM_ERR_MISSING, "eegldm_unet_finalize has not been called");
+    if (a && !a->finalized) return fail(EEGLDM_ERR_MISSING, "eegldm_aekl_finalize has not been called");
+    if (u->cfg.in_channels != u->cfg.out_channels) return fail(EEGLDM_ERR_INVALID, "sampling needs in_channels == out_channels");
+    if (a && a->cfg.latent_channels != u->cfg.in_channels) return fail(EEGLDM_ERR_INVALID, "latent_channels mismatch");
+    if (B < 0) return fail(EEGLDM_ERR_SHAPE, "negative batch");
+    if (scale_factor == 0.f) return fail(EEGLDM_ERR_INVALID, "scale_factor must be non-zero");
+    if (B == 0) return EEGLDM_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int z = u->cfg.in_channels;
+    const size_t nz = (size_t)B * T * z;
+
+    // per-step tables (timestep embedding rows through the time MLP + DDIM coefficients), cached
+    std::vector<int64_t> ts; std::vector<float> coef;
+    int r = sched_ddim_tables(sc, n_steps, ts, coef);
+    if (r) return r;
+    std::vector<float> key{(float)sc->num_train_timesteps, sc->beta_start, sc->beta_end, (float)sc->schedule,
+                           (float)sc->prediction_type, (float)sc->set_alpha_to_one, (float)sc->steps_offset, (float)n_steps};
+    if (key != u->table_key) {
+        r = ensure(u->temb_table, u->temb_table_cap, (size_t)n_steps * u->emb_total);
+        if (r) return r;
+        r = ensure(u->coef_table, u->coef_table_cap, (size_t)2 * n_steps);
+        if (r) return r;
+        std::vector<float> tf(ts.begin(), ts.end());
+        r = run_time_mlp(u, tf.data(), n_steps, u->temb_table, st);
+        if (r) return r;
+        CU(cudaMemcpyAsync(u->coef_table, coef.data(), coef.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+        CU(cudaStreamSynchronize(st));  // coef (host vector) must outlive the copy; tables are built once
+        u->table_key = key;
+    }
+    if (nz > u->xbuf_cap) u->drop_graphs();
+    r = ensure(u->xbuf, u->xbuf_cap, nz);
+    if (r) return r;
+    r = ensure(u->xtmp, u->xtmp_cap, 2 * nz);
+    if (r) return r;
+    // x_T = noise (sample_trials.py:151), engine layout
+    if (z == 1) CU(cudaMemcpyAsync(u->xbuf, noise_dev, nz * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    else CU(launch_transpose_ncl_to_nlc(noise_dev, u->xbuf, B, z, T, st));
+    CU(cudaMemsetAsync(u->step_ctr, 0, sizeof(int), st));
+
+    UNetIO io{};
+    io.x = u->xbuf; io.out = u->xbuf; io.temb = u->temb_step; io.temb_stride = 0;
+    io.ddim_x = u->xbuf; io.ddim_coef = u->coef_cur;
+    auto emit_step = [&](const Builder& bd, cudaStream_t s) -> int {
+        cudaError_t e = launch_step_advance(u->temb_table, u->emb_total, u->temb_step, u->coef_table, u->coef_cur, u->step_ctr, s);
+        if (e != cudaSuccess) return cuda_fail(e, "step_advance");
+        return run_ops(bd, s);
+    };
+    if (g_graphs_enabled) {
+        auto key2 = std::make_pair(B, T);
+        auto it = u->graphs.find(key2);
+        if (it == u->graphs.end()) {
+            Builder bd;
+            r = build_unet_plan(u, B, T, io, bd);   // may grow the arena (and drop stale graphs)
+            if (r) return r;
+            GraphEntry ge;
+            const long long before = g_launch_count.load();
+            CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            r = emit_step(bd, st);
+            cudaError_t e = cudaStreamEndCapture(st, &ge.graph);
+            if (r) { if (ge.graph) cudaGraphDestroy(ge.graph); return r; }
+            if (e != cudaSuccess) return cuda_fail(e, "cudaStreamEndCapture");
+            ge.n_kernels = (int)(g_launch_count.load() - before);
+            g_launch_count.store(before);  // capture did not launch anything
+            e = cudaGraphInstantiate(&ge.exec, ge.graph, 0);
+            if (e != cudaSuccess) { cudaGraphDestroy(ge.graph); return cuda_fail(e, "cudaGraphInstantiate"); }
+            it = u->graphs.emplace(key2, ge).first;
+        }
+        for (int s = 0; s < n_steps; ++s) {
+            CU(cudaGraphLaunch(it->second.exec, st));
+            g_launch_count += it->second.n_kernels;
+        }
+    } else {
+        Builder bd;
+        r = build_unet_plan(u, B, T, io, bd);
+        if (r) return r;
+        for (int s = 0; s < n_steps; ++s) { r = emit_step(bd, st); if (r) return r; }
+    }
+    if (!a) {
+        if (z == 1) CU(cudaMemcpyAsync(out_dev, u->xbuf, nz * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        else CU(launch_transpose_nlc_to_ncl(u->xbuf, out_dev, B, z, T, st));
+        return EEGLDM_OK;
+    }
+    // decode_stage_2_outputs(latent / scale_factor)   sample_trials.py:166
+    float* zs = u->xtmp;  // NCL staging for the decoder's boundary
+    if (z == 1) CU(launch_scale(u->xbuf, zs, 1.0f / scale_factor, nz, st));
+    else {
+        CU(launch_transpose_nlc_to_ncl(u->xbuf, zs + nz, B, z, T, st));
+        CU(launch_scale(zs + nz, zs, 1.0f / scale_factor, nz, st));
+    }
+    return eegldm_aekl_decode(a, zs, out_dev, B, T, stream);
+}
+
+int eegldm_ddim_sample_host(eegldm_unet* u, eegldm_aekl* a, const eegldm_sched_cfg* sc, const float* noise_host,
+                            float scale_factor, int n_steps, float* out_host, int B, int T, void* stream) {
+    if (!u || !noise_host || !out_host) return fail(EEGLDM_ERR_INVALID, "null argument");
+    if (B <= 0) return B == 0 ? EEGLDM_OK : fail(EEGLDM_ERR_SHAPE, "negative batch");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t nz = (size_t)B * T * u->cfg.in_channels;
+    const size_t nout = a ? (size_t)B * T * a->down_factor() * a->cfg.out_channels : nz;
+    float *d_in = nullptr, *d_out = nullptr;
+    CU(cudaMallocAsync((void**)&d_in, nz * sizeof(float), st));
+    cudaError_t e = cudaMallocAsync((void**)&d_out, nout * sizeof(float), st);
+    if (e != cudaSuccess) { cudaFreeAsync(d_in, st); return cuda_fail(e, "cudaMallocAsync"); }
+    int r = EEGLDM_OK;
+    e = cudaMemcpyAsync(d_in, noise_host, nz * sizeof(float), cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) r = cuda_fail(e, "H2D copy");
+    if (!r) r = eegldm_ddim_sample(u, a, sc, d_in, scale_factor, n_steps, d_out, B, T, stream);
+    if (!r) {
+        e = cudaMemcpyAsync(out_host, d_out, nout * sizeof(float), cudaMemcpyDeviceToHost, st);
+        if (e != cudaSuccess) r = cuda_fail(e, "D2H copy");
+    }
+    cudaFreeAsync(d_in, st);
+    cudaFreeAsync(d_out, st);
+    e = cudaStreamSynchronize(st);
+    if (!r && e != cudaSuccess) r = cuda_fail(e, "cudaStreamSynchronize");
+    return r;
+}
+
+}  // extern "C"

@@ -1,0 +1,90 @@
+// Kernel-level interface of the eegldm engine (internal; the public boundary is include/eegldm.h).
+//
+// Data layout in HBM: every activation is fp32 channels-last  [B][T][C]  (C contiguous).
+// For the 1-channel signals / latents at the API boundary this is bit-identical to the
+// reference's NCL layout; multi-channel latents are transposed once at the boundary.
+#pragma once
+#include <cuda_runtime.h>
+#include <atomic>
+#include <cstdint>
+
+namespace eegldm {
+
+// kernels launched by this library since process start (eegldm_launch_count)
+extern std::atomic<long long> g_launch_count;
+
+enum Resample : int { RS_NONE = 0, RS_AVGPOOL2 = 1, RS_NEAREST2 = 2 };
+
+// One K-segment of the implicit GEMM  out[b,t,co] += sum_{ci,k} W[ci,k,co] * u[b, t*stride+k-pad, ci]
+// where u = resample(act(concat(src0,src1))) and act(x) = silu?(scale*x + shift).
+struct ConvSeg {
+    const float* src0;   // [B][Tin][C0]
+    const float* src1;   // [B][Tin][C1] or null (virtual channel concat, reference unet.py:553)
+    int C0, C1;
+    const float* scale;  // [B][C0+C1] GroupNorm scale (gamma*rstd) or null
+    const float* shift;  // [B][C0+C1] GroupNorm shift (beta-mean*gamma*rstd)
+    int silu;            // SiLU after the affine
+    int resample;        // Resample applied AFTER act (unet.py:308-313)
+    int Tin;             // source length (before resample)
+    const float* w;      // packed [(ci*taps+k)][Cout]
+    int taps;            // 1 or 3
+};
+
+struct ConvParams {
+    ConvSeg seg[2];
+    int nseg;
+    int Cout, Tout;
+    int Tc;              // conv-input length after resample
+    int stride;          // 1 or 2 (seg[0] only; seg[1] is a 1x1 at output resolution)
+    int pad_left;        // 1 for "same" k3, 0 for k1 and for the AEKL pad-right-1/stride-2 downsample
+    const float* bias;   // [Cout] (already summed over segments) or null
+    const float* temb;   // temb[b*temb_stride + co] or null
+    int temb_stride;
+    const float* res;    // identity residual [B][res_Tin][Cout] or null
+    int res_mode;        // Resample of the residual
+    int res_Tin;
+    float* out;          // [B][Tout][Cout]
+    const float* ddim_x;     // if non-null: out = coef[0]*ddim_x + coef[1]*value   (DDIM step epilogue)
+    const float* ddim_coef;  // device [2]
+    int B;
+};
+
+struct GnParams {
+    const float* src0; const float* src1; int C0, C1;
+    int T, G;
+    const float* gamma; const float* beta; float eps;
+    float* scale; float* shift;   // [B][C]
+    float* partial;               // [B][nsplit][G][3] scratch
+    int nsplit;
+    int B;
+};
+
+struct AttnParams {
+    const float* qkv;   // [B][T][H*3*ch]  (legacy head layout, unet.py:116-118)
+    float* out;         // [B][T][H*ch]
+    int T, H, ch, B;
+};
+
+cudaError_t launch_conv_simt(const ConvParams& p, cudaStream_t st);
+cudaError_t launch_groupnorm(const GnParams& p, cudaStream_t st);
+int groupnorm_nsplit(int C, int T, int G);
+cudaError_t launch_attention_simt(const AttnParams& p, cudaStream_t st);
+// y[r][o] = bias[o] + sum_i act(x[r][i]) * W[o][i];  act = SiLU if silu_in
+cudaError_t launch_linear(const float* x, const float* W, const float* bias, float* y, int R, int I, int O,
+                          int silu_in, cudaStream_t st);
+// NCL <-> NLC transposes for multi-channel boundary tensors
+cudaError_t launch_transpose_ncl_to_nlc(const float* in, float* out, int B, int C, int T, cudaStream_t st);
+cudaError_t launch_transpose_nlc_to_ncl(const float* in, float* out, int B, int C, int T, cudaStream_t st);
+// standalone Downsample/Upsample without conv (unet.py:195,221) on [B][Tin][C]
+cudaError_t launch_resample(const float* in, float* out, int B, int Tin, int C, int mode, cudaStream_t st);
+// dst[i] = src[i] * alpha
+cudaError_t launch_scale(const float* src, float* dst, float alpha, size_t n, cudaStream_t st);
+// copies row `*step` of the per-step tables into the "current" buffers and increments *step
+cudaError_t launch_step_advance(const float* temb_table, int temb_row, float* temb_cur, const float* coef_table,
+                                float* coef_cur, int* step, cudaStream_t st);
+// AEKL sampling: z = mu + eps * sigma ; sigma = exp(clamp(logvar,-30,20)/2)
+cudaError_t launch_kl_sigma(const float* logvar, float* sigma, size_t n, cudaStream_t st);
+cudaError_t launch_axpy_sampling(const float* mu, const float* sigma, const float* eps, float* z, size_t n,
+                                 cudaStream_t st);
+
+}  // namespace eegldm

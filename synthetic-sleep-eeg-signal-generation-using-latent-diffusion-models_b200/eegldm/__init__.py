@@ -1,0 +1,25 @@
+"""eegldm -- B200-native drop-in for the reference's latent-diffusion sampling path.
+
+Re-exposes, on top of the C ABI in ``include/eegldm.h`` (hand-written sm_100a CUDA kernels):
+
+* ``UNetModel``            <- ``src/models/unet.py:330``  (``forward(x, timesteps)``)
+* ``AutoencoderKL``        <- ``generative.networks.nets.AutoencoderKL`` as built at ``src/sample_trials.py:95-100``
+* ``DDIMScheduler`` / ``DDPMScheduler`` <- ``generative.networks.schedulers`` as used at ``src/sample_trials.py:136-163``
+* ``ddim_sample``          <- the sampling loop ``src/sample_trials.py:153-169`` as one fused call
+
+PyTorch is used for device memory, streams and ``nn.Module`` plumbing only.
+"""
+from ._lib import EegldmError, lib, LIB_PATH  # noqa: F401
+from .unet import UNetModel  # noqa: F401
+from .aekl import AutoencoderKL  # noqa: F401
+from .schedulers import DDIMScheduler, DDPMScheduler  # noqa: F401
+from .sampler import ddim_sample, ddim_sample_host, shard_range, sample_sharded  # noqa: F401
+
+
+def launch_count() -> int:
+    """CUDA kernels launched by libeegldm since process start."""
+    return int(lib().eegldm_launch_count())
+
+
+def version() -> str:
+    return lib().eegldm_version().decode()

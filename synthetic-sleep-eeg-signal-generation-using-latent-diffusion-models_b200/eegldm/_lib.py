@@ -1,0 +1,138 @@
+"""ctypes binding of the eegldm C ABI (include/eegldm.h).
+
+There is no CPU fallback: if ``libeegldm.so`` has not been built (``python <package>/build.py`` or
+``__graft_entry__.build()``) importing this module raises, and every compute entry point returns
+``EEGLDM_ERR_CUDA`` without a CUDA device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libeegldm.so")
+
+
+class EegldmError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"eegldm error {code}: {msg}")
+        self.code = code
+
+
+class UNetCfg(C.Structure):
+    _fields_ = [
+        ("image_size", C.c_int32), ("in_channels", C.c_int32), ("model_channels", C.c_int32),
+        ("out_channels", C.c_int32), ("num_res_blocks", C.c_int32),
+        ("n_attention_resolutions", C.c_int32), ("attention_resolutions", C.c_int32 * 8),
+        ("n_channel_mult", C.c_int32), ("channel_mult", C.c_int32 * 8),
+        ("num_heads", C.c_int32), ("num_head_channels", C.c_int32), ("num_heads_upsample", C.c_int32),
+        ("resblock_updown", C.c_int32), ("conv_resample", C.c_int32), ("use_scale_shift_norm", C.c_int32),
+    ]
+
+
+class AeklCfg(C.Structure):
+    _fields_ = [
+        ("in_channels", C.c_int32), ("out_channels", C.c_int32), ("n_levels", C.c_int32),
+        ("num_channels", C.c_int32 * 8), ("num_res_blocks", C.c_int32 * 8),
+        ("latent_channels", C.c_int32), ("norm_num_groups", C.c_int32),
+    ]
+
+
+class SchedCfg(C.Structure):
+    _fields_ = [
+        ("num_train_timesteps", C.c_int32), ("beta_start", C.c_float), ("beta_end", C.c_float),
+        ("schedule", C.c_int32), ("prediction_type", C.c_int32), ("set_alpha_to_one", C.c_int32),
+        ("steps_offset", C.c_int32),
+    ]
+
+
+MATH_FP32_SIMT, MATH_BF16X3_TC, MATH_BF16_TC = 0, 1, 2
+MATH_MODES = {"fp32": MATH_FP32_SIMT, "fp32_simt": MATH_FP32_SIMT, "bf16x3": MATH_BF16X3_TC, "bf16x3_tc": MATH_BF16X3_TC,
+              "bf16": MATH_BF16_TC, "bf16_tc": MATH_BF16_TC}
+
+_P = C.c_void_p
+_FP = C.POINTER(C.c_float)
+_I64P = C.POINTER(C.c_int64)
+
+# name -> (restype, argtypes); must list every symbol include/eegldm.h declares
+SIGNATURES = {
+    "eegldm_last_error": (C.c_char_p, []),
+    "eegldm_version": (C.c_char_p, []),
+    "eegldm_launch_count": (C.c_int64, []),
+    "eegldm_set_graphs": (C.c_int, [C.c_int]),
+    "eegldm_profile_enable": (C.c_int, [C.c_int]),
+    "eegldm_profile_read": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                      C.POINTER(C.c_int64)]),
+    "eegldm_unet_create": (C.c_int, [C.POINTER(UNetCfg), C.POINTER(_P)]),
+    "eegldm_unet_destroy": (None, [_P]),
+    "eegldm_unet_num_params": (C.c_int, [_P]),
+    "eegldm_unet_param_info": (C.c_int, [_P, C.c_int, C.POINTER(C.c_char_p), _I64P, C.POINTER(C.c_int)]),
+    "eegldm_unet_load": (C.c_int, [_P, C.c_char_p, _P, _I64P, C.c_int]),
+    "eegldm_unet_finalize": (C.c_int, [_P]),
+    "eegldm_unet_set_math": (C.c_int, [_P, C.c_int]),
+    "eegldm_unet_forward": (C.c_int, [_P, _P, _FP, C.c_int, _P, C.c_int, C.c_int, _P]),
+    "eegldm_aekl_create": (C.c_int, [C.POINTER(AeklCfg), C.POINTER(_P)]),
+    "eegldm_aekl_destroy": (None, [_P]),
+    "eegldm_aekl_num_params": (C.c_int, [_P]),
+    "eegldm_aekl_param_info": (C.c_int, [_P, C.c_int, C.POINTER(C.c_char_p), _I64P, C.POINTER(C.c_int)]),
+    "eegldm_aekl_load": (C.c_int, [_P, C.c_char_p, _P, _I64P, C.c_int]),
+    "eegldm_aekl_finalize": (C.c_int, [_P]),
+    "eegldm_aekl_encode": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, _P]),
+    "eegldm_aekl_decode": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P]),
+    "eegldm_aekl_forward": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, _P]),
+    "eegldm_sched_alphas_cumprod": (C.c_int, [C.POINTER(SchedCfg), _FP]),
+    "eegldm_sched_ddim_tables": (C.c_int, [C.POINTER(SchedCfg), C.c_int, _I64P, _FP]),
+    "eegldm_timestep_embedding": (C.c_int, [_FP, C.c_int, C.c_int, _FP]),
+    "eegldm_ddim_sample": (C.c_int, [_P, _P, C.POINTER(SchedCfg), _P, C.c_float, C.c_int, _P, C.c_int, C.c_int, _P]),
+    "eegldm_ddim_sample_host": (C.c_int, [_P, _P, C.POINTER(SchedCfg), _P, C.c_float, C.c_int, _P, C.c_int, C.c_int, _P]),
+}
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load libeegldm.so (once) and bind every symbol; raises if the library is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} not found: the CUDA library has not been built. Run "
+                f"`python {os.path.join(os.path.dirname(_HERE), 'build.py')}` (needs nvcc). "
+                "eegldm has no CPU fallback.")
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)  # AttributeError if the .so is stale
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(code: int) -> None:
+    if code != 0:
+        raise EegldmError(code, lib().eegldm_last_error().decode("utf-8", "replace"))
+
+
+def current_stream_ptr(device) -> int:
+    import torch
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def load_state_dict_into(handle, load_fn, state_dict) -> None:
+    """One C-ABI load call per entry (host fp32, contiguous, reference [Cout,Cin,k] layout)."""
+    import torch
+    for name, t in state_dict.items():
+        ht = t.detach().to(device="cpu", dtype=torch.float32).contiguous()
+        shape = (C.c_int64 * max(ht.dim(), 1))(*ht.shape)
+        check(load_fn(handle, name.encode(), C.c_void_p(ht.data_ptr()), shape, ht.dim()))
+
+
+def param_infos(handle, num_fn, info_fn):
+    out = []
+    for i in range(num_fn(handle)):
+        name = C.c_char_p()
+        shape = (C.c_int64 * 4)()
+        nd = C.c_int()
+        check(info_fn(handle, i, C.byref(name), shape, C.byref(nd)))
+        out.append((name.value.decode(), tuple(int(shape[k]) for k in range(nd.value))))
+    return out

@@ -1,0 +1,122 @@
+"""Drop-in for ``generative.networks.nets.AutoencoderKL`` (monai-generative) as the reference builds
+it (``src/train_autoencoderkl.py:129-133``, ``src/sample_trials.py:95-100``, ``config/config_aekl_eeg*.yaml``):
+1-D, GroupNorm(norm_num_groups) + SiLU ResBlocks, no attention.  Same ``state_dict`` keys (MONAI's
+``Convolution(conv_only=True)`` naming) and the same method surface.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._module import EngineModule, check_cuda_f32, default_init, register_tree
+
+
+class AutoencoderKL(EngineModule):
+    def __init__(self, spatial_dims=1, in_channels=1, out_channels=1, num_res_blocks=(2, 2, 2, 2),
+                 num_channels=(32, 64, 64, 64), attention_levels=(False, False, True, True), latent_channels=3,
+                 norm_num_groups=32, norm_eps=1e-6, with_encoder_nonlocal_attn=True, with_decoder_nonlocal_attn=True,
+                 use_flash_attention=False):
+        super().__init__()
+        if spatial_dims != 1:
+            raise NotImplementedError("the reference's EEG autoencoder is 1-D (config_aekl_eeg.yaml:20)")
+        num_channels = list(num_channels)
+        if isinstance(num_res_blocks, int):
+            num_res_blocks = [num_res_blocks] * len(num_channels)
+        num_res_blocks = list(num_res_blocks)
+        attention_levels = list(attention_levels)[:len(num_channels)]
+        if any(attention_levels) or with_encoder_nonlocal_attn or with_decoder_nonlocal_attn:
+            raise NotImplementedError("attention is off in every reference autoencoder config "
+                                      "(config_aekl_eeg.yaml:26-28); pass attention_levels=[False,...], "
+                                      "with_encoder_nonlocal_attn=False, with_decoder_nonlocal_attn=False")
+        if abs(norm_eps - 1e-6) > 0:
+            raise NotImplementedError("norm_eps is fixed at 1e-6")
+        if len(num_res_blocks) != len(num_channels) or len(num_channels) > 8:
+            raise ValueError("num_res_blocks / num_channels length mismatch")
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.num_channels, self.latent_channels = num_channels, latent_channels
+        cfg = _lib.AeklCfg()
+        cfg.in_channels, cfg.out_channels, cfg.n_levels = int(in_channels), int(out_channels), len(num_channels)
+        for i, (c, r) in enumerate(zip(num_channels, num_res_blocks)):
+            cfg.num_channels[i], cfg.num_res_blocks[i] = int(c), int(r)
+        cfg.latent_channels, cfg.norm_num_groups = int(latent_channels), int(norm_num_groups)
+        self._cfg = cfg
+        self._factor = 1 << (len(num_channels) - 1)
+        L = _lib.lib()
+        h = C.c_void_p()
+        _lib.check(L.eegldm_aekl_create(C.byref(cfg), C.byref(h)))
+        self._h = h
+        infos = _lib.param_infos(h, L.eegldm_aekl_num_params, L.eegldm_aekl_param_info)
+        shapes = dict(infos)
+
+        def init(name, shape):
+            return default_init(name, shape, shapes[name.rsplit(".", 1)[0] + ".weight"])
+
+        register_tree(self, infos, init)
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            try:
+                _lib.lib().eegldm_aekl_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    def _upload(self, state_dict) -> None:
+        L = _lib.lib()
+        _lib.load_state_dict_into(self._h, L.eegldm_aekl_load, state_dict)
+        _lib.check(L.eegldm_aekl_finalize(self._h))
+
+    # --- reference method surface ---------------------------------------------------------------
+    @torch.no_grad()
+    def encode(self, x):
+        """-> (z_mu, z_sigma)"""
+        x = check_cuda_f32(x, "x")
+        B, Cin, Lx = x.shape
+        if Cin != self.in_channels:
+            raise ValueError("channel mismatch")
+        T = Lx // self._factor
+        z_mu = torch.empty((B, self.latent_channels, T), device=x.device, dtype=torch.float32)
+        z_sigma = torch.empty_like(z_mu)
+        with torch.cuda.device(x.device):
+            self._sync_weights()
+            _lib.check(_lib.lib().eegldm_aekl_encode(
+                self._h, C.c_void_p(x.data_ptr()), C.c_void_p(z_mu.data_ptr()), C.c_void_p(z_sigma.data_ptr()),
+                int(B), int(Lx), C.c_void_p(_lib.current_stream_ptr(x.device))))
+        return z_mu, z_sigma
+
+    def sampling(self, z_mu, z_sigma):
+        eps = torch.randn_like(z_sigma)
+        return z_mu + eps * z_sigma
+
+    @torch.no_grad()
+    def decode(self, z):
+        z = check_cuda_f32(z, "z")
+        B, Cz, T = z.shape
+        if Cz != self.latent_channels:
+            raise ValueError("channel mismatch")
+        out = torch.empty((B, self.out_channels, T * self._factor), device=z.device, dtype=torch.float32)
+        with torch.cuda.device(z.device):
+            self._sync_weights()
+            _lib.check(_lib.lib().eegldm_aekl_decode(
+                self._h, C.c_void_p(z.data_ptr()), C.c_void_p(out.data_ptr()), int(B), int(T),
+                C.c_void_p(_lib.current_stream_ptr(z.device))))
+        return out
+
+    def reconstruct(self, x):
+        z_mu, _ = self.encode(x)
+        return self.decode(z_mu)
+
+    def forward(self, x):
+        z_mu, z_sigma = self.encode(x)
+        z = self.sampling(z_mu, z_sigma)
+        return self.decode(z), z_mu, z_sigma
+
+    def encode_stage_2_inputs(self, x):
+        z_mu, z_sigma = self.encode(x)
+        return self.sampling(z_mu, z_sigma)
+
+    def decode_stage_2_outputs(self, z):
+        return self.decode(z)

@@ -1,0 +1,117 @@
+"""Drop-in for the reference denoiser ``UNetModel`` (``/root/reference/src/models/unet.py:330-563``).
+
+Same constructor keywords (``unet.py:331-351``), same ``state_dict`` keys, same
+``forward(x, timesteps=None, context=None, y=None, **kwargs)`` contract (``unet.py:512``); the
+computation is ``eegldm_unet_forward`` in ``libeegldm.so``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._module import EngineModule, check_cuda_f32, default_init, register_tree
+
+
+def _zero_init(name: str) -> bool:
+    """Tensors the reference wraps in ``zero_module`` (unet.py:161,290-292,504)."""
+    return (".out_layers.3." in name) or (".proj_out." in name) or name.startswith("out.2.")
+
+
+class UNetModel(EngineModule):
+    def __init__(self, image_size, in_channels, model_channels, out_channels, num_res_blocks, attention_resolutions,
+                 dropout=0, channel_mult=(1, 2, 4, 8), conv_resample=True, num_classes=None, num_heads=1,
+                 num_head_channels=-1, num_heads_upsample=-1, use_scale_shift_norm=False, resblock_updown=False,
+                 n_embed=None, math="fp32"):
+        super().__init__()
+        if num_classes is not None or n_embed is not None:
+            raise NotImplementedError("class-conditional / codebook heads are not on the reference's live path")
+        if use_scale_shift_norm:
+            raise NotImplementedError("use_scale_shift_norm=True is not used by any reference config")
+        self.image_size = image_size
+        self.in_channels = in_channels
+        self.model_channels = model_channels
+        self.out_channels = out_channels
+        self.num_res_blocks = num_res_blocks
+        self.attention_resolutions = list(attention_resolutions)
+        self.dropout = dropout  # Dropout is the identity in eval mode; this engine is inference-only
+        self.channel_mult = tuple(channel_mult)
+        self.conv_resample = conv_resample
+        self.num_classes = None
+        self.num_heads = num_heads
+        self.num_head_channels = num_head_channels
+        self.num_heads_upsample = num_heads_upsample
+        self.predict_codebook_ids = False
+
+        cfg = _lib.UNetCfg()
+        cfg.image_size = int(image_size)
+        cfg.in_channels, cfg.model_channels, cfg.out_channels = int(in_channels), int(model_channels), int(out_channels)
+        cfg.num_res_blocks = int(num_res_blocks)
+        if len(self.attention_resolutions) > 8 or len(self.channel_mult) > 8:
+            raise ValueError("at most 8 attention_resolutions / channel_mult entries")
+        cfg.n_attention_resolutions = len(self.attention_resolutions)
+        for i, v in enumerate(self.attention_resolutions):
+            cfg.attention_resolutions[i] = int(v)
+        cfg.n_channel_mult = len(self.channel_mult)
+        for i, v in enumerate(self.channel_mult):
+            cfg.channel_mult[i] = int(v)
+        cfg.num_heads, cfg.num_head_channels = int(num_heads), int(num_head_channels)
+        cfg.num_heads_upsample = int(num_heads_upsample)
+        cfg.resblock_updown, cfg.conv_resample = int(bool(resblock_updown)), int(bool(conv_resample))
+        cfg.use_scale_shift_norm = 0
+        self._cfg = cfg
+        L = _lib.lib()
+        h = C.c_void_p()
+        _lib.check(L.eegldm_unet_create(C.byref(cfg), C.byref(h)))
+        self._h = h
+        infos = _lib.param_infos(h, L.eegldm_unet_num_params, L.eegldm_unet_param_info)
+        shapes = dict(infos)
+
+        def init(name, shape):
+            wname = name.rsplit(".", 1)[0] + ".weight"
+            return default_init(name, shape, shapes[wname], zero=_zero_init(name))
+
+        register_tree(self, infos, init)
+        self._math = "fp32"
+        self.set_math(math)
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            try:
+                _lib.lib().eegldm_unet_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    def set_math(self, mode: str) -> "UNetModel":
+        """``"fp32"`` (SIMT, exact fp32), ``"bf16x3"`` (tcgen05, split-bf16, fp32-accurate to ~2^-16),
+        ``"bf16"`` (tcgen05, fast; does NOT meet the fp32 parity tolerance)."""
+        _lib.check(_lib.lib().eegldm_unet_set_math(self._h, _lib.MATH_MODES[mode]))
+        self._math = mode
+        return self
+
+    def _upload(self, state_dict) -> None:
+        L = _lib.lib()
+        _lib.load_state_dict_into(self._h, L.eegldm_unet_load, state_dict)
+        _lib.check(L.eegldm_unet_finalize(self._h))
+
+    @torch.no_grad()
+    def forward(self, x, timesteps=None, context=None, y=None, **kwargs):
+        assert y is None, "must specify y if and only if the model is class-conditional"   # unet.py:521-523
+        assert timesteps is not None, "need to implement no-timestep usage"               # unet.py:524
+        x = check_cuda_f32(x, "x")
+        if x.dim() != 3 or x.shape[1] != self.in_channels:
+            raise ValueError(f"x must be [B, {self.in_channels}, T], got {tuple(x.shape)}")
+        B, _, T = x.shape
+        ts = torch.as_tensor(timesteps).reshape(-1).to(device="cpu", dtype=torch.float32).contiguous()  # .float(): unet.py:28
+        if ts.numel() not in (1, B):
+            raise ValueError("timesteps must have 1 or B entries")
+        out = torch.empty((B, self.out_channels, T), device=x.device, dtype=torch.float32)
+        with torch.cuda.device(x.device):
+            self._sync_weights()
+            _lib.check(_lib.lib().eegldm_unet_forward(
+                self._h, C.c_void_p(x.data_ptr()), C.cast(C.c_void_p(ts.data_ptr()), C.POINTER(C.c_float)), int(ts.numel()),
+                C.c_void_p(out.data_ptr()), int(B), int(T), C.c_void_p(_lib.current_stream_ptr(x.device))))
+        return out
