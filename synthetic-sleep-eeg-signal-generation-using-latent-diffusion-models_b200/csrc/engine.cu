@@ -292,12 +292,14 @@ struct eegldm_unet {
     float* coef_table = nullptr; size_t coef_table_cap = 0;  // ddim: [n_steps][2]
     float* coef_cur = nullptr;                             // [2]
     int* step_ctr = nullptr;
+    cudaStream_t cap_stream = nullptr;                     // private stream used only for graph capture
     float* xbuf = nullptr; size_t xbuf_cap = 0;            // ddim state [B][T][z]
     float* xtmp = nullptr; size_t xtmp_cap = 0;            // NCL<->NLC staging
     std::vector<float> table_key;                          // identifies the cached temb/coef tables
     std::map<std::pair<int, int>, GraphEntry> graphs;      // (B,T) -> one denoise step
     ~eegldm_unet() {
         drop_graphs();
+        if (cap_stream) cudaStreamDestroy(cap_stream);
         for (void* p : {(void*)arena, (void*)temb_fwd, (void*)tscratch, (void*)temb_step, (void*)temb_table,
                         (void*)coef_table, (void*)coef_cur, (void*)step_ctr, (void*)xbuf, (void*)xtmp})
             if (p) cudaFree(p);
@@ -1133,10 +1135,11 @@ int eegldm_unet_set_math(eegldm_unet* h, eegldm_math mode) {
 
 int eegldm_unet_forward(eegldm_unet* h, const float* x_dev, const float* timesteps_host, int nt, float* out_dev, int B,
                         int T, void* stream) {
-    if (!h || !x_dev || !timesteps_host || !out_dev) return fail(EEGLDM_ERR_INVALID, "null argument");
+    if (!h) return fail(EEGLDM_ERR_INVALID, "null handle");
     if (!h->finalized) return fail(EEGLDM_ERR_MISSING, "eegldm_unet_finalize has not been called");
     if (B < 0 || (nt != 1 && nt != B)) return fail(EEGLDM_ERR_SHAPE, "timesteps must have 1 or B entries");
-    if (B == 0) return EEGLDM_OK;
+    if (B == 0) return EEGLDM_OK;  // empty batch: nothing to do (pointers may be null)
+    if (!x_dev || !timesteps_host || !out_dev) return fail(EEGLDM_ERR_INVALID, "null argument");
     cudaStream_t st = (cudaStream_t)stream;
     const int zin = h->cfg.in_channels, zout = h->cfg.out_channels;
     int r = ensure(h->temb_fwd, h->temb_fwd_cap, (size_t)nt * h->emb_total);
@@ -1192,11 +1195,12 @@ int eegldm_aekl_finalize(eegldm_aekl* h) {
 }
 
 int eegldm_aekl_encode(eegldm_aekl* h, const float* x_dev, float* z_mu_dev, float* z_sigma_dev, int B, int L, void* stream) {
-    if (!h || !x_dev || !z_mu_dev || !z_sigma_dev) return fail(EEGLDM_ERR_INVALID, "null argument");
+    if (!h) return fail(EEGLDM_ERR_INVALID, "null handle");
     if (!h->finalized) return fail(EEGLDM_ERR_MISSING, "eegldm_aekl_finalize has not been called");
     const int f = h->down_factor();
     if (B < 0 || L <= 0 || L % f) return fail(EEGLDM_ERR_SHAPE, "L must be a positive multiple of 2^(levels-1)");
     if (B == 0) return EEGLDM_OK;
+    if (!x_dev || !z_mu_dev || !z_sigma_dev) return fail(EEGLDM_ERR_INVALID, "null argument");
     cudaStream_t st = (cudaStream_t)stream;
     const int cin = h->cfg.in_channels, z = h->cfg.latent_channels, T = L / f;
     const size_t nin = (size_t)B * L * cin, nz = (size_t)B * T * z;
@@ -1220,10 +1224,11 @@ int eegldm_aekl_encode(eegldm_aekl* h, const float* x_dev, float* z_mu_dev, floa
 }
 
 int eegldm_aekl_decode(eegldm_aekl* h, const float* z_dev, float* out_dev, int B, int T, void* stream) {
-    if (!h || !z_dev || !out_dev) return fail(EEGLDM_ERR_INVALID, "null argument");
+    if (!h) return fail(EEGLDM_ERR_INVALID, "null handle");
     if (!h->finalized) return fail(EEGLDM_ERR_MISSING, "eegldm_aekl_finalize has not been called");
     if (B < 0 || T <= 0) return fail(EEGLDM_ERR_SHAPE, "bad latent shape");
     if (B == 0) return EEGLDM_OK;
+    if (!z_dev || !out_dev) return fail(EEGLDM_ERR_INVALID, "null argument");
     cudaStream_t st = (cudaStream_t)stream;
     const int z = h->cfg.latent_channels, co = h->cfg.out_channels, L = T * h->down_factor();
     const size_t nz = (size_t)B * T * z, nout = (size_t)B * L * co;
@@ -1286,7 +1291,8 @@ int eegldm_timestep_embedding(const float* timesteps, int nt, int dim, float* ou
 // ---------------------------------------------------------------------------------------------- sampling
 int eegldm_ddim_sample(eegldm_unet* u, eegldm_aekl* a, const eegldm_sched_cfg* sc, const float* noise_dev, float scale_factor,
                        int n_steps, float* out_dev, int B, int T, void* stream) {
-    if (!u || !sc || !noise_dev || !out_dev) return fail(EEGLDM_ERR_INVALID, "null argument");
+    if (!u || !sc) return fail(EEGLDM_ERR_INVALID, "null argument");
+    if (B > 0 && (!noise_dev || !out_dev)) return fail(EEGLDM_ERR_INVALID, "null argument");
     if (!u->finalized) return fail(EEGLDM_ERR_MISSING, "eegldm_unet_finalize has not been called");
     if (a && !a->finalized) return fail(EEGLDM_ERR_MISSING, "eegldm_aekl_finalize has not been called");
     if (u->cfg.in_channels != u->cfg.out_channels) return fail(EEGLDM_ERR_INVALID, "sampling needs in_channels == out_channels");
@@ -1343,9 +1349,11 @@ int eegldm_ddim_sample(eegldm_unet* u, eegldm_aekl* a, const eegldm_sched_cfg* s
             if (r) return r;
             GraphEntry ge;
             const long long before = g_launch_count.load();
-            CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-            r = emit_step(bd, st);
-            cudaError_t e = cudaStreamEndCapture(st, &ge.graph);
+            // capture on a private stream: the caller's stream may be the legacy default stream, which cannot capture
+            if (!u->cap_stream) CU(cudaStreamCreateWithFlags(&u->cap_stream, cudaStreamNonBlocking));
+            CU(cudaStreamBeginCapture(u->cap_stream, cudaStreamCaptureModeThreadLocal));
+            r = emit_step(bd, u->cap_stream);
+            cudaError_t e = cudaStreamEndCapture(u->cap_stream, &ge.graph);
             if (r) { if (ge.graph) cudaGraphDestroy(ge.graph); return r; }
             if (e != cudaSuccess) return cuda_fail(e, "cudaStreamEndCapture");
             ge.n_kernels = (int)(g_launch_count.load() - before);

@@ -85,6 +85,7 @@ def test_load_errors(built_lib):
     # forward before finalize -> EEGLDM_ERR_MISSING, never a crash
     one = (C.c_float * 1)(5.0)
     assert built_lib.eegldm_unet_forward(m._h, C.c_void_p(16), one, 1, C.c_void_p(16), 1, 32, None) == -3
+    assert built_lib.eegldm_unet_forward(None, C.c_void_p(16), one, 1, C.c_void_p(16), 1, 32, None) == -1
     # DataParallel "module." prefix is accepted (testing/MSSIM_reconstruction.py:66-69)
     w = np.zeros((128, 32), dtype=np.float32)
     shape = (C.c_int64 * 2)(128, 32)

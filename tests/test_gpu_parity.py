@@ -7,7 +7,7 @@ import pytest
 import torch
 
 from conftest import GOLDEN
-from golden.make_golden import CASES
+from golden.cases import CASES
 from oracle import aekl as oa
 from oracle import sample as osamp
 from oracle import unet as ou

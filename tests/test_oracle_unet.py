@@ -10,7 +10,7 @@ import torch
 
 from conftest import GOLDEN, REFERENCE
 from oracle import unet as ou
-from golden.make_golden import CASES  # noqa: F401  (tests/ is on sys.path via rootdir conftest)
+from golden.cases import CASES
 
 
 def _golden():
