@@ -166,6 +166,15 @@ int eegldm_ddim_sample_host(eegldm_unet* unet, eegldm_aekl* aekl, const eegldm_s
 /* disable (0) / enable (1) CUDA-graph replay inside eegldm_ddim_sample (default 1) */
 int eegldm_set_graphs(int enabled);
 
+/* ------------------------------------------------------------------------------------------------
+ * Test hook (not part of the drop-in surface): ONE fused convolution launch
+ *   out[B][Tc][Cout] = bias + res + Conv1d_k( resample( silu?( scale*x + shift ) ) ),  x [B][Tin][Cin] channels-last,
+ * w_host in the reference's [Cout][Cin][k] layout, in the requested math mode.  Lets the tests compare the
+ * tcgen05 kernel with the fp32 SIMT kernel and torch's conv1d one layer at a time.  Synchronises the stream. */
+int eegldm_test_conv(const float* x_dev, const float* scale_dev, const float* shift_dev, int silu, int resample,
+                     const float* w_host, const float* bias_host, const float* res_dev, int B, int Tin, int Cin, int Cout, int k,
+                     int math, float* out_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

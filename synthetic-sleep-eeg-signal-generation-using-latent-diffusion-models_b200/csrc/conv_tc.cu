@@ -1,0 +1,411 @@
+// tcgen05 implicit-GEMM convolution for sm_100a (the tensor-pipe path of the eegldm engine).
+//
+// Computes, for channels-last activations,
+//     out[b,t,co] = bias[co] + temb[b,co] + res[b,t,co] + sum_seg sum_{k,ci} W_seg[co,ci,k] * u_seg[b, t+k-pad, ci]
+//     u = resample(silu?(scale*x + shift))           (GroupNorm apply + SiLU + AvgPool/nearest folded into the operand load)
+// i.e. the same contract as conv_simt_kernel (reference: src/models/unet.py:263,291,302,158,161 + 308-327),
+// as a GEMM with M = 128 output positions, N = 128 output channels, K = taps*Cin per CTA:
+//
+//   * D (fp32) lives in TMEM (128 lanes x 128 columns); tcgen05.mma.cta_group::1.kind::f16, M=128 N=128 K=16.
+//   * fp32 parity on a bf16 tensor pipe: every fp32 operand is split x = hi + lo (two bf16) and three products
+//     are accumulated, hi*hi + hi*lo + lo*hi ("bf16x3", ~2^-16 relative operand error).  EEGLDM_MATH_BF16_TC
+//     issues only hi*hi.
+//   * B operand = weights, pre-split and pre-packed on the host into the exact shared-memory image of one
+//     pipeline stage (K-major, no swizzle, 8x16-byte core matrices) so a stage is ONE cp.async.bulk (UBLKCP).
+//   * A operand = activations, produced by 4 warps: coalesced fp32 loads -> affine/SiLU/resample -> bf16 hi/lo
+//     -> st.shared in a "phase-strided halo" K-major layout: the 128 M rows are 8 segments of 16 consecutive
+//     positions; rows of one 8-row core matrix are the SAME offset in the 8 segments, and each segment carries
+//     its own 2 halo positions (18 slots).  A tap shift of +-1 position is then a whole-core-matrix shift
+//     = +-SBO bytes on the descriptor start address, so the 3 taps of a k=3 conv read ONE staged tile
+//     (12.5 % halo overhead instead of 3 copies).  Segments may belong to different samples / be zero padded.
+//   * warp roles: 0-3 A producers then epilogue (TMEM -> registers -> global), 4 weight loader, 5 MMA issuer.
+//     ~101 KB smem + 128 TMEM columns per CTA -> 2 CTAs per SM, so one CTA's epilogue overlaps the other's mainloop.
+#include <cuda_bf16.h>
+
+#include <cstring>
+#include <vector>
+
+#include "kernels.cuh"
+
+namespace eegldm {
+namespace {
+
+constexpr int BM = 128;            // output positions per CTA (8 segments x 16)
+constexpr int BN = TC_BN;          // output channels per CTA
+constexpr int BK = TC_BK;          // input channels per k-step
+constexpr int SLOTS = 18;          // 16 positions + 2 halo slots per segment
+constexpr int A_SBO = 128;         // bytes between core matrices along M (between slots)
+constexpr int A_LBO = SLOTS * A_SBO;   // bytes between core matrices along K (8-channel chunks)
+constexpr int A_TILE = (BK / 8) * A_LBO;   // one hi (or lo) activation tile
+constexpr int A_STAGE = 2 * A_TILE;
+constexpr int B_SBO = 128;
+constexpr int B_LBO = (BN / 8) * B_SBO;    // 2048
+constexpr int B_HALF = (BK / 8) * B_LBO;   // 8192: hi (or lo) weight tile of one (tap, k-step)
+constexpr int B_STAGE = 2 * B_HALF;
+static_assert(B_HALF == TC_W_HALF_BYTES, "host packing and kernel disagree");
+constexpr int NA = 2;              // activation ring
+constexpr int NB = 4;              // weight ring
+constexpr int N_ITEMS = 8 * SLOTS * (BK / 8);   // 576 16-byte items per activation tile
+constexpr int ITEMS_PER_THREAD = (N_ITEMS + 127) / 128;
+constexpr int SMEM_BYTES = NA * A_STAGE + NB * B_STAGE + 256;
+constexpr int NUM_THREADS = 192;
+
+// ---------------------------------------------------------------------------------------------- PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1 = sm_100)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
+           (1ull << 46);
+}
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N=128, M=128 (cute::UMMA::InstrDescriptor)
+constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+__device__ __forceinline__ float silu_fast(float v) { return __fdividef(v, 1.f + __expf(-v)); }
+__device__ __forceinline__ float act(float x, float a, float s, int silu) {
+    const float v = fmaf(a, x, s);
+    return silu ? silu_fast(v) : v;
+}
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// fp32 x8 -> bf16 hi x8 (uint4) and bf16 lo x8 (uint4), element e at the lower address
+__device__ __forceinline__ void split8(const float (&v)[8], uint4& hi, uint4& lo) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        __nv_bfloat162 hb = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        h[i] = *reinterpret_cast<uint32_t*>(&hb);
+        const float r0 = v[2 * i] - __uint_as_float(h[i] << 16);
+        const float r1 = v[2 * i + 1] - __uint_as_float(h[i] & 0xFFFF0000u);
+        __nv_bfloat162 lb = __floats2bfloat162_rn(r0, r1);
+        l[i] = *reinterpret_cast<uint32_t*>(&lb);
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+struct Item {      // one 16-byte (8-channel) slot of the activation tile, fixed for the whole K loop
+    int b, t;      // sample / conv-input position (valid only if inb)
+    uint32_t soff; // byte offset inside a hi tile
+    bool live, inb;
+};
+
+template <bool X3>
+__global__ void __launch_bounds__(NUM_THREADS, 2) conv_tc_kernel(const TcConvParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t sA = sbase, sB = sbase + NA * A_STAGE;
+    const uint32_t bars = sB + NB * B_STAGE;           // 8-byte mbarriers
+    const uint32_t barAfull = bars, barAempty = bars + 8 * NA, barBfull = bars + 16 * NA, barBempty = barBfull + 8 * NB,
+                   barAcc = barBempty + 8 * NB;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + NA * A_STAGE + NB * B_STAGE + 16 * NA + 16 * NB + 8);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n_tile = blockIdx.x, m_tile = blockIdx.y;
+    const int nks0 = p.seg[0].nks, nks = nks0 + (p.nseg > 1 ? p.seg[1].nks : 0);
+    const int spt = p.Tout >> 4;   // 16-position segments per sample
+
+    if (tid == 0) {
+        for (int i = 0; i < NA; ++i) { mbar_init(barAfull + 8 * i, 128); mbar_init(barAempty + 8 * i, 1); }
+        for (int i = 0; i < NB; ++i) { mbar_init(barBfull + 8 * i, 1); mbar_init(barBempty + 8 * i, 1); }
+        mbar_init(barAcc, 1);
+        fence_mbar_init();
+    }
+    if (warp == 5) tmem_alloc(smem_u32(tmem_slot), BN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp < 4) {
+        // ================================================================ A producers
+        const int c = tid & 3;   // 8-channel chunk inside the k-step
+        Item items[ITEMS_PER_THREAD];
+#pragma unroll
+        for (int j = 0; j < ITEMS_PER_THREAD; ++j) {
+            const int idx = tid + 128 * j;
+            Item it{};
+            it.live = idx < N_ITEMS;
+            const int rq = idx >> 2, q = rq % SLOTS, r = rq / SLOTS;
+            const int g = m_tile * 8 + r;
+            const bool segv = g < p.nsegs16;
+            it.b = segv ? g / spt : 0;
+            it.t = (g % spt) * 16 + q - 1;
+            it.inb = it.live && segv && it.t >= 0 && it.t < p.Tout;
+            it.soff = (uint32_t)(c * A_LBO + q * A_SBO + r * 16);
+            items[j] = it;
+        }
+        for (int ks = 0; ks < nks; ++ks) {
+            const int sa = ks % NA;
+            const TcSeg& sg = ks < nks0 ? p.seg[0] : p.seg[1];
+            const int cc = (ks < nks0 ? ks : ks - nks0) * BK + c * 8;   // channel inside the (virtual) concat
+            const float* src; int ch, Cs;
+            if (cc < sg.C0) { src = sg.src0; ch = cc; Cs = sg.C0; } else { src = sg.src1; ch = cc - sg.C0; Cs = sg.C1; }
+            const int Cin = sg.C0 + sg.C1;
+            float vals[ITEMS_PER_THREAD][8];
+#pragma unroll
+            for (int j = 0; j < ITEMS_PER_THREAD; ++j) {
+                const Item& it = items[j];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) vals[j][e] = 0.f;
+                if (!it.inb) continue;
+                float a[8], s[8];
+                if (sg.scale) {
+                    const float4 a0 = ldg4(sg.scale + (size_t)it.b * Cin + cc), a1 = ldg4(sg.scale + (size_t)it.b * Cin + cc + 4);
+                    const float4 s0 = ldg4(sg.shift + (size_t)it.b * Cin + cc), s1 = ldg4(sg.shift + (size_t)it.b * Cin + cc + 4);
+                    a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+                    s[0] = s0.x; s[1] = s0.y; s[2] = s0.z; s[3] = s0.w; s[4] = s1.x; s[5] = s1.y; s[6] = s1.z; s[7] = s1.w;
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) { a[e] = 1.f; s[e] = 0.f; }
+                }
+                const float* base = src + (size_t)it.b * sg.Tin * Cs + ch;
+                if (sg.resample == RS_AVGPOOL2) {
+                    const float* r0 = base + (size_t)(2 * it.t) * Cs;
+                    const float4 x0 = ldg4(r0), x1 = ldg4(r0 + 4), y0 = ldg4(r0 + Cs), y1 = ldg4(r0 + Cs + 4);
+                    const float xa[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+                    const float ya[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) vals[j][e] = 0.5f * (act(xa[e], a[e], s[e], sg.silu) + act(ya[e], a[e], s[e], sg.silu));
+                } else {
+                    const int tt = sg.resample == RS_NEAREST2 ? (it.t >> 1) : it.t;
+                    const float* r0 = base + (size_t)tt * Cs;
+                    const float4 x0 = ldg4(r0), x1 = ldg4(r0 + 4);
+                    const float xa[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) vals[j][e] = act(xa[e], a[e], s[e], sg.silu);
+                }
+            }
+            mbar_wait(barAempty + 8 * sa, ((ks / NA) & 1) ^ 1);
+            uint8_t* tile = smem + sa * A_STAGE;
+#pragma unroll
+            for (int j = 0; j < ITEMS_PER_THREAD; ++j) {
+                if (!items[j].live) continue;
+                uint4 hi, lo;
+                split8(vals[j], hi, lo);
+                *reinterpret_cast<uint4*>(tile + items[j].soff) = hi;
+                if (X3) *reinterpret_cast<uint4*>(tile + A_TILE + items[j].soff) = lo;
+            }
+            fence_proxy_async_smem();
+            mbar_arrive(barAfull + 8 * sa);
+        }
+        // ================================================================ epilogue
+        mbar_wait(barAcc, 0);
+        tc_fence_after();
+        const int row = warp * 32 + lane;          // TMEM lane = M row
+        const int r = row & 7, m = row >> 3;       // segment / offset inside the segment
+        const int g = m_tile * 8 + r;
+        const bool rowv = g < p.nsegs16;
+        const int b = rowv ? g / spt : 0;
+        const int t = (g % spt) * 16 + m;
+        const int co0 = n_tile * BN;
+        float* orow = p.out + ((size_t)b * p.Tout + t) * p.Cout + co0;
+        const float* tb = p.temb ? p.temb + (size_t)b * p.temb_stride + co0 : nullptr;
+        const float* bs = p.bias ? p.bias + co0 : nullptr;
+        const float *res0 = nullptr, *res1 = nullptr;
+        if (p.res) {
+            const float* rb = p.res + (size_t)b * p.res_Tin * p.Cout + co0;
+            if (p.res_mode == RS_AVGPOOL2) { res0 = rb + (size_t)(2 * t) * p.Cout; res1 = res0 + p.Cout; }
+            else res0 = rb + (size_t)(p.res_mode == RS_NEAREST2 ? (t >> 1) : t) * p.Cout;
+        }
+#pragma unroll 1
+        for (int cb = 0; cb < BN; cb += 32) {
+            uint32_t v[32];
+            tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)cb, v);   // warp-collective: no divergence before this
+            if (!rowv) continue;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                float4 o = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                                       __uint_as_float(v[4 * q + 3]));
+                const int co = cb + 4 * q;
+                if (bs) { const float4 x = ldg4(bs + co); o.x += x.x; o.y += x.y; o.z += x.z; o.w += x.w; }
+                if (tb) { const float4 x = ldg4(tb + co); o.x += x.x; o.y += x.y; o.z += x.z; o.w += x.w; }
+                if (res0) {
+                    float4 x = ldg4(res0 + co);
+                    if (res1) { const float4 y = ldg4(res1 + co); x.x = 0.5f * (x.x + y.x); x.y = 0.5f * (x.y + y.y); x.z = 0.5f * (x.z + y.z); x.w = 0.5f * (x.w + y.w); }
+                    o.x += x.x; o.y += x.y; o.z += x.z; o.w += x.w;
+                }
+                *reinterpret_cast<float4*>(orow + co) = o;
+            }
+        }
+    } else if (warp == 4) {
+        // ================================================================ weight loader (one thread, bulk async copies)
+        if (lane == 0) {
+            const uint32_t bytes = X3 ? B_STAGE : B_HALF;
+            int it = 0;
+            for (int ks = 0; ks < nks; ++ks) {
+                const bool first = ks < nks0;
+                const TcSeg& sg = first ? p.seg[0] : p.seg[1];
+                const int kl = first ? ks : ks - nks0;
+                const uint8_t* wsrc = sg.w + ((size_t)n_tile * sg.nks + kl) * sg.taps * B_STAGE;
+                for (int tap = 0; tap < sg.taps; ++tap, ++it) {
+                    const int sb = it % NB;
+                    mbar_wait(barBempty + 8 * sb, ((it / NB) & 1) ^ 1);
+                    mbar_arrive_expect_tx(barBfull + 8 * sb, bytes);
+                    bulk_copy_g2s(sB + sb * B_STAGE, wsrc + (size_t)tap * B_STAGE, bytes, barBfull + 8 * sb);
+                }
+            }
+        }
+    } else {
+        // ================================================================ MMA issuer (one thread)
+        if (lane == 0) {
+            int it = 0;
+            uint32_t accum = 0;
+            for (int ks = 0; ks < nks; ++ks) {
+                const int sa = ks % NA;
+                const int taps = ks < nks0 ? p.seg[0].taps : p.seg[1].taps;
+                mbar_wait(barAfull + 8 * sa, (ks / NA) & 1);
+                tc_fence_after();
+                for (int tap = 0; tap < taps; ++tap, ++it) {
+                    const int sb = it % NB;
+                    mbar_wait(barBfull + 8 * sb, (it / NB) & 1);
+                    tc_fence_after();
+                    const int shift = taps == 3 ? tap : 1;   // slot of the first row: position - 1 + tap
+                    const uint32_t a_hi = sA + sa * A_STAGE + shift * A_SBO, a_lo = a_hi + A_TILE;
+                    const uint32_t b_hi = sB + sb * B_STAGE, b_lo = b_hi + B_HALF;
+#pragma unroll
+                    for (int kk = 0; kk < BK / 16; ++kk) {
+                        const uint64_t dah = make_desc(a_hi + kk * 2 * A_LBO, A_LBO, A_SBO);
+                        const uint64_t dbh = make_desc(b_hi + kk * 2 * B_LBO, B_LBO, B_SBO);
+                        umma_bf16(tmem, dah, dbh, IDESC, accum);
+                        accum = 1;
+                        if (X3) {
+                            const uint64_t dal = make_desc(a_lo + kk * 2 * A_LBO, A_LBO, A_SBO);
+                            const uint64_t dbl = make_desc(b_lo + kk * 2 * B_LBO, B_LBO, B_SBO);
+                            umma_bf16(tmem, dah, dbl, IDESC, 1);
+                            umma_bf16(tmem, dal, dbh, IDESC, 1);
+                        }
+                    }
+                    umma_commit(barBempty + 8 * sb);   // weight stage free once these MMAs retire
+                }
+                umma_commit(barAempty + 8 * sa);
+            }
+            umma_commit(barAcc);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) tmem_dealloc(tmem, BN);
+}
+
+uint16_t bf16_rn(float f) {
+    uint32_t u;
+    std::memcpy(&u, &f, 4);
+    if ((u & 0x7F800000u) == 0x7F800000u) return (uint16_t)(u >> 16);   // inf / nan
+    u += 0x7FFFu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+}
+float bf16_to_f(uint16_t h) {
+    uint32_t u = (uint32_t)h << 16;
+    float f;
+    std::memcpy(&f, &u, 4);
+    return f;
+}
+
+}  // namespace
+
+bool conv_tc_eligible(int Cin0, int Cin1, int Cout, int Tout, int taps, int stride) {
+    return stride == 1 && (taps == 1 || taps == 3) && Cin0 > 0 && Cin0 % TC_BK == 0 && Cin1 % TC_BK == 0 && Cout % TC_BN == 0 &&
+           Tout > 0 && Tout % 16 == 0;
+}
+
+// [Cout][Cin][k] fp32 -> per (n_tile, k-step, tap): [hi 8 KB | lo 8 KB], each the shared-memory image
+//   byte(kc, ng, r, e) = kc*2048 + ng*128 + r*16 + e*2   for  co = n_tile*128 + ng*8 + r,  ci = ks*32 + kc*8 + e
+void pack_conv_tc(const float* w, int Cout, int Cin, int k, std::vector<uint16_t>& out) {
+    const int nt = Cout / TC_BN, nks = Cin / TC_BK;
+    out.assign((size_t)nt * nks * k * (2 * TC_W_HALF_BYTES / 2), 0);
+    for (int n = 0; n < nt; ++n)
+        for (int ks = 0; ks < nks; ++ks)
+            for (int tap = 0; tap < k; ++tap) {
+                uint16_t* hi = out.data() + (((size_t)n * nks + ks) * k + tap) * TC_W_HALF_BYTES;   // 2 halves of HALF/2 u16
+                uint16_t* lo = hi + TC_W_HALF_BYTES / 2;
+                for (int kc = 0; kc < TC_BK / 8; ++kc)
+                    for (int ng = 0; ng < TC_BN / 8; ++ng)
+                        for (int r = 0; r < 8; ++r)
+                            for (int e = 0; e < 8; ++e) {
+                                const int co = n * TC_BN + ng * 8 + r, ci = ks * TC_BK + kc * 8 + e;
+                                const float v = w[((size_t)co * Cin + ci) * k + tap];
+                                const uint16_t h = bf16_rn(v);
+                                const size_t o = (size_t)kc * 1024 + ng * 64 + r * 8 + e;
+                                hi[o] = h;
+                                lo[o] = bf16_rn(v - bf16_to_f(h));
+                            }
+            }
+}
+
+cudaError_t launch_conv_tc(const TcConvParams& p, bool x3, cudaStream_t st) {
+    if (p.nsegs16 <= 0) return cudaSuccess;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    dim3 grid(p.Cout / BN, (p.nsegs16 + 7) / 8);
+    if (x3) conv_tc_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(p);
+    else conv_tc_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(p);
+    g_launch_count += 1;
+    return cudaGetLastError();
+}
+
+}  // namespace eegldm

@@ -111,6 +111,13 @@ struct WeightPool {
         return off;
     }
     size_t push(const std::vector<float>& v) { return push(v.data(), v.size()); }
+    size_t push_u16(const std::vector<uint16_t>& v) {   // raw bf16 images (tcgen05 weight tiles), 256-byte aligned
+        const size_t nfl = (v.size() + 1) / 2;
+        size_t off = (stage.size() + 63) & ~size_t(63);
+        stage.resize(off + nfl);
+        std::memcpy(stage.data() + off, v.data(), v.size() * sizeof(uint16_t));
+        return off;
+    }
     int upload() {
         if (dev) { cudaFree(dev); dev = nullptr; }
         if (stage.empty()) return EEGLDM_OK;
@@ -193,6 +200,7 @@ struct Builder {
     std::vector<OpMeta> meta;
     int n_kernels = 0;
     int B = 0;
+    int math = EEGLDM_MATH_FP32_SIMT;
     size_t peak = 0;
     Act act(int C, int T) {
         Act a;
@@ -261,6 +269,10 @@ struct ULayer {
     int emb_off = 0;
     const float *wqkv = nullptr, *bqkv = nullptr, *wproj = nullptr, *bproj = nullptr;
     size_t o_g1, o_be1, o_w1, o_b1, o_g2, o_be2, o_w2, o_b2, o_wskip, o_wqkv, o_bqkv, o_wproj, o_bproj;
+    // tcgen05 weight images (null when the layer's channel counts are not tensor-pipe eligible)
+    const uint8_t *t_w1 = nullptr, *t_w2 = nullptr, *t_wskip = nullptr, *t_wqkv = nullptr, *t_wproj = nullptr;
+    size_t ot_w1 = 0, ot_w2 = 0, ot_wskip = 0, ot_wqkv = 0, ot_wproj = 0;
+    bool h_w1 = false, h_w2 = false, h_wskip = false, h_wqkv = false, h_wproj = false;
 };
 
 struct GraphEntry {
@@ -460,6 +472,32 @@ int finalize_unet(eegldm_unet* h) {
     });
     h->emb_total = (int)embb.size();
     const size_t o_embw = wp.push(embw), o_embb = wp.push(embb);
+    // tcgen05 images: bf16 hi/lo split, packed as shared-memory stage images (conv_tc.cu)
+    auto tc_pack = [&](const std::string& name, int cout, int cin, int k, size_t& off, bool& has) {
+        has = conv_tc_eligible(cin, 0, cout, 16, k, 1);
+        if (!has) return;
+        std::vector<uint16_t> img;
+        pack_conv_tc(ps.get(name).data(), cout, cin, k, img);
+        off = wp.push_u16(img);
+    };
+    for_each_layer(h, [&](ULayer& l) {
+        const std::string& p = l.prefix;
+        switch (l.kind) {
+            case ULayer::RES:
+                tc_pack(p + ".in_layers.2.weight", l.cout, l.cin, 3, l.ot_w1, l.h_w1);
+                tc_pack(p + ".out_layers.3.weight", l.cout, l.cout, 3, l.ot_w2, l.h_w2);
+                if (l.cin != l.cout) tc_pack(p + ".skip_connection.weight", l.cout, l.cin, 1, l.ot_wskip, l.h_wskip);
+                break;
+            case ULayer::ATTN:
+                tc_pack(p + ".qkv.weight", 3 * l.ch, l.ch, 1, l.ot_wqkv, l.h_wqkv);
+                tc_pack(p + ".proj_out.weight", l.ch, l.ch, 1, l.ot_wproj, l.h_wproj);
+                break;
+            case ULayer::UP:
+                if (l.use_conv) tc_pack(p + ".conv.weight", l.ch, l.ch, 3, l.ot_w1, l.h_w1);
+                break;
+            default: break;
+        }
+    });
     for_each_layer(h, [&](ULayer& l) {
         const std::string& p = l.prefix;
         switch (l.kind) {
@@ -506,6 +544,9 @@ int finalize_unet(eegldm_unet* h) {
     h->emb_w = wp.at(o_embw); h->emb_b = wp.at(o_embb);
     h->out_g = wp.at(o_og); h->out_be = wp.at(o_obe); h->out_w = wp.at(o_ow); h->out_b = wp.at(o_ob);
     for_each_layer(h, [&](ULayer& l) {
+        auto tcp = [&](bool has, size_t off) { return has ? reinterpret_cast<const uint8_t*>(wp.at(off)) : nullptr; };
+        l.t_w1 = tcp(l.h_w1, l.ot_w1); l.t_w2 = tcp(l.h_w2, l.ot_w2); l.t_wskip = tcp(l.h_wskip, l.ot_wskip);
+        l.t_wqkv = tcp(l.h_wqkv, l.ot_wqkv); l.t_wproj = tcp(l.h_wproj, l.ot_wproj);
         switch (l.kind) {
             case ULayer::CONV_IN: l.w1 = wp.at(l.o_w1); l.b1 = wp.at(l.o_b1); break;
             case ULayer::RES:
@@ -540,7 +581,7 @@ struct UNetIO {
     const float* ddim_coef;
 };
 
-void plan_conv(Builder& bd, ConvParams p) {
+void plan_conv(Builder& bd, ConvParams p, const uint8_t* tw0 = nullptr, const uint8_t* tw1 = nullptr) {
     p.B = bd.B;
     double flops = 0, bytes = 4.0 * p.B * (double)p.Tout * p.Cout;   // output write
     for (int s = 0; s < p.nseg; ++s) {
@@ -550,6 +591,25 @@ void plan_conv(Builder& bd, ConvParams p) {
         bytes += 4.0 * cin * p.Cout * p.seg[s].taps;                                                     // weights
     }
     if (p.res) bytes += 4.0 * p.B * (double)p.res_Tin * p.Cout;
+    // tensor-pipe path when the math mode asks for it and the shape is eligible; otherwise fp32 SIMT
+    bool tc = bd.math != EEGLDM_MATH_FP32_SIMT && tw0 && (p.nseg == 1 || tw1) && !p.ddim_x && p.stride == 1 && p.Tc == p.Tout &&
+              p.pad_left == p.seg[0].taps / 2 && (p.nseg == 1 || p.seg[1].taps == 1);
+    for (int s = 0; tc && s < p.nseg; ++s)
+        tc = conv_tc_eligible(p.seg[s].C0, p.seg[s].C1, p.Cout, p.Tout, p.seg[s].taps, 1);
+    if (tc) {
+        TcConvParams q{};
+        for (int s = 0; s < p.nseg; ++s) {
+            const ConvSeg& a = p.seg[s];
+            q.seg[s] = TcSeg{a.src0, a.src1, a.C0, a.C1, a.scale, a.shift, a.silu, a.resample, a.Tin, s == 0 ? tw0 : tw1, a.taps,
+                             (a.C0 + a.C1) / TC_BK};
+        }
+        q.nseg = p.nseg; q.Cout = p.Cout; q.Tout = p.Tout; q.nsegs16 = (int)((long long)p.B * p.Tout / 16);
+        q.bias = p.bias; q.temb = p.temb; q.temb_stride = p.temb_stride; q.res = p.res; q.res_mode = p.res_mode; q.res_Tin = p.res_Tin;
+        q.out = p.out;
+        const bool x3 = bd.math == EEGLDM_MATH_BF16X3_TC;
+        bd.add([q, x3](cudaStream_t st) { return launch_conv_tc(q, x3, st); }, 1, OP_CONV, flops, bytes);
+        return;
+    }
     bd.add([p](cudaStream_t st) { return launch_conv_simt(p, st); }, 1, OP_CONV, flops, bytes);
 }
 
@@ -563,7 +623,7 @@ Act plan_res(Builder& bd, const ULayer& l, const Act& x0, const Act* x1, const U
         p.nseg = 1; p.Cout = l.cout; p.Tout = Tc; p.Tc = Tc; p.stride = 1; p.pad_left = 1;
         p.bias = l.b1; p.temb = io.temb + l.emb_off; p.temb_stride = io.temb_stride;
         p.out = bd.wptr(h1);
-        plan_conv(bd, p);
+        plan_conv(bd, p, l.t_w1);
     }
     Act y = bd.act(l.cout, Tc);
     {
@@ -579,7 +639,7 @@ Act plan_res(Builder& bd, const ULayer& l, const Act& x0, const Act* x1, const U
             p.res = bd.ptr(x0); p.res_mode = l.mode; p.res_Tin = x0.T;
         }
         p.out = bd.wptr(y);
-        plan_conv(bd, p);
+        plan_conv(bd, p, l.t_w2, l.t_wskip);
     }
     return y;
 }
@@ -592,7 +652,7 @@ Act plan_attn(Builder& bd, const ULayer& l, const Act& x) {
         p.seg[0] = make_seg(bd, x, nullptr, &ss, 0, RS_NONE, l.wqkv, 1);
         p.nseg = 1; p.Cout = 3 * l.ch; p.Tout = x.T; p.Tc = x.T; p.stride = 1; p.pad_left = 0;
         p.bias = l.bqkv; p.out = bd.wptr(qkv);
-        plan_conv(bd, p);
+        plan_conv(bd, p, l.t_wqkv);
     }
     Act a = bd.act(l.ch, x.T);
     {
@@ -609,7 +669,7 @@ Act plan_attn(Builder& bd, const ULayer& l, const Act& x) {
         p.nseg = 1; p.Cout = l.ch; p.Tout = x.T; p.Tc = x.T; p.stride = 1; p.pad_left = 0;
         p.bias = l.bproj; p.res = bd.ptr(x); p.res_mode = RS_NONE; p.res_Tin = x.T;
         p.out = bd.wptr(y);
-        plan_conv(bd, p);
+        plan_conv(bd, p, l.t_wproj);
     }
     return y;
 }
@@ -651,7 +711,7 @@ Act plan_layer(Builder& bd, const ULayer& l, const Act& x0, const Act* x1, const
                 p.seg[0] = make_seg(bd, x0, nullptr, nullptr, 0, RS_NEAREST2, l.w1, 3);
                 p.nseg = 1; p.Cout = l.ch; p.Tout = x0.T * 2; p.Tc = x0.T * 2; p.stride = 1; p.pad_left = 1;
                 p.bias = l.b1; p.out = bd.wptr(y);
-                plan_conv(bd, p);
+                plan_conv(bd, p, l.t_w1);
                 return y;
             }
             Act y = bd.act(l.ch, x0.T * 2);
@@ -698,7 +758,7 @@ int build_unet_plan(eegldm_unet* h, int B, int T, const UNetIO& io, Builder& out
     const int levels = h->cfg.n_channel_mult;
     if (T <= 0 || (T % (1 << (levels - 1))) != 0)
         return fail(EEGLDM_ERR_SHAPE, "T must be a positive multiple of 2^(levels-1)");
-    Builder sizing; sizing.B = B;
+    Builder sizing; sizing.B = B; sizing.math = h->math;
     int r = plan_unet_body(h, sizing, T, io);
     if (r) return r;
     if (sizing.peak > h->arena_cap) {
@@ -706,7 +766,7 @@ int build_unet_plan(eegldm_unet* h, int B, int T, const UNetIO& io, Builder& out
         r = ensure(h->arena, h->arena_cap, sizing.peak);
         if (r) return r;
     }
-    out.B = B; out.base = h->arena;
+    out.B = B; out.base = h->arena; out.math = h->math;
     return plan_unet_body(h, out, T, io);
 }
 
@@ -1127,7 +1187,8 @@ int eegldm_unet_finalize(eegldm_unet* h) {
 }
 int eegldm_unet_set_math(eegldm_unet* h, eegldm_math mode) {
     if (!h) return fail(EEGLDM_ERR_INVALID, "null handle");
-    if (mode != EEGLDM_MATH_FP32_SIMT) return fail(EEGLDM_ERR_INVALID, "only EEGLDM_MATH_FP32_SIMT is built in this version");
+    if (mode != EEGLDM_MATH_FP32_SIMT && mode != EEGLDM_MATH_BF16X3_TC && mode != EEGLDM_MATH_BF16_TC)
+        return fail(EEGLDM_ERR_INVALID, "unknown math mode");
     if (mode != h->math) h->drop_graphs();
     h->math = mode;
     return EEGLDM_OK;
@@ -1411,6 +1472,50 @@ int eegldm_ddim_sample_host(eegldm_unet* u, eegldm_aekl* a, const eegldm_sched_c
     e = cudaStreamSynchronize(st);
     if (!r && e != cudaSuccess) r = cuda_fail(e, "cudaStreamSynchronize");
     return r;
+}
+
+// ---------------------------------------------------------------------------------------------- test hook
+// One fused convolution launch in a chosen math mode (tests/test_gpu_conv.py compares the tcgen05 kernel with
+// the SIMT kernel and with torch.nn.functional.conv1d layer by layer).
+int eegldm_test_conv(const float* x_dev, const float* scale_dev, const float* shift_dev, int silu, int resample,
+                     const float* w_host, const float* bias_host, const float* res_dev, int B, int Tin, int Cin, int Cout, int k,
+                     int math, float* out_dev, void* stream) {
+    if (!x_dev || !w_host || !out_dev) return fail(EEGLDM_ERR_INVALID, "null argument");
+    if (k != 1 && k != 3) return fail(EEGLDM_ERR_INVALID, "k must be 1 or 3");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int Tc = resampled_len(Tin, resample);
+    std::vector<float> w(w_host, w_host + (size_t)Cout * Cin * k);
+    WeightPool wp;
+    const size_t o_w = wp.push(pack_conv(w, Cout, Cin, k));
+    size_t o_b = 0, o_t = 0;
+    if (bias_host) o_b = wp.push(bias_host, Cout);
+    const bool tc = math != EEGLDM_MATH_FP32_SIMT;
+    if (tc) {
+        if (!conv_tc_eligible(Cin, 0, Cout, Tc, k, 1)) return fail(EEGLDM_ERR_SHAPE, "shape not eligible for the tcgen05 path");
+        std::vector<uint16_t> img;
+        pack_conv_tc(w.data(), Cout, Cin, k, img);
+        o_t = wp.push_u16(img);
+    }
+    int r = wp.upload();
+    if (r) return r;
+    ConvParams p{};
+    p.seg[0] = ConvSeg{x_dev, nullptr, Cin, 0, scale_dev, shift_dev, silu, resample, Tin, wp.at(o_w), k};
+    p.nseg = 1; p.Cout = Cout; p.Tout = Tc; p.Tc = Tc; p.stride = 1; p.pad_left = k / 2;
+    p.bias = bias_host ? wp.at(o_b) : nullptr;
+    p.res = res_dev; p.res_mode = RS_NONE; p.res_Tin = Tc;
+    p.out = out_dev; p.B = B;
+    cudaError_t ce;
+    if (tc) {
+        TcConvParams q{};
+        q.seg[0] = TcSeg{x_dev, nullptr, Cin, 0, scale_dev, shift_dev, silu, resample, Tin, reinterpret_cast<const uint8_t*>(wp.at(o_t)), k,
+                         Cin / TC_BK};
+        q.nseg = 1; q.Cout = Cout; q.Tout = Tc; q.nsegs16 = (int)((long long)B * Tc / 16);
+        q.bias = p.bias; q.res = res_dev; q.res_mode = RS_NONE; q.res_Tin = Tc; q.out = out_dev;
+        ce = launch_conv_tc(q, math == EEGLDM_MATH_BF16X3_TC, st);
+    } else ce = launch_conv_simt(p, st);
+    if (ce != cudaSuccess) return cuda_fail(ce, "conv launch");
+    CU(cudaStreamSynchronize(st));   // the temporary weight pool is freed on return
+    return EEGLDM_OK;
 }
 
 }  // extern "C"

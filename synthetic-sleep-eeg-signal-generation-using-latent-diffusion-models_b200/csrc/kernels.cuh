@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 #include <atomic>
 #include <cstdint>
+#include <vector>
 
 namespace eegldm {
 
@@ -66,6 +67,30 @@ struct AttnParams {
 };
 
 cudaError_t launch_conv_simt(const ConvParams& p, cudaStream_t st);
+
+// ---- tcgen05 path (conv_tc.cu) ---------------------------------------------------------------
+constexpr int TC_BN = 128;              // output channels per CTA
+constexpr int TC_BK = 32;               // input channels per k-step
+constexpr int TC_W_HALF_BYTES = 8192;   // one bf16 (hi or lo) weight tile [TC_BN x TC_BK]
+struct TcSeg {
+    const float* src0; const float* src1; int C0, C1;   // (virtual concat of) fp32 sources [B][Tin][C]
+    const float* scale; const float* shift;             // [B][C0+C1] or null
+    int silu, resample, Tin;
+    const uint8_t* w;   // packed by pack_conv_tc: [n_tile][k-step][tap][hi|lo] 8 KB blocks
+    int taps, nks;      // nks = (C0+C1)/TC_BK
+};
+struct TcConvParams {
+    TcSeg seg[2];
+    int nseg;
+    int Cout, Tout;     // stride 1, "same" padding: conv-input length == Tout
+    int nsegs16;        // B*Tout/16 segments of 16 positions (8 per CTA)
+    const float* bias; const float* temb; int temb_stride;
+    const float* res; int res_mode; int res_Tin;
+    float* out;
+};
+bool conv_tc_eligible(int Cin0, int Cin1, int Cout, int Tout, int taps, int stride);
+void pack_conv_tc(const float* w, int Cout, int Cin, int k, std::vector<uint16_t>& out);
+cudaError_t launch_conv_tc(const TcConvParams& p, bool x3, cudaStream_t st);
 cudaError_t launch_groupnorm(const GnParams& p, cudaStream_t st);
 int groupnorm_nsplit(int C, int T, int G);
 cudaError_t launch_attention_simt(const AttnParams& p, cudaStream_t st);

@@ -1,0 +1,80 @@
+"""Layer-level checks of the fused convolution kernels through the C-ABI test hook: the tcgen05 (bf16x3)
+kernel and the fp32 SIMT kernel against torch's conv1d on the CPU, including the fused
+GroupNorm-apply/SiLU/resample prologue and the bias/residual epilogue."""
+import ctypes as C
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+MODES = {"fp32": 0, "bf16x3": 1, "bf16": 2}
+
+
+def _run(lib, dev, x_nlc, w, bias, scale, shift, silu, resample, res, math):
+    from eegldm import _lib
+    B, Tin, Cin = x_nlc.shape
+    Cout, _, k = w.shape
+    Tc = {0: Tin, 1: Tin // 2, 2: Tin * 2}[resample]
+    xd = x_nlc.contiguous().to(dev)
+    sd = scale.contiguous().to(dev) if scale is not None else None
+    hd = shift.contiguous().to(dev) if shift is not None else None
+    rd = res.contiguous().to(dev) if res is not None else None
+    out = torch.full((B, Tc, Cout), float("nan"), device=dev)
+    p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+    wc, bc = w.contiguous(), bias.contiguous() if bias is not None else None
+    _lib.check(lib.eegldm_test_conv(p(xd), p(sd), p(hd), int(silu), int(resample), p(wc), p(bc), p(rd), B, Tin, Cin, Cout, k,
+                                    MODES[math], p(out), None))
+    return out.cpu()
+
+
+def _ref(x_nlc, w, bias, scale, shift, silu, resample, res):
+    x = x_nlc.double()
+    if scale is not None:
+        x = x * scale[:, None, :].double() + shift[:, None, :].double()
+    if silu:
+        x = F.silu(x)
+    x = x.transpose(1, 2)
+    if resample == 1:
+        x = F.avg_pool1d(x, 2, 2)
+    elif resample == 2:
+        x = F.interpolate(x, scale_factor=2, mode="nearest")
+    y = F.conv1d(x, w.double(), bias.double() if bias is not None else None, padding=w.shape[2] // 2).transpose(1, 2)
+    if res is not None:
+        y = y + res.double()
+    return y.float()
+
+
+CASES = [
+    # B, Tin, Cin, Cout, k, affine+silu, resample, residual
+    (1, 128, 32, 128, 1, False, 0, False),
+    (1, 128, 32, 128, 3, False, 0, False),
+    (2, 192, 128, 128, 3, True, 0, True),
+    (3, 48, 64, 256, 3, True, 0, False),       # partial last tile (9 segments), several samples per tile
+    (2, 64, 256, 128, 3, True, 1, False),      # AvgPool1d(2,2) folded into the load
+    (2, 32, 128, 384, 3, True, 2, True),       # nearest x2 folded into the load
+    (5, 16, 512, 512, 1, False, 0, True),
+    (2, 768, 384, 128, 3, True, 0, False),
+]
+
+
+@pytest.mark.parametrize("math", ["fp32", "bf16x3", "bf16"])
+@pytest.mark.parametrize("case", CASES)
+def test_fused_conv_matches_torch(built_lib, cuda_device, case, math):
+    B, Tin, Cin, Cout, k, aff, rs, has_res = case
+    g = torch.Generator().manual_seed(hash(case) % 1000)
+    x = torch.randn(B, Tin, Cin, generator=g)
+    w = torch.randn(Cout, Cin, k, generator=g) / (Cin * k) ** 0.5
+    bias = 0.1 * torch.randn(Cout, generator=g)
+    scale = 1 + 0.2 * torch.randn(B, Cin, generator=g) if aff else None
+    shift = 0.2 * torch.randn(B, Cin, generator=g) if aff else None
+    Tc = {0: Tin, 1: Tin // 2, 2: Tin * 2}[rs]
+    res = torch.randn(B, Tc, Cout, generator=g) if has_res else None
+    y = _run(built_lib, cuda_device, x, w, bias, scale, shift, aff, rs, res, math)
+    ref = _ref(x, w, bias, scale, shift, aff, rs, res)
+    assert torch.isfinite(y).all()
+    err = (y - ref).abs().max().item()
+    if math == "bf16":      # fast mode: single bf16 product, ~2^-8 relative operand error; NOT a parity mode
+        assert err < 5e-2, err
+    else:                   # fp32 SIMT and bf16x3: fp32-level agreement
+        torch.testing.assert_close(y, ref, rtol=1e-4, atol=2e-5)
