@@ -280,7 +280,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=1024, help="windows per GPU per step (config 3: 1024)")
-    ap.add_argument("--math", default=os.environ.get("EEGLDM_BENCH_MATH", "fp32"), help="fp32 | bf16x3 (both parity-green)")
+    ap.add_argument("--math", default=os.environ.get("EEGLDM_BENCH_MATH", "f16x3"), help="fp32 | f16x3 (both parity-green)")
     ap.add_argument("--ref-batch", type=int, default=8, help="windows per CPU-baseline step (bounded sample)")
     ap.add_argument("--profile-batch", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")

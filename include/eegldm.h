@@ -39,11 +39,12 @@ typedef enum {
 } eegldm_status;
 
 /* Arithmetic used by the convolution GEMMs.
- *  FP32_SIMT : fp32 FMA on the CUDA cores -- exact-order-independent fp32, the parity baseline.
- *  BF16X3_TC : tcgen05 tensor cores, each fp32 operand split into bf16 hi+lo, 3 products
- *              (hi*hi + hi*lo + lo*hi), fp32 accumulate in TMEM: ~2^-16 relative operand error.
+ *  FP32_SIMT : fp32 FMA on the CUDA cores, the parity baseline.
+ *  F16X3_TC  : tcgen05 tensor cores; each fp32 operand is split x = hi + lo*2^-11 (hi, lo fp16) and 3 products
+ *              are issued (hi*hi | hi*lo + lo*hi in a second TMEM accumulator): ~2^-22 operand error, fp32
+ *              accumulate.  Meets the fp32 parity tolerance; operands must satisfy |x| < 65504.
  *  BF16_TC   : single bf16 product (fast mode; does NOT meet the fp32 parity tolerance). */
-typedef enum { EEGLDM_MATH_FP32_SIMT = 0, EEGLDM_MATH_BF16X3_TC = 1, EEGLDM_MATH_BF16_TC = 2 } eegldm_math;
+typedef enum { EEGLDM_MATH_FP32_SIMT = 0, EEGLDM_MATH_F16X3_TC = 1, EEGLDM_MATH_BF16_TC = 2 } eegldm_math;
 
 const char* eegldm_last_error(void);
 const char* eegldm_version(void);

@@ -7,9 +7,12 @@
 // as a GEMM with M = 128 output positions, N = 128 output channels, K = taps*Cin per CTA:
 //
 //   * D (fp32) lives in TMEM (128 lanes x 128 columns); tcgen05.mma.cta_group::1.kind::f16, M=128 N=128 K=16.
-//   * fp32 parity on a bf16 tensor pipe: every fp32 operand is split x = hi + lo (two bf16) and three products
-//     are accumulated, hi*hi + hi*lo + lo*hi ("bf16x3", ~2^-16 relative operand error).  EEGLDM_MATH_BF16_TC
-//     issues only hi*hi.
+//   * fp32 parity on a 16-bit tensor pipe ("f16x3"): every fp32 operand is split x = hi + lo/2048 with hi and lo
+//     fp16 (11 + 11 significand bits, lo pre-scaled by 2^11 so it stays in fp16's normal range) and three products
+//     are issued per K-slice: hi*hi into accumulator 0, hi*lo + lo*hi into accumulator 1; the epilogue returns
+//     acc0 + acc1 * 2^-11.  Operand error ~2^-22; the tensor core's fp32 accumulate truncates (measured
+//     ~2^-25 per K=16 step, tools/conv_precision.py), which the separate correction accumulator keeps off the
+//     long chain.  EEGLDM_MATH_BF16_TC issues a single bf16 product (fast, NOT a parity mode).
 //   * B operand = weights, pre-split and pre-packed on the host into the exact shared-memory image of one
 //     pipeline stage (K-major, no swizzle, 8x16-byte core matrices) so a stage is ONE cp.async.bulk (UBLKCP).
 //   * A operand = activations, produced by 4 warps: coalesced fp32 loads -> affine/SiLU/resample -> bf16 hi/lo
@@ -21,6 +24,7 @@
 //   * warp roles: 0-3 A producers then epilogue (TMEM -> registers -> global), 4 weight loader, 5 MMA issuer.
 //     ~101 KB smem + 128 TMEM columns per CTA -> 2 CTAs per SM, so one CTA's epilogue overlaps the other's mainloop.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include <cstring>
 #include <vector>
@@ -116,8 +120,12 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
            (1ull << 46);
 }
-// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N=128, M=128 (cute::UMMA::InstrDescriptor)
-constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+// kind::f16 instruction descriptor: D=f32, A=B=fp16 (0) or bf16 (1), both K-major, N=128, M=128
+// (cute::UMMA::InstrDescriptor: c_format [4,6), a_format [7,10), b_format [10,13), n>>3 [17,23), m>>4 [24,29))
+__host__ __device__ constexpr uint32_t idesc_for(uint32_t fmt) {
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+constexpr float LO_SCALE = 2048.f;   // 2^11: keeps the fp16 low part in the normal range
 
 __device__ __forceinline__ float silu_fast(float v) { return __fdividef(v, 1.f + __expf(-v)); }
 __device__ __forceinline__ float act(float x, float a, float s, int silu) {
@@ -126,20 +134,29 @@ __device__ __forceinline__ float act(float x, float a, float s, int silu) {
 }
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
-// fp32 x8 -> bf16 hi x8 (uint4) and bf16 lo x8 (uint4), element e at the lower address
-__device__ __forceinline__ void split8(const float (&v)[8], uint4& hi, uint4& lo) {
+// fp32 x8 -> fp16 hi x8 and fp16 lo x8 with lo = (v - hi) * 2^11 (element e at the lower address)
+__device__ __forceinline__ void split8_f16(const float (&v)[8], uint4& hi, uint4& lo) {
     uint32_t h[4], l[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        __nv_bfloat162 hb = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-        h[i] = *reinterpret_cast<uint32_t*>(&hb);
-        const float r0 = v[2 * i] - __uint_as_float(h[i] << 16);
-        const float r1 = v[2 * i + 1] - __uint_as_float(h[i] & 0xFFFF0000u);
-        __nv_bfloat162 lb = __floats2bfloat162_rn(r0, r1);
-        l[i] = *reinterpret_cast<uint32_t*>(&lb);
+        const __half2 hb = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+        const float2 hf = __half22float2(hb);
+        const __half2 lb = __floats2half2_rn((v[2 * i] - hf.x) * LO_SCALE, (v[2 * i + 1] - hf.y) * LO_SCALE);
+        h[i] = *reinterpret_cast<const uint32_t*>(&hb);
+        l[i] = *reinterpret_cast<const uint32_t*>(&lb);
     }
     hi = make_uint4(h[0], h[1], h[2], h[3]);
     lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+// fp32 x8 -> bf16 x8 (fast mode)
+__device__ __forceinline__ void round8_bf16(const float (&v)[8], uint4& hi) {
+    uint32_t h[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __nv_bfloat162 hb = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        h[i] = *reinterpret_cast<const uint32_t*>(&hb);
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
 }
 
 struct Item {      // one 16-byte (8-channel) slot of the activation tile, fixed for the whole K loop
@@ -169,7 +186,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) conv_tc_kernel(const TcConvPar
         mbar_init(barAcc, 1);
         fence_mbar_init();
     }
-    if (warp == 5) tmem_alloc(smem_u32(tmem_slot), BN);
+    constexpr uint32_t TMEM_COLS = X3 ? 2 * BN : BN;   // X3: accumulator 0 = hi*hi, accumulator 1 = cross terms * 2^11
+    constexpr uint32_t IDESC = idesc_for(X3 ? 0u : 1u);
+    if (warp == 5) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -240,9 +259,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) conv_tc_kernel(const TcConvPar
             for (int j = 0; j < ITEMS_PER_THREAD; ++j) {
                 if (!items[j].live) continue;
                 uint4 hi, lo;
-                split8(vals[j], hi, lo);
+                if (X3) {
+                    split8_f16(vals[j], hi, lo);
+                    *reinterpret_cast<uint4*>(tile + A_TILE + items[j].soff) = lo;
+                } else round8_bf16(vals[j], hi);
                 *reinterpret_cast<uint4*>(tile + items[j].soff) = hi;
-                if (X3) *reinterpret_cast<uint4*>(tile + A_TILE + items[j].soff) = lo;
             }
             fence_proxy_async_smem();
             mbar_arrive(barAfull + 8 * sa);
@@ -270,6 +291,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) conv_tc_kernel(const TcConvPar
         for (int cb = 0; cb < BN; cb += 32) {
             uint32_t v[32];
             tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)cb, v);   // warp-collective: no divergence before this
+            if (X3) {
+                uint32_t c2[32];
+                tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(BN + cb), c2);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(fmaf(__uint_as_float(c2[i]), 1.0f / LO_SCALE, __uint_as_float(v[i])));
+            }
             if (!rowv) continue;
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
@@ -308,7 +335,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) conv_tc_kernel(const TcConvPar
         // ================================================================ MMA issuer (one thread)
         if (lane == 0) {
             int it = 0;
-            uint32_t accum = 0;
+            uint32_t accum = 0, accum2 = 0;
             for (int ks = 0; ks < nks; ++ks) {
                 const int sa = ks % NA;
                 const int taps = ks < nks0 ? p.seg[0].taps : p.seg[1].taps;
@@ -330,8 +357,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) conv_tc_kernel(const TcConvPar
                         if (X3) {
                             const uint64_t dal = make_desc(a_lo + kk * 2 * A_LBO, A_LBO, A_SBO);
                             const uint64_t dbl = make_desc(b_lo + kk * 2 * B_LBO, B_LBO, B_SBO);
-                            umma_bf16(tmem, dah, dbl, IDESC, 1);
-                            umma_bf16(tmem, dal, dbh, IDESC, 1);
+                            umma_bf16(tmem + BN, dah, dbl, IDESC, accum2);
+                            umma_bf16(tmem + BN, dal, dbh, IDESC, 1);
+                            accum2 = 1;
                         }
                     }
                     umma_commit(barBempty + 8 * sb);   // weight stage free once these MMAs retire
@@ -343,7 +371,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) conv_tc_kernel(const TcConvPar
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 5) tmem_dealloc(tmem, BN);
+    if (warp == 5) tmem_dealloc(tmem, TMEM_COLS);
 }
 
 uint16_t bf16_rn(float f) {
@@ -353,12 +381,8 @@ uint16_t bf16_rn(float f) {
     u += 0x7FFFu + ((u >> 16) & 1u);
     return (uint16_t)(u >> 16);
 }
-float bf16_to_f(uint16_t h) {
-    uint32_t u = (uint32_t)h << 16;
-    float f;
-    std::memcpy(&f, &u, 4);
-    return f;
-}
+uint16_t f16_rn(float f) { return __half_as_ushort(__float2half_rn(f)); }
+float f16_to_f(uint16_t h) { return __half2float(__ushort_as_half(h)); }
 
 }  // namespace
 
@@ -369,7 +393,8 @@ bool conv_tc_eligible(int Cin0, int Cin1, int Cout, int Tout, int taps, int stri
 
 // [Cout][Cin][k] fp32 -> per (n_tile, k-step, tap): [hi 8 KB | lo 8 KB], each the shared-memory image
 //   byte(kc, ng, r, e) = kc*2048 + ng*128 + r*16 + e*2   for  co = n_tile*128 + ng*8 + r,  ci = ks*32 + kc*8 + e
-void pack_conv_tc(const float* w, int Cout, int Cin, int k, std::vector<uint16_t>& out) {
+// x3: hi = fp16(w), lo = fp16((w - hi) * 2^11);  otherwise hi = bf16(w), lo = 0 (never read).
+void pack_conv_tc(const float* w, int Cout, int Cin, int k, bool x3, std::vector<uint16_t>& out) {
     const int nt = Cout / TC_BN, nks = Cin / TC_BK;
     out.assign((size_t)nt * nks * k * (2 * TC_W_HALF_BYTES / 2), 0);
     for (int n = 0; n < nt; ++n)
@@ -383,10 +408,12 @@ void pack_conv_tc(const float* w, int Cout, int Cin, int k, std::vector<uint16_t
                             for (int e = 0; e < 8; ++e) {
                                 const int co = n * TC_BN + ng * 8 + r, ci = ks * TC_BK + kc * 8 + e;
                                 const float v = w[((size_t)co * Cin + ci) * k + tap];
-                                const uint16_t h = bf16_rn(v);
                                 const size_t o = (size_t)kc * 1024 + ng * 64 + r * 8 + e;
-                                hi[o] = h;
-                                lo[o] = bf16_rn(v - bf16_to_f(h));
+                                if (x3) {
+                                    const uint16_t h = f16_rn(v);
+                                    hi[o] = h;
+                                    lo[o] = f16_rn((v - f16_to_f(h)) * LO_SCALE);
+                                } else hi[o] = bf16_rn(v);
                             }
             }
 }

@@ -474,10 +474,10 @@ int finalize_unet(eegldm_unet* h) {
     const size_t o_embw = wp.push(embw), o_embb = wp.push(embb);
     // tcgen05 images: bf16 hi/lo split, packed as shared-memory stage images (conv_tc.cu)
     auto tc_pack = [&](const std::string& name, int cout, int cin, int k, size_t& off, bool& has) {
-        has = conv_tc_eligible(cin, 0, cout, 16, k, 1);
+        has = h->math != EEGLDM_MATH_FP32_SIMT && conv_tc_eligible(cin, 0, cout, 16, k, 1);
         if (!has) return;
         std::vector<uint16_t> img;
-        pack_conv_tc(ps.get(name).data(), cout, cin, k, img);
+        pack_conv_tc(ps.get(name).data(), cout, cin, k, h->math == EEGLDM_MATH_F16X3_TC, img);
         off = wp.push_u16(img);
     };
     for_each_layer(h, [&](ULayer& l) {
@@ -606,7 +606,7 @@ void plan_conv(Builder& bd, ConvParams p, const uint8_t* tw0 = nullptr, const ui
         q.nseg = p.nseg; q.Cout = p.Cout; q.Tout = p.Tout; q.nsegs16 = (int)((long long)p.B * p.Tout / 16);
         q.bias = p.bias; q.temb = p.temb; q.temb_stride = p.temb_stride; q.res = p.res; q.res_mode = p.res_mode; q.res_Tin = p.res_Tin;
         q.out = p.out;
-        const bool x3 = bd.math == EEGLDM_MATH_BF16X3_TC;
+        const bool x3 = bd.math == EEGLDM_MATH_F16X3_TC;
         bd.add([q, x3](cudaStream_t st) { return launch_conv_tc(q, x3, st); }, 1, OP_CONV, flops, bytes);
         return;
     }
@@ -1187,10 +1187,12 @@ int eegldm_unet_finalize(eegldm_unet* h) {
 }
 int eegldm_unet_set_math(eegldm_unet* h, eegldm_math mode) {
     if (!h) return fail(EEGLDM_ERR_INVALID, "null handle");
-    if (mode != EEGLDM_MATH_FP32_SIMT && mode != EEGLDM_MATH_BF16X3_TC && mode != EEGLDM_MATH_BF16_TC)
+    if (mode != EEGLDM_MATH_FP32_SIMT && mode != EEGLDM_MATH_F16X3_TC && mode != EEGLDM_MATH_BF16_TC)
         return fail(EEGLDM_ERR_INVALID, "unknown math mode");
-    if (mode != h->math) h->drop_graphs();
+    if (mode == h->math) return EEGLDM_OK;
+    h->drop_graphs();
     h->math = mode;
+    if (h->finalized) return finalize_unet(h);   // weight images depend on the math mode
     return EEGLDM_OK;
 }
 
@@ -1493,7 +1495,7 @@ int eegldm_test_conv(const float* x_dev, const float* scale_dev, const float* sh
     if (tc) {
         if (!conv_tc_eligible(Cin, 0, Cout, Tc, k, 1)) return fail(EEGLDM_ERR_SHAPE, "shape not eligible for the tcgen05 path");
         std::vector<uint16_t> img;
-        pack_conv_tc(w.data(), Cout, Cin, k, img);
+        pack_conv_tc(w.data(), Cout, Cin, k, math == EEGLDM_MATH_F16X3_TC, img);
         o_t = wp.push_u16(img);
     }
     int r = wp.upload();
@@ -1511,7 +1513,7 @@ int eegldm_test_conv(const float* x_dev, const float* scale_dev, const float* sh
                          Cin / TC_BK};
         q.nseg = 1; q.Cout = Cout; q.Tout = Tc; q.nsegs16 = (int)((long long)B * Tc / 16);
         q.bias = p.bias; q.res = res_dev; q.res_mode = RS_NONE; q.res_Tin = Tc; q.out = out_dev;
-        ce = launch_conv_tc(q, math == EEGLDM_MATH_BF16X3_TC, st);
+        ce = launch_conv_tc(q, math == EEGLDM_MATH_F16X3_TC, st);
     } else ce = launch_conv_simt(p, st);
     if (ce != cudaSuccess) return cuda_fail(ce, "conv launch");
     CU(cudaStreamSynchronize(st));   // the temporary weight pool is freed on return

@@ -71,7 +71,7 @@ cudaError_t launch_conv_simt(const ConvParams& p, cudaStream_t st);
 // ---- tcgen05 path (conv_tc.cu) ---------------------------------------------------------------
 constexpr int TC_BN = 128;              // output channels per CTA
 constexpr int TC_BK = 32;               // input channels per k-step
-constexpr int TC_W_HALF_BYTES = 8192;   // one bf16 (hi or lo) weight tile [TC_BN x TC_BK]
+constexpr int TC_W_HALF_BYTES = 8192;   // one 16-bit (hi or lo) weight tile [TC_BN x TC_BK]
 struct TcSeg {
     const float* src0; const float* src1; int C0, C1;   // (virtual concat of) fp32 sources [B][Tin][C]
     const float* scale; const float* shift;             // [B][C0+C1] or null
@@ -89,7 +89,7 @@ struct TcConvParams {
     float* out;
 };
 bool conv_tc_eligible(int Cin0, int Cin1, int Cout, int Tout, int taps, int stride);
-void pack_conv_tc(const float* w, int Cout, int Cin, int k, std::vector<uint16_t>& out);
+void pack_conv_tc(const float* w, int Cout, int Cin, int k, bool x3, std::vector<uint16_t>& out);
 cudaError_t launch_conv_tc(const TcConvParams& p, bool x3, cudaStream_t st);
 cudaError_t launch_groupnorm(const GnParams& p, cudaStream_t st);
 int groupnorm_nsplit(int C, int T, int G);

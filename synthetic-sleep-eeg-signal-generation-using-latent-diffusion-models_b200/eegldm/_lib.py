@@ -46,8 +46,8 @@ class SchedCfg(C.Structure):
     ]
 
 
-MATH_FP32_SIMT, MATH_BF16X3_TC, MATH_BF16_TC = 0, 1, 2
-MATH_MODES = {"fp32": MATH_FP32_SIMT, "fp32_simt": MATH_FP32_SIMT, "bf16x3": MATH_BF16X3_TC, "bf16x3_tc": MATH_BF16X3_TC,
+MATH_FP32_SIMT, MATH_F16X3_TC, MATH_BF16_TC = 0, 1, 2
+MATH_MODES = {"fp32": MATH_FP32_SIMT, "fp32_simt": MATH_FP32_SIMT, "f16x3": MATH_F16X3_TC, "f16x3_tc": MATH_F16X3_TC,
               "bf16": MATH_BF16_TC, "bf16_tc": MATH_BF16_TC}
 
 _P = C.c_void_p

@@ -86,7 +86,7 @@ class UNetModel(EngineModule):
             self._h = None
 
     def set_math(self, mode: str) -> "UNetModel":
-        """``"fp32"`` (SIMT, exact fp32), ``"bf16x3"`` (tcgen05, split-bf16, fp32-accurate to ~2^-16),
+        """``"fp32"`` (SIMT, exact fp32), ``"f16x3"`` (tcgen05, fp16 hi + scaled fp16 lo, 3 products, ~fp32-accurate),
         ``"bf16"`` (tcgen05, fast; does NOT meet the fp32 parity tolerance)."""
         _lib.check(_lib.lib().eegldm_unet_set_math(self._h, _lib.MATH_MODES[mode]))
         self._math = mode

@@ -1,4 +1,4 @@
-"""Layer-level checks of the fused convolution kernels through the C-ABI test hook: the tcgen05 (bf16x3)
+"""Layer-level checks of the fused convolution kernels through the C-ABI test hook: the tcgen05 (f16x3)
 kernel and the fp32 SIMT kernel against torch's conv1d on the CPU, including the fused
 GroupNorm-apply/SiLU/resample prologue and the bias/residual epilogue."""
 import ctypes as C
@@ -8,7 +8,7 @@ import torch
 import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
-MODES = {"fp32": 0, "bf16x3": 1, "bf16": 2}
+MODES = {"fp32": 0, "f16x3": 1, "bf16": 2}
 
 
 def _run(lib, dev, x_nlc, w, bias, scale, shift, silu, resample, res, math):
@@ -58,7 +58,7 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("math", ["fp32", "bf16x3", "bf16"])
+@pytest.mark.parametrize("math", ["fp32", "f16x3", "bf16"])
 @pytest.mark.parametrize("case", CASES)
 def test_fused_conv_matches_torch(built_lib, cuda_device, case, math):
     B, Tin, Cin, Cout, k, aff, rs, has_res = case
@@ -76,5 +76,5 @@ def test_fused_conv_matches_torch(built_lib, cuda_device, case, math):
     err = (y - ref).abs().max().item()
     if math == "bf16":      # fast mode: single bf16 product, ~2^-8 relative operand error; NOT a parity mode
         assert err < 5e-2, err
-    else:                   # fp32 SIMT and bf16x3: fp32-level agreement
+    else:                   # fp32 SIMT and f16x3: fp32-level agreement
         torch.testing.assert_close(y, ref, rtol=1e-4, atol=2e-5)

@@ -15,7 +15,7 @@ from oracle.sample import SAMPLER_DEFAULTS
 
 pytestmark = pytest.mark.gpu
 RTOL, ATOL = 1e-3, 1e-4
-MATH = os.environ.get("EEGLDM_TEST_MATH", "fp32,bf16x3").split(",")
+MATH = os.environ.get("EEGLDM_TEST_MATH", "fp32,f16x3").split(",")
 
 
 def _unet(cfg, sd, dev, math="fp32"):
