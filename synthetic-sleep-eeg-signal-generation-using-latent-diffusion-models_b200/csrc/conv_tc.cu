@@ -196,6 +196,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) conv_tc_kernel(const TcConvPar
 
     if (warp < 4) {
         // ================================================================ A producers
+        // Software-pipelined: the raw fp32 rows of k-step ks+1 are in flight (registers) while k-step ks is
+        // transformed and stored, so global-load latency is paid once, not per item.
         const int c = tid & 3;   // 8-channel chunk inside the k-step
         Item items[ITEMS_PER_THREAD];
 #pragma unroll
@@ -212,58 +214,92 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) conv_tc_kernel(const TcConvPar
             it.soff = (uint32_t)(c * A_LBO + q * A_SBO + r * 16);
             items[j] = it;
         }
-        for (int ks = 0; ks < nks; ++ks) {
-            const int sa = ks % NA;
-            const TcSeg& sg = ks < nks0 ? p.seg[0] : p.seg[1];
-            const int cc = (ks < nks0 ? ks : ks - nks0) * BK + c * 8;   // channel inside the (virtual) concat
+        // a tile of 8 consecutive segments touches at most two samples when Tout >= 112; otherwise the
+        // GroupNorm scale/shift rows are fetched per item (slow path, tiny T only)
+        const int b_first = (m_tile * 8) / spt;
+        const int b_last = min(m_tile * 8 + 7, p.nsegs16 - 1) / spt;
+        const bool two_b = b_last - b_first <= 1;
+
+        auto seg_of = [&](int ks) -> const TcSeg& { return ks < nks0 ? p.seg[0] : p.seg[1]; };
+        auto chan_of = [&](int ks) { return (ks < nks0 ? ks : ks - nks0) * BK + c * 8; };   // channel inside the virtual concat
+        float4 nxt[ITEMS_PER_THREAD][2];
+        auto prefetch = [&](int ks) {
+            const TcSeg& sg = seg_of(ks);
+            const int cc = chan_of(ks);
             const float* src; int ch, Cs;
             if (cc < sg.C0) { src = sg.src0; ch = cc; Cs = sg.C0; } else { src = sg.src1; ch = cc - sg.C0; Cs = sg.C1; }
-            const int Cin = sg.C0 + sg.C1;
-            float vals[ITEMS_PER_THREAD][8];
+            if (sg.resample == RS_AVGPOOL2) return;   // two rows per position: loaded in the transform phase
 #pragma unroll
             for (int j = 0; j < ITEMS_PER_THREAD; ++j) {
                 const Item& it = items[j];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) vals[j][e] = 0.f;
-                if (!it.inb) continue;
-                float a[8], s[8];
-                if (sg.scale) {
-                    const float4 a0 = ldg4(sg.scale + (size_t)it.b * Cin + cc), a1 = ldg4(sg.scale + (size_t)it.b * Cin + cc + 4);
-                    const float4 s0 = ldg4(sg.shift + (size_t)it.b * Cin + cc), s1 = ldg4(sg.shift + (size_t)it.b * Cin + cc + 4);
-                    a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
-                    s[0] = s0.x; s[1] = s0.y; s[2] = s0.z; s[3] = s0.w; s[4] = s1.x; s[5] = s1.y; s[6] = s1.z; s[7] = s1.w;
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) { a[e] = 1.f; s[e] = 0.f; }
-                }
-                const float* base = src + (size_t)it.b * sg.Tin * Cs + ch;
-                if (sg.resample == RS_AVGPOOL2) {
-                    const float* r0 = base + (size_t)(2 * it.t) * Cs;
-                    const float4 x0 = ldg4(r0), x1 = ldg4(r0 + 4), y0 = ldg4(r0 + Cs), y1 = ldg4(r0 + Cs + 4);
-                    const float xa[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-                    const float ya[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) vals[j][e] = 0.5f * (act(xa[e], a[e], s[e], sg.silu) + act(ya[e], a[e], s[e], sg.silu));
-                } else {
-                    const int tt = sg.resample == RS_NEAREST2 ? (it.t >> 1) : it.t;
-                    const float* r0 = base + (size_t)tt * Cs;
-                    const float4 x0 = ldg4(r0), x1 = ldg4(r0 + 4);
-                    const float xa[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) vals[j][e] = act(xa[e], a[e], s[e], sg.silu);
-                }
+                const int tt = sg.resample == RS_NEAREST2 ? (it.t >> 1) : it.t;
+                const float* ptr = src + ch + (it.inb ? ((size_t)it.b * sg.Tin + tt) * Cs : 0);   // always a valid address
+                nxt[j][0] = ldg4(ptr);
+                nxt[j][1] = ldg4(ptr + 4);
             }
+        };
+        prefetch(0);
+        for (int ks = 0; ks < nks; ++ks) {
+            const int sa = ks % NA;
+            const TcSeg& sg = seg_of(ks);
+            const int cc = chan_of(ks);
+            const int Cin = sg.C0 + sg.C1;
+            float4 cur[ITEMS_PER_THREAD][2];
+#pragma unroll
+            for (int j = 0; j < ITEMS_PER_THREAD; ++j) { cur[j][0] = nxt[j][0]; cur[j][1] = nxt[j][1]; }
+            // GroupNorm scale/shift of this k-step's 8 channels for the (at most two) samples of the tile
+            float a2[2][8], s2[2][8];
+            if (sg.scale && two_b) {
+#pragma unroll
+                for (int w = 0; w < 2; ++w) {
+                    const size_t o = (size_t)(w ? b_last : b_first) * Cin + cc;
+                    const float4 a0 = ldg4(sg.scale + o), a1 = ldg4(sg.scale + o + 4), s0 = ldg4(sg.shift + o), s1 = ldg4(sg.shift + o + 4);
+                    a2[w][0] = a0.x; a2[w][1] = a0.y; a2[w][2] = a0.z; a2[w][3] = a0.w; a2[w][4] = a1.x; a2[w][5] = a1.y; a2[w][6] = a1.z; a2[w][7] = a1.w;
+                    s2[w][0] = s0.x; s2[w][1] = s0.y; s2[w][2] = s0.z; s2[w][3] = s0.w; s2[w][4] = s1.x; s2[w][5] = s1.y; s2[w][6] = s1.z; s2[w][7] = s1.w;
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { a2[0][e] = a2[1][e] = 1.f; s2[0][e] = s2[1][e] = 0.f; }
+            }
+            if (ks + 1 < nks) prefetch(ks + 1);
             mbar_wait(barAempty + 8 * sa, ((ks / NA) & 1) ^ 1);
             uint8_t* tile = smem + sa * A_STAGE;
 #pragma unroll
             for (int j = 0; j < ITEMS_PER_THREAD; ++j) {
-                if (!items[j].live) continue;
+                const Item& it = items[j];
+                if (!it.live) continue;
+                float a[8], s[8], v[8];
+                const bool hi_b = it.b != b_first;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { a[e] = hi_b ? a2[1][e] : a2[0][e]; s[e] = hi_b ? s2[1][e] : s2[0][e]; }
+                if (sg.scale && !two_b && it.inb) {   // slow path: per-item rows
+                    const size_t o = (size_t)it.b * Cin + cc;
+                    const float4 a0 = ldg4(sg.scale + o), a1 = ldg4(sg.scale + o + 4), s0 = ldg4(sg.shift + o), s1 = ldg4(sg.shift + o + 4);
+                    a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+                    s[0] = s0.x; s[1] = s0.y; s[2] = s0.z; s[3] = s0.w; s[4] = s1.x; s[5] = s1.y; s[6] = s1.z; s[7] = s1.w;
+                }
+                if (sg.resample == RS_AVGPOOL2) {
+                    const float* src; int ch, Cs;
+                    if (cc < sg.C0) { src = sg.src0; ch = cc; Cs = sg.C0; } else { src = sg.src1; ch = cc - sg.C0; Cs = sg.C1; }
+                    const float* r0 = src + ch + (it.inb ? ((size_t)it.b * sg.Tin + 2 * it.t) * Cs : 0);
+                    const float4 x0 = ldg4(r0), x1 = ldg4(r0 + 4), y0 = ldg4(r0 + Cs), y1 = ldg4(r0 + Cs + 4);
+                    const float xa[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+                    const float ya[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) v[e] = 0.5f * (act(xa[e], a[e], s[e], sg.silu) + act(ya[e], a[e], s[e], sg.silu));
+                } else {
+                    const float xa[8] = {cur[j][0].x, cur[j][0].y, cur[j][0].z, cur[j][0].w, cur[j][1].x, cur[j][1].y, cur[j][1].z, cur[j][1].w};
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) v[e] = act(xa[e], a[e], s[e], sg.silu);
+                }
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = it.inb ? v[e] : 0.f;   // conv zero padding / rows past the batch
                 uint4 hi, lo;
                 if (X3) {
-                    split8_f16(vals[j], hi, lo);
-                    *reinterpret_cast<uint4*>(tile + A_TILE + items[j].soff) = lo;
-                } else round8_bf16(vals[j], hi);
-                *reinterpret_cast<uint4*>(tile + items[j].soff) = hi;
+                    split8_f16(v, hi, lo);
+                    *reinterpret_cast<uint4*>(tile + A_TILE + it.soff) = lo;
+                } else round8_bf16(v, hi);
+                *reinterpret_cast<uint4*>(tile + it.soff) = hi;
             }
             fence_proxy_async_smem();
             mbar_arrive(barAfull + 8 * sa);
