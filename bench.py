@@ -225,7 +225,7 @@ def run_ours(args):
         eegldm.ddim_sample(unet, sched, noise[:pb], psteps, aekl)
         torch.cuda.synchronize(dev)
         fam = {}
-        for kind, name in enumerate(("conv", "groupnorm", "attention", "other")):
+        for kind, name in enumerate(("conv", "groupnorm", "attention", "other", "act_split")):
             m, f, b, n = C.c_double(), C.c_double(), C.c_double(), C.c_int64()
             _lib.check(L.eegldm_profile_read(kind, C.byref(m), C.byref(f), C.byref(b), C.byref(n)))
             fam[name] = dict(ms=m.value, flops=f.value, bytes=b.value, launches=n.value)

@@ -53,7 +53,7 @@ int64_t eegldm_launch_count(void);
 
 /* Live per-kernel profile (bench.py's roofline leg).  While enabled, every launch made outside CUDA-graph
  * capture is bracketed by CUDA events on the launching stream.  eegldm_profile_read sums, for one kernel
- * family (0 = conv implicit-GEMM, 1 = GroupNorm statistics, 2 = attention, 3 = other), the measured
+ * family (0 = conv implicit-GEMM, 1 = GroupNorm statistics, 2 = attention, 3 = other, 4 = activation split pre-pass), the measured
  * milliseconds, the ALGORITHMIC flops and HBM bytes and the launch count since enable. */
 int eegldm_profile_enable(int on);
 int eegldm_profile_read(int kind, double* ms, double* flops, double* bytes, int64_t* launches);

@@ -2,27 +2,32 @@
 //
 // Computes, for channels-last activations,
 //     out[b,t,co] = bias[co] + temb[b,co] + res[b,t,co] + sum_seg sum_{k,ci} W_seg[co,ci,k] * u_seg[b, t+k-pad, ci]
-//     u = resample(silu?(scale*x + shift))           (GroupNorm apply + SiLU + AvgPool/nearest folded into the operand load)
+//     u = resample(silu?(scale*x + shift))           (GroupNorm apply + SiLU + AvgPool/nearest)
 // i.e. the same contract as conv_simt_kernel (reference: src/models/unet.py:263,291,302,158,161 + 308-327),
-// as a GEMM with M = 128 output positions, N = 128 output channels, K = taps*Cin per CTA:
+// in two launches:
 //
-//   * D (fp32) lives in TMEM (128 lanes x 128 columns); tcgen05.mma.cta_group::1.kind::f16, M=128 N=128 K=16.
+//   act_split_kernel   one pass over x: apply the GroupNorm affine / SiLU / resample, split every fp32 value into
+//                      16-bit parts and write them as ready-made shared-memory tile images ("U" tensors).
+//   conv_tc_kernel     a pure async-copy + tcgen05 GEMM: M = 128 output positions, N = 128 output channels,
+//                      K = taps*Cin per CTA; both operands arrive by cp.async.bulk (UBLKCP), D lives in TMEM.
+//
 //   * fp32 parity on a 16-bit tensor pipe ("f16x3"): every fp32 operand is split x = hi + lo/2048 with hi and lo
 //     fp16 (11 + 11 significand bits, lo pre-scaled by 2^11 so it stays in fp16's normal range) and three products
 //     are issued per K-slice: hi*hi into accumulator 0, hi*lo + lo*hi into accumulator 1; the epilogue returns
-//     acc0 + acc1 * 2^-11.  Operand error ~2^-22; the tensor core's fp32 accumulate truncates (measured
-//     ~2^-25 per K=16 step, tools/conv_precision.py), which the separate correction accumulator keeps off the
-//     long chain.  EEGLDM_MATH_BF16_TC issues a single bf16 product (fast, NOT a parity mode).
+//     acc0 + acc1 * 2^-11.  Operand error ~2^-22; the tensor core's fp32 accumulate truncates (measured,
+//     tools/conv_precision.py), which the separate correction accumulator keeps off the long chain.
+//     EEGLDM_MATH_BF16_TC issues a single bf16 product (fast, NOT a parity mode).
 //   * B operand = weights, pre-split and pre-packed on the host into the exact shared-memory image of one
-//     pipeline stage (K-major, no swizzle, 8x16-byte core matrices) so a stage is ONE cp.async.bulk (UBLKCP).
-//   * A operand = activations, produced by 4 warps: coalesced fp32 loads -> affine/SiLU/resample -> bf16 hi/lo
-//     -> st.shared in a "phase-strided halo" K-major layout: the 128 M rows are 8 segments of 16 consecutive
-//     positions; rows of one 8-row core matrix are the SAME offset in the 8 segments, and each segment carries
-//     its own 2 halo positions (18 slots).  A tap shift of +-1 position is then a whole-core-matrix shift
-//     = +-SBO bytes on the descriptor start address, so the 3 taps of a k=3 conv read ONE staged tile
-//     (12.5 % halo overhead instead of 3 copies).  Segments may belong to different samples / be zero padded.
-//   * warp roles: 0-3 A producers then epilogue (TMEM -> registers -> global), 4 weight loader, 5 MMA issuer.
-//     ~101 KB smem + 128 TMEM columns per CTA -> 2 CTAs per SM, so one CTA's epilogue overlaps the other's mainloop.
+//     pipeline stage (K-major, no swizzle, 8x16-byte core matrices): a stage is ONE bulk copy.
+//   * A operand = activations in a "phase-strided halo" K-major layout: the 128 M rows of a tile are 8 segments of
+//     16 consecutive positions; the 8 rows of one core matrix are the SAME offset in the 8 segments, and each
+//     segment carries its own 2 halo positions (18 slots).  A tap shift of +-1 position is then a whole-core-matrix
+//     shift = +-SBO bytes on the descriptor start address, so the 3 taps of a k=3 conv read ONE staged tile
+//     (12.5 % halo overhead instead of 3 copies).  Segments may belong to different samples; halos at sample
+//     edges are zero (the conv's padding).  U is stored [m_tile][k-step][hi|lo][kc][slot][segment][8 ch], i.e. one
+//     contiguous 18 KB block per (tile, k-step): ONE bulk copy per stage.
+//   * warp roles: 0-3 epilogue (TMEM -> registers -> global), 4 loader (one thread), 5 MMA issuer (one thread).
+//     ~104 KB smem + <= 256 TMEM columns per CTA -> 2 CTAs per SM: one CTA's epilogue overlaps the other's mainloop.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
@@ -40,19 +45,21 @@ constexpr int BK = TC_BK;          // input channels per k-step
 constexpr int SLOTS = 18;          // 16 positions + 2 halo slots per segment
 constexpr int A_SBO = 128;         // bytes between core matrices along M (between slots)
 constexpr int A_LBO = SLOTS * A_SBO;   // bytes between core matrices along K (8-channel chunks)
-constexpr int A_TILE = (BK / 8) * A_LBO;   // one hi (or lo) activation tile
+constexpr int A_TILE = (BK / 8) * A_LBO;   // one hi (or lo) activation tile: 9216 B
 constexpr int A_STAGE = 2 * A_TILE;
+static_assert(A_TILE == TC_U_HALF_BYTES, "engine and kernel disagree on the U tile size");
 constexpr int B_SBO = 128;
 constexpr int B_LBO = (BN / 8) * B_SBO;    // 2048
 constexpr int B_HALF = (BK / 8) * B_LBO;   // 8192: hi (or lo) weight tile of one (tap, k-step)
 constexpr int B_STAGE = 2 * B_HALF;
 static_assert(B_HALF == TC_W_HALF_BYTES, "host packing and kernel disagree");
-constexpr int NA = 2;              // activation ring
-constexpr int NB = 4;              // weight ring
+constexpr int NA = 3;              // activation ring
+constexpr int NB = 3;              // weight ring
 constexpr int N_ITEMS = 8 * SLOTS * (BK / 8);   // 576 16-byte items per activation tile
-constexpr int ITEMS_PER_THREAD = (N_ITEMS + 127) / 128;
 constexpr int SMEM_BYTES = NA * A_STAGE + NB * B_STAGE + 256;
 constexpr int NUM_THREADS = 192;
+constexpr int SPLIT_THREADS = 192;
+static_assert(N_ITEMS % SPLIT_THREADS == 0, "items must divide evenly over the act_split block");
 
 // ---------------------------------------------------------------------------------------------- PTX
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -159,12 +166,69 @@ __device__ __forceinline__ void round8_bf16(const float (&v)[8], uint4& hi) {
     hi = make_uint4(h[0], h[1], h[2], h[3]);
 }
 
-struct Item {      // one 16-byte (8-channel) slot of the activation tile, fixed for the whole K loop
-    int b, t;      // sample / conv-input position (valid only if inb)
-    uint32_t soff; // byte offset inside a hi tile
-    bool live, inb;
-};
+// ------------------------------------------------------------------------------------------------ act_split
+// grid (nks, n_mtiles), block 192.  Item (q, c, r): slot q of segment r, 8-channel chunk c of k-step blockIdx.x.
+// Lanes run over r fastest (8 segments = one 128-byte line of the image), then c: full-line stores, and the 4 lanes
+// of one (q, r) read 128 contiguous bytes of one position.
+template <bool X3>
+__global__ void __launch_bounds__(SPLIT_THREADS) act_split_kernel(const ActSplitParams p) {
+    const int ks = blockIdx.x, m_tile = blockIdx.y;
+    const int spt = p.Tout >> 4;
+    uint8_t* img = p.U + ((size_t)m_tile * p.nks + ks) * A_STAGE;
+    const int Cin = p.C0 + p.C1;
+#pragma unroll
+    for (int j = 0; j < N_ITEMS / SPLIT_THREADS; ++j) {
+        const int idx = threadIdx.x + SPLIT_THREADS * j;
+        const int r = idx & 7, c = (idx >> 3) & 3, q = idx >> 5;
+        const int g = m_tile * 8 + r;
+        const bool segv = g < p.nsegs16;
+        const int b = segv ? g / spt : 0;
+        const int t = (g % spt) * 16 + q - 1;
+        const bool inb = segv && t >= 0 && t < p.Tout;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = 0.f;   // conv zero padding / rows past the batch
+        if (inb) {
+            const int cc = ks * BK + c * 8;
+            const float* src; int ch, Cs;
+            if (cc < p.C0) { src = p.src0; ch = cc; Cs = p.C0; } else { src = p.src1; ch = cc - p.C0; Cs = p.C1; }
+            float a[8], s[8];
+            if (p.scale) {
+                const size_t o = (size_t)b * Cin + cc;
+                const float4 a0 = ldg4(p.scale + o), a1 = ldg4(p.scale + o + 4), s0 = ldg4(p.shift + o), s1 = ldg4(p.shift + o + 4);
+                a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+                s[0] = s0.x; s[1] = s0.y; s[2] = s0.z; s[3] = s0.w; s[4] = s1.x; s[5] = s1.y; s[6] = s1.z; s[7] = s1.w;
+            } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { a[e] = 1.f; s[e] = 0.f; }
+            }
+            const float* base = src + (size_t)b * p.Tin * Cs + ch;
+            if (p.resample == RS_AVGPOOL2) {
+                const float* r0 = base + (size_t)(2 * t) * Cs;
+                const float4 x0 = ldg4(r0), x1 = ldg4(r0 + 4), y0 = ldg4(r0 + Cs), y1 = ldg4(r0 + Cs + 4);
+                const float xa[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+                const float ya[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = 0.5f * (act(xa[e], a[e], s[e], p.silu) + act(ya[e], a[e], s[e], p.silu));
+            } else {
+                const float* r0 = base + (size_t)(p.resample == RS_NEAREST2 ? (t >> 1) : t) * Cs;
+                const float4 x0 = ldg4(r0), x1 = ldg4(r0 + 4);
+                const float xa[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = act(xa[e], a[e], s[e], p.silu);
+            }
+        }
+        const uint32_t off = (uint32_t)(c * A_LBO + q * A_SBO + r * 16);
+        uint4 hi, lo;
+        if (X3) {
+            split8_f16(v, hi, lo);
+            *reinterpret_cast<uint4*>(img + A_TILE + off) = lo;
+        } else round8_bf16(v, hi);
+        *reinterpret_cast<uint4*>(img + off) = hi;
+    }
+}
 
+// ------------------------------------------------------------------------------------------------ conv_tc
 template <bool X3>
 __global__ void __launch_bounds__(NUM_THREADS, 2) conv_tc_kernel(const TcConvParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -181,7 +245,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) conv_tc_kernel(const TcConvPar
     const int spt = p.Tout >> 4;   // 16-position segments per sample
 
     if (tid == 0) {
-        for (int i = 0; i < NA; ++i) { mbar_init(barAfull + 8 * i, 128); mbar_init(barAempty + 8 * i, 1); }
+        for (int i = 0; i < NA; ++i) { mbar_init(barAfull + 8 * i, 1); mbar_init(barAempty + 8 * i, 1); }
         for (int i = 0; i < NB; ++i) { mbar_init(barBfull + 8 * i, 1); mbar_init(barBempty + 8 * i, 1); }
         mbar_init(barAcc, 1);
         fence_mbar_init();
@@ -195,115 +259,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) conv_tc_kernel(const TcConvPar
     const uint32_t tmem = *tmem_slot;
 
     if (warp < 4) {
-        // ================================================================ A producers
-        // Software-pipelined: the raw fp32 rows of k-step ks+1 are in flight (registers) while k-step ks is
-        // transformed and stored, so global-load latency is paid once, not per item.
-        const int c = tid & 3;   // 8-channel chunk inside the k-step
-        Item items[ITEMS_PER_THREAD];
-#pragma unroll
-        for (int j = 0; j < ITEMS_PER_THREAD; ++j) {
-            const int idx = tid + 128 * j;
-            Item it{};
-            it.live = idx < N_ITEMS;
-            const int rq = idx >> 2, q = rq % SLOTS, r = rq / SLOTS;
-            const int g = m_tile * 8 + r;
-            const bool segv = g < p.nsegs16;
-            it.b = segv ? g / spt : 0;
-            it.t = (g % spt) * 16 + q - 1;
-            it.inb = it.live && segv && it.t >= 0 && it.t < p.Tout;
-            it.soff = (uint32_t)(c * A_LBO + q * A_SBO + r * 16);
-            items[j] = it;
-        }
-        // a tile of 8 consecutive segments touches at most two samples when Tout >= 112; otherwise the
-        // GroupNorm scale/shift rows are fetched per item (slow path, tiny T only)
-        const int b_first = (m_tile * 8) / spt;
-        const int b_last = min(m_tile * 8 + 7, p.nsegs16 - 1) / spt;
-        const bool two_b = b_last - b_first <= 1;
-
-        auto seg_of = [&](int ks) -> const TcSeg& { return ks < nks0 ? p.seg[0] : p.seg[1]; };
-        auto chan_of = [&](int ks) { return (ks < nks0 ? ks : ks - nks0) * BK + c * 8; };   // channel inside the virtual concat
-        float4 nxt[ITEMS_PER_THREAD][2];
-        auto prefetch = [&](int ks) {
-            const TcSeg& sg = seg_of(ks);
-            const int cc = chan_of(ks);
-            const float* src; int ch, Cs;
-            if (cc < sg.C0) { src = sg.src0; ch = cc; Cs = sg.C0; } else { src = sg.src1; ch = cc - sg.C0; Cs = sg.C1; }
-            if (sg.resample == RS_AVGPOOL2) return;   // two rows per position: loaded in the transform phase
-#pragma unroll
-            for (int j = 0; j < ITEMS_PER_THREAD; ++j) {
-                const Item& it = items[j];
-                const int tt = sg.resample == RS_NEAREST2 ? (it.t >> 1) : it.t;
-                const float* ptr = src + ch + (it.inb ? ((size_t)it.b * sg.Tin + tt) * Cs : 0);   // always a valid address
-                nxt[j][0] = ldg4(ptr);
-                nxt[j][1] = ldg4(ptr + 4);
-            }
-        };
-        prefetch(0);
-        for (int ks = 0; ks < nks; ++ks) {
-            const int sa = ks % NA;
-            const TcSeg& sg = seg_of(ks);
-            const int cc = chan_of(ks);
-            const int Cin = sg.C0 + sg.C1;
-            float4 cur[ITEMS_PER_THREAD][2];
-#pragma unroll
-            for (int j = 0; j < ITEMS_PER_THREAD; ++j) { cur[j][0] = nxt[j][0]; cur[j][1] = nxt[j][1]; }
-            // GroupNorm scale/shift of this k-step's 8 channels for the (at most two) samples of the tile
-            float a2[2][8], s2[2][8];
-            if (sg.scale && two_b) {
-#pragma unroll
-                for (int w = 0; w < 2; ++w) {
-                    const size_t o = (size_t)(w ? b_last : b_first) * Cin + cc;
-                    const float4 a0 = ldg4(sg.scale + o), a1 = ldg4(sg.scale + o + 4), s0 = ldg4(sg.shift + o), s1 = ldg4(sg.shift + o + 4);
-                    a2[w][0] = a0.x; a2[w][1] = a0.y; a2[w][2] = a0.z; a2[w][3] = a0.w; a2[w][4] = a1.x; a2[w][5] = a1.y; a2[w][6] = a1.z; a2[w][7] = a1.w;
-                    s2[w][0] = s0.x; s2[w][1] = s0.y; s2[w][2] = s0.z; s2[w][3] = s0.w; s2[w][4] = s1.x; s2[w][5] = s1.y; s2[w][6] = s1.z; s2[w][7] = s1.w;
-                }
-            } else {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) { a2[0][e] = a2[1][e] = 1.f; s2[0][e] = s2[1][e] = 0.f; }
-            }
-            if (ks + 1 < nks) prefetch(ks + 1);
-            mbar_wait(barAempty + 8 * sa, ((ks / NA) & 1) ^ 1);
-            uint8_t* tile = smem + sa * A_STAGE;
-#pragma unroll
-            for (int j = 0; j < ITEMS_PER_THREAD; ++j) {
-                const Item& it = items[j];
-                if (!it.live) continue;
-                float a[8], s[8], v[8];
-                const bool hi_b = it.b != b_first;
-#pragma unroll
-                for (int e = 0; e < 8; ++e) { a[e] = hi_b ? a2[1][e] : a2[0][e]; s[e] = hi_b ? s2[1][e] : s2[0][e]; }
-                if (sg.scale && !two_b && it.inb) {   // slow path: per-item rows
-                    const size_t o = (size_t)it.b * Cin + cc;
-                    const float4 a0 = ldg4(sg.scale + o), a1 = ldg4(sg.scale + o + 4), s0 = ldg4(sg.shift + o), s1 = ldg4(sg.shift + o + 4);
-                    a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
-                    s[0] = s0.x; s[1] = s0.y; s[2] = s0.z; s[3] = s0.w; s[4] = s1.x; s[5] = s1.y; s[6] = s1.z; s[7] = s1.w;
-                }
-                if (sg.resample == RS_AVGPOOL2) {
-                    const float* src; int ch, Cs;
-                    if (cc < sg.C0) { src = sg.src0; ch = cc; Cs = sg.C0; } else { src = sg.src1; ch = cc - sg.C0; Cs = sg.C1; }
-                    const float* r0 = src + ch + (it.inb ? ((size_t)it.b * sg.Tin + 2 * it.t) * Cs : 0);
-                    const float4 x0 = ldg4(r0), x1 = ldg4(r0 + 4), y0 = ldg4(r0 + Cs), y1 = ldg4(r0 + Cs + 4);
-                    const float xa[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-                    const float ya[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) v[e] = 0.5f * (act(xa[e], a[e], s[e], sg.silu) + act(ya[e], a[e], s[e], sg.silu));
-                } else {
-                    const float xa[8] = {cur[j][0].x, cur[j][0].y, cur[j][0].z, cur[j][0].w, cur[j][1].x, cur[j][1].y, cur[j][1].z, cur[j][1].w};
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) v[e] = act(xa[e], a[e], s[e], sg.silu);
-                }
-#pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] = it.inb ? v[e] : 0.f;   // conv zero padding / rows past the batch
-                uint4 hi, lo;
-                if (X3) {
-                    split8_f16(v, hi, lo);
-                    *reinterpret_cast<uint4*>(tile + A_TILE + it.soff) = lo;
-                } else round8_bf16(v, hi);
-                *reinterpret_cast<uint4*>(tile + it.soff) = hi;
-            }
-            fence_proxy_async_smem();
-            mbar_arrive(barAfull + 8 * sa);
-        }
         // ================================================================ epilogue
         mbar_wait(barAcc, 0);
         tc_fence_after();
@@ -350,20 +305,24 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) conv_tc_kernel(const TcConvPar
             }
         }
     } else if (warp == 4) {
-        // ================================================================ weight loader (one thread, bulk async copies)
+        // ================================================================ loader (one thread, bulk async copies)
         if (lane == 0) {
-            const uint32_t bytes = X3 ? B_STAGE : B_HALF;
+            const uint32_t a_bytes = X3 ? A_STAGE : A_TILE, b_bytes = X3 ? B_STAGE : B_HALF;
             int it = 0;
             for (int ks = 0; ks < nks; ++ks) {
                 const bool first = ks < nks0;
                 const TcSeg& sg = first ? p.seg[0] : p.seg[1];
                 const int kl = first ? ks : ks - nks0;
+                const int sa = ks % NA;
+                mbar_wait(barAempty + 8 * sa, ((ks / NA) & 1) ^ 1);
+                mbar_arrive_expect_tx(barAfull + 8 * sa, a_bytes);
+                bulk_copy_g2s(sA + sa * A_STAGE, sg.U + ((size_t)m_tile * sg.nks + kl) * A_STAGE, a_bytes, barAfull + 8 * sa);
                 const uint8_t* wsrc = sg.w + ((size_t)n_tile * sg.nks + kl) * sg.taps * B_STAGE;
                 for (int tap = 0; tap < sg.taps; ++tap, ++it) {
                     const int sb = it % NB;
                     mbar_wait(barBempty + 8 * sb, ((it / NB) & 1) ^ 1);
-                    mbar_arrive_expect_tx(barBfull + 8 * sb, bytes);
-                    bulk_copy_g2s(sB + sb * B_STAGE, wsrc + (size_t)tap * B_STAGE, bytes, barBfull + 8 * sb);
+                    mbar_arrive_expect_tx(barBfull + 8 * sb, b_bytes);
+                    bulk_copy_g2s(sB + sb * B_STAGE, wsrc + (size_t)tap * B_STAGE, b_bytes, barBfull + 8 * sb);
                 }
             }
         }
@@ -452,6 +411,17 @@ void pack_conv_tc(const float* w, int Cout, int Cin, int k, bool x3, std::vector
                                 } else hi[o] = bf16_rn(v);
                             }
             }
+}
+
+size_t act_split_bytes(int nsegs16, int Cin) { return (size_t)((nsegs16 + 7) / 8) * (Cin / TC_BK) * A_STAGE; }
+
+cudaError_t launch_act_split(const ActSplitParams& p, bool x3, cudaStream_t st) {
+    if (p.nsegs16 <= 0) return cudaSuccess;
+    dim3 grid(p.nks, (p.nsegs16 + 7) / 8);
+    if (x3) act_split_kernel<true><<<grid, SPLIT_THREADS, 0, st>>>(p);
+    else act_split_kernel<false><<<grid, SPLIT_THREADS, 0, st>>>(p);
+    g_launch_count += 1;
+    return cudaGetLastError();
 }
 
 cudaError_t launch_conv_tc(const TcConvParams& p, bool x3, cudaStream_t st) {

@@ -190,7 +190,7 @@ struct Act {  // channels-last activation [B][T][C]
 using OpFn = std::function<cudaError_t(cudaStream_t)>;
 
 // per-launch bookkeeping for the live profile (eegldm_profile_*): algorithmic FLOPs / HBM bytes
-enum OpKind : int { OP_CONV = 0, OP_GN = 1, OP_ATTN = 2, OP_OTHER = 3, OP_NKIND = 4 };
+enum OpKind : int { OP_CONV = 0, OP_GN = 1, OP_ATTN = 2, OP_OTHER = 3, OP_SPLIT = 4, OP_NKIND = 5 };
 struct OpMeta { int kind; double flops, bytes; };
 
 struct Builder {
@@ -597,16 +597,24 @@ void plan_conv(Builder& bd, ConvParams p, const uint8_t* tw0 = nullptr, const ui
     for (int s = 0; tc && s < p.nseg; ++s)
         tc = conv_tc_eligible(p.seg[s].C0, p.seg[s].C1, p.Cout, p.Tout, p.seg[s].taps, 1);
     if (tc) {
+        const bool x3 = bd.math == EEGLDM_MATH_F16X3_TC;
         TcConvParams q{};
-        for (int s = 0; s < p.nseg; ++s) {
-            const ConvSeg& a = p.seg[s];
-            q.seg[s] = TcSeg{a.src0, a.src1, a.C0, a.C1, a.scale, a.shift, a.silu, a.resample, a.Tin, s == 0 ? tw0 : tw1, a.taps,
-                             (a.C0 + a.C1) / TC_BK};
-        }
         q.nseg = p.nseg; q.Cout = p.Cout; q.Tout = p.Tout; q.nsegs16 = (int)((long long)p.B * p.Tout / 16);
+        std::shared_ptr<Buf> ubuf[2];
+        for (int s = 0; s < p.nseg; ++s) {
+            // pre-pass: GroupNorm apply + SiLU + resample + 16-bit split -> tile images (one pass per conv input)
+            const ConvSeg& a = p.seg[s];
+            const int cin = a.C0 + a.C1;
+            const size_t ub = act_split_bytes(q.nsegs16, cin);
+            ubuf[s] = bd.scratch((ub + 3) / 4);
+            ActSplitParams sp{a.src0, a.src1, a.C0, a.C1, a.scale, a.shift, a.silu, a.resample, a.Tin, p.Tout, q.nsegs16, cin / TC_BK,
+                              reinterpret_cast<uint8_t*>(bd.ptr(ubuf[s]))};
+            bd.add([sp, x3](cudaStream_t st) { return launch_act_split(sp, x3, st); }, 1, OP_SPLIT, 0.0,
+                   4.0 * p.B * (double)a.Tin * cin + (double)ub * (x3 ? 1.0 : 0.5));
+            q.seg[s] = TcSeg{sp.U, s == 0 ? tw0 : tw1, a.taps, cin / TC_BK};
+        }
         q.bias = p.bias; q.temb = p.temb; q.temb_stride = p.temb_stride; q.res = p.res; q.res_mode = p.res_mode; q.res_Tin = p.res_Tin;
         q.out = p.out;
-        const bool x3 = bd.math == EEGLDM_MATH_F16X3_TC;
         bd.add([q, x3](cudaStream_t st) { return launch_conv_tc(q, x3, st); }, 1, OP_CONV, flops, bytes);
         return;
     }
@@ -1143,7 +1151,7 @@ int eegldm_profile_enable(int on) {
     return EEGLDM_OK;
 }
 int eegldm_profile_read(int kind, double* ms, double* flops, double* bytes, int64_t* launches) {
-    if (kind < 0 || kind >= OP_NKIND) return fail(EEGLDM_ERR_INVALID, "kind must be 0 (conv), 1 (groupnorm), 2 (attention) or 3 (other)");
+    if (kind < 0 || kind >= OP_NKIND) return fail(EEGLDM_ERR_INVALID, "kind must be 0 (conv), 1 (groupnorm), 2 (attention), 3 (other) or 4 (activation split)");
     double t = 0, f = 0, b = 0; int64_t n = 0;
     for (auto& r : g_prof) {
         if (r.m.kind != kind) continue;
@@ -1507,16 +1515,21 @@ int eegldm_test_conv(const float* x_dev, const float* scale_dev, const float* sh
     p.res = res_dev; p.res_mode = RS_NONE; p.res_Tin = Tc;
     p.out = out_dev; p.B = B;
     cudaError_t ce;
+    uint8_t* U = nullptr;
     if (tc) {
+        const bool x3 = math == EEGLDM_MATH_F16X3_TC;
         TcConvParams q{};
-        q.seg[0] = TcSeg{x_dev, nullptr, Cin, 0, scale_dev, shift_dev, silu, resample, Tin, reinterpret_cast<const uint8_t*>(wp.at(o_t)), k,
-                         Cin / TC_BK};
         q.nseg = 1; q.Cout = Cout; q.Tout = Tc; q.nsegs16 = (int)((long long)B * Tc / 16);
+        CU(cudaMalloc((void**)&U, act_split_bytes(q.nsegs16, Cin)));
+        ActSplitParams sp{x_dev, nullptr, Cin, 0, scale_dev, shift_dev, silu, resample, Tin, Tc, q.nsegs16, Cin / TC_BK, U};
+        ce = launch_act_split(sp, x3, st);
+        q.seg[0] = TcSeg{U, reinterpret_cast<const uint8_t*>(wp.at(o_t)), k, Cin / TC_BK};
         q.bias = p.bias; q.res = res_dev; q.res_mode = RS_NONE; q.res_Tin = Tc; q.out = out_dev;
-        ce = launch_conv_tc(q, math == EEGLDM_MATH_F16X3_TC, st);
+        if (ce == cudaSuccess) ce = launch_conv_tc(q, x3, st);
     } else ce = launch_conv_simt(p, st);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);   // the temporary weight pool / U are freed on return
+    if (U) cudaFree(U);
     if (ce != cudaSuccess) return cuda_fail(ce, "conv launch");
-    CU(cudaStreamSynchronize(st));   // the temporary weight pool is freed on return
     return EEGLDM_OK;
 }
 

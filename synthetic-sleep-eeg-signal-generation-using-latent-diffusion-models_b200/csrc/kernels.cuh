@@ -72,12 +72,21 @@ cudaError_t launch_conv_simt(const ConvParams& p, cudaStream_t st);
 constexpr int TC_BN = 128;              // output channels per CTA
 constexpr int TC_BK = 32;               // input channels per k-step
 constexpr int TC_W_HALF_BYTES = 8192;   // one 16-bit (hi or lo) weight tile [TC_BN x TC_BK]
-struct TcSeg {
+constexpr int TC_U_HALF_BYTES = 9216;   // one 16-bit (hi or lo) activation tile image [8 seg x 18 slots x TC_BK]
+// act_split: fp32 activations -> tile images U[m_tile][k-step][hi|lo][kc][slot][segment][8 ch]
+struct ActSplitParams {
     const float* src0; const float* src1; int C0, C1;   // (virtual concat of) fp32 sources [B][Tin][C]
-    const float* scale; const float* shift;             // [B][C0+C1] or null
+    const float* scale; const float* shift;             // [B][C0+C1] GroupNorm scale/shift or null
     int silu, resample, Tin;
+    int Tout, nsegs16, nks;                             // conv-input length after resample; B*Tout/16; (C0+C1)/TC_BK
+    uint8_t* U;
+};
+size_t act_split_bytes(int nsegs16, int Cin);
+cudaError_t launch_act_split(const ActSplitParams& p, bool x3, cudaStream_t st);
+struct TcSeg {
+    const uint8_t* U;   // activation tile images written by act_split
     const uint8_t* w;   // packed by pack_conv_tc: [n_tile][k-step][tap][hi|lo] 8 KB blocks
-    int taps, nks;      // nks = (C0+C1)/TC_BK
+    int taps, nks;      // nks = Cin/TC_BK
 };
 struct TcConvParams {
     TcSeg seg[2];
