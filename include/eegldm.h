@@ -176,6 +176,10 @@ int eegldm_test_conv(const float* x_dev, const float* scale_dev, const float* sh
                      const float* w_host, const float* bias_host, const float* res_dev, int B, int Tin, int Cin, int Cout, int k,
                      int math, float* out_dev, void* stream);
 
+/* Test hook: ONE attention launch, QKVAttentionLegacy.forward (unet.py:107-125), on channels-last
+ * qkv [B][T][H*3*ch] (legacy head layout) -> out [B][T][H*ch].  Synchronises the stream. */
+int eegldm_test_attention(const float* qkv_dev, int B, int T, int H, int ch, int math, float* out_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

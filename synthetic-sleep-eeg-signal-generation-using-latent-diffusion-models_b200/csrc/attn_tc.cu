@@ -1,0 +1,301 @@
+// tcgen05 self-attention for the latent UNet (QKVAttentionLegacy.forward, src/models/unet.py:107-125):
+//     w = softmax_fp32( (q * ch^-1/4)^T (k * ch^-1/4) )   over keys,   a = v w^T        per (sample, head)
+// as two tensor-pipe GEMMs around an in-kernel softmax, with the scores never leaving the SM.
+//
+//   qkv_split_kernel   fp32 qkv [B][T][H*3*ch] (legacy head layout, unet.py:116-118) -> fp16 hi/lo images:
+//                        Q, K : [k-step = ch/32][hi|lo][T/8][4][8 pos][8 ch]   (K-major core matrices; a row range is contiguous)
+//                        V    : [ch/128][T/32][hi|lo][4][16][8 key][8 ch]      (MN-major B operand for P.V)
+//   attn_tc_kernel     one CTA per (128-query tile, head, sample):
+//                        S = Q K^T   : M=128, N=T (<=256), K=ch, accumulators in TMEM columns [0,T) and [256,256+T)
+//                        softmax     : 128 threads, one query row each: TMEM -> registers, max, exp2, sum,
+//                                      P = exp(.) split to fp16 hi/lo -> shared memory (K-major core matrices)
+//                        O = P V     : per 128-channel chunk, M=128, N=128, K=T, double-buffered in TMEM;
+//                                      epilogue scales by 1/rowsum and stores fp32 channels-last.
+//   Arithmetic is the same f16x3 scheme as conv_tc.cu (hi*hi | hi*lo + lo*hi in a second accumulator); the
+//   non-X3 instantiation issues hi*hi only (fast mode, not a parity mode).
+#include "kernels.cuh"
+#include "tc_common.cuh"
+
+namespace eegldm {
+using namespace tc;
+namespace {
+
+constexpr int NST = 2;                 // operand stage ring
+constexpr int Q_HALF = 8192;           // 128 rows x 32 ch x 2 B
+constexpr int V_HALF = 8192;           // 32 keys x 128 ch x 2 B
+constexpr int NUM_THREADS = 192;
+
+__host__ __device__ inline int stage_bytes(int T) { return 2 * Q_HALF + 2 * T * 64; }   // Q hi/lo + K hi/lo of one 32-ch k-step
+__host__ __device__ inline int p_half_bytes(int T) { return (T / 8) * 2048; }           // P hi (or lo): [T/8][16][8][8] fp16
+
+// ------------------------------------------------------------------------------------------------ qkv split
+// one thread per (sample, head, q|k|v, 8-channel chunk, position); position fastest so that 8 lanes fill a 128-byte line
+__global__ void qkv_split_kernel(const float* __restrict__ qkv, uint8_t* __restrict__ dst, int T, int H, int ch, size_t total) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int t = (int)(idx % T);
+    size_t rest = idx / T;
+    const int c8 = (int)(rest % (ch / 8)); rest /= (ch / 8);
+    const int which = (int)(rest % 3); rest /= 3;
+    const int h = (int)(rest % H);
+    const size_t b = rest / H;
+    const int c = c8 * 8;
+    const float* src = qkv + ((size_t)b * T + t) * ((size_t)H * 3 * ch) + (size_t)h * 3 * ch + (size_t)which * ch + c;
+    const float4 x0 = __ldg(reinterpret_cast<const float4*>(src)), x1 = __ldg(reinterpret_cast<const float4*>(src + 4));
+    const float v[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+    uint4 hi, lo;
+    split8_f16(v, hi, lo);
+    const size_t plane = (size_t)4 * ch * T;                       // bytes of one of q / k / v (hi + lo)
+    uint8_t* base = dst + ((size_t)b * H + h) * 3 * plane + (size_t)which * plane;
+    size_t ohi, olo;
+    if (which < 2) {   // Q, K: [ks][hi|lo][T/8][4][8][8]
+        const int ks = c / 32, cg = (c % 32) / 8;
+        const size_t o = (size_t)(t / 8) * 512 + cg * 128 + (t % 8) * 16;
+        ohi = ((size_t)ks * 2 + 0) * ((size_t)T * 64) + o;
+        olo = ((size_t)ks * 2 + 1) * ((size_t)T * 64) + o;
+    } else {           // V: [ch/128][T/32][hi|lo][4][16][8][8]
+        const size_t blk = (size_t)(c / 128) * (T / 32) + t / 32;
+        const size_t o = (size_t)((t % 32) / 8) * 2048 + ((c % 128) / 8) * 128 + (t % 8) * 16;
+        ohi = (blk * 2 + 0) * V_HALF + o;
+        olo = (blk * 2 + 1) * V_HALF + o;
+    }
+    *reinterpret_cast<uint4*>(base + ohi) = hi;
+    *reinterpret_cast<uint4*>(base + olo) = lo;
+}
+
+// ------------------------------------------------------------------------------------------------ attention
+template <bool X3>
+__global__ void __launch_bounds__(NUM_THREADS, 1) attn_tc_kernel(const AttnTcParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int T = p.T, ch = p.ch;
+    const int SB = stage_bytes(T), PH = p_half_bytes(T);
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t sStage = sbase, sP = sbase + NST * SB, bars = sP + 2 * PH;
+    const uint32_t barFull = bars, barEmpty = bars + 8 * NST, barS = bars + 16 * NST, barP = barS + 8, barOfull = barP + 8,
+                   barOempty = barOfull + 16;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + NST * SB + 2 * PH + 16 * NST + 48);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int mt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int nks = ch / 32, nchunk = ch / 128, nss = T / 32;
+    const int rows_pg = min(16, T / 8 - mt * 16);   // 8-row groups of this query tile that exist
+    const size_t plane = (size_t)4 * ch * T;
+    const uint8_t* gq = p.qkv16 + ((size_t)b * p.H + h) * 3 * plane;
+    const uint8_t* gk = gq + plane;
+    const uint8_t* gv = gk + plane;
+
+    if (tid == 0) {
+        for (int i = 0; i < NST; ++i) { mbar_init(barFull + 8 * i, 1); mbar_init(barEmpty + 8 * i, 1); }
+        mbar_init(barS, 1);
+        mbar_init(barP, 128);
+        for (int i = 0; i < 2; ++i) { mbar_init(barOfull + 8 * i, 1); mbar_init(barOempty + 8 * i, 128); }
+        fence_mbar_init();
+    }
+    if (warp == 5) tmem_alloc(smem_u32(tmem_slot), 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp < 4) {
+        // ================================================================ softmax, then epilogue
+        const int row = warp * 32 + lane;
+        const int t = mt * 128 + row;
+        const bool rowv = t < T;
+        const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+        mbar_wait(barS, 0);
+        tc_fence_after();
+        float mx = -INFINITY;
+        for (int cb = 0; cb < T; cb += 32) {
+            uint32_t v[32];
+            tmem_ld32(lane_addr + cb, v);
+            if (X3) {
+                uint32_t c2[32];
+                tmem_ld32(lane_addr + 256 + cb, c2);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(fmaf(__uint_as_float(c2[i]), 1.0f / LO_SCALE, __uint_as_float(v[i])));
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+        }
+        float sum = 0.f;
+        const float sc = p.scale_log2e;               // ch^-1/2 * log2(e): scores are (q.k) * ch^-1/2 (unet.py:119-121)
+        const float mxs = mx * sc;
+        uint8_t* prow = smem + NST * SB + (row >> 3) * 128 + (row & 7) * 16;
+        for (int cb = 0; cb < T; cb += 32) {
+            uint32_t v[32];
+            tmem_ld32(lane_addr + cb, v);
+            if (X3) {
+                uint32_t c2[32];
+                tmem_ld32(lane_addr + 256 + cb, c2);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(fmaf(__uint_as_float(c2[i]), 1.0f / LO_SCALE, __uint_as_float(v[i])));
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float e[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    e[i] = exp2f(fmaf(__uint_as_float(v[8 * j + i]), sc, -mxs));
+                    sum += e[i];
+                }
+                uint4 hi, lo;
+                split8_f16(e, hi, lo);
+                uint8_t* dst = prow + (size_t)((cb >> 3) + j) * 2048;
+                *reinterpret_cast<uint4*>(dst) = hi;
+                if (X3) *reinterpret_cast<uint4*>(dst + PH) = lo;
+            }
+        }
+        fence_proxy_async_smem();      // P (generic-proxy stores) -> visible to the tensor core's async proxy
+        tc_fence_before();             // the TMEM reads above are ordered before the MMAs that reuse the columns
+        mbar_arrive(barP);
+        const float inv = 1.0f / sum;
+        float* orow = p.out + ((size_t)b * T + t) * ((size_t)p.H * ch) + (size_t)h * ch;
+        for (int c = 0; c < nchunk; ++c) {
+            const int buf = c & 1;
+            mbar_wait(barOfull + 8 * buf, (c >> 1) & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int cb = 0; cb < 128; cb += 32) {
+                uint32_t v[32];
+                tmem_ld32(lane_addr + buf * 256 + cb, v);
+                if (X3) {
+                    uint32_t c2[32];
+                    tmem_ld32(lane_addr + buf * 256 + 128 + cb, c2);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(fmaf(__uint_as_float(c2[i]), 1.0f / LO_SCALE, __uint_as_float(v[i])));
+                }
+                if (rowv) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        *reinterpret_cast<float4*>(orow + c * 128 + cb + 4 * q) =
+                            make_float4(__uint_as_float(v[4 * q]) * inv, __uint_as_float(v[4 * q + 1]) * inv,
+                                        __uint_as_float(v[4 * q + 2]) * inv, __uint_as_float(v[4 * q + 3]) * inv);
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(barOempty + 8 * buf);
+        }
+    } else if (warp == 4) {
+        // ================================================================ loader
+        if (lane == 0) {
+            int it = 0;
+            const uint32_t qb = (uint32_t)rows_pg * 512, kb = (uint32_t)T * 64;
+            for (int ks = 0; ks < nks; ++ks, ++it) {
+                const int st = it % NST;
+                const uint32_t dst = sStage + st * SB;
+                mbar_wait(barEmpty + 8 * st, ((it / NST) & 1) ^ 1);
+                mbar_arrive_expect_tx(barFull + 8 * st, X3 ? 2 * (qb + kb) : qb + kb);
+                const uint8_t* qs = gq + ((size_t)ks * 2) * kb + (size_t)mt * 16 * 512;
+                const uint8_t* ks_ = gk + ((size_t)ks * 2) * kb;
+                bulk_copy_g2s(dst, qs, qb, barFull + 8 * st);
+                bulk_copy_g2s(dst + 2 * Q_HALF, ks_, kb, barFull + 8 * st);
+                if (X3) {
+                    bulk_copy_g2s(dst + Q_HALF, qs + kb, qb, barFull + 8 * st);
+                    bulk_copy_g2s(dst + 2 * Q_HALF + kb, ks_ + kb, kb, barFull + 8 * st);
+                }
+            }
+            for (int c = 0; c < nchunk; ++c)
+                for (int ss = 0; ss < nss; ++ss, ++it) {
+                    const int st = it % NST;
+                    mbar_wait(barEmpty + 8 * st, ((it / NST) & 1) ^ 1);
+                    const uint32_t bytes = X3 ? 2 * V_HALF : V_HALF;
+                    mbar_arrive_expect_tx(barFull + 8 * st, bytes);
+                    bulk_copy_g2s(sStage + st * SB, gv + ((size_t)c * nss + ss) * 2 * V_HALF, bytes, barFull + 8 * st);
+                }
+        }
+    } else {
+        // ================================================================ MMA issuer
+        if (lane == 0) {
+            const uint32_t idescS = make_idesc(0u, 128u, (uint32_t)T);
+            constexpr uint32_t idescO = make_idesc(0u, 128u, 128u, 1u);   // B (= V) is MN-major
+            int it = 0;
+            uint32_t acc = 0, acc2 = 0;
+            for (int ks = 0; ks < nks; ++ks, ++it) {
+                const int st = it % NST;
+                mbar_wait(barFull + 8 * st, (it / NST) & 1);
+                tc_fence_after();
+                const uint32_t q_hi = sStage + st * SB, q_lo = q_hi + Q_HALF, k_hi = q_hi + 2 * Q_HALF, k_lo = k_hi + T * 64;
+#pragma unroll
+                for (int kk = 0; kk < 2; ++kk) {
+                    const uint64_t dah = make_desc(q_hi + kk * 256, 128, 512), dbh = make_desc(k_hi + kk * 256, 128, 512);
+                    umma_bf16(tmem, dah, dbh, idescS, acc);
+                    acc = 1;
+                    if (X3) {
+                        const uint64_t dal = make_desc(q_lo + kk * 256, 128, 512), dbl = make_desc(k_lo + kk * 256, 128, 512);
+                        umma_bf16(tmem + 256, dah, dbl, idescS, acc2);
+                        umma_bf16(tmem + 256, dal, dbh, idescS, 1);
+                        acc2 = 1;
+                    }
+                }
+                umma_commit(barEmpty + 8 * st);
+            }
+            umma_commit(barS);
+            mbar_wait(barP, 0);
+            tc_fence_after();
+            for (int c = 0; c < nchunk; ++c) {
+                const int buf = c & 1;
+                mbar_wait(barOempty + 8 * buf, ((c >> 1) & 1) ^ 1);
+                tc_fence_after();
+                uint32_t a0 = 0, a1 = 0;
+                for (int ss = 0; ss < nss; ++ss, ++it) {
+                    const int st = it % NST;
+                    mbar_wait(barFull + 8 * st, (it / NST) & 1);
+                    tc_fence_after();
+                    const uint32_t v_hi = sStage + st * SB, v_lo = v_hi + V_HALF;
+#pragma unroll
+                    for (int kk = 0; kk < 2; ++kk) {
+                        const uint32_t po = (uint32_t)(ss * 4 + kk * 2) * 2048;
+                        const uint64_t dah = make_desc(sP + po, 2048, 128), dbh = make_desc(v_hi + kk * 4096, 2048, 128);
+                        umma_bf16(tmem + buf * 256, dah, dbh, idescO, a0);
+                        a0 = 1;
+                        if (X3) {
+                            const uint64_t dal = make_desc(sP + PH + po, 2048, 128), dbl = make_desc(v_lo + kk * 4096, 2048, 128);
+                            umma_bf16(tmem + buf * 256 + 128, dah, dbl, idescO, a1);
+                            umma_bf16(tmem + buf * 256 + 128, dal, dbh, idescO, 1);
+                            a1 = 1;
+                        }
+                    }
+                    umma_commit(barEmpty + 8 * st);
+                }
+                umma_commit(barOfull + 8 * buf);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) tmem_dealloc(tmem, 512);
+}
+
+}  // namespace
+
+bool attn_tc_eligible(int T, int ch) { return T >= 32 && T <= 256 && T % 32 == 0 && ch >= 128 && ch % 128 == 0; }
+size_t attn_qkv16_bytes(int B, int T, int H, int ch) { return (size_t)B * H * 12 * ch * T; }
+
+cudaError_t launch_qkv_split(const float* qkv, uint8_t* dst, int B, int T, int H, int ch, cudaStream_t st) {
+    const size_t total = (size_t)B * H * 3 * (ch / 8) * T;
+    if (!total) return cudaSuccess;
+    qkv_split_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(qkv, dst, T, H, ch, total);
+    g_launch_count += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_attention_tc(const AttnTcParams& p, bool x3, cudaStream_t st) {
+    if (p.B <= 0) return cudaSuccess;
+    const int smem = NST * stage_bytes(p.T) + 2 * p_half_bytes(p.T) + 256;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(attn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    dim3 grid((p.T + 127) / 128, p.H, p.B);
+    if (x3) attn_tc_kernel<true><<<grid, NUM_THREADS, smem, st>>>(p);
+    else attn_tc_kernel<false><<<grid, NUM_THREADS, smem, st>>>(p);
+    g_launch_count += 1;
+    return cudaGetLastError();
+}
+
+}  // namespace eegldm

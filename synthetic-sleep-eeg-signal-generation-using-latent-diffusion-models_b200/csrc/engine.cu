@@ -663,7 +663,20 @@ Act plan_attn(Builder& bd, const ULayer& l, const Act& x) {
         plan_conv(bd, p, l.t_wqkv);
     }
     Act a = bd.act(l.ch, x.T);
-    {
+    const int hch = l.ch / l.heads;
+    if (bd.math != EEGLDM_MATH_FP32_SIMT && attn_tc_eligible(x.T, hch)) {
+        // tensor-pipe attention: split q,k,v into fp16 hi/lo operand images, then S = QK^T -> softmax -> PV in one kernel
+        const bool x3 = bd.math == EEGLDM_MATH_F16X3_TC;
+        auto q16 = bd.scratch((attn_qkv16_bytes(bd.B, x.T, l.heads, hch) + 3) / 4);
+        const float* qsrc = bd.ptr(qkv);
+        uint8_t* qdst = reinterpret_cast<uint8_t*>(bd.ptr(q16));
+        const int B = bd.B, T = x.T, H = l.heads;
+        bd.add([=](cudaStream_t st) { return launch_qkv_split(qsrc, qdst, B, T, H, hch, st); }, 1, OP_SPLIT, 0.0,
+               8.0 * B * (double)T * 3 * l.ch);
+        AttnTcParams tp{qdst, bd.wptr(a), T, H, hch, B, 1.4426950408889634f / sqrtf((float)hch)};
+        bd.add([tp, x3](cudaStream_t st) { return launch_attention_tc(tp, x3, st); }, 1, OP_ATTN,
+               4.0 * B * (double)T * T * l.ch, 4.0 * B * (double)T * l.ch * 4.0);
+    } else {
         AttnParams ap{};
         ap.qkv = bd.ptr(qkv); ap.out = bd.wptr(a); ap.T = x.T; ap.H = l.heads; ap.ch = l.ch / l.heads; ap.B = bd.B;
         bd.add([ap](cudaStream_t st) { return launch_attention_simt(ap, st); }, 1, OP_ATTN,
@@ -1530,6 +1543,28 @@ int eegldm_test_conv(const float* x_dev, const float* scale_dev, const float* sh
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);   // the temporary weight pool / U are freed on return
     if (U) cudaFree(U);
     if (ce != cudaSuccess) return cuda_fail(ce, "conv launch");
+    return EEGLDM_OK;
+}
+
+// One attention launch (QKVAttentionLegacy.forward) on channels-last qkv [B][T][H*3*ch] -> out [B][T][H*ch].
+int eegldm_test_attention(const float* qkv_dev, int B, int T, int H, int ch, int math, float* out_dev, void* stream) {
+    if (!qkv_dev || !out_dev) return fail(EEGLDM_ERR_INVALID, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t ce;
+    uint8_t* q16 = nullptr;
+    if (math != EEGLDM_MATH_FP32_SIMT) {
+        if (!attn_tc_eligible(T, ch)) return fail(EEGLDM_ERR_SHAPE, "shape not eligible for the tcgen05 attention");
+        CU(cudaMalloc((void**)&q16, attn_qkv16_bytes(B, T, H, ch)));
+        ce = launch_qkv_split(qkv_dev, q16, B, T, H, ch, st);
+        AttnTcParams tp{q16, out_dev, T, H, ch, B, 1.4426950408889634f / sqrtf((float)ch)};
+        if (ce == cudaSuccess) ce = launch_attention_tc(tp, math == EEGLDM_MATH_F16X3_TC, st);
+    } else {
+        AttnParams ap{qkv_dev, out_dev, T, H, ch, B};
+        ce = launch_attention_simt(ap, st);
+    }
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+    if (q16) cudaFree(q16);
+    if (ce != cudaSuccess) return cuda_fail(ce, "attention launch");
     return EEGLDM_OK;
 }
 

@@ -103,6 +103,17 @@ cudaError_t launch_conv_tc(const TcConvParams& p, bool x3, cudaStream_t st);
 cudaError_t launch_groupnorm(const GnParams& p, cudaStream_t st);
 int groupnorm_nsplit(int C, int T, int G);
 cudaError_t launch_attention_simt(const AttnParams& p, cudaStream_t st);
+// ---- tcgen05 attention (attn_tc.cu) ----------------------------------------------------------
+struct AttnTcParams {
+    const uint8_t* qkv16;   // fp16 hi/lo images written by launch_qkv_split
+    float* out;             // [B][T][H*ch] fp32
+    int T, H, ch, B;
+    float scale_log2e;      // ch^-1/2 * log2(e)
+};
+bool attn_tc_eligible(int T, int ch);
+size_t attn_qkv16_bytes(int B, int T, int H, int ch);
+cudaError_t launch_qkv_split(const float* qkv, uint8_t* dst, int B, int T, int H, int ch, cudaStream_t st);
+cudaError_t launch_attention_tc(const AttnTcParams& p, bool x3, cudaStream_t st);
 // y[r][o] = bias[o] + sum_i act(x[r][i]) * W[o][i];  act = SiLU if silu_in
 cudaError_t launch_linear(const float* x, const float* W, const float* bias, float* y, int R, int I, int O,
                           int silu_in, cudaStream_t st);

@@ -85,6 +85,7 @@ SIGNATURES = {
     "eegldm_timestep_embedding": (C.c_int, [_FP, C.c_int, C.c_int, _FP]),
     "eegldm_ddim_sample": (C.c_int, [_P, _P, C.POINTER(SchedCfg), _P, C.c_float, C.c_int, _P, C.c_int, C.c_int, _P]),
     "eegldm_test_conv": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "eegldm_test_attention": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
     "eegldm_ddim_sample_host": (C.c_int, [_P, _P, C.POINTER(SchedCfg), _P, C.c_float, C.c_int, _P, C.c_int, C.c_int, _P]),
 }
 

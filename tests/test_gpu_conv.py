@@ -78,3 +78,29 @@ def test_fused_conv_matches_torch(built_lib, cuda_device, case, math):
         assert err < 5e-2, err
     else:                   # fp32 SIMT and f16x3: fp32-level agreement
         torch.testing.assert_close(y, ref, rtol=1e-4, atol=2e-5)
+
+
+ATTN_CASES = [(2, 192, 1, 512), (1, 128, 1, 128), (3, 64, 2, 128), (2, 256, 1, 256), (1, 32, 4, 128)]
+
+
+@pytest.mark.parametrize("math", ["fp32", "f16x3", "bf16"])
+@pytest.mark.parametrize("case", ATTN_CASES)
+def test_attention_matches_torch(built_lib, cuda_device, case, math):
+    """QKVAttentionLegacy.forward (unet.py:107-125) on the legacy [q;k;v]-per-head channel layout."""
+    from eegldm import _lib
+    B, T, H, ch = case
+    g = torch.Generator().manual_seed(T + ch)
+    qkv = torch.randn(B, H * 3 * ch, T, generator=g)                       # reference layout [B, 3C, T]
+    q, k, v = qkv.double().reshape(B * H, 3 * ch, T).split(ch, dim=1)
+    scale = 1.0 / (ch ** 0.25)
+    w = torch.softmax(torch.einsum("bct,bcs->bts", q * scale, k * scale), dim=-1)
+    ref = torch.einsum("bts,bcs->bct", w, v).reshape(B, H * ch, T).float()
+    xd = qkv.transpose(1, 2).contiguous().to(cuda_device)                  # engine layout [B][T][3C]
+    out = torch.full((B, T, H * ch), float("nan"), device=cuda_device)
+    _lib.check(built_lib.eegldm_test_attention(C.c_void_p(xd.data_ptr()), B, T, H, ch, MODES[math], C.c_void_p(out.data_ptr()), None))
+    y = out.cpu().transpose(1, 2)
+    assert torch.isfinite(y).all()
+    if math == "bf16":
+        assert (y - ref).abs().max().item() < 2e-2
+    else:
+        torch.testing.assert_close(y, ref, rtol=1e-4, atol=2e-5)
