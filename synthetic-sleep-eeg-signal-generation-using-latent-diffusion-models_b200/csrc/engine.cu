@@ -581,7 +581,14 @@ struct UNetIO {
     const float* ddim_coef;
 };
 
-void plan_conv(Builder& bd, ConvParams p, const uint8_t* tw0 = nullptr, const uint8_t* tw1 = nullptr) {
+// tcgen05 plumbing between the two convs of a ResBlock: conv1's activation pre-pass also emits the raw twin of x
+// that conv2's skip_connection segment consumes, so x is read once.
+struct TcShare {
+    std::shared_ptr<Buf> raw;   // U image of the raw (resampled) block input
+    bool want_raw = false;      // conv1: produce it;   conv2: consume it for segment 1
+};
+
+void plan_conv(Builder& bd, ConvParams p, const uint8_t* tw0 = nullptr, const uint8_t* tw1 = nullptr, TcShare* share = nullptr) {
     p.B = bd.B;
     double flops = 0, bytes = 4.0 * p.B * (double)p.Tout * p.Cout;   // output write
     for (int s = 0; s < p.nseg; ++s) {
@@ -606,11 +613,20 @@ void plan_conv(Builder& bd, ConvParams p, const uint8_t* tw0 = nullptr, const ui
             const ConvSeg& a = p.seg[s];
             const int cin = a.C0 + a.C1;
             const size_t ub = act_split_bytes(q.nsegs16, cin);
+            if (s == 1 && share && share->raw) {   // raw twin already written by conv1's pre-pass
+                q.seg[s] = TcSeg{reinterpret_cast<const uint8_t*>(bd.ptr(share->raw)), tw1, a.taps, cin / TC_BK};
+                continue;
+            }
             ubuf[s] = bd.scratch((ub + 3) / 4);
+            uint8_t* uraw = nullptr;
+            if (s == 0 && share && share->want_raw) {
+                share->raw = bd.scratch((ub + 3) / 4);
+                uraw = reinterpret_cast<uint8_t*>(bd.ptr(share->raw));
+            }
             ActSplitParams sp{a.src0, a.src1, a.C0, a.C1, a.scale, a.shift, a.silu, a.resample, a.Tin, p.Tout, q.nsegs16, cin / TC_BK,
-                              reinterpret_cast<uint8_t*>(bd.ptr(ubuf[s]))};
+                              reinterpret_cast<uint8_t*>(bd.ptr(ubuf[s])), uraw};
             bd.add([sp, x3](cudaStream_t st) { return launch_act_split(sp, x3, st); }, 1, OP_SPLIT, 0.0,
-                   4.0 * p.B * (double)a.Tin * cin + (double)ub * (x3 ? 1.0 : 0.5));
+                   4.0 * p.B * (double)a.Tin * cin + (double)ub * (x3 ? 1.0 : 0.5) * (uraw ? 2.0 : 1.0));
             q.seg[s] = TcSeg{sp.U, s == 0 ? tw0 : tw1, a.taps, cin / TC_BK};
         }
         q.bias = p.bias; q.temb = p.temb; q.temb_stride = p.temb_stride; q.res = p.res; q.res_mode = p.res_mode; q.res_Tin = p.res_Tin;
@@ -624,6 +640,10 @@ void plan_conv(Builder& bd, ConvParams p, const uint8_t* tw0 = nullptr, const ui
 Act plan_res(Builder& bd, const ULayer& l, const Act& x0, const Act* x1, const UNetIO& io) {
     const int Tc = resampled_len(x0.T, l.mode);
     Act h1 = bd.act(l.cout, Tc);
+    TcShare share;
+    // the skip_connection's operand is produced by conv1's pre-pass when both convs take the tensor-pipe path
+    share.want_raw = bd.math != EEGLDM_MATH_FP32_SIMT && l.cin != l.cout && l.t_w1 && l.t_w2 && l.t_wskip &&
+                     conv_tc_eligible(x0.C, x1 ? x1->C : 0, l.cout, Tc, 3, 1);
     {
         ScaleShift ss = plan_gn(bd, x0, x1, 32, l.g1, l.be1, 1e-6f);
         ConvParams p{};
@@ -631,7 +651,7 @@ Act plan_res(Builder& bd, const ULayer& l, const Act& x0, const Act* x1, const U
         p.nseg = 1; p.Cout = l.cout; p.Tout = Tc; p.Tc = Tc; p.stride = 1; p.pad_left = 1;
         p.bias = l.b1; p.temb = io.temb + l.emb_off; p.temb_stride = io.temb_stride;
         p.out = bd.wptr(h1);
-        plan_conv(bd, p, l.t_w1);
+        plan_conv(bd, p, l.t_w1, nullptr, &share);
     }
     Act y = bd.act(l.cout, Tc);
     {
@@ -647,7 +667,8 @@ Act plan_res(Builder& bd, const ULayer& l, const Act& x0, const Act* x1, const U
             p.res = bd.ptr(x0); p.res_mode = l.mode; p.res_Tin = x0.T;
         }
         p.out = bd.wptr(y);
-        plan_conv(bd, p, l.t_w2, l.t_wskip);
+        share.want_raw = false;
+        plan_conv(bd, p, l.t_w2, l.t_wskip, &share);
     }
     return y;
 }
@@ -1534,7 +1555,7 @@ int eegldm_test_conv(const float* x_dev, const float* scale_dev, const float* sh
         TcConvParams q{};
         q.nseg = 1; q.Cout = Cout; q.Tout = Tc; q.nsegs16 = (int)((long long)B * Tc / 16);
         CU(cudaMalloc((void**)&U, act_split_bytes(q.nsegs16, Cin)));
-        ActSplitParams sp{x_dev, nullptr, Cin, 0, scale_dev, shift_dev, silu, resample, Tin, Tc, q.nsegs16, Cin / TC_BK, U};
+        ActSplitParams sp{x_dev, nullptr, Cin, 0, scale_dev, shift_dev, silu, resample, Tin, Tc, q.nsegs16, Cin / TC_BK, U, nullptr};
         ce = launch_act_split(sp, x3, st);
         q.seg[0] = TcSeg{U, reinterpret_cast<const uint8_t*>(wp.at(o_t)), k, Cin / TC_BK};
         q.bias = p.bias; q.res = res_dev; q.res_mode = RS_NONE; q.res_Tin = Tc; q.out = out_dev;

@@ -80,6 +80,7 @@ struct ActSplitParams {
     int silu, resample, Tin;
     int Tout, nsegs16, nks;                             // conv-input length after resample; B*Tout/16; (C0+C1)/TC_BK
     uint8_t* U;
+    uint8_t* U_raw;   // optional second image: the same rows WITHOUT affine / SiLU (skip_connection operand, unet.py:327)
 };
 size_t act_split_bytes(int nsegs16, int Cin);
 cudaError_t launch_act_split(const ActSplitParams& p, bool x3, cudaStream_t st);
