@@ -57,6 +57,8 @@ int64_t eegldm_launch_count(void);
  * milliseconds, the ALGORITHMIC flops and HBM bytes and the launch count since enable. */
 int eegldm_profile_enable(int on);
 int eegldm_profile_read(int kind, double* ms, double* flops, double* bytes, int64_t* launches);
+/* the i-th recorded launch (in launch order) since enable; returns EEGLDM_ERR_INVALID past the end */
+int eegldm_profile_record(int i, int* kind, double* ms, double* flops, double* bytes);
 
 /* ------------------------------------------------------------------------------------------------
  * Denoiser: replaces UNetModel (src/models/unet.py:330-563).  Fields mirror the constructor kwargs

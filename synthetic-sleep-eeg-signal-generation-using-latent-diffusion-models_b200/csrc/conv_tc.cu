@@ -43,7 +43,6 @@ using namespace tc;
 namespace {
 
 constexpr int BM = 128;            // output positions per CTA (8 segments x 16)
-constexpr int BN = TC_BN;          // output channels per CTA
 constexpr int BK = TC_BK;          // input channels per k-step
 constexpr int SLOTS = 18;          // 16 positions + 2 halo slots per segment
 constexpr int A_SBO = 128;         // bytes between core matrices along M (between slots)
@@ -52,14 +51,11 @@ constexpr int A_TILE = (BK / 8) * A_LBO;   // one hi (or lo) activation tile: 92
 constexpr int A_STAGE = 2 * A_TILE;
 static_assert(A_TILE == TC_U_HALF_BYTES, "engine and kernel disagree on the U tile size");
 constexpr int B_SBO = 128;
-constexpr int B_LBO = (BN / 8) * B_SBO;    // 2048
-constexpr int B_HALF = (BK / 8) * B_LBO;   // 8192: hi (or lo) weight tile of one (tap, k-step)
-constexpr int B_STAGE = 2 * B_HALF;
-static_assert(B_HALF == TC_W_HALF_BYTES, "host packing and kernel disagree");
 constexpr int NA = 4;              // activation ring (18 KB stages)
-constexpr int NB = 8;              // weight ring (16 KB stages)
+constexpr int B_RING_BYTES = 128 * 1024;   // weight ring: 4 x 32 KB (N=256) or 8 x 16 KB (N=128)
 constexpr int N_ITEMS = 8 * SLOTS * (BK / 8);   // 576 16-byte items per activation tile
-constexpr int SMEM_BYTES = NA * A_STAGE + NB * B_STAGE + 256;
+constexpr int STAGING_OFF = NA * A_STAGE + B_RING_BYTES + 256;   // 4 warps x [32][33] fp32 epilogue transpose buffers
+constexpr int SMEM_BYTES = STAGING_OFF + 4 * 32 * 33 * 4;
 constexpr int NUM_THREADS = 192;
 constexpr int SPLIT_THREADS = 192;
 static_assert(N_ITEMS % SPLIT_THREADS == 0, "items must divide evenly over the act_split block");
@@ -147,8 +143,12 @@ __global__ void __launch_bounds__(SPLIT_THREADS) act_split_kernel(const ActSplit
 // ------------------------------------------------------------------------------------------------ conv_tc
 // Persistent: one CTA per SM walks tiles (n_tile fastest, so concurrently running CTAs share activation tiles in L2);
 // two TMEM accumulator sets, so the epilogue of tile i overlaps the mainloop of tile i+1.
-template <bool X3>
+template <bool X3, int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const TcConvParams p) {
+    constexpr int B_LBO = (BN / 8) * B_SBO;    // bytes between 8-channel K chunks of the weight tile
+    constexpr int B_HALF = (BK / 8) * B_LBO;   // hi (or lo) weight tile of one (tap, k-step): BN x 32 x 2 B
+    constexpr int B_STAGE = 2 * B_HALF;
+    constexpr int NB = B_RING_BYTES / B_STAGE;
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t sbase = smem_u32(smem);
     const uint32_t sA = sbase, sB = sbase + NA * A_STAGE;
@@ -170,7 +170,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const TcConvPar
         fence_mbar_init();
     }
     constexpr uint32_t ACC_COLS = X3 ? 2 * BN : BN;    // X3: accumulator 0 = hi*hi, accumulator 1 = cross terms * 2^11
-    constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;       // two sets
+    constexpr int NSETS = ACC_COLS * 2 <= 512 ? 2 : 1; // N=256 in f16x3 fills TMEM: no epilogue overlap (used for long K only)
+    constexpr uint32_t TMEM_COLS = NSETS * ACC_COLS;
     constexpr uint32_t IDESC = make_idesc(X3 ? 0u : 1u, BM, BN);
     if (warp == 5) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
     tc_fence_before();
@@ -180,54 +181,78 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const TcConvPar
 
     if (warp < 4) {
         // ================================================================ epilogue
-        const int row = warp * 32 + lane;          // TMEM lane = M row
-        const int r = row & 7, m = row >> 3;       // segment / offset inside the segment
+        // TMEM gives each thread one M row (32 columns per load).  The 32x32 block is transposed through a padded
+        // per-warp staging buffer so that global loads (residual, time embedding) and stores are 128-byte row segments:
+        // lane -> (row 4*i + lane/8, columns 4*(lane%8)..+3), i = 0..7.
+        float* stg = reinterpret_cast<float*>(smem + STAGING_OFF) + warp * (32 * 33);
+        const int col4 = (lane & 7) * 4;
         int lt = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++lt) {
             const int n_tile = tile % n_ntiles, m_tile = tile / n_ntiles;
-            const int as = lt & 1;
-            const int g = m_tile * 8 + r;
-            const bool rowv = g < p.nsegs16;
-            const int b = rowv ? g / spt : 0;
-            const int t = (g % spt) * 16 + m;
+            const int as = lt % NSETS, use = lt / NSETS;
             const int co0 = n_tile * BN;
-            float* orow = p.out + ((size_t)b * p.Tout + t) * p.Cout + co0;
-            const float* tb = p.temb ? p.temb + (size_t)b * p.temb_stride + co0 : nullptr;
-            const float* bs = p.bias ? p.bias + co0 : nullptr;
-            const float *res0 = nullptr, *res1 = nullptr;
-            if (p.res) {
-                const float* rb = p.res + (size_t)b * p.res_Tin * p.Cout + co0;
-                if (p.res_mode == RS_AVGPOOL2) { res0 = rb + (size_t)(2 * t) * p.Cout; res1 = res0 + p.Cout; }
-                else res0 = rb + (size_t)(p.res_mode == RS_NEAREST2 ? (t >> 1) : t) * p.Cout;
+            int rb[8], rt[8];   // sample / position of this thread's 8 rows (rb < 0: row past the batch)
+            size_t ooff[8], roff[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int grow = warp * 32 + 4 * i + (lane >> 3);   // M row = TMEM lane
+                const int g = m_tile * 8 + (grow & 7);              // segment
+                rb[i] = g < p.nsegs16 ? g / spt : -1;
+                rt[i] = (g % spt) * 16 + (grow >> 3);
+                const int bb = max(rb[i], 0), t = rt[i];            // clamped: loads stay in bounds, stores are predicated
+                ooff[i] = ((size_t)bb * p.Tout + t) * p.Cout + co0 + col4;
+                const int tr = p.res_mode == RS_AVGPOOL2 ? 2 * t : (p.res_mode == RS_NEAREST2 ? (t >> 1) : t);
+                roff[i] = ((size_t)bb * p.res_Tin + tr) * p.Cout + co0 + col4;
             }
-            mbar_wait(barAccFull + 8 * as, (lt >> 1) & 1);
+            // residual rows of one 32-column chunk, all 8 loads in flight at once (prefetched one chunk ahead)
+            auto load_res = [&](int cb, float4 (&R)[8]) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (p.res_mode == RS_AVGPOOL2) {
+                        const float4 x0 = ldg4(p.res + roff[i] + cb), x1 = ldg4(p.res + roff[i] + p.Cout + cb);
+                        R[i] = make_float4(0.5f * (x0.x + x1.x), 0.5f * (x0.y + x1.y), 0.5f * (x0.z + x1.z), 0.5f * (x0.w + x1.w));
+                    } else R[i] = ldg4(p.res + roff[i] + cb);
+                }
+            };
+            float4 Rn[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) Rn[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.res) load_res(0, Rn);
+            mbar_wait(barAccFull + 8 * as, use & 1);
             tc_fence_after();
             const uint32_t acc_addr = tmem + ((uint32_t)(warp * 32) << 16) + as * ACC_COLS;
 #pragma unroll 1
             for (int cb = 0; cb < BN; cb += 32) {
+                float4 R[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) R[i] = Rn[i];
+                if (p.res && cb + 32 < BN) load_res(cb + 32, Rn);
                 uint32_t v[32];
-                tmem_ld32(acc_addr + (uint32_t)cb, v);   // warp-collective: no divergence before this
+                tmem_ld32(acc_addr + (uint32_t)cb, v);
                 if (X3) {
                     uint32_t c2[32];
                     tmem_ld32(acc_addr + (uint32_t)(BN + cb), c2);
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(fmaf(__uint_as_float(c2[i]), 1.0f / LO_SCALE, __uint_as_float(v[i])));
                 }
-                if (!rowv) continue;
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    float4 o = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
-                                           __uint_as_float(v[4 * q + 3]));
-                    const int co = cb + 4 * q;
-                    if (bs) { const float4 x = ldg4(bs + co); o.x += x.x; o.y += x.y; o.z += x.z; o.w += x.w; }
-                    if (tb) { const float4 x = ldg4(tb + co); o.x += x.x; o.y += x.y; o.z += x.z; o.w += x.w; }
-                    if (res0) {
-                        float4 x = ldg4(res0 + co);
-                        if (res1) { const float4 y = ldg4(res1 + co); x.x = 0.5f * (x.x + y.x); x.y = 0.5f * (x.y + y.y); x.z = 0.5f * (x.z + y.z); x.w = 0.5f * (x.w + y.w); }
-                        o.x += x.x; o.y += x.y; o.z += x.z; o.w += x.w;
-                    }
-                    *reinterpret_cast<float4*>(orow + co) = o;
+                for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(v[j]);
+                __syncwarp();
+                const int co = co0 + cb + col4;
+                float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p.bias) bias4 = ldg4(p.bias + co);
+                float4 Tm[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    Tm[i] = p.temb ? ldg4(p.temb + (size_t)max(rb[i], 0) * p.temb_stride + co) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float* sp = stg + (4 * i + (lane >> 3)) * 33 + col4;
+                    const float4 o = make_float4(sp[0] + bias4.x + Tm[i].x + R[i].x, sp[1] + bias4.y + Tm[i].y + R[i].y,
+                                                 sp[2] + bias4.z + Tm[i].z + R[i].z, sp[3] + bias4.w + Tm[i].w + R[i].w);
+                    if (rb[i] >= 0) *reinterpret_cast<float4*>(p.out + ooff[i] + cb) = o;
                 }
+                __syncwarp();   // staging buffer is reused by the next chunk
             }
             tc_fence_before();
             mbar_arrive(barAccEmpty + 8 * as);   // this accumulator set may be overwritten
@@ -262,9 +287,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const TcConvPar
         if (lane == 0) {
             int ia = 0, ib = 0, lt = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++lt) {
-                const int as = lt & 1;
+                const int as = lt % NSETS, use = lt / NSETS;
                 const uint32_t d0 = tmem + as * ACC_COLS, d1 = d0 + BN;
-                mbar_wait(barAccEmpty + 8 * as, ((lt >> 1) & 1) ^ 1);   // epilogue has drained this set
+                mbar_wait(barAccEmpty + 8 * as, (use & 1) ^ 1);   // epilogue has drained this set
                 tc_fence_after();
                 uint32_t accum = 0, accum2 = 0;
                 for (int ks = 0; ks < nks; ++ks, ++ia) {
@@ -319,28 +344,34 @@ float f16_to_f(uint16_t h) { return __half2float(__ushort_as_half(h)); }
 }  // namespace
 
 bool conv_tc_eligible(int Cin0, int Cin1, int Cout, int Tout, int taps, int stride) {
-    return stride == 1 && (taps == 1 || taps == 3) && Cin0 > 0 && Cin0 % TC_BK == 0 && Cin1 % TC_BK == 0 && Cout % TC_BN == 0 &&
+    return stride == 1 && (taps == 1 || taps == 3) && Cin0 > 0 && Cin0 % TC_BK == 0 && Cin1 % TC_BK == 0 && Cout % 128 == 0 &&
            Tout > 0 && Tout % 16 == 0;
 }
 
-// [Cout][Cin][k] fp32 -> per (n_tile, k-step, tap): [hi 8 KB | lo 8 KB], each the shared-memory image
-//   byte(kc, ng, r, e) = kc*2048 + ng*128 + r*16 + e*2   for  co = n_tile*128 + ng*8 + r,  ci = ks*32 + kc*8 + e
-// x3: hi = fp16(w), lo = fp16((w - hi) * 2^11);  otherwise hi = bf16(w), lo = 0 (never read).
-void pack_conv_tc(const float* w, int Cout, int Cin, int k, bool x3, std::vector<uint16_t>& out) {
-    const int nt = Cout / TC_BN, nks = Cin / TC_BK;
-    out.assign((size_t)nt * nks * k * (2 * TC_W_HALF_BYTES / 2), 0);
+// Output channels per CTA tile.  N=256 halves the shared-memory operand traffic per MMA (the N=128 shape reads
+// 128 B/cycle and is smem-bound near 65 % of the tensor peak) but, with the second f16x3 accumulator, fills TMEM, so the
+// epilogue no longer overlaps the next mainloop: use it when the mainloop is long (>= 24 weight stages per tile).
+int conv_tc_bn(int Cout, int weight_stages) { return (Cout % 256 == 0 && weight_stages >= 24) ? 256 : 128; }
+
+// [Cout][Cin][k] fp32 -> per (n_tile, k-step, tap): [hi | lo] halves of bn*64 bytes, each the shared-memory image
+//   byte(kc, ng, r, e) = kc*(bn*16) + ng*128 + r*16 + e*2   for  co = n_tile*bn + ng*8 + r,  ci = ks*32 + kc*8 + e
+// x3: hi = fp16(w), lo = fp16((w - hi) * 2^11);  otherwise hi = bf16(w), lo unused.
+void pack_conv_tc(const float* w, int Cout, int Cin, int k, int bn, bool x3, std::vector<uint16_t>& out) {
+    const int nt = Cout / bn, nks = Cin / TC_BK;
+    const size_t half = (size_t)bn * TC_BK;   // u16 elements per half
+    out.assign((size_t)nt * nks * k * 2 * half, 0);
     for (int n = 0; n < nt; ++n)
         for (int ks = 0; ks < nks; ++ks)
             for (int tap = 0; tap < k; ++tap) {
-                uint16_t* hi = out.data() + (((size_t)n * nks + ks) * k + tap) * TC_W_HALF_BYTES;   // 2 halves of HALF/2 u16
-                uint16_t* lo = hi + TC_W_HALF_BYTES / 2;
+                uint16_t* hi = out.data() + (((size_t)n * nks + ks) * k + tap) * 2 * half;
+                uint16_t* lo = hi + half;
                 for (int kc = 0; kc < TC_BK / 8; ++kc)
-                    for (int ng = 0; ng < TC_BN / 8; ++ng)
+                    for (int ng = 0; ng < bn / 8; ++ng)
                         for (int r = 0; r < 8; ++r)
                             for (int e = 0; e < 8; ++e) {
-                                const int co = n * TC_BN + ng * 8 + r, ci = ks * TC_BK + kc * 8 + e;
+                                const int co = n * bn + ng * 8 + r, ci = ks * TC_BK + kc * 8 + e;
                                 const float v = w[((size_t)co * Cin + ci) * k + tap];
-                                const size_t o = (size_t)kc * 1024 + ng * 64 + r * 8 + e;
+                                const size_t o = (size_t)kc * (bn * 8) + ng * 64 + r * 8 + e;
                                 if (x3) {
                                     const uint16_t h = f16_rn(v);
                                     hi[o] = h;
@@ -365,9 +396,10 @@ cudaError_t launch_conv_tc(const TcConvParams& p, bool x3, cudaStream_t st) {
     if (p.nsegs16 <= 0) return cudaSuccess;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<false, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
@@ -377,10 +409,16 @@ cudaError_t launch_conv_tc(const TcConvParams& p, bool x3, cudaStream_t st) {
         cudaGetDevice(&dev);
         if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
     }
-    const int ntiles = (p.Cout / BN) * ((p.nsegs16 + 7) / 8);
+    if (p.bn != 128 && p.bn != 256) return cudaErrorInvalidValue;
+    const int ntiles = (p.Cout / p.bn) * ((p.nsegs16 + 7) / 8);
     dim3 grid(ntiles < num_sms ? ntiles : num_sms);   // persistent: one CTA per SM
-    if (x3) conv_tc_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(p);
-    else conv_tc_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(p);
+    if (p.bn == 256) {
+        if (x3) conv_tc_kernel<true, 256><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(p);
+        else conv_tc_kernel<false, 256><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(p);
+    } else {
+        if (x3) conv_tc_kernel<true, 128><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(p);
+        else conv_tc_kernel<false, 128><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(p);
+    }
     g_launch_count += 1;
     return cudaGetLastError();
 }

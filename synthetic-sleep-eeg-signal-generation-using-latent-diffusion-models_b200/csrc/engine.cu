@@ -473,27 +473,30 @@ int finalize_unet(eegldm_unet* h) {
     h->emb_total = (int)embb.size();
     const size_t o_embw = wp.push(embw), o_embb = wp.push(embb);
     // tcgen05 images: bf16 hi/lo split, packed as shared-memory stage images (conv_tc.cu)
-    auto tc_pack = [&](const std::string& name, int cout, int cin, int k, size_t& off, bool& has) {
+    auto tc_pack = [&](const std::string& name, int cout, int cin, int k, int stages, size_t& off, bool& has) {
         has = h->math != EEGLDM_MATH_FP32_SIMT && conv_tc_eligible(cin, 0, cout, 16, k, 1);
         if (!has) return;
         std::vector<uint16_t> img;
-        pack_conv_tc(ps.get(name).data(), cout, cin, k, h->math == EEGLDM_MATH_F16X3_TC, img);
+        pack_conv_tc(ps.get(name).data(), cout, cin, k, conv_tc_bn(cout, stages), h->math == EEGLDM_MATH_F16X3_TC, img);
         off = wp.push_u16(img);
     };
     for_each_layer(h, [&](ULayer& l) {
         const std::string& p = l.prefix;
         switch (l.kind) {
-            case ULayer::RES:
-                tc_pack(p + ".in_layers.2.weight", l.cout, l.cin, 3, l.ot_w1, l.h_w1);
-                tc_pack(p + ".out_layers.3.weight", l.cout, l.cout, 3, l.ot_w2, l.h_w2);
-                if (l.cin != l.cout) tc_pack(p + ".skip_connection.weight", l.cout, l.cin, 1, l.ot_wskip, l.h_wskip);
+            case ULayer::RES: {
+                // weight stages per tile = sum over K segments of (Cin/32)*taps; conv2 and its skip segment share one tile shape
+                const int st1 = l.cin / TC_BK * 3, st2 = l.cout / TC_BK * 3 + (l.cin != l.cout ? l.cin / TC_BK : 0);
+                tc_pack(p + ".in_layers.2.weight", l.cout, l.cin, 3, st1, l.ot_w1, l.h_w1);
+                tc_pack(p + ".out_layers.3.weight", l.cout, l.cout, 3, st2, l.ot_w2, l.h_w2);
+                if (l.cin != l.cout) tc_pack(p + ".skip_connection.weight", l.cout, l.cin, 1, st2, l.ot_wskip, l.h_wskip);
                 break;
+            }
             case ULayer::ATTN:
-                tc_pack(p + ".qkv.weight", 3 * l.ch, l.ch, 1, l.ot_wqkv, l.h_wqkv);
-                tc_pack(p + ".proj_out.weight", l.ch, l.ch, 1, l.ot_wproj, l.h_wproj);
+                tc_pack(p + ".qkv.weight", 3 * l.ch, l.ch, 1, l.ch / TC_BK, l.ot_wqkv, l.h_wqkv);
+                tc_pack(p + ".proj_out.weight", l.ch, l.ch, 1, l.ch / TC_BK, l.ot_wproj, l.h_wproj);
                 break;
             case ULayer::UP:
-                if (l.use_conv) tc_pack(p + ".conv.weight", l.ch, l.ch, 3, l.ot_w1, l.h_w1);
+                if (l.use_conv) tc_pack(p + ".conv.weight", l.ch, l.ch, 3, l.ch / TC_BK * 3, l.ot_w1, l.h_w1);
                 break;
             default: break;
         }
@@ -607,6 +610,9 @@ void plan_conv(Builder& bd, ConvParams p, const uint8_t* tw0 = nullptr, const ui
         const bool x3 = bd.math == EEGLDM_MATH_F16X3_TC;
         TcConvParams q{};
         q.nseg = p.nseg; q.Cout = p.Cout; q.Tout = p.Tout; q.nsegs16 = (int)((long long)p.B * p.Tout / 16);
+        int stages = 0;
+        for (int s = 0; s < p.nseg; ++s) stages += (p.seg[s].C0 + p.seg[s].C1) / TC_BK * p.seg[s].taps;
+        q.bn = conv_tc_bn(p.Cout, stages);   // must match the packing done in finalize_unet
         std::shared_ptr<Buf> ubuf[2];
         for (int s = 0; s < p.nseg; ++s) {
             // pre-pass: GroupNorm apply + SiLU + resample + 16-bit split -> tile images (one pass per conv input)
@@ -1184,6 +1190,15 @@ int eegldm_profile_enable(int on) {
     g_profile = on != 0;
     return EEGLDM_OK;
 }
+int eegldm_profile_record(int i, int* kind, double* ms, double* flops, double* bytes) {
+    if (i < 0 || i >= (int)g_prof.size()) return fail(EEGLDM_ERR_INVALID, "record index out of range");
+    ProfRec& r = g_prof[i];
+    CU(cudaEventSynchronize(r.e1));
+    float dt = 0.f;
+    CU(cudaEventElapsedTime(&dt, r.e0, r.e1));
+    if (kind) *kind = r.m.kind; if (ms) *ms = dt; if (flops) *flops = r.m.flops; if (bytes) *bytes = r.m.bytes;
+    return EEGLDM_OK;
+}
 int eegldm_profile_read(int kind, double* ms, double* flops, double* bytes, int64_t* launches) {
     if (kind < 0 || kind >= OP_NKIND) return fail(EEGLDM_ERR_INVALID, "kind must be 0 (conv), 1 (groupnorm), 2 (attention), 3 (other) or 4 (activation split)");
     double t = 0, f = 0, b = 0; int64_t n = 0;
@@ -1537,7 +1552,7 @@ int eegldm_test_conv(const float* x_dev, const float* scale_dev, const float* sh
     if (tc) {
         if (!conv_tc_eligible(Cin, 0, Cout, Tc, k, 1)) return fail(EEGLDM_ERR_SHAPE, "shape not eligible for the tcgen05 path");
         std::vector<uint16_t> img;
-        pack_conv_tc(w.data(), Cout, Cin, k, math == EEGLDM_MATH_F16X3_TC, img);
+        pack_conv_tc(w.data(), Cout, Cin, k, conv_tc_bn(Cout, Cin / TC_BK * k), math == EEGLDM_MATH_F16X3_TC, img);
         o_t = wp.push_u16(img);
     }
     int r = wp.upload();
@@ -1554,6 +1569,7 @@ int eegldm_test_conv(const float* x_dev, const float* scale_dev, const float* sh
         const bool x3 = math == EEGLDM_MATH_F16X3_TC;
         TcConvParams q{};
         q.nseg = 1; q.Cout = Cout; q.Tout = Tc; q.nsegs16 = (int)((long long)B * Tc / 16);
+        q.bn = conv_tc_bn(Cout, Cin / TC_BK * k);
         CU(cudaMalloc((void**)&U, act_split_bytes(q.nsegs16, Cin)));
         ActSplitParams sp{x_dev, nullptr, Cin, 0, scale_dev, shift_dev, silu, resample, Tin, Tc, q.nsegs16, Cin / TC_BK, U, nullptr};
         ce = launch_act_split(sp, x3, st);

@@ -69,9 +69,7 @@ struct AttnParams {
 cudaError_t launch_conv_simt(const ConvParams& p, cudaStream_t st);
 
 // ---- tcgen05 path (conv_tc.cu) ---------------------------------------------------------------
-constexpr int TC_BN = 128;              // output channels per CTA
 constexpr int TC_BK = 32;               // input channels per k-step
-constexpr int TC_W_HALF_BYTES = 8192;   // one 16-bit (hi or lo) weight tile [TC_BN x TC_BK]
 constexpr int TC_U_HALF_BYTES = 9216;   // one 16-bit (hi or lo) activation tile image [8 seg x 18 slots x TC_BK]
 // act_split: fp32 activations -> tile images U[m_tile][k-step][hi|lo][kc][slot][segment][8 ch]
 struct ActSplitParams {
@@ -86,20 +84,22 @@ size_t act_split_bytes(int nsegs16, int Cin);
 cudaError_t launch_act_split(const ActSplitParams& p, bool x3, cudaStream_t st);
 struct TcSeg {
     const uint8_t* U;   // activation tile images written by act_split
-    const uint8_t* w;   // packed by pack_conv_tc: [n_tile][k-step][tap][hi|lo] 8 KB blocks
+    const uint8_t* w;   // packed by pack_conv_tc: [n_tile][k-step][tap][hi|lo] blocks of bn*64 bytes
     int taps, nks;      // nks = Cin/TC_BK
 };
 struct TcConvParams {
     TcSeg seg[2];
     int nseg;
     int Cout, Tout;     // stride 1, "same" padding: conv-input length == Tout
+    int bn;             // output channels per CTA tile the weights were packed for (conv_tc_bn)
     int nsegs16;        // B*Tout/16 segments of 16 positions (8 per CTA)
     const float* bias; const float* temb; int temb_stride;
     const float* res; int res_mode; int res_Tin;
     float* out;
 };
 bool conv_tc_eligible(int Cin0, int Cin1, int Cout, int Tout, int taps, int stride);
-void pack_conv_tc(const float* w, int Cout, int Cin, int k, bool x3, std::vector<uint16_t>& out);
+int conv_tc_bn(int Cout, int weight_stages);   // weight_stages = sum over segments of (Cin/32)*taps
+void pack_conv_tc(const float* w, int Cout, int Cin, int k, int bn, bool x3, std::vector<uint16_t>& out);
 cudaError_t launch_conv_tc(const TcConvParams& p, bool x3, cudaStream_t st);
 cudaError_t launch_groupnorm(const GnParams& p, cudaStream_t st);
 int groupnorm_nsplit(int C, int T, int G);

@@ -55,6 +55,9 @@ CASES = [
     (2, 32, 128, 384, 3, True, 2, True),       # nearest x2 folded into the load
     (5, 16, 512, 512, 1, False, 0, True),
     (2, 768, 384, 128, 3, True, 0, False),
+    (2, 64, 512, 256, 3, True, 0, True),       # long K -> 256-channel tiles (single TMEM accumulator set)
+    (3, 48, 256, 512, 3, False, 0, False),
+    (2, 192, 1024, 512, 1, True, 0, True),
 ]
 
 
