@@ -51,6 +51,10 @@ const char* eegldm_version(void);
 /* number of CUDA kernels launched by this library since process start (bench.py's gpu_launches) */
 int64_t eegldm_launch_count(void);
 
+/* Tuning knob of the tcgen05 conv kernel: CTAs per thread-block cluster that share each weight stage through a
+ * multicast bulk copy (1, 2 or 4; default 2).  Changing it invalidates nothing but must not race with launches. */
+int eegldm_set_conv_cluster(int ctas);
+
 /* Live per-kernel profile (bench.py's roofline leg).  While enabled, every launch made outside CUDA-graph
  * capture is bracketed by CUDA events on the launching stream.  eegldm_profile_read sums, for one kernel
  * family (0 = conv implicit-GEMM, 1 = GroupNorm statistics, 2 = attention, 3 = other, 4 = activation split pre-pass), the measured

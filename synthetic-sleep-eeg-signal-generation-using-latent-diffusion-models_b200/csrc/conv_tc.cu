@@ -143,7 +143,9 @@ __global__ void __launch_bounds__(SPLIT_THREADS) act_split_kernel(const ActSplit
 // ------------------------------------------------------------------------------------------------ conv_tc
 // Persistent: one CTA per SM walks tiles (n_tile fastest, so concurrently running CTAs share activation tiles in L2);
 // two TMEM accumulator sets, so the epilogue of tile i overlaps the mainloop of tile i+1.
-template <bool X3, int BN>
+// CL CTAs of a cluster work on CL consecutive M tiles of the same N tile: the weight stage is identical for all of them,
+// so each CTA fetches 1/CL of it and multicasts it to the whole cluster (L2 -> SM weight traffic / CL).
+template <bool X3, int BN, int CL>
 __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const TcConvParams p) {
     constexpr int B_LBO = (BN / 8) * B_SBO;    // bytes between 8-channel K chunks of the weight tile
     constexpr int B_HALF = (BK / 8) * B_LBO;   // hi (or lo) weight tile of one (tap, k-step): BN x 32 x 2 B
@@ -161,11 +163,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const TcConvPar
     const int nks0 = p.seg[0].nks, nks = nks0 + (p.nseg > 1 ? p.seg[1].nks : 0);
     const int spt = p.Tout >> 4;   // 16-position segments per sample
     const int n_ntiles = p.Cout / BN;
-    const int ntiles = n_ntiles * ((p.nsegs16 + 7) / 8);
+    const int n_mtiles = (p.nsegs16 + 7) / 8;
+    const int nwork = n_ntiles * ((n_mtiles + CL - 1) / CL);   // work item = (group of CL M tiles, N tile), per cluster
+    const int crank = CL > 1 ? (int)cluster_ctarank() : 0;
+    const int cid = CL > 1 ? (int)cluster_id_x() : (int)blockIdx.x;
+    const int ncl = CL > 1 ? (int)num_clusters_x() : (int)gridDim.x;
+    constexpr uint16_t CMASK = (uint16_t)((1u << CL) - 1);
 
     if (tid == 0) {
         for (int i = 0; i < NA; ++i) { mbar_init(barAfull + 8 * i, 1); mbar_init(barAempty + 8 * i, 1); }
-        for (int i = 0; i < NB; ++i) { mbar_init(barBfull + 8 * i, 1); mbar_init(barBempty + 8 * i, 1); }
+        for (int i = 0; i < NB; ++i) { mbar_init(barBfull + 8 * i, 1); mbar_init(barBempty + 8 * i, CL); }
         for (int i = 0; i < 2; ++i) { mbar_init(barAccFull + 8 * i, 1); mbar_init(barAccEmpty + 8 * i, 128); }
         fence_mbar_init();
     }
@@ -176,6 +183,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const TcConvPar
     if (warp == 5) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();   // peers' mbarriers are initialised before anything is multicast to them
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
@@ -187,8 +195,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const TcConvPar
         float* stg = reinterpret_cast<float*>(smem + STAGING_OFF) + warp * (32 * 33);
         const int col4 = (lane & 7) * 4;
         int lt = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++lt) {
-            const int n_tile = tile % n_ntiles, m_tile = tile / n_ntiles;
+        for (int w = cid; w < nwork; w += ncl, ++lt) {
+            const int n_tile = w % n_ntiles, m_tile = (w / n_ntiles) * CL + crank;   // m_tile >= n_mtiles: idle slot of the last group
             const int as = lt % NSETS, use = lt / NSETS;
             const int co0 = n_tile * BN;
             int rb[8], rt[8];   // sample / position of this thread's 8 rows (rb < 0: row past the batch)
@@ -217,7 +225,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const TcConvPar
             float4 Rn[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) Rn[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p.res) load_res(0, Rn);
+            if (p.res) {
+                // the mainloop of this tile is still running: pull the tile's residual rows into L2 now so that the
+                // epilogue's loads below are L2 hits (each lane owns one 128-byte line per row and 32-column chunk pair)
+                if ((lane & 7) == 0) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        for (int cb = 0; cb < BN; cb += 32) {
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.res + roff[i] + cb));
+                            if (p.res_mode == RS_AVGPOOL2) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.res + roff[i] + p.Cout + cb));
+                        }
+                }
+                load_res(0, Rn);
+            }
             mbar_wait(barAccFull + 8 * as, use & 1);
             tc_fence_after();
             const uint32_t acc_addr = tmem + ((uint32_t)(warp * 32) << 16) + as * ACC_COLS;
@@ -258,35 +278,45 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const TcConvPar
             mbar_arrive(barAccEmpty + 8 * as);   // this accumulator set may be overwritten
         }
     } else if (warp == 4) {
-        // ================================================================ loader (one thread, bulk async copies)
-        if (lane == 0) {
+        // ================================================================ loader (whole warp runs the loop, one elected lane issues)
+        {
             const uint32_t a_bytes = X3 ? A_STAGE : A_TILE, b_bytes = X3 ? B_STAGE : B_HALF;
             int ia = 0, ib = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                const int n_tile = tile % n_ntiles, m_tile = tile / n_ntiles;
+            for (int w = cid; w < nwork; w += ncl) {
+                const int n_tile = w % n_ntiles;
+                const int m_tile = min((w / n_ntiles) * CL + crank, n_mtiles - 1);   // idle slot: reload a valid tile, never stored
                 for (int ks = 0; ks < nks; ++ks, ++ia) {
                     const bool first = ks < nks0;
                     const TcSeg& sg = first ? p.seg[0] : p.seg[1];
                     const int kl = first ? ks : ks - nks0;
                     const int sa = ia % NA;
                     mbar_wait(barAempty + 8 * sa, ((ia / NA) & 1) ^ 1);
-                    mbar_arrive_expect_tx(barAfull + 8 * sa, a_bytes);
-                    bulk_copy_g2s(sA + sa * A_STAGE, sg.U + ((size_t)m_tile * sg.nks + kl) * A_STAGE, a_bytes, barAfull + 8 * sa);
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx(barAfull + 8 * sa, a_bytes);
+                        bulk_copy_g2s(sA + sa * A_STAGE, sg.U + ((size_t)m_tile * sg.nks + kl) * A_STAGE, a_bytes, barAfull + 8 * sa);
+                    }
+                    __syncwarp();
                     const uint8_t* wsrc = sg.w + ((size_t)n_tile * sg.nks + kl) * sg.taps * B_STAGE;
                     for (int tap = 0; tap < sg.taps; ++tap, ++ib) {
                         const int sb = ib % NB;
-                        mbar_wait(barBempty + 8 * sb, ((ib / NB) & 1) ^ 1);
-                        mbar_arrive_expect_tx(barBfull + 8 * sb, b_bytes);
-                        bulk_copy_g2s(sB + sb * B_STAGE, wsrc + (size_t)tap * B_STAGE, b_bytes, barBfull + 8 * sb);
+                        mbar_wait(barBempty + 8 * sb, ((ib / NB) & 1) ^ 1);   // all CL consumers of this stage are done
+                        if (elect_one()) {
+                            mbar_arrive_expect_tx(barBfull + 8 * sb, b_bytes);
+                            if (CL > 1) {
+                                const uint32_t part = b_bytes / CL, off = crank * part;
+                                bulk_copy_g2s_multicast(sB + sb * B_STAGE + off, wsrc + (size_t)tap * B_STAGE + off, part, barBfull + 8 * sb, CMASK);
+                            } else bulk_copy_g2s(sB + sb * B_STAGE, wsrc + (size_t)tap * B_STAGE, b_bytes, barBfull + 8 * sb);
+                        }
+                        __syncwarp();
                     }
                 }
             }
         }
     } else {
-        // ================================================================ MMA issuer (one thread)
-        if (lane == 0) {
+        // ================================================================ MMA issuer (whole warp runs the loop, one elected lane issues)
+        {
             int ia = 0, ib = 0, lt = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++lt) {
+            for (int w = cid; w < nwork; w += ncl, ++lt) {
                 const int as = lt % NSETS, use = lt / NSETS;
                 const uint32_t d0 = tmem + as * ACC_COLS, d1 = d0 + BN;
                 mbar_wait(barAccEmpty + 8 * as, (use & 1) ^ 1);   // epilogue has drained this set
@@ -304,30 +334,34 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const TcConvPar
                         const int shift = taps == 3 ? tap : 1;   // slot of the first row: position - 1 + tap
                         const uint32_t a_hi = sA + sa * A_STAGE + shift * A_SBO, a_lo = a_hi + A_TILE;
                         const uint32_t b_hi = sB + sb * B_STAGE, b_lo = b_hi + B_HALF;
+                        if (elect_one()) {
 #pragma unroll
                         for (int kk = 0; kk < BK / 16; ++kk) {
                             const uint64_t dah = make_desc(a_hi + kk * 2 * A_LBO, A_LBO, A_SBO);
                             const uint64_t dbh = make_desc(b_hi + kk * 2 * B_LBO, B_LBO, B_SBO);
-                            umma_bf16(d0, dah, dbh, IDESC, accum);
-                            accum = 1;
+                            umma_bf16(d0, dah, dbh, IDESC, kk == 0 ? accum : 1u);
                             if (X3) {
                                 const uint64_t dal = make_desc(a_lo + kk * 2 * A_LBO, A_LBO, A_SBO);
                                 const uint64_t dbl = make_desc(b_lo + kk * 2 * B_LBO, B_LBO, B_SBO);
-                                umma_bf16(d1, dah, dbl, IDESC, accum2);
+                                umma_bf16(d1, dah, dbl, IDESC, kk == 0 ? accum2 : 1u);
                                 umma_bf16(d1, dal, dbh, IDESC, 1);
-                                accum2 = 1;
                             }
                         }
-                        umma_commit(barBempty + 8 * sb);   // weight stage free once these MMAs retire
+                        if (CL > 1) umma_commit_multicast(barBempty + 8 * sb, CMASK);   // every CTA's loader writes into this stage
+                        else umma_commit(barBempty + 8 * sb);                           // weight stage free once these MMAs retire
+                        if (tap == taps - 1) umma_commit(barAempty + 8 * sa);
+                        if (tap == taps - 1 && ks == nks - 1) umma_commit(barAccFull + 8 * as);
+                        }
+                        __syncwarp();
+                        accum = 1; accum2 = 1;
                     }
-                    umma_commit(barAempty + 8 * sa);
                 }
-                umma_commit(barAccFull + 8 * as);
             }
         }
     }
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();   // no CTA leaves while a peer may still multicast into its shared memory
     if (warp == 5) tmem_dealloc(tmem, TMEM_COLS);
 }
 
@@ -392,17 +426,34 @@ cudaError_t launch_act_split(const ActSplitParams& p, bool x3, cudaStream_t st) 
     return cudaGetLastError();
 }
 
-cudaError_t launch_conv_tc(const TcConvParams& p, bool x3, cudaStream_t st) {
-    if (p.nsegs16 <= 0) return cudaSuccess;
+template <bool X3, int BN, int CL>
+cudaError_t launch_conv_tc_t(const TcConvParams& p, int num_sms, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<false, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<X3, BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
+    const int n_mtiles = (p.nsegs16 + 7) / 8;
+    const int nwork = (p.Cout / BN) * ((n_mtiles + CL - 1) / CL);
+    int nclusters = num_sms / CL;
+    if (nwork < nclusters) nclusters = nwork;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(nclusters * CL);   // persistent: one CTA per SM
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, conv_tc_kernel<X3, BN, CL>, p);
+}
+
+int g_conv_tc_cluster = 2;   // CTAs per cluster sharing weight stages by multicast (1, 2 or 4); eegldm_set_conv_cluster
+
+cudaError_t launch_conv_tc(const TcConvParams& p, bool x3, cudaStream_t st) {
+    if (p.nsegs16 <= 0) return cudaSuccess;
     static int num_sms = 0;
     if (!num_sms) {
         int dev = 0;
@@ -410,15 +461,14 @@ cudaError_t launch_conv_tc(const TcConvParams& p, bool x3, cudaStream_t st) {
         if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
     }
     if (p.bn != 128 && p.bn != 256) return cudaErrorInvalidValue;
-    const int ntiles = (p.Cout / p.bn) * ((p.nsegs16 + 7) / 8);
-    dim3 grid(ntiles < num_sms ? ntiles : num_sms);   // persistent: one CTA per SM
-    if (p.bn == 256) {
-        if (x3) conv_tc_kernel<true, 256><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(p);
-        else conv_tc_kernel<false, 256><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(p);
-    } else {
-        if (x3) conv_tc_kernel<true, 128><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(p);
-        else conv_tc_kernel<false, 128><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(p);
-    }
+    cudaError_t e;
+#define EEGLDM_TC(X3, BN)                                                              \
+    (g_conv_tc_cluster == 4 ? launch_conv_tc_t<X3, BN, 4>(p, num_sms, st)               \
+     : g_conv_tc_cluster == 2 ? launch_conv_tc_t<X3, BN, 2>(p, num_sms, st) : launch_conv_tc_t<X3, BN, 1>(p, num_sms, st))
+    if (p.bn == 256) e = x3 ? EEGLDM_TC(true, 256) : EEGLDM_TC(false, 256);
+    else e = x3 ? EEGLDM_TC(true, 128) : EEGLDM_TC(false, 128);
+#undef EEGLDM_TC
+    if (e != cudaSuccess) return e;
     g_launch_count += 1;
     return cudaGetLastError();
 }

@@ -1184,6 +1184,12 @@ const char* eegldm_version(void) { return "eegldm 0.1 (sm_100a)"; }
 int64_t eegldm_launch_count(void) { return (int64_t)g_launch_count.load(); }
 int eegldm_set_graphs(int enabled) { g_graphs_enabled = enabled != 0; return EEGLDM_OK; }
 
+int eegldm_set_conv_cluster(int ctas) {
+    if (ctas != 1 && ctas != 2 && ctas != 4) return fail(EEGLDM_ERR_INVALID, "cluster size must be 1, 2 or 4");
+    g_conv_tc_cluster = ctas;
+    return EEGLDM_OK;
+}
+
 int eegldm_profile_enable(int on) {
     for (auto& r : g_prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
     g_prof.clear();

@@ -101,6 +101,7 @@ bool conv_tc_eligible(int Cin0, int Cin1, int Cout, int Tout, int taps, int stri
 int conv_tc_bn(int Cout, int weight_stages);   // weight_stages = sum over segments of (Cin/32)*taps
 void pack_conv_tc(const float* w, int Cout, int Cin, int k, int bn, bool x3, std::vector<uint16_t>& out);
 cudaError_t launch_conv_tc(const TcConvParams& p, bool x3, cudaStream_t st);
+extern int g_conv_tc_cluster;   // CTAs per cluster sharing weight stages (1, 2, 4)
 cudaError_t launch_groupnorm(const GnParams& p, cudaStream_t st);
 int groupnorm_nsplit(int C, int T, int G);
 cudaError_t launch_attention_simt(const AttnParams& p, cudaStream_t st);

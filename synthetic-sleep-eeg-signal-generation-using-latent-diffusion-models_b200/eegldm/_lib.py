@@ -60,6 +60,7 @@ SIGNATURES = {
     "eegldm_version": (C.c_char_p, []),
     "eegldm_launch_count": (C.c_int64, []),
     "eegldm_set_graphs": (C.c_int, [C.c_int]),
+    "eegldm_set_conv_cluster": (C.c_int, [C.c_int]),
     "eegldm_profile_enable": (C.c_int, [C.c_int]),
     "eegldm_profile_record": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "eegldm_profile_read": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
