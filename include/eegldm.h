@@ -138,6 +138,33 @@ int eegldm_aekl_forward(eegldm_aekl* h, const float* x_dev, const float* eps_dev
                         float* z_mu_dev, float* z_sigma_dev, int B, int L, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Spectral loss: replaces generative.losses.JukeboxLoss(spatial_dims=1, reduction=...) as called at
+ * src/train_autoencoderkl.py:158,208.  input/target [B, C=1, N] fp32 device; loss_dev receives
+ * reduce((|fft_ortho(target)| - |fft_ortho(input)|)^2) (reduction 0 = "sum", 1 = "mean"); grad_input_dev
+ * (nullable) receives d loss / d input.  Batched cuFFT R2C (+ C2R for the gradient) and one custom kernel. */
+int eegldm_jukebox_loss(const float* input_dev, const float* target_dev, int B, int C, int N, int reduction, float* loss_dev,
+                        float* grad_input_dev, void* stream);
+
+/* Generator half of the autoencoder training step, src/train_autoencoderkl.py:204-220 (adversarial term excluded):
+ *   recon, mu, sigma = model(x)  with  z = mu + eps * sigma  (eps supplied by the caller, [B, z, L/2^(levels-1)])
+ *   loss = L1Loss(recon, x) + kl_weight * KL(mu, sigma) + spectral_weight * JukeboxLoss(recon, x);  backward;  Adam step.
+ * lr <= 0 computes losses and gradients only.  losses_host (nullable; synchronises) receives
+ * {l1, kl, spectral, total}.  Parameters, gradients and Adam moments live on the device in the engine's packed
+ * layouts; eegldm_aekl_train_export returns one state_dict entry (what = 0) or its gradient (what = 1) in the
+ * reference layout; eegldm_aekl_train_sync copies the trained parameters back into the inference weights
+ * (encode / decode / sampling use them from then on). */
+typedef struct {
+    float kl_weight;        /* 1e-9  (config_aekl_eeg.yaml:15) */
+    float spectral_weight;  /* 1e4   (config_aekl_eeg.yaml:17) */
+    float lr;               /* 5e-3  optimizer_g_lr (config_aekl_eeg.yaml:12) */
+    float beta1, beta2, adam_eps;   /* torch.optim.Adam defaults 0.9, 0.999, 1e-8 */
+} eegldm_aekl_train_cfg;
+int eegldm_aekl_train_step(eegldm_aekl* h, const float* x_dev, const float* eps_dev, int B, int L, const eegldm_aekl_train_cfg* cfg,
+                           float* losses_host, void* stream);
+int eegldm_aekl_train_export(eegldm_aekl* h, int what, const char* name, float* host_out);
+int eegldm_aekl_train_sync(eegldm_aekl* h);
+
+/* ------------------------------------------------------------------------------------------------
  * Scheduler + sampling loop: replaces generative.networks.schedulers.DDIMScheduler as used at
  * src/sample_trials.py:136-145 and the loop at src/sample_trials.py:153-166. */
 typedef struct {

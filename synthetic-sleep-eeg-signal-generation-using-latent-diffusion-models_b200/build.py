@@ -15,8 +15,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "eegldm", "libeegldm.so")
-SOURCES = ["engine.cu", "kernels_simt.cu", "conv_tc.cu", "attn_tc.cu"]
-OPTIONAL_SOURCES = ["spectral.cu", "aekl_train.cu"]
+SOURCES = ["engine.cu", "kernels_simt.cu", "conv_tc.cu", "attn_tc.cu", "train_kernels.cu", "spectral.cu"]
+OPTIONAL_SOURCES = []
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 
@@ -63,8 +63,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if p.returncode:
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
     link = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC", "-o", OUT] + objs
-    if any(os.path.basename(s) == "spectral.cu" for s in srcs):
-        link += ["-lcufft", "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
+    link += ["-ldl"]   # cuFFT is dlopen'ed at first use (spectral.cu)
     subprocess.run(link, check=True)
     with open(stamp_path, "w") as f:
         f.write(stamp)

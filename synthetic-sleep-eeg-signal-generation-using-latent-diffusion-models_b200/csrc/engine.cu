@@ -936,7 +936,28 @@ struct ALayer {
 };
 }  // namespace
 
+// Training state of the autoencoder (eegldm_aekl_train_step): flat parameter / gradient / Adam-moment buffers in the
+// engine's packed layouts, plus the map back to the reference's state_dict entries.
+namespace {
+struct TrainOff { size_t w1 = 0, b1 = 0, g1 = 0, be1 = 0, w2 = 0, b2 = 0, g2 = 0, be2 = 0, ws = 0, bs = 0; };
+struct TrainEntry { std::string name; size_t off; std::vector<int64_t> shape; bool conv; };
+struct AeklTrain {
+    std::vector<TrainOff> enc, dec;
+    TrainOff qmu, qls, pq;
+    std::vector<TrainEntry> entries;
+    size_t n = 0;
+    float *P = nullptr, *G = nullptr, *M = nullptr, *V = nullptr, *losses = nullptr, *arena = nullptr;
+    size_t arena_cap = 0;
+    int step = 0;
+    bool dirty = false;   // P has moved away from the host state_dict / inference weights
+    ~AeklTrain() {
+        for (float* p : {P, G, M, V, losses, arena}) if (p) cudaFree(p);
+    }
+};
+}  // namespace
+
 struct eegldm_aekl {
+    AeklTrain* train = nullptr;
     eegldm_aekl_cfg cfg{};
     ParamSet ps;
     std::vector<ALayer> enc, dec;
@@ -946,7 +967,7 @@ struct eegldm_aekl {
     float* arena = nullptr; size_t arena_cap = 0;
     float* io_tmp = nullptr; size_t io_tmp_cap = 0;
     int down_factor() const { return 1 << (cfg.n_levels - 1); }
-    ~eegldm_aekl() { if (arena) cudaFree(arena); if (io_tmp) cudaFree(io_tmp); }
+    ~eegldm_aekl() { if (arena) cudaFree(arena); if (io_tmp) cudaFree(io_tmp); delete train; }
 };
 
 namespace {
@@ -1313,6 +1334,7 @@ int eegldm_aekl_param_info(const eegldm_aekl* h, int i, const char** name, int64
 int eegldm_aekl_load(eegldm_aekl* h, const char* name, const float* host, const int64_t* shape, int ndim) {
     if (!h) return fail(EEGLDM_ERR_INVALID, "null handle");
     h->finalized = false;
+    if (h->train) { delete h->train; h->train = nullptr; }   // new weights: optimiser state starts over
     return h->ps.load(name, host, shape, ndim);
 }
 int eegldm_aekl_finalize(eegldm_aekl* h) {
@@ -1609,6 +1631,333 @@ int eegldm_test_attention(const float* qkv_dev, int B, int T, int H, int ch, int
     if (q16) cudaFree(q16);
     if (ce != cudaSuccess) return cuda_fail(ce, "attention launch");
     return EEGLDM_OK;
+}
+
+}  // extern "C"
+
+// ================================================================================================ AEKL training step
+namespace {
+
+std::vector<float> unpack_conv(const float* packed, int Cout, int Cin, int k) {   // inverse of pack_conv
+    std::vector<float> out((size_t)Cout * Cin * k);
+    for (int co = 0; co < Cout; ++co)
+        for (int ci = 0; ci < Cin; ++ci)
+            for (int kk = 0; kk < k; ++kk) out[((size_t)co * Cin + ci) * k + kk] = packed[((size_t)ci * k + kk) * Cout + co];
+    return out;
+}
+
+int aekl_train_init(eegldm_aekl* h) {
+    int r = h->ps.check_all_loaded();
+    if (r) return r;
+    delete h->train;
+    h->train = new AeklTrain();
+    AeklTrain& t = *h->train;
+    std::vector<float> flat;
+    const ParamSet& ps = h->ps;
+    auto push = [&](const std::string& name, bool conv, int cout = 0, int cin = 0, int k = 0) -> size_t {
+        const HostParam& hp = ps.params[ps.index.at(name)];
+        const size_t off = (flat.size() + 63) & ~size_t(63);
+        flat.resize(off);
+        if (conv) { auto pk = pack_conv(hp.data, cout, cin, k); flat.insert(flat.end(), pk.begin(), pk.end()); }
+        else flat.insert(flat.end(), hp.data.begin(), hp.data.end());
+        t.entries.push_back({name, off, hp.shape, conv});
+        return off;
+    };
+    auto stage = [&](const ALayer& l) {
+        TrainOff o;
+        const std::string& p = l.prefix;
+        switch (l.kind) {
+            case ALayer::CONV: o.w1 = push(p + ".conv.weight", true, l.cout, l.cin, l.k); o.b1 = push(p + ".conv.bias", false); break;
+            case ALayer::RES:
+                o.g1 = push(p + ".norm1.weight", false); o.be1 = push(p + ".norm1.bias", false);
+                o.w1 = push(p + ".conv1.conv.weight", true, l.cout, l.cin, 3); o.b1 = push(p + ".conv1.conv.bias", false);
+                o.g2 = push(p + ".norm2.weight", false); o.be2 = push(p + ".norm2.bias", false);
+                o.w2 = push(p + ".conv2.conv.weight", true, l.cout, l.cout, 3); o.b2 = push(p + ".conv2.conv.bias", false);
+                if (l.cin != l.cout) { o.ws = push(p + ".nin_shortcut.conv.weight", true, l.cout, l.cin, 1); o.bs = push(p + ".nin_shortcut.conv.bias", false); }
+                break;
+            case ALayer::DOWN: case ALayer::UP:
+                o.w1 = push(p + ".conv.conv.weight", true, l.cin, l.cin, 3); o.b1 = push(p + ".conv.conv.bias", false); break;
+            case ALayer::NORM: o.g1 = push(p + ".weight", false); o.be1 = push(p + ".bias", false); break;
+        }
+        return o;
+    };
+    for (auto& l : h->enc) t.enc.push_back(stage(l));
+    for (auto& l : h->dec) t.dec.push_back(stage(l));
+    t.qmu = stage(h->q_mu); t.qls = stage(h->q_ls); t.pq = stage(h->post_q);
+    t.n = (flat.size() + 63) & ~size_t(63);
+    flat.resize(t.n, 0.f);
+    CU(cudaMalloc((void**)&t.P, t.n * sizeof(float)));
+    CU(cudaMalloc((void**)&t.G, t.n * sizeof(float)));
+    CU(cudaMalloc((void**)&t.M, t.n * sizeof(float)));
+    CU(cudaMalloc((void**)&t.V, t.n * sizeof(float)));
+    CU(cudaMalloc((void**)&t.losses, 4 * sizeof(float)));
+    CU(cudaMemcpy(t.P, flat.data(), t.n * sizeof(float), cudaMemcpyHostToDevice));
+    CU(cudaMemset(t.G, 0, t.n * sizeof(float)));
+    CU(cudaMemset(t.M, 0, t.n * sizeof(float)));
+    CU(cudaMemset(t.V, 0, t.n * sizeof(float)));
+    return EEGLDM_OK;
+}
+
+// copy the trained parameters back into the host state_dict and the inference weight pool
+int aekl_train_sync(eegldm_aekl* h) {
+    AeklTrain* t = h->train;
+    if (!t || !t->dirty) return EEGLDM_OK;
+    std::vector<float> flat(t->n);
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(flat.data(), t->P, t->n * sizeof(float), cudaMemcpyDeviceToHost));
+    for (auto& en : t->entries) {
+        HostParam& hp = h->ps.params[h->ps.index.at(en.name)];
+        if (en.conv) hp.data = unpack_conv(flat.data() + en.off, (int)en.shape[0], (int)en.shape[1], (int)en.shape[2]);
+        else hp.data.assign(flat.begin() + en.off, flat.begin() + en.off + hp.numel());
+    }
+    t->dirty = false;
+    return finalize_aekl(h);
+}
+
+struct TT { float* p = nullptr; int C = 0, T = 0; };
+
+struct TrainRun {
+    eegldm_aekl* h; AeklTrain* t; int B; cudaStream_t st; bool dry;
+    float* base = nullptr; size_t off = 0;
+    cudaError_t err = cudaSuccess;
+    enum Kind { CONV, NORM, LATENT };
+    struct Op {
+        Kind kind; TT in, out, res; bool has_res = false, in_needs_grad = true;
+        size_t ow = 0, ob = 0; int taps = 0, stride = 1, pad = 0, ups = 0;
+        float *mean = nullptr, *rstd = nullptr; size_t og = 0, obe = 0; int G = 1, silu = 0;
+        TT mu, lv, sigma; const float* eps = nullptr;
+    };
+    std::vector<Op> tape;
+    std::unordered_map<const float*, std::pair<float*, bool>> grads;
+
+    float* alloc(size_t n) { n = (n + 63) & ~size_t(63); float* p = dry ? nullptr : base + off; off += n; return p; }
+    TT tensor(int C, int T) { TT x; x.C = C; x.T = T; x.p = alloc((size_t)B * T * C); return x; }
+    void ck(cudaError_t e) { if (err == cudaSuccess && e != cudaSuccess) err = e; }
+    size_t numel(const TT& x) const { return (size_t)B * x.T * x.C; }
+
+    TT conv(const TT& in, size_t ow, size_t ob, int Cout, int taps, int stride, int pad, int ups, const TT* res, bool in_needs_grad = true) {
+        const int Tc = ups ? in.T * 2 : in.T;
+        const int Tout = stride == 1 ? Tc : (Tc + 1 - 3) / 2 + 1;
+        TT out = tensor(Cout, Tout);
+        if (!dry) {
+            ConvParams p{};
+            p.seg[0] = ConvSeg{in.p, nullptr, in.C, 0, nullptr, nullptr, 0, ups ? RS_NEAREST2 : RS_NONE, in.T, t->P + ow, taps};
+            p.nseg = 1; p.Cout = Cout; p.Tout = Tout; p.Tc = Tc; p.stride = stride; p.pad_left = pad; p.bias = t->P + ob;
+            if (res) { p.res = res->p; p.res_mode = RS_NONE; p.res_Tin = Tout; }
+            p.out = out.p; p.B = B;
+            ck(launch_conv_simt(p, st));
+            Op op; op.kind = CONV; op.in = in; op.out = out; op.has_res = res != nullptr; if (res) op.res = *res;
+            op.ow = ow; op.ob = ob; op.taps = taps; op.stride = stride; op.pad = pad; op.ups = ups; op.in_needs_grad = in_needs_grad;
+            tape.push_back(op);
+        }
+        return out;
+    }
+    TT norm(const TT& x, size_t og, size_t obe, int G, int silu) {
+        float* ss = alloc((size_t)B * x.C * 2);
+        float* mr = alloc((size_t)B * G * 2);
+        const int nsplit = groupnorm_nsplit(x.C, x.T, G);
+        float* part = alloc((size_t)B * nsplit * G * 3);
+        TT a = tensor(x.C, x.T);
+        if (!dry) {
+            GnParams p{};
+            p.src0 = x.p; p.C0 = x.C; p.T = x.T; p.G = G; p.gamma = t->P + og; p.beta = t->P + obe; p.eps = 1e-6f; p.B = B;
+            p.nsplit = nsplit; p.scale = ss; p.shift = ss + (size_t)B * x.C; p.partial = part;
+            p.mean_out = mr; p.rstd_out = mr + (size_t)B * G;
+            ck(launch_groupnorm(p, st));
+            ck(launch_norm_act_fwd(x.p, p.scale, p.shift, a.p, B, x.T, x.C, silu, st));
+            Op op; op.kind = NORM; op.in = x; op.out = a; op.mean = p.mean_out; op.rstd = p.rstd_out; op.og = og; op.obe = obe; op.G = G; op.silu = silu;
+            tape.push_back(op);
+        }
+        return a;
+    }
+    TT blocks(const std::vector<ALayer>& layers, const std::vector<TrainOff>& offs, TT cur, bool first_needs_grad) {
+        const int G = h->cfg.norm_num_groups;
+        bool needs = first_needs_grad;
+        for (size_t i = 0; i < layers.size(); ++i) {
+            const ALayer& l = layers[i]; const TrainOff& o = offs[i];
+            switch (l.kind) {
+                case ALayer::CONV: cur = conv(cur, o.w1, o.b1, l.cout, l.k, 1, l.k / 2, 0, nullptr, needs); break;
+                case ALayer::RES: {
+                    TT a1 = norm(cur, o.g1, o.be1, G, 1);
+                    TT h1 = conv(a1, o.w1, o.b1, l.cout, 3, 1, 1, 0, nullptr);
+                    TT a2 = norm(h1, o.g2, o.be2, G, 1);
+                    if (l.cin != l.cout) {
+                        TT sc = conv(cur, o.ws, o.bs, l.cout, 1, 1, 0, 0, nullptr);
+                        cur = conv(a2, o.w2, o.b2, l.cout, 3, 1, 1, 0, &sc);
+                    } else {
+                        TT x = cur;
+                        cur = conv(a2, o.w2, o.b2, l.cout, 3, 1, 1, 0, &x);
+                    }
+                    break;
+                }
+                case ALayer::DOWN: cur = conv(cur, o.w1, o.b1, l.cin, 3, 2, 0, 0, nullptr); break;
+                case ALayer::UP: cur = conv(cur, o.w1, o.b1, l.cin, 3, 1, 1, 1, nullptr); break;
+                case ALayer::NORM: cur = norm(cur, o.g1, o.be1, G, 0); break;
+            }
+            needs = true;
+        }
+        return cur;
+    }
+    // gradient slot of a tensor: (pointer, already holds a value?)
+    std::pair<float*, bool>& slot(const TT& x) {
+        auto it = grads.find(x.p);
+        if (it == grads.end()) it = grads.emplace(x.p, std::make_pair(alloc(numel(x)), false)).first;
+        return it->second;
+    }
+    void backward(float kl_weight) {
+        for (auto it = tape.rbegin(); it != tape.rend(); ++it) {
+            Op& op = *it;
+            if (op.kind == CONV) {
+                auto dy = grads.find(op.out.p);
+                if (dy == grads.end() || !dy->second.second) continue;   // output unused by the loss
+                if (op.has_res) {
+                    auto& gr = slot(op.res);
+                    ck(launch_axpy(dy->second.first, gr.first, 1.f, gr.second, numel(op.res), st));
+                    gr.second = true;
+                }
+                ConvGradParams p{};
+                p.dy = dy->second.first; p.a = op.in.p; p.w = t->P + op.ow; p.dw = t->G + op.ow; p.db = t->G + op.ob;
+                p.Cin = op.in.C; p.Cout = op.out.C; p.taps = op.taps; p.stride = op.stride; p.pad = op.pad; p.ups = op.ups;
+                p.Tin = op.in.T; p.Tc = op.ups ? op.in.T * 2 : op.in.T; p.Tout = op.out.T; p.B = B;
+                ck(launch_conv_bwd_weight(p, st));
+                if (op.in_needs_grad) {
+                    auto& gi = slot(op.in);
+                    p.da = gi.first; p.accumulate = gi.second;
+                    ck(launch_conv_bwd_data(p, st));
+                    gi.second = true;
+                }
+            } else if (op.kind == NORM) {
+                auto da = grads.find(op.out.p);
+                if (da == grads.end() || !da->second.second) continue;
+                auto& gx = slot(op.in);
+                NormGradParams p{};
+                p.da = da->second.first; p.x = op.in.p; p.mean = op.mean; p.rstd = op.rstd; p.gamma = t->P + op.og; p.beta = t->P + op.obe;
+                p.m12 = alloc((size_t)B * op.G * 2); p.dgamma = t->G + op.og; p.dbeta = t->G + op.obe; p.dx = gx.first;
+                p.C = op.in.C; p.T = op.in.T; p.G = op.G; p.B = B; p.silu = op.silu; p.accumulate = gx.second;
+                ck(launch_norm_act_bwd(p, st));
+                gx.second = true;
+            } else {   // LATENT: z = mu + eps*sigma ; KL
+                auto dz = grads.find(op.out.p);
+                if (dz == grads.end() || !dz->second.second) continue;
+                auto& gm = slot(op.mu); auto& gl = slot(op.lv);
+                ck(launch_latent(op.mu.p, op.lv.p, op.eps, nullptr, nullptr, dz->second.first, gm.first, gl.first, nullptr, kl_weight, B,
+                                 numel(op.mu), st));
+                gm.second = gl.second = true;
+            }
+        }
+    }
+};
+
+}  // namespace
+
+extern "C" {
+
+int eegldm_jukebox_loss(const float* input_dev, const float* target_dev, int B, int C, int N, int reduction, float* loss_dev,
+                        float* grad_input_dev, void* stream) {
+    if (!input_dev || !target_dev || !loss_dev) return fail(EEGLDM_ERR_INVALID, "null argument");
+    if (C != 1) return fail(EEGLDM_ERR_INVALID, "JukeboxLoss: only single-channel signals (the reference's in/out_channels = 1)");
+    if (reduction != 0 && reduction != 1) return fail(EEGLDM_ERR_INVALID, "reduction must be 0 (sum) or 1 (mean)");
+    if (B < 0 || N < 2) return fail(EEGLDM_ERR_SHAPE, "bad shape");
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(cudaMemsetAsync(loss_dev, 0, sizeof(float), st));
+    std::string err;
+    const int r = spectral_loss(input_dev, target_dev, B, N, reduction, 1.f, loss_dev, grad_input_dev, 1.f, 0, st, &err);
+    if (r == 1) return fail(EEGLDM_ERR_CUDA, "cuFFT: " + err);
+    if (r) return cuda_fail((cudaError_t)r, "spectral loss");
+    return EEGLDM_OK;
+}
+
+int eegldm_aekl_train_step(eegldm_aekl* h, const float* x_dev, const float* eps_dev, int B, int L, const eegldm_aekl_train_cfg* cfg,
+                           float* losses_host, void* stream) {
+    if (!h || !cfg) return fail(EEGLDM_ERR_INVALID, "null argument");
+    if (h->cfg.in_channels != 1 || h->cfg.out_channels != 1)
+        return fail(EEGLDM_ERR_INVALID, "training step supports in/out_channels = 1 (every reference config)");
+    const int f = h->down_factor();
+    if (B <= 0 || L <= 0 || L % f) return fail(EEGLDM_ERR_SHAPE, "L must be a positive multiple of 2^(levels-1), B > 0");
+    if (!x_dev || !eps_dev) return fail(EEGLDM_ERR_INVALID, "null argument");
+    for (int i = 0; i < h->cfg.n_levels; ++i)
+        if (h->cfg.num_channels[i] / h->cfg.norm_num_groups > 256) return fail(EEGLDM_ERR_INVALID, "channels per group > 256 not supported in training");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!h->train) { int r = aekl_train_init(h); if (r) return r; }
+    AeklTrain& t = *h->train;
+    const int z = h->cfg.latent_channels, T = L / f;
+    auto run = [&](TrainRun& tr) {
+        TT x; x.p = const_cast<float*>(x_dev); x.C = 1; x.T = L;
+        TT h3 = tr.blocks(h->enc, t.enc, x, /*first_needs_grad=*/false);
+        TT mu = tr.conv(h3, t.qmu.w1, t.qmu.b1, z, 1, 1, 0, 0, nullptr);
+        TT lv = tr.conv(h3, t.qls.w1, t.qls.b1, z, 1, 1, 0, 0, nullptr);
+        TT sigma = tr.tensor(z, T), zz = tr.tensor(z, T);
+        if (!tr.dry) {
+            tr.ck(launch_latent(mu.p, lv.p, eps_dev, sigma.p, zz.p, nullptr, nullptr, nullptr, t.losses + 1, 0.f, B, tr.numel(mu), st));
+            TrainRun::Op op; op.kind = TrainRun::LATENT; op.out = zz; op.mu = mu; op.lv = lv; op.sigma = sigma; op.eps = eps_dev;
+            tr.tape.push_back(op);
+        }
+        TT pq = tr.conv(zz, t.pq.w1, t.pq.b1, z, 1, 1, 0, 0, nullptr);
+        return tr.blocks(h->dec, t.dec, pq, true);
+    };
+    // eps is given in the reference NCL layout; the engine's latent tensors are channels-last
+    if (z != 1) return fail(EEGLDM_ERR_INVALID, "training step supports latent_channels = 1 (config_aekl_eeg_2_2_4_spec.yaml)");
+    TrainRun sizing{h, &t, B, st, true};
+    run(sizing);
+    const size_t need = sizing.off * 2 + (size_t)(1 << 20);
+    int r = ensure(t.arena, t.arena_cap, need);
+    if (r) return r;
+    CU(cudaMemsetAsync(t.G, 0, t.n * sizeof(float), st));
+    CU(cudaMemsetAsync(t.losses, 0, 4 * sizeof(float), st));
+    TrainRun tr{h, &t, B, st, false};
+    tr.base = t.arena;
+    TT recon = run(tr);
+    if (tr.err != cudaSuccess) return cuda_fail(tr.err, "training forward");
+    // losses: L1 (mean) + spectral_weight * Jukebox(sum) on the reconstruction; KL handled in the latent op
+    auto& gr = tr.slot(recon);
+    CU(launch_l1_loss(recon.p, x_dev, gr.first, t.losses + 0, 1.f, tr.numel(recon), st));
+    gr.second = true;
+    if (cfg->spectral_weight != 0.f) {
+        std::string err;
+        const int sr = spectral_loss(recon.p, x_dev, B, L, 0, 1.f, t.losses + 2, gr.first, cfg->spectral_weight, 1, st, &err);
+        if (sr == 1) return fail(EEGLDM_ERR_CUDA, "cuFFT: " + err);
+        if (sr) return cuda_fail((cudaError_t)sr, "spectral loss");
+    }
+    tr.backward(cfg->kl_weight);
+    if (tr.err != cudaSuccess) return cuda_fail(tr.err, "training backward");
+    if (tr.off > t.arena_cap) return fail(EEGLDM_ERR_NOMEM, "training arena overflow");
+    CU(launch_axpy(t.losses + 0, t.losses + 3, 1.f, 0, 1, st));
+    CU(launch_axpy(t.losses + 1, t.losses + 3, cfg->kl_weight, 1, 1, st));
+    CU(launch_axpy(t.losses + 2, t.losses + 3, cfg->spectral_weight, 1, 1, st));
+    if (cfg->lr > 0.f) {
+        t.step += 1;
+        CU(launch_adam(t.P, t.G, t.M, t.V, cfg->lr, cfg->beta1, cfg->beta2, cfg->adam_eps, t.step, t.n, st));
+        t.dirty = true;
+    }
+    if (losses_host) {
+        CU(cudaMemcpyAsync(losses_host, t.losses, 4 * sizeof(float), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    return EEGLDM_OK;
+}
+
+int eegldm_aekl_train_export(eegldm_aekl* h, int what, const char* name, float* host_out) {
+    if (!h || !name || !host_out) return fail(EEGLDM_ERR_INVALID, "null argument");
+    if (!h->train) return fail(EEGLDM_ERR_MISSING, "no training step has run");
+    AeklTrain& t = *h->train;
+    if (what != 0 && what != 1) return fail(EEGLDM_ERR_INVALID, "what must be 0 (parameter) or 1 (gradient)");
+    for (auto& en : t.entries) {
+        if (en.name != name) continue;
+        size_t n = 1;
+        for (auto s : en.shape) n *= (size_t)s;
+        std::vector<float> tmp(n);
+        CU(cudaDeviceSynchronize());
+        CU(cudaMemcpy(tmp.data(), (what ? t.G : t.P) + en.off, n * sizeof(float), cudaMemcpyDeviceToHost));
+        if (en.conv) tmp = unpack_conv(tmp.data(), (int)en.shape[0], (int)en.shape[1], (int)en.shape[2]);
+        std::memcpy(host_out, tmp.data(), n * sizeof(float));
+        return EEGLDM_OK;
+    }
+    return fail(EEGLDM_ERR_MISSING, std::string("unknown state_dict key: ") + name);
+}
+
+int eegldm_aekl_train_sync(eegldm_aekl* h) {
+    if (!h) return fail(EEGLDM_ERR_INVALID, "null handle");
+    return aekl_train_sync(h);
 }
 
 }  // extern "C"

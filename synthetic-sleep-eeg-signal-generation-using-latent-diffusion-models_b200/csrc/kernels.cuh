@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 #include <atomic>
 #include <cstdint>
+#include <string>
 #include <vector>
 
 namespace eegldm {
@@ -58,6 +59,8 @@ struct GnParams {
     float* partial;               // [B][nsplit][G][3] scratch
     int nsplit;
     int B;
+    float* mean_out;              // optional [B][G] (training: saved for the backward pass)
+    float* rstd_out;
 };
 
 struct AttnParams {
@@ -133,5 +136,30 @@ cudaError_t launch_step_advance(const float* temb_table, int temb_row, float* te
 cudaError_t launch_kl_sigma(const float* logvar, float* sigma, size_t n, cudaStream_t st);
 cudaError_t launch_axpy_sampling(const float* mu, const float* sigma, const float* eps, float* z, size_t n,
                                  cudaStream_t st);
+
+int spectral_loss(const float* input, const float* target, int B, int N, int reduction, float loss_weight, float* loss_dev,
+                  float* grad_dev, float grad_weight, int grad_accumulate, cudaStream_t st, std::string* err);
+// ---- AutoencoderKL training step (train_kernels.cu, spectral.cu) --------------------------------
+cudaError_t launch_norm_act_fwd(const float* x, const float* scale, const float* shift, float* a, int B, int T, int C, int silu,
+                                cudaStream_t st);
+struct ConvGradParams {   // y = conv(upsample?(a)): taps, stride, left pad; Tc = conv-input length, Tin = length of a
+    const float* dy; const float* a; const float* w;   // w: SIMT image [(ci*taps + k)][Cout]
+    float* da; float* dw; float* db;
+    int Cin, Cout, taps, stride, pad, ups, Tin, Tc, Tout, B, accumulate;
+};
+cudaError_t launch_conv_bwd_data(const ConvGradParams& p, cudaStream_t st);
+cudaError_t launch_conv_bwd_weight(const ConvGradParams& p, cudaStream_t st);   // dw, db are accumulated (atomicAdd)
+struct NormGradParams {
+    const float* da; const float* x; const float* mean; const float* rstd; const float* gamma; const float* beta;
+    float* m12; float* dgamma; float* dbeta; float* dx;
+    int C, T, G, B, silu, accumulate;
+};
+cudaError_t launch_norm_act_bwd(const NormGradParams& p, cudaStream_t st);
+cudaError_t launch_axpy(const float* src, float* dst, float alpha, int accumulate, size_t n, cudaStream_t st);
+cudaError_t launch_l1_loss(const float* r, const float* x, float* dr, float* loss, float weight, size_t n, cudaStream_t st);
+cudaError_t launch_latent(const float* mu, const float* lv, const float* eps, float* sigma, float* z, const float* dz, float* dmu,
+                          float* dlv, float* kl_loss, float kl_weight, int B, size_t n, cudaStream_t st);
+cudaError_t launch_adam(float* p, const float* g, float* m, float* v, float lr, float b1, float b2, float eps, int step, size_t n,
+                        cudaStream_t st);
 
 }  // namespace eegldm

@@ -339,6 +339,7 @@ __global__ void gn_finalize_kernel(const GnParams p) {
         const float var = r.m2 / r.n;  // biased variance, as nn.GroupNorm
         s_mean[g] = r.mean;
         s_rstd[g] = 1.0f / sqrtf(var + p.eps);
+        if (p.mean_out) { p.mean_out[(size_t)b * p.G + g] = s_mean[g]; p.rstd_out[(size_t)b * p.G + g] = s_rstd[g]; }
     }
     __syncthreads();
     for (int c = threadIdx.x; c < C; c += blockDim.x) {

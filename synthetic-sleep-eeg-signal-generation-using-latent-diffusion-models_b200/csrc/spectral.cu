@@ -1,0 +1,152 @@
+// Spectral (Jukebox) loss: generative.losses.JukeboxLoss(spatial_dims=1, reduction="sum") [monai-generative], as called at
+// src/train_autoencoderkl.py:158,208:   A(x) = |fftn(x, dim=(1,2), norm="ortho")| ;  loss = reduce((A(target) - A(input))^2).
+// For the reference's single-channel signals the (1,2)-FFT is a 1-D FFT of length N per sample.  Real input => Hermitian
+// spectrum, so one batched cuFFT R2C per signal and Hermitian weights (1 for bins 0 and N/2, 2 otherwise) replace the
+// reference's full complex transform; the backward pass is one C2R:
+//   dL/dinput = C2R(H) / sqrt(N),  H_k = -2 (A_t[k] - A_i[k]) * F_i[k] / |F_i[k]|     (F unnormalised, A = |F| / sqrt(N))
+// cuFFT is loaded with dlopen at first use so that libeegldm.so has no link-time dependency on it.
+#include <cufft.h>
+#include <dlfcn.h>
+
+#include <map>
+#include <mutex>
+#include <string>
+
+#include "kernels.cuh"
+
+namespace eegldm {
+namespace {
+
+struct CufftApi {
+    void* lib = nullptr;
+    cufftResult (*PlanMany)(cufftHandle*, int, int*, int*, int, int, int*, int, int, cufftType, int) = nullptr;
+    cufftResult (*SetStream)(cufftHandle, cudaStream_t) = nullptr;
+    cufftResult (*ExecR2C)(cufftHandle, cufftReal*, cufftComplex*) = nullptr;
+    cufftResult (*ExecC2R)(cufftHandle, cufftComplex*, cufftReal*) = nullptr;
+    cufftResult (*Destroy)(cufftHandle) = nullptr;
+    std::string err;
+    bool load() {
+        if (lib) return true;
+        for (const char* name : {"libcufft.so.11", "/usr/local/cuda/lib64/libcufft.so.11", "libcufft.so"}) {
+            lib = dlopen(name, RTLD_NOW | RTLD_LOCAL);
+            if (lib) break;
+        }
+        if (!lib) { err = "cannot dlopen libcufft.so.11"; return false; }
+        PlanMany = (decltype(PlanMany))dlsym(lib, "cufftPlanMany");
+        SetStream = (decltype(SetStream))dlsym(lib, "cufftSetStream");
+        ExecR2C = (decltype(ExecR2C))dlsym(lib, "cufftExecR2C");
+        ExecC2R = (decltype(ExecC2R))dlsym(lib, "cufftExecC2R");
+        Destroy = (decltype(Destroy))dlsym(lib, "cufftDestroy");
+        if (!PlanMany || !SetStream || !ExecR2C || !ExecC2R || !Destroy) { err = "libcufft is missing symbols"; return false; }
+        return true;
+    }
+};
+
+struct SpectralState {
+    CufftApi api;
+    std::map<std::pair<int, int>, std::pair<cufftHandle, cufftHandle>> plans;   // (N, batch) -> (r2c, c2r)
+    float2* freq = nullptr; size_t freq_cap = 0;    // [2][B][N/2+1]
+    float* time = nullptr; size_t time_cap = 0;     // [B][N]
+    std::mutex mu;
+};
+SpectralState g_spec;
+
+// per bin: amplitude difference, weighted squared error, gradient spectrum (in place over Fi)
+__global__ void __launch_bounds__(256) spectral_bins_kernel(float2* __restrict__ Fi, const float2* __restrict__ Ft, float* __restrict__ loss,
+                                                             int N, size_t nbins_total, float loss_scale, int want_grad) {
+    __shared__ float red[32];
+    const int nb = N / 2 + 1;
+    const float inv_sqrt_n = rsqrtf((float)N);
+    float s = 0.f;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nbins_total; i += (size_t)gridDim.x * blockDim.x) {
+        const int k = (int)(i % nb);
+        const float2 fi = Fi[i], ft = Ft[i];
+        const float mi = sqrtf(fi.x * fi.x + fi.y * fi.y), mt = sqrtf(ft.x * ft.x + ft.y * ft.y);
+        const float d = (mt - mi) * inv_sqrt_n;                       // A_t - A_i
+        const float wk = (k == 0 || 2 * k == N) ? 1.f : 2.f;         // Hermitian twin
+        s += wk * d * d;
+        if (want_grad) {
+            const float c = mi > 0.f ? -2.f * d / mi : 0.f;          // d|F|/dF = F/|F|; sqrt at 0 has no usable gradient
+            Fi[i] = make_float2(c * fi.x, c * fi.y);
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) red[warp] = s;
+    __syncthreads();
+    if (warp == 0) {
+        s = lane < (int)(blockDim.x >> 5) ? red[lane] : 0.f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) atomicAdd(loss, s * loss_scale);
+    }
+}
+
+__global__ void scale_store_kernel(const float* __restrict__ src, float* __restrict__ dst, float alpha, int accumulate, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = accumulate ? dst[i] + alpha * src[i] : alpha * src[i];
+}
+
+}  // namespace
+
+// loss_dev += loss_weight * reduce(...);  grad_dev (+)= grad_weight * dloss/dinput   (grad_dev may be null)
+// reduction: 0 = sum, 1 = mean.  Returns 0 on success, 1 = cuFFT unavailable / failed (message in *err), else a cudaError_t.
+int spectral_loss(const float* input, const float* target, int B, int N, int reduction, float loss_weight, float* loss_dev,
+                  float* grad_dev, float grad_weight, int grad_accumulate, cudaStream_t st, std::string* err) {
+    if (B <= 0 || N <= 0) return 0;
+    std::lock_guard<std::mutex> lock(g_spec.mu);
+    if (!g_spec.api.load()) { if (err) *err = g_spec.api.err; return 1; }
+    const int nb = N / 2 + 1;
+    auto key = std::make_pair(N, B);
+    auto it = g_spec.plans.find(key);
+    if (it == g_spec.plans.end()) {
+        cufftHandle r2c, c2r;
+        int n[1] = {N};
+        if (g_spec.api.PlanMany(&r2c, 1, n, nullptr, 1, N, nullptr, 1, nb, CUFFT_R2C, B) != CUFFT_SUCCESS ||
+            g_spec.api.PlanMany(&c2r, 1, n, nullptr, 1, nb, nullptr, 1, N, CUFFT_C2R, B) != CUFFT_SUCCESS) {
+            if (err) *err = "cufftPlanMany failed";
+            return 1;
+        }
+        it = g_spec.plans.emplace(key, std::make_pair(r2c, c2r)).first;
+    }
+    const size_t nfreq = (size_t)2 * B * nb, ntime = (size_t)B * N;
+    if (nfreq > g_spec.freq_cap) {
+        if (g_spec.freq) cudaFree(g_spec.freq);
+        cudaError_t e = cudaMalloc((void**)&g_spec.freq, nfreq * sizeof(float2));
+        if (e != cudaSuccess) { g_spec.freq = nullptr; g_spec.freq_cap = 0; return (int)e; }
+        g_spec.freq_cap = nfreq;
+    }
+    if (grad_dev && ntime > g_spec.time_cap) {
+        if (g_spec.time) cudaFree(g_spec.time);
+        cudaError_t e = cudaMalloc((void**)&g_spec.time, ntime * sizeof(float));
+        if (e != cudaSuccess) { g_spec.time = nullptr; g_spec.time_cap = 0; return (int)e; }
+        g_spec.time_cap = ntime;
+    }
+    float2* Fi = g_spec.freq;
+    float2* Ft = g_spec.freq + (size_t)B * nb;
+    const cufftHandle r2c = it->second.first, c2r = it->second.second;
+    if (g_spec.api.SetStream(r2c, st) != CUFFT_SUCCESS || g_spec.api.SetStream(c2r, st) != CUFFT_SUCCESS ||
+        g_spec.api.ExecR2C(r2c, const_cast<float*>(input), reinterpret_cast<cufftComplex*>(Fi)) != CUFFT_SUCCESS ||
+        g_spec.api.ExecR2C(r2c, const_cast<float*>(target), reinterpret_cast<cufftComplex*>(Ft)) != CUFFT_SUCCESS) {
+        if (err) *err = "cufftExecR2C failed";
+        return 1;
+    }
+    const size_t nbins = (size_t)B * nb;
+    const float red = reduction == 1 ? 1.f / ((float)B * (float)N) : 1.f;
+    const unsigned blocks = (unsigned)std::min<size_t>((nbins + 255) / 256, 148 * 8);
+    spectral_bins_kernel<<<blocks, 256, 0, st>>>(Fi, Ft, loss_dev, N, nbins, loss_weight * red, grad_dev != nullptr);
+    g_launch_count += 1;
+    if (grad_dev) {
+        if (g_spec.api.ExecC2R(c2r, reinterpret_cast<cufftComplex*>(Fi), g_spec.time) != CUFFT_SUCCESS) {
+            if (err) *err = "cufftExecC2R failed";
+            return 1;
+        }
+        scale_store_kernel<<<(unsigned)((ntime + 255) / 256), 256, 0, st>>>(g_spec.time, grad_dev, grad_weight * red * rsqrtf((float)N),
+                                                                          grad_accumulate, ntime);
+        g_launch_count += 1;
+    }
+    return (int)cudaGetLastError();
+}
+
+}  // namespace eegldm

@@ -1,0 +1,324 @@
+// Backward / loss / optimiser kernels of the AutoencoderKL training step (src/train_autoencoderkl.py:204-220):
+//   recon, mu, sigma = model(x);  loss = L1(recon, x) + kl_w * KL(mu, sigma) + spec_w * Jukebox(recon, x);  Adam step.
+// The autoencoder's channels are narrow (2..64), so everything here is fp32 SIMT and HBM / latency bound; tensors are
+// channels-last [B][T][C] like the rest of the engine, conv weights use the SIMT image [(ci*taps + k)][Cout].
+// (The cuFFT side of the spectral loss is in spectral.cu.)
+#include "kernels.cuh"
+
+namespace eegldm {
+namespace {
+
+__device__ __forceinline__ float sigmoid_f(float v) { return 1.f / (1.f + expf(-v)); }
+
+template <int N>
+__device__ __forceinline__ void block_reduce_sum(float (&v)[N], float* sm /* [N][32] */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
+        if (lane == 0) sm[i * 32 + warp] = v[i];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        float s = (threadIdx.x < nw) ? sm[i * 32 + threadIdx.x] : 0.f;
+        if (warp == 0) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        }
+        v[i] = s;   // valid in thread 0
+    }
+    __syncthreads();
+}
+
+// a = silu?(scale[b][c] * x + shift[b][c])
+__global__ void norm_act_fwd_kernel(const float* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
+                                    float* __restrict__ a, int C, int T, int silu, size_t total) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c = (int)(i % C);
+    const size_t b = i / ((size_t)C * T);
+    float v = fmaf(scale[b * C + c], x[i], shift[b * C + c]);
+    if (silu) v = v * sigmoid_f(v);
+    a[i] = v;
+}
+
+// Conv1d backward w.r.t. its input.  The conv consumed u = upsample?(a) with length Tc, stride s, left pad p:
+//   y[t][co] = sum_{k,ci} W[ci][k][co] * u[t*s + k - p][ci]        da[b][i][ci] (+)= sum over the conv-input rows that read a[i]
+__global__ void conv_bwd_data_kernel(const float* __restrict__ dy, const float* __restrict__ w, float* __restrict__ da, int Cin,
+                                     int Cout, int taps, int stride, int pad, int ups, int Tin, int Tc, int Tout, int accumulate,
+                                     size_t total) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int ci = (int)(idx % Cin);
+    const size_t bt = idx / Cin;
+    const int i = (int)(bt % Tin);
+    const size_t b = bt / Tin;
+    float acc = 0.f;
+    const int n_uc = ups ? 2 : 1;
+    for (int j = 0; j < n_uc; ++j) {
+        const int uc = ups ? 2 * i + j : i;
+        if (uc >= Tc) continue;
+        for (int k = 0; k < taps; ++k) {
+            const int num = uc + pad - k;
+            if (num < 0 || num % stride) continue;
+            const int t = num / stride;
+            if (t >= Tout) continue;
+            const float* dyr = dy + (b * Tout + t) * Cout;
+            const float* wr = w + (size_t)(ci * taps + k) * Cout;
+            for (int co = 0; co < Cout; ++co) acc = fmaf(dyr[co], __ldg(wr + co), acc);
+        }
+    }
+    da[idx] = accumulate ? da[idx] + acc : acc;
+}
+
+// Conv1d backward w.r.t. weight and bias; grid (ceil(Tout/P), B), dynamic smem: dy tile [P][Cout] + input tile [P*stride+taps-1][Cin]
+constexpr int WG_P = 64;
+__global__ void __launch_bounds__(256) conv_bwd_weight_kernel(const float* __restrict__ dy, const float* __restrict__ a,
+                                                               float* __restrict__ dw, float* __restrict__ db, int Cin, int Cout,
+                                                               int taps, int stride, int pad, int ups, int Tin, int Tc, int Tout) {
+    extern __shared__ float sm[];
+    float* dys = sm;                       // [P][Cout]
+    float* as = sm + WG_P * Cout;          // [rows][Cin]
+    const int b = blockIdx.y, t0 = blockIdx.x * WG_P;
+    const int np = min(WG_P, Tout - t0);
+    const int rows = (WG_P - 1) * stride + taps;
+    const int u0 = t0 * stride - pad;
+    for (int i = threadIdx.x; i < WG_P * Cout; i += blockDim.x) {
+        const int p = i / Cout, co = i % Cout;
+        dys[i] = p < np ? dy[((size_t)b * Tout + t0 + p) * Cout + co] : 0.f;
+    }
+    for (int i = threadIdx.x; i < rows * Cin; i += blockDim.x) {
+        const int r = i / Cin, ci = i % Cin;
+        const int uc = u0 + r;
+        float v = 0.f;
+        if (uc >= 0 && uc < Tc) v = a[((size_t)b * Tin + (ups ? (uc >> 1) : uc)) * Cin + ci];
+        as[i] = v;
+    }
+    __syncthreads();
+    const int nw = Cin * taps * Cout;
+    for (int i = threadIdx.x; i < nw; i += blockDim.x) {
+        const int co = i % Cout, ck = i / Cout, k = ck % taps, ci = ck / taps;   // i == packed weight index
+        float acc = 0.f;
+        for (int p = 0; p < np; ++p) acc = fmaf(dys[p * Cout + co], as[(p * stride + k) * Cin + ci], acc);
+        atomicAdd(dw + i, acc);
+    }
+    if (db)
+        for (int co = threadIdx.x; co < Cout; co += blockDim.x) {
+            float acc = 0.f;
+            for (int p = 0; p < np; ++p) acc += dys[p * Cout + co];
+            atomicAdd(db + co, acc);
+        }
+}
+
+// GroupNorm(+SiLU) backward, pass 1: per (sample, group) means of g = dv*gamma and g*xhat; per-channel dgamma / dbeta.
+//   v = xhat*gamma + beta,  a = silu?(v),  dv = da * silu'(v)
+// grid (G, B), block 256; requires cpg = C/G <= 256.
+__global__ void __launch_bounds__(256) norm_act_bwd_reduce_kernel(const float* __restrict__ da, const float* __restrict__ x,
+                                                                   const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                   float* __restrict__ m12 /* [B][G][2] */, float* __restrict__ dgamma,
+                                                                   float* __restrict__ dbeta, int C, int T, int G, int silu) {
+    __shared__ float red[2 * 32];
+    __shared__ float chs[2 * 256];
+    const int g = blockIdx.x, b = blockIdx.y, cpg = C / G;
+    const float mu = mean[b * G + g], rs = rstd[b * G + g];
+    const int cl = threadIdx.x % cpg, tl = threadIdx.x / cpg, tstep = blockDim.x / cpg;
+    const int c = g * cpg + cl;
+    const float ga = gamma[c], be = beta[c];
+    float s[2] = {0.f, 0.f};
+    float dg = 0.f, dbv = 0.f;
+    if (tl < tstep)
+        for (int t = tl; t < T; t += tstep) {
+            const size_t i = ((size_t)b * T + t) * C + c;
+            const float xh = (x[i] - mu) * rs;
+            const float v = fmaf(xh, ga, be);
+            float dv = da[i];
+            if (silu) { const float sg = sigmoid_f(v); dv *= sg * (1.f + v * (1.f - sg)); }
+            s[0] += dv * ga;
+            s[1] += dv * ga * xh;
+            dg += dv * xh;
+            dbv += dv;
+        }
+    chs[threadIdx.x] = dg;
+    chs[256 + threadIdx.x] = dbv;
+    block_reduce_sum<2>(s, red);   // contains __syncthreads
+    if (threadIdx.x == 0) {
+        const float n = (float)cpg * (float)T;
+        m12[((size_t)b * G + g) * 2 + 0] = s[0] / n;
+        m12[((size_t)b * G + g) * 2 + 1] = s[1] / n;
+    }
+    if ((int)threadIdx.x < cpg) {
+        float a0 = 0.f, a1 = 0.f;
+        for (int j = threadIdx.x; j < tstep * cpg; j += cpg) { a0 += chs[j]; a1 += chs[256 + j]; }
+        atomicAdd(dgamma + c, a0);
+        atomicAdd(dbeta + c, a1);
+    }
+}
+
+// pass 2: dx (+)= rstd * (dv*gamma - m1 - xhat*m2)
+__global__ void norm_act_bwd_apply_kernel(const float* __restrict__ da, const float* __restrict__ x, const float* __restrict__ mean,
+                                          const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                          const float* __restrict__ beta, const float* __restrict__ m12, float* __restrict__ dx, int C,
+                                          int T, int G, int silu, int accumulate, size_t total) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c = (int)(i % C);
+    const size_t b = i / ((size_t)C * T);
+    const int g = c / (C / G);
+    const float mu = mean[b * G + g], rs = rstd[b * G + g], ga = gamma[c];
+    const float xh = (x[i] - mu) * rs;
+    const float v = fmaf(xh, ga, beta[c]);
+    float dv = da[i];
+    if (silu) { const float sg = sigmoid_f(v); dv *= sg * (1.f + v * (1.f - sg)); }
+    const float r = rs * (dv * ga - m12[(b * G + g) * 2] - xh * m12[(b * G + g) * 2 + 1]);
+    dx[i] = accumulate ? dx[i] + r : r;
+}
+
+__global__ void axpy_kernel(const float* __restrict__ src, float* __restrict__ dst, float alpha, int accumulate, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = accumulate ? dst[i] + alpha * src[i] : alpha * src[i];
+}
+
+// L1Loss(mean): loss += sum|r-x| / n ;  drecon = w * sign(r-x)/n
+__global__ void __launch_bounds__(256) l1_loss_kernel(const float* __restrict__ r, const float* __restrict__ x, float* __restrict__ dr,
+                                                       float* __restrict__ loss, float weight, size_t n) {
+    __shared__ float red[32];
+    float s[1] = {0.f};
+    const float inv = 1.f / (float)n;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float d = r[i] - x[i];
+        s[0] += fabsf(d);
+        dr[i] = weight * inv * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f));
+    }
+    block_reduce_sum<1>(s, red);
+    if (threadIdx.x == 0) atomicAdd(loss, s[0] * inv);
+}
+
+// KL term of train_autoencoderkl.py:210-211 and the reparameterisation z = mu + eps*sigma, sigma = exp(clamp(lv,-30,20)/2).
+// forward (dz == null): writes sigma, z.   backward (dz != null): dmu = dz + kl_w*mu/B ; dlv = (dz*eps + kl_w*(sigma - 1/sigma)/B) * sigma/2 (0 outside the clamp)
+__global__ void __launch_bounds__(256) latent_kernel(const float* __restrict__ mu, const float* __restrict__ lv, const float* __restrict__ eps,
+                                                      float* __restrict__ sigma, float* __restrict__ z, const float* __restrict__ dz,
+                                                      float* __restrict__ dmu, float* __restrict__ dlv, float* __restrict__ kl_loss,
+                                                      float kl_weight, int B, size_t n) {
+    __shared__ float red[32];
+    float s[1] = {0.f};
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float raw = lv[i];
+        const float sg = expf(fminf(fmaxf(raw, -30.f), 20.f) * 0.5f);
+        if (!dz) {
+            sigma[i] = sg;
+            z[i] = fmaf(eps[i], sg, mu[i]);
+            const float m = mu[i];
+            s[0] += 0.5f * (m * m + sg * sg - logf(sg * sg) - 1.f);
+        } else {
+            const float m = mu[i];
+            dmu[i] = dz[i] + kl_weight * m / (float)B;
+            const float dsg = dz[i] * eps[i] + kl_weight * (sg - 1.f / sg) / (float)B;
+            dlv[i] = (raw > -30.f && raw < 20.f) ? dsg * sg * 0.5f : 0.f;
+        }
+    }
+    if (!dz) {
+        block_reduce_sum<1>(s, red);
+        if (threadIdx.x == 0) atomicAdd(kl_loss, s[0] / (float)B);
+    }
+}
+
+// torch.optim.Adam (no weight decay, amsgrad off)
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, float lr,
+                            float b1, float b2, float eps, float bc1, float bc2_sqrt, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float gi = g[i];
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    p[i] -= (lr / bc1) * mi / (sqrtf(vi) / bc2_sqrt + eps);
+}
+
+unsigned blocks_for(size_t n, int bs = 256) { return (unsigned)((n + bs - 1) / bs); }
+
+}  // namespace
+
+cudaError_t launch_norm_act_fwd(const float* x, const float* scale, const float* shift, float* a, int B, int T, int C, int silu,
+                                cudaStream_t st) {
+    const size_t total = (size_t)B * T * C;
+    if (!total) return cudaSuccess;
+    norm_act_fwd_kernel<<<blocks_for(total), 256, 0, st>>>(x, scale, shift, a, C, T, silu, total);
+    g_launch_count += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_conv_bwd_data(const ConvGradParams& p, cudaStream_t st) {
+    const size_t total = (size_t)p.B * p.Tin * p.Cin;
+    if (!total) return cudaSuccess;
+    conv_bwd_data_kernel<<<blocks_for(total), 256, 0, st>>>(p.dy, p.w, p.da, p.Cin, p.Cout, p.taps, p.stride, p.pad, p.ups, p.Tin, p.Tc,
+                                                            p.Tout, p.accumulate, total);
+    g_launch_count += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_conv_bwd_weight(const ConvGradParams& p, cudaStream_t st) {
+    if (p.B <= 0 || p.Tout <= 0) return cudaSuccess;
+    const int rows = (WG_P - 1) * p.stride + p.taps;
+    const size_t smem = ((size_t)WG_P * p.Cout + (size_t)rows * p.Cin) * sizeof(float);
+    if (smem > 200 * 1024) return cudaErrorInvalidValue;
+    static size_t attr = 0;
+    if (smem > 48 * 1024 && smem > attr) {
+        cudaError_t e = cudaFuncSetAttribute(conv_bwd_weight_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;
+        attr = 200 * 1024;
+    }
+    dim3 grid((p.Tout + WG_P - 1) / WG_P, p.B);
+    conv_bwd_weight_kernel<<<grid, 256, smem, st>>>(p.dy, p.a, p.dw, p.db, p.Cin, p.Cout, p.taps, p.stride, p.pad, p.ups, p.Tin, p.Tc, p.Tout);
+    g_launch_count += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_norm_act_bwd(const NormGradParams& p, cudaStream_t st) {
+    if (p.B <= 0) return cudaSuccess;
+    if (p.C / p.G > 256) return cudaErrorInvalidValue;
+    dim3 grid(p.G, p.B);
+    norm_act_bwd_reduce_kernel<<<grid, 256, 0, st>>>(p.da, p.x, p.mean, p.rstd, p.gamma, p.beta, p.m12, p.dgamma, p.dbeta, p.C, p.T, p.G, p.silu);
+    const size_t total = (size_t)p.B * p.T * p.C;
+    norm_act_bwd_apply_kernel<<<blocks_for(total), 256, 0, st>>>(p.da, p.x, p.mean, p.rstd, p.gamma, p.beta, p.m12, p.dx, p.C, p.T, p.G, p.silu,
+                                                                p.accumulate, total);
+    g_launch_count += 2;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_axpy(const float* src, float* dst, float alpha, int accumulate, size_t n, cudaStream_t st) {
+    if (!n) return cudaSuccess;
+    axpy_kernel<<<blocks_for(n), 256, 0, st>>>(src, dst, alpha, accumulate, n);
+    g_launch_count += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_l1_loss(const float* r, const float* x, float* dr, float* loss, float weight, size_t n, cudaStream_t st) {
+    if (!n) return cudaSuccess;
+    const unsigned blocks = (unsigned)std::min<size_t>((n + 255) / 256, 148 * 8);
+    l1_loss_kernel<<<blocks, 256, 0, st>>>(r, x, dr, loss, weight, n);
+    g_launch_count += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_latent(const float* mu, const float* lv, const float* eps, float* sigma, float* z, const float* dz, float* dmu,
+                          float* dlv, float* kl_loss, float kl_weight, int B, size_t n, cudaStream_t st) {
+    if (!n) return cudaSuccess;
+    const unsigned blocks = (unsigned)std::min<size_t>((n + 255) / 256, 148 * 8);
+    latent_kernel<<<blocks, 256, 0, st>>>(mu, lv, eps, sigma, z, dz, dmu, dlv, kl_loss, kl_weight, B, n);
+    g_launch_count += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_adam(float* p, const float* g, float* m, float* v, float lr, float b1, float b2, float eps, int step, size_t n,
+                        cudaStream_t st) {
+    if (!n) return cudaSuccess;
+    const float bc1 = 1.f - powf(b1, (float)step), bc2 = 1.f - powf(b2, (float)step);
+    adam_kernel<<<blocks_for(n), 256, 0, st>>>(p, g, m, v, lr, b1, b2, eps, bc1, sqrtf(bc2), n);
+    g_launch_count += 1;
+    return cudaGetLastError();
+}
+
+}  // namespace eegldm

@@ -38,6 +38,11 @@ class AeklCfg(C.Structure):
     ]
 
 
+class AeklTrainCfg(C.Structure):
+    _fields_ = [("kl_weight", C.c_float), ("spectral_weight", C.c_float), ("lr", C.c_float), ("beta1", C.c_float),
+                ("beta2", C.c_float), ("adam_eps", C.c_float)]
+
+
 class SchedCfg(C.Structure):
     _fields_ = [
         ("num_train_timesteps", C.c_int32), ("beta_start", C.c_float), ("beta_end", C.c_float),
@@ -82,6 +87,10 @@ SIGNATURES = {
     "eegldm_aekl_encode": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, _P]),
     "eegldm_aekl_decode": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P]),
     "eegldm_aekl_forward": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, _P]),
+    "eegldm_jukebox_loss": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
+    "eegldm_aekl_train_step": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.POINTER(AeklTrainCfg), _FP, _P]),
+    "eegldm_aekl_train_export": (C.c_int, [_P, C.c_int, C.c_char_p, _FP]),
+    "eegldm_aekl_train_sync": (C.c_int, [_P]),
     "eegldm_sched_alphas_cumprod": (C.c_int, [C.POINTER(SchedCfg), _FP]),
     "eegldm_sched_ddim_tables": (C.c_int, [C.POINTER(SchedCfg), C.c_int, _I64P, _FP]),
     "eegldm_timestep_embedding": (C.c_int, [_FP, C.c_int, C.c_int, _FP]),

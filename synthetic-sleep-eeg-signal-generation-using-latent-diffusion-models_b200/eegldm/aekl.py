@@ -105,6 +105,56 @@ class AutoencoderKL(EngineModule):
                 C.c_void_p(_lib.current_stream_ptr(z.device))))
         return out
 
+    # --- training step (generator half of src/train_autoencoderkl.py:204-220) ------------------------
+    def train_step(self, x, eps=None, kl_weight=1e-9, spectral_weight=1e4, lr=5e-3, betas=(0.9, 0.999), adam_eps=1e-8,
+                   return_losses=True):
+        """One fused step on the device: forward, L1 + kl_weight*KL + spectral_weight*JukeboxLoss, backward, Adam.
+        ``eps`` is the reparameterisation noise (drawn with torch.randn if omitted); ``lr <= 0`` computes losses and
+        gradients only.  Parameters are updated inside the engine; call ``sync_trained()`` to copy them back into this
+        module's ``nn.Parameter``s / the inference weights.  Returns {"l1", "kl", "spectral", "total"} (one sync)."""
+        x = check_cuda_f32(x, "x")
+        B, Cin, Lx = x.shape
+        T = Lx // self._factor
+        if eps is None:
+            eps = torch.randn((B, self.latent_channels, T), device=x.device, dtype=torch.float32)
+        eps = check_cuda_f32(eps, "eps")
+        cfg = _lib.AeklTrainCfg(float(kl_weight), float(spectral_weight), float(lr), float(betas[0]), float(betas[1]), float(adam_eps))
+        out = (C.c_float * 4)()
+        with torch.cuda.device(x.device):
+            self._sync_weights()
+            _lib.check(_lib.lib().eegldm_aekl_train_step(
+                self._h, C.c_void_p(x.data_ptr()), C.c_void_p(eps.data_ptr()), int(B), int(Lx), C.byref(cfg),
+                out if return_losses else None, C.c_void_p(_lib.current_stream_ptr(x.device))))
+        self._trained = True
+        if return_losses:
+            return {"l1": out[0], "kl": out[1], "spectral": out[2], "total": out[3]}
+        return None
+
+    def _export(self, what: int):
+        res = {}
+        L = _lib.lib()
+        for name, p in self.named_parameters():
+            buf = torch.empty(tuple(p.shape), dtype=torch.float32)
+            _lib.check(L.eegldm_aekl_train_export(self._h, what, name.encode(), C.cast(C.c_void_p(buf.data_ptr()), C.POINTER(C.c_float))))
+            res[name] = buf
+        return res
+
+    def grad_dict(self):
+        """Gradients of the last train_step, keyed and laid out like ``state_dict()``."""
+        return self._export(1)
+
+    @torch.no_grad()
+    def sync_trained(self):
+        """Copy the engine's trained parameters into this module and into the inference weights."""
+        if not getattr(self, "_trained", False):
+            return self
+        new = self._export(0)
+        for name, p in self.named_parameters():
+            p.copy_(new[name].to(p.device))
+        _lib.check(_lib.lib().eegldm_aekl_train_sync(self._h))
+        self._uploaded_key = self._weights_key()   # the engine already holds exactly these values
+        return self
+
     def reconstruct(self, x):
         z_mu, _ = self.encode(x)
         return self.decode(z_mu)
