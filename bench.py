@@ -273,6 +273,79 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_train(args):
+    """Config 5: AutoencoderKL training step (2-2-4, z=1, batch 512, L1 + 1e-9 KL + 1e4 Jukebox, Adam lr 5e-3;
+    adversarial term excluded -- the PatchDiscriminator is a SURVEY 8(f) 'next' row)."""
+    import torch
+    import eegldm
+    from oracle import aekl as oa, jukebox as oj
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    cfg = oa.full_cfg()
+    sd = oa.make_aekl_state_dict(cfg, 42)
+    m = eegldm.AutoencoderKL(**cfg)
+    m.load_state_dict(sd)
+    m = m.to(dev)
+    B = args.batch if args.batch != 1024 else 512
+    xh = torch.rand(B, 1, 3072, generator=torch.Generator().manual_seed(0)).pin_memory()
+    eh = torch.randn(B, 1, 768, generator=torch.Generator().manual_seed(1)).pin_memory()
+    x, eps = xh.to(dev), eh.to(dev)
+    for _ in range(args.warmup):
+        m.train_step(x, eps, return_losses=False)
+    torch.cuda.synchronize()
+    l0 = eegldm.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        m.train_step(x, eps, return_losses=False)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    launches = eegldm.launch_count() - l0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):   # e2e: batch from pinned host memory, losses read back every step
+        m.train_step(xh.to(dev, non_blocking=True), eh.to(dev, non_blocking=True))
+    torch.cuda.synchronize()
+    ms_e2e = (time.perf_counter() - t0) * 1e3 / args.steps
+    # CPU baseline: the oracle with torch autograd + Adam, bounded sample
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    Bc = 16
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    opt = torch.optim.Adam(list(params.values()), lr=5e-3)
+    xc, ec = xh[:Bc].clone(), eh[:Bc].clone()
+    def cpu_step():
+        opt.zero_grad(set_to_none=True)
+        recon, mu, sigma = oa.forward(cfg, params, xc, ec)
+        loss = torch.nn.functional.l1_loss(recon, xc) + 1e-9 * oa.kl_loss(mu, sigma) + 1e4 * oj.jukebox_loss(recon, xc)
+        loss.backward()
+        opt.step()
+    cpu_step()
+    t0 = time.perf_counter()
+    n = 5
+    for _ in range(n):
+        cpu_step()
+    cpu = Bc * n / (time.perf_counter() - t0)
+    peaks = _peaks()
+    # algorithmic HBM bytes per window of the step: every activation of the 2-2-4 autoencoder written once and read once in the
+    # forward pass and once more in the backward pass, gradients written + read once (fp32): ~ 3 x 2 x sum(C*T) x 4 B
+    acts = 4 * (3072 * (1 + 2 * 9) + 1536 * 2 * 9 + 768 * (4 * 9 + 4))   # rough per-direction activation bytes / window
+    line = {"metric": "AEKL training-step windows/sec", "value": B / (ms / 1e3), "unit": "windows/s", "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "config 5: AutoencoderKL 2-2-4 z=1 training step, batch %d x [1,3072], L1 + 1e-9 KL + 1e4 Jukebox "
+                                   "(adversarial term excluded), Adam lr 5e-3" % B},
+            "e2e": {"value": B / (ms_e2e / 1e3), "unit": "windows/s", "h2d_bytes_per_step": (xh.numel() + eh.numel()) * 4,
+                    "d2h_bytes_per_step": 16, "ms_per_step": ms_e2e},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": 6 * acts * B / (ms / 1e3) / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
+                         "frac": 6 * acts * B / (ms / 1e3) / 1e9 / peaks["hbm"], "traffic": None,
+                         "note": "whole step (about %d launches of narrow-channel SIMT kernels); latency / launch bound" % (launches // max(args.steps, 1))},
+            "cpu_baseline": {"value": cpu, "unit": "windows/s", "cores": threads, "kind": "port",
+                             "sample": f"{Bc} windows x {n} steps, oracle forward + torch autograd + Adam"}}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -284,8 +357,12 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=8, help="windows per CPU-baseline step (bounded sample)")
     ap.add_argument("--profile-batch", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="sample", choices=["sample", "train"],
+                    help="sample = config 3/4 (headline); train = config 5 (AEKL training step)")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.workload == "train":
+        run_train(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

@@ -8,6 +8,8 @@
 //   attention            = QKVAttentionLegacy.forward                      unet.py:107-125
 #include "kernels.cuh"
 
+#include <algorithm>
+
 namespace eegldm {
 namespace {
 
@@ -235,6 +237,99 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvParams p) {
             if (p.ddim_x) v = p.ddim_coef[0] * p.ddim_x[o] + p.ddim_coef[1] * v;
             p.out[o] = v;
         }
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Narrow-input conv (UNet input conv, unet.py:385: Conv1d(z -> model_channels, 3, padding=1), z <= 4): pure HBM-write bound.
+// One thread = one position x 4 output channels; weights/bias in shared memory.
+__global__ void __launch_bounds__(256) conv_narrow_in_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                              const float* __restrict__ bias, float* __restrict__ out, int Cin, int Cout,
+                                                              int T, size_t total4) {
+    extern __shared__ float ws[];   // [Cin*3][Cout] + [Cout]
+    for (int i = threadIdx.x; i < Cin * 3 * Cout; i += blockDim.x) ws[i] = w[i];
+    for (int i = threadIdx.x; i < Cout; i += blockDim.x) ws[Cin * 3 * Cout + i] = bias ? bias[i] : 0.f;
+    __syncthreads();
+    const int q = Cout >> 2;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
+        const int co = (int)(i % q) * 4;
+        const size_t bt = i / q;
+        const int t = (int)(bt % T);
+        float4 acc = *reinterpret_cast<const float4*>(ws + Cin * 3 * Cout + co);
+        for (int k = 0; k < 3; ++k) {
+            const int u = t + k - 1;
+            if (u < 0 || u >= T) continue;
+            const float* xr = x + (bt + k - 1) * Cin;
+            for (int ci = 0; ci < Cin; ++ci) {
+                const float xv = __ldg(xr + ci);
+                const float4 wv = *reinterpret_cast<const float4*>(ws + (ci * 3 + k) * Cout + co);
+                acc.x = fmaf(xv, wv.x, acc.x); acc.y = fmaf(xv, wv.y, acc.y); acc.z = fmaf(xv, wv.z, acc.z); acc.w = fmaf(xv, wv.w, acc.w);
+            }
+        }
+        *reinterpret_cast<float4*>(out + bt * Cout + co) = acc;
+    }
+}
+
+// Narrow-output conv (UNet output head, unet.py:501-505: Conv1d(model_channels -> z, 3, padding=1) on SiLU(GN(h)), z <= 4)
+// with the DDIM update in the epilogue: pure HBM-read bound.  One warp walks a strip of positions; each lane owns 4 of every
+// 128 input channels, applies the GroupNorm affine + SiLU once per element and scatters it into the 3 output rows it feeds;
+// a rolling window of 3 partial rows is warp-reduced as each row completes.
+constexpr int NO_STRIP = 32;
+template <int CO>
+__global__ void __launch_bounds__(256) conv_narrow_out_kernel(const ConvParams p) {
+    const ConvSeg& sg = p.seg[0];
+    const int Cin = sg.C0, T = p.Tout;
+    const int lane = threadIdx.x & 31;
+    const int strips = (T + NO_STRIP - 1) / NO_STRIP;
+    const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (wid >= (long long)p.B * strips) return;
+    const int b = (int)(wid / strips), t0 = (int)(wid % strips) * NO_STRIP;
+    const int t1 = min(T, t0 + NO_STRIP);
+    float acc[3][CO];   // partial sums of output rows r-1, r, r+1 (rolling)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+        for (int c = 0; c < CO; ++c) acc[j][c] = 0.f;
+    const float* hb = sg.src0 + (size_t)b * T * Cin;
+    for (int r = t0 - 1; r <= t1; ++r) {   // input rows feeding outputs t0..t1-1
+        if (r >= 0 && r < T) {
+            for (int c0 = lane * 4; c0 < Cin; c0 += 128) {
+                const float4 hv = ld4(hb + (size_t)r * Cin + c0);
+                float v[4] = {hv.x, hv.y, hv.z, hv.w};
+                if (sg.scale) {
+                    const float4 a4 = ld4(sg.scale + (size_t)b * Cin + c0), s4 = ld4(sg.shift + (size_t)b * Cin + c0);
+                    v[0] = act1(v[0], a4.x, s4.x, sg.silu); v[1] = act1(v[1], a4.y, s4.y, sg.silu);
+                    v[2] = act1(v[2], a4.z, s4.z, sg.silu); v[3] = act1(v[3], a4.w, s4.w, sg.silu);
+                }
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {   // input row r is tap k of output row r + 1 - k  ->  window slot 2 - k
+                        const float* wr = sg.w + (size_t)((c0 + e) * 3 + k) * p.Cout;
+#pragma unroll
+                        for (int c = 0; c < CO; ++c) if (c < p.Cout) acc[2 - k][c] = fmaf(v[e], __ldg(wr + c), acc[2 - k][c]);
+                    }
+            }
+        }
+        // output row r-1 is complete once input row r has been added
+        const int to = r - 1;
+        if (to >= t0 && to < t1) {
+#pragma unroll
+            for (int c = 0; c < CO; ++c) {
+                float s = acc[0][c];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                if (lane == c && c < p.Cout) {
+                    float val = s + (p.bias ? p.bias[c] : 0.f);
+                    const size_t oi = ((size_t)b * T + to) * p.Cout + c;
+                    if (p.ddim_x) val = p.ddim_coef[0] * p.ddim_x[oi] + p.ddim_coef[1] * val;
+                    p.out[oi] = val;
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < CO; ++c) { acc[0][c] = acc[1][c]; acc[1][c] = acc[2][c]; acc[2][c] = 0.f; }
     }
 }
 
@@ -532,6 +627,23 @@ __global__ void axpy_sampling_kernel(const float* __restrict__ mu, const float* 
 // ================================================================================================ launchers
 cudaError_t launch_conv_simt(const ConvParams& p, cudaStream_t st) {
     if (p.B <= 0) return cudaSuccess;
+    const ConvSeg& s0 = p.seg[0];
+    const bool plain = p.nseg == 1 && s0.taps == 3 && p.stride == 1 && p.pad_left == 1 && !s0.src1 && s0.resample == RS_NONE &&
+                       p.Tc == p.Tout && !p.temb && !p.res;
+    if (plain && s0.C0 <= 4 && !s0.scale && !p.ddim_x && (p.Cout & 3) == 0 && p.Cout >= 32 && (size_t)(s0.C0 * 3 + 1) * p.Cout * sizeof(float) <= 40 * 1024) {
+        const size_t total4 = (size_t)p.B * p.Tout * (p.Cout / 4);
+        const size_t smem = ((size_t)s0.C0 * 3 * p.Cout + p.Cout) * sizeof(float);
+        const unsigned blocks = (unsigned)std::min<size_t>((total4 + 255) / 256, 148 * 16);
+        conv_narrow_in_kernel<<<blocks, 256, smem, st>>>(s0.src0, s0.w, p.bias, p.out, s0.C0, p.Cout, p.Tout, total4);
+        g_launch_count += 1;
+        return cudaGetLastError();
+    }
+    if (plain && p.Cout <= 4 && s0.C0 % 128 == 0) {
+        const long long warps = (long long)p.B * ((p.Tout + NO_STRIP - 1) / NO_STRIP);
+        conv_narrow_out_kernel<4><<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(p);
+        g_launch_count += 1;
+        return cudaGetLastError();
+    }
     const int gx = (p.Tout + BN - 1) / BN;
     if (p.Cout >= 96) {
         dim3 grid(gx, (p.Cout + 127) / 128, p.B);
