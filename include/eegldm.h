@@ -54,6 +54,11 @@ int64_t eegldm_launch_count(void);
 /* Tuning knob of the tcgen05 conv kernel: CTAs per thread-block cluster that share each weight stage through a
  * multicast bulk copy (1, 2 or 4; default 2).  Changing it invalidates nothing but must not race with launches. */
 int eegldm_set_conv_cluster(int ctas);
+/* Shape selection of the tcgen05 conv kernel.  pair = 1: the two CTAs of a cluster issue one M=256 cta_group::2 MMA over
+ * both (each stages half of the weight columns); pair = 0 (default, measured faster): single-CTA MMAs with the multicast
+ * cluster of eegldm_set_conv_cluster.  bn256_min_stages (default 1): tiles are 256 output channels wide when Cout % 256 == 0
+ * and a tile's mainloop has at least this many weight stages (else 128).  Call before creating models: plans cache it. */
+int eegldm_set_conv_tuning(int pair, int bn256_min_stages);
 
 /* Live per-kernel profile (bench.py's roofline leg).  While enabled, every launch made outside CUDA-graph
  * capture is bracketed by CUDA events on the launching stream.  eegldm_profile_read sums, for one kernel
@@ -208,6 +213,10 @@ int eegldm_set_graphs(int enabled);
 int eegldm_test_conv(const float* x_dev, const float* scale_dev, const float* shift_dev, int silu, int resample,
                      const float* w_host, const float* bias_host, const float* res_dev, int B, int Tin, int Cin, int Cout, int k,
                      int math, float* out_dev, void* stream);
+/* Timing hook (tools/conv_bench.py): average milliseconds of `reps` launches of the tcgen05 convolution on synthetic
+ * data of the given shape; debug 0 = real kernel, 1 = operand copies skipped, 2 = MMAs skipped (timing experiments). */
+int eegldm_bench_conv(int B, int T, int Cin, int Cout, int k, int with_res, int math, int debug, int reps, float* ms_out,
+                      void* stream);
 
 /* Test hook: ONE attention launch, QKVAttentionLegacy.forward (unet.py:107-125), on channels-last
  * qkv [B][T][H*3*ch] (legacy head layout) -> out [B][T][H*ch].  Synchronises the stream. */

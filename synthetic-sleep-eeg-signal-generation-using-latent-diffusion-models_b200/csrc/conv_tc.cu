@@ -50,12 +50,16 @@ constexpr int A_LBO = SLOTS * A_SBO;   // bytes between core matrices along K (8
 constexpr int A_TILE = (BK / 8) * A_LBO;   // one hi (or lo) activation tile: 9216 B
 constexpr int A_STAGE = 2 * A_TILE;
 static_assert(A_TILE == TC_U_HALF_BYTES, "engine and kernel disagree on the U tile size");
-constexpr int B_SBO = 128;
-constexpr int NA = 4;              // activation ring (18 KB stages)
-constexpr int B_RING_BYTES = 128 * 1024;   // weight ring: 4 x 32 KB (N=256) or 8 x 16 KB (N=128)
+constexpr int B_LBO = 128;         // weight image: bytes between the 8-channel K chunks of one 8-column group
+constexpr int B_SBO = (BK / 8) * B_LBO;    // bytes between 8-column groups (512): any N tile is a contiguous slice
 constexpr int N_ITEMS = 8 * SLOTS * (BK / 8);   // 576 16-byte items per activation tile
-constexpr int STAGING_OFF = NA * A_STAGE + B_RING_BYTES + 256;   // 4 warps x [32][33] fp32 epilogue transpose buffers
-constexpr int SMEM_BYTES = STAGING_OFF + 4 * 32 * 33 * 4;
+// shared-memory plan: activation ring | weight ring | mbarriers (<= 8*(2*6 + 2*16 + 4) = 384 B), TMEM slot at +448 |
+// 4 warps x [32][33] fp32 epilogue transpose buffers.  A CTA pair stages half the weight bytes per MMA, so it trades
+// weight-ring bytes for two more activation stages (the activation stream comes from HBM: latency x bandwidth).
+__host__ __device__ constexpr int ring_na(bool pair) { return pair ? 6 : 4; }                        // 18 KB stages
+__host__ __device__ constexpr int ring_b_bytes(bool pair) { return (pair ? 96 : 128) * 1024; }       // 3 x 32 KB ... 12 x 8 KB stages
+__host__ __device__ constexpr int bar_off(bool pair) { return ring_na(pair) * A_STAGE + ring_b_bytes(pair); }
+__host__ __device__ constexpr int smem_bytes(bool pair) { return bar_off(pair) + 512 + 4 * 32 * 33 * 4; }
 constexpr int NUM_THREADS = 192;
 constexpr int SPLIT_THREADS = 192;
 static_assert(N_ITEMS % SPLIT_THREADS == 0, "items must divide evenly over the act_split block");
@@ -145,19 +149,30 @@ __global__ void __launch_bounds__(SPLIT_THREADS) act_split_kernel(const ActSplit
 // two TMEM accumulator sets, so the epilogue of tile i overlaps the mainloop of tile i+1.
 // CL CTAs of a cluster work on CL consecutive M tiles of the same N tile: the weight stage is identical for all of them,
 // so each CTA fetches 1/CL of it and multicasts it to the whole cluster (L2 -> SM weight traffic / CL).
-template <bool X3, int BN, int CL>
+//
+// PAIR (cta_group::2): the two CTAs of a cluster form one M=256 x N=BN MMA.  Each CTA stages its own 128-row activation
+// tile and only ITS HALF of the weight columns (BN/2), the leader (cluster rank 0) issues every MMA for both, and each
+// CTA drains its own 128 TMEM lanes.  Per MMA an SM then reads 4 KB of A + BN/2 x 32 B of B instead of BN x 32 B, and
+// stages half the weight bytes: the shared-memory operand traffic that bounds the single-CTA shape (profiles/r01_summary.md)
+// drops below the tensor pipe's time.  Synchronisation: loads complete on each CTA's own "full" mbarriers; warp 5 of the
+// peer relays them to the leader's (count 2 = own expect_tx arrive + relay); the leader's tcgen05.commit multicasts the
+// "empty" / "accumulator full" arrivals to both CTAs; both CTAs' epilogue threads arrive on the leader's "accumulator empty".
+template <bool X3, int BN, int CL, bool PAIR>
 __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const TcConvParams p) {
-    constexpr int B_LBO = (BN / 8) * B_SBO;    // bytes between 8-channel K chunks of the weight tile
-    constexpr int B_HALF = (BK / 8) * B_LBO;   // hi (or lo) weight tile of one (tap, k-step): BN x 32 x 2 B
+    static_assert(!PAIR || CL == 2, "a CTA pair is a cluster of 2");
+    constexpr int BNL = PAIR ? BN / 2 : BN;    // weight columns staged in THIS CTA's shared memory
+    constexpr int B_HALF = BNL * BK * 2;       // hi (or lo) weight tile of one (tap, k-step): BNL x 32 x 2 B
     constexpr int B_STAGE = 2 * B_HALF;
-    constexpr int NB = B_RING_BYTES / B_STAGE;
+    constexpr int NA = ring_na(PAIR), BAR_OFF = bar_off(PAIR), STAGING_OFF = BAR_OFF + 512;
+    constexpr int NB = ring_b_bytes(PAIR) / B_STAGE;
+    static_assert(NB <= 16 && NA <= 6, "barrier area sized for at most 6 + 16 stages");
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t sbase = smem_u32(smem);
     const uint32_t sA = sbase, sB = sbase + NA * A_STAGE;
-    const uint32_t bars = sB + NB * B_STAGE;           // 8-byte mbarriers
+    const uint32_t bars = sbase + BAR_OFF;             // 8-byte mbarriers
     const uint32_t barAfull = bars, barAempty = bars + 8 * NA, barBfull = bars + 16 * NA, barBempty = barBfull + 8 * NB,
                    barAccFull = barBempty + 8 * NB, barAccEmpty = barAccFull + 16;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + NA * A_STAGE + NB * B_STAGE + 16 * NA + 16 * NB + 32);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + BAR_OFF + 448);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nks0 = p.seg[0].nks, nks = nks0 + (p.nseg > 1 ? p.seg[1].nks : 0);
@@ -170,17 +185,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const TcConvPar
     const int ncl = CL > 1 ? (int)num_clusters_x() : (int)gridDim.x;
     constexpr uint16_t CMASK = (uint16_t)((1u << CL) - 1);
 
+    const bool leader = !PAIR || crank == 0;
     if (tid == 0) {
-        for (int i = 0; i < NA; ++i) { mbar_init(barAfull + 8 * i, 1); mbar_init(barAempty + 8 * i, 1); }
-        for (int i = 0; i < NB; ++i) { mbar_init(barBfull + 8 * i, 1); mbar_init(barBempty + 8 * i, CL); }
-        for (int i = 0; i < 2; ++i) { mbar_init(barAccFull + 8 * i, 1); mbar_init(barAccEmpty + 8 * i, 128); }
+        const uint32_t nfull = PAIR && leader ? 2 : 1;   // pair leader: own expect_tx arrive + the peer's relay
+        for (int i = 0; i < NA; ++i) { mbar_init(barAfull + 8 * i, nfull); mbar_init(barAempty + 8 * i, 1); }
+        for (int i = 0; i < NB; ++i) { mbar_init(barBfull + 8 * i, nfull); mbar_init(barBempty + 8 * i, PAIR ? 1 : CL); }
+        for (int i = 0; i < 2; ++i) { mbar_init(barAccFull + 8 * i, 1); mbar_init(barAccEmpty + 8 * i, PAIR ? 256 : 128); }
         fence_mbar_init();
     }
     constexpr uint32_t ACC_COLS = X3 ? 2 * BN : BN;    // X3: accumulator 0 = hi*hi, accumulator 1 = cross terms * 2^11
     constexpr int NSETS = ACC_COLS * 2 <= 512 ? 2 : 1; // N=256 in f16x3 fills TMEM: no epilogue overlap (used for long K only)
     constexpr uint32_t TMEM_COLS = NSETS * ACC_COLS;
-    constexpr uint32_t IDESC = make_idesc(X3 ? 0u : 1u, BM, BN);
-    if (warp == 5) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+    constexpr uint32_t IDESC = make_idesc(X3 ? 0u : 1u, PAIR ? 2 * BM : BM, BN);
+    if (warp == 5) {
+        if (PAIR) tmem_alloc2(smem_u32(tmem_slot), TMEM_COLS);
+        else tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+    }
     tc_fence_before();
     __syncthreads();
     if (CL > 1) cluster_sync_all();   // peers' mbarriers are initialised before anything is multicast to them
@@ -275,7 +295,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const TcConvPar
                 __syncwarp();   // staging buffer is reused by the next chunk
             }
             tc_fence_before();
-            mbar_arrive(barAccEmpty + 8 * as);   // this accumulator set may be overwritten
+            if (PAIR) mbar_arrive_cluster(barAccEmpty + 8 * as, 0);   // the leader's MMA warp owns both CTAs' accumulators
+            else mbar_arrive(barAccEmpty + 8 * as);                   // this accumulator set may be overwritten
         }
     } else if (warp == 4) {
         // ================================================================ loader (whole warp runs the loop, one elected lane issues)
@@ -292,23 +313,58 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const TcConvPar
                     const int sa = ia % NA;
                     mbar_wait(barAempty + 8 * sa, ((ia / NA) & 1) ^ 1);
                     if (elect_one()) {
-                        mbar_arrive_expect_tx(barAfull + 8 * sa, a_bytes);
-                        bulk_copy_g2s(sA + sa * A_STAGE, sg.U + ((size_t)m_tile * sg.nks + kl) * A_STAGE, a_bytes, barAfull + 8 * sa);
+                        if (p.debug & 1) mbar_arrive(barAfull + 8 * sa);   // timing experiment: no operand traffic
+                        else {
+                            mbar_arrive_expect_tx(barAfull + 8 * sa, a_bytes);
+                            bulk_copy_g2s(sA + sa * A_STAGE, sg.U + ((size_t)m_tile * sg.nks + kl) * A_STAGE, a_bytes, barAfull + 8 * sa);
+                        }
                     }
                     __syncwarp();
-                    const uint8_t* wsrc = sg.w + ((size_t)n_tile * sg.nks + kl) * sg.taps * B_STAGE;
+                    // weight image [k-step][tap][hi|lo][Cout/8][4 kc][8][8]: the BN columns of this tile are one contiguous slice
+                    const size_t whalf = (size_t)p.Cout * (BK * 2);
+                    const uint8_t* wsrc = sg.w + (size_t)kl * sg.taps * 2 * whalf + (size_t)n_tile * BN * (BK * 2);
                     for (int tap = 0; tap < sg.taps; ++tap, ++ib) {
                         const int sb = ib % NB;
-                        mbar_wait(barBempty + 8 * sb, ((ib / NB) & 1) ^ 1);   // all CL consumers of this stage are done
+                        mbar_wait(barBempty + 8 * sb, ((ib / NB) & 1) ^ 1);   // all consumers of this stage are done
                         if (elect_one()) {
+                          if (p.debug & 1) mbar_arrive(barBfull + 8 * sb);
+                          else {
                             mbar_arrive_expect_tx(barBfull + 8 * sb, b_bytes);
-                            if (CL > 1) {
-                                const uint32_t part = b_bytes / CL, off = crank * part;
-                                bulk_copy_g2s_multicast(sB + sb * B_STAGE + off, wsrc + (size_t)tap * B_STAGE + off, part, barBfull + 8 * sb, CMASK);
-                            } else bulk_copy_g2s(sB + sb * B_STAGE, wsrc + (size_t)tap * B_STAGE, b_bytes, barBfull + 8 * sb);
+                            const uint8_t* hi = wsrc + (size_t)tap * 2 * whalf;
+                            const uint32_t dst = sB + sb * B_STAGE, bar = barBfull + 8 * sb;
+                            if (PAIR) {            // this CTA's half of the columns only
+                                bulk_copy_g2s(dst, hi + crank * B_HALF, B_HALF, bar);
+                                if (X3) bulk_copy_g2s(dst + B_HALF, hi + whalf + crank * B_HALF, B_HALF, bar);
+                            } else if (CL > 1) {   // fetch 1/CL of the stage, deliver it to every CTA of the cluster
+                                const uint32_t part = B_HALF / CL, off = crank * part;
+                                bulk_copy_g2s_multicast(dst + off, hi + off, part, bar, CMASK);
+                                if (X3) bulk_copy_g2s_multicast(dst + B_HALF + off, hi + whalf + off, part, bar, CMASK);
+                            } else {
+                                bulk_copy_g2s(dst, hi, B_HALF, bar);
+                                if (X3) bulk_copy_g2s(dst + B_HALF, hi + whalf, B_HALF, bar);
+                            }
+                        }
                         }
                         __syncwarp();
                     }
+                }
+            }
+        }
+    } else if (PAIR && !leader) {
+        // ================================================================ pair peer: relay "stage landed" to the leader's barriers
+        int ia = 0, ib = 0;
+        for (int w = cid; w < nwork; w += ncl) {
+            for (int ks = 0; ks < nks; ++ks, ++ia) {
+                const int sa = ia % NA;
+                const int taps = ks < nks0 ? p.seg[0].taps : p.seg[1].taps;
+                mbar_wait(barAfull + 8 * sa, (ia / NA) & 1);
+                if (elect_one()) mbar_arrive_cluster(barAfull + 8 * sa, 0);
+                __syncwarp();
+                for (int tap = 0; tap < taps; ++tap, ++ib) {
+                    const int sb = ib % NB;
+                    mbar_wait(barBfull + 8 * sb, (ib / NB) & 1);
+                    if (elect_one()) mbar_arrive_cluster(barBfull + 8 * sb, 0);
+                    __syncwarp();
                 }
             }
         }
@@ -319,17 +375,26 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const TcConvPar
             for (int w = cid; w < nwork; w += ncl, ++lt) {
                 const int as = lt % NSETS, use = lt / NSETS;
                 const uint32_t d0 = tmem + as * ACC_COLS, d1 = d0 + BN;
-                mbar_wait(barAccEmpty + 8 * as, (use & 1) ^ 1);   // epilogue has drained this set
+                if (PAIR) mbar_wait_cluster(barAccEmpty + 8 * as, (use & 1) ^ 1);   // both CTAs' epilogues have drained this set
+                else mbar_wait(barAccEmpty + 8 * as, (use & 1) ^ 1);
                 tc_fence_after();
                 uint32_t accum = 0, accum2 = 0;
+                const bool skip_mma = (p.debug & 2) != 0;   // timing experiment: operand traffic only
+                auto mma = [skip_mma](uint32_t d, uint64_t da, uint64_t db, uint32_t acc) {
+                    if (skip_mma) return;
+                    if (PAIR) umma2_bf16(d, da, db, IDESC, acc);
+                    else umma_bf16(d, da, db, IDESC, acc);
+                };
                 for (int ks = 0; ks < nks; ++ks, ++ia) {
                     const int sa = ia % NA;
                     const int taps = ks < nks0 ? p.seg[0].taps : p.seg[1].taps;
-                    mbar_wait(barAfull + 8 * sa, (ia / NA) & 1);
+                    if (PAIR) mbar_wait_cluster(barAfull + 8 * sa, (ia / NA) & 1);
+                    else mbar_wait(barAfull + 8 * sa, (ia / NA) & 1);
                     tc_fence_after();
                     for (int tap = 0; tap < taps; ++tap, ++ib) {
                         const int sb = ib % NB;
-                        mbar_wait(barBfull + 8 * sb, (ib / NB) & 1);
+                        if (PAIR) mbar_wait_cluster(barBfull + 8 * sb, (ib / NB) & 1);
+                        else mbar_wait(barBfull + 8 * sb, (ib / NB) & 1);
                         tc_fence_after();
                         const int shift = taps == 3 ? tap : 1;   // slot of the first row: position - 1 + tap
                         const uint32_t a_hi = sA + sa * A_STAGE + shift * A_SBO, a_lo = a_hi + A_TILE;
@@ -339,18 +404,24 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const TcConvPar
                         for (int kk = 0; kk < BK / 16; ++kk) {
                             const uint64_t dah = make_desc(a_hi + kk * 2 * A_LBO, A_LBO, A_SBO);
                             const uint64_t dbh = make_desc(b_hi + kk * 2 * B_LBO, B_LBO, B_SBO);
-                            umma_bf16(d0, dah, dbh, IDESC, kk == 0 ? accum : 1u);
+                            mma(d0, dah, dbh, kk == 0 ? accum : 1u);
                             if (X3) {
                                 const uint64_t dal = make_desc(a_lo + kk * 2 * A_LBO, A_LBO, A_SBO);
                                 const uint64_t dbl = make_desc(b_lo + kk * 2 * B_LBO, B_LBO, B_SBO);
-                                umma_bf16(d1, dah, dbl, IDESC, kk == 0 ? accum2 : 1u);
-                                umma_bf16(d1, dal, dbh, IDESC, 1);
+                                mma(d1, dah, dbl, kk == 0 ? accum2 : 1u);
+                                mma(d1, dal, dbh, 1u);
                             }
                         }
-                        if (CL > 1) umma_commit_multicast(barBempty + 8 * sb, CMASK);   // every CTA's loader writes into this stage
-                        else umma_commit(barBempty + 8 * sb);                           // weight stage free once these MMAs retire
-                        if (tap == taps - 1) umma_commit(barAempty + 8 * sa);
-                        if (tap == taps - 1 && ks == nks - 1) umma_commit(barAccFull + 8 * as);
+                        if (PAIR) {   // one commit per barrier, delivered to the same barrier of both CTAs
+                            umma2_commit_multicast(barBempty + 8 * sb, CMASK);
+                            if (tap == taps - 1) umma2_commit_multicast(barAempty + 8 * sa, CMASK);
+                            if (tap == taps - 1 && ks == nks - 1) umma2_commit_multicast(barAccFull + 8 * as, CMASK);
+                        } else {
+                            if (CL > 1) umma_commit_multicast(barBempty + 8 * sb, CMASK);   // every CTA's loader writes into this stage
+                            else umma_commit(barBempty + 8 * sb);                           // weight stage free once these MMAs retire
+                            if (tap == taps - 1) umma_commit(barAempty + 8 * sa);
+                            if (tap == taps - 1 && ks == nks - 1) umma_commit(barAccFull + 8 * as);
+                        }
                         }
                         __syncwarp();
                         accum = 1; accum2 = 1;
@@ -362,7 +433,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const TcConvPar
     tc_fence_before();
     __syncthreads();
     if (CL > 1) cluster_sync_all();   // no CTA leaves while a peer may still multicast into its shared memory
-    if (warp == 5) tmem_dealloc(tmem, TMEM_COLS);
+    if (warp == 5) {
+        if (PAIR) tmem_dealloc2(tmem, TMEM_COLS);
+        else tmem_dealloc(tmem, TMEM_COLS);
+    }
 }
 
 uint16_t bf16_rn(float f) {
@@ -382,37 +456,44 @@ bool conv_tc_eligible(int Cin0, int Cin1, int Cout, int Tout, int taps, int stri
            Tout > 0 && Tout % 16 == 0;
 }
 
-// Output channels per CTA tile.  N=256 halves the shared-memory operand traffic per MMA (the N=128 shape reads
-// 128 B/cycle and is smem-bound near 65 % of the tensor peak) but, with the second f16x3 accumulator, fills TMEM, so the
-// epilogue no longer overlaps the next mainloop: use it when the mainloop is long (>= 24 weight stages per tile).
-int conv_tc_bn(int Cout, int weight_stages) { return (Cout % 256 == 0 && weight_stages >= 24) ? 256 : 128; }
+// Output channels per tile.  N=128 reads 128 B/cycle of operands from shared memory: the MMAs alone (no copies) stop
+// near 400 TFLOP/s fp32-equivalent; N=256 needs 96 B/cycle and reaches 590, but with the second f16x3 accumulator it
+// fills TMEM, so its epilogue does not overlap the next mainloop.  Measured per layer shape (tools/conv_bench.py,
+// profiles/r01_conv_bench.txt) N=256 wins wherever Cout % 256 == 0, including the K=512 1x1 convs (qkv 0.93 vs 1.32 ms).
+// The CTA-pair shapes (cta_group::2) issue MMAs at the same rate and halve the weight staging, but the peer -> leader
+// barrier relay doubles the load -> consume -> free round trip (2.7 vs 1.3 us) and the rings that fit in 227 KB no longer
+// cover it: 25-45 % slower on every layer, so they are off by default.
+int g_conv_tc_cluster = 2;          // CTAs per cluster sharing weight stages by multicast (1, 2 or 4); eegldm_set_conv_cluster
+int g_conv_tc_pair = 0;             // 1: cta_group::2 CTA pairs (M=256 per MMA); 0: single-CTA MMAs (+ multicast clusters)
+int g_conv_tc_bn256_stages = 1;     // minimum weight stages per tile for the N=256 shape
+int conv_tc_bn(int Cout, int weight_stages) { return (Cout % 256 == 0 && weight_stages >= g_conv_tc_bn256_stages) ? 256 : 128; }
 
-// [Cout][Cin][k] fp32 -> per (n_tile, k-step, tap): [hi | lo] halves of bn*64 bytes, each the shared-memory image
-//   byte(kc, ng, r, e) = kc*(bn*16) + ng*128 + r*16 + e*2   for  co = n_tile*bn + ng*8 + r,  ci = ks*32 + kc*8 + e
-// x3: hi = fp16(w), lo = fp16((w - hi) * 2^11);  otherwise hi = bf16(w), lo unused.
-void pack_conv_tc(const float* w, int Cout, int Cin, int k, int bn, bool x3, std::vector<uint16_t>& out) {
-    const int nt = Cout / bn, nks = Cin / TC_BK;
-    const size_t half = (size_t)bn * TC_BK;   // u16 elements per half
-    out.assign((size_t)nt * nks * k * 2 * half, 0);
-    for (int n = 0; n < nt; ++n)
-        for (int ks = 0; ks < nks; ++ks)
-            for (int tap = 0; tap < k; ++tap) {
-                uint16_t* hi = out.data() + (((size_t)n * nks + ks) * k + tap) * 2 * half;
-                uint16_t* lo = hi + half;
+// [Cout][Cin][k] fp32 -> [k-step][tap][hi|lo][Cout/8][kc 4][r 8][e 8] 16-bit: per (k-step, tap, half) the 8-column
+// groups are consecutive 512-byte blocks of 4 K-major core matrices, so the columns of ANY tile width are one contiguous
+// slice that is also the tile's shared-memory image (LBO 128, SBO 512):
+//   element (co, ci) at  ((ks*k + tap)*2 + half) * Cout*32  +  (co/8)*256 + kc*64 + (co%8)*8 + e,   ci = ks*32 + kc*8 + e
+// x3: hi = fp16(w), lo = fp16((w - hi) * 2^11);  otherwise hi = bf16(w), lo unused (left zero).
+void pack_conv_tc(const float* w, int Cout, int Cin, int k, bool x3, std::vector<uint16_t>& out) {
+    const int nks = Cin / TC_BK;
+    const size_t half = (size_t)Cout * TC_BK;   // u16 elements per half
+    out.assign((size_t)nks * k * 2 * half, 0);
+    for (int ks = 0; ks < nks; ++ks)
+        for (int tap = 0; tap < k; ++tap) {
+            uint16_t* hi = out.data() + ((size_t)ks * k + tap) * 2 * half;
+            uint16_t* lo = hi + half;
+            for (int co = 0; co < Cout; ++co)
                 for (int kc = 0; kc < TC_BK / 8; ++kc)
-                    for (int ng = 0; ng < bn / 8; ++ng)
-                        for (int r = 0; r < 8; ++r)
-                            for (int e = 0; e < 8; ++e) {
-                                const int co = n * bn + ng * 8 + r, ci = ks * TC_BK + kc * 8 + e;
-                                const float v = w[((size_t)co * Cin + ci) * k + tap];
-                                const size_t o = (size_t)kc * (bn * 8) + ng * 64 + r * 8 + e;
-                                if (x3) {
-                                    const uint16_t h = f16_rn(v);
-                                    hi[o] = h;
-                                    lo[o] = f16_rn((v - f16_to_f(h)) * LO_SCALE);
-                                } else hi[o] = bf16_rn(v);
-                            }
-            }
+                    for (int e = 0; e < 8; ++e) {
+                        const int ci = ks * TC_BK + kc * 8 + e;
+                        const float v = w[((size_t)co * Cin + ci) * k + tap];
+                        const size_t o = (size_t)(co >> 3) * 256 + kc * 64 + (co & 7) * 8 + e;
+                        if (x3) {
+                            const uint16_t h = f16_rn(v);
+                            hi[o] = h;
+                            lo[o] = f16_rn((v - f16_to_f(h)) * LO_SCALE);
+                        } else hi[o] = bf16_rn(v);
+                    }
+        }
 }
 
 size_t act_split_bytes(int nsegs16, int Cin) { return (size_t)((nsegs16 + 7) / 8) * (Cin / TC_BK) * A_STAGE; }
@@ -426,11 +507,11 @@ cudaError_t launch_act_split(const ActSplitParams& p, bool x3, cudaStream_t st) 
     return cudaGetLastError();
 }
 
-template <bool X3, int BN, int CL>
+template <bool X3, int BN, int CL, bool PAIR>
 cudaError_t launch_conv_tc_t(const TcConvParams& p, int num_sms, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<X3, BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<X3, BN, CL, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(PAIR));
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
@@ -441,16 +522,14 @@ cudaError_t launch_conv_tc_t(const TcConvParams& p, int num_sms, cudaStream_t st
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(nclusters * CL);   // persistent: one CTA per SM
     cfg.blockDim = dim3(NUM_THREADS);
-    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.dynamicSmemBytes = smem_bytes(PAIR);
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, conv_tc_kernel<X3, BN, CL>, p);
+    return cudaLaunchKernelEx(&cfg, conv_tc_kernel<X3, BN, CL, PAIR>, p);
 }
-
-int g_conv_tc_cluster = 2;   // CTAs per cluster sharing weight stages by multicast (1, 2 or 4); eegldm_set_conv_cluster
 
 cudaError_t launch_conv_tc(const TcConvParams& p, bool x3, cudaStream_t st) {
     if (p.nsegs16 <= 0) return cudaSuccess;
@@ -462,9 +541,10 @@ cudaError_t launch_conv_tc(const TcConvParams& p, bool x3, cudaStream_t st) {
     }
     if (p.bn != 128 && p.bn != 256) return cudaErrorInvalidValue;
     cudaError_t e;
-#define EEGLDM_TC(X3, BN)                                                              \
-    (g_conv_tc_cluster == 4 ? launch_conv_tc_t<X3, BN, 4>(p, num_sms, st)               \
-     : g_conv_tc_cluster == 2 ? launch_conv_tc_t<X3, BN, 2>(p, num_sms, st) : launch_conv_tc_t<X3, BN, 1>(p, num_sms, st))
+#define EEGLDM_TC(X3, BN)                                                                         \
+    (g_conv_tc_pair ? launch_conv_tc_t<X3, BN, 2, true>(p, num_sms, st)                             \
+     : g_conv_tc_cluster == 4 ? launch_conv_tc_t<X3, BN, 4, false>(p, num_sms, st)                 \
+     : g_conv_tc_cluster == 2 ? launch_conv_tc_t<X3, BN, 2, false>(p, num_sms, st) : launch_conv_tc_t<X3, BN, 1, false>(p, num_sms, st))
     if (p.bn == 256) e = x3 ? EEGLDM_TC(true, 256) : EEGLDM_TC(false, 256);
     else e = x3 ? EEGLDM_TC(true, 128) : EEGLDM_TC(false, 128);
 #undef EEGLDM_TC

@@ -477,7 +477,7 @@ int finalize_unet(eegldm_unet* h) {
         has = h->math != EEGLDM_MATH_FP32_SIMT && conv_tc_eligible(cin, 0, cout, 16, k, 1);
         if (!has) return;
         std::vector<uint16_t> img;
-        pack_conv_tc(ps.get(name).data(), cout, cin, k, conv_tc_bn(cout, stages), h->math == EEGLDM_MATH_F16X3_TC, img);
+        pack_conv_tc(ps.get(name).data(), cout, cin, k, h->math == EEGLDM_MATH_F16X3_TC, img);
         off = wp.push_u16(img);
     };
     for_each_layer(h, [&](ULayer& l) {
@@ -612,7 +612,7 @@ void plan_conv(Builder& bd, ConvParams p, const uint8_t* tw0 = nullptr, const ui
         q.nseg = p.nseg; q.Cout = p.Cout; q.Tout = p.Tout; q.nsegs16 = (int)((long long)p.B * p.Tout / 16);
         int stages = 0;
         for (int s = 0; s < p.nseg; ++s) stages += (p.seg[s].C0 + p.seg[s].C1) / TC_BK * p.seg[s].taps;
-        q.bn = conv_tc_bn(p.Cout, stages);   // must match the packing done in finalize_unet
+        q.bn = conv_tc_bn(p.Cout, stages);   // tile width is a launch-time choice: the weight image is width-agnostic
         std::shared_ptr<Buf> ubuf[2];
         for (int s = 0; s < p.nseg; ++s) {
             // pre-pass: GroupNorm apply + SiLU + resample + 16-bit split -> tile images (one pass per conv input)
@@ -1211,6 +1211,14 @@ int eegldm_set_conv_cluster(int ctas) {
     return EEGLDM_OK;
 }
 
+int eegldm_set_conv_tuning(int pair, int bn256_min_stages) {
+    if (pair != 0 && pair != 1) return fail(EEGLDM_ERR_INVALID, "pair must be 0 or 1");
+    if (bn256_min_stages < 1) return fail(EEGLDM_ERR_INVALID, "bn256_min_stages must be >= 1");
+    g_conv_tc_pair = pair;
+    g_conv_tc_bn256_stages = bn256_min_stages;
+    return EEGLDM_OK;
+}
+
 int eegldm_profile_enable(int on) {
     for (auto& r : g_prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
     g_prof.clear();
@@ -1580,7 +1588,7 @@ int eegldm_test_conv(const float* x_dev, const float* scale_dev, const float* sh
     if (tc) {
         if (!conv_tc_eligible(Cin, 0, Cout, Tc, k, 1)) return fail(EEGLDM_ERR_SHAPE, "shape not eligible for the tcgen05 path");
         std::vector<uint16_t> img;
-        pack_conv_tc(w.data(), Cout, Cin, k, conv_tc_bn(Cout, Cin / TC_BK * k), math == EEGLDM_MATH_F16X3_TC, img);
+        pack_conv_tc(w.data(), Cout, Cin, k, math == EEGLDM_MATH_F16X3_TC, img);
         o_t = wp.push_u16(img);
     }
     int r = wp.upload();
@@ -1608,6 +1616,68 @@ int eegldm_test_conv(const float* x_dev, const float* scale_dev, const float* sh
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);   // the temporary weight pool / U are freed on return
     if (U) cudaFree(U);
     if (ce != cudaSuccess) return cuda_fail(ce, "conv launch");
+    return EEGLDM_OK;
+}
+
+// Timing of one tcgen05 convolution launch on synthetic data (tools/conv_bench.py): `reps` back-to-back launches
+// bracketed by CUDA events on `stream`; debug: 0 = the real kernel, 1 = no operand copies, 2 = no MMAs (experiments that
+// separate the tensor-pipe time from the operand-staging time; their outputs are garbage).  Inputs are pseudo-random.
+__global__ void bench_fill_kernel(float* x, size_t n, uint32_t seed) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        uint32_t h = (uint32_t)i * 2654435761u + seed;
+        h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+        x[i] = (float)(h & 0xFFFF) * (2.0f / 65535.0f) - 1.0f;
+    }
+}
+int eegldm_bench_conv(int B, int T, int Cin, int Cout, int k, int with_res, int math, int debug, int reps, float* ms_out,
+                      void* stream) {
+    if (!ms_out || reps <= 0) return fail(EEGLDM_ERR_INVALID, "bad argument");
+    if (math == EEGLDM_MATH_FP32_SIMT || !conv_tc_eligible(Cin, 0, Cout, T, k, 1))
+        return fail(EEGLDM_ERR_SHAPE, "shape / math not eligible for the tcgen05 path");
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool x3 = math == EEGLDM_MATH_F16X3_TC;
+    std::vector<float> w((size_t)Cout * Cin * k);
+    uint32_t h = 12345u;
+    for (auto& v : w) { h = h * 1664525u + 1013904223u; v = ((float)(h >> 8) / 8388608.0f - 1.0f) / sqrtf((float)Cin * k); }
+    std::vector<uint16_t> img;
+    pack_conv_tc(w.data(), Cout, Cin, k, x3, img);
+    WeightPool wp;
+    const size_t o_t = wp.push_u16(img);
+    int r = wp.upload();
+    if (r) return r;
+    TcConvParams q{};
+    q.nseg = 1; q.Cout = Cout; q.Tout = T; q.nsegs16 = (int)((long long)B * T / 16);
+    q.bn = conv_tc_bn(Cout, Cin / TC_BK * k);
+    float *x = nullptr, *out = nullptr, *res = nullptr;
+    uint8_t* U = nullptr;
+    const size_t nx = (size_t)B * T * Cin, no = (size_t)B * T * Cout;
+    cudaError_t ce = cudaMalloc((void**)&x, nx * 4);
+    if (ce == cudaSuccess) ce = cudaMalloc((void**)&out, no * 4);
+    if (ce == cudaSuccess && with_res) ce = cudaMalloc((void**)&res, no * 4);
+    if (ce == cudaSuccess) ce = cudaMalloc((void**)&U, act_split_bytes(q.nsegs16, Cin));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (ce == cudaSuccess) {
+        bench_fill_kernel<<<1024, 256, 0, st>>>(x, nx, 1u);
+        if (res) bench_fill_kernel<<<1024, 256, 0, st>>>(res, no, 2u);
+        ActSplitParams sp{x, nullptr, Cin, 0, nullptr, nullptr, 0, RS_NONE, T, T, q.nsegs16, Cin / TC_BK, U, nullptr};
+        ce = launch_act_split(sp, x3, st);
+    }
+    q.seg[0] = TcSeg{U, reinterpret_cast<const uint8_t*>(wp.at(o_t)), k, Cin / TC_BK};
+    q.res = res; q.res_mode = RS_NONE; q.res_Tin = T; q.out = out; q.debug = debug;
+    if (ce == cudaSuccess) ce = launch_conv_tc(q, x3, st);   // warm-up
+    if (ce == cudaSuccess) ce = cudaEventCreate(&e0);
+    if (ce == cudaSuccess) ce = cudaEventCreate(&e1);
+    if (ce == cudaSuccess) ce = cudaEventRecord(e0, st);
+    for (int i = 0; i < reps && ce == cudaSuccess; ++i) ce = launch_conv_tc(q, x3, st);
+    if (ce == cudaSuccess) ce = cudaEventRecord(e1, st);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+    float ms = 0.f;
+    if (ce == cudaSuccess) ce = cudaEventElapsedTime(&ms, e0, e1);
+    *ms_out = ms / reps;
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    cudaFree(x); cudaFree(out); cudaFree(res); cudaFree(U);
+    if (ce != cudaSuccess) return cuda_fail(ce, "conv bench");
     return EEGLDM_OK;
 }
 

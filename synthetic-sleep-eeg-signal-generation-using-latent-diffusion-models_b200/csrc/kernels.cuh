@@ -87,24 +87,27 @@ size_t act_split_bytes(int nsegs16, int Cin);
 cudaError_t launch_act_split(const ActSplitParams& p, bool x3, cudaStream_t st);
 struct TcSeg {
     const uint8_t* U;   // activation tile images written by act_split
-    const uint8_t* w;   // packed by pack_conv_tc: [n_tile][k-step][tap][hi|lo] blocks of bn*64 bytes
+    const uint8_t* w;   // packed by pack_conv_tc: [k-step][tap][hi|lo][Cout/8][4][8][8] 16-bit (tile-width agnostic)
     int taps, nks;      // nks = Cin/TC_BK
 };
 struct TcConvParams {
     TcSeg seg[2];
     int nseg;
     int Cout, Tout;     // stride 1, "same" padding: conv-input length == Tout
-    int bn;             // output channels per CTA tile the weights were packed for (conv_tc_bn)
+    int bn;             // output channels per tile: 128 or 256 (conv_tc_bn)
     int nsegs16;        // B*Tout/16 segments of 16 positions (8 per CTA)
     const float* bias; const float* temb; int temb_stride;
     const float* res; int res_mode; int res_Tin;
     float* out;
+    int debug;          // timing experiments only (eegldm_bench_conv): 1 = no operand copies, 2 = no MMAs; results are garbage
 };
 bool conv_tc_eligible(int Cin0, int Cin1, int Cout, int Tout, int taps, int stride);
 int conv_tc_bn(int Cout, int weight_stages);   // weight_stages = sum over segments of (Cin/32)*taps
-void pack_conv_tc(const float* w, int Cout, int Cin, int k, int bn, bool x3, std::vector<uint16_t>& out);
+void pack_conv_tc(const float* w, int Cout, int Cin, int k, bool x3, std::vector<uint16_t>& out);
 cudaError_t launch_conv_tc(const TcConvParams& p, bool x3, cudaStream_t st);
-extern int g_conv_tc_cluster;   // CTAs per cluster sharing weight stages (1, 2, 4)
+extern int g_conv_tc_cluster;        // CTAs per cluster sharing weight stages (1, 2, 4) when g_conv_tc_pair == 0
+extern int g_conv_tc_pair;           // cta_group::2 CTA pairs (default 1)
+extern int g_conv_tc_bn256_stages;   // N=256 tiles from this many weight stages per tile
 cudaError_t launch_groupnorm(const GnParams& p, cudaStream_t st);
 int groupnorm_nsplit(int C, int T, int G);
 cudaError_t launch_attention_simt(const AttnParams& p, cudaStream_t st);

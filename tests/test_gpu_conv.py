@@ -83,6 +83,44 @@ def test_fused_conv_matches_torch(built_lib, cuda_device, case, math):
         torch.testing.assert_close(y, ref, rtol=1e-4, atol=2e-5)
 
 
+# tile shapes of the tcgen05 kernel: (CTA pair?, minimum weight stages for 256-wide tiles).  The default is (0, 1):
+# single-CTA MMAs, 256-wide tiles wherever Cout % 256 == 0; (x, 10**6) forces 128-wide tiles, pair=1 is cta_group::2.
+SHAPES = [(1, 1), (1, 10 ** 6), (0, 24), (0, 10 ** 6)]
+BIG_CASES = [
+    (40, 768, 128, 128, 3, True, 0, True),     # 240 M tiles: every persistent CTA walks several tiles (ring wrap, both TMEM sets)
+    (37, 192, 512, 512, 3, True, 0, True),     # tiles straddle samples, odd tile count (idle slot in the last pair), 2-4 N tiles
+    (33, 192, 512, 1536, 1, False, 0, False),  # the qkv shape
+]
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("case", CASES + BIG_CASES)
+def test_conv_tile_shapes(built_lib, cuda_device, case, shape):
+    from eegldm import _lib
+    B, Tin, Cin, Cout, k, aff, rs, has_res = case
+    g = torch.Generator().manual_seed(hash(case) % 1000)
+    x = torch.randn(B, Tin, Cin, generator=g)
+    w = torch.randn(Cout, Cin, k, generator=g) / (Cin * k) ** 0.5
+    bias = 0.1 * torch.randn(Cout, generator=g)
+    scale = 1 + 0.2 * torch.randn(B, Cin, generator=g) if aff else None
+    shift = 0.2 * torch.randn(B, Cin, generator=g) if aff else None
+    Tc = {0: Tin, 1: Tin // 2, 2: Tin * 2}[rs]
+    res = torch.randn(B, Tc, Cout, generator=g) if has_res else None
+    ref = _ref(x, w, bias, scale, shift, aff, rs, res)
+    _lib.check(built_lib.eegldm_set_conv_tuning(*shape))
+    try:
+        y = _run(built_lib, cuda_device, x, w, bias, scale, shift, aff, rs, res, "f16x3")
+    finally:
+        _lib.check(built_lib.eegldm_set_conv_tuning(0, 1))
+    assert torch.isfinite(y).all()
+    torch.testing.assert_close(y, ref, rtol=1e-4, atol=2e-5)
+
+
+@pytest.mark.parametrize("case", BIG_CASES)
+def test_conv_default_shape_big(built_lib, cuda_device, case):
+    test_conv_tile_shapes(built_lib, cuda_device, case, (0, 1))
+
+
 ATTN_CASES = [(2, 192, 1, 512), (1, 128, 1, 128), (3, 64, 2, 128), (2, 256, 1, 256), (1, 32, 4, 128)]
 
 

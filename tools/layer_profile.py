@@ -13,9 +13,12 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=1024)
 ap.add_argument("--math", default="f16x3")
 ap.add_argument("--cluster", type=int, default=2)
+ap.add_argument("--pair", type=int, default=0)
+ap.add_argument("--bn256", type=int, default=1)
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 _lib.check(eegldm.lib().eegldm_set_conv_cluster(a.cluster))
+_lib.check(eegldm.lib().eegldm_set_conv_tuning(a.pair, a.bn256))
 cfg = ou.full_cfg()
 m = eegldm.UNetModel(**cfg, math=a.math)
 m.load_state_dict(ou.make_unet_state_dict(cfg, 0))
