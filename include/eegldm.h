@@ -57,8 +57,11 @@ int eegldm_set_conv_cluster(int ctas);
 /* Shape selection of the tcgen05 conv kernel.  pair = 1: the two CTAs of a cluster issue one M=256 cta_group::2 MMA over
  * both (each stages half of the weight columns); pair = 0 (default, measured faster): single-CTA MMAs with the multicast
  * cluster of eegldm_set_conv_cluster.  bn256_min_stages (default 1): tiles are 256 output channels wide when Cout % 256 == 0
- * and a tile's mainloop has at least this many weight stages (else 128).  Call before creating models: plans cache it. */
-int eegldm_set_conv_tuning(int pair, int bn256_min_stages);
+ * and a tile's mainloop has at least this many weight stages (else 128).  fuse_epilogues (bit mask, default 3):
+ * bit 0 -- a conv whose output feeds a GroupNorm writes that GroupNorm's statistics from its epilogue (no separate pass);
+ * bit 1 -- an AttentionBlock's qkv conv writes the attention kernel's fp16 hi/lo operand images instead of fp32 (f16x3).
+ * Call before creating models: plans cache the choices. */
+int eegldm_set_conv_tuning(int pair, int bn256_min_stages, int fuse_epilogues);
 
 /* Live per-kernel profile (bench.py's roofline leg).  While enabled, every launch made outside CUDA-graph
  * capture is bracketed by CUDA events on the launching stream.  eegldm_profile_read sums, for one kernel
@@ -213,6 +216,14 @@ int eegldm_set_graphs(int enabled);
 int eegldm_test_conv(const float* x_dev, const float* scale_dev, const float* shift_dev, int silu, int resample,
                      const float* w_host, const float* bias_host, const float* res_dev, int B, int Tin, int Cin, int Cout, int k,
                      int math, float* out_dev, void* stream);
+/* tcgen05 convolution (f16x3, bias only) whose epilogue also writes the GroupNorm(G, eps 1e-6) statistics of its output:
+ * out_dev [B][T][Cout], mean_dev / rstd_dev [B][G].  Shapes must satisfy the tensor-pipe constraints and Cout/G in {4,8,16,32}. */
+int eegldm_test_conv_gn(const float* x_dev, const float* w_host, const float* bias_host, int B, int T, int Cin, int Cout, int k,
+                        int G, float* out_dev, float* mean_dev, float* rstd_dev, void* stream);
+/* AttentionBlock core on the fused path: qkv = Conv1d(C, 3C, 1)(x) written as attention operand images by the conv epilogue,
+ * then QKVAttentionLegacy (unet.py:107-125).  x_dev, out_dev [B][T][C] channels-last, C = H*ch; w_host [3C][C][1]. */
+int eegldm_test_qkv_attention(const float* x_dev, const float* w_host, const float* bias_host, int B, int T, int H, int ch,
+                              float* out_dev, void* stream);
 /* Timing hook (tools/conv_bench.py): average milliseconds of `reps` launches of the tcgen05 convolution on synthetic
  * data of the given shape; debug 0 = real kernel, 1 = operand copies skipped, 2 = MMAs skipped (timing experiments). */
 int eegldm_bench_conv(int B, int T, int Cin, int Cout, int k, int with_res, int math, int debug, int reps, float* ms_out,

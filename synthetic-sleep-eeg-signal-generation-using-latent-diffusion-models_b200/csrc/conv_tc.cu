@@ -56,10 +56,13 @@ constexpr int N_ITEMS = 8 * SLOTS * (BK / 8);   // 576 16-byte items per activat
 // shared-memory plan: activation ring | weight ring | mbarriers (<= 8*(2*6 + 2*16 + 4) = 384 B), TMEM slot at +448 |
 // 4 warps x [32][33] fp32 epilogue transpose buffers.  A CTA pair stages half the weight bytes per MMA, so it trades
 // weight-ring bytes for two more activation stages (the activation stream comes from HBM: latency x bandwidth).
-__host__ __device__ constexpr int ring_na(bool pair) { return pair ? 6 : 4; }                        // 18 KB stages
+__host__ __device__ constexpr int ring_na(bool pair) { return pair ? 5 : 4; }                        // 18 KB stages
 __host__ __device__ constexpr int ring_b_bytes(bool pair) { return (pair ? 96 : 128) * 1024; }       // 3 x 32 KB ... 12 x 8 KB stages
 __host__ __device__ constexpr int bar_off(bool pair) { return ring_na(pair) * A_STAGE + ring_b_bytes(pair); }
-__host__ __device__ constexpr int smem_bytes(bool pair) { return bar_off(pair) + 512 + 4 * 32 * 33 * 4; }
+constexpr int STG_LD = 36;         // staging row stride in floats: 16-byte aligned rows, conflict-free 128-bit writes and reads
+constexpr int STAGING_BYTES = 4 * 32 * STG_LD * 4;
+constexpr int STATS_BYTES = 4 * 256 * 8;   // per epilogue warp: (mean, M2) of up to 8 segments x 32 groups (GroupNorm statistics)
+__host__ __device__ constexpr int smem_bytes(bool pair) { return bar_off(pair) + 512 + STAGING_BYTES + STATS_BYTES; }
 constexpr int NUM_THREADS = 192;
 constexpr int SPLIT_THREADS = 192;
 static_assert(N_ITEMS % SPLIT_THREADS == 0, "items must divide evenly over the act_split block");
@@ -212,7 +215,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const TcConvPar
         // TMEM gives each thread one M row (32 columns per load).  The 32x32 block is transposed through a padded
         // per-warp staging buffer so that global loads (residual, time embedding) and stores are 128-byte row segments:
         // lane -> (row 4*i + lane/8, columns 4*(lane%8)..+3), i = 0..7.
-        float* stg = reinterpret_cast<float*>(smem + STAGING_OFF) + warp * (32 * 33);
+        float* stg = reinterpret_cast<float*>(smem + STAGING_OFF) + warp * (32 * STG_LD);
+        float2* stats = reinterpret_cast<float2*>(smem + STAGING_OFF + STAGING_BYTES);   // [warp][segment * gpt + group]
+        const int cpg = p.gn_cpg, gpt = p.gn_partial ? BN / cpg : 0;                        // channels per group, groups per tile
+        const int cpg_sh = 31 - __clz(max(cpg, 1));                                         // cpg is a power of two
         const int col4 = (lane & 7) * 4;
         int lt = 0;
         for (int w = cid; w < nwork; w += ncl, ++lt) {
@@ -268,15 +274,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const TcConvPar
                 for (int i = 0; i < 8; ++i) R[i] = Rn[i];
                 if (p.res && cb + 32 < BN) load_res(cb + 32, Rn);
                 uint32_t v[32];
-                tmem_ld32(acc_addr + (uint32_t)cb, v);
                 if (X3) {
                     uint32_t c2[32];
-                    tmem_ld32(acc_addr + (uint32_t)(BN + cb), c2);
+                    tmem_ld32_async(acc_addr + (uint32_t)cb, v);
+                    tmem_ld32_async(acc_addr + (uint32_t)(BN + cb), c2);
+                    tmem_ld_wait();
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(fmaf(__uint_as_float(c2[i]), 1.0f / LO_SCALE, __uint_as_float(v[i])));
-                }
+                } else tmem_ld32(acc_addr + (uint32_t)cb, v);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(v[j]);
+                for (int j = 0; j < 8; ++j)
+                    *reinterpret_cast<uint4*>(stg + lane * STG_LD + 4 * j) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                 __syncwarp();
                 const int co = co0 + cb + col4;
                 float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -285,18 +293,97 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const TcConvPar
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
                     Tm[i] = p.temb ? ldg4(p.temb + (size_t)max(rb[i], 0) * p.temb_stride + co) : make_float4(0.f, 0.f, 0.f, 0.f);
+                float4 O[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const float* sp = stg + (4 * i + (lane >> 3)) * 33 + col4;
-                    const float4 o = make_float4(sp[0] + bias4.x + Tm[i].x + R[i].x, sp[1] + bias4.y + Tm[i].y + R[i].y,
-                                                 sp[2] + bias4.z + Tm[i].z + R[i].z, sp[3] + bias4.w + Tm[i].w + R[i].w);
-                    if (rb[i] >= 0) *reinterpret_cast<float4*>(p.out + ooff[i] + cb) = o;
+                    const float4 a = *reinterpret_cast<const float4*>(stg + (4 * i + (lane >> 3)) * STG_LD + col4);
+                    const float4 o = make_float4(a.x + bias4.x + Tm[i].x + R[i].x, a.y + bias4.y + Tm[i].y + R[i].y,
+                                                 a.z + bias4.z + Tm[i].z + R[i].z, a.w + bias4.w + Tm[i].w + R[i].w);
+                    if (!p.qkv16 && rb[i] >= 0) *reinterpret_cast<float4*>(p.out + ooff[i] + cb) = o;
+                    O[i] = o;
+                }
+                if (p.qkv16) {
+                    // qkv conv of an AttentionBlock (unet.py:158): write q, k, v straight into the fp16 hi/lo operand images
+                    // of attn_tc.cu (layout: qkv_split_kernel) instead of fp32 -- the attention kernel's only input.
+                    const int ch = p.qkv_ch, T = p.Tout;
+                    const int cq = co / (3 * ch), rem = co - cq * 3 * ch, which = rem / ch, c = rem - which * ch;   // head, q|k|v, channel
+                    const size_t plane = (size_t)4 * ch * T;
+                    const size_t half = which < 2 ? (size_t)T * 64 : 8192;
+                    const size_t cpart = which < 2 ? (size_t)(c >> 5) * 2 * half + ((c & 31) >> 3) * 128 + (c & 7) * 2
+                                                   : (size_t)(c >> 7) * (T >> 5) * 2 * half + ((c & 127) >> 3) * 128 + (c & 7) * 2;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        if (rb[i] < 0) continue;
+                        const int t = rt[i];
+                        const size_t tpart = which < 2 ? (size_t)(t >> 3) * 512 + (t & 7) * 16
+                                                       : (size_t)(t >> 5) * 2 * half + ((t & 31) >> 3) * 2048 + (t & 7) * 16;
+                        uint8_t* dst = p.qkv16 + (((size_t)rb[i] * p.qkv_H + cq) * 3 + which) * plane + cpart + tpart;
+                        uint2 hi, lo;
+                        split4_f16(O[i], hi, lo);
+                        *reinterpret_cast<uint2*>(dst) = hi;
+                        *reinterpret_cast<uint2*>(dst + half) = lo;
+                    }
+                }
+                if (p.gn_partial) {
+                    // GroupNorm statistics of the tensor being written (the consumer's Normalize, unet.py:71-74): this thread
+                    // holds 4 positions x 4 channels of segment lane/8 (even i) and of segment 4 + lane/8 (odd i).  One pass
+                    // of sums shifted by the first value (no E[x^2]-E[x]^2 cancellation), four independent chains per
+                    // segment, then Chan's equal-count combination over the lanes that share a group.
+                    float mean[2], m2[2];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const float K = O[h].x;
+                        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float d0 = O[2 * j + h].x - K, d1 = O[2 * j + h].y - K, d2 = O[2 * j + h].z - K, d3 = O[2 * j + h].w - K;
+                            s0 += d0; s1 += d1; s2 += d2; s3 += d3;
+                            q0 = fmaf(d0, d0, q0); q1 = fmaf(d1, d1, q1); q2 = fmaf(d2, d2, q2); q3 = fmaf(d3, d3, q3);
+                        }
+                        const float sd = (s0 + s1) + (s2 + s3);
+                        mean[h] = fmaf(sd, 1.f / 16.f, K);
+                        m2[h] = fmaxf((q0 + q1) + (q2 + q3) - sd * sd * (1.f / 16.f), 0.f);
+                    }
+                    float n = 16.f;
+                    for (int off = 1; off * 4 < cpg; off <<= 1) {
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const float mo = __shfl_xor_sync(0xffffffffu, mean[h], off), qo = __shfl_xor_sync(0xffffffffu, m2[h], off);
+                            const float d = mo - mean[h];
+                            m2[h] = m2[h] + qo + d * d * (0.5f * n);
+                            mean[h] = 0.5f * (mean[h] + mo);
+                        }
+                        n *= 2.f;
+                    }
+                    if (((col4) & (cpg - 1)) == 0) {
+                        const int e = (lane >> 3) * gpt + ((cb + col4) >> cpg_sh);
+                        stats[warp * 256 + e] = make_float2(mean[0], m2[0]);
+                        stats[warp * 256 + 4 * gpt + e] = make_float2(mean[1], m2[1]);
+                    }
                 }
                 __syncwarp();   // staging buffer is reused by the next chunk
             }
             tc_fence_before();
             if (PAIR) mbar_arrive_cluster(barAccEmpty + 8 * as, 0);   // the leader's MMA warp owns both CTAs' accumulators
             else mbar_arrive(barAccEmpty + 8 * as);                   // this accumulator set may be overwritten
+            if (p.gn_partial) {
+                // the 4 epilogue warps hold the 4 position-quarters of every segment: combine them and write one
+                // (count, mean, M2) record per (sample, 16-position segment, group) for gn_finalize
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                const float nq = 4.f * cpg;
+                for (int e = tid; e < 8 * gpt; e += 128) {
+                    const float2 a = stats[e], b = stats[256 + e], c = stats[512 + e], d = stats[768 + e];
+                    const float mean = 0.25f * ((a.x + b.x) + (c.x + d.x));
+                    const float da = a.x - mean, db = b.x - mean, dc = c.x - mean, dd = d.x - mean;
+                    const float m2 = (a.y + b.y) + (c.y + d.y) + nq * ((da * da + db * db) + (dc * dc + dd * dd));
+                    const int seg = e / gpt, gi = e - seg * gpt, g16 = m_tile * 8 + seg;
+                    if (g16 < p.nsegs16) {
+                        float* o = p.gn_partial + ((size_t)g16 * (p.Cout / cpg) + co0 / cpg + gi) * 3;   // [b][segment][group][3]
+                        o[0] = 4.f * nq; o[1] = mean; o[2] = m2;
+                    }
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");   // the stats buffer is rewritten by the next tile
+            }
         }
     } else if (warp == 4) {
         // ================================================================ loader (whole warp runs the loop, one elected lane issues)
@@ -466,6 +553,11 @@ bool conv_tc_eligible(int Cin0, int Cin1, int Cout, int Tout, int taps, int stri
 int g_conv_tc_cluster = 2;          // CTAs per cluster sharing weight stages by multicast (1, 2 or 4); eegldm_set_conv_cluster
 int g_conv_tc_pair = 0;             // 1: cta_group::2 CTA pairs (M=256 per MMA); 0: single-CTA MMAs (+ multicast clusters)
 int g_conv_tc_bn256_stages = 1;     // minimum weight stages per tile for the N=256 shape
+bool conv_tc_gn_ok(int Cout, int G) {
+    if (G <= 0 || Cout % G) return false;
+    const int cpg = Cout / G;
+    return (cpg == 4 || cpg == 8 || cpg == 16 || cpg == 32) && Cout % 128 == 0 && (Cout % 256 == 0 ? 256 : 128) / cpg <= 32;
+}
 int conv_tc_bn(int Cout, int weight_stages) { return (Cout % 256 == 0 && weight_stages >= g_conv_tc_bn256_stages) ? 256 : 128; }
 
 // [Cout][Cin][k] fp32 -> [k-step][tap][hi|lo][Cout/8][kc 4][r 8][e 8] 16-bit: per (k-step, tap, half) the 8-column

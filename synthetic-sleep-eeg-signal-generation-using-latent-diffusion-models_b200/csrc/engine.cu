@@ -185,6 +185,9 @@ struct Act {  // channels-last activation [B][T][C]
     std::shared_ptr<Buf> buf;
     const float* ext = nullptr;  // external (caller-owned) tensor instead of an arena slot
     int C = 0, T = 0;
+    // GroupNorm statistics emitted by the producing conv's epilogue: [B][gn_nsplit][gn_G][3] records (count, mean, M2)
+    std::shared_ptr<Buf> gn_part;
+    int gn_nsplit = 0, gn_G = 0;
 };
 
 using OpFn = std::function<cudaError_t(cudaStream_t)>;
@@ -233,12 +236,19 @@ ScaleShift plan_gn(Builder& bd, const Act& x0, const Act* x1, int G, const float
     p.src0 = bd.ptr(x0); p.C0 = x0.C;
     p.src1 = x1 ? bd.ptr(*x1) : nullptr; p.C1 = x1 ? x1->C : 0;
     p.T = x0.T; p.G = G; p.gamma = gamma; p.beta = beta; p.eps = eps; p.B = bd.B;
-    p.nsplit = groupnorm_nsplit(C, x0.T, G);
-    auto part = bd.scratch((size_t)bd.B * p.nsplit * G * 3);
     p.scale = bd.ptr(ss.buf);
     p.shift = p.scale + (size_t)bd.B * C;
-    p.partial = bd.ptr(part);
     ss.scale = p.scale; ss.shift = p.shift;
+    if (!x1 && x0.gn_part && x0.gn_G == G) {   // the producer's epilogue already wrote the statistics: no pass over x0
+        p.nsplit = x0.gn_nsplit;
+        p.partial = bd.ptr(x0.gn_part);
+        bd.add([p](cudaStream_t st) { return launch_groupnorm_finalize(p, st); }, 1, OP_GN, 0.0,
+               4.0 * bd.B * (3.0 * p.nsplit * G + 2.0 * C));
+        return ss;
+    }
+    p.nsplit = groupnorm_nsplit(C, x0.T, G);
+    auto part = bd.scratch((size_t)bd.B * p.nsplit * G * 3);
+    p.partial = bd.ptr(part);
     bd.add([p](cudaStream_t st) { return launch_groupnorm(p, st); }, 2, OP_GN, 3.0 * bd.B * C * x0.T,
            4.0 * bd.B * C * (x0.T + 2.0));
     return ss;
@@ -327,6 +337,8 @@ struct eegldm_unet {
 
 namespace {
 
+bool g_conv_qkv_fused = true;  // the qkv conv writes attention operand images directly (f16x3; eegldm_set_conv_tuning)
+bool g_conv_gn_fused = true;   // tensor-pipe convs emit the GroupNorm statistics of their output (eegldm_set_conv_tuning)
 bool g_graphs_enabled = true;
 
 template <class T>
@@ -591,7 +603,12 @@ struct TcShare {
     bool want_raw = false;      // conv1: produce it;   conv2: consume it for segment 1
 };
 
-void plan_conv(Builder& bd, ConvParams p, const uint8_t* tw0 = nullptr, const uint8_t* tw1 = nullptr, TcShare* share = nullptr) {
+// out_act / gn_G: when the tensor-pipe path is taken and the output's next consumer is a GroupNorm(gn_G), the conv's
+// epilogue also emits the statistics (attached to *out_act; plan_gn then skips its pass over the tensor).
+// qkv: the output is written as attention operand images instead of fp32 (tensor-pipe f16x3 path only; the caller checks).
+struct QkvOut { uint8_t* dst; int H, ch; };
+void plan_conv(Builder& bd, ConvParams p, const uint8_t* tw0 = nullptr, const uint8_t* tw1 = nullptr, TcShare* share = nullptr,
+               Act* out_act = nullptr, int gn_G = 0, const QkvOut* qkv = nullptr) {
     p.B = bd.B;
     double flops = 0, bytes = 4.0 * p.B * (double)p.Tout * p.Cout;   // output write
     for (int s = 0; s < p.nseg; ++s) {
@@ -637,6 +654,12 @@ void plan_conv(Builder& bd, ConvParams p, const uint8_t* tw0 = nullptr, const ui
         }
         q.bias = p.bias; q.temb = p.temb; q.temb_stride = p.temb_stride; q.res = p.res; q.res_mode = p.res_mode; q.res_Tin = p.res_Tin;
         q.out = p.out;
+        if (qkv) { q.qkv16 = qkv->dst; q.qkv_H = qkv->H; q.qkv_ch = qkv->ch; }
+        if (out_act && g_conv_gn_fused && conv_tc_gn_ok(p.Cout, gn_G)) {
+            out_act->gn_nsplit = p.Tout / 16; out_act->gn_G = gn_G;
+            out_act->gn_part = bd.scratch((size_t)bd.B * out_act->gn_nsplit * gn_G * 3);
+            q.gn_partial = bd.ptr(out_act->gn_part); q.gn_cpg = p.Cout / gn_G;
+        }
         bd.add([q, x3](cudaStream_t st) { return launch_conv_tc(q, x3, st); }, 1, OP_CONV, flops, bytes);
         return;
     }
@@ -657,7 +680,7 @@ Act plan_res(Builder& bd, const ULayer& l, const Act& x0, const Act* x1, const U
         p.nseg = 1; p.Cout = l.cout; p.Tout = Tc; p.Tc = Tc; p.stride = 1; p.pad_left = 1;
         p.bias = l.b1; p.temb = io.temb + l.emb_off; p.temb_stride = io.temb_stride;
         p.out = bd.wptr(h1);
-        plan_conv(bd, p, l.t_w1, nullptr, &share);
+        plan_conv(bd, p, l.t_w1, nullptr, &share, &h1, 32);
     }
     Act y = bd.act(l.cout, Tc);
     {
@@ -674,32 +697,41 @@ Act plan_res(Builder& bd, const ULayer& l, const Act& x0, const Act* x1, const U
         }
         p.out = bd.wptr(y);
         share.want_raw = false;
-        plan_conv(bd, p, l.t_w2, l.t_wskip, &share);
+        plan_conv(bd, p, l.t_w2, l.t_wskip, &share, &y, 32);   // every consumer of a block output normalises with 32 groups
     }
     return y;
 }
 
 Act plan_attn(Builder& bd, const ULayer& l, const Act& x) {
-    Act qkv = bd.act(3 * l.ch, x.T);
+    const int hch = l.ch / l.heads;
+    const bool attn_tc = bd.math != EEGLDM_MATH_FP32_SIMT && attn_tc_eligible(x.T, hch);
+    // f16x3: the qkv conv's epilogue writes the attention kernel's fp16 hi/lo operand images directly (no fp32 qkv tensor)
+    const bool fuse_qkv = attn_tc && g_conv_qkv_fused && bd.math == EEGLDM_MATH_F16X3_TC && l.t_wqkv &&
+                          conv_tc_eligible(x.C, 0, 3 * l.ch, x.T, 1, 1);
+    std::shared_ptr<Buf> q16;
+    if (attn_tc) q16 = bd.scratch((attn_qkv16_bytes(bd.B, x.T, l.heads, hch) + 3) / 4);
+    Act qkv;
+    if (!fuse_qkv) qkv = bd.act(3 * l.ch, x.T);
     {
         ScaleShift ss = plan_gn(bd, x, nullptr, 32, l.g1, l.be1, 1e-6f);
         ConvParams p{};
         p.seg[0] = make_seg(bd, x, nullptr, &ss, 0, RS_NONE, l.wqkv, 1);
         p.nseg = 1; p.Cout = 3 * l.ch; p.Tout = x.T; p.Tc = x.T; p.stride = 1; p.pad_left = 0;
-        p.bias = l.bqkv; p.out = bd.wptr(qkv);
-        plan_conv(bd, p, l.t_wqkv);
+        p.bias = l.bqkv; p.out = fuse_qkv ? nullptr : bd.wptr(qkv);
+        QkvOut qo{fuse_qkv ? reinterpret_cast<uint8_t*>(bd.ptr(q16)) : nullptr, l.heads, hch};
+        plan_conv(bd, p, l.t_wqkv, nullptr, nullptr, nullptr, 0, fuse_qkv ? &qo : nullptr);
     }
     Act a = bd.act(l.ch, x.T);
-    const int hch = l.ch / l.heads;
-    if (bd.math != EEGLDM_MATH_FP32_SIMT && attn_tc_eligible(x.T, hch)) {
-        // tensor-pipe attention: split q,k,v into fp16 hi/lo operand images, then S = QK^T -> softmax -> PV in one kernel
+    if (attn_tc) {
+        // tensor-pipe attention: q,k,v as fp16 hi/lo operand images, then S = QK^T -> softmax -> PV in one kernel
         const bool x3 = bd.math == EEGLDM_MATH_F16X3_TC;
-        auto q16 = bd.scratch((attn_qkv16_bytes(bd.B, x.T, l.heads, hch) + 3) / 4);
-        const float* qsrc = bd.ptr(qkv);
         uint8_t* qdst = reinterpret_cast<uint8_t*>(bd.ptr(q16));
         const int B = bd.B, T = x.T, H = l.heads;
-        bd.add([=](cudaStream_t st) { return launch_qkv_split(qsrc, qdst, B, T, H, hch, st); }, 1, OP_SPLIT, 0.0,
-               8.0 * B * (double)T * 3 * l.ch);
+        if (!fuse_qkv) {
+            const float* qsrc = bd.ptr(qkv);
+            bd.add([=](cudaStream_t st) { return launch_qkv_split(qsrc, qdst, B, T, H, hch, st); }, 1, OP_SPLIT, 0.0,
+                   8.0 * B * (double)T * 3 * l.ch);
+        }
         AttnTcParams tp{qdst, bd.wptr(a), T, H, hch, B, 1.4426950408889634f / sqrtf((float)hch)};
         bd.add([tp, x3](cudaStream_t st) { return launch_attention_tc(tp, x3, st); }, 1, OP_ATTN,
                4.0 * B * (double)T * T * l.ch, 4.0 * B * (double)T * l.ch * 4.0);
@@ -710,6 +742,7 @@ Act plan_attn(Builder& bd, const ULayer& l, const Act& x) {
                4.0 * bd.B * (double)x.T * x.T * l.ch, 4.0 * bd.B * (double)x.T * l.ch * 4.0);
     }
     qkv.buf.reset();
+    q16.reset();
     Act y = bd.act(l.ch, x.T);
     {
         ConvParams p{};
@@ -717,7 +750,7 @@ Act plan_attn(Builder& bd, const ULayer& l, const Act& x) {
         p.nseg = 1; p.Cout = l.ch; p.Tout = x.T; p.Tc = x.T; p.stride = 1; p.pad_left = 0;
         p.bias = l.bproj; p.res = bd.ptr(x); p.res_mode = RS_NONE; p.res_Tin = x.T;
         p.out = bd.wptr(y);
-        plan_conv(bd, p, l.t_wproj);
+        plan_conv(bd, p, l.t_wproj, nullptr, nullptr, &y, 32);
     }
     return y;
 }
@@ -1211,8 +1244,10 @@ int eegldm_set_conv_cluster(int ctas) {
     return EEGLDM_OK;
 }
 
-int eegldm_set_conv_tuning(int pair, int bn256_min_stages) {
+int eegldm_set_conv_tuning(int pair, int bn256_min_stages, int fuse_epilogues) {
     if (pair != 0 && pair != 1) return fail(EEGLDM_ERR_INVALID, "pair must be 0 or 1");
+    g_conv_gn_fused = (fuse_epilogues & 1) != 0;
+    g_conv_qkv_fused = (fuse_epilogues & 2) != 0;
     if (bn256_min_stages < 1) return fail(EEGLDM_ERR_INVALID, "bn256_min_stages must be >= 1");
     g_conv_tc_pair = pair;
     g_conv_tc_bn256_stages = bn256_min_stages;
@@ -1616,6 +1651,84 @@ int eegldm_test_conv(const float* x_dev, const float* scale_dev, const float* sh
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);   // the temporary weight pool / U are freed on return
     if (U) cudaFree(U);
     if (ce != cudaSuccess) return cuda_fail(ce, "conv launch");
+    return EEGLDM_OK;
+}
+
+// tcgen05 convolution (no prologue, bias only) whose epilogue also emits the GroupNorm(G) statistics of its output;
+// gn_finalize turns them into mean / rstd [B][G] (tests/test_gpu_conv.py compares both with torch on the same output).
+int eegldm_test_conv_gn(const float* x_dev, const float* w_host, const float* bias_host, int B, int T, int Cin, int Cout, int k,
+                        int G, float* out_dev, float* mean_dev, float* rstd_dev, void* stream) {
+    if (!x_dev || !w_host || !out_dev || !mean_dev || !rstd_dev) return fail(EEGLDM_ERR_INVALID, "null argument");
+    if (!conv_tc_eligible(Cin, 0, Cout, T, k, 1) || !conv_tc_gn_ok(Cout, G)) return fail(EEGLDM_ERR_SHAPE, "shape not eligible");
+    cudaStream_t st = (cudaStream_t)stream;
+    std::vector<uint16_t> img;
+    pack_conv_tc(w_host, Cout, Cin, k, true, img);
+    WeightPool wp;
+    const size_t o_t = wp.push_u16(img);
+    const size_t o_b = bias_host ? wp.push(bias_host, Cout) : 0;
+    const size_t o_one = wp.push(std::vector<float>((size_t)Cout, 1.0f)), o_zero = wp.push(std::vector<float>((size_t)Cout, 0.0f));
+    int r = wp.upload();
+    if (r) return r;
+    TcConvParams q{};
+    q.nseg = 1; q.Cout = Cout; q.Tout = T; q.nsegs16 = (int)((long long)B * T / 16);
+    q.bn = conv_tc_bn(Cout, Cin / TC_BK * k);
+    uint8_t* U = nullptr;
+    float *part = nullptr, *ss = nullptr;
+    const int nsplit = T / 16;
+    cudaError_t ce = cudaMalloc((void**)&U, act_split_bytes(q.nsegs16, Cin));
+    if (ce == cudaSuccess) ce = cudaMalloc((void**)&part, (size_t)B * nsplit * G * 3 * sizeof(float));
+    if (ce == cudaSuccess) ce = cudaMalloc((void**)&ss, (size_t)B * Cout * 2 * sizeof(float));
+    if (ce == cudaSuccess) {
+        ActSplitParams sp{x_dev, nullptr, Cin, 0, nullptr, nullptr, 0, RS_NONE, T, T, q.nsegs16, Cin / TC_BK, U, nullptr};
+        ce = launch_act_split(sp, true, st);
+    }
+    q.seg[0] = TcSeg{U, reinterpret_cast<const uint8_t*>(wp.at(o_t)), k, Cin / TC_BK};
+    q.bias = bias_host ? wp.at(o_b) : nullptr; q.out = out_dev; q.gn_partial = part; q.gn_cpg = Cout / G;
+    if (ce == cudaSuccess) ce = launch_conv_tc(q, true, st);
+    GnParams g{};
+    g.C0 = Cout; g.T = T; g.G = G; g.gamma = wp.at(o_one); g.beta = wp.at(o_zero); g.eps = 1e-6f; g.B = B;
+    g.scale = ss; g.shift = ss ? ss + (size_t)B * Cout : nullptr; g.partial = part; g.nsplit = nsplit;
+    g.mean_out = mean_dev; g.rstd_out = rstd_dev;
+    if (ce == cudaSuccess) ce = launch_groupnorm_finalize(g, st);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+    cudaFree(U); cudaFree(part); cudaFree(ss);
+    if (ce != cudaSuccess) return cuda_fail(ce, "conv + GroupNorm statistics");
+    return EEGLDM_OK;
+}
+
+// qkv 1x1 convolution writing attention operand images from its epilogue, followed by the tcgen05 attention kernel
+// (the fused path of plan_attn): x [B][T][C] fp32, w [3C][C][1], out [B][T][C]; C = H*ch.
+int eegldm_test_qkv_attention(const float* x_dev, const float* w_host, const float* bias_host, int B, int T, int H, int ch,
+                              float* out_dev, void* stream) {
+    if (!x_dev || !w_host || !out_dev) return fail(EEGLDM_ERR_INVALID, "null argument");
+    const int Cc = H * ch;
+    if (!conv_tc_eligible(Cc, 0, 3 * Cc, T, 1, 1) || !attn_tc_eligible(T, ch)) return fail(EEGLDM_ERR_SHAPE, "shape not eligible");
+    cudaStream_t st = (cudaStream_t)stream;
+    std::vector<uint16_t> img;
+    pack_conv_tc(w_host, 3 * Cc, Cc, 1, true, img);
+    WeightPool wp;
+    const size_t o_t = wp.push_u16(img);
+    const size_t o_b = bias_host ? wp.push(bias_host, 3 * Cc) : 0;
+    int r = wp.upload();
+    if (r) return r;
+    TcConvParams q{};
+    q.nseg = 1; q.Cout = 3 * Cc; q.Tout = T; q.nsegs16 = (int)((long long)B * T / 16);
+    q.bn = conv_tc_bn(3 * Cc, Cc / TC_BK);
+    uint8_t *U = nullptr, *q16 = nullptr;
+    cudaError_t ce = cudaMalloc((void**)&U, act_split_bytes(q.nsegs16, Cc));
+    if (ce == cudaSuccess) ce = cudaMalloc((void**)&q16, attn_qkv16_bytes(B, T, H, ch));
+    if (ce == cudaSuccess) {
+        ActSplitParams sp{x_dev, nullptr, Cc, 0, nullptr, nullptr, 0, RS_NONE, T, T, q.nsegs16, Cc / TC_BK, U, nullptr};
+        ce = launch_act_split(sp, true, st);
+    }
+    q.seg[0] = TcSeg{U, reinterpret_cast<const uint8_t*>(wp.at(o_t)), 1, Cc / TC_BK};
+    q.bias = bias_host ? wp.at(o_b) : nullptr; q.qkv16 = q16; q.qkv_H = H; q.qkv_ch = ch;
+    if (ce == cudaSuccess) ce = launch_conv_tc(q, true, st);
+    AttnTcParams tp{q16, out_dev, T, H, ch, B, 1.4426950408889634f / sqrtf((float)ch)};
+    if (ce == cudaSuccess) ce = launch_attention_tc(tp, true, st);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+    cudaFree(U); cudaFree(q16);
+    if (ce != cudaSuccess) return cuda_fail(ce, "qkv conv + attention");
     return EEGLDM_OK;
 }
 

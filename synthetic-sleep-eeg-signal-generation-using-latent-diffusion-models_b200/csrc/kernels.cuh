@@ -99,9 +99,14 @@ struct TcConvParams {
     const float* bias; const float* temb; int temb_stride;
     const float* res; int res_mode; int res_Tin;
     float* out;
+    uint8_t* qkv16;     // optional (then `out` is unused): the output is an AttentionBlock's qkv tensor -- write it as the fp16 hi/lo
+    int qkv_H, qkv_ch;  //   q/k/v operand images of attn_tc.cu (layout of launch_qkv_split) for qkv_H heads of qkv_ch channels; f16x3 only
+    float* gn_partial;  // optional: GroupNorm statistics of `out`, one (count, mean, M2) record per (sample, 16-position segment, group):
+    int gn_cpg;         //   [B][Tout/16][Cout/gn_cpg][3]; gn_cpg = channels per group in {4, 8, 16, 32} (conv_tc_gn_ok)
     int debug;          // timing experiments only (eegldm_bench_conv): 1 = no operand copies, 2 = no MMAs; results are garbage
 };
 bool conv_tc_eligible(int Cin0, int Cin1, int Cout, int Tout, int taps, int stride);
+bool conv_tc_gn_ok(int Cout, int G);         // can the conv epilogue emit the GroupNorm(G) statistics of its output?
 int conv_tc_bn(int Cout, int weight_stages);   // weight_stages = sum over segments of (Cin/32)*taps
 void pack_conv_tc(const float* w, int Cout, int Cin, int k, bool x3, std::vector<uint16_t>& out);
 cudaError_t launch_conv_tc(const TcConvParams& p, bool x3, cudaStream_t st);
@@ -109,6 +114,7 @@ extern int g_conv_tc_cluster;        // CTAs per cluster sharing weight stages (
 extern int g_conv_tc_pair;           // cta_group::2 CTA pairs (default 1)
 extern int g_conv_tc_bn256_stages;   // N=256 tiles from this many weight stages per tile
 cudaError_t launch_groupnorm(const GnParams& p, cudaStream_t st);
+cudaError_t launch_groupnorm_finalize(const GnParams& p, cudaStream_t st);   // statistics already in p.partial (p.nsplit records)
 int groupnorm_nsplit(int C, int T, int G);
 cudaError_t launch_attention_simt(const AttnParams& p, cudaStream_t st);
 // ---- tcgen05 attention (attn_tc.cu) ----------------------------------------------------------

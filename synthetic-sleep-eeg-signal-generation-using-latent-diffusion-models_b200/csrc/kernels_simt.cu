@@ -420,21 +420,54 @@ __global__ void gn_partial_generic_kernel(const GnParams p) {
     }
 }
 
-// grid (B); block 256
+// grid (B); block 256.  The nsplit partial records of a group are combined by 256/G' threads in parallel (G' = G rounded
+// up to a power of two <= 256), then pairwise through shared memory.
 __global__ void gn_finalize_kernel(const GnParams p) {
+    __shared__ Mom sm[256];
     __shared__ float s_mean[256], s_rstd[256];
     const int C = p.C0 + p.C1, b = blockIdx.x, cpg = C / p.G;
-    for (int g = threadIdx.x; g < p.G; g += blockDim.x) {
+    int gp = 1;
+    while (gp < p.G) gp <<= 1;
+    if (gp <= 256) {
+        const int lanes = 256 / gp;                       // threads per group
+        const int g = threadIdx.x % gp, part = threadIdx.x / gp;
         Mom r; r.n = 0.f; r.mean = 0.f; r.m2 = 0.f;
-        for (int sp = 0; sp < p.nsplit; ++sp) {
-            const float* o = p.partial + (((size_t)b * p.nsplit + sp) * p.G + g) * 3;
-            Mom m; m.n = o[0]; m.mean = o[1]; m.m2 = o[2];
-            r = mom_combine(r, m);
+        if (g < p.G)
+            for (int sp = part; sp < p.nsplit; sp += lanes) {
+                const float* o = p.partial + (((size_t)b * p.nsplit + sp) * p.G + g) * 3;
+                Mom m; m.n = o[0]; m.mean = o[1]; m.m2 = o[2];
+                r = mom_combine(r, m);
+            }
+        sm[threadIdx.x] = r;
+        __syncthreads();
+        for (int off = lanes / 2; off > 0; off >>= 1) {
+            if (part < off) sm[threadIdx.x] = mom_combine(sm[threadIdx.x], sm[threadIdx.x + off * gp]);
+            __syncthreads();
         }
-        const float var = r.m2 / r.n;  // biased variance, as nn.GroupNorm
-        s_mean[g] = r.mean;
-        s_rstd[g] = 1.0f / sqrtf(var + p.eps);
-        if (p.mean_out) { p.mean_out[(size_t)b * p.G + g] = s_mean[g]; p.rstd_out[(size_t)b * p.G + g] = s_rstd[g]; }
+        if (part == 0 && g < p.G) {
+            r = sm[g];
+            s_mean[g] = r.mean;
+            s_rstd[g] = 1.0f / sqrtf(r.m2 / r.n + p.eps);   // biased variance, as nn.GroupNorm
+            if (p.mean_out) { p.mean_out[(size_t)b * p.G + g] = s_mean[g]; p.rstd_out[(size_t)b * p.G + g] = s_rstd[g]; }
+        }
+    } else {
+        for (int g = threadIdx.x; g < p.G; g += blockDim.x) {
+            Mom r; r.n = 0.f; r.mean = 0.f; r.m2 = 0.f;
+            for (int sp = 0; sp < p.nsplit; ++sp) {
+                const float* o = p.partial + (((size_t)b * p.nsplit + sp) * p.G + g) * 3;
+                Mom m; m.n = o[0]; m.mean = o[1]; m.m2 = o[2];
+                r = mom_combine(r, m);
+            }
+            s_mean[g % 256] = r.mean;   // G > 256 is not used by any model here; scale/shift written directly below
+            s_rstd[g % 256] = 1.0f / sqrtf(r.m2 / r.n + p.eps);
+            if (p.mean_out) { p.mean_out[(size_t)b * p.G + g] = r.mean; p.rstd_out[(size_t)b * p.G + g] = s_rstd[g % 256]; }
+            for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+                const float a = p.gamma[c] * s_rstd[g % 256];
+                p.scale[(size_t)b * C + c] = a;
+                p.shift[(size_t)b * C + c] = p.beta[c] - r.mean * a;
+            }
+        }
+        return;
     }
     __syncthreads();
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -687,6 +720,13 @@ cudaError_t launch_groupnorm(const GnParams& p, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     gn_finalize_kernel<<<p.B, 256, 0, st>>>(p);
     g_launch_count += 2;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_groupnorm_finalize(const GnParams& p, cudaStream_t st) {
+    if (p.B <= 0) return cudaSuccess;
+    gn_finalize_kernel<<<p.B, 256, 0, st>>>(p);
+    g_launch_count += 1;
     return cudaGetLastError();
 }
 

@@ -66,7 +66,7 @@ SIGNATURES = {
     "eegldm_launch_count": (C.c_int64, []),
     "eegldm_set_graphs": (C.c_int, [C.c_int]),
     "eegldm_set_conv_cluster": (C.c_int, [C.c_int]),
-    "eegldm_set_conv_tuning": (C.c_int, [C.c_int, C.c_int]),
+    "eegldm_set_conv_tuning": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "eegldm_profile_enable": (C.c_int, [C.c_int]),
     "eegldm_profile_record": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "eegldm_profile_read": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
@@ -96,6 +96,8 @@ SIGNATURES = {
     "eegldm_sched_ddim_tables": (C.c_int, [C.POINTER(SchedCfg), C.c_int, _I64P, _FP]),
     "eegldm_timestep_embedding": (C.c_int, [_FP, C.c_int, C.c_int, _FP]),
     "eegldm_ddim_sample": (C.c_int, [_P, _P, C.POINTER(SchedCfg), _P, C.c_float, C.c_int, _P, C.c_int, C.c_int, _P]),
+    "eegldm_test_conv_gn": (C.c_int, [_P, _P, _P] + [C.c_int] * 6 + [_P, _P, _P, _P]),
+    "eegldm_test_qkv_attention": (C.c_int, [_P, _P, _P] + [C.c_int] * 4 + [_P, _P]),
     "eegldm_bench_conv": (C.c_int, [C.c_int] * 9 + [_P, _P]),
     "eegldm_test_conv": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
     "eegldm_test_attention": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),

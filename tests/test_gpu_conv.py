@@ -107,11 +107,11 @@ def test_conv_tile_shapes(built_lib, cuda_device, case, shape):
     Tc = {0: Tin, 1: Tin // 2, 2: Tin * 2}[rs]
     res = torch.randn(B, Tc, Cout, generator=g) if has_res else None
     ref = _ref(x, w, bias, scale, shift, aff, rs, res)
-    _lib.check(built_lib.eegldm_set_conv_tuning(*shape))
+    _lib.check(built_lib.eegldm_set_conv_tuning(*shape, 3))
     try:
         y = _run(built_lib, cuda_device, x, w, bias, scale, shift, aff, rs, res, "f16x3")
     finally:
-        _lib.check(built_lib.eegldm_set_conv_tuning(0, 1))
+        _lib.check(built_lib.eegldm_set_conv_tuning(0, 1, 3))
     assert torch.isfinite(y).all()
     torch.testing.assert_close(y, ref, rtol=1e-4, atol=2e-5)
 
@@ -119,6 +119,34 @@ def test_conv_tile_shapes(built_lib, cuda_device, case, shape):
 @pytest.mark.parametrize("case", BIG_CASES)
 def test_conv_default_shape_big(built_lib, cuda_device, case):
     test_conv_tile_shapes(built_lib, cuda_device, case, (0, 1))
+
+
+GN_CASES = [(3, 768, 128, 128, 3), (5, 192, 256, 512, 3), (2, 384, 128, 256, 1), (7, 48, 64, 128, 3), (3, 192, 512, 1024, 1)]
+
+
+@pytest.mark.parametrize("case", GN_CASES)
+def test_conv_epilogue_groupnorm_statistics(built_lib, cuda_device, case):
+    """The conv epilogue's GroupNorm(32) statistics of its own output (consumer: Normalize, unet.py:71-74) against
+    torch's mean / biased variance of that output; data with a large common offset exercises the cancellation-free path."""
+    from eegldm import _lib
+    B, T, Cin, Cout, k = case
+    G = 32
+    g = torch.Generator().manual_seed(Cin + Cout + T)
+    x = torch.randn(B, T, Cin, generator=g) + 3.0
+    w = torch.randn(Cout, Cin, k, generator=g) / (Cin * k) ** 0.5
+    bias = 5.0 + torch.randn(Cout, generator=g)
+    xd = x.to(cuda_device)
+    out = torch.empty(B, T, Cout, device=cuda_device)
+    mean = torch.empty(B, G, device=cuda_device)
+    rstd = torch.empty(B, G, device=cuda_device)
+    p = lambda t: C.c_void_p(t.data_ptr())
+    _lib.check(built_lib.eegldm_test_conv_gn(p(xd), p(w.contiguous()), p(bias.contiguous()), B, T, Cin, Cout, k, G, p(out), p(mean),
+                                             p(rstd), None))
+    y = out.cpu().double().reshape(B, T, G, Cout // G)
+    ref_mean = y.mean(dim=(1, 3))
+    ref_var = y.var(dim=(1, 3), unbiased=False)
+    torch.testing.assert_close(mean.cpu().double(), ref_mean, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(rstd.cpu().double(), 1.0 / torch.sqrt(ref_var + 1e-6), rtol=2e-5, atol=1e-6)
 
 
 ATTN_CASES = [(2, 192, 1, 512), (1, 128, 1, 128), (3, 64, 2, 128), (2, 256, 1, 256), (1, 32, 4, 128)]
@@ -145,3 +173,27 @@ def test_attention_matches_torch(built_lib, cuda_device, case, math):
         assert (y - ref).abs().max().item() < 2e-2
     else:
         torch.testing.assert_close(y, ref, rtol=1e-4, atol=2e-5)
+
+
+@pytest.mark.parametrize("case", [(3, 192, 1, 512), (2, 64, 2, 128), (5, 256, 1, 256), (2, 32, 4, 128)])
+def test_fused_qkv_conv_attention(built_lib, cuda_device, case):
+    """qkv conv -> attention with q, k, v handed over as fp16 hi/lo operand images written by the conv epilogue."""
+    from eegldm import _lib
+    B, T, H, ch = case
+    Cc = H * ch
+    g = torch.Generator().manual_seed(T + ch + H)
+    x = torch.randn(B, T, Cc, generator=g)
+    w = torch.randn(3 * Cc, Cc, 1, generator=g) / Cc ** 0.5
+    bias = 0.1 * torch.randn(3 * Cc, generator=g)
+    qkv = F.conv1d(x.double().transpose(1, 2), w.double(), bias.double())              # [B, 3C, T], legacy head layout
+    q, k, v = qkv.reshape(B * H, 3 * ch, T).split(ch, dim=1)
+    scale = 1.0 / (ch ** 0.25)
+    wgt = torch.softmax(torch.einsum("bct,bcs->bts", q * scale, k * scale), dim=-1)
+    ref = torch.einsum("bts,bcs->bct", wgt, v).reshape(B, Cc, T).float()
+    xd = x.to(cuda_device)
+    out = torch.full((B, T, Cc), float("nan"), device=cuda_device)
+    p = lambda t: C.c_void_p(t.data_ptr())
+    _lib.check(built_lib.eegldm_test_qkv_attention(p(xd), p(w.contiguous()), p(bias.contiguous()), B, T, H, ch, p(out), None))
+    y = out.cpu().transpose(1, 2)
+    assert torch.isfinite(y).all()
+    torch.testing.assert_close(y, ref, rtol=1e-4, atol=2e-5)
