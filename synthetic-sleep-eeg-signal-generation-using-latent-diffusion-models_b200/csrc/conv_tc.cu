@@ -225,27 +225,32 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const TcConvPar
             const int n_tile = w % n_ntiles, m_tile = (w / n_ntiles) * CL + crank;   // m_tile >= n_mtiles: idle slot of the last group
             const int as = lt % NSETS, use = lt / NSETS;
             const int co0 = n_tile * BN;
-            int rb[8], rt[8];   // sample / position of this thread's 8 rows (rb < 0: row past the batch)
-            size_t ooff[8], roff[8];
+            // This thread's 8 rows: row i is M row (TMEM lane) warp*32 + 4*i + lane/8 = segment 4*(i&1) + lane/8, position
+            // warp*4 + i/2 of that segment -- two segments (h = i & 1), four consecutive positions (j = i >> 1) each.
+            int rb[2], rt[2];   // sample (< 0: segment past the batch) and first position per segment
+            size_t obase[2], rbase[2];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int grow = warp * 32 + 4 * i + (lane >> 3);   // M row = TMEM lane
-                const int g = m_tile * 8 + (grow & 7);              // segment
-                rb[i] = g < p.nsegs16 ? g / spt : -1;
-                rt[i] = (g % spt) * 16 + (grow >> 3);
-                const int bb = max(rb[i], 0), t = rt[i];            // clamped: loads stay in bounds, stores are predicated
-                ooff[i] = ((size_t)bb * p.Tout + t) * p.Cout + co0 + col4;
+            for (int h = 0; h < 2; ++h) {
+                const int g = m_tile * 8 + 4 * h + (lane >> 3);
+                rb[h] = g < p.nsegs16 ? g / spt : -1;
+                rt[h] = (g % spt) * 16 + warp * 4;
+                const int bb = max(rb[h], 0), t = rt[h];            // clamped: loads stay in bounds, stores are predicated
+                obase[h] = ((size_t)bb * p.Tout + t) * p.Cout + co0 + col4;
                 const int tr = p.res_mode == RS_AVGPOOL2 ? 2 * t : (p.res_mode == RS_NEAREST2 ? (t >> 1) : t);
-                roff[i] = ((size_t)bb * p.res_Tin + tr) * p.Cout + co0 + col4;
+                rbase[h] = ((size_t)bb * p.res_Tin + tr) * p.Cout + co0 + col4;
             }
+            // residual row of position j: 2j (pooled pair), j/2 (nearest x2; rt is a multiple of 4) or j
+            const int rmul = p.res_mode == RS_AVGPOOL2 ? 4 : (p.res_mode == RS_NEAREST2 ? 1 : 2);   // half-rows per position
+#define OOFF(i) (obase[(i) & 1] + (size_t)((i) >> 1) * p.Cout)
+#define ROFF(i) (rbase[(i) & 1] + (size_t)((((i) >> 1) * rmul) >> 1) * p.Cout)
             // residual rows of one 32-column chunk, all 8 loads in flight at once (prefetched one chunk ahead)
             auto load_res = [&](int cb, float4 (&R)[8]) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     if (p.res_mode == RS_AVGPOOL2) {
-                        const float4 x0 = ldg4(p.res + roff[i] + cb), x1 = ldg4(p.res + roff[i] + p.Cout + cb);
+                        const float4 x0 = ldg4(p.res + ROFF(i) + cb), x1 = ldg4(p.res + ROFF(i) + p.Cout + cb);
                         R[i] = make_float4(0.5f * (x0.x + x1.x), 0.5f * (x0.y + x1.y), 0.5f * (x0.z + x1.z), 0.5f * (x0.w + x1.w));
-                    } else R[i] = ldg4(p.res + roff[i] + cb);
+                    } else R[i] = ldg4(p.res + ROFF(i) + cb);
                 }
             };
             float4 Rn[8];
@@ -258,8 +263,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const TcConvPar
 #pragma unroll
                     for (int i = 0; i < 8; ++i)
                         for (int cb = 0; cb < BN; cb += 32) {
-                            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.res + roff[i] + cb));
-                            if (p.res_mode == RS_AVGPOOL2) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.res + roff[i] + p.Cout + cb));
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.res + ROFF(i) + cb));
+                            if (p.res_mode == RS_AVGPOOL2) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.res + ROFF(i) + p.Cout + cb));
                         }
                 }
                 load_res(0, Rn);
@@ -273,6 +278,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const TcConvPar
 #pragma unroll
                 for (int i = 0; i < 8; ++i) R[i] = Rn[i];
                 if (p.res && cb + 32 < BN) load_res(cb + 32, Rn);
+                // bias / time-embedding rows of this chunk: issued before the TMEM loads so their latency is covered
+                const int co = co0 + cb + col4;
+                float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p.bias) bias4 = ldg4(p.bias + co);
+                float4 Tm[2];   // rows i and i+2 lie in the same segment, hence the same sample: two distinct rows per thread
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+                    Tm[h] = p.temb ? ldg4(p.temb + (size_t)max(rb[h], 0) * p.temb_stride + co) : make_float4(0.f, 0.f, 0.f, 0.f);
                 uint32_t v[32];
                 if (X3) {
                     uint32_t c2[32];
@@ -286,20 +299,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const TcConvPar
                 for (int j = 0; j < 8; ++j)
                     *reinterpret_cast<uint4*>(stg + lane * STG_LD + 4 * j) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                 __syncwarp();
-                const int co = co0 + cb + col4;
-                float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (p.bias) bias4 = ldg4(p.bias + co);
-                float4 Tm[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    Tm[i] = p.temb ? ldg4(p.temb + (size_t)max(rb[i], 0) * p.temb_stride + co) : make_float4(0.f, 0.f, 0.f, 0.f);
                 float4 O[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const float4 a = *reinterpret_cast<const float4*>(stg + (4 * i + (lane >> 3)) * STG_LD + col4);
-                    const float4 o = make_float4(a.x + bias4.x + Tm[i].x + R[i].x, a.y + bias4.y + Tm[i].y + R[i].y,
-                                                 a.z + bias4.z + Tm[i].z + R[i].z, a.w + bias4.w + Tm[i].w + R[i].w);
-                    if (!p.qkv16 && rb[i] >= 0) *reinterpret_cast<float4*>(p.out + ooff[i] + cb) = o;
+                    const float4 tb = Tm[i & 1];
+                    const float4 o = make_float4(a.x + bias4.x + tb.x + R[i].x, a.y + bias4.y + tb.y + R[i].y,
+                                                 a.z + bias4.z + tb.z + R[i].z, a.w + bias4.w + tb.w + R[i].w);
+                    if (!p.qkv16 && rb[i & 1] >= 0) *reinterpret_cast<float4*>(p.out + OOFF(i) + cb) = o;
                     O[i] = o;
                 }
                 if (p.qkv16) {
@@ -313,11 +320,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const TcConvPar
                                                    : (size_t)(c >> 7) * (T >> 5) * 2 * half + ((c & 127) >> 3) * 128 + (c & 7) * 2;
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        if (rb[i] < 0) continue;
-                        const int t = rt[i];
+                        if (rb[i & 1] < 0) continue;
+                        const int t = rt[i & 1] + (i >> 1);
                         const size_t tpart = which < 2 ? (size_t)(t >> 3) * 512 + (t & 7) * 16
                                                        : (size_t)(t >> 5) * 2 * half + ((t & 31) >> 3) * 2048 + (t & 7) * 16;
-                        uint8_t* dst = p.qkv16 + (((size_t)rb[i] * p.qkv_H + cq) * 3 + which) * plane + cpart + tpart;
+                        uint8_t* dst = p.qkv16 + (((size_t)rb[i & 1] * p.qkv_H + cq) * 3 + which) * plane + cpart + tpart;
                         uint2 hi, lo;
                         split4_f16(O[i], hi, lo);
                         *reinterpret_cast<uint2*>(dst) = hi;
@@ -363,6 +370,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const TcConvPar
                 }
                 __syncwarp();   // staging buffer is reused by the next chunk
             }
+#undef OOFF
+#undef ROFF
             tc_fence_before();
             if (PAIR) mbar_arrive_cluster(barAccEmpty + 8 * as, 0);   // the leader's MMA warp owns both CTAs' accumulators
             else mbar_arrive(barAccEmpty + 8 * as);                   // this accumulator set may be overwritten

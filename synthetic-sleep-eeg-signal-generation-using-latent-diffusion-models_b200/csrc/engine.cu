@@ -337,7 +337,7 @@ struct eegldm_unet {
 
 namespace {
 
-bool g_conv_qkv_fused = true;  // the qkv conv writes attention operand images directly (f16x3; eegldm_set_conv_tuning)
+bool g_conv_qkv_fused = false; // the qkv conv writes attention operand images directly (f16x3; eegldm_set_conv_tuning): measured no faster
 bool g_conv_gn_fused = true;   // tensor-pipe convs emit the GroupNorm statistics of their output (eegldm_set_conv_tuning)
 bool g_graphs_enabled = true;
 

@@ -29,7 +29,7 @@ for (T, ci, co, k, res) in SHAPES:
             if bn256 == 1 and co % 256:
                 continue
             _lib.check(L.eegldm_set_conv_cluster(cl))
-            _lib.check(L.eegldm_set_conv_tuning(pair, bn256, 3))
+            _lib.check(L.eegldm_set_conv_tuning(pair, bn256, 1))
             ms = []
             for dbg in (0, 1, 2, 4):
                 m = C.c_float()
