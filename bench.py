@@ -154,6 +154,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
 
     ucfg, usd, acfg, asd = _oracle_models()     # seeded random-init weights (no checkpoint ships)
+    _lib.check(eegldm.lib().eegldm_set_sample_lanes(args.lanes))
     unet = eegldm.UNetModel(**ucfg, math=args.math)
     unet.load_state_dict(usd)
     unet = unet.to(dev).eval()
@@ -261,7 +262,7 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "config 3: DDIM-50 sampling, batch %d per GPU of [1,768] latents, config_ldm.yaml UNet "
                                    "(30.5M params), AEKL 2-2-4 decode -> [B,1,3072]" % B,
-                       "math": args.math, "batch_per_gpu": B, "ddim_steps": DDIM_STEPS,
+                       "math": args.math, "batch_per_gpu": B, "ddim_steps": DDIM_STEPS, "graph_lanes": args.lanes,
                        "parallelism": f"batch-shard x{world}, one all-gather of decoded windows" if world > 1 else "single GPU",
                        "l2": "activations per launch (>= 400 MB at B=1024) exceed the 126 MB L2; no explicit flush"},
             "e2e": {"value": e2e, "unit": "windows/s", "h2d_bytes_per_step": world * noise_host.numel() * 4,
@@ -354,6 +355,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=1024, help="windows per GPU per step (config 3: 1024)")
     ap.add_argument("--math", default=os.environ.get("EEGLDM_BENCH_MATH", "f16x3"), help="fp32 | f16x3 (both parity-green)")
+    ap.add_argument("--lanes", type=int, default=1, help="independent batch halves inside the denoise-step graph (1 or 2)")
     ap.add_argument("--ref-batch", type=int, default=8, help="windows per CPU-baseline step (bounded sample)")
     ap.add_argument("--profile-batch", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")

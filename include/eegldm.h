@@ -51,6 +51,12 @@ const char* eegldm_version(void);
 /* number of CUDA kernels launched by this library since process start (bench.py's gpu_launches) */
 int64_t eegldm_launch_count(void);
 
+/* Denoise-step graph of eegldm_ddim_sample: lanes = 2 plans the batch as two independent halves captured on two streams
+ * inside the graph, so the HBM-bound passes of one half overlap the tensor-bound convolutions of the other; lanes = 1
+ * (default; measured faster under the board power cap) is a single chain.  Rows are independent: results are bit-identical.  Takes effect for graphs captured afterwards
+ * (new (B, T) shapes or new models). */
+int eegldm_set_sample_lanes(int lanes);
+
 /* Tuning knob of the tcgen05 conv kernel: CTAs per thread-block cluster that share each weight stage through a
  * multicast bulk copy (1, 2 or 4; default 2).  Changing it invalidates nothing but must not race with launches. */
 int eegldm_set_conv_cluster(int ctas);

@@ -315,6 +315,8 @@ struct eegldm_unet {
     float* coef_cur = nullptr;                             // [2]
     int* step_ctr = nullptr;
     cudaStream_t cap_stream = nullptr;                     // private stream used only for graph capture
+    cudaStream_t cap_stream2 = nullptr;                    // second capture stream: the other batch half of a two-lane step
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     float* xbuf = nullptr; size_t xbuf_cap = 0;            // ddim state [B][T][z]
     float* xtmp = nullptr; size_t xtmp_cap = 0;            // NCL<->NLC staging
     std::vector<float> table_key;                          // identifies the cached temb/coef tables
@@ -322,6 +324,9 @@ struct eegldm_unet {
     ~eegldm_unet() {
         drop_graphs();
         if (cap_stream) cudaStreamDestroy(cap_stream);
+        if (cap_stream2) cudaStreamDestroy(cap_stream2);
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        if (ev_join) cudaEventDestroy(ev_join);
         for (void* p : {(void*)arena, (void*)temb_fwd, (void*)tscratch, (void*)temb_step, (void*)temb_table,
                         (void*)coef_table, (void*)coef_cur, (void*)step_ctr, (void*)xbuf, (void*)xtmp})
             if (p) cudaFree(p);
@@ -340,6 +345,12 @@ namespace {
 bool g_conv_qkv_fused = false; // the qkv conv writes attention operand images directly (f16x3; eegldm_set_conv_tuning): measured no faster
 bool g_conv_gn_fused = true;   // tensor-pipe convs emit the GroupNorm statistics of their output (eegldm_set_conv_tuning)
 bool g_graphs_enabled = true;
+// Denoise-step graph of eegldm_ddim_sample: 2 = the batch is planned as two independent halves captured on two streams
+// (fork / join inside the graph), so the HBM-bound passes of one half (GroupNorm, activation split) run underneath the
+// tensor-bound convolutions of the other half instead of in series with them; 1 = one chain (default: the step runs
+// at the board's power cap, ~1.63 GHz of 1.965, so overlapping the two kinds of work buys nothing -- measured 312 vs 320
+// windows/s at B=1024, profiles/r01_summary.md).
+int g_sample_lanes = 1;
 
 template <class T>
 int ensure(T*& p, size_t& cap, size_t n) {
@@ -851,6 +862,34 @@ int build_unet_plan(eegldm_unet* h, int B, int T, const UNetIO& io, Builder& out
     return plan_unet_body(h, out, T, io);
 }
 
+// Two independent plans over the batch halves [0, B0) and [B0, B) with disjoint arena regions (B0 = ceil(B/2)).
+// io describes the whole batch; per-sample tensors of the second half are offset by B0 rows.
+int build_unet_plan_lanes(eegldm_unet* h, int B, int T, const UNetIO& io, Builder& lane0, Builder& lane1) {
+    const int levels = h->cfg.n_channel_mult;
+    if (T <= 0 || (T % (1 << (levels - 1))) != 0)
+        return fail(EEGLDM_ERR_SHAPE, "T must be a positive multiple of 2^(levels-1)");
+    const int B0 = (B + 1) / 2, B1 = B - B0;
+    Builder sizing; sizing.B = B0; sizing.math = h->math;
+    int r = plan_unet_body(h, sizing, T, io);
+    if (r) return r;
+    const size_t region = (sizing.peak + 63) & ~size_t(63);
+    if (2 * region > h->arena_cap) {
+        h->drop_graphs();
+        r = ensure(h->arena, h->arena_cap, 2 * region);
+        if (r) return r;
+    }
+    lane0.B = B0; lane0.base = h->arena; lane0.math = h->math;
+    r = plan_unet_body(h, lane0, T, io);
+    if (r) return r;
+    UNetIO io1 = io;
+    const size_t xo = (size_t)B0 * T * h->cfg.in_channels, oo = (size_t)B0 * T * h->cfg.out_channels;
+    io1.x = io.x + xo; io1.out = io.out + oo;
+    if (io.ddim_x) io1.ddim_x = io.ddim_x + oo;
+    if (io.temb_stride) io1.temb = io.temb + (size_t)B0 * io.temb_stride;
+    lane1.B = B1; lane1.base = h->arena + region; lane1.math = h->math;
+    return plan_unet_body(h, lane1, T, io1);
+}
+
 struct ProfRec { OpMeta m; cudaEvent_t e0, e1; };
 bool g_profile = false;
 std::vector<ProfRec> g_prof;
@@ -1237,6 +1276,11 @@ const char* eegldm_last_error(void) { return g_err.c_str(); }
 const char* eegldm_version(void) { return "eegldm 0.1 (sm_100a)"; }
 int64_t eegldm_launch_count(void) { return (int64_t)g_launch_count.load(); }
 int eegldm_set_graphs(int enabled) { g_graphs_enabled = enabled != 0; return EEGLDM_OK; }
+int eegldm_set_sample_lanes(int lanes) {
+    if (lanes != 1 && lanes != 2) return fail(EEGLDM_ERR_INVALID, "lanes must be 1 or 2");
+    g_sample_lanes = lanes;
+    return EEGLDM_OK;
+}
 
 int eegldm_set_conv_cluster(int ctas) {
     if (ctas != 1 && ctas != 2 && ctas != 4) return fail(EEGLDM_ERR_INVALID, "cluster size must be 1, 2 or 4");
@@ -1535,16 +1579,38 @@ int eegldm_ddim_sample(eegldm_unet* u, eegldm_aekl* a, const eegldm_sched_cfg* s
         auto key2 = std::make_pair(B, T);
         auto it = u->graphs.find(key2);
         if (it == u->graphs.end()) {
-            Builder bd;
-            r = build_unet_plan(u, B, T, io, bd);   // may grow the arena (and drop stale graphs)
+            const bool two = g_sample_lanes == 2 && B >= 2;
+            Builder bd, bd1;
+            r = two ? build_unet_plan_lanes(u, B, T, io, bd, bd1) : build_unet_plan(u, B, T, io, bd);   // may grow the arena (and drop stale graphs)
             if (r) return r;
             GraphEntry ge;
             const long long before = g_launch_count.load();
             // capture on a private stream: the caller's stream may be the legacy default stream, which cannot capture
             if (!u->cap_stream) CU(cudaStreamCreateWithFlags(&u->cap_stream, cudaStreamNonBlocking));
+            if (two && !u->cap_stream2) {
+                CU(cudaStreamCreateWithFlags(&u->cap_stream2, cudaStreamNonBlocking));
+                CU(cudaEventCreateWithFlags(&u->ev_fork, cudaEventDisableTiming));
+                CU(cudaEventCreateWithFlags(&u->ev_join, cudaEventDisableTiming));
+            }
             CU(cudaStreamBeginCapture(u->cap_stream, cudaStreamCaptureModeThreadLocal));
-            r = emit_step(bd, u->cap_stream);
-            cudaError_t e = cudaStreamEndCapture(u->cap_stream, &ge.graph);
+            cudaError_t e = launch_step_advance(u->temb_table, u->emb_total, u->temb_step, u->coef_table, u->coef_cur, u->step_ctr,
+                                                u->cap_stream);
+            if (e != cudaSuccess) r = cuda_fail(e, "step_advance");
+            bool forked = false;
+            if (!r && two) {   // fork: the second half's chain depends on step_advance only
+                e = cudaEventRecord(u->ev_fork, u->cap_stream);
+                if (e == cudaSuccess) e = cudaStreamWaitEvent(u->cap_stream2, u->ev_fork, 0);
+                if (e != cudaSuccess) r = cuda_fail(e, "graph fork");
+                else forked = true;
+            }
+            if (!r) r = run_ops(bd, u->cap_stream);
+            if (forked) {
+                if (!r) r = run_ops(bd1, u->cap_stream2);
+                e = cudaEventRecord(u->ev_join, u->cap_stream2);   // join (also on the error path: a capture cannot end forked)
+                if (e == cudaSuccess) e = cudaStreamWaitEvent(u->cap_stream, u->ev_join, 0);
+                if (e != cudaSuccess && !r) r = cuda_fail(e, "graph join");
+            }
+            e = cudaStreamEndCapture(u->cap_stream, &ge.graph);
             if (r) { if (ge.graph) cudaGraphDestroy(ge.graph); return r; }
             if (e != cudaSuccess) return cuda_fail(e, "cudaStreamEndCapture");
             ge.n_kernels = (int)(g_launch_count.load() - before);

@@ -66,6 +66,7 @@ SIGNATURES = {
     "eegldm_launch_count": (C.c_int64, []),
     "eegldm_set_graphs": (C.c_int, [C.c_int]),
     "eegldm_set_conv_cluster": (C.c_int, [C.c_int]),
+    "eegldm_set_sample_lanes": (C.c_int, [C.c_int]),
     "eegldm_set_conv_tuning": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "eegldm_profile_enable": (C.c_int, [C.c_int]),
     "eegldm_profile_record": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),

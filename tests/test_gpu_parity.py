@@ -178,6 +178,14 @@ def test_ddim_z3_and_graph_vs_eager(built_lib, cuda_device):
     finally:
         built_lib.eegldm_set_graphs(1)
     assert torch.equal(y, y2)     # graph replay == eager launches, bit for bit
+    # two-lane graph (batch halves on two captured streams, B = 5 -> 3 + 2): rows are independent, so bit-identical again
+    built_lib.eegldm_set_sample_lanes(2)
+    try:
+        unet2 = _unet(ucfg, usd, cuda_device)     # fresh handle: graphs are cached per (B, T)
+        y3 = eegldm.ddim_sample(unet2, sched, noise.to(cuda_device), 10, aekl, scale_factor=1.3)
+    finally:
+        built_lib.eegldm_set_sample_lanes(1)
+    assert torch.equal(y, y3)
 
 
 @pytest.mark.parametrize("math", MATH)
