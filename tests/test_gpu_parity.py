@@ -107,6 +107,19 @@ def test_aekl_encode_decode_matches_oracle(built_lib, cuda_device, nc, z):
     assert m.encode_stage_2_inputs(x.to(cuda_device)).shape == mu.shape
 
 
+@pytest.mark.parametrize("name", ["c32_112_z1", "c32_12_z3"])
+def test_aekl_matches_reference_golden(built_lib, cuda_device, name):
+    """CUDA autoencoder against vectors produced by the reference's in-tree class (tests/golden/make_golden_aekl.py)."""
+    from test_oracle_aekl import golden_case
+    cfg, sd, t = golden_case(name)
+    m = _aekl(cfg, sd, cuda_device)
+    gmu, gsigma = m.encode(t["x"].to(cuda_device))
+    torch.testing.assert_close(gmu.cpu(), t["mu"], rtol=RTOL, atol=ATOL)
+    torch.testing.assert_close(gsigma.cpu(), t["sigma"], rtol=RTOL, atol=ATOL)
+    z = t["mu"] + t["eps"] * t["sigma"]
+    torch.testing.assert_close(m.decode(z.to(cuda_device)).cpu(), t["recon"], rtol=RTOL, atol=ATOL)
+
+
 def test_aekl_forward_abi_with_supplied_eps(built_lib, cuda_device):
     import ctypes as C
     from eegldm import _lib

@@ -97,3 +97,20 @@ def test_aekl_kl_and_sampling():
     assert float(oa.kl_loss(mu, sigma)) == 0.0
     eps = torch.full((2, 1, 8), 2.0)
     torch.testing.assert_close(oa.sampling(mu + 1, sigma * 3, eps), torch.full((2, 1, 8), 7.0))
+
+
+@pytest.mark.parametrize("name", ["scaled_linear", "linear"])
+def test_noise_schedule_matches_reference_in_tree_golden(name):
+    """betas / cumulative alphas / add_noise against the reference's in-tree ancestor of the MONAI schedulers
+    (src/models/ldm.py make_beta_schedule + DDPM.q_sample; tests/golden/make_golden_sched.py).  The reference computes
+    the tables in float64, upstream (and the oracle) in float32: agreement to fp32 round-off of a 1000-term product."""
+    import os
+    from conftest import GOLDEN
+    from golden.make_golden_sched import SCHEDULES
+    g = np.load(os.path.join(GOLDEN, "sched_golden.npz"))
+    _, oname, b0, b1 = SCHEDULES[name]
+    s = DDPMScheduler(num_train_timesteps=1000, beta_start=b0, beta_end=b1, schedule=oname)
+    np.testing.assert_allclose(s.betas.numpy(), g[name + "/betas"], rtol=2e-6)
+    np.testing.assert_allclose(s.alphas_cumprod.numpy(), g[name + "/alphas_cumprod"], rtol=2e-4)   # 1000 fp32 factors
+    xt = s.add_noise(torch.from_numpy(g["x0"]), torch.from_numpy(g["noise"]), torch.from_numpy(g["t"]))
+    torch.testing.assert_close(xt, torch.from_numpy(g[name + "/x_t"]), rtol=1e-4, atol=1e-5)
