@@ -2,7 +2,9 @@
 
 Upstream: ``monai-generative`` ``generative/networks/nets/autoencoderkl.py`` (classes
 Upsample, Downsample, ResBlock, Encoder, Decoder, AutoencoderKL) -- not installable
-here, version unpinned (``requirements.txt:12``) -> **parity unpinned**.  Restated
+here, version unpinned (``requirements.txt:12``) -> **parity unpinned against upstream,
+pinned against its in-tree ancestor**: golden vectors produced by the reference's
+``src/models/ae_kl.py`` (tests/golden/make_golden_aekl.py, tests/test_oracle_aekl.py).  Restated
 from the published algorithm as specified in SURVEY.md section 8a rows 10-12 and
 cross-checked against the in-tree ancestor ``/root/reference/src/models/ae_kl.py``:
 ResBlock ``:48-80``, Downsample pad-right-1 + stride-2 ``:33-45``, Upsample

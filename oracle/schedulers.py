@@ -5,8 +5,9 @@ Upstream: ``monai-generative`` (PyPI, GitHub Project-MONAI/GenerativeModels),
 reference (``requirements.txt:12``), 0.2.x API implied by the call sites
 ``src/sample_trials.py:136-145,163`` (``schedule="scaled_linear_beta"``, 2-tuple
 ``step`` return).  The package is not installable here -> **parity unpinned**
-against upstream; pinned instead by the closed-form known answers of SURVEY.md
-section 4 (tests/test_oracle_schedulers.py).
+against upstream; the beta / cumulative-alpha tables and ``add_noise`` are pinned against the
+in-tree ancestor ``src/models/ldm.py`` (tests/golden/make_golden_sched.py), the DDIM step by the
+closed-form known answers of SURVEY.md section 4 (tests/test_oracle_misc.py).
 
 Call sites this follows: ``src/sample_trials.py:136-166`` (DDIM, v-prediction,
 scaled-linear), ``src/train_ldm.py:199-202`` + ``src/training/training.py:420-437``
