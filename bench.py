@@ -40,6 +40,21 @@ def _peaks():
     return dict(hbm=6650.0, tc_burst=1590.0, tc_sustained=1400.0, src="fallback")   # B200_PROFILING.md fallback
 
 
+def _ncu_conv_traffic(batch, math):
+    """dram__bytes_read.sum + dram__bytes_write.sum per conv_tc launch (average over the 54 tensor-pipe convs of one UNet
+    forward) from the committed ncu pass profiles/r01_ncu_forward_b1024.csv -- captured at B=1024, f16x3, so only then."""
+    path = os.path.join(ROOT, "profiles", "r01_ncu_forward_b1024.csv")
+    if batch != 1024 or math != "f16x3" or not os.path.exists(path):
+        return None
+    n, tot = 0, 0.0
+    for line in open(path):
+        f = line.strip().split(",")
+        if len(f) >= 9 and f[1].startswith("conv_tc_kernel"):
+            n += 1
+            tot += (float(f[-5]) + float(f[-4])) * 1e6
+    return tot / n if n else None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -238,7 +253,9 @@ def run_ours(args):
         peak_tc = peaks["tc_sustained"]
         ach = conv["flops"] / (conv["ms"] / 1e3) / 1e12 if conv["ms"] else 0.0
         roof = {"bound": "tensor", "kernel": "conv implicit-GEMM (" + args.math + ")", "achieved": ach, "peak": peak_tc,
-                "unit": "TFLOP/s", "frac": ach / peak_tc, "traffic": None, "peak_source": peaks["src"] + " bf16 sustained",
+                "unit": "TFLOP/s", "frac": ach / peak_tc, "traffic": _ncu_conv_traffic(pb, args.math),
+                "traffic_source": "profiles/r01_ncu_forward_b1024.csv (ncu dram bytes per conv_tc launch, B=1024)",
+                "algorithmic_bytes_per_launch": conv["bytes"] / max(conv["launches"], 1), "peak_source": peaks["src"] + " bf16 sustained",
                 "avg_launch_ms": conv["ms"] / max(conv["launches"], 1), "share_of_step": conv["ms"] / tot,
                 "algorithmic_flops_per_launch": conv["flops"] / max(conv["launches"], 1),
                 "profile_batch": pb,

@@ -62,7 +62,7 @@ class AutoencoderKL(EngineModule):
                 _lib.lib().eegldm_aekl_destroy(h)
             except Exception:
                 pass
-            self._h = None
+            object.__setattr__(self, "_h", None)   # nn.Module.__setattr__ may already be torn down at interpreter exit
 
     def _upload(self, state_dict) -> None:
         L = _lib.lib()

@@ -83,7 +83,7 @@ class UNetModel(EngineModule):
                 _lib.lib().eegldm_unet_destroy(h)
             except Exception:
                 pass
-            self._h = None
+            object.__setattr__(self, "_h", None)   # nn.Module.__setattr__ may already be torn down at interpreter exit
 
     def set_math(self, mode: str) -> "UNetModel":
         """``"fp32"`` (SIMT, exact fp32), ``"f16x3"`` (tcgen05, fp16 hi + scaled fp16 lo, 3 products, ~fp32-accurate),

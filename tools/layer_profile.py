@@ -13,6 +13,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=1024)
 ap.add_argument("--math", default="f16x3")
 ap.add_argument("--cluster", type=int, default=2)
+ap.add_argument("--warmup", type=int, default=2, help="untimed forwards before the profiled one (0 under ncu)")
 ap.add_argument("--pair", type=int, default=0)
 ap.add_argument("--bn256", type=int, default=1)
 ap.add_argument("--gnfuse", type=int, default=1)
@@ -26,7 +27,7 @@ m.load_state_dict(ou.make_unet_state_dict(cfg, 0))
 m = m.to(dev).eval()
 x = torch.randn(a.batch, 1, 768, device=dev)
 t = torch.tensor([500])
-for _ in range(2):
+for _ in range(a.warmup):
     m(x, timesteps=t)
 torch.cuda.synchronize()
 L = eegldm.lib()
