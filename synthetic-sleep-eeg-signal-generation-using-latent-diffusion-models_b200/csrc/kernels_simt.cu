@@ -581,6 +581,187 @@ __global__ void __launch_bounds__(256) attention_simt_kernel(const AttnParams p)
 }
 
 // ------------------------------------------------------------------------------------------------
+// Tiny-channel convolution (the 2-2-4 autoencoder of config_aekl_eeg_2_2_4_spec.yaml: 1, 2 or 4 channels everywhere).
+// One thread computes P = 4 consecutive output positions x all CO channels of one sample from (P-1)*S + TAPS input rows
+// held in registers (vector loads of CI floats per row); weights, bias and the optional 1x1 skip weights sit in shared
+// memory (broadcast reads).  Same fused contract as conv_simt_kernel: GroupNorm apply + SiLU prologue, nearest x2 upsample
+// folded into the row index, stride 1 | 2 with explicit left pad, + bias + identity residual | + 1x1 skip conv of the raw
+// block input (nin_shortcut).  HBM-bound: every input row is read once per 4 outputs, every output written once.
+template <int C> struct RowVec;
+template <> struct RowVec<1> { using T = float; };
+template <> struct RowVec<2> { using T = float2; };
+template <> struct RowVec<4> { using T = float4; };
+template <int C>
+__device__ __forceinline__ void load_row(const float* p, float (&v)[C]) {
+    const typename RowVec<C>::T r = *reinterpret_cast<const typename RowVec<C>::T*>(p);
+    const float* f = reinterpret_cast<const float*>(&r);
+#pragma unroll
+    for (int c = 0; c < C; ++c) v[c] = f[c];
+}
+template <int C>
+__device__ __forceinline__ void store_row(float* p, const float (&v)[C]) {
+    typename RowVec<C>::T r;
+    float* f = reinterpret_cast<float*>(&r);
+#pragma unroll
+    for (int c = 0; c < C; ++c) f[c] = v[c];
+    *reinterpret_cast<typename RowVec<C>::T*>(p) = r;
+}
+
+constexpr int TINY_P = 4;
+template <int CI, int CO, int TAPS, int S>
+__global__ void __launch_bounds__(256) conv_tiny_kernel(const ConvParams p) {
+    constexpr int NR = (TINY_P - 1) * S + TAPS;
+    __shared__ float ws[CI * TAPS * CO], bs[CO], w2[4 * CO];
+    const ConvSeg& s0 = p.seg[0];
+    for (int i = threadIdx.x; i < CI * TAPS * CO; i += blockDim.x) ws[i] = s0.w[i];
+    for (int i = threadIdx.x; i < CO; i += blockDim.x) bs[i] = p.bias ? p.bias[i] : 0.f;
+    const int C2 = p.nseg > 1 ? p.seg[1].C0 : 0;
+    for (int i = threadIdx.x; i < C2 * CO; i += blockDim.x) w2[i] = p.seg[1].w[i];
+    __syncthreads();
+    const int groups = (p.Tout + TINY_P - 1) / TINY_P;
+    const size_t total = (size_t)p.B * groups;
+    const bool ups = s0.resample == RS_NEAREST2;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int b = (int)(idx / groups), t0 = (int)(idx % groups) * TINY_P;
+        float a[CI], sh[CI];
+#pragma unroll
+        for (int c = 0; c < CI; ++c) {
+            a[c] = s0.scale ? s0.scale[(size_t)b * CI + c] : 1.f;
+            sh[c] = s0.scale ? s0.shift[(size_t)b * CI + c] : 0.f;
+        }
+        float x[NR][CI];
+        const int u0 = t0 * S - p.pad_left;
+        const float* src = s0.src0 + (size_t)b * s0.Tin * CI;
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            const int u = u0 + r;
+            if (u >= 0 && u < p.Tc) {
+                load_row<CI>(src + (size_t)(ups ? (u >> 1) : u) * CI, x[r]);
+#pragma unroll
+                for (int c = 0; c < CI; ++c) x[r][c] = act1(x[r][c], a[c], sh[c], s0.silu);
+            } else {
+#pragma unroll
+                for (int c = 0; c < CI; ++c) x[r][c] = 0.f;   // the conv's zero padding (applied after the activation)
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < TINY_P; ++j) {
+            const int t = t0 + j;
+            if (t >= p.Tout) break;
+            float acc[CO];
+#pragma unroll
+            for (int co = 0; co < CO; ++co) acc[co] = bs[co];
+#pragma unroll
+            for (int c = 0; c < CI; ++c)
+#pragma unroll
+                for (int k = 0; k < TAPS; ++k)
+#pragma unroll
+                    for (int co = 0; co < CO; ++co) acc[co] = fmaf(x[j * S + k][c], ws[(c * TAPS + k) * CO + co], acc[co]);
+            if (p.res) {
+                float r[CO];
+                load_row<CO>(p.res + ((size_t)b * p.res_Tin + t) * CO, r);
+#pragma unroll
+                for (int co = 0; co < CO; ++co) acc[co] += r[co];
+            }
+            if (C2) {
+                const float* x2 = p.seg[1].src0 + ((size_t)b * p.seg[1].Tin + t) * C2;
+                for (int c = 0; c < C2; ++c) {
+                    const float v = x2[c];
+#pragma unroll
+                    for (int co = 0; co < CO; ++co) acc[co] = fmaf(v, w2[c * CO + co], acc[co]);
+                }
+            }
+            store_row<CO>(p.out + ((size_t)b * p.Tout + t) * CO, acc);
+        }
+    }
+}
+
+template <int CI, int CO>
+cudaError_t launch_conv_tiny_t(const ConvParams& p, cudaStream_t st) {
+    const size_t total = (size_t)p.B * ((p.Tout + TINY_P - 1) / TINY_P);
+    const unsigned blocks = (unsigned)std::min<size_t>((total + 255) / 256, 148 * 16);
+    const int taps = p.seg[0].taps;
+    if (taps == 3 && p.stride == 1) conv_tiny_kernel<CI, CO, 3, 1><<<blocks, 256, 0, st>>>(p);
+    else if (taps == 3 && p.stride == 2) conv_tiny_kernel<CI, CO, 3, 2><<<blocks, 256, 0, st>>>(p);
+    else if (taps == 1 && p.stride == 1) conv_tiny_kernel<CI, CO, 1, 1><<<blocks, 256, 0, st>>>(p);
+    else return cudaErrorInvalidValue;
+    return cudaGetLastError();
+}
+bool conv_tiny_ok(const ConvParams& p) {
+    const ConvSeg& a = p.seg[0];
+    auto c124 = [](int c) { return c == 1 || c == 2 || c == 4; };
+    if (!c124(a.C0) || a.C1 || !c124(p.Cout) || p.temb || p.ddim_x) return false;
+    if (!(a.taps == 3 || (a.taps == 1 && p.stride == 1)) || (p.stride != 1 && p.stride != 2)) return false;
+    if (a.resample != RS_NONE && a.resample != RS_NEAREST2) return false;
+    if (p.res && (p.res_mode != RS_NONE || p.nseg > 1)) return false;
+    if (p.nseg > 1) {
+        const ConvSeg& q = p.seg[1];
+        if (q.taps != 1 || q.C1 || q.C0 > 4 || q.scale || q.silu || q.resample != RS_NONE || q.Tin != p.Tout) return false;
+    }
+    return true;
+}
+cudaError_t launch_conv_tiny(const ConvParams& p, cudaStream_t st) {
+    const int ci = p.seg[0].C0, co = p.Cout;
+#define EEGLDM_TINY(CI, CO) if (ci == CI && co == CO) return launch_conv_tiny_t<CI, CO>(p, st);
+    EEGLDM_TINY(1, 1) EEGLDM_TINY(1, 2) EEGLDM_TINY(1, 4) EEGLDM_TINY(2, 1) EEGLDM_TINY(2, 2) EEGLDM_TINY(2, 4)
+    EEGLDM_TINY(4, 1) EEGLDM_TINY(4, 2) EEGLDM_TINY(4, 4)
+#undef EEGLDM_TINY
+    return cudaErrorInvalidValue;
+}
+
+// GroupNorm statistics for tensors of at most 8 channels (single source): grid (nsplit, B), block 256.  Per-channel shifted
+// sums per thread, Chan combination through warp shuffles and shared memory, channels folded into groups by thread 0.
+__global__ void __launch_bounds__(256) gn_partial_tiny_kernel(const GnParams p) {
+    __shared__ Mom sm[8][8];
+    const int C = p.C0, b = blockIdx.y, split = blockIdx.x;
+    const int rps = (p.T + p.nsplit - 1) / p.nsplit;
+    const int t_lo = split * rps, t_hi = min(p.T, t_lo + rps);
+    const float* base = p.src0 + (size_t)b * p.T * C;
+    float K[8], s[8], ss[8];
+    float n = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) { K[c] = 0.f; s[c] = 0.f; ss[c] = 0.f; }
+    for (int t = t_lo + threadIdx.x; t < t_hi; t += blockDim.x) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            if (c < C) {
+                const float v = base[(size_t)t * C + c];
+                if (n == 0.f) K[c] = v;
+                const float d = v - K[c];
+                s[c] += d; ss[c] = fmaf(d, d, ss[c]);
+            }
+        }
+        n += 1.f;
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        if (c >= C) break;
+        Mom m;
+        m.n = n; m.mean = n > 0.f ? K[c] + s[c] / n : 0.f; m.m2 = n > 0.f ? fmaxf(ss[c] - s[c] * s[c] / n, 0.f) : 0.f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            Mom q;
+            q.n = __shfl_xor_sync(0xffffffffu, m.n, o); q.mean = __shfl_xor_sync(0xffffffffu, m.mean, o);
+            q.m2 = __shfl_xor_sync(0xffffffffu, m.m2, o);
+            m = mom_combine(m, q);
+        }
+        if (lane == 0) sm[c][warp] = m;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int cpg = C / p.G, nw = blockDim.x >> 5;
+        for (int g = 0; g < p.G; ++g) {
+            Mom r; r.n = 0.f; r.mean = 0.f; r.m2 = 0.f;
+            for (int c = g * cpg; c < (g + 1) * cpg; ++c)
+                for (int w = 0; w < nw; ++w) r = mom_combine(r, sm[c][w]);
+            float* o = p.partial + (((size_t)b * p.nsplit + split) * p.G + g) * 3;
+            o[0] = r.n; o[1] = r.mean; o[2] = r.m2;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // y[r][o] = bias[o] + sum_i act(x[r][i]) W[o][i]   -- one warp per output
 __global__ void linear_kernel(const float* __restrict__ x, const float* __restrict__ W,
                               const float* __restrict__ bias, float* __restrict__ y, int R, int I, int O,
@@ -677,6 +858,11 @@ cudaError_t launch_conv_simt(const ConvParams& p, cudaStream_t st) {
         g_launch_count += 1;
         return cudaGetLastError();
     }
+    if (conv_tiny_ok(p)) {
+        cudaError_t e = launch_conv_tiny(p, st);
+        g_launch_count += 1;
+        return e;
+    }
     const int gx = (p.Tout + BN - 1) / BN;
     if (p.Cout >= 96) {
         dim3 grid(gx, (p.Cout + 127) / 128, p.B);
@@ -693,7 +879,8 @@ cudaError_t launch_conv_simt(const ConvParams& p, cudaStream_t st) {
 }
 
 int groupnorm_nsplit(int C, int T, int G) {
-    (void)C; (void)G;
+    (void)G;
+    if (C <= 8) { int n = T / 768; return n < 1 ? 1 : n; }   // gn_partial_tiny_kernel: >= 3 rows per thread
     int n = T / 96;
     if (n < 1) n = 1;
     if (n > 32) n = 32;
@@ -705,7 +892,10 @@ cudaError_t launch_groupnorm(const GnParams& p, cudaStream_t st) {
     const int C = p.C0 + p.C1;
     const int cpg = C / p.G;
     const bool vec = (p.C0 % 4 == 0) && (p.C1 % 4 == 0) && (cpg % 4 == 0) && (C / 4 <= 256) && (p.G <= 32);
-    if (vec) {
+    if (C <= 8 && !p.src1) {
+        dim3 grid(p.nsplit, p.B);
+        gn_partial_tiny_kernel<<<grid, 256, 0, st>>>(p);
+    } else if (vec) {
         const int nx = C / 4;
         int ny = 256 / nx;
         if (ny < 1) ny = 1;
