@@ -5,6 +5,8 @@
 // (The cuFFT side of the spectral loss is in spectral.cu.)
 #include "kernels.cuh"
 
+#include <algorithm>
+
 namespace eegldm {
 namespace {
 
@@ -110,6 +112,140 @@ __global__ void __launch_bounds__(256) conv_bwd_weight_kernel(const float* __res
             for (int p = 0; p < np; ++p) acc += dys[p * Cout + co];
             atomicAdd(db + co, acc);
         }
+}
+
+// ---- tiny-channel (1 / 2 / 4) variants for the 2-2-4 autoencoder: rows are vector loads, weights live in shared memory,
+// ---- the weight gradient is reduced in registers -> warp shuffles -> shared memory -> ONE atomicAdd per weight per block.
+template <int C> struct RowVecT;
+template <> struct RowVecT<1> { using T = float; };
+template <> struct RowVecT<2> { using T = float2; };
+template <> struct RowVecT<4> { using T = float4; };
+template <int C>
+__device__ __forceinline__ void ld_row(const float* p, float (&v)[C]) {
+    const typename RowVecT<C>::T r = *reinterpret_cast<const typename RowVecT<C>::T*>(p);
+    const float* f = reinterpret_cast<const float*>(&r);
+#pragma unroll
+    for (int c = 0; c < C; ++c) v[c] = f[c];
+}
+template <int C>
+__device__ __forceinline__ void st_row(float* p, const float (&v)[C]) {
+    typename RowVecT<C>::T r;
+    float* f = reinterpret_cast<float*>(&r);
+#pragma unroll
+    for (int c = 0; c < C; ++c) f[c] = v[c];
+    *reinterpret_cast<typename RowVecT<C>::T*>(p) = r;
+}
+
+// one thread per (sample, input position): da[b][i][:] over all CI channels
+template <int CI, int CO, int TAPS>
+__global__ void __launch_bounds__(256) conv_bwd_data_tiny_kernel(const ConvGradParams p) {
+    __shared__ float ws[CI * TAPS * CO];
+    for (int i = threadIdx.x; i < CI * TAPS * CO; i += blockDim.x) ws[i] = p.w[i];
+    __syncthreads();
+    const size_t total = (size_t)p.B * p.Tin;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int i = (int)(idx % p.Tin);
+        const size_t b = idx / p.Tin;
+        float acc[CI];
+#pragma unroll
+        for (int c = 0; c < CI; ++c) acc[c] = 0.f;
+        const int n_uc = p.ups ? 2 : 1;
+        for (int j = 0; j < n_uc; ++j) {
+            const int uc = p.ups ? 2 * i + j : i;
+            if (uc >= p.Tc) continue;
+#pragma unroll
+            for (int k = 0; k < TAPS; ++k) {
+                const int num = uc + p.pad - k;
+                if (num < 0 || num % p.stride) continue;
+                const int t = num / p.stride;
+                if (t >= p.Tout) continue;
+                float d[CO];
+                ld_row<CO>(p.dy + (b * p.Tout + t) * CO, d);
+#pragma unroll
+                for (int c = 0; c < CI; ++c)
+#pragma unroll
+                    for (int co = 0; co < CO; ++co) acc[c] = fmaf(d[co], ws[(c * TAPS + k) * CO + co], acc[c]);
+            }
+        }
+        float* o = p.da + idx * CI;
+        if (p.accumulate) {
+            float old[CI];
+            ld_row<CI>(o, old);
+#pragma unroll
+            for (int c = 0; c < CI; ++c) acc[c] += old[c];
+        }
+        st_row<CI>(o, acc);
+    }
+}
+
+// grid-stride over (sample, output position); dw [(ci*TAPS + k)][CO] and db [CO] accumulated with atomics, one per block
+template <int CI, int CO, int TAPS>
+__global__ void __launch_bounds__(256) conv_bwd_weight_tiny_kernel(const ConvGradParams p) {
+    constexpr int NW = CI * TAPS * CO, NV = NW + CO;
+    __shared__ float red[8][NV];
+    float acc[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) acc[i] = 0.f;
+    const size_t total = (size_t)p.B * p.Tout;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int t = (int)(idx % p.Tout);
+        const size_t b = idx / p.Tout;
+        float d[CO];
+        ld_row<CO>(p.dy + idx * CO, d);
+#pragma unroll
+        for (int co = 0; co < CO; ++co) acc[NW + co] += d[co];
+#pragma unroll
+        for (int k = 0; k < TAPS; ++k) {
+            const int uc = t * p.stride + k - p.pad;
+            if (uc < 0 || uc >= p.Tc) continue;
+            float a[CI];
+            ld_row<CI>(p.a + (b * p.Tin + (p.ups ? (uc >> 1) : uc)) * CI, a);
+#pragma unroll
+            for (int c = 0; c < CI; ++c)
+#pragma unroll
+                for (int co = 0; co < CO; ++co) acc[(c * TAPS + k) * CO + co] = fmaf(d[co], a[c], acc[(c * TAPS + k) * CO + co]);
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        float v = acc[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) red[warp][i] = v;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < NV; i += blockDim.x) {
+        float v = 0.f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += red[w][i];
+        if (i < NW) atomicAdd(p.dw + i, v);
+        else if (p.db) atomicAdd(p.db + (i - NW), v);
+    }
+}
+
+template <int CI, int CO>
+cudaError_t launch_conv_grad_tiny_t(const ConvGradParams& p, bool weight, cudaStream_t st) {
+    const size_t total = (size_t)p.B * (weight ? p.Tout : p.Tin);
+    const unsigned blocks = (unsigned)std::min<size_t>((total + 255) / 256, weight ? 148 * 4 : 148 * 16);
+    if (p.taps == 3) {
+        if (weight) conv_bwd_weight_tiny_kernel<CI, CO, 3><<<blocks, 256, 0, st>>>(p);
+        else conv_bwd_data_tiny_kernel<CI, CO, 3><<<blocks, 256, 0, st>>>(p);
+    } else {
+        if (weight) conv_bwd_weight_tiny_kernel<CI, CO, 1><<<blocks, 256, 0, st>>>(p);
+        else conv_bwd_data_tiny_kernel<CI, CO, 1><<<blocks, 256, 0, st>>>(p);
+    }
+    return cudaGetLastError();
+}
+bool conv_grad_tiny_ok(const ConvGradParams& p) {
+    auto c124 = [](int c) { return c == 1 || c == 2 || c == 4; };
+    return c124(p.Cin) && c124(p.Cout) && (p.taps == 1 || p.taps == 3) && (p.stride == 1 || p.stride == 2);
+}
+cudaError_t launch_conv_grad_tiny(const ConvGradParams& p, bool weight, cudaStream_t st) {
+#define EEGLDM_TINY(CI, CO) if (p.Cin == CI && p.Cout == CO) return launch_conv_grad_tiny_t<CI, CO>(p, weight, st);
+    EEGLDM_TINY(1, 1) EEGLDM_TINY(1, 2) EEGLDM_TINY(1, 4) EEGLDM_TINY(2, 1) EEGLDM_TINY(2, 2) EEGLDM_TINY(2, 4)
+    EEGLDM_TINY(4, 1) EEGLDM_TINY(4, 2) EEGLDM_TINY(4, 4)
+#undef EEGLDM_TINY
+    return cudaErrorInvalidValue;
 }
 
 // GroupNorm(+SiLU) backward, pass 1: per (sample, group) means of g = dv*gamma and g*xhat; per-channel dgamma / dbeta.
@@ -253,6 +389,10 @@ cudaError_t launch_norm_act_fwd(const float* x, const float* scale, const float*
 cudaError_t launch_conv_bwd_data(const ConvGradParams& p, cudaStream_t st) {
     const size_t total = (size_t)p.B * p.Tin * p.Cin;
     if (!total) return cudaSuccess;
+    if (conv_grad_tiny_ok(p)) {
+        g_launch_count += 1;
+        return launch_conv_grad_tiny(p, false, st);
+    }
     conv_bwd_data_kernel<<<blocks_for(total), 256, 0, st>>>(p.dy, p.w, p.da, p.Cin, p.Cout, p.taps, p.stride, p.pad, p.ups, p.Tin, p.Tc,
                                                             p.Tout, p.accumulate, total);
     g_launch_count += 1;
@@ -261,6 +401,10 @@ cudaError_t launch_conv_bwd_data(const ConvGradParams& p, cudaStream_t st) {
 
 cudaError_t launch_conv_bwd_weight(const ConvGradParams& p, cudaStream_t st) {
     if (p.B <= 0 || p.Tout <= 0) return cudaSuccess;
+    if (conv_grad_tiny_ok(p)) {
+        g_launch_count += 1;
+        return launch_conv_grad_tiny(p, true, st);
+    }
     const int rows = (WG_P - 1) * p.stride + p.taps;
     const size_t smem = ((size_t)WG_P * p.Cout + (size_t)rows * p.Cin) * sizeof(float);
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
