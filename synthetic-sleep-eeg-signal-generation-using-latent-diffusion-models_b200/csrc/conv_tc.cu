@@ -160,9 +160,20 @@ __global__ void __launch_bounds__(SPLIT_THREADS) act_split_kernel(const ActSplit
 // drops below the tensor pipe's time.  Synchronisation: loads complete on each CTA's own "full" mbarriers; warp 5 of the
 // peer relays them to the leader's (count 2 = own expect_tx arrive + relay); the leader's tcgen05.commit multicasts the
 // "empty" / "accumulator full" arrivals to both CTAs; both CTAs' epilogue threads arrive on the leader's "accumulator empty".
-template <bool X3, int BN, int CL, bool PAIR>
-__global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const TcConvParams p) {
+//
+// DIRECT: no activation pre-pass.  Six producer warps (the act_split thread mapping: 192 threads x 3 sixteen-byte items per
+// k-step) read the fp32 source rows themselves, apply the GroupNorm affine / SiLU / nearest-x2, split to fp16 hi/lo and
+// write the stage image into the activation ring with st.shared (+ fence.proxy.async, 192 arrivals on the "full" barrier),
+// one k-step of global loads in flight in registers ahead of the stage being written.  The U tensors -- 8.5 B per element
+// of HBM traffic in act_split plus 4.5 B per element read here -- disappear; the conv reads 4 B per element instead.
+// Registers: launched at 384 threads (168 registers), then setmaxnreg moves registers from the producer / loader / MMA
+// warpgroups (136) to the epilogue warpgroup (232).
+template <bool X3, int BN, int CL, bool PAIR, bool DIRECT>
+__global__ void __launch_bounds__(DIRECT ? 384 : NUM_THREADS, 1) conv_tc_kernel(const TcConvParams p) {
     static_assert(!PAIR || CL == 2, "a CTA pair is a cluster of 2");
+    static_assert(!(PAIR && DIRECT), "the fused producer is implemented for single-CTA MMAs");
+    constexpr int NPROD = DIRECT ? 6 : 0;            // producer warps 4 .. 4+NPROD-1
+    constexpr int W_LOAD = 4 + NPROD, W_MMA = 5 + NPROD;
     constexpr int BNL = PAIR ? BN / 2 : BN;    // weight columns staged in THIS CTA's shared memory
     constexpr int B_HALF = BNL * BK * 2;       // hi (or lo) weight tile of one (tap, k-step): BNL x 32 x 2 B
     constexpr int B_STAGE = 2 * B_HALF;
@@ -191,7 +202,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const TcConvPar
     const bool leader = !PAIR || crank == 0;
     if (tid == 0) {
         const uint32_t nfull = PAIR && leader ? 2 : 1;   // pair leader: own expect_tx arrive + the peer's relay
-        for (int i = 0; i < NA; ++i) { mbar_init(barAfull + 8 * i, nfull); mbar_init(barAempty + 8 * i, 1); }
+        for (int i = 0; i < NA; ++i) { mbar_init(barAfull + 8 * i, DIRECT ? 32 * NPROD : nfull); mbar_init(barAempty + 8 * i, 1); }
         for (int i = 0; i < NB; ++i) { mbar_init(barBfull + 8 * i, nfull); mbar_init(barBempty + 8 * i, PAIR ? 1 : CL); }
         for (int i = 0; i < 2; ++i) { mbar_init(barAccFull + 8 * i, 1); mbar_init(barAccEmpty + 8 * i, PAIR ? 256 : 128); }
         fence_mbar_init();
@@ -200,7 +211,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const TcConvPar
     constexpr int NSETS = ACC_COLS * 2 <= 512 ? 2 : 1; // N=256 in f16x3 fills TMEM: no epilogue overlap (used for long K only)
     constexpr uint32_t TMEM_COLS = NSETS * ACC_COLS;
     constexpr uint32_t IDESC = make_idesc(X3 ? 0u : 1u, PAIR ? 2 * BM : BM, BN);
-    if (warp == 5) {
+    if (warp == W_MMA) {
         if (PAIR) tmem_alloc2(smem_u32(tmem_slot), TMEM_COLS);
         else tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
     }
@@ -209,6 +220,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const TcConvPar
     if (CL > 1) cluster_sync_all();   // peers' mbarriers are initialised before anything is multicast to them
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    if (DIRECT) {   // warpgroup 0 = epilogue, warpgroups 1-2 = producers + loader + MMA issuer
+        if (warp < 4) asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+        else asm volatile("setmaxnreg.dec.sync.aligned.u32 136;");
+    }
 
     if (warp < 4) {
         // ================================================================ epilogue
@@ -394,7 +409,87 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const TcConvPar
                 asm volatile("bar.sync 1, 128;" ::: "memory");   // the stats buffer is rewritten by the next tile
             }
         }
-    } else if (warp == 4) {
+    } else if (DIRECT && warp < W_LOAD) {
+        // ================================================================ activation producers (192 threads)
+        const int pt = tid - 128;
+        // act_split_kernel's mapping: item idx = pt + 192*j -> segment r = idx & 7, 8-channel chunk c = (idx >> 3) & 3, slot
+        // q = idx >> 5.  192 = 6 * 32, so the three items of a thread share r and c (one sample, one channel chunk -> ONE
+        // set of GroupNorm scale / shift values per k-step) and differ in the slot only: q = pt/32 + 6*j.
+        const int r = pt & 7, c = (pt >> 3) & 3, q0 = pt >> 5;
+        struct Pre { float4 x[3][2]; float4 a[2], s[2]; uint32_t ok; };
+        // raw rows + scale / shift of k-step ks of work item w; bit j of ok: item j is inside the batch and the sample
+        auto issue = [&](int w, int ks, Pre& P) {
+            const int m_tile = min((w / n_ntiles) * CL + crank, n_mtiles - 1);
+            const bool first = ks < nks0;
+            const TcSeg& sg = first ? p.seg[0] : p.seg[1];
+            const int kl = first ? ks : ks - nks0;
+            const int g = m_tile * 8 + r, b = g / spt, tb = (g % spt) * 16 - 1, cc = kl * BK + c * 8;
+            const float* src; int ch, Cs;
+            if (cc < sg.C0) { src = sg.src0; ch = cc; Cs = sg.C0; } else { src = sg.src1; ch = cc - sg.C0; Cs = sg.C1; }
+            P.ok = 0;
+            const bool segv = g < p.nsegs16;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const int t = tb + q0 + 6 * j;
+                P.x[j][0] = P.x[j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (segv && t >= 0 && t < p.Tout) {
+                    const float* row = src + ((size_t)b * sg.Tin + (sg.resample == RS_NEAREST2 ? (t >> 1) : t)) * Cs + ch;
+                    P.x[j][0] = ldg4(row); P.x[j][1] = ldg4(row + 4);
+                    P.ok |= 1u << j;
+                }
+            }
+            if (sg.scale && segv) {
+                const size_t o = (size_t)b * (sg.C0 + sg.C1) + cc;
+                P.a[0] = ldg4(sg.scale + o); P.a[1] = ldg4(sg.scale + o + 4);
+                P.s[0] = ldg4(sg.shift + o); P.s[1] = ldg4(sg.shift + o + 4);
+            } else {
+                P.a[0] = P.a[1] = make_float4(1.f, 1.f, 1.f, 1.f);
+                P.s[0] = P.s[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        int ia = 0, w = cid, ks = 0;
+        bool have = w < nwork;
+        Pre N;
+        if (have) issue(w, 0, N);
+        while (have) {
+            const Pre C = N;
+            const int kc_ = ks;
+            if (++ks == nks) { ks = 0; w += ncl; }
+            have = w < nwork;
+            if (have) issue(w, ks, N);                 // next k-step's loads are in flight while this one is transformed
+            const TcSeg& sg = kc_ < nks0 ? p.seg[0] : p.seg[1];
+            const bool aff = sg.scale != nullptr;
+            const int silu = sg.silu;
+            const float a[8] = {C.a[0].x, C.a[0].y, C.a[0].z, C.a[0].w, C.a[1].x, C.a[1].y, C.a[1].z, C.a[1].w};
+            const float sh[8] = {C.s[0].x, C.s[0].y, C.s[0].z, C.s[0].w, C.s[1].x, C.s[1].y, C.s[1].z, C.s[1].w};
+            const int sa = ia % NA;
+            mbar_wait(barAempty + 8 * sa, ((ia / NA) & 1) ^ 1);
+            uint8_t* img = smem + sa * A_STAGE;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                float v[8] = {C.x[j][0].x, C.x[j][0].y, C.x[j][0].z, C.x[j][0].w, C.x[j][1].x, C.x[j][1].y, C.x[j][1].z, C.x[j][1].w};
+                if ((C.ok >> j) & 1) {                 // padding / rows past the batch stay exactly zero
+                    if (aff) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) v[e] = act(v[e], a[e], sh[e], silu);
+                    } else if (silu) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) v[e] = silu_fast(v[e]);
+                    }
+                }
+                const uint32_t off = (uint32_t)(c * A_LBO + (q0 + 6 * j) * A_SBO + r * 16);
+                uint4 hi, lo;
+                if (X3) {
+                    split8_f16(v, hi, lo);
+                    *reinterpret_cast<uint4*>(img + A_TILE + off) = lo;
+                } else round8_bf16(v, hi);
+                *reinterpret_cast<uint4*>(img + off) = hi;
+            }
+            fence_proxy_async_smem();                  // generic-proxy stores -> visible to the tensor core's async proxy
+            mbar_arrive(barAfull + 8 * sa);
+            ++ia;
+        }
+    } else if (warp == W_LOAD) {
         // ================================================================ loader (whole warp runs the loop, one elected lane issues)
         {
             const uint32_t a_bytes = X3 ? A_STAGE : A_TILE, b_bytes = X3 ? B_STAGE : B_HALF;
@@ -407,15 +502,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const TcConvPar
                     const TcSeg& sg = first ? p.seg[0] : p.seg[1];
                     const int kl = first ? ks : ks - nks0;
                     const int sa = ia % NA;
-                    mbar_wait(barAempty + 8 * sa, ((ia / NA) & 1) ^ 1);
-                    if (elect_one()) {
-                        if (p.debug & 1) mbar_arrive(barAfull + 8 * sa);   // timing experiment: no operand traffic
-                        else {
-                            mbar_arrive_expect_tx(barAfull + 8 * sa, a_bytes);
-                            bulk_copy_g2s(sA + sa * A_STAGE, sg.U + ((size_t)m_tile * sg.nks + kl) * A_STAGE, a_bytes, barAfull + 8 * sa);
+                    if (!DIRECT) {   // DIRECT: the producer warps fill the activation ring
+                        mbar_wait(barAempty + 8 * sa, ((ia / NA) & 1) ^ 1);
+                        if (elect_one()) {
+                            if (p.debug & 1) mbar_arrive(barAfull + 8 * sa);   // timing experiment: no operand traffic
+                            else {
+                                mbar_arrive_expect_tx(barAfull + 8 * sa, a_bytes);
+                                bulk_copy_g2s(sA + sa * A_STAGE, sg.U + ((size_t)m_tile * sg.nks + kl) * A_STAGE, a_bytes, barAfull + 8 * sa);
+                            }
                         }
+                        __syncwarp();
                     }
-                    __syncwarp();
                     // weight image [k-step][tap][hi|lo][Cout/8][4 kc][8][8]: the BN columns of this tile are one contiguous slice
                     const size_t whalf = (size_t)p.Cout * (BK * 2);
                     const uint8_t* wsrc = sg.w + (size_t)kl * sg.taps * 2 * whalf + (size_t)n_tile * BN * (BK * 2);
@@ -529,7 +626,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_tc_kernel(const TcConvPar
     tc_fence_before();
     __syncthreads();
     if (CL > 1) cluster_sync_all();   // no CTA leaves while a peer may still multicast into its shared memory
-    if (warp == 5) {
+    if (warp == W_MMA) {
         if (PAIR) tmem_dealloc2(tmem, TMEM_COLS);
         else tmem_dealloc(tmem, TMEM_COLS);
     }
@@ -608,11 +705,11 @@ cudaError_t launch_act_split(const ActSplitParams& p, bool x3, cudaStream_t st) 
     return cudaGetLastError();
 }
 
-template <bool X3, int BN, int CL, bool PAIR>
+template <bool X3, int BN, int CL, bool PAIR, bool DIRECT = false>
 cudaError_t launch_conv_tc_t(const TcConvParams& p, int num_sms, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<X3, BN, CL, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(PAIR));
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<X3, BN, CL, PAIR, DIRECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(PAIR));
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
@@ -622,14 +719,14 @@ cudaError_t launch_conv_tc_t(const TcConvParams& p, int num_sms, cudaStream_t st
     if (nwork < nclusters) nclusters = nwork;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(nclusters * CL);   // persistent: one CTA per SM
-    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.blockDim = dim3(DIRECT ? 384 : NUM_THREADS);
     cfg.dynamicSmemBytes = smem_bytes(PAIR);
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, conv_tc_kernel<X3, BN, CL, PAIR>, p);
+    return cudaLaunchKernelEx(&cfg, conv_tc_kernel<X3, BN, CL, PAIR, DIRECT>, p);
 }
 
 cudaError_t launch_conv_tc(const TcConvParams& p, bool x3, cudaStream_t st) {
@@ -643,7 +740,8 @@ cudaError_t launch_conv_tc(const TcConvParams& p, bool x3, cudaStream_t st) {
     if (p.bn != 128 && p.bn != 256) return cudaErrorInvalidValue;
     cudaError_t e;
 #define EEGLDM_TC(X3, BN)                                                                         \
-    (g_conv_tc_pair ? launch_conv_tc_t<X3, BN, 2, true>(p, num_sms, st)                             \
+    (p.direct ? launch_conv_tc_t<X3, BN, 2, false, true>(p, num_sms, st)                            \
+     : g_conv_tc_pair ? launch_conv_tc_t<X3, BN, 2, true>(p, num_sms, st)                           \
      : g_conv_tc_cluster == 4 ? launch_conv_tc_t<X3, BN, 4, false>(p, num_sms, st)                 \
      : g_conv_tc_cluster == 2 ? launch_conv_tc_t<X3, BN, 2, false>(p, num_sms, st) : launch_conv_tc_t<X3, BN, 1, false>(p, num_sms, st))
     if (p.bn == 256) e = x3 ? EEGLDM_TC(true, 256) : EEGLDM_TC(false, 256);

@@ -343,6 +343,7 @@ struct eegldm_unet {
 namespace {
 
 bool g_conv_qkv_fused = false; // the qkv conv writes attention operand images directly (f16x3; eegldm_set_conv_tuning): measured no faster
+bool g_conv_direct = true;     // tensor-pipe convs produce their activation operands in-kernel (no act_split pre-pass)
 bool g_conv_gn_fused = true;   // tensor-pipe convs emit the GroupNorm statistics of their output (eegldm_set_conv_tuning)
 bool g_graphs_enabled = true;
 // Denoise-step graph of eegldm_ddim_sample: 2 = the batch is planned as two independent halves captured on two streams
@@ -642,10 +643,21 @@ void plan_conv(Builder& bd, ConvParams p, const uint8_t* tw0 = nullptr, const ui
         for (int s = 0; s < p.nseg; ++s) stages += (p.seg[s].C0 + p.seg[s].C1) / TC_BK * p.seg[s].taps;
         q.bn = conv_tc_bn(p.Cout, stages);   // tile width is a launch-time choice: the weight image is width-agnostic
         std::shared_ptr<Buf> ubuf[2];
+        // fused producer: the conv kernel reads the fp32 sources itself (no act_split pass, no U tensors); AvgPool inputs
+        // (the two down-sampling ResBlocks) keep the pre-pass
+        // and 1x1 convs with many N tiles (qkv: 6) would redo the transform per N tile with only one tap of MMAs to hide it
+        bool direct = g_conv_direct && !qkv && !(p.seg[0].taps == 1 && p.Cout / q.bn > 2);
+        for (int s = 0; direct && s < p.nseg; ++s) direct = p.seg[s].resample == RS_NONE || p.seg[s].resample == RS_NEAREST2;
+        q.direct = direct ? 1 : 0;
         for (int s = 0; s < p.nseg; ++s) {
             // pre-pass: GroupNorm apply + SiLU + resample + 16-bit split -> tile images (one pass per conv input)
             const ConvSeg& a = p.seg[s];
             const int cin = a.C0 + a.C1;
+            if (direct) {
+                q.seg[s] = TcSeg{nullptr, s == 0 ? tw0 : tw1, a.taps, cin / TC_BK, a.src0, a.src1, a.C0, a.C1, a.scale, a.shift, a.silu,
+                                 a.resample, a.Tin};
+                continue;
+            }
             const size_t ub = act_split_bytes(q.nsegs16, cin);
             if (s == 1 && share && share->raw) {   // raw twin already written by conv1's pre-pass
                 q.seg[s] = TcSeg{reinterpret_cast<const uint8_t*>(bd.ptr(share->raw)), tw1, a.taps, cin / TC_BK};
@@ -1292,6 +1304,7 @@ int eegldm_set_conv_tuning(int pair, int bn256_min_stages, int fuse_epilogues) {
     if (pair != 0 && pair != 1) return fail(EEGLDM_ERR_INVALID, "pair must be 0 or 1");
     g_conv_gn_fused = (fuse_epilogues & 1) != 0;
     g_conv_qkv_fused = (fuse_epilogues & 2) != 0;
+    g_conv_direct = (fuse_epilogues & 4) != 0;
     if (bn256_min_stages < 1) return fail(EEGLDM_ERR_INVALID, "bn256_min_stages must be >= 1");
     g_conv_tc_pair = pair;
     g_conv_tc_bn256_stages = bn256_min_stages;
@@ -1707,10 +1720,17 @@ int eegldm_test_conv(const float* x_dev, const float* scale_dev, const float* sh
         TcConvParams q{};
         q.nseg = 1; q.Cout = Cout; q.Tout = Tc; q.nsegs16 = (int)((long long)B * Tc / 16);
         q.bn = conv_tc_bn(Cout, Cin / TC_BK * k);
-        CU(cudaMalloc((void**)&U, act_split_bytes(q.nsegs16, Cin)));
-        ActSplitParams sp{x_dev, nullptr, Cin, 0, scale_dev, shift_dev, silu, resample, Tin, Tc, q.nsegs16, Cin / TC_BK, U, nullptr};
-        ce = launch_act_split(sp, x3, st);
-        q.seg[0] = TcSeg{U, reinterpret_cast<const uint8_t*>(wp.at(o_t)), k, Cin / TC_BK};
+        if (g_conv_direct && (resample == RS_NONE || resample == RS_NEAREST2)) {   // fused producer: no pre-pass
+            q.direct = 1;
+            q.seg[0] = TcSeg{nullptr, reinterpret_cast<const uint8_t*>(wp.at(o_t)), k, Cin / TC_BK, x_dev, nullptr, Cin, 0, scale_dev, shift_dev,
+                             silu, resample, Tin};
+            ce = cudaSuccess;
+        } else {
+            CU(cudaMalloc((void**)&U, act_split_bytes(q.nsegs16, Cin)));
+            ActSplitParams sp{x_dev, nullptr, Cin, 0, scale_dev, shift_dev, silu, resample, Tin, Tc, q.nsegs16, Cin / TC_BK, U, nullptr};
+            ce = launch_act_split(sp, x3, st);
+            q.seg[0] = TcSeg{U, reinterpret_cast<const uint8_t*>(wp.at(o_t)), k, Cin / TC_BK};
+        }
         q.bias = p.bias; q.res = res_dev; q.res_mode = RS_NONE; q.res_Tin = Tc; q.out = out_dev;
         if (ce == cudaSuccess) ce = launch_conv_tc(q, x3, st);
     } else ce = launch_conv_simt(p, st);

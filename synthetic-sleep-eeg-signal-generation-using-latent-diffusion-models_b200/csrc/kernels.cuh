@@ -86,9 +86,12 @@ struct ActSplitParams {
 size_t act_split_bytes(int nsegs16, int Cin);
 cudaError_t launch_act_split(const ActSplitParams& p, bool x3, cudaStream_t st);
 struct TcSeg {
-    const uint8_t* U;   // activation tile images written by act_split
+    const uint8_t* U;   // pre-pass form: activation tile images written by act_split
     const uint8_t* w;   // packed by pack_conv_tc: [k-step][tap][hi|lo][Cout/8][4][8][8] 16-bit (tile-width agnostic)
     int taps, nks;      // nks = Cin/TC_BK
+    // fused-producer form (TcConvParams.direct): the conv reads the fp32 source itself (resample: RS_NONE | RS_NEAREST2)
+    const float* src0; const float* src1; int C0, C1;
+    const float* scale; const float* shift; int silu, resample, Tin;
 };
 struct TcConvParams {
     TcSeg seg[2];
@@ -103,6 +106,7 @@ struct TcConvParams {
     int qkv_H, qkv_ch;  //   q/k/v operand images of attn_tc.cu (layout of launch_qkv_split) for qkv_H heads of qkv_ch channels; f16x3 only
     float* gn_partial;  // optional: GroupNorm statistics of `out`, one (count, mean, M2) record per (sample, 16-position segment, group):
     int gn_cpg;         //   [B][Tout/16][Cout/gn_cpg][3]; gn_cpg = channels per group in {4, 8, 16, 32} (conv_tc_gn_ok)
+    int direct;         // 1: activation operands produced inside the conv kernel from TcSeg.src0/src1 (no act_split pre-pass)
     int debug;          // timing experiments only (eegldm_bench_conv): 1 = no operand copies, 2 = no MMAs; results are garbage
 };
 bool conv_tc_eligible(int Cin0, int Cin1, int Cout, int Tout, int taps, int stride);
