@@ -167,7 +167,10 @@ __global__ void __launch_bounds__(SPLIT_THREADS) act_split_kernel(const ActSplit
 // one k-step of global loads in flight in registers ahead of the stage being written.  The U tensors -- 8.5 B per element
 // of HBM traffic in act_split plus 4.5 B per element read here -- disappear; the conv reads 4 B per element instead.
 // Registers: launched at 384 threads (168 registers), then setmaxnreg moves registers from the producer / loader / MMA
-// warpgroups (136) to the epilogue warpgroup (232).
+// warpgroups (136) to the epilogue warpgroup (232): 128*232 + 256*136 = 384*168 exactly -- the CTA's register pool is fixed at
+// launch, and a split that needs more makes setmaxnreg.inc wait forever.  The producer is bounded by the XU pipe (ex2 + rcp
+// of SiLU, fp16 pack / unpack: ~1000 cycles per k-step), which hides under a 3-tap N=256 k-step (2304 tensor cycles) but
+// not under 1-tap or N=128 k-steps; a two-k-step prefetch distance measured no different from one.
 template <bool X3, int BN, int CL, bool PAIR, bool DIRECT>
 __global__ void __launch_bounds__(DIRECT ? 384 : NUM_THREADS, 1) conv_tc_kernel(const TcConvParams p) {
     static_assert(!PAIR || CL == 2, "a CTA pair is a cluster of 2");
