@@ -251,11 +251,15 @@ __global__ void __launch_bounds__(256) conv_narrow_in_kernel(const float* __rest
     for (int i = threadIdx.x; i < Cin * 3 * Cout; i += blockDim.x) ws[i] = w[i];
     for (int i = threadIdx.x; i < Cout; i += blockDim.x) ws[Cin * 3 * Cout + i] = bias ? bias[i] : 0.f;
     __syncthreads();
+    // thread = fixed group of 4 output channels, positions strided over the grid (no 64-bit divisions in the loop);
+    // requires (Cout/4) | blockDim.x, checked by the launcher
     const int q = Cout >> 2;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
-        const int co = (int)(i % q) * 4;
-        const size_t bt = i / q;
-        const int t = (int)(bt % T);
+    const int co = (int)(threadIdx.x % q) * 4;
+    const unsigned ppb = blockDim.x / q;                       // positions per block per iteration
+    const unsigned npos = (unsigned)(total4 / q);
+    for (unsigned pos = blockIdx.x * ppb + threadIdx.x / q; pos < npos; pos += gridDim.x * ppb) {
+        const size_t bt = pos;
+        const int t = (int)(pos % (unsigned)T);
         float4 acc = *reinterpret_cast<const float4*>(ws + Cin * 3 * Cout + co);
         for (int k = 0; k < 3; ++k) {
             const int u = t + k - 1;
@@ -292,8 +296,35 @@ __global__ void __launch_bounds__(256) conv_narrow_out_kernel(const ConvParams p
 #pragma unroll
         for (int c = 0; c < CO; ++c) acc[j][c] = 0.f;
     const float* hb = sg.src0 + (size_t)b * T * Cin;
+    // Cin == 128 (the UNet head): this lane's 4 channels never change -> affine and the 12*CO weights live in registers
+    const bool hoist = Cin == 128;
+    float4 ha = make_float4(1.f, 1.f, 1.f, 1.f), hs = make_float4(0.f, 0.f, 0.f, 0.f);
+    float hw[4][3][CO];
+    if (hoist) {
+        if (sg.scale) { ha = ld4(sg.scale + (size_t)b * Cin + lane * 4); hs = ld4(sg.shift + (size_t)b * Cin + lane * 4); }
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+#pragma unroll
+                for (int c = 0; c < CO; ++c) hw[e][k][c] = c < p.Cout ? __ldg(sg.w + (size_t)((lane * 4 + e) * 3 + k) * p.Cout + c) : 0.f;
+    }
     for (int r = t0 - 1; r <= t1; ++r) {   // input rows feeding outputs t0..t1-1
         if (r >= 0 && r < T) {
+            if (hoist) {
+                const float4 hv = ld4(hb + (size_t)r * Cin + lane * 4);
+                float v[4] = {hv.x, hv.y, hv.z, hv.w};
+                if (sg.scale) {
+                    v[0] = act1(v[0], ha.x, hs.x, sg.silu); v[1] = act1(v[1], ha.y, hs.y, sg.silu);
+                    v[2] = act1(v[2], ha.z, hs.z, sg.silu); v[3] = act1(v[3], ha.w, hs.w, sg.silu);
+                }
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+#pragma unroll
+                    for (int k = 0; k < 3; ++k)
+#pragma unroll
+                        for (int c = 0; c < CO; ++c) acc[2 - k][c] = fmaf(v[e], hw[e][k][c], acc[2 - k][c]);
+            } else
             for (int c0 = lane * 4; c0 < Cin; c0 += 128) {
                 const float4 hv = ld4(hb + (size_t)r * Cin + c0);
                 float v[4] = {hv.x, hv.y, hv.z, hv.w};
@@ -844,7 +875,8 @@ cudaError_t launch_conv_simt(const ConvParams& p, cudaStream_t st) {
     const ConvSeg& s0 = p.seg[0];
     const bool plain = p.nseg == 1 && s0.taps == 3 && p.stride == 1 && p.pad_left == 1 && !s0.src1 && s0.resample == RS_NONE &&
                        p.Tc == p.Tout && !p.temb && !p.res;
-    if (plain && s0.C0 <= 4 && !s0.scale && !p.ddim_x && (p.Cout & 3) == 0 && p.Cout >= 32 && (size_t)(s0.C0 * 3 + 1) * p.Cout * sizeof(float) <= 40 * 1024) {
+    if (plain && s0.C0 <= 4 && !s0.scale && !p.ddim_x && (p.Cout & 3) == 0 && p.Cout >= 32 && 256 % (p.Cout / 4) == 0 &&
+        (size_t)p.B * p.Tout < (1u << 31) && (size_t)(s0.C0 * 3 + 1) * p.Cout * sizeof(float) <= 40 * 1024) {
         const size_t total4 = (size_t)p.B * p.Tout * (p.Cout / 4);
         const size_t smem = ((size_t)s0.C0 * 3 * p.Cout + p.Cout) * sizeof(float);
         const unsigned blocks = (unsigned)std::min<size_t>((total4 + 255) / 256, 148 * 16);
@@ -854,7 +886,10 @@ cudaError_t launch_conv_simt(const ConvParams& p, cudaStream_t st) {
     }
     if (plain && p.Cout <= 4 && s0.C0 % 128 == 0) {
         const long long warps = (long long)p.B * ((p.Tout + NO_STRIP - 1) / NO_STRIP);
-        conv_narrow_out_kernel<4><<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(p);
+        const unsigned nb = (unsigned)((warps * 32 + 255) / 256);
+        if (p.Cout == 1) conv_narrow_out_kernel<1><<<nb, 256, 0, st>>>(p);
+        else if (p.Cout == 2) conv_narrow_out_kernel<2><<<nb, 256, 0, st>>>(p);
+        else conv_narrow_out_kernel<4><<<nb, 256, 0, st>>>(p);
         g_launch_count += 1;
         return cudaGetLastError();
     }

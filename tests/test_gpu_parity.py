@@ -202,6 +202,24 @@ def test_ddim_z3_and_graph_vs_eager(built_lib, cuda_device):
 
 
 @pytest.mark.parametrize("math", MATH)
+def test_raw_signal_dm_variant(built_lib, cuda_device, math):
+    """the raw-signal diffusion model (config_dm.yaml: the same UNet on [B,1,3072], self-attention at T = 768)
+    sampled as sample_trials_ddpm.py:83-102 does -- DDIM steps on the signal itself, no autoencoder, crop [36:-36].
+    T = 768 exceeds the tcgen05 attention's 256-key tile, so attention takes the fp32 SIMT kernel; convs take the math mode."""
+    import eegldm
+    ucfg = ou.full_cfg()
+    usd = ou.make_unet_state_dict(ucfg, 0)
+    unet = _unet(ucfg, usd, cuda_device, math)
+    noise = torch.randn(2, 1, 3072, generator=torch.Generator().manual_seed(2))
+    ref = osamp.ddim_sample(ucfg, usd, noise, 3)[:, :, 36:-36]
+    sched = eegldm.DDIMScheduler(**SAMPLER_DEFAULTS)
+    sched.set_timesteps(3)
+    y = eegldm.ddim_sample(unet, sched, noise.to(cuda_device), 3, None)[:, :, 36:-36]
+    assert y.shape == (2, 1, 3000)
+    torch.testing.assert_close(y.cpu(), ref, rtol=RTOL, atol=ATOL)
+
+
+@pytest.mark.parametrize("math", MATH)
 def test_full_size_properties(built_lib, cuda_device, math):
     """Size-independent properties at bench batch sizes (the oracle is too slow here):
     windows are independent, so any batch split gives bit-identical rows; results are deterministic."""
