@@ -170,7 +170,9 @@ __global__ void __launch_bounds__(SPLIT_THREADS) act_split_kernel(const ActSplit
 // warpgroups (136) to the epilogue warpgroup (232): 128*232 + 256*136 = 384*168 exactly -- the CTA's register pool is fixed at
 // launch, and a split that needs more makes setmaxnreg.inc wait forever.  The producer is bounded by the XU pipe (ex2 + rcp
 // of SiLU, fp16 pack / unpack: ~1000 cycles per k-step), which hides under a 3-tap N=256 k-step (2304 tensor cycles) but
-// not under 1-tap or N=128 k-steps; a two-k-step prefetch distance measured no different from one.
+// not under 1-tap or N=128 k-steps; a two-k-step prefetch distance measured no different from one, and nine producer warps
+// with two items each (512 threads, 232 / 88 registers) measured 6 % slower than six with three.  tools/producer_bench.py
+// (profiles/r01_producer_bench.txt) switches parts of the producer off: no single part dominates.
 template <bool X3, int BN, int CL, bool PAIR, bool DIRECT>
 __global__ void __launch_bounds__(DIRECT ? 384 : NUM_THREADS, 1) conv_tc_kernel(const TcConvParams p) {
     static_assert(!PAIR || CL == 2, "a CTA pair is a cluster of 2");
@@ -437,7 +439,7 @@ __global__ void __launch_bounds__(DIRECT ? 384 : NUM_THREADS, 1) conv_tc_kernel(
                 P.x[j][0] = P.x[j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (segv && t >= 0 && t < p.Tout) {
                     const float* row = src + ((size_t)b * sg.Tin + (sg.resample == RS_NEAREST2 ? (t >> 1) : t)) * Cs + ch;
-                    P.x[j][0] = ldg4(row); P.x[j][1] = ldg4(row + 4);
+                    if (!(p.debug & 8)) { P.x[j][0] = ldg4(row); P.x[j][1] = ldg4(row + 4); }   // 8: timing experiment, no row loads
                     P.ok |= 1u << j;
                 }
             }
@@ -471,7 +473,7 @@ __global__ void __launch_bounds__(DIRECT ? 384 : NUM_THREADS, 1) conv_tc_kernel(
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
                 float v[8] = {C.x[j][0].x, C.x[j][0].y, C.x[j][0].z, C.x[j][0].w, C.x[j][1].x, C.x[j][1].y, C.x[j][1].z, C.x[j][1].w};
-                if ((C.ok >> j) & 1) {                 // padding / rows past the batch stay exactly zero
+                if (((C.ok >> j) & 1) && !(p.debug & 16)) {   // padding / rows past the batch stay exactly zero (16: no transform)
                     if (aff) {
 #pragma unroll
                         for (int e = 0; e < 8; ++e) v[e] = act(v[e], a[e], sh[e], silu);
@@ -482,11 +484,16 @@ __global__ void __launch_bounds__(DIRECT ? 384 : NUM_THREADS, 1) conv_tc_kernel(
                 }
                 const uint32_t off = (uint32_t)(c * A_LBO + (q0 + 6 * j) * A_SBO + r * 16);
                 uint4 hi, lo;
-                if (X3) {
+                if (p.debug & 32) {                    // 32: timing experiment, no split
+                    hi = make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
+                    lo = make_uint4(__float_as_uint(v[4]), __float_as_uint(v[5]), __float_as_uint(v[6]), __float_as_uint(v[7]));
+                    if (X3 && !(p.debug & 64)) *reinterpret_cast<uint4*>(img + A_TILE + off) = lo;
+                } else if (X3) {
                     split8_f16(v, hi, lo);
-                    *reinterpret_cast<uint4*>(img + A_TILE + off) = lo;
+                    if (!(p.debug & 64)) *reinterpret_cast<uint4*>(img + A_TILE + off) = lo;
                 } else round8_bf16(v, hi);
-                *reinterpret_cast<uint4*>(img + off) = hi;
+                if (!(p.debug & 64)) *reinterpret_cast<uint4*>(img + off) = hi;   // 64: timing experiment, no shared-memory stores
+                else if (hi.x == 0x12345678u && lo.y == 0x9abcdef0u) *reinterpret_cast<uint4*>(img + off) = hi;   // keep the math alive
             }
             fence_proxy_async_smem();                  // generic-proxy stores -> visible to the tensor core's async proxy
             mbar_arrive(barAfull + 8 * sa);

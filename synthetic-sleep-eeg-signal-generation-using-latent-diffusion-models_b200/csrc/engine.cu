@@ -1862,6 +1862,14 @@ int eegldm_bench_conv(int B, int T, int Cin, int Cout, int k, int with_res, int 
         ce = launch_act_split(sp, x3, st);
     }
     q.seg[0] = TcSeg{U, reinterpret_cast<const uint8_t*>(wp.at(o_t)), k, Cin / TC_BK};
+    float* ss = nullptr;
+    if (g_conv_direct) {   // fused producer with a GroupNorm affine + SiLU prologue (the ResBlock conv1 / conv2 shape)
+        if (ce == cudaSuccess) ce = cudaMalloc((void**)&ss, (size_t)B * Cin * 2 * 4);
+        if (ce == cudaSuccess) { bench_fill_kernel<<<64, 256, 0, st>>>(ss, (size_t)B * Cin * 2, 3u); ce = cudaGetLastError(); }
+        q.direct = 1;
+        q.seg[0] = TcSeg{nullptr, reinterpret_cast<const uint8_t*>(wp.at(o_t)), k, Cin / TC_BK, x, nullptr, Cin, 0,
+                         (debug & 128) ? nullptr : ss, (debug & 128) ? nullptr : ss + (size_t)B * Cin, (debug & 128) ? 0 : 1, RS_NONE, T};
+    }
     q.res = res; q.res_mode = RS_NONE; q.res_Tin = T; q.out = out; q.debug = debug;
     if (ce == cudaSuccess) ce = launch_conv_tc(q, x3, st);   // warm-up
     if (ce == cudaSuccess) ce = cudaEventCreate(&e0);
@@ -1875,7 +1883,7 @@ int eegldm_bench_conv(int B, int T, int Cin, int Cout, int k, int with_res, int 
     *ms_out = ms / reps;
     if (e0) cudaEventDestroy(e0);
     if (e1) cudaEventDestroy(e1);
-    cudaFree(x); cudaFree(out); cudaFree(res); cudaFree(U);
+    cudaFree(x); cudaFree(out); cudaFree(res); cudaFree(U); cudaFree(ss);
     if (ce != cudaSuccess) return cuda_fail(ce, "conv bench");
     return EEGLDM_OK;
 }
