@@ -63,10 +63,11 @@ int eegldm_set_conv_cluster(int ctas);
 /* Shape selection of the tcgen05 conv kernel.  pair = 1: the two CTAs of a cluster issue one M=256 cta_group::2 MMA over
  * both (each stages half of the weight columns); pair = 0 (default, measured faster): single-CTA MMAs with the multicast
  * cluster of eegldm_set_conv_cluster.  bn256_min_stages (default 1): tiles are 256 output channels wide when Cout % 256 == 0
- * and a tile's mainloop has at least this many weight stages (else 128).  fuse_epilogues (bit mask, default 5):
+ * and a tile's mainloop has at least this many weight stages (else 128).  fuse_epilogues (bit mask, default 13):
  * bit 0 -- a conv whose output feeds a GroupNorm writes that GroupNorm's statistics from its epilogue (no separate pass);
  * bit 2 -- the conv kernel's producer warps read the fp32 input and build the fp16 hi/lo operand tiles in shared memory
  *          themselves (GroupNorm apply + SiLU + nearest-x2 + split), replacing the act_split pre-pass and its U tensors;
+ * bit 3 -- the tcgen05 attention kernel writes its result as proj_out's operand image (no fp32 attention output, no pre-pass);
  * bit 1 -- an AttentionBlock's qkv conv writes the attention kernel's fp16 hi/lo operand images instead of fp32 (f16x3; measured no faster than the separate split pass).
  * Call before creating models: plans cache the choices. */
 int eegldm_set_conv_tuning(int pair, int bn256_min_stages, int fuse_epilogues);

@@ -165,7 +165,26 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_tc_kernel(const AttnTcPar
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(fmaf(__uint_as_float(c2[i]), 1.0f / LO_SCALE, __uint_as_float(v[i])));
                 }
-                if (rowv) {
+                if (rowv && p.out_u) {
+                    // proj_out's operand image (conv_tc.cu U layout, 1x1 conv: halo slots are never read): this row is slot
+                    // t%16 + 1 of 16-position segment b*T/16 + t/16; 8 channels = one 16-byte item per hi / lo half
+                    const int g16 = b * (T >> 4) + (t >> 4);
+                    uint8_t* ub = p.out_u + (size_t)(g16 >> 3) * ((size_t)p.H * ch / 32) * (2 * TC_U_HALF_BYTES) +
+                                  ((t & 15) + 1) * 128 + (g16 & 7) * 16;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        float e[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) e[i] = __uint_as_float(v[8 * q + i]) * inv;
+                        uint4 hi, lo;
+                        if (X3) split8_f16(e, hi, lo);
+                        else round8_bf16(e, hi);
+                        const int cc = h * ch + c * 128 + cb + 8 * q;      // channel of the block output
+                        uint8_t* dst = ub + (size_t)(cc >> 5) * (2 * TC_U_HALF_BYTES) + ((cc >> 3) & 3) * (TC_U_HALF_BYTES / 4);
+                        *reinterpret_cast<uint4*>(dst) = hi;
+                        if (X3) *reinterpret_cast<uint4*>(dst + TC_U_HALF_BYTES) = lo;
+                    }
+                } else if (rowv) {
 #pragma unroll
                     for (int q = 0; q < 8; ++q)
                         *reinterpret_cast<float4*>(orow + c * 128 + cb + 4 * q) =

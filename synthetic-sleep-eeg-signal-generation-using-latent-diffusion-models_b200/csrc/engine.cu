@@ -343,6 +343,7 @@ struct eegldm_unet {
 namespace {
 
 bool g_conv_qkv_fused = false; // the qkv conv writes attention operand images directly (f16x3; eegldm_set_conv_tuning): measured no faster
+bool g_attn_u_fused = true;    // the tcgen05 attention writes proj_out's operand image instead of fp32 (eegldm_set_conv_tuning bit 3)
 bool g_conv_direct = true;     // tensor-pipe convs produce their activation operands in-kernel (no act_split pre-pass)
 bool g_conv_gn_fused = true;   // tensor-pipe convs emit the GroupNorm statistics of their output (eegldm_set_conv_tuning)
 bool g_graphs_enabled = true;
@@ -619,8 +620,9 @@ struct TcShare {
 // epilogue also emits the statistics (attached to *out_act; plan_gn then skips its pass over the tensor).
 // qkv: the output is written as attention operand images instead of fp32 (tensor-pipe f16x3 path only; the caller checks).
 struct QkvOut { uint8_t* dst; int H, ch; };
+// premade_u0: segment 0's operand image already exists (written by the attention kernel's epilogue): no pre-pass, no producer.
 void plan_conv(Builder& bd, ConvParams p, const uint8_t* tw0 = nullptr, const uint8_t* tw1 = nullptr, TcShare* share = nullptr,
-               Act* out_act = nullptr, int gn_G = 0, const QkvOut* qkv = nullptr) {
+               Act* out_act = nullptr, int gn_G = 0, const QkvOut* qkv = nullptr, const uint8_t* premade_u0 = nullptr) {
     p.B = bd.B;
     double flops = 0, bytes = 4.0 * p.B * (double)p.Tout * p.Cout;   // output write
     for (int s = 0; s < p.nseg; ++s) {
@@ -646,7 +648,7 @@ void plan_conv(Builder& bd, ConvParams p, const uint8_t* tw0 = nullptr, const ui
         // fused producer: the conv kernel reads the fp32 sources itself (no act_split pass, no U tensors); AvgPool inputs
         // (the two down-sampling ResBlocks) keep the pre-pass
         // and 1x1 convs with many N tiles (qkv: 6) would redo the transform per N tile with only one tap of MMAs to hide it
-        bool direct = g_conv_direct && !qkv && !(p.seg[0].taps == 1 && p.Cout / q.bn > 2);
+        bool direct = g_conv_direct && !qkv && !premade_u0 && !(p.seg[0].taps == 1 && p.Cout / q.bn > 2);
         for (int s = 0; direct && s < p.nseg; ++s) direct = p.seg[s].resample == RS_NONE || p.seg[s].resample == RS_NEAREST2;
         q.direct = direct ? 1 : 0;
         for (int s = 0; s < p.nseg; ++s) {
@@ -659,6 +661,10 @@ void plan_conv(Builder& bd, ConvParams p, const uint8_t* tw0 = nullptr, const ui
                 continue;
             }
             const size_t ub = act_split_bytes(q.nsegs16, cin);
+            if (s == 0 && premade_u0) {
+                q.seg[s] = TcSeg{premade_u0, tw0, a.taps, cin / TC_BK};
+                continue;
+            }
             if (s == 1 && share && share->raw) {   // raw twin already written by conv1's pre-pass
                 q.seg[s] = TcSeg{reinterpret_cast<const uint8_t*>(bd.ptr(share->raw)), tw1, a.taps, cin / TC_BK};
                 continue;
@@ -744,7 +750,13 @@ Act plan_attn(Builder& bd, const ULayer& l, const Act& x) {
         QkvOut qo{fuse_qkv ? reinterpret_cast<uint8_t*>(bd.ptr(q16)) : nullptr, l.heads, hch};
         plan_conv(bd, p, l.t_wqkv, nullptr, nullptr, nullptr, 0, fuse_qkv ? &qo : nullptr);
     }
-    Act a = bd.act(l.ch, x.T);
+    // tensor-pipe attention followed by a tensor-pipe proj_out: the attention epilogue writes proj_out's fp16 hi/lo operand
+    // image directly (no fp32 attention output, no pre-pass / producer for the 1x1 conv)
+    const bool fuse_proj = attn_tc && g_attn_u_fused && l.t_wproj && x.T % 16 == 0 && conv_tc_eligible(l.ch, 0, l.ch, x.T, 1, 1);
+    std::shared_ptr<Buf> au;
+    Act a;
+    if (fuse_proj) au = bd.scratch((act_split_bytes((int)((long long)bd.B * x.T / 16), l.ch) + 3) / 4);
+    else a = bd.act(l.ch, x.T);
     if (attn_tc) {
         // tensor-pipe attention: q,k,v as fp16 hi/lo operand images, then S = QK^T -> softmax -> PV in one kernel
         const bool x3 = bd.math == EEGLDM_MATH_F16X3_TC;
@@ -755,7 +767,8 @@ Act plan_attn(Builder& bd, const ULayer& l, const Act& x) {
             bd.add([=](cudaStream_t st) { return launch_qkv_split(qsrc, qdst, B, T, H, hch, st); }, 1, OP_SPLIT, 0.0,
                    8.0 * B * (double)T * 3 * l.ch);
         }
-        AttnTcParams tp{qdst, bd.wptr(a), T, H, hch, B, 1.4426950408889634f / sqrtf((float)hch)};
+        AttnTcParams tp{qdst, fuse_proj ? nullptr : bd.wptr(a), T, H, hch, B, 1.4426950408889634f / sqrtf((float)hch),
+                        fuse_proj ? reinterpret_cast<uint8_t*>(bd.ptr(au)) : nullptr};
         bd.add([tp, x3](cudaStream_t st) { return launch_attention_tc(tp, x3, st); }, 1, OP_ATTN,
                4.0 * B * (double)T * T * l.ch, 4.0 * B * (double)T * l.ch * 4.0);
     } else {
@@ -769,11 +782,12 @@ Act plan_attn(Builder& bd, const ULayer& l, const Act& x) {
     Act y = bd.act(l.ch, x.T);
     {
         ConvParams p{};
-        p.seg[0] = make_seg(bd, a, nullptr, nullptr, 0, RS_NONE, l.wproj, 1);
+        if (fuse_proj) { Act ph; ph.ext = bd.ptr(x); ph.C = l.ch; ph.T = x.T; p.seg[0] = make_seg(bd, ph, nullptr, nullptr, 0, RS_NONE, l.wproj, 1); }
+        else p.seg[0] = make_seg(bd, a, nullptr, nullptr, 0, RS_NONE, l.wproj, 1);   // (fused: the source pointer is a placeholder)
         p.nseg = 1; p.Cout = l.ch; p.Tout = x.T; p.Tc = x.T; p.stride = 1; p.pad_left = 0;
         p.bias = l.bproj; p.res = bd.ptr(x); p.res_mode = RS_NONE; p.res_Tin = x.T;
         p.out = bd.wptr(y);
-        plan_conv(bd, p, l.t_wproj, nullptr, nullptr, &y, 32);
+        plan_conv(bd, p, l.t_wproj, nullptr, nullptr, &y, 32, nullptr, fuse_proj ? reinterpret_cast<const uint8_t*>(bd.ptr(au)) : nullptr);
     }
     return y;
 }
@@ -1305,6 +1319,7 @@ int eegldm_set_conv_tuning(int pair, int bn256_min_stages, int fuse_epilogues) {
     g_conv_gn_fused = (fuse_epilogues & 1) != 0;
     g_conv_qkv_fused = (fuse_epilogues & 2) != 0;
     g_conv_direct = (fuse_epilogues & 4) != 0;
+    g_attn_u_fused = (fuse_epilogues & 8) != 0;
     if (bn256_min_stages < 1) return fail(EEGLDM_ERR_INVALID, "bn256_min_stages must be >= 1");
     g_conv_tc_pair = pair;
     g_conv_tc_bn256_stages = bn256_min_stages;

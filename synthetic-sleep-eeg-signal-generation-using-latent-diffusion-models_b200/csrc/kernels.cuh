@@ -127,6 +127,8 @@ struct AttnTcParams {
     float* out;             // [B][T][H*ch] fp32
     int T, H, ch, B;
     float scale_log2e;      // ch^-1/2 * log2(e)
+    uint8_t* out_u;         // optional (then `out` is unused): write the result as the U operand image of the following 1x1
+                            // proj_out conv (conv_tc.cu layout, T % 16 == 0) instead of fp32
 };
 bool attn_tc_eligible(int T, int ch);
 size_t attn_qkv16_bytes(int B, int T, int H, int ch);

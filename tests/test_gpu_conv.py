@@ -109,11 +109,11 @@ def test_conv_tile_shapes(built_lib, cuda_device, case, shape):
     Tc = {0: Tin, 1: Tin // 2, 2: Tin * 2}[rs]
     res = torch.randn(B, Tc, Cout, generator=g) if has_res else None
     ref = _ref(x, w, bias, scale, shift, aff, rs, res)
-    _lib.check(built_lib.eegldm_set_conv_tuning(*shape, FUSE[tuple(shape)] if tuple(shape) in FUSE else 5))
+    _lib.check(built_lib.eegldm_set_conv_tuning(*shape, FUSE[tuple(shape)] if tuple(shape) in FUSE else 13))
     try:
         y = _run(built_lib, cuda_device, x, w, bias, scale, shift, aff, rs, res, "f16x3")
     finally:
-        _lib.check(built_lib.eegldm_set_conv_tuning(0, 1, 5))
+        _lib.check(built_lib.eegldm_set_conv_tuning(0, 1, 13))
     assert torch.isfinite(y).all()
     torch.testing.assert_close(y, ref, rtol=1e-4, atol=2e-5)
 
