@@ -20,13 +20,19 @@ namespace eegldm {
 using namespace tc;
 namespace {
 
-constexpr int NST = 2;                 // operand stage ring
+// operand stage ring: as many stages as fit next to the two P buffers (T = 192: 3, T = 256: 2, T <= 128: 4) -- the S phase
+// streams 40 KB per k-step and is bound by the load round trip with only two in flight
+__host__ __device__ inline int attn_stages(int T);
 constexpr int Q_HALF = 8192;           // 128 rows x 32 ch x 2 B
 constexpr int V_HALF = 8192;           // 32 keys x 128 ch x 2 B
 constexpr int NUM_THREADS = 192;
 
 __host__ __device__ inline int stage_bytes(int T) { return 2 * Q_HALF + 2 * T * 64; }   // Q hi/lo + K hi/lo of one 32-ch k-step
 __host__ __device__ inline int p_half_bytes(int T) { return (T / 8) * 2048; }           // P hi (or lo): [T/8][16][8][8] fp16
+__host__ __device__ inline int attn_stages(int T) {
+    const int n = (227 * 1024 - 2 * p_half_bytes(T) - 256) / stage_bytes(T);
+    return n > 4 ? 4 : n;
+}
 
 // ------------------------------------------------------------------------------------------------ qkv split
 // one thread per (sample, head, q|k|v, 8-channel chunk, position); position fastest so that 8 lanes fill a 128-byte line
@@ -68,7 +74,7 @@ template <bool X3>
 __global__ void __launch_bounds__(NUM_THREADS, 1) attn_tc_kernel(const AttnTcParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int T = p.T, ch = p.ch;
-    const int SB = stage_bytes(T), PH = p_half_bytes(T);
+    const int SB = stage_bytes(T), PH = p_half_bytes(T), NST = attn_stages(T);
     const uint32_t sbase = smem_u32(smem);
     const uint32_t sStage = sbase, sP = sbase + NST * SB, bars = sP + 2 * PH;
     const uint32_t barFull = bars, barEmpty = bars + 8 * NST, barS = bars + 16 * NST, barP = barS + 8, barOfull = barP + 8,
@@ -301,7 +307,7 @@ cudaError_t launch_qkv_split(const float* qkv, uint8_t* dst, int B, int T, int H
 
 cudaError_t launch_attention_tc(const AttnTcParams& p, bool x3, cudaStream_t st) {
     if (p.B <= 0) return cudaSuccess;
-    const int smem = NST * stage_bytes(p.T) + 2 * p_half_bytes(p.T) + 256;
+    const int smem = attn_stages(p.T) * stage_bytes(p.T) + 2 * p_half_bytes(p.T) + 256;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
