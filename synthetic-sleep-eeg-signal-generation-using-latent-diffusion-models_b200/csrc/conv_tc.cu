@@ -336,20 +336,36 @@ __global__ void __launch_bounds__(DIRECT ? 384 : NUM_THREADS, 1) conv_tc_kernel(
                     const int cq = co / (3 * ch), rem = co - cq * 3 * ch, which = rem / ch, c = rem - which * ch;   // head, q|k|v, channel
                     const size_t plane = (size_t)4 * ch * T;
                     const size_t half = which < 2 ? (size_t)T * 64 : 8192;
-                    const size_t cpart = which < 2 ? (size_t)(c >> 5) * 2 * half + ((c & 31) >> 3) * 128 + (c & 7) * 2
-                                                   : (size_t)(c >> 7) * (T >> 5) * 2 * half + ((c & 127) >> 3) * 128 + (c & 7) * 2;
+                    const int c8 = c & ~7;                      // the 8-channel item this lane pair (2m, 2m+1) fills together
+                    const size_t cpart = which < 2 ? (size_t)(c8 >> 5) * 2 * half + ((c8 & 31) >> 3) * 128
+                                                   : (size_t)(c8 >> 7) * (T >> 5) * 2 * half + ((c8 & 127) >> 3) * 128;
+                    // Full 32-byte sectors per store instruction (an 8-byte scatter makes L2 read-modify-write every sector):
+                    // the even lane of a pair holds channels 0-3 and the odd lane channels 4-7 of the item, for the same four
+                    // positions.  Per position pair (2pp, 2pp+1) the lanes swap halves, so the even lane owns the whole
+                    // 16-byte item of the even position and the odd lane that of the odd position -- adjacent in the image.
+                    const bool odd = lane & 1;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        if (rb[i & 1] < 0) continue;
-                        const int t = rt[i & 1] + (i >> 1);
-                        const size_t tpart = which < 2 ? (size_t)(t >> 3) * 512 + (t & 7) * 16
-                                                       : (size_t)(t >> 5) * 2 * half + ((t & 31) >> 3) * 2048 + (t & 7) * 16;
-                        uint8_t* dst = p.qkv16 + (((size_t)rb[i & 1] * p.qkv_H + cq) * 3 + which) * plane + cpart + tpart;
-                        uint2 hi, lo;
-                        split4_f16(O[i], hi, lo);
-                        *reinterpret_cast<uint2*>(dst) = hi;
-                        *reinterpret_cast<uint2*>(dst + half) = lo;
-                    }
+                    for (int h = 0; h < 2; ++h)
+#pragma unroll
+                        for (int pp = 0; pp < 2; ++pp) {
+                            uint2 hi0, lo0, hi1, lo1;
+                            split4_f16(O[2 * (2 * pp) + h], hi0, lo0);        // position 2pp     (row i = 2j + h)
+                            split4_f16(O[2 * (2 * pp + 1) + h], hi1, lo1);    // position 2pp + 1
+                            const uint2 sh = odd ? hi0 : hi1, sl = odd ? lo0 : lo1;     // what the partner needs
+                            uint2 rh, rl;
+                            rh.x = __shfl_xor_sync(0xffffffffu, sh.x, 1); rh.y = __shfl_xor_sync(0xffffffffu, sh.y, 1);
+                            rl.x = __shfl_xor_sync(0xffffffffu, sl.x, 1); rl.y = __shfl_xor_sync(0xffffffffu, sl.y, 1);
+                            const uint2 mh = odd ? hi1 : hi0, ml = odd ? lo1 : lo0;
+                            const uint4 ihi = odd ? make_uint4(rh.x, rh.y, mh.x, mh.y) : make_uint4(mh.x, mh.y, rh.x, rh.y);
+                            const uint4 ilo = odd ? make_uint4(rl.x, rl.y, ml.x, ml.y) : make_uint4(ml.x, ml.y, rl.x, rl.y);
+                            if (rb[h] < 0) continue;
+                            const int t = rt[h] + 2 * pp + (odd ? 1 : 0);
+                            const size_t tpart = which < 2 ? (size_t)(t >> 3) * 512 + (t & 7) * 16
+                                                           : (size_t)(t >> 5) * 2 * half + ((t & 31) >> 3) * 2048 + (t & 7) * 16;
+                            uint8_t* dst = p.qkv16 + (((size_t)rb[h] * p.qkv_H + cq) * 3 + which) * plane + cpart + tpart;
+                            *reinterpret_cast<uint4*>(dst) = ihi;
+                            *reinterpret_cast<uint4*>(dst + half) = ilo;
+                        }
                 }
                 if (p.gn_partial) {
                     // GroupNorm statistics of the tensor being written (the consumer's Normalize, unet.py:71-74): this thread
