@@ -319,6 +319,8 @@ struct eegldm_unet {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     float* xbuf = nullptr; size_t xbuf_cap = 0;            // ddim state [B][T][z]
     float* xtmp = nullptr; size_t xtmp_cap = 0;            // NCL<->NLC staging
+    float* host_in = nullptr; size_t host_in_cap = 0;      // eegldm_ddim_sample_host: device copies of the host buffers
+    float* host_out = nullptr; size_t host_out_cap = 0;
     std::vector<float> table_key;                          // identifies the cached temb/coef tables
     std::map<std::pair<int, int>, GraphEntry> graphs;      // (B,T) -> one denoise step
     ~eegldm_unet() {
@@ -328,7 +330,7 @@ struct eegldm_unet {
         if (ev_fork) cudaEventDestroy(ev_fork);
         if (ev_join) cudaEventDestroy(ev_join);
         for (void* p : {(void*)arena, (void*)temb_fwd, (void*)tscratch, (void*)temb_step, (void*)temb_table,
-                        (void*)coef_table, (void*)coef_cur, (void*)step_ctr, (void*)xbuf, (void*)xtmp})
+                        (void*)coef_table, (void*)coef_cur, (void*)step_ctr, (void*)xbuf, (void*)xtmp, (void*)host_in, (void*)host_out})
             if (p) cudaFree(p);
     }
     void drop_graphs() {
@@ -1679,20 +1681,19 @@ int eegldm_ddim_sample_host(eegldm_unet* u, eegldm_aekl* a, const eegldm_sched_c
     cudaStream_t st = (cudaStream_t)stream;
     const size_t nz = (size_t)B * T * u->cfg.in_channels;
     const size_t nout = a ? (size_t)B * T * a->down_factor() * a->cfg.out_channels : nz;
-    float *d_in = nullptr, *d_out = nullptr;
-    CU(cudaMallocAsync((void**)&d_in, nz * sizeof(float), st));
-    cudaError_t e = cudaMallocAsync((void**)&d_out, nout * sizeof(float), st);
-    if (e != cudaSuccess) { cudaFreeAsync(d_in, st); return cuda_fail(e, "cudaMallocAsync"); }
-    int r = EEGLDM_OK;
-    e = cudaMemcpyAsync(d_in, noise_host, nz * sizeof(float), cudaMemcpyHostToDevice, st);
+    // device staging owned by the handle (grown on demand, reused): the stream-ordered allocator's trim / re-map at every
+    // synchronisation showed up as occasional 0.2 - 1 s stalls of this call
+    int r = ensure(u->host_in, u->host_in_cap, nz);
+    if (r) return r;
+    r = ensure(u->host_out, u->host_out_cap, nout);
+    if (r) return r;
+    cudaError_t e = cudaMemcpyAsync(u->host_in, noise_host, nz * sizeof(float), cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess) r = cuda_fail(e, "H2D copy");
-    if (!r) r = eegldm_ddim_sample(u, a, sc, d_in, scale_factor, n_steps, d_out, B, T, stream);
+    if (!r) r = eegldm_ddim_sample(u, a, sc, u->host_in, scale_factor, n_steps, u->host_out, B, T, stream);
     if (!r) {
-        e = cudaMemcpyAsync(out_host, d_out, nout * sizeof(float), cudaMemcpyDeviceToHost, st);
+        e = cudaMemcpyAsync(out_host, u->host_out, nout * sizeof(float), cudaMemcpyDeviceToHost, st);
         if (e != cudaSuccess) r = cuda_fail(e, "D2H copy");
     }
-    cudaFreeAsync(d_in, st);
-    cudaFreeAsync(d_out, st);
     e = cudaStreamSynchronize(st);
     if (!r && e != cudaSuccess) r = cuda_fail(e, "cudaStreamSynchronize");
     return r;
