@@ -166,6 +166,7 @@ def run_ours(args):
     torch.cuda.set_device(dev)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line (NCCL prints its version)
         dist.init_process_group("nccl", device_id=dev)
 
     ucfg, usd, acfg, asd = _oracle_models()     # seeded random-init weights (no checkpoint ships)
