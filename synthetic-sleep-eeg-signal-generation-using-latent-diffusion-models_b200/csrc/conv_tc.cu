@@ -172,7 +172,9 @@ __global__ void __launch_bounds__(SPLIT_THREADS) act_split_kernel(const ActSplit
 // of SiLU, fp16 pack / unpack: ~1000 cycles per k-step), which hides under a 3-tap N=256 k-step (2304 tensor cycles) but
 // not under 1-tap or N=128 k-steps; a two-k-step prefetch distance measured no different from one, and nine producer warps
 // with two items each (512 threads, 232 / 88 registers) measured 6 % slower than six with three.  tools/producer_bench.py
-// (profiles/r01_producer_bench.txt) switches parts of the producer off: no single part dominates.
+// (profiles/r01_producer_bench.txt) switches parts of the producer off: no single part dominates.  Interleaving the 1-tap
+// k-steps of a skip_connection segment with the 3-tap ones (so the ring averages their tensor time) measured 10 % SLOWER on the
+// two-segment layers and was dropped.
 template <bool X3, int BN, int CL, bool PAIR, bool DIRECT>
 __global__ void __launch_bounds__(DIRECT ? 384 : NUM_THREADS, 1) conv_tc_kernel(const TcConvParams p) {
     static_assert(!PAIR || CL == 2, "a CTA pair is a cluster of 2");
