@@ -259,6 +259,12 @@ def run_ours(args):
                 "unit": "TFLOP/s", "frac": ach / peak_tc, "traffic": _ncu_conv_traffic(pb, args.math),
                 "traffic_source": "profiles/r01_ncu_forward_b1024.csv (ncu dram bytes per conv_tc launch, B=1024)",
                 "algorithmic_bytes_per_launch": conv["bytes"] / max(conv["launches"], 1), "peak_source": peaks["src"] + " bf16 sustained",
+                # f16x3 issues 3 fp16 MMAs per algorithmic MAC (hi*hi, hi*lo, lo*hi): the fraction of the 16-bit tensor peak the
+                # kernel actually sustains is 3x `frac`; 1/3 is the ceiling of `frac` for an fp32-parity path on this pipe
+                "products_per_mac": 3 if args.math == "f16x3" else 1,
+                "tensor_pipe_frac": ach * (3 if args.math == "f16x3" else 1) / peak_tc,
+                "note": "since the fused producer (fuse bit 4) the conv launches also do the GroupNorm-apply/SiLU/fp16-split of their "
+                        "input, formerly the act_split family: compare conv + act_split across revisions, not conv alone",
                 "avg_launch_ms": conv["ms"] / max(conv["launches"], 1), "share_of_step": conv["ms"] / tot,
                 "algorithmic_flops_per_launch": conv["flops"] / max(conv["launches"], 1),
                 "profile_batch": pb,

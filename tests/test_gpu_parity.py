@@ -201,6 +201,22 @@ def test_ddim_z3_and_graph_vs_eager(built_lib, cuda_device):
     assert torch.equal(y, y3)
 
 
+@pytest.mark.parametrize("B,T", [(5, 192), (3, 320), (1, 64)])
+def test_tensor_pipe_vs_simt_odd_shapes(built_lib, cuda_device, B, T):
+    """Full config_ldm.yaml UNet at shapes whose 128-row tiles straddle samples and end in partial tiles (T = 192: 12
+    sixteen-position segments per sample at level 0, 3 at level 2; B odd): the tcgen05 path (fused producer, two-segment
+    convs with virtual concat, nearest-x2 / AvgPool ResBlocks, attention where eligible) against the fp32 SIMT path of the
+    same engine, per-sample timesteps."""
+    ucfg = ou.full_cfg()
+    usd = ou.make_unet_state_dict(ucfg, 0)
+    x = torch.randn(B, 1, T, generator=torch.Generator().manual_seed(B * 1000 + T)).to(cuda_device)
+    t = torch.randint(0, 1000, (B,), generator=torch.Generator().manual_seed(7))
+    y32 = _unet(ucfg, usd, cuda_device, "fp32")(x, timesteps=t)
+    y16 = _unet(ucfg, usd, cuda_device, "f16x3")(x, timesteps=t)
+    assert torch.isfinite(y16).all()
+    torch.testing.assert_close(y16, y32, rtol=RTOL, atol=ATOL)
+
+
 @pytest.mark.parametrize("math", MATH)
 def test_raw_signal_dm_variant(built_lib, cuda_device, math):
     """the raw-signal diffusion model (config_dm.yaml: the same UNet on [B,1,3072], self-attention at T = 768)
