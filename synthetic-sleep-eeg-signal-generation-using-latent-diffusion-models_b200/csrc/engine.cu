@@ -2056,8 +2056,7 @@ struct TrainRun {
             p.src0 = x.p; p.C0 = x.C; p.T = x.T; p.G = G; p.gamma = t->P + og; p.beta = t->P + obe; p.eps = 1e-6f; p.B = B;
             p.nsplit = nsplit; p.scale = ss; p.shift = ss + (size_t)B * x.C; p.partial = part;
             p.mean_out = mr; p.rstd_out = mr + (size_t)B * G;
-            ck(launch_groupnorm(p, st));
-            ck(launch_norm_act_fwd(x.p, p.scale, p.shift, a.p, B, x.T, x.C, silu, st));
+            ck(launch_gn_act_fwd(p, a.p, silu, st));
             Op op; op.kind = NORM; op.in = x; op.out = a; op.mean = p.mean_out; op.rstd = p.rstd_out; op.og = og; op.obe = obe; op.G = G; op.silu = silu;
             tape.push_back(op);
         }

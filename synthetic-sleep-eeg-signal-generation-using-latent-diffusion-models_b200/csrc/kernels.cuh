@@ -170,6 +170,7 @@ struct NormGradParams {
     int C, T, G, B, silu, accumulate;
 };
 cudaError_t launch_norm_act_bwd(const NormGradParams& p, cudaStream_t st);
+cudaError_t launch_gn_act_fwd(const GnParams& p, float* a, int silu, cudaStream_t st);   // statistics + apply (+ SiLU), mean / rstd saved
 cudaError_t launch_axpy(const float* src, float* dst, float alpha, int accumulate, size_t n, cudaStream_t st);
 cudaError_t launch_l1_loss(const float* r, const float* x, float* dr, float* loss, float weight, size_t n, cudaStream_t st);
 cudaError_t launch_latent(const float* mu, const float* lv, const float* eps, float* sigma, float* z, const float* dz, float* dmu,

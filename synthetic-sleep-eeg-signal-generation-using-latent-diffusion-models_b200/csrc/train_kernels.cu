@@ -248,6 +248,120 @@ cudaError_t launch_conv_grad_tiny(const ConvGradParams& p, bool weight, cudaStre
     return cudaErrorInvalidValue;
 }
 
+// ---- one CTA per sample (tensors of the 2-2-4 autoencoder are <= 6144 elements per sample): GroupNorm statistics, apply and
+// ---- SiLU in ONE kernel with the sample in registers (forward), reduce + apply in ONE kernel (backward).  256 % C == 0, so a
+// ---- thread's elements e = tid + 256*k all belong to channel tid % C: per-thread partials are per (channel, group).
+constexpr int SAMPLE_NE = 32;   // elements per thread at most (C*T <= 8192)
+// Per-channel block totals of one value per thread (thread's channel = tid % C, C in {1,2,4,8} divides the warp size):
+// xor-shuffles over the lanes of equal channel, one row per warp in shared memory, then channel c's total in out[c].
+// All 256 threads call it; out[] is valid after the trailing __syncthreads().
+__device__ __forceinline__ void block_channel_sums(float v, int C, float (*rows)[8] /* [8 warps][8] */, float* out /* [8] */) {
+    for (int o = 16; o >= C; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane < C) rows[warp][lane] = v;
+    __syncthreads();
+    if ((int)threadIdx.x < C) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += rows[w][threadIdx.x];
+        out[threadIdx.x] = t;
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ float group_of(const float* chs, int cpg, int g) {
+    float s = 0.f;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) s += chs[c];
+    return s;
+}
+__global__ void __launch_bounds__(256) gn_act_fwd_sample_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                                 const float* __restrict__ beta, float eps, float* __restrict__ a,
+                                                                 float* __restrict__ mean_out, float* __restrict__ rstd_out, int C, int T,
+                                                                 int G, int silu) {
+    __shared__ float rows[8][8], chs[8];
+    const int b = blockIdx.x, n = C * T, cpg = C / G, ch = threadIdx.x % C, g = ch / cpg;
+    const float* xb = x + (size_t)b * n;
+    const float inv = 1.f / (float)(cpg * T);
+    float v[SAMPLE_NE];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < SAMPLE_NE; ++k) {
+        const int e = threadIdx.x + 256 * k;
+        v[k] = e < n ? xb[e] : 0.f;
+        s += v[k];
+    }
+    block_channel_sums(s, C, rows, chs);
+    const float mu = group_of(chs, cpg, g) * inv;
+    __syncthreads();                       // chs is rewritten below
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < SAMPLE_NE; ++k) {
+        const int e = threadIdx.x + 256 * k;
+        if (e < n) { const float d = v[k] - mu; q = fmaf(d, d, q); }
+    }
+    block_channel_sums(q, C, rows, chs);
+    const float rs = 1.0f / sqrtf(group_of(chs, cpg, g) * inv + eps);   // biased variance, as nn.GroupNorm
+    if ((int)threadIdx.x < C && ch % cpg == 0) {
+        mean_out[(size_t)b * G + g] = mu;
+        rstd_out[(size_t)b * G + g] = rs;
+    }
+    const float sc = gamma[ch] * rs, sh = beta[ch] - mu * sc;
+    float* ab = a + (size_t)b * n;
+#pragma unroll
+    for (int k = 0; k < SAMPLE_NE; ++k) {
+        const int e = threadIdx.x + 256 * k;
+        if (e < n) {
+            float y = fmaf(sc, v[k], sh);
+            if (silu) y = y * sigmoid_f(y);
+            ab[e] = y;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) norm_act_bwd_sample_kernel(const NormGradParams p) {
+    __shared__ float rows[8][8], c1[8], c2[8];
+    const int b = blockIdx.x, C = p.C, n = C * p.T, cpg = C / p.G, ch = threadIdx.x % C, g = ch / cpg;
+    const float mu = p.mean[(size_t)b * p.G + g], rs = p.rstd[(size_t)b * p.G + g], ga = p.gamma[ch], be = p.beta[ch];
+    const float* xb = p.x + (size_t)b * n;
+    const float* db = p.da + (size_t)b * n;
+    float gq[SAMPLE_NE], xh[SAMPLE_NE];
+    float s1 = 0.f, s2 = 0.f, dg = 0.f, dbv = 0.f;
+#pragma unroll
+    for (int k = 0; k < SAMPLE_NE; ++k) {
+        const int e = threadIdx.x + 256 * k;
+        gq[k] = 0.f; xh[k] = 0.f;
+        if (e < n) {
+            xh[k] = (xb[e] - mu) * rs;
+            const float v = fmaf(xh[k], ga, be);
+            float dv = db[e];
+            if (p.silu) { const float sg = sigmoid_f(v); dv *= sg * (1.f + v * (1.f - sg)); }
+            gq[k] = dv * ga;
+            s1 += gq[k]; s2 = fmaf(gq[k], xh[k], s2);
+            dg = fmaf(dv, xh[k], dg); dbv += dv;
+        }
+    }
+    block_channel_sums(s1, C, rows, c1);
+    block_channel_sums(s2, C, rows, c2);
+    const float inv = 1.f / (float)(cpg * p.T);
+    const float m1 = group_of(c1, cpg, g) * inv, m2 = group_of(c2, cpg, g) * inv;
+    __syncthreads();                       // c1 / c2 are rewritten below
+    float* dxb = p.dx + (size_t)b * n;
+#pragma unroll
+    for (int k = 0; k < SAMPLE_NE; ++k) {
+        const int e = threadIdx.x + 256 * k;
+        if (e < n) {
+            const float r = rs * (gq[k] - m1 - xh[k] * m2);
+            dxb[e] = p.accumulate ? dxb[e] + r : r;
+        }
+    }
+    block_channel_sums(dg, C, rows, c1);   // per-channel dgamma / dbeta of this sample
+    block_channel_sums(dbv, C, rows, c2);
+    if ((int)threadIdx.x < C) {
+        atomicAdd(p.dgamma + threadIdx.x, c1[threadIdx.x]);
+        atomicAdd(p.dbeta + threadIdx.x, c2[threadIdx.x]);
+    }
+}
+bool norm_sample_ok(int C, int T, int G) { return C >= 1 && C <= 8 && 256 % C == 0 && G >= 1 && G <= 8 && C % G == 0 && (size_t)C * T <= 256 * SAMPLE_NE; }
+
 // GroupNorm(+SiLU) backward, pass 1: per (sample, group) means of g = dv*gamma and g*xhat; per-channel dgamma / dbeta.
 //   v = xhat*gamma + beta,  a = silu?(v),  dv = da * silu'(v)
 // grid (G, B), block 256; requires cpg = C/G <= 256.
@@ -422,6 +536,11 @@ cudaError_t launch_conv_bwd_weight(const ConvGradParams& p, cudaStream_t st) {
 
 cudaError_t launch_norm_act_bwd(const NormGradParams& p, cudaStream_t st) {
     if (p.B <= 0) return cudaSuccess;
+    if (norm_sample_ok(p.C, p.T, p.G)) {
+        norm_act_bwd_sample_kernel<<<p.B, 256, 0, st>>>(p);
+        g_launch_count += 1;
+        return cudaGetLastError();
+    }
     if (p.C / p.G > 256) return cudaErrorInvalidValue;
     dim3 grid(p.G, p.B);
     norm_act_bwd_reduce_kernel<<<grid, 256, 0, st>>>(p.da, p.x, p.mean, p.rstd, p.gamma, p.beta, p.m12, p.dgamma, p.dbeta, p.C, p.T, p.G, p.silu);
@@ -430,6 +549,20 @@ cudaError_t launch_norm_act_bwd(const NormGradParams& p, cudaStream_t st) {
                                                                 p.accumulate, total);
     g_launch_count += 2;
     return cudaGetLastError();
+}
+
+// GroupNorm statistics + apply (+ SiLU) of a training forward pass: a = silu?(GN(x)), mean / rstd [B][G] saved for the backward
+// pass.  Tiny tensors: one kernel; otherwise statistics (launch_groupnorm with p prepared by the caller) + launch_norm_act_fwd.
+cudaError_t launch_gn_act_fwd(const GnParams& p, float* a, int silu, cudaStream_t st) {
+    if (p.B <= 0) return cudaSuccess;
+    if (!p.src1 && norm_sample_ok(p.C0, p.T, p.G) && p.mean_out && p.rstd_out) {
+        gn_act_fwd_sample_kernel<<<p.B, 256, 0, st>>>(p.src0, p.gamma, p.beta, p.eps, a, p.mean_out, p.rstd_out, p.C0, p.T, p.G, silu);
+        g_launch_count += 1;
+        return cudaGetLastError();
+    }
+    cudaError_t e = launch_groupnorm(p, st);
+    if (e != cudaSuccess) return e;
+    return launch_norm_act_fwd(p.src0, p.scale, p.shift, a, p.B, p.T, p.C0, silu, st);
 }
 
 cudaError_t launch_axpy(const float* src, float* dst, float alpha, int accumulate, size_t n, cudaStream_t st) {
