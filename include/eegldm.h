@@ -67,6 +67,8 @@ int eegldm_set_conv_cluster(int ctas);
  * bit 0 -- a conv whose output feeds a GroupNorm writes that GroupNorm's statistics from its epilogue (no separate pass);
  * bit 2 -- the conv kernel's producer warps read the fp32 input and build the fp16 hi/lo operand tiles in shared memory
  *          themselves (GroupNorm apply + SiLU + nearest-x2 + split), replacing the act_split pre-pass and its U tensors;
+ * bit 4 -- the tcgen05 attention kernel reads the fp32 qkv tensor and splits q, k, v to fp16 hi/lo in its own producer warps
+ *          (no qkv_split pass); T <= 208; measured no faster (the kernel slows down by what the pass cost): off;
  * bit 3 -- the tcgen05 attention kernel writes its result as proj_out's operand image (no fp32 attention output, no pre-pass);
  * bit 1 -- an AttentionBlock's qkv conv writes the attention kernel's fp16 hi/lo operand images instead of fp32 (f16x3; measured no faster than the separate split pass).
  * Call before creating models: plans cache the choices. */

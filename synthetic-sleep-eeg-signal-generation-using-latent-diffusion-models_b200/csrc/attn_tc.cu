@@ -70,8 +70,15 @@ __global__ void qkv_split_kernel(const float* __restrict__ qkv, uint8_t* __restr
 }
 
 // ------------------------------------------------------------------------------------------------ attention
-template <bool X3>
-__global__ void __launch_bounds__(NUM_THREADS, 1) attn_tc_kernel(const AttnTcParams p) {
+// DIRECT: q, k, v are read as fp32 straight from the qkv conv's output [B][T][H*3*ch] (legacy head layout): six producer warps
+// split them to fp16 hi/lo and write the stage images with st.shared (the qkv_split pass and its 2 x 1.2 GB of HBM traffic
+// per block at B = 1024 disappear; measured: the attention kernel slows down by exactly what the pass cost, 0.47 -> 0.99 ms,
+// so this form is OFF by default -- eegldm_set_conv_tuning bit 4).  Item = 8 channels of one row (two float4 loads, two 16-byte stores); one stage of loads
+// is in flight in registers while the previous one is split.  Lane mapping: S stages -- 4 consecutive lanes cover one row's
+// 32 channels (128 contiguous bytes in, 8 rows x 64 B = 512 contiguous bytes of the image out per warp); PV stages -- a warp
+// covers 8 keys x 4 channel groups, which is conflict-free on the MN-major V image (4 x 128 contiguous bytes).
+template <bool X3, bool DIRECT>
+__global__ void __launch_bounds__(DIRECT ? 2 * NUM_THREADS : NUM_THREADS, 1) attn_tc_kernel(const AttnTcParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int T = p.T, ch = p.ch;
     const int SB = stage_bytes(T), PH = p_half_bytes(T), NST = attn_stages(T);
@@ -91,7 +98,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_tc_kernel(const AttnTcPar
     const uint8_t* gv = gk + plane;
 
     if (tid == 0) {
-        for (int i = 0; i < NST; ++i) { mbar_init(barFull + 8 * i, 1); mbar_init(barEmpty + 8 * i, 1); }
+        for (int i = 0; i < NST; ++i) { mbar_init(barFull + 8 * i, DIRECT ? NUM_THREADS : 1); mbar_init(barEmpty + 8 * i, 1); }
         mbar_init(barS, 1);
         mbar_init(barP, 128);
         for (int i = 0; i < 2; ++i) { mbar_init(barOfull + 8 * i, 1); mbar_init(barOempty + 8 * i, 128); }
@@ -201,9 +208,75 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_tc_kernel(const AttnTcPar
             tc_fence_before();
             mbar_arrive(barOempty + 8 * buf);
         }
+    } else if (DIRECT && warp >= 6) {
+        // ================================================================ producers (192 threads): fp32 rows -> fp16 hi/lo stage images
+        const int pt = tid - NUM_THREADS;              // warps 6-11
+        const size_t rs = (size_t)p.H * 3 * ch;          // floats per qkv row
+        const float* qrow0 = p.qkv32 + (size_t)b * T * rs + (size_t)h * 3 * ch;   // q of position 0; k at +ch, v at +2ch
+        const int rowsQ = rows_pg * 8, nS = (rowsQ + T) * 4, nV = 512;
+        const int total = nks + nchunk * nss;
+        constexpr int MAXI = 7;                          // items per thread and stage: (128 + 256) * 4 / 192 = 8 would need T = 256: see launcher
+        struct Pre { float4 x[MAXI][2]; };
+        auto src_of = [&](int it, int idx) -> const float* {
+            if (it < nks) {
+                const int row = idx >> 2, cg = idx & 3;
+                return row < rowsQ ? qrow0 + (size_t)(mt * 128 + row) * rs + it * 32 + cg * 8
+                                   : qrow0 + ch + (size_t)(row - rowsQ) * rs + it * 32 + cg * 8;
+            }
+            const int c = (it - nks) / nss, ss = (it - nks) % nss;
+            const int cgrp = (idx & 3) | (((idx >> 5) & 3) << 2), key = ((idx >> 2) & 7) | ((idx >> 7) << 3);
+            return qrow0 + 2 * ch + (size_t)(ss * 32 + key) * rs + c * 128 + cgrp * 8;
+        };
+        auto issue = [&](int it, Pre& P) {
+            const int n = it < nks ? nS : nV;
+#pragma unroll
+            for (int j = 0; j < MAXI; ++j) {
+                const int idx = pt + NUM_THREADS * j;
+                if (idx < n) {
+                    const float* sp = src_of(it, idx);
+                    P.x[j][0] = __ldg(reinterpret_cast<const float4*>(sp));
+                    P.x[j][1] = __ldg(reinterpret_cast<const float4*>(sp + 4));
+                }
+            }
+        };
+        Pre N;
+        issue(0, N);
+        for (int it = 0; it < total; ++it) {
+            const Pre C = N;
+            if (it + 1 < total) issue(it + 1, N);
+            const int st = it % NST;
+            mbar_wait(barEmpty + 8 * st, ((it / NST) & 1) ^ 1);
+            uint8_t* stage = smem + (size_t)st * SB;
+            const int n = it < nks ? nS : nV;
+#pragma unroll
+            for (int j = 0; j < MAXI; ++j) {
+                const int idx = pt + NUM_THREADS * j;
+                if (idx < n) {
+                    const float v[8] = {C.x[j][0].x, C.x[j][0].y, C.x[j][0].z, C.x[j][0].w, C.x[j][1].x, C.x[j][1].y, C.x[j][1].z, C.x[j][1].w};
+                    uint32_t off, half;
+                    if (it < nks) {
+                        const int row = idx >> 2, cg = idx & 3;
+                        if (row < rowsQ) { off = (uint32_t)((row >> 3) * 512 + cg * 128 + (row & 7) * 16); half = Q_HALF; }
+                        else {
+                            const int tk = row - rowsQ;
+                            off = (uint32_t)(2 * Q_HALF + (tk >> 3) * 512 + cg * 128 + (tk & 7) * 16); half = (uint32_t)T * 64;
+                        }
+                    } else {
+                        const int cgrp = (idx & 3) | (((idx >> 5) & 3) << 2), key = ((idx >> 2) & 7) | ((idx >> 7) << 3);
+                        off = (uint32_t)((key >> 3) * 2048 + cgrp * 128 + (key & 7) * 16); half = V_HALF;
+                    }
+                    uint4 hi, lo;
+                    split8_f16(v, hi, lo);             // the attention MMAs are fp16 in both modes (the fast mode drops lo)
+                    if (X3) *reinterpret_cast<uint4*>(stage + off + half) = lo;
+                    *reinterpret_cast<uint4*>(stage + off) = hi;
+                }
+            }
+            fence_proxy_async_smem();
+            mbar_arrive(barFull + 8 * st);
+        }
     } else if (warp == 4) {
-        // ================================================================ loader
-        if (lane == 0) {
+        // ================================================================ loader (pre-split images; idle in the DIRECT form)
+        if (lane == 0 && !DIRECT) {
             int it = 0;
             const uint32_t qb = (uint32_t)rows_pg * 512, kb = (uint32_t)T * 64;
             for (int ks = 0; ks < nks; ++ks, ++it) {
@@ -294,6 +367,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_tc_kernel(const AttnTcPar
 
 }  // namespace
 
+bool attn_direct_eligible(int T, int ch) { return attn_tc_eligible(T, ch) && (128 + T) * 4 <= 7 * NUM_THREADS; }
 bool attn_tc_eligible(int T, int ch) { return T >= 32 && T <= 256 && T % 32 == 0 && ch >= 128 && ch % 128 == 0; }
 size_t attn_qkv16_bytes(int B, int T, int H, int ch) { return (size_t)B * H * 12 * ch * T; }
 
@@ -310,15 +384,20 @@ cudaError_t launch_attention_tc(const AttnTcParams& p, bool x3, cudaStream_t st)
     const int smem = attn_stages(p.T) * stage_bytes(p.T) + 2 * p_half_bytes(p.T) + 256;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(attn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
     dim3 grid((p.T + 127) / 128, p.H, p.B);
-    if (x3) attn_tc_kernel<true><<<grid, NUM_THREADS, smem, st>>>(p);
-    else attn_tc_kernel<false><<<grid, NUM_THREADS, smem, st>>>(p);
+    if (p.qkv32) {
+        if ((128 + p.T) * 4 > 7 * NUM_THREADS) return cudaErrorInvalidValue;   // producer item budget: T <= 208 (attn_direct_eligible)
+        if (x3) attn_tc_kernel<true, true><<<grid, 2 * NUM_THREADS, smem, st>>>(p);
+        else attn_tc_kernel<false, true><<<grid, 2 * NUM_THREADS, smem, st>>>(p);
+    } else if (x3) attn_tc_kernel<true, false><<<grid, NUM_THREADS, smem, st>>>(p);
+    else attn_tc_kernel<false, false><<<grid, NUM_THREADS, smem, st>>>(p);
     g_launch_count += 1;
     return cudaGetLastError();
 }

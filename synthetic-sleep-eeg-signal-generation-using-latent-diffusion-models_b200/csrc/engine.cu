@@ -345,6 +345,7 @@ struct eegldm_unet {
 namespace {
 
 bool g_conv_qkv_fused = false; // the qkv conv writes attention operand images directly (f16x3; eegldm_set_conv_tuning): measured no faster
+bool g_attn_direct = false;    // the tcgen05 attention splits fp32 q, k, v itself (eegldm_set_conv_tuning bit 4): measured no faster
 bool g_attn_u_fused = true;    // the tcgen05 attention writes proj_out's operand image instead of fp32 (eegldm_set_conv_tuning bit 3)
 bool g_conv_direct = true;     // tensor-pipe convs produce their activation operands in-kernel (no act_split pre-pass)
 bool g_conv_gn_fused = true;   // tensor-pipe convs emit the GroupNorm statistics of their output (eegldm_set_conv_tuning)
@@ -739,8 +740,10 @@ Act plan_attn(Builder& bd, const ULayer& l, const Act& x) {
     // f16x3: the qkv conv's epilogue writes the attention kernel's fp16 hi/lo operand images directly (no fp32 qkv tensor)
     const bool fuse_qkv = attn_tc && g_conv_qkv_fused && bd.math == EEGLDM_MATH_F16X3_TC && l.t_wqkv &&
                           conv_tc_eligible(x.C, 0, 3 * l.ch, x.T, 1, 1);
+    // the attention kernel reads the fp32 qkv tensor itself and splits q, k, v in its producer warps (no qkv_split pass)
+    const bool attn_direct = attn_tc && !fuse_qkv && g_attn_direct && attn_direct_eligible(x.T, hch);
     std::shared_ptr<Buf> q16;
-    if (attn_tc) q16 = bd.scratch((attn_qkv16_bytes(bd.B, x.T, l.heads, hch) + 3) / 4);
+    if (attn_tc && !attn_direct) q16 = bd.scratch((attn_qkv16_bytes(bd.B, x.T, l.heads, hch) + 3) / 4);
     Act qkv;
     if (!fuse_qkv) qkv = bd.act(3 * l.ch, x.T);
     {
@@ -762,15 +765,15 @@ Act plan_attn(Builder& bd, const ULayer& l, const Act& x) {
     if (attn_tc) {
         // tensor-pipe attention: q,k,v as fp16 hi/lo operand images, then S = QK^T -> softmax -> PV in one kernel
         const bool x3 = bd.math == EEGLDM_MATH_F16X3_TC;
-        uint8_t* qdst = reinterpret_cast<uint8_t*>(bd.ptr(q16));
+        uint8_t* qdst = attn_direct ? nullptr : reinterpret_cast<uint8_t*>(bd.ptr(q16));
         const int B = bd.B, T = x.T, H = l.heads;
-        if (!fuse_qkv) {
+        if (!fuse_qkv && !attn_direct) {
             const float* qsrc = bd.ptr(qkv);
             bd.add([=](cudaStream_t st) { return launch_qkv_split(qsrc, qdst, B, T, H, hch, st); }, 1, OP_SPLIT, 0.0,
                    8.0 * B * (double)T * 3 * l.ch);
         }
         AttnTcParams tp{qdst, fuse_proj ? nullptr : bd.wptr(a), T, H, hch, B, 1.4426950408889634f / sqrtf((float)hch),
-                        fuse_proj ? reinterpret_cast<uint8_t*>(bd.ptr(au)) : nullptr};
+                        fuse_proj ? reinterpret_cast<uint8_t*>(bd.ptr(au)) : nullptr, attn_direct ? bd.ptr(qkv) : nullptr};
         bd.add([tp, x3](cudaStream_t st) { return launch_attention_tc(tp, x3, st); }, 1, OP_ATTN,
                4.0 * B * (double)T * T * l.ch, 4.0 * B * (double)T * l.ch * 4.0);
     } else {
@@ -1322,6 +1325,7 @@ int eegldm_set_conv_tuning(int pair, int bn256_min_stages, int fuse_epilogues) {
     g_conv_qkv_fused = (fuse_epilogues & 2) != 0;
     g_conv_direct = (fuse_epilogues & 4) != 0;
     g_attn_u_fused = (fuse_epilogues & 8) != 0;
+    g_attn_direct = (fuse_epilogues & 16) != 0;
     if (bn256_min_stages < 1) return fail(EEGLDM_ERR_INVALID, "bn256_min_stages must be >= 1");
     g_conv_tc_pair = pair;
     g_conv_tc_bn256_stages = bn256_min_stages;
@@ -1912,10 +1916,15 @@ int eegldm_test_attention(const float* qkv_dev, int B, int T, int H, int ch, int
     uint8_t* q16 = nullptr;
     if (math != EEGLDM_MATH_FP32_SIMT) {
         if (!attn_tc_eligible(T, ch)) return fail(EEGLDM_ERR_SHAPE, "shape not eligible for the tcgen05 attention");
-        CU(cudaMalloc((void**)&q16, attn_qkv16_bytes(B, T, H, ch)));
-        ce = launch_qkv_split(qkv_dev, q16, B, T, H, ch, st);
-        AttnTcParams tp{q16, out_dev, T, H, ch, B, 1.4426950408889634f / sqrtf((float)ch)};
-        if (ce == cudaSuccess) ce = launch_attention_tc(tp, math == EEGLDM_MATH_F16X3_TC, st);
+        if (g_attn_direct && attn_direct_eligible(T, ch)) {   // q, k, v split inside the kernel
+            AttnTcParams tp{nullptr, out_dev, T, H, ch, B, 1.4426950408889634f / sqrtf((float)ch), nullptr, qkv_dev};
+            ce = launch_attention_tc(tp, math == EEGLDM_MATH_F16X3_TC, st);
+        } else {
+            CU(cudaMalloc((void**)&q16, attn_qkv16_bytes(B, T, H, ch)));
+            ce = launch_qkv_split(qkv_dev, q16, B, T, H, ch, st);
+            AttnTcParams tp{q16, out_dev, T, H, ch, B, 1.4426950408889634f / sqrtf((float)ch)};
+            if (ce == cudaSuccess) ce = launch_attention_tc(tp, math == EEGLDM_MATH_F16X3_TC, st);
+        }
     } else {
         AttnParams ap{qkv_dev, out_dev, T, H, ch, B};
         ce = launch_attention_simt(ap, st);

@@ -129,8 +129,11 @@ struct AttnTcParams {
     float scale_log2e;      // ch^-1/2 * log2(e)
     uint8_t* out_u;         // optional (then `out` is unused): write the result as the U operand image of the following 1x1
                             // proj_out conv (conv_tc.cu layout, T % 16 == 0) instead of fp32
+    const float* qkv32;     // optional (then `qkv16` is unused): fp32 qkv [B][T][H*3*ch]; q, k, v are split to fp16 hi/lo inside the
+                            // kernel (attn_direct_eligible), no launch_qkv_split pass
 };
 bool attn_tc_eligible(int T, int ch);
+bool attn_direct_eligible(int T, int ch);   // in-kernel fp32 -> fp16 hi/lo split of q, k, v (T <= 208)
 size_t attn_qkv16_bytes(int B, int T, int H, int ch);
 cudaError_t launch_qkv_split(const float* qkv, uint8_t* dst, int B, int T, int H, int ch, cudaStream_t st);
 cudaError_t launch_attention_tc(const AttnTcParams& p, bool x3, cudaStream_t st);

@@ -154,6 +154,19 @@ def test_conv_epilogue_groupnorm_statistics(built_lib, cuda_device, case):
 ATTN_CASES = [(2, 192, 1, 512), (1, 128, 1, 128), (3, 64, 2, 128), (2, 256, 1, 256), (1, 32, 4, 128)]
 
 
+@pytest.mark.parametrize("case", ATTN_CASES)
+@pytest.mark.parametrize("math", ["f16x3", "bf16"])
+def test_attention_in_kernel_split(built_lib, cuda_device, case, math):
+    """The same attention reading fp32 q, k, v and splitting them in its own producer warps (fuse bit 4; T <= 208, else the
+    pre-split path is taken)."""
+    from eegldm import _lib
+    _lib.check(built_lib.eegldm_set_conv_tuning(0, 1, 29))
+    try:
+        test_attention_matches_torch(built_lib, cuda_device, case, math)
+    finally:
+        _lib.check(built_lib.eegldm_set_conv_tuning(0, 1, 13))
+
+
 @pytest.mark.parametrize("math", ["fp32", "f16x3", "bf16"])
 @pytest.mark.parametrize("case", ATTN_CASES)
 def test_attention_matches_torch(built_lib, cuda_device, case, math):
