@@ -151,8 +151,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     import eegldm
-    from eegldm import _lib
-    from oracle.sample import SAMPLER_DEFAULTS
+    from eegldm import _lib, synthetic
     import ctypes as C
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -169,16 +168,16 @@ def run_ours(args):
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line (NCCL prints its version)
         dist.init_process_group("nccl", device_id=dev)
 
-    ucfg, usd, acfg, asd = _oracle_models()     # seeded random-init weights (no checkpoint ships)
+    # seeded random-init weights of the reference's architecture (no checkpoint ships); product-side helper, no oracle/ here
     _lib.check(eegldm.lib().eegldm_set_sample_lanes(args.lanes))
     _lib.check(eegldm.lib().eegldm_set_conv_tuning(0, 1, args.fuse))
-    unet = eegldm.UNetModel(**ucfg, math=args.math)
-    unet.load_state_dict(usd)
+    unet = eegldm.UNetModel(**synthetic.LDM_UNET_CFG, math=args.math)
+    unet.load_state_dict(synthetic.seeded_state_dict(unet, 0))
     unet = unet.to(dev).eval()
-    aekl = eegldm.AutoencoderKL(**acfg)
-    aekl.load_state_dict(asd)
+    aekl = eegldm.AutoencoderKL(**synthetic.AEKL_224_CFG)
+    aekl.load_state_dict(synthetic.seeded_state_dict(aekl, 42))
     aekl = aekl.to(dev).eval()
-    sched = eegldm.DDIMScheduler(**SAMPLER_DEFAULTS)
+    sched = eegldm.DDIMScheduler(**synthetic.DDIM_CFG)
     sched.set_timesteps(DDIM_STEPS)
 
     B = args.batch
@@ -218,7 +217,9 @@ def run_ours(args):
         return float(ms.item())
 
     for _ in range(args.warmup):
-        step_device()
+        y = step_device()
+    if args.warmup and not bool(torch.isfinite(y).all()):
+        raise SystemExit("bench: non-finite windows from the synthetic weights (outside the f16x3 operand range?)")
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
@@ -305,12 +306,12 @@ def run_train(args):
     adversarial term excluded -- the PatchDiscriminator is a SURVEY 8(f) 'next' row)."""
     import torch
     import eegldm
-    from oracle import aekl as oa, jukebox as oj
+    from eegldm import synthetic
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
     torch.cuda.set_device(dev)
-    cfg = oa.full_cfg()
-    sd = oa.make_aekl_state_dict(cfg, 42)
+    cfg = dict(synthetic.AEKL_224_CFG)
     m = eegldm.AutoencoderKL(**cfg)
+    sd = synthetic.seeded_state_dict(m, 42)
     m.load_state_dict(sd)
     m = m.to(dev)
     B = args.batch if args.batch != 1024 else 512
@@ -334,7 +335,8 @@ def run_train(args):
         m.train_step(xh.to(dev, non_blocking=True), eh.to(dev, non_blocking=True))
     torch.cuda.synchronize()
     ms_e2e = (time.perf_counter() - t0) * 1e3 / args.steps
-    # CPU baseline: the oracle with torch autograd + Adam, bounded sample
+    # CPU baseline: the oracle with torch autograd + Adam, bounded sample (the only use of oracle/ in this function)
+    from oracle import aekl as oa, jukebox as oj
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
     Bc = 16

@@ -17,6 +17,7 @@ from .aekl import AutoencoderKL  # noqa: F401
 from .schedulers import DDIMScheduler, DDPMScheduler  # noqa: F401
 from .losses import JukeboxLoss  # noqa: F401
 from .sampler import ddim_sample, ddim_sample_host, shard_range, sample_sharded  # noqa: F401
+from . import synthetic  # noqa: F401
 
 
 def launch_count() -> int:
