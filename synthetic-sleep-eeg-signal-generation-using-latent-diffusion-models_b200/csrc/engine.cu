@@ -246,6 +246,19 @@ ScaleShift plan_gn(Builder& bd, const Act& x0, const Act* x1, int G, const float
                4.0 * bd.B * (3.0 * p.nsplit * G + 2.0 * C));
         return ss;
     }
+    // virtual concat whose sources both carry epilogue statistics and whose groups are whole numbers of source records
+    // (the 1024 = 512 + 512 inputs of output_blocks.0 / .1: 32-channel groups = two 16-channel records of one source)
+    if (x1 && x0.gn_part && x1->gn_part && x0.gn_nsplit == x1->gn_nsplit && G <= 256) {
+        const int cpg = C / G, r0 = x0.C / x0.gn_G, r1 = x1->C / x1->gn_G;
+        if (x0.C % cpg == 0 && cpg % r0 == 0 && cpg % r1 == 0) {
+            p.nsplit = x0.gn_nsplit;
+            p.partial = bd.ptr(x0.gn_part); p.partial1 = bd.ptr(x1->gn_part);
+            p.rec_G0 = x0.gn_G; p.rec_G1 = x1->gn_G;
+            bd.add([p](cudaStream_t st) { return launch_groupnorm_finalize(p, st); }, 1, OP_GN, 0.0,
+                   4.0 * bd.B * (3.0 * p.nsplit * (x0.gn_G + x1->gn_G) + 2.0 * C));
+            return ss;
+        }
+    }
     p.nsplit = groupnorm_nsplit(C, x0.T, G);
     auto part = bd.scratch((size_t)bd.B * p.nsplit * G * 3);
     p.partial = bd.ptr(part);

@@ -61,6 +61,11 @@ struct GnParams {
     int B;
     float* mean_out;              // optional [B][G] (training: saved for the backward pass)
     float* rstd_out;
+    // launch_groupnorm_finalize only: records written by the producing convs' epilogues at THEIR group width.  The normalised
+    // tensor is concat(src0, src1); source i has rec_G[i] record groups per split (rec_G = 0: `partial` is already at this
+    // norm's G, single source).  Every group of this norm must be a whole number of records of ONE source.
+    const float* partial1;
+    int rec_G0, rec_G1;
 };
 
 struct AttnParams {

@@ -463,12 +463,22 @@ __global__ void gn_finalize_kernel(const GnParams p) {
         const int lanes = 256 / gp;                       // threads per group
         const int g = threadIdx.x % gp, part = threadIdx.x / gp;
         Mom r; r.n = 0.f; r.mean = 0.f; r.m2 = 0.f;
-        if (g < p.G)
-            for (int sp = part; sp < p.nsplit; sp += lanes) {
-                const float* o = p.partial + (((size_t)b * p.nsplit + sp) * p.G + g) * 3;
-                Mom m; m.n = o[0]; m.mean = o[1]; m.m2 = o[2];
-                r = mom_combine(r, m);
+        if (g < p.G) {
+            // where this group's records live: its own column of `partial`, or `nrec` consecutive record groups of one source
+            const float* base = p.partial;
+            int recG = p.G, first = g, nrec = 1;
+            if (p.rec_G0) {
+                const int c0 = g * cpg;                       // first channel of the group in the concatenated tensor
+                if (c0 < p.C0) { recG = p.rec_G0; nrec = cpg / (p.C0 / recG); first = c0 / (p.C0 / recG); }
+                else { base = p.partial1; recG = p.rec_G1; nrec = cpg / (p.C1 / recG); first = (c0 - p.C0) / (p.C1 / recG); }
             }
+            for (int sp = part; sp < p.nsplit; sp += lanes)
+                for (int k = 0; k < nrec; ++k) {
+                    const float* o = base + (((size_t)b * p.nsplit + sp) * recG + first + k) * 3;
+                    Mom m; m.n = o[0]; m.mean = o[1]; m.m2 = o[2];
+                    r = mom_combine(r, m);
+                }
+        }
         sm[threadIdx.x] = r;
         __syncthreads();
         for (int off = lanes / 2; off > 0; off >>= 1) {
