@@ -249,13 +249,14 @@ cudaError_t launch_conv_grad_tiny(const ConvGradParams& p, bool weight, cudaStre
 }
 
 // ---- one CTA per sample (tensors of the 2-2-4 autoencoder are <= 6144 elements per sample): GroupNorm statistics, apply and
-// ---- SiLU in ONE kernel with the sample in registers (forward), reduce + apply in ONE kernel (backward).  256 % C == 0, so a
-// ---- thread's elements e = tid + 256*k all belong to channel tid % C: per-thread partials are per (channel, group).
-constexpr int SAMPLE_NE = 32;   // elements per thread at most (C*T <= 8192)
+// ---- SiLU in ONE kernel with the sample in registers (forward), reduce + apply in ONE kernel (backward).  SAMPLE_NT % C == 0, so a
+// ---- thread's elements e = tid + SAMPLE_NT*k all belong to channel tid % C: per-thread partials are per (channel, group).
+constexpr int SAMPLE_NT = 512;   // threads per sample CTA: 4 CTAs per SM, short phases
+constexpr int SAMPLE_NE = 16;   // elements per thread at most (C*T <= 8192)
 // Per-channel block totals of one value per thread (thread's channel = tid % C, C in {1,2,4,8} divides the warp size):
 // xor-shuffles over the lanes of equal channel, one row per warp in shared memory, then channel c's total in out[c].
-// All 256 threads call it; out[] is valid after the trailing __syncthreads().
-__device__ __forceinline__ void block_channel_sums(float v, int C, float (*rows)[8] /* [8 warps][8] */, float* out /* [8] */) {
+// All SAMPLE_NT threads call it; out[] is valid after the trailing __syncthreads().
+__device__ __forceinline__ void block_channel_sums(float v, int C, float (*rows)[8] /* [SAMPLE_NT/32 warps][8] */, float* out /* [8] */) {
     for (int o = 16; o >= C; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (lane < C) rows[warp][lane] = v;
@@ -263,7 +264,7 @@ __device__ __forceinline__ void block_channel_sums(float v, int C, float (*rows)
     if ((int)threadIdx.x < C) {
         float t = 0.f;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) t += rows[w][threadIdx.x];
+        for (int w = 0; w < SAMPLE_NT / 32; ++w) t += rows[w][threadIdx.x];
         out[threadIdx.x] = t;
     }
     __syncthreads();
@@ -273,11 +274,11 @@ __device__ __forceinline__ float group_of(const float* chs, int cpg, int g) {
     for (int c = g * cpg; c < (g + 1) * cpg; ++c) s += chs[c];
     return s;
 }
-__global__ void __launch_bounds__(256) gn_act_fwd_sample_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+__global__ void __launch_bounds__(SAMPLE_NT) gn_act_fwd_sample_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                                  const float* __restrict__ beta, float eps, float* __restrict__ a,
                                                                  float* __restrict__ mean_out, float* __restrict__ rstd_out, int C, int T,
                                                                  int G, int silu) {
-    __shared__ float rows[8][8], chs[8];
+    __shared__ float rows[SAMPLE_NT / 32][8], chs[8];
     const int b = blockIdx.x, n = C * T, cpg = C / G, ch = threadIdx.x % C, g = ch / cpg;
     const float* xb = x + (size_t)b * n;
     const float inv = 1.f / (float)(cpg * T);
@@ -285,7 +286,7 @@ __global__ void __launch_bounds__(256) gn_act_fwd_sample_kernel(const float* __r
     float s = 0.f;
 #pragma unroll
     for (int k = 0; k < SAMPLE_NE; ++k) {
-        const int e = threadIdx.x + 256 * k;
+        const int e = threadIdx.x + SAMPLE_NT * k;
         v[k] = e < n ? xb[e] : 0.f;
         s += v[k];
     }
@@ -295,7 +296,7 @@ __global__ void __launch_bounds__(256) gn_act_fwd_sample_kernel(const float* __r
     float q = 0.f;
 #pragma unroll
     for (int k = 0; k < SAMPLE_NE; ++k) {
-        const int e = threadIdx.x + 256 * k;
+        const int e = threadIdx.x + SAMPLE_NT * k;
         if (e < n) { const float d = v[k] - mu; q = fmaf(d, d, q); }
     }
     block_channel_sums(q, C, rows, chs);
@@ -308,7 +309,7 @@ __global__ void __launch_bounds__(256) gn_act_fwd_sample_kernel(const float* __r
     float* ab = a + (size_t)b * n;
 #pragma unroll
     for (int k = 0; k < SAMPLE_NE; ++k) {
-        const int e = threadIdx.x + 256 * k;
+        const int e = threadIdx.x + SAMPLE_NT * k;
         if (e < n) {
             float y = fmaf(sc, v[k], sh);
             if (silu) y = y * sigmoid_f(y);
@@ -317,8 +318,8 @@ __global__ void __launch_bounds__(256) gn_act_fwd_sample_kernel(const float* __r
     }
 }
 
-__global__ void __launch_bounds__(256) norm_act_bwd_sample_kernel(const NormGradParams p) {
-    __shared__ float rows[8][8], c1[8], c2[8];
+__global__ void __launch_bounds__(SAMPLE_NT) norm_act_bwd_sample_kernel(const NormGradParams p) {
+    __shared__ float rows[SAMPLE_NT / 32][8], c1[8], c2[8];
     const int b = blockIdx.x, C = p.C, n = C * p.T, cpg = C / p.G, ch = threadIdx.x % C, g = ch / cpg;
     const float mu = p.mean[(size_t)b * p.G + g], rs = p.rstd[(size_t)b * p.G + g], ga = p.gamma[ch], be = p.beta[ch];
     const float* xb = p.x + (size_t)b * n;
@@ -327,7 +328,7 @@ __global__ void __launch_bounds__(256) norm_act_bwd_sample_kernel(const NormGrad
     float s1 = 0.f, s2 = 0.f, dg = 0.f, dbv = 0.f;
 #pragma unroll
     for (int k = 0; k < SAMPLE_NE; ++k) {
-        const int e = threadIdx.x + 256 * k;
+        const int e = threadIdx.x + SAMPLE_NT * k;
         gq[k] = 0.f; xh[k] = 0.f;
         if (e < n) {
             xh[k] = (xb[e] - mu) * rs;
@@ -347,7 +348,7 @@ __global__ void __launch_bounds__(256) norm_act_bwd_sample_kernel(const NormGrad
     float* dxb = p.dx + (size_t)b * n;
 #pragma unroll
     for (int k = 0; k < SAMPLE_NE; ++k) {
-        const int e = threadIdx.x + 256 * k;
+        const int e = threadIdx.x + SAMPLE_NT * k;
         if (e < n) {
             const float r = rs * (gq[k] - m1 - xh[k] * m2);
             dxb[e] = p.accumulate ? dxb[e] + r : r;
@@ -360,7 +361,7 @@ __global__ void __launch_bounds__(256) norm_act_bwd_sample_kernel(const NormGrad
         atomicAdd(p.dbeta + threadIdx.x, c2[threadIdx.x]);
     }
 }
-bool norm_sample_ok(int C, int T, int G) { return C >= 1 && C <= 8 && 256 % C == 0 && G >= 1 && G <= 8 && C % G == 0 && (size_t)C * T <= 256 * SAMPLE_NE; }
+bool norm_sample_ok(int C, int T, int G) { return C >= 1 && C <= 8 && SAMPLE_NT % C == 0 && G >= 1 && G <= 8 && C % G == 0 && (size_t)C * T <= SAMPLE_NT * SAMPLE_NE; }
 
 // GroupNorm(+SiLU) backward, pass 1: per (sample, group) means of g = dv*gamma and g*xhat; per-channel dgamma / dbeta.
 //   v = xhat*gamma + beta,  a = silu?(v),  dv = da * silu'(v)
@@ -537,7 +538,7 @@ cudaError_t launch_conv_bwd_weight(const ConvGradParams& p, cudaStream_t st) {
 cudaError_t launch_norm_act_bwd(const NormGradParams& p, cudaStream_t st) {
     if (p.B <= 0) return cudaSuccess;
     if (norm_sample_ok(p.C, p.T, p.G)) {
-        norm_act_bwd_sample_kernel<<<p.B, 256, 0, st>>>(p);
+        norm_act_bwd_sample_kernel<<<p.B, SAMPLE_NT, 0, st>>>(p);
         g_launch_count += 1;
         return cudaGetLastError();
     }
@@ -556,7 +557,7 @@ cudaError_t launch_norm_act_bwd(const NormGradParams& p, cudaStream_t st) {
 cudaError_t launch_gn_act_fwd(const GnParams& p, float* a, int silu, cudaStream_t st) {
     if (p.B <= 0) return cudaSuccess;
     if (!p.src1 && norm_sample_ok(p.C0, p.T, p.G) && p.mean_out && p.rstd_out) {
-        gn_act_fwd_sample_kernel<<<p.B, 256, 0, st>>>(p.src0, p.gamma, p.beta, p.eps, a, p.mean_out, p.rstd_out, p.C0, p.T, p.G, silu);
+        gn_act_fwd_sample_kernel<<<p.B, SAMPLE_NT, 0, st>>>(p.src0, p.gamma, p.beta, p.eps, a, p.mean_out, p.rstd_out, p.C0, p.T, p.G, silu);
         g_launch_count += 1;
         return cudaGetLastError();
     }
