@@ -2133,13 +2133,12 @@ struct TrainRun {
                 p.dy = dy->second.first; p.a = op.in.p; p.w = t->P + op.ow; p.dw = t->G + op.ow; p.db = t->G + op.ob;
                 p.Cin = op.in.C; p.Cout = op.out.C; p.taps = op.taps; p.stride = op.stride; p.pad = op.pad; p.ups = op.ups;
                 p.Tin = op.in.T; p.Tc = op.ups ? op.in.T * 2 : op.in.T; p.Tout = op.out.T; p.B = B;
-                ck(launch_conv_bwd_weight(p, st));
                 if (op.in_needs_grad) {
                     auto& gi = slot(op.in);
                     p.da = gi.first; p.accumulate = gi.second;
-                    ck(launch_conv_bwd_data(p, st));
                     gi.second = true;
                 }
+                ck(launch_conv_bwd(p, st));
             } else if (op.kind == NORM) {
                 auto da = grads.find(op.out.p);
                 if (da == grads.end() || !da->second.second) continue;

@@ -172,6 +172,7 @@ struct ConvGradParams {   // y = conv(upsample?(a)): taps, stride, left pad; Tc 
 };
 cudaError_t launch_conv_bwd_data(const ConvGradParams& p, cudaStream_t st);
 cudaError_t launch_conv_bwd_weight(const ConvGradParams& p, cudaStream_t st);   // dw, db are accumulated (atomicAdd)
+cudaError_t launch_conv_bwd(const ConvGradParams& p, cudaStream_t st);          // both (da == null: weights only)
 struct NormGradParams {
     const float* da; const float* x; const float* mean; const float* rstd; const float* gamma; const float* beta;
     float* m12; float* dgamma; float* dbeta; float* dx;

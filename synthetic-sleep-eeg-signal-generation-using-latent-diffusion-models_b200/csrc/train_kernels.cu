@@ -223,6 +223,93 @@ __global__ void __launch_bounds__(256) conv_bwd_weight_tiny_kernel(const ConvGra
     }
 }
 
+// stride-1, same-length convs (30 of the 37 in the 2-2-4 autoencoder): weight gradient AND input gradient from one pass.
+// The thread of output position t also owns input position t: da[t] = sum_k dy[t + pad - k] . W[:, k, :], and its weight
+// contribution is dy[t] (x) a[t + k - pad]; the rows t-1 .. t+1 of dy and a are each read once per thread (L1 serves the
+// overlap between neighbours).
+template <int CI, int CO, int TAPS>
+__global__ void __launch_bounds__(256) conv_bwd_fused_tiny_kernel(const ConvGradParams p) {
+    constexpr int NW = CI * TAPS * CO, NV = NW + CO;
+    __shared__ float red[8][NV];
+    __shared__ float ws[NW];
+    for (int i = threadIdx.x; i < NW; i += blockDim.x) ws[i] = p.w[i];
+    __syncthreads();
+    float acc[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) acc[i] = 0.f;
+    const int T = p.Tout;   // == Tin == Tc
+    const size_t total = (size_t)p.B * T;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int t = (int)(idx % T);
+        float d[TAPS][CO], a[TAPS][CI];   // rows t + k - pad of dy and a (zero outside the sample)
+#pragma unroll
+        for (int k = 0; k < TAPS; ++k) {
+            const int u = t + k - p.pad;
+            if (u >= 0 && u < T) {
+                ld_row<CO>(p.dy + (idx + k - p.pad) * CO, d[k]);
+                ld_row<CI>(p.a + (idx + k - p.pad) * CI, a[k]);
+            } else {
+#pragma unroll
+                for (int c = 0; c < CO; ++c) d[k][c] = 0.f;
+#pragma unroll
+                for (int c = 0; c < CI; ++c) a[k][c] = 0.f;
+            }
+        }
+        constexpr int MID = TAPS / 2;      // row t itself (pad == TAPS / 2 for these convs)
+#pragma unroll
+        for (int co = 0; co < CO; ++co) acc[NW + co] += d[MID][co];
+#pragma unroll
+        for (int k = 0; k < TAPS; ++k)
+#pragma unroll
+            for (int c = 0; c < CI; ++c)
+#pragma unroll
+                for (int co = 0; co < CO; ++co) acc[(c * TAPS + k) * CO + co] = fmaf(d[MID][co], a[k][c], acc[(c * TAPS + k) * CO + co]);
+        if (p.da) {
+            float g[CI];
+#pragma unroll
+            for (int c = 0; c < CI; ++c) g[c] = 0.f;
+            // da[t] = sum_k dy[t + pad - k] W[ci][k][:]: output row t + pad - k is window row (TAPS - 1 - k)
+#pragma unroll
+            for (int k = 0; k < TAPS; ++k)
+#pragma unroll
+                for (int c = 0; c < CI; ++c)
+#pragma unroll
+                    for (int co = 0; co < CO; ++co) g[c] = fmaf(d[TAPS - 1 - k][co], ws[(c * TAPS + k) * CO + co], g[c]);
+            float* o = p.da + idx * CI;
+            if (p.accumulate) {
+                float old[CI];
+                ld_row<CI>(o, old);
+#pragma unroll
+                for (int c = 0; c < CI; ++c) g[c] += old[c];
+            }
+            st_row<CI>(o, g);
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        float v = acc[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) red[warp][i] = v;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < NV; i += blockDim.x) {
+        float v = 0.f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += red[w][i];
+        if (i < NW) atomicAdd(p.dw + i, v);
+        else if (p.db) atomicAdd(p.db + (i - NW), v);
+    }
+}
+template <int CI, int CO>
+cudaError_t launch_conv_bwd_fused_tiny_t(const ConvGradParams& p, cudaStream_t st) {
+    const size_t total = (size_t)p.B * p.Tout;
+    const unsigned blocks = (unsigned)std::min<size_t>((total + 255) / 256, 148 * 8);
+    if (p.taps == 3) conv_bwd_fused_tiny_kernel<CI, CO, 3><<<blocks, 256, 0, st>>>(p);
+    else conv_bwd_fused_tiny_kernel<CI, CO, 1><<<blocks, 256, 0, st>>>(p);
+    return cudaGetLastError();
+}
+
 template <int CI, int CO>
 cudaError_t launch_conv_grad_tiny_t(const ConvGradParams& p, bool weight, cudaStream_t st) {
     const size_t total = (size_t)p.B * (weight ? p.Tout : p.Tin);
@@ -499,6 +586,22 @@ cudaError_t launch_norm_act_fwd(const float* x, const float* scale, const float*
     norm_act_fwd_kernel<<<blocks_for(total), 256, 0, st>>>(x, scale, shift, a, C, T, silu, total);
     g_launch_count += 1;
     return cudaGetLastError();
+}
+
+// weight gradient and (if p.da) input gradient of one conv; one fused launch for the tiny stride-1 same-length case
+cudaError_t launch_conv_bwd(const ConvGradParams& p, cudaStream_t st) {
+    if (p.B <= 0 || p.Tout <= 0) return cudaSuccess;
+    if (conv_grad_tiny_ok(p) && p.stride == 1 && !p.ups && p.Tin == p.Tout && p.pad == p.taps / 2) {
+        g_launch_count += 1;
+#define EEGLDM_TINY(CI, CO) if (p.Cin == CI && p.Cout == CO) return launch_conv_bwd_fused_tiny_t<CI, CO>(p, st);
+        EEGLDM_TINY(1, 1) EEGLDM_TINY(1, 2) EEGLDM_TINY(1, 4) EEGLDM_TINY(2, 1) EEGLDM_TINY(2, 2) EEGLDM_TINY(2, 4)
+        EEGLDM_TINY(4, 1) EEGLDM_TINY(4, 2) EEGLDM_TINY(4, 4)
+#undef EEGLDM_TINY
+        return cudaErrorInvalidValue;
+    }
+    cudaError_t e = launch_conv_bwd_weight(p, st);
+    if (e == cudaSuccess && p.da) e = launch_conv_bwd_data(p, st);
+    return e;
 }
 
 cudaError_t launch_conv_bwd_data(const ConvGradParams& p, cudaStream_t st) {
