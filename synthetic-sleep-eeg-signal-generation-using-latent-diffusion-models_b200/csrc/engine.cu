@@ -2124,12 +2124,12 @@ struct TrainRun {
             if (op.kind == CONV) {
                 auto dy = grads.find(op.out.p);
                 if (dy == grads.end() || !dy->second.second) continue;   // output unused by the loss
-                if (op.has_res) {
+                ConvGradParams p{};
+                if (op.has_res) {   // identity residual: its gradient slot receives dy in the same launch
                     auto& gr = slot(op.res);
-                    ck(launch_axpy(dy->second.first, gr.first, 1.f, gr.second, numel(op.res), st));
+                    p.dres = gr.first; p.dres_accumulate = gr.second;
                     gr.second = true;
                 }
-                ConvGradParams p{};
                 p.dy = dy->second.first; p.a = op.in.p; p.w = t->P + op.ow; p.dw = t->G + op.ow; p.db = t->G + op.ob;
                 p.Cin = op.in.C; p.Cout = op.out.C; p.taps = op.taps; p.stride = op.stride; p.pad = op.pad; p.ups = op.ups;
                 p.Tin = op.in.T; p.Tc = op.ups ? op.in.T * 2 : op.in.T; p.Tout = op.out.T; p.B = B;

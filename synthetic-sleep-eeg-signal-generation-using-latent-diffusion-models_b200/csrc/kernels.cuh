@@ -169,6 +169,8 @@ struct ConvGradParams {   // y = conv(upsample?(a)): taps, stride, left pad; Tc 
     const float* dy; const float* a; const float* w;   // w: SIMT image [(ci*taps + k)][Cout]
     float* da; float* dw; float* db;
     int Cin, Cout, taps, stride, pad, ups, Tin, Tc, Tout, B, accumulate;
+    float* dres;           // optional: gradient slot of the conv's identity-residual input, dres (+)= dy (launch_conv_bwd only)
+    int dres_accumulate;
 };
 cudaError_t launch_conv_bwd_data(const ConvGradParams& p, cudaStream_t st);
 cudaError_t launch_conv_bwd_weight(const ConvGradParams& p, cudaStream_t st);   // dw, db are accumulated (atomicAdd)

@@ -258,6 +258,18 @@ __global__ void __launch_bounds__(256) conv_bwd_fused_tiny_kernel(const ConvGrad
         constexpr int MID = TAPS / 2;      // row t itself (pad == TAPS / 2 for these convs)
 #pragma unroll
         for (int co = 0; co < CO; ++co) acc[NW + co] += d[MID][co];
+        if (p.dres) {                      // y = conv(a) + res  ->  dres (+)= dy
+            float g[CO];
+            if (p.dres_accumulate) {
+                ld_row<CO>(p.dres + idx * CO, g);
+#pragma unroll
+                for (int co = 0; co < CO; ++co) g[co] += d[MID][co];
+            } else {
+#pragma unroll
+                for (int co = 0; co < CO; ++co) g[co] = d[MID][co];
+            }
+            st_row<CO>(p.dres + idx * CO, g);
+        }
 #pragma unroll
         for (int k = 0; k < TAPS; ++k)
 #pragma unroll
@@ -599,7 +611,9 @@ cudaError_t launch_conv_bwd(const ConvGradParams& p, cudaStream_t st) {
 #undef EEGLDM_TINY
         return cudaErrorInvalidValue;
     }
-    cudaError_t e = launch_conv_bwd_weight(p, st);
+    cudaError_t e = cudaSuccess;
+    if (p.dres) e = launch_axpy(p.dy, p.dres, 1.f, p.dres_accumulate, (size_t)p.B * p.Tout * p.Cout, st);
+    if (e == cudaSuccess) e = launch_conv_bwd_weight(p, st);
     if (e == cudaSuccess && p.da) e = launch_conv_bwd_data(p, st);
     return e;
 }
