@@ -768,7 +768,8 @@ cudaError_t launch_conv_tc(const TcConvParams& p, bool x3, cudaStream_t st) {
     if (p.bn != 128 && p.bn != 256) return cudaErrorInvalidValue;
     cudaError_t e;
 #define EEGLDM_TC(X3, BN)                                                                         \
-    (p.direct ? launch_conv_tc_t<X3, BN, 2, false, true>(p, num_sms, st)                            \
+    (p.direct ? (g_conv_tc_cluster == 1 ? launch_conv_tc_t<X3, BN, 1, false, true>(p, num_sms, st)   \
+                                        : launch_conv_tc_t<X3, BN, 2, false, true>(p, num_sms, st))  \
      : g_conv_tc_pair ? launch_conv_tc_t<X3, BN, 2, true>(p, num_sms, st)                           \
      : g_conv_tc_cluster == 4 ? launch_conv_tc_t<X3, BN, 4, false>(p, num_sms, st)                 \
      : g_conv_tc_cluster == 2 ? launch_conv_tc_t<X3, BN, 2, false>(p, num_sms, st) : launch_conv_tc_t<X3, BN, 1, false>(p, num_sms, st))

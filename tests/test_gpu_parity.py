@@ -217,6 +217,24 @@ def test_tensor_pipe_vs_simt_odd_shapes(built_lib, cuda_device, B, T):
     torch.testing.assert_close(y16, y32, rtol=RTOL, atol=ATOL)
 
 
+def test_large_batch_rows_match_small_batch(built_lib, cuda_device):
+    """Bench-scale batch through the fused sampling call (B = 3000: 2.3e9 activation elements at level 0, beyond 2^31): finite,
+    and the last rows equal the same rows sampled as a small batch bit for bit (64-bit offsets, persistent tile walks with
+    thousands of tiles per CTA)."""
+    import eegldm
+    ucfg, acfg = ou.full_cfg(), oa.full_cfg()
+    unet = _unet(ucfg, ou.make_unet_state_dict(ucfg, 0), cuda_device, "f16x3")
+    aekl = _aekl(acfg, oa.make_aekl_state_dict(acfg, 42), cuda_device)
+    sched = eegldm.DDIMScheduler(**SAMPLER_DEFAULTS)
+    sched.set_timesteps(2)
+    B = 3000
+    noise = torch.randn(B, 1, 768, generator=torch.Generator().manual_seed(3)).to(cuda_device)
+    y = eegldm.ddim_sample(unet, sched, noise, 2, aekl)
+    assert y.shape == (B, 1, 3072) and torch.isfinite(y).all()
+    tail = eegldm.ddim_sample(unet, sched, noise[B - 77:], 2, aekl)
+    assert torch.equal(y[B - 77:], tail)
+
+
 @pytest.mark.parametrize("math", MATH)
 def test_raw_signal_dm_variant(built_lib, cuda_device, math):
     """the raw-signal diffusion model (config_dm.yaml: the same UNet on [B,1,3072], self-attention at T = 768)
