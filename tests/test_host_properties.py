@@ -19,7 +19,7 @@ def _shard_range(n, rank, world):
     return shard_range(n, rank, world)
 
 
-@settings(max_examples=200, deadline=None)
+@settings(max_examples=200, deadline=None, derandomize=True)
 @given(n=st.integers(0, 20000), world=st.integers(1, 16))
 def test_shard_range_is_a_contiguous_balanced_partition(n, world):
     parts = [_shard_range(n, r, world) for r in range(world)]
@@ -30,7 +30,7 @@ def test_shard_range_is_a_contiguous_balanced_partition(n, world):
     assert max(sizes) - min(sizes) <= 1 and sizes == sorted(sizes, reverse=True)   # balanced, the extra rows on the first ranks
 
 
-@settings(max_examples=60, deadline=None)
+@settings(max_examples=60, deadline=None, derandomize=True)
 @given(n_steps=st.sampled_from([1, 2, 4, 10, 20, 25, 50, 100, 200, 250, 1000]),
        pred=st.sampled_from(["v_prediction", "epsilon"]),
        schedule=st.sampled_from(["scaled_linear_beta", "linear_beta"]),
