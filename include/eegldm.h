@@ -124,6 +124,15 @@ int eegldm_unet_set_math(eegldm_unet* h, eegldm_math mode);
  *   float, as the reference converts with .float() (unet.py:28). */
 int eegldm_unet_forward(eegldm_unet* h, const float* x_dev, const float* timesteps_host, int nt, float* out_dev,
                         int B, int T, void* stream);
+/* Same with DEVICE-resident timesteps (fp32, nt values): no host round trip.  The reference's training loop draws the
+ * timesteps on the GPU (src/training/training.py:420-430) and its sampler passes a CUDA tensor (sample_trials.py:157-159). */
+int eegldm_unet_forward_devt(eegldm_unet* h, const float* x_dev, const float* timesteps_dev, int nt, float* out_dev,
+                             int B, int T, void* stream);
+/* F16X3_TC operand-range guard.  Every kernel that splits fp32 values into fp16 hi/lo raises a device flag when a value has
+ * |x| >= 65504 or is NaN (the split would yield inf/NaN: the output is then invalid).  This call synchronises with the
+ * device, returns the flag in *overflow_out and clears it.  eegldm_ddim_sample_host checks it itself and fails with
+ * EEGLDM_ERR_INVALID; weights outside the range keep their layer on the fp32 SIMT kernel at finalize time. */
+int eegldm_unet_range_status(eegldm_unet* h, int* overflow_out);
 
 /* ------------------------------------------------------------------------------------------------
  * Autoencoder: replaces generative.networks.nets.AutoencoderKL as constructed at
@@ -239,6 +248,12 @@ int eegldm_test_qkv_attention(const float* x_dev, const float* w_host, const flo
  * data of the given shape; debug 0 = real kernel, 1 = operand copies skipped, 2 = MMAs skipped (timing experiments). */
 int eegldm_bench_conv(int B, int T, int Cin, int Cout, int k, int with_res, int math, int debug, int reps, float* ms_out,
                       void* stream);
+/* Same, followed by one launch with per-CTA cycle counters: timeline_out[16] receives, averaged over the CTAs that ran,
+ * {0 total cycles, 1 MMA warp waiting for a free accumulator, 2 ... for an activation stage, 3 ... for a weight stage,
+ *  4 epilogue waiting for a full accumulator, 5 epilogue busy, 6 producer waiting for a free stage, 7 producer busy,
+ *  8 loader waiting for a free weight stage, 9 tiles per CTA, ..., 15 CTAs}.  tools/conv_timeline.py */
+int eegldm_bench_conv_timeline(int B, int T, int Cin, int Cout, int k, int with_res, int math, int debug, int reps, float* ms_out,
+                               double* timeline_out, void* stream);
 
 /* Test hook: ONE attention launch, QKVAttentionLegacy.forward (unet.py:107-125), on channels-last
  * qkv [B][T][H*3*ch] (legacy head layout) -> out [B][T][H*ch].  Synchronises the stream. */

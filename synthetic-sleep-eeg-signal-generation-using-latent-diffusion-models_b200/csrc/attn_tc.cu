@@ -36,7 +36,8 @@ __host__ __device__ inline int attn_stages(int T) {
 
 // ------------------------------------------------------------------------------------------------ qkv split
 // one thread per (sample, head, q|k|v, 8-channel chunk, position); position fastest so that 8 lanes fill a 128-byte line
-__global__ void qkv_split_kernel(const float* __restrict__ qkv, uint8_t* __restrict__ dst, int T, int H, int ch, size_t total) {
+__global__ void qkv_split_kernel(const float* __restrict__ qkv, uint8_t* __restrict__ dst, int T, int H, int ch, size_t total,
+                                 int* __restrict__ range_flag) {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
     const int t = (int)(idx % T);
@@ -50,6 +51,12 @@ __global__ void qkv_split_kernel(const float* __restrict__ qkv, uint8_t* __restr
     const float4 x0 = __ldg(reinterpret_cast<const float4*>(src)), x1 = __ldg(reinterpret_cast<const float4*>(src + 4));
     const float v[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
     uint4 hi, lo;
+    if (range_flag) {   // f16x3 operand range (|x| < 65504, include/eegldm.h); inf and NaN compare above every finite magnitude
+        uint32_t m = 0;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) m = max(m, __float_as_uint(v[e]) & 0x7FFFFFFFu);
+        if (m >= 0x477FE000u) atomicOr(range_flag, 1);
+    }
     split8_f16(v, hi, lo);
     const size_t plane = (size_t)4 * ch * T;                       // bytes of one of q / k / v (hi + lo)
     uint8_t* base = dst + ((size_t)b * H + h) * 3 * plane + (size_t)which * plane;
@@ -371,10 +378,10 @@ bool attn_direct_eligible(int T, int ch) { return attn_tc_eligible(T, ch) && (12
 bool attn_tc_eligible(int T, int ch) { return T >= 32 && T <= 256 && T % 32 == 0 && ch >= 128 && ch % 128 == 0; }
 size_t attn_qkv16_bytes(int B, int T, int H, int ch) { return (size_t)B * H * 12 * ch * T; }
 
-cudaError_t launch_qkv_split(const float* qkv, uint8_t* dst, int B, int T, int H, int ch, cudaStream_t st) {
+cudaError_t launch_qkv_split(const float* qkv, uint8_t* dst, int B, int T, int H, int ch, cudaStream_t st, int* range_flag) {
     const size_t total = (size_t)B * H * 3 * (ch / 8) * T;
     if (!total) return cudaSuccess;
-    qkv_split_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(qkv, dst, T, H, ch, total);
+    qkv_split_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(qkv, dst, T, H, ch, total, range_flag);
     g_launch_count += 1;
     return cudaGetLastError();
 }

@@ -26,9 +26,11 @@
 //     (12.5 % halo overhead instead of 3 copies).  Segments may belong to different samples; halos at sample
 //     edges are zero (the conv's padding).  U is stored [m_tile][k-step][hi|lo][kc][slot][segment][8 ch], i.e. one
 //     contiguous 18 KB block per (tile, k-step): ONE bulk copy per stage.
-//   * persistent, warp-specialised: one CTA per SM; warps 0-3 epilogue (TMEM -> registers -> global), warp 4 loader
-//     (one thread), warp 5 MMA issuer (one thread); 4 x 18 KB activation + 8 x 16 KB weight stages (~205 KB smem);
-//     two TMEM accumulator sets (512 columns) so the epilogue of tile i overlaps the mainloop of tile i+1.
+//   * persistent, warp-specialised: one CTA per SM; warps 0-3 epilogue (TMEM -> registers -> global), then (fused-producer
+//     form) six producer warps, one loader warp, one MMA warp.  Tiles are 128 positions x 128 or 256 output channels
+//     (conv_tc_bn); rings: 4 x 18 KB activation + 128 KB of weight stages (pre-pass form) or 5 x 18 KB + 96 KB (fused-producer
+//     and CTA-pair forms), see ring_na / ring_b_bytes.  N = 128: two TMEM accumulator sets, the epilogue of tile i overlaps the
+//     mainloop of tile i+1; N = 256 in f16x3 fills all 512 TMEM columns (one set).
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
@@ -75,6 +77,15 @@ __device__ __forceinline__ float act(float x, float a, float s, int silu) {
     return silu ? silu_fast(v) : v;
 }
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+// f16x3 operand range: hi = fp16(v) is inf from 65520 up and lo = (v - inf) * 2^11 is NaN -- the split is only meaningful for
+// |v| < 65504 (include/eegldm.h).  true when any of the 8 values is outside (or NaN).
+__device__ __forceinline__ bool out_of_f16_range(const float (&v)[8]) {
+    // magnitude bits as unsigned integers order like the magnitudes, with inf and every NaN above all finite values
+    uint32_t m = 0;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) m = max(m, __float_as_uint(v[e]) & 0x7FFFFFFFu);
+    return m >= 0x477FE000u;   // 65504.0f
+}
 
 // ------------------------------------------------------------------------------------------------ act_split
 // grid (nks, n_mtiles), block 192.  Item (q, c, r): slot q of segment r, 8-channel chunk c of k-step blockIdx.x.
@@ -87,6 +98,7 @@ __global__ void __launch_bounds__(SPLIT_THREADS) act_split_kernel(const ActSplit
     uint8_t* img = p.U + ((size_t)m_tile * p.nks + ks) * A_STAGE;
     uint8_t* img2 = p.U_raw ? p.U_raw + ((size_t)m_tile * p.nks + ks) * A_STAGE : nullptr;   // raw (no affine / SiLU) twin
     const int Cin = p.C0 + p.C1;
+    bool bad = false;
 #pragma unroll
     for (int j = 0; j < N_ITEMS / SPLIT_THREADS; ++j) {
         const int idx = threadIdx.x + SPLIT_THREADS * j;
@@ -135,18 +147,21 @@ __global__ void __launch_bounds__(SPLIT_THREADS) act_split_kernel(const ActSplit
         const uint32_t off = (uint32_t)(c * A_LBO + q * A_SBO + r * 16);
         uint4 hi, lo;
         if (X3) {
+            bad |= out_of_f16_range(v);
             split8_f16(v, hi, lo);
             *reinterpret_cast<uint4*>(img + A_TILE + off) = lo;
         } else round8_bf16(v, hi);
         *reinterpret_cast<uint4*>(img + off) = hi;
         if (img2) {
             if (X3) {
+                bad |= out_of_f16_range(vr);
                 split8_f16(vr, hi, lo);
                 *reinterpret_cast<uint4*>(img2 + A_TILE + off) = lo;
             } else round8_bf16(vr, hi);
             *reinterpret_cast<uint4*>(img2 + off) = hi;
         }
     }
+    if (X3 && bad && p.range_flag) atomicOr(p.range_flag, 1);
 }
 
 // ------------------------------------------------------------------------------------------------ conv_tc
@@ -230,6 +245,12 @@ __global__ void __launch_bounds__(DIRECT ? 384 : NUM_THREADS, 1) conv_tc_kernel(
     if (CL > 1) cluster_sync_all();   // peers' mbarriers are initialised before anything is multicast to them
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    // eegldm_bench_conv_timeline: cycle counters per warp role (one writer each: epilogue warp 0, producer warp 4, loader, MMA warp)
+    const bool tl = p.timeline != nullptr;
+    unsigned long long* tlo = tl ? p.timeline + (size_t)blockIdx.x * TC_TL_N : nullptr;
+    long long tl_a = 0, tl_b = 0, tl_c = 0;
+    const long long tl_start = tl ? clock64() : 0;
+#define TL_WAIT(acc, stmt) do { if (tl) { const long long t0__ = clock64(); stmt; acc += clock64() - t0__; } else { stmt; } } while (0)
     if (DIRECT) {   // warpgroup 0 = epilogue, warpgroups 1-2 = producers + loader + MMA issuer
         if (warp < 4) asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
         else asm volatile("setmaxnreg.dec.sync.aligned.u32 136;");
@@ -294,8 +315,9 @@ __global__ void __launch_bounds__(DIRECT ? 384 : NUM_THREADS, 1) conv_tc_kernel(
                 }
                 load_res(0, Rn);
             }
-            mbar_wait(barAccFull + 8 * as, use & 1);
+            TL_WAIT(tl_a, mbar_wait(barAccFull + 8 * as, use & 1));
             tc_fence_after();
+            const long long tl_e0 = tl ? clock64() : 0;
             const uint32_t acc_addr = tmem + ((uint32_t)(warp * 32) << 16) + as * ACC_COLS;
 #pragma unroll 1
             for (int cb = 0; cb < BN; cb += 32) {
@@ -416,6 +438,7 @@ __global__ void __launch_bounds__(DIRECT ? 384 : NUM_THREADS, 1) conv_tc_kernel(
             tc_fence_before();
             if (PAIR) mbar_arrive_cluster(barAccEmpty + 8 * as, 0);   // the leader's MMA warp owns both CTAs' accumulators
             else mbar_arrive(barAccEmpty + 8 * as);                   // this accumulator set may be overwritten
+            if (tl) tl_b += clock64() - tl_e0;
             if (p.gn_partial) {
                 // the 4 epilogue warps hold the 4 position-quarters of every segment: combine them and write one
                 // (count, mean, M2) record per (sample, 16-position segment, group) for gn_finalize
@@ -435,9 +458,11 @@ __global__ void __launch_bounds__(DIRECT ? 384 : NUM_THREADS, 1) conv_tc_kernel(
                 asm volatile("bar.sync 1, 128;" ::: "memory");   // the stats buffer is rewritten by the next tile
             }
         }
+        if (tl && tid == 0) { tlo[TC_TL_EPI_WAIT] = tl_a; tlo[TC_TL_EPI_BUSY] = tl_b; tlo[TC_TL_TILES] = lt; tlo[TC_TL_TOTAL] = clock64() - tl_start; }
     } else if (DIRECT && warp < W_LOAD) {
         // ================================================================ activation producers (192 threads)
         const int pt = tid - 128;
+        bool bad = false;
         // act_split_kernel's mapping: item idx = pt + 192*j -> segment r = idx & 7, 8-channel chunk c = (idx >> 3) & 3, slot
         // q = idx >> 5.  192 = 6 * 32, so the three items of a thread share r and c (one sample, one channel chunk -> ONE
         // set of GroupNorm scale / shift values per k-step) and differ in the slot only: q = pt/32 + 6*j.
@@ -489,7 +514,7 @@ __global__ void __launch_bounds__(DIRECT ? 384 : NUM_THREADS, 1) conv_tc_kernel(
             const float a[8] = {C.a[0].x, C.a[0].y, C.a[0].z, C.a[0].w, C.a[1].x, C.a[1].y, C.a[1].z, C.a[1].w};
             const float sh[8] = {C.s[0].x, C.s[0].y, C.s[0].z, C.s[0].w, C.s[1].x, C.s[1].y, C.s[1].z, C.s[1].w};
             const int sa = ia % NA;
-            mbar_wait(barAempty + 8 * sa, ((ia / NA) & 1) ^ 1);
+            TL_WAIT(tl_a, mbar_wait(barAempty + 8 * sa, ((ia / NA) & 1) ^ 1));
             uint8_t* img = smem + sa * A_STAGE;
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
@@ -510,6 +535,7 @@ __global__ void __launch_bounds__(DIRECT ? 384 : NUM_THREADS, 1) conv_tc_kernel(
                     lo = make_uint4(__float_as_uint(v[4]), __float_as_uint(v[5]), __float_as_uint(v[6]), __float_as_uint(v[7]));
                     if (X3 && !(p.debug & 64)) *reinterpret_cast<uint4*>(img + A_TILE + off) = lo;
                 } else if (X3) {
+                    bad |= out_of_f16_range(v);
                     split8_f16(v, hi, lo);
                     if (!(p.debug & 64)) *reinterpret_cast<uint4*>(img + A_TILE + off) = lo;
                 } else round8_bf16(v, hi);
@@ -520,6 +546,8 @@ __global__ void __launch_bounds__(DIRECT ? 384 : NUM_THREADS, 1) conv_tc_kernel(
             mbar_arrive(barAfull + 8 * sa);
             ++ia;
         }
+        if (X3 && bad && p.range_flag) atomicOr(p.range_flag, 1);
+        if (tl && pt == 0) { tlo[TC_TL_PROD_WAIT] = tl_a; tlo[TC_TL_PROD_BUSY] = clock64() - tl_start - tl_a; }
     } else if (warp == W_LOAD) {
         // ================================================================ loader (whole warp runs the loop, one elected lane issues)
         {
@@ -549,7 +577,7 @@ __global__ void __launch_bounds__(DIRECT ? 384 : NUM_THREADS, 1) conv_tc_kernel(
                     const uint8_t* wsrc = sg.w + (size_t)kl * sg.taps * 2 * whalf + (size_t)n_tile * BN * (BK * 2);
                     for (int tap = 0; tap < sg.taps; ++tap, ++ib) {
                         const int sb = ib % NB;
-                        mbar_wait(barBempty + 8 * sb, ((ib / NB) & 1) ^ 1);   // all consumers of this stage are done
+                        TL_WAIT(tl_a, mbar_wait(barBempty + 8 * sb, ((ib / NB) & 1) ^ 1));   // all consumers of this stage are done
                         if (elect_one()) {
                           if (p.debug & 1) mbar_arrive(barBfull + 8 * sb);
                           else {
@@ -573,6 +601,7 @@ __global__ void __launch_bounds__(DIRECT ? 384 : NUM_THREADS, 1) conv_tc_kernel(
                     }
                 }
             }
+            if (tl && lane == 0) tlo[TC_TL_LOAD_WAIT_B] = tl_a;
         }
     } else if (PAIR && !leader) {
         // ================================================================ pair peer: relay "stage landed" to the leader's barriers
@@ -600,7 +629,7 @@ __global__ void __launch_bounds__(DIRECT ? 384 : NUM_THREADS, 1) conv_tc_kernel(
                 const int as = lt % NSETS, use = lt / NSETS;
                 const uint32_t d0 = tmem + as * ACC_COLS, d1 = d0 + BN;
                 if (PAIR) mbar_wait_cluster(barAccEmpty + 8 * as, (use & 1) ^ 1);   // both CTAs' epilogues have drained this set
-                else mbar_wait(barAccEmpty + 8 * as, (use & 1) ^ 1);
+                else TL_WAIT(tl_a, mbar_wait(barAccEmpty + 8 * as, (use & 1) ^ 1));
                 tc_fence_after();
                 uint32_t accum = 0, accum2 = 0;
                 const bool skip_mma = (p.debug & 2) != 0;   // timing experiment: operand traffic only
@@ -613,12 +642,12 @@ __global__ void __launch_bounds__(DIRECT ? 384 : NUM_THREADS, 1) conv_tc_kernel(
                     const int sa = ia % NA;
                     const int taps = ks < nks0 ? p.seg[0].taps : p.seg[1].taps;
                     if (PAIR) mbar_wait_cluster(barAfull + 8 * sa, (ia / NA) & 1);
-                    else mbar_wait(barAfull + 8 * sa, (ia / NA) & 1);
+                    else TL_WAIT(tl_b, mbar_wait(barAfull + 8 * sa, (ia / NA) & 1));
                     tc_fence_after();
                     for (int tap = 0; tap < taps; ++tap, ++ib) {
                         const int sb = ib % NB;
                         if (PAIR) mbar_wait_cluster(barBfull + 8 * sb, (ib / NB) & 1);
-                        else mbar_wait(barBfull + 8 * sb, (ib / NB) & 1);
+                        else TL_WAIT(tl_c, mbar_wait(barBfull + 8 * sb, (ib / NB) & 1));
                         tc_fence_after();
                         const int shift = taps == 3 ? tap : 1;   // slot of the first row: position - 1 + tap
                         const uint32_t a_hi = sA + sa * A_STAGE + shift * A_SBO, a_lo = a_hi + A_TILE;
@@ -652,8 +681,12 @@ __global__ void __launch_bounds__(DIRECT ? 384 : NUM_THREADS, 1) conv_tc_kernel(
                     }
                 }
             }
+            if (tl && lane == 0) {
+                tlo[TC_TL_MMA_WAIT_ACC] = tl_a; tlo[TC_TL_MMA_WAIT_A] = tl_b; tlo[TC_TL_MMA_WAIT_B] = tl_c;
+            }
         }
     }
+#undef TL_WAIT
     tc_fence_before();
     __syncthreads();
     if (CL > 1) cluster_sync_all();   // no CTA leaves while a peer may still multicast into its shared memory

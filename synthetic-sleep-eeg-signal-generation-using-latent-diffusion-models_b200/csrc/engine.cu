@@ -204,6 +204,7 @@ struct Builder {
     int n_kernels = 0;
     int B = 0;
     int math = EEGLDM_MATH_FP32_SIMT;
+    int* range_flag = nullptr;   // device word the f16x3 operand producers raise when a value is outside the fp16 range
     size_t peak = 0;
     Act act(int C, int T) {
         Act a;
@@ -327,6 +328,7 @@ struct eegldm_unet {
     float* coef_table = nullptr; size_t coef_table_cap = 0;  // ddim: [n_steps][2]
     float* coef_cur = nullptr;                             // [2]
     int* step_ctr = nullptr;
+    int* range_flag = nullptr;                             // f16x3: raised by operand producers on |x| >= 65504 / NaN
     cudaStream_t cap_stream = nullptr;                     // private stream used only for graph capture
     cudaStream_t cap_stream2 = nullptr;                    // second capture stream: the other batch half of a two-lane step
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -343,7 +345,8 @@ struct eegldm_unet {
         if (ev_fork) cudaEventDestroy(ev_fork);
         if (ev_join) cudaEventDestroy(ev_join);
         for (void* p : {(void*)arena, (void*)temb_fwd, (void*)tscratch, (void*)temb_step, (void*)temb_table,
-                        (void*)coef_table, (void*)coef_cur, (void*)step_ctr, (void*)xbuf, (void*)xtmp, (void*)host_in, (void*)host_out})
+                        (void*)coef_table, (void*)coef_cur, (void*)step_ctr, (void*)range_flag, (void*)xbuf, (void*)xtmp, (void*)host_in,
+                        (void*)host_out})
             if (p) cudaFree(p);
     }
     void drop_graphs() {
@@ -516,6 +519,10 @@ int finalize_unet(eegldm_unet* h) {
     // tcgen05 images: bf16 hi/lo split, packed as shared-memory stage images (conv_tc.cu)
     auto tc_pack = [&](const std::string& name, int cout, int cin, int k, int stages, size_t& off, bool& has) {
         has = h->math != EEGLDM_MATH_FP32_SIMT && conv_tc_eligible(cin, 0, cout, 16, k, 1);
+        if (has && h->math == EEGLDM_MATH_F16X3_TC) {
+            // f16x3 operand range: a weight with |w| >= 65504 (or NaN) cannot be split; that layer stays on the fp32 SIMT kernel
+            for (float v : ps.get(name)) if (!(std::fabs(v) < 65504.f)) { has = false; break; }
+        }
         if (!has) return;
         std::vector<uint16_t> img;
         pack_conv_tc(ps.get(name).data(), cout, cin, k, h->math == EEGLDM_MATH_F16X3_TC, img);
@@ -611,6 +618,8 @@ int finalize_unet(eegldm_unet* h) {
     else { cudaFree(h->temb_step); h->temb_step = nullptr; CU(cudaMalloc((void**)&h->temb_step, (size_t)std::max(h->emb_total, 1) * sizeof(float))); }
     if (!h->coef_cur) CU(cudaMalloc((void**)&h->coef_cur, 2 * sizeof(float)));
     if (!h->step_ctr) CU(cudaMalloc((void**)&h->step_ctr, sizeof(int)));
+    if (!h->range_flag) CU(cudaMalloc((void**)&h->range_flag, sizeof(int)));
+    CU(cudaMemset(h->range_flag, 0, sizeof(int)));
     h->finalized = true;
     return EEGLDM_OK;
 }
@@ -692,13 +701,14 @@ void plan_conv(Builder& bd, ConvParams p, const uint8_t* tw0 = nullptr, const ui
                 uraw = reinterpret_cast<uint8_t*>(bd.ptr(share->raw));
             }
             ActSplitParams sp{a.src0, a.src1, a.C0, a.C1, a.scale, a.shift, a.silu, a.resample, a.Tin, p.Tout, q.nsegs16, cin / TC_BK,
-                              reinterpret_cast<uint8_t*>(bd.ptr(ubuf[s])), uraw};
+                              reinterpret_cast<uint8_t*>(bd.ptr(ubuf[s])), uraw, bd.range_flag};
             bd.add([sp, x3](cudaStream_t st) { return launch_act_split(sp, x3, st); }, 1, OP_SPLIT, 0.0,
                    4.0 * p.B * (double)a.Tin * cin + (double)ub * (x3 ? 1.0 : 0.5) * (uraw ? 2.0 : 1.0));
             q.seg[s] = TcSeg{sp.U, s == 0 ? tw0 : tw1, a.taps, cin / TC_BK};
         }
         q.bias = p.bias; q.temb = p.temb; q.temb_stride = p.temb_stride; q.res = p.res; q.res_mode = p.res_mode; q.res_Tin = p.res_Tin;
         q.out = p.out;
+        q.range_flag = bd.range_flag;
         if (qkv) { q.qkv16 = qkv->dst; q.qkv_H = qkv->H; q.qkv_ch = qkv->ch; }
         if (out_act && g_conv_gn_fused && conv_tc_gn_ok(p.Cout, gn_G)) {
             out_act->gn_nsplit = p.Tout / 16; out_act->gn_G = gn_G;
@@ -782,7 +792,8 @@ Act plan_attn(Builder& bd, const ULayer& l, const Act& x) {
         const int B = bd.B, T = x.T, H = l.heads;
         if (!fuse_qkv && !attn_direct) {
             const float* qsrc = bd.ptr(qkv);
-            bd.add([=](cudaStream_t st) { return launch_qkv_split(qsrc, qdst, B, T, H, hch, st); }, 1, OP_SPLIT, 0.0,
+            int* rf = x3 ? bd.range_flag : nullptr;
+            bd.add([=](cudaStream_t st) { return launch_qkv_split(qsrc, qdst, B, T, H, hch, st, rf); }, 1, OP_SPLIT, 0.0,
                    8.0 * B * (double)T * 3 * l.ch);
         }
         AttnTcParams tp{qdst, fuse_proj ? nullptr : bd.wptr(a), T, H, hch, B, 1.4426950408889634f / sqrtf((float)hch),
@@ -902,7 +913,7 @@ int build_unet_plan(eegldm_unet* h, int B, int T, const UNetIO& io, Builder& out
         r = ensure(h->arena, h->arena_cap, sizing.peak);
         if (r) return r;
     }
-    out.B = B; out.base = h->arena; out.math = h->math;
+    out.B = B; out.base = h->arena; out.math = h->math; out.range_flag = h->range_flag;
     return plan_unet_body(h, out, T, io);
 }
 
@@ -922,7 +933,7 @@ int build_unet_plan_lanes(eegldm_unet* h, int B, int T, const UNetIO& io, Builde
         r = ensure(h->arena, h->arena_cap, 2 * region);
         if (r) return r;
     }
-    lane0.B = B0; lane0.base = h->arena; lane0.math = h->math;
+    lane0.B = B0; lane0.base = h->arena; lane0.math = h->math; lane0.range_flag = h->range_flag;
     r = plan_unet_body(h, lane0, T, io);
     if (r) return r;
     UNetIO io1 = io;
@@ -930,7 +941,7 @@ int build_unet_plan_lanes(eegldm_unet* h, int B, int T, const UNetIO& io, Builde
     io1.x = io.x + xo; io1.out = io.out + oo;
     if (io.ddim_x) io1.ddim_x = io.ddim_x + oo;
     if (io.temb_stride) io1.temb = io.temb + (size_t)B0 * io.temb_stride;
-    lane1.B = B1; lane1.base = h->arena + region; lane1.math = h->math;
+    lane1.B = B1; lane1.base = h->arena + region; lane1.math = h->math; lane1.range_flag = h->range_flag;
     return plan_unet_body(h, lane1, T, io1);
 }
 
@@ -971,16 +982,20 @@ void timestep_embedding_host(const float* t, int nt, int dim, float* out) {
 }
 
 // time MLP + every ResBlock's emb projection: temb_out[nt][emb_total]   (unet.py:372-377, 277-285)
-int run_time_mlp(eegldm_unet* h, const float* t_host, int nt, float* temb_out, cudaStream_t st) {
+// t_host: host timesteps (embedding computed on the host), or null with t_dev: device timesteps (embedding kernel, no host
+// round trip -- the reference's training loop passes a CUDA tensor, training.py:430)
+int run_time_mlp(eegldm_unet* h, const float* t_host, int nt, float* temb_out, cudaStream_t st, const float* t_dev = nullptr) {
     const int mc = h->cfg.model_channels, ted = h->ted;
-    std::vector<float> te((size_t)nt * mc);
-    timestep_embedding_host(t_host, nt, mc, te.data());
     int r = ensure(h->tscratch, h->tscratch_cap, (size_t)nt * (mc + 2 * ted));
     if (r) return r;
     float* d_te = h->tscratch;
     float* d_h0 = d_te + (size_t)nt * mc;
     float* d_emb = d_h0 + (size_t)nt * ted;
-    CU(cudaMemcpyAsync(d_te, te.data(), te.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+    if (t_host) {
+        std::vector<float> te((size_t)nt * mc);
+        timestep_embedding_host(t_host, nt, mc, te.data());
+        CU(cudaMemcpyAsync(d_te, te.data(), te.size() * sizeof(float), cudaMemcpyHostToDevice, st));   // pageable source: staged before return
+    } else CU(launch_timestep_embedding(t_dev, nt, mc, d_te, st));
     CU(launch_linear(d_te, h->te0_w, h->te0_b, d_h0, nt, mc, ted, 0, st));
     CU(launch_linear(d_h0, h->te2_w, h->te2_b, d_emb, nt, ted, ted, 1, st));
     CU(launch_linear(d_emb, h->emb_w, h->emb_b, temb_out, nt, ted, h->emb_total, 1, st));
@@ -1414,18 +1429,18 @@ int eegldm_unet_set_math(eegldm_unet* h, eegldm_math mode) {
     return EEGLDM_OK;
 }
 
-int eegldm_unet_forward(eegldm_unet* h, const float* x_dev, const float* timesteps_host, int nt, float* out_dev, int B,
-                        int T, void* stream) {
+static int unet_forward_impl(eegldm_unet* h, const float* x_dev, const float* timesteps_host, const float* timesteps_dev, int nt,
+                             float* out_dev, int B, int T, void* stream) {
     if (!h) return fail(EEGLDM_ERR_INVALID, "null handle");
     if (!h->finalized) return fail(EEGLDM_ERR_MISSING, "eegldm_unet_finalize has not been called");
     if (B < 0 || (nt != 1 && nt != B)) return fail(EEGLDM_ERR_SHAPE, "timesteps must have 1 or B entries");
     if (B == 0) return EEGLDM_OK;  // empty batch: nothing to do (pointers may be null)
-    if (!x_dev || !timesteps_host || !out_dev) return fail(EEGLDM_ERR_INVALID, "null argument");
+    if (!x_dev || (!timesteps_host && !timesteps_dev) || !out_dev) return fail(EEGLDM_ERR_INVALID, "null argument");
     cudaStream_t st = (cudaStream_t)stream;
     const int zin = h->cfg.in_channels, zout = h->cfg.out_channels;
     int r = ensure(h->temb_fwd, h->temb_fwd_cap, (size_t)nt * h->emb_total);
     if (r) return r;
-    r = run_time_mlp(h, timesteps_host, nt, h->temb_fwd, st);
+    r = run_time_mlp(h, timesteps_host, nt, h->temb_fwd, st, timesteps_dev);
     if (r) return r;
     const size_t nin = (size_t)B * T * zin, nout = (size_t)B * T * zout;
     r = ensure(h->xtmp, h->xtmp_cap, nin + nout);
@@ -1441,6 +1456,28 @@ int eegldm_unet_forward(eegldm_unet* h, const float* x_dev, const float* timeste
     r = run_ops(bd, st);
     if (r) return r;
     if (zout != 1) CU(launch_transpose_nlc_to_ncl(io.out, out_dev, B, zout, T, st));
+    return EEGLDM_OK;
+}
+
+int eegldm_unet_forward(eegldm_unet* h, const float* x_dev, const float* timesteps_host, int nt, float* out_dev, int B,
+                        int T, void* stream) {
+    if (!timesteps_host && B > 0) return fail(EEGLDM_ERR_INVALID, "null argument");
+    return unet_forward_impl(h, x_dev, timesteps_host, nullptr, nt, out_dev, B, T, stream);
+}
+int eegldm_unet_forward_devt(eegldm_unet* h, const float* x_dev, const float* timesteps_dev, int nt, float* out_dev, int B,
+                             int T, void* stream) {
+    if (!timesteps_dev && B > 0) return fail(EEGLDM_ERR_INVALID, "null argument");
+    return unet_forward_impl(h, x_dev, nullptr, timesteps_dev, nt, out_dev, B, T, stream);
+}
+
+int eegldm_unet_range_status(eegldm_unet* h, int* overflow_out) {
+    if (!h || !overflow_out) return fail(EEGLDM_ERR_INVALID, "null argument");
+    *overflow_out = 0;
+    if (!h->range_flag) return EEGLDM_OK;
+    int v = 0;
+    CU(cudaMemcpy(&v, h->range_flag, sizeof(int), cudaMemcpyDeviceToHost));   // synchronises with the work that may raise it
+    if (v) CU(cudaMemset(h->range_flag, 0, sizeof(int)));
+    *overflow_out = v != 0;
     return EEGLDM_OK;
 }
 
@@ -1593,9 +1630,13 @@ int eegldm_ddim_sample(eegldm_unet* u, eegldm_aekl* a, const eegldm_sched_cfg* s
     std::vector<float> key{(float)sc->num_train_timesteps, sc->beta_start, sc->beta_end, (float)sc->schedule,
                            (float)sc->prediction_type, (float)sc->set_alpha_to_one, (float)sc->steps_offset, (float)n_steps};
     if (key != u->table_key) {
-        r = ensure(u->temb_table, u->temb_table_cap, (size_t)n_steps * u->emb_total);
+        // The captured step graphs bake the table pointers into their step_advance node: size both tables for the longest
+        // schedule this scheduler can ask for (num_train_timesteps rows), and drop the graphs if they still have to move.
+        const size_t rows = (size_t)std::max(n_steps, sc->num_train_timesteps);
+        if (rows * u->emb_total > u->temb_table_cap || 2 * rows > u->coef_table_cap) u->drop_graphs();
+        r = ensure(u->temb_table, u->temb_table_cap, rows * u->emb_total);
         if (r) return r;
-        r = ensure(u->coef_table, u->coef_table_cap, (size_t)2 * n_steps);
+        r = ensure(u->coef_table, u->coef_table_cap, 2 * rows);
         if (r) return r;
         std::vector<float> tf(ts.begin(), ts.end());
         r = run_time_mlp(u, tf.data(), n_steps, u->temb_table, st);
@@ -1713,6 +1754,13 @@ int eegldm_ddim_sample_host(eegldm_unet* u, eegldm_aekl* a, const eegldm_sched_c
     }
     e = cudaStreamSynchronize(st);
     if (!r && e != cudaSuccess) r = cuda_fail(e, "cudaStreamSynchronize");
+    if (!r && u->math == EEGLDM_MATH_F16X3_TC) {
+        int over = 0;
+        r = eegldm_unet_range_status(u, &over);
+        if (!r && over)
+            r = fail(EEGLDM_ERR_INVALID, "f16x3: an activation left the fp16 operand range (|x| >= 65504 or NaN); the result is invalid -- "
+                                         "use EEGLDM_MATH_FP32_SIMT for this model");
+    }
     return r;
 }
 
@@ -1861,8 +1909,8 @@ __global__ void bench_fill_kernel(float* x, size_t n, uint32_t seed) {
         x[i] = (float)(h & 0xFFFF) * (2.0f / 65535.0f) - 1.0f;
     }
 }
-int eegldm_bench_conv(int B, int T, int Cin, int Cout, int k, int with_res, int math, int debug, int reps, float* ms_out,
-                      void* stream) {
+static int bench_conv_impl(int B, int T, int Cin, int Cout, int k, int with_res, int math, int debug, int reps, float* ms_out,
+                           double* timeline_out, void* stream) {
     if (!ms_out || reps <= 0) return fail(EEGLDM_ERR_INVALID, "bad argument");
     if (math == EEGLDM_MATH_FP32_SIMT || !conv_tc_eligible(Cin, 0, Cout, T, k, 1))
         return fail(EEGLDM_ERR_SHAPE, "shape / math not eligible for the tcgen05 path");
@@ -1916,9 +1964,40 @@ int eegldm_bench_conv(int B, int T, int Cin, int Cout, int k, int with_res, int 
     *ms_out = ms / reps;
     if (e0) cudaEventDestroy(e0);
     if (e1) cudaEventDestroy(e1);
+    if (timeline_out && ce == cudaSuccess) {
+        // one more launch with the per-CTA cycle counters switched on; averaged over the CTAs that ran
+        const int max_ctas = 1024;
+        unsigned long long* tl = nullptr;
+        ce = cudaMalloc((void**)&tl, (size_t)max_ctas * TC_TL_N * sizeof(unsigned long long));
+        if (ce == cudaSuccess) ce = cudaMemsetAsync(tl, 0, (size_t)max_ctas * TC_TL_N * sizeof(unsigned long long), st);
+        q.timeline = tl;
+        if (ce == cudaSuccess) ce = launch_conv_tc(q, x3, st);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+        std::vector<unsigned long long> hst((size_t)max_ctas * TC_TL_N);
+        if (ce == cudaSuccess) ce = cudaMemcpy(hst.data(), tl, hst.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+        for (int j = 0; j < TC_TL_N; ++j) timeline_out[j] = 0.0;
+        int n = 0;
+        for (int c = 0; c < max_ctas; ++c)
+            if (hst[(size_t)c * TC_TL_N + TC_TL_TOTAL]) {
+                ++n;
+                for (int j = 0; j < TC_TL_N; ++j) timeline_out[j] += (double)hst[(size_t)c * TC_TL_N + j];
+            }
+        for (int j = 0; j < TC_TL_N; ++j) timeline_out[j] /= std::max(n, 1);
+        timeline_out[TC_TL_N - 1] = n;
+        cudaFree(tl);
+    }
     cudaFree(x); cudaFree(out); cudaFree(res); cudaFree(U); cudaFree(ss);
     if (ce != cudaSuccess) return cuda_fail(ce, "conv bench");
     return EEGLDM_OK;
+}
+int eegldm_bench_conv(int B, int T, int Cin, int Cout, int k, int with_res, int math, int debug, int reps, float* ms_out,
+                      void* stream) {
+    return bench_conv_impl(B, T, Cin, Cout, k, with_res, math, debug, reps, ms_out, nullptr, stream);
+}
+int eegldm_bench_conv_timeline(int B, int T, int Cin, int Cout, int k, int with_res, int math, int debug, int reps, float* ms_out,
+                               double* timeline_out, void* stream) {
+    if (!timeline_out) return fail(EEGLDM_ERR_INVALID, "null argument");
+    return bench_conv_impl(B, T, Cin, Cout, k, with_res, math, debug, reps, ms_out, timeline_out, stream);
 }
 
 // One attention launch (QKVAttentionLegacy.forward) on channels-last qkv [B][T][H*3*ch] -> out [B][T][H*ch].

@@ -87,6 +87,7 @@ struct ActSplitParams {
     int Tout, nsegs16, nks;                             // conv-input length after resample; B*Tout/16; (C0+C1)/TC_BK
     uint8_t* U;
     uint8_t* U_raw;   // optional second image: the same rows WITHOUT affine / SiLU (skip_connection operand, unet.py:327)
+    int* range_flag;  // optional: set to 1 when a value to be split is outside the f16x3 operand range (|x| >= 65504 or NaN)
 };
 size_t act_split_bytes(int nsegs16, int Cin);
 cudaError_t launch_act_split(const ActSplitParams& p, bool x3, cudaStream_t st);
@@ -113,7 +114,12 @@ struct TcConvParams {
     int gn_cpg;         //   [B][Tout/16][Cout/gn_cpg][3]; gn_cpg = channels per group in {4, 8, 16, 32} (conv_tc_gn_ok)
     int direct;         // 1: activation operands produced inside the conv kernel from TcSeg.src0/src1 (no act_split pre-pass)
     int debug;          // timing experiments only (eegldm_bench_conv): 1 = no operand copies, 2 = no MMAs; results are garbage
+    int* range_flag;    // optional (fused producer): set to 1 when an operand is outside the f16x3 range (|x| >= 65504 or NaN)
+    unsigned long long* timeline;   // optional (eegldm_bench_conv_timeline): per-CTA cycle counters, TC_TL_N per CTA
 };
+// per-CTA counters of the conv kernel's warp roles (cycles, summed over the CTA's tiles)
+enum TcTimeline : int { TC_TL_TOTAL = 0, TC_TL_MMA_WAIT_ACC, TC_TL_MMA_WAIT_A, TC_TL_MMA_WAIT_B, TC_TL_EPI_WAIT, TC_TL_EPI_BUSY,
+                        TC_TL_PROD_WAIT, TC_TL_PROD_BUSY, TC_TL_LOAD_WAIT_B, TC_TL_TILES, TC_TL_N = 16 };
 bool conv_tc_eligible(int Cin0, int Cin1, int Cout, int Tout, int taps, int stride);
 bool conv_tc_gn_ok(int Cout, int G);         // can the conv epilogue emit the GroupNorm(G) statistics of its output?
 int conv_tc_bn(int Cout, int weight_stages);   // weight_stages = sum over segments of (Cin/32)*taps
@@ -140,11 +146,13 @@ struct AttnTcParams {
 bool attn_tc_eligible(int T, int ch);
 bool attn_direct_eligible(int T, int ch);   // in-kernel fp32 -> fp16 hi/lo split of q, k, v (T <= 208)
 size_t attn_qkv16_bytes(int B, int T, int H, int ch);
-cudaError_t launch_qkv_split(const float* qkv, uint8_t* dst, int B, int T, int H, int ch, cudaStream_t st);
+cudaError_t launch_qkv_split(const float* qkv, uint8_t* dst, int B, int T, int H, int ch, cudaStream_t st, int* range_flag = nullptr);
 cudaError_t launch_attention_tc(const AttnTcParams& p, bool x3, cudaStream_t st);
 // y[r][o] = bias[o] + sum_i act(x[r][i]) * W[o][i];  act = SiLU if silu_in
 cudaError_t launch_linear(const float* x, const float* W, const float* bias, float* y, int R, int I, int O,
                           int silu_in, cudaStream_t st);
+// timestep_embedding (unet.py:12-36) of device-resident timesteps: out[nt][dim], same rounding points as the host version
+cudaError_t launch_timestep_embedding(const float* t_dev, int nt, int dim, float* out, cudaStream_t st);
 // NCL <-> NLC transposes for multi-channel boundary tensors
 cudaError_t launch_transpose_ncl_to_nlc(const float* in, float* out, int B, int C, int T, cudaStream_t st);
 cudaError_t launch_transpose_nlc_to_ncl(const float* in, float* out, int B, int C, int T, cudaStream_t st);

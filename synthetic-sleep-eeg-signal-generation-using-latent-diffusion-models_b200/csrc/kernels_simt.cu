@@ -859,6 +859,20 @@ __global__ void scale_kernel(const float* __restrict__ src, float* __restrict__ 
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = src[i] * alpha;
 }
+// timestep_embedding (unet.py:12-36) for device-resident timesteps; double precision with fp32 rounding at the points the
+// reference rounds (freqs, t*freq, cos / sin), identical to the host version in engine.cu
+__global__ void timestep_embedding_kernel(const float* __restrict__ t, int nt, int dim, float* __restrict__ out) {
+    const int half = dim / 2;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nt * half) return;
+    const int i = idx / half, j = idx % half;
+    const float fr = (float)exp((double)(-(float)log(10000.0) * (float)j / (float)half));
+    const float arg = t[i] * fr;
+    out[(size_t)i * dim + j] = (float)cos((double)arg);
+    out[(size_t)i * dim + half + j] = (float)sin((double)arg);
+    if ((dim & 1) && j == 0) out[(size_t)i * dim + dim - 1] = 0.f;
+}
+
 __global__ void step_advance_kernel(const float* __restrict__ temb_table, int temb_row, float* __restrict__ temb_cur,
                                     const float* __restrict__ coef_table, float* __restrict__ coef_cur, int* step) {
     const int s = *step;
@@ -1030,6 +1044,14 @@ cudaError_t launch_scale(const float* src, float* dst, float alpha, size_t n, cu
     g_launch_count += 1;
     return cudaGetLastError();
 }
+cudaError_t launch_timestep_embedding(const float* t_dev, int nt, int dim, float* out, cudaStream_t st) {
+    const int n = nt * (dim / 2);
+    if (n <= 0) return cudaSuccess;
+    timestep_embedding_kernel<<<(n + 127) / 128, 128, 0, st>>>(t_dev, nt, dim, out);
+    g_launch_count += 1;
+    return cudaGetLastError();
+}
+
 cudaError_t launch_step_advance(const float* temb_table, int temb_row, float* temb_cur, const float* coef_table,
                                 float* coef_cur, int* step, cudaStream_t st) {
     step_advance_kernel<<<1, 256, 0, st>>>(temb_table, temb_row, temb_cur, coef_table, coef_cur, step);

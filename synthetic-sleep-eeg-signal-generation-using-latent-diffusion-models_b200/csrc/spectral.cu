@@ -11,6 +11,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <tuple>
 
 #include "kernels.cuh"
 
@@ -42,11 +43,17 @@ struct CufftApi {
     }
 };
 
-struct SpectralState {
-    CufftApi api;
-    std::map<std::pair<int, int>, std::pair<cufftHandle, cufftHandle>> plans;   // (N, batch) -> (r2c, c2r)
+// cuFFT plans and their work areas belong to the device they were created on, and a scratch buffer may only be reused by
+// work ordered on the same stream: plans are keyed by (device, stream, N, batch), scratch by (device, stream).  The mutex covers the
+// host-side bookkeeping; launches on different streams use different scratch and do not race.
+struct SpectralScratch {
     float2* freq = nullptr; size_t freq_cap = 0;    // [2][B][N/2+1]
     float* time = nullptr; size_t time_cap = 0;     // [B][N]
+};
+struct SpectralState {
+    CufftApi api;
+    std::map<std::tuple<int, cudaStream_t, int, int>, std::pair<cufftHandle, cufftHandle>> plans;   // (device, stream, N, batch) -> (r2c, c2r)
+    std::map<std::pair<int, cudaStream_t>, SpectralScratch> scratch;                   // (device, stream)
     std::mutex mu;
 };
 SpectralState g_spec;
@@ -98,7 +105,9 @@ int spectral_loss(const float* input, const float* target, int B, int N, int red
     std::lock_guard<std::mutex> lock(g_spec.mu);
     if (!g_spec.api.load()) { if (err) *err = g_spec.api.err; return 1; }
     const int nb = N / 2 + 1;
-    auto key = std::make_pair(N, B);
+    int dev = 0;
+    { cudaError_t e = cudaGetDevice(&dev); if (e != cudaSuccess) return (int)e; }
+    auto key = std::make_tuple(dev, st, N, B);   // a plan owns a work area: one per stream
     auto it = g_spec.plans.find(key);
     if (it == g_spec.plans.end()) {
         cufftHandle r2c, c2r;
@@ -111,20 +120,21 @@ int spectral_loss(const float* input, const float* target, int B, int N, int red
         it = g_spec.plans.emplace(key, std::make_pair(r2c, c2r)).first;
     }
     const size_t nfreq = (size_t)2 * B * nb, ntime = (size_t)B * N;
-    if (nfreq > g_spec.freq_cap) {
-        if (g_spec.freq) cudaFree(g_spec.freq);
-        cudaError_t e = cudaMalloc((void**)&g_spec.freq, nfreq * sizeof(float2));
-        if (e != cudaSuccess) { g_spec.freq = nullptr; g_spec.freq_cap = 0; return (int)e; }
-        g_spec.freq_cap = nfreq;
+    SpectralScratch& sc = g_spec.scratch[std::make_pair(dev, st)];
+    if (nfreq > sc.freq_cap) {   // growth only (cudaFree waits for the device: once per shape)
+        if (sc.freq) cudaFree(sc.freq);
+        cudaError_t e = cudaMalloc((void**)&sc.freq, nfreq * sizeof(float2));
+        if (e != cudaSuccess) { sc.freq = nullptr; sc.freq_cap = 0; return (int)e; }
+        sc.freq_cap = nfreq;
     }
-    if (grad_dev && ntime > g_spec.time_cap) {
-        if (g_spec.time) cudaFree(g_spec.time);
-        cudaError_t e = cudaMalloc((void**)&g_spec.time, ntime * sizeof(float));
-        if (e != cudaSuccess) { g_spec.time = nullptr; g_spec.time_cap = 0; return (int)e; }
-        g_spec.time_cap = ntime;
+    if (grad_dev && ntime > sc.time_cap) {
+        if (sc.time) cudaFree(sc.time);
+        cudaError_t e = cudaMalloc((void**)&sc.time, ntime * sizeof(float));
+        if (e != cudaSuccess) { sc.time = nullptr; sc.time_cap = 0; return (int)e; }
+        sc.time_cap = ntime;
     }
-    float2* Fi = g_spec.freq;
-    float2* Ft = g_spec.freq + (size_t)B * nb;
+    float2* Fi = sc.freq;
+    float2* Ft = sc.freq + (size_t)B * nb;
     const cufftHandle r2c = it->second.first, c2r = it->second.second;
     if (g_spec.api.SetStream(r2c, st) != CUFFT_SUCCESS || g_spec.api.SetStream(c2r, st) != CUFFT_SUCCESS ||
         g_spec.api.ExecR2C(r2c, const_cast<float*>(input), reinterpret_cast<cufftComplex*>(Fi)) != CUFFT_SUCCESS ||
@@ -138,11 +148,11 @@ int spectral_loss(const float* input, const float* target, int B, int N, int red
     spectral_bins_kernel<<<blocks, 256, 0, st>>>(Fi, Ft, loss_dev, N, nbins, loss_weight * red, grad_dev != nullptr);
     g_launch_count += 1;
     if (grad_dev) {
-        if (g_spec.api.ExecC2R(c2r, reinterpret_cast<cufftComplex*>(Fi), g_spec.time) != CUFFT_SUCCESS) {
+        if (g_spec.api.ExecC2R(c2r, reinterpret_cast<cufftComplex*>(Fi), sc.time) != CUFFT_SUCCESS) {
             if (err) *err = "cufftExecC2R failed";
             return 1;
         }
-        scale_store_kernel<<<(unsigned)((ntime + 255) / 256), 256, 0, st>>>(g_spec.time, grad_dev, grad_weight * red * rsqrtf((float)N),
+        scale_store_kernel<<<(unsigned)((ntime + 255) / 256), 256, 0, st>>>(sc.time, grad_dev, grad_weight * red * rsqrtf((float)N),
                                                                           grad_accumulate, ntime);
         g_launch_count += 1;
     }

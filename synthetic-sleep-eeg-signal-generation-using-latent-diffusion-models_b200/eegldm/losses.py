@@ -14,12 +14,11 @@ from ._module import check_cuda_f32
 class _JukeboxFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, inp, target, reduction):
-        inp, target = check_cuda_f32(inp, "input"), check_cuda_f32(target, "target")
-        if inp.shape != target.shape or inp.dim() != 3:
-            raise ValueError("input/target must both be [B, C, N]")
+        # inp / target arrive fp32 and contiguous (JukeboxLoss.forward normalises them OUTSIDE this Function, where autograd
+        # tracks the cast / copy); whether a gradient is wanted is a property of the argument, not of a detached copy
         B, Cc, N = inp.shape
         loss = torch.empty((), device=inp.device, dtype=torch.float32)
-        grad = torch.empty_like(inp) if inp.requires_grad else None
+        grad = torch.empty_like(inp) if ctx.needs_input_grad[0] else None
         with torch.cuda.device(inp.device):
             _lib.check(_lib.lib().eegldm_jukebox_loss(
                 C.c_void_p(inp.data_ptr()), C.c_void_p(target.data_ptr()), int(B), int(Cc), int(N), int(reduction),
@@ -44,4 +43,9 @@ class JukeboxLoss(torch.nn.Module):
         self.reduction = reduction
 
     def forward(self, input, target):
+        if input.shape != target.shape or input.dim() != 3:
+            raise ValueError("input/target must both be [B, C, N]")
+        # dtype / contiguity normalisation happens here, under autograd (a sliced reconstruction such as recon[:, :, 36:-36]
+        # or a half tensor under autocast keeps its gradient path)
+        input, target = check_cuda_f32(input, "input"), check_cuda_f32(target.detach(), "target")
         return _JukeboxFn.apply(input, target, 0 if self.reduction == "sum" else 1)

@@ -27,12 +27,32 @@ def _crop(y, crop):
     return y[:, :, crop:-crop] if crop else y   # sample_trials.py:169
 
 
+def _resolve_steps(scheduler, num_inference_steps):
+    """``scheduler.set_timesteps(n)`` is how the reference chooses the step count (sample_trials.py:144): honour it when the
+    caller does not pass one, and refuse a silent mismatch."""
+    set_n = getattr(scheduler, "num_inference_steps", None)
+    if num_inference_steps is None:
+        return int(set_n) if set_n else 50
+    if set_n and int(set_n) != int(num_inference_steps):
+        raise ValueError(f"num_inference_steps={num_inference_steps} but scheduler.set_timesteps({set_n}) was called")
+    return int(num_inference_steps)
+
+
+def _check_range(unet):
+    if unet._math == "f16x3" and unet.range_overflow():
+        raise _lib.EegldmError(-1, "f16x3: an activation left the fp16 operand range (|x| >= 65504 or NaN); the result is "
+                                   "invalid -- use math='fp32' for this model")
+
+
 @torch.no_grad()
-def ddim_sample(unet, scheduler: DDIMScheduler, noise, num_inference_steps: int = 50, aekl=None,
-                scale_factor: float = 1.0, crop: int = 0):
-    """x_T = noise -> DDIM(num_inference_steps) -> decode(x_0 / scale_factor)[..., crop:-crop]."""
+def ddim_sample(unet, scheduler: DDIMScheduler, noise, num_inference_steps=None, aekl=None,
+                scale_factor: float = 1.0, crop: int = 0, check_range: bool = True):
+    """x_T = noise -> DDIM(num_inference_steps) -> decode(x_0 / scale_factor)[..., crop:-crop].
+    ``num_inference_steps`` defaults to what ``scheduler.set_timesteps`` chose (50 if it was never called).
+    ``check_range`` (f16x3 only) reads the operand-range flag after the last step -- one device synchronisation per call."""
     if scheduler.clip_sample:
         raise NotImplementedError("fused sampling implements clip_sample=False (sample_trials.py:142)")
+    num_inference_steps = _resolve_steps(scheduler, num_inference_steps)
     noise = check_cuda_f32(noise, "noise")
     B, z, T = noise.shape
     out = torch.empty(_out_shape(unet, aekl, B, T), device=noise.device, dtype=torch.float32)
@@ -44,21 +64,27 @@ def ddim_sample(unet, scheduler: DDIMScheduler, noise, num_inference_steps: int 
             unet._h, aekl._h if aekl is not None else None, C.byref(scheduler._cfg), C.c_void_p(noise.data_ptr()),
             float(scale_factor), int(num_inference_steps), C.c_void_p(out.data_ptr()), int(B), int(T),
             C.c_void_p(_lib.current_stream_ptr(noise.device))))
+        if check_range:
+            _check_range(unet)
     return _crop(out, crop)
 
 
 @torch.no_grad()
-def ddim_sample_host(unet, scheduler: DDIMScheduler, noise_host, num_inference_steps: int = 50, aekl=None,
+def ddim_sample_host(unet, scheduler: DDIMScheduler, noise_host, num_inference_steps=None, aekl=None,
                      scale_factor: float = 1.0, out_host=None, device=None):
     """Same, with HOST tensors (ideally pinned): H2D, sampling, D2H, synchronised on return."""
     if scheduler.clip_sample:
         raise NotImplementedError("fused sampling implements clip_sample=False (sample_trials.py:142)")
+    num_inference_steps = _resolve_steps(scheduler, num_inference_steps)
     if noise_host.is_cuda or noise_host.dtype != torch.float32 or not noise_host.is_contiguous():
         raise ValueError("noise_host must be a contiguous fp32 CPU tensor")
     B, z, T = noise_host.shape
     shape = _out_shape(unet, aekl, B, T)
     if out_host is None:
         out_host = torch.empty(shape, dtype=torch.float32, pin_memory=True)
+    elif (out_host.is_cuda or out_host.dtype != torch.float32 or not out_host.is_contiguous()
+          or tuple(out_host.shape) != tuple(shape)):
+        raise ValueError(f"out_host must be a contiguous fp32 CPU tensor of shape {tuple(shape)}")
     device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
     with torch.cuda.device(device):
         unet._sync_weights()

@@ -23,7 +23,7 @@ class UNetModel(EngineModule):
     def __init__(self, image_size, in_channels, model_channels, out_channels, num_res_blocks, attention_resolutions,
                  dropout=0, channel_mult=(1, 2, 4, 8), conv_resample=True, num_classes=None, num_heads=1,
                  num_head_channels=-1, num_heads_upsample=-1, use_scale_shift_norm=False, resblock_updown=False,
-                 n_embed=None, math="fp32"):
+                 n_embed=None, math="f16x3"):
         super().__init__()
         if num_classes is not None or n_embed is not None:
             raise NotImplementedError("class-conditional / codebook heads are not on the reference's live path")
@@ -74,7 +74,7 @@ class UNetModel(EngineModule):
 
         register_tree(self, infos, init)
         self._math = "fp32"
-        self.set_math(math)
+        self.set_math(math)   # default f16x3: the tensor-pipe parity mode (layers whose shapes are not eligible run fp32 SIMT)
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -105,13 +105,27 @@ class UNetModel(EngineModule):
         if x.dim() != 3 or x.shape[1] != self.in_channels:
             raise ValueError(f"x must be [B, {self.in_channels}, T], got {tuple(x.shape)}")
         B, _, T = x.shape
-        ts = torch.as_tensor(timesteps).reshape(-1).to(device="cpu", dtype=torch.float32).contiguous()  # .float(): unet.py:28
+        ts = torch.as_tensor(timesteps).reshape(-1)
         if ts.numel() not in (1, B):
             raise ValueError("timesteps must have 1 or B entries")
         out = torch.empty((B, self.out_channels, T), device=x.device, dtype=torch.float32)
         with torch.cuda.device(x.device):
             self._sync_weights()
-            _lib.check(_lib.lib().eegldm_unet_forward(
-                self._h, C.c_void_p(x.data_ptr()), C.cast(C.c_void_p(ts.data_ptr()), C.POINTER(C.c_float)), int(ts.numel()),
-                C.c_void_p(out.data_ptr()), int(B), int(T), C.c_void_p(_lib.current_stream_ptr(x.device))))
+            L = _lib.lib()
+            stream = C.c_void_p(_lib.current_stream_ptr(x.device))
+            if ts.is_cuda:   # the reference's loops pass a CUDA tensor (training.py:430, sample_trials.py:157): no host sync
+                ts = ts.to(device=x.device, dtype=torch.float32).contiguous()   # .float(): unet.py:28
+                _lib.check(L.eegldm_unet_forward_devt(self._h, C.c_void_p(x.data_ptr()), C.c_void_p(ts.data_ptr()), int(ts.numel()),
+                                                      C.c_void_p(out.data_ptr()), int(B), int(T), stream))
+            else:
+                ts = ts.to(dtype=torch.float32).contiguous()
+                _lib.check(L.eegldm_unet_forward(self._h, C.c_void_p(x.data_ptr()), C.cast(C.c_void_p(ts.data_ptr()), C.POINTER(C.c_float)),
+                                                 int(ts.numel()), C.c_void_p(out.data_ptr()), int(B), int(T), stream))
         return out
+
+    def range_overflow(self) -> bool:
+        """f16x3 operand-range guard: True when, since the last call, some activation handed to the tensor pipe had
+        |x| >= 65504 or was NaN (that forward's output is invalid: switch to ``set_math("fp32")``).  Synchronises."""
+        v = C.c_int(0)
+        _lib.check(_lib.lib().eegldm_unet_range_status(self._h, C.byref(v)))
+        return bool(v.value)

@@ -262,7 +262,7 @@ def test_full_size_properties(built_lib, cuda_device, math):
     unet = _unet(ucfg, ou.make_unet_state_dict(ucfg, 0), cuda_device, math)
     aekl = _aekl(acfg, oa.make_aekl_state_dict(acfg, 42), cuda_device)
     sched = eegldm.DDIMScheduler(**SAMPLER_DEFAULTS)
-    sched.set_timesteps(50)
+    sched.set_timesteps(3)
     B = 64
     noise = torch.randn(B, 1, 768, generator=torch.Generator().manual_seed(0)).to(cuda_device)
     full = eegldm.ddim_sample(unet, sched, noise, 3, aekl, crop=36)
