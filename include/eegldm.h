@@ -70,13 +70,16 @@ int eegldm_set_conv_cluster(int ctas);
  * bit 4 -- the tcgen05 attention kernel reads the fp32 qkv tensor and splits q, k, v to fp16 hi/lo in its own producer warps
  *          (no qkv_split pass); T <= 208; measured no faster (the kernel slows down by what the pass cost): off;
  * bit 3 -- the tcgen05 attention kernel writes its result as proj_out's operand image (no fp32 attention output, no pre-pass);
+ * bit 5 -- (default clear) set to switch OFF the N = 128 tiles' concatenated MMA a_hi x [w_hi | w_lo] (one N = 256 instruction
+ *          into both f16x3 accumulators instead of two N = 128 ones; same arithmetic, fewer shared-memory operand reads);
  * bit 1 -- an AttentionBlock's qkv conv writes the attention kernel's fp16 hi/lo operand images instead of fp32 (f16x3; measured no faster than the separate split pass).
  * Call before creating models: plans cache the choices. */
 int eegldm_set_conv_tuning(int pair, int bn256_min_stages, int fuse_epilogues);
 
 /* Live per-kernel profile (bench.py's roofline leg).  While enabled, every launch made outside CUDA-graph
  * capture is bracketed by CUDA events on the launching stream.  eegldm_profile_read sums, for one kernel
- * family (0 = conv implicit-GEMM, 1 = GroupNorm statistics, 2 = attention, 3 = other, 4 = activation split pre-pass), the measured
+ * family (0 = conv implicit-GEMM [in a tensor-pipe math mode: the tcgen05 launches only], 1 = GroupNorm statistics, 2 = attention,
+ * 3 = other, 4 = activation split pre-pass, 5 = the narrow fp32 SIMT convs of a tensor-pipe model: 1-channel in / out convs and the autoencoder), the measured
  * milliseconds, the ALGORITHMIC flops and HBM bytes and the launch count since enable. */
 int eegldm_profile_enable(int on);
 int eegldm_profile_read(int kind, double* ms, double* flops, double* bytes, int64_t* launches);
@@ -227,6 +230,40 @@ int eegldm_ddim_sample_host(eegldm_unet* unet, eegldm_aekl* aekl, const eegldm_s
                             void* stream);
 /* disable (0) / enable (1) CUDA-graph replay inside eegldm_ddim_sample (default 1) */
 int eegldm_set_graphs(int enabled);
+
+/* ------------------------------------------------------------------------------------------------
+ * Output tail of the sampling scripts: replaces, batched over all windows, what src/sample_trials.py:169-197 (and
+ * sample_trials_ddpm.py:105-128, util.py:66-112) do per window on the host --
+ *   cropped = sample.cpu().numpy()[:, :, 36:-36];  np.save(sample_i.npy, cropped);
+ *   spectrum = mne.EpochsArray(cropped, sfreq=100).compute_psd(fmax=18);  psds = 10 * log10(spectrum.average().get_data()). */
+typedef struct {
+    int32_t method;         /* 0 = multitaper (mne Epochs.compute_psd default), 1 = welch (mne Raw.compute_psd default) */
+    float sfreq;            /* 100 (util.py:83) */
+    float fmin, fmax;       /* 0, 18 (sample_trials.py:174); frequencies with fmin <= f <= fmax are returned */
+    float bandwidth;        /* multitaper: full bandwidth in Hz; <= 0 = mne's default (half-bandwidth product NW = 4) */
+    int32_t low_bias;       /* multitaper: keep tapers with concentration > 0.9 (mne default 1) */
+    int32_t normalization;  /* multitaper: 0 = "length" (mne default), 1 = "full" (divide by sfreq) */
+    int32_t n_fft;          /* welch: segment / FFT length (<= 0 = mne's default 256) */
+    int32_t n_overlap;      /* welch: overlap between segments (mne default 0) */
+    int32_t remove_dc;      /* subtract the mean of each segment (mne default 1) */
+    int32_t db;             /* 1: return 10 * log10(psd) (sample_trials.py:181) */
+} eegldm_psd_cfg;
+/* number of returned frequencies and (freqs_host nullable) their values for signals of N samples */
+int eegldm_psd_freqs(const eegldm_psd_cfg* cfg, int N, int* n_freqs_out, float* freqs_host);
+/* PSD of B signals of N samples; signal b starts at x_dev + b * row_stride (row_stride >= N: a crop is an offset pointer, no
+ * copy); psd_dev [B][n_freqs].  One window kernel, ONE batched cuFFT R2C over all windows x tapers (or segments), one reduction
+ * kernel; asynchronous on `stream`. */
+int eegldm_psd(const eegldm_psd_cfg* cfg, const float* x_dev, int B, int N, int64_t row_stride, float* psd_dev, void* stream);
+/* host helper: scipy.signal.windows.dpss(N, half_nbw, Kmax, sym, norm=2, return_ratios=True) -- windows_out [Kmax][N] (unit
+ * L2 norm before the sym = 0 truncation), ratios_out [Kmax] (spectral concentrations).  No GPU needed. */
+int eegldm_dpss(int N, double half_nbw, int Kmax, int sym, double* windows_out, double* ratios_out);
+/* sample[:, :, crop_left : L - crop_right] of `rows` device rows of L floats, copied straight into host memory (one strided
+ * copy; synchronises the stream) */
+int eegldm_crop_to_host(const float* x_dev, int64_t rows, int L, int crop_left, int crop_right, float* out_host, void* stream);
+/* numpy .npy writer (format 1.0, '<f4', C order) and the per-window files of sample_trials.py:170:
+ * <dir>/<prefix><first_index + i>.npy, each of shape [1, C, L], from a host batch [B][C][L] */
+int eegldm_write_npy_f32(const char* path, const float* data_host, const int64_t* shape, int ndim);
+int eegldm_save_windows_npy(const char* dir, const char* prefix, int64_t first_index, const float* data_host, int B, int C, int L);
 
 /* ------------------------------------------------------------------------------------------------
  * Test hook (not part of the drop-in surface): ONE fused convolution launch

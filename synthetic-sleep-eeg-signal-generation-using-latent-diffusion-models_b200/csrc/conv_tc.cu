@@ -77,14 +77,23 @@ __device__ __forceinline__ float act(float x, float a, float s, int silu) {
     return silu ? silu_fast(v) : v;
 }
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+// SiLU on the bare special-function instructions: v * rcp(1 + ex2(-v * log2 e)).  ex2.approx.ftz needs none of __expf's
+// denormal-range fix-ups (3 extra instructions per value): an underflowing exponential is 0 (v large: silu = v), an
+// overflowing one is +inf (v very negative: rcp = 0, silu = -0); both approximations are within 2 ulp, as before.
+__device__ __forceinline__ float silu_ftz(float v) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v * -1.4426950408889634f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    return v * r;
+}
 // f16x3 operand range: hi = fp16(v) is inf from 65520 up and lo = (v - inf) * 2^11 is NaN -- the split is only meaningful for
-// |v| < 65504 (include/eegldm.h).  true when any of the 8 values is outside (or NaN).
+// |v| < 65504 (include/eegldm.h).  true when any of the 8 values is outside.
 __device__ __forceinline__ bool out_of_f16_range(const float (&v)[8]) {
-    // magnitude bits as unsigned integers order like the magnitudes, with inf and every NaN above all finite values
-    uint32_t m = 0;
-#pragma unroll
-    for (int e = 0; e < 8; ++e) m = max(m, __float_as_uint(v[e]) & 0x7FFFFFFFu);
-    return m >= 0x477FE000u;   // 65504.0f
+    // 3-input max with |.| source modifiers: 4 instructions per 8 values.  (A NaN operand is not an overflow: it reaches the
+    // output as NaN in every math mode.)
+    const float m = fmaxf(fmaxf(fmaxf(fabsf(v[0]), fabsf(v[1])), fmaxf(fabsf(v[2]), fabsf(v[3]))),
+                          fmaxf(fmaxf(fabsf(v[4]), fabsf(v[5])), fmaxf(fabsf(v[6]), fabsf(v[7]))));
+    return !(m < 65504.f);
 }
 
 // ------------------------------------------------------------------------------------------------ act_split
@@ -236,6 +245,9 @@ __global__ void __launch_bounds__(DIRECT ? 384 : NUM_THREADS, 1) conv_tc_kernel(
     constexpr int NSETS = ACC_COLS * 2 <= 512 ? 2 : 1; // N=256 in f16x3 fills TMEM: no epilogue overlap (used for long K only)
     constexpr uint32_t TMEM_COLS = NSETS * ACC_COLS;
     constexpr uint32_t IDESC = make_idesc(X3 ? 0u : 1u, PAIR ? 2 * BM : BM, BN);
+    constexpr bool CAT = X3 && BN == 128 && !PAIR;                 // hi x [hi | lo] as one N = 256 MMA (see the MMA issuer)
+    constexpr uint32_t IDESC_CAT = make_idesc(0u, BM, 2 * BN);
+    static_assert(!CAT || B_HALF == (BN / 8) * B_SBO, "the lo weight tile must continue the hi tile's 8-column group stride");
     if (warp == W_MMA) {
         if (PAIR) tmem_alloc2(smem_u32(tmem_slot), TMEM_COLS);
         else tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
@@ -319,6 +331,12 @@ __global__ void __launch_bounds__(DIRECT ? 384 : NUM_THREADS, 1) conv_tc_kernel(
             tc_fence_after();
             const long long tl_e0 = tl ? clock64() : 0;
             const uint32_t acc_addr = tmem + ((uint32_t)(warp * 32) << 16) + as * ACC_COLS;
+            // TMEM reads run one 32-column chunk ahead of the chunk being stored: the load of chunk i+1 is issued as soon as
+            // chunk i has been moved to the staging buffer, so its latency overlaps the transpose, the adds, the global stores
+            // and the GroupNorm statistics of chunk i (one warp per scheduler: nothing else hides it)
+            uint32_t vn[32], c2n[32];
+            tmem_ld32_async(acc_addr, vn);
+            if (X3) tmem_ld32_async(acc_addr + (uint32_t)BN, c2n);
 #pragma unroll 1
             for (int cb = 0; cb < BN; cb += 32) {
                 float4 R[8];
@@ -334,17 +352,21 @@ __global__ void __launch_bounds__(DIRECT ? 384 : NUM_THREADS, 1) conv_tc_kernel(
                 for (int h = 0; h < 2; ++h)
                     Tm[h] = p.temb ? ldg4(p.temb + (size_t)max(rb[h], 0) * p.temb_stride + co) : make_float4(0.f, 0.f, 0.f, 0.f);
                 uint32_t v[32];
+                tmem_ld_wait();
                 if (X3) {
-                    uint32_t c2[32];
-                    tmem_ld32_async(acc_addr + (uint32_t)cb, v);
-                    tmem_ld32_async(acc_addr + (uint32_t)(BN + cb), c2);
-                    tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(fmaf(__uint_as_float(c2[i]), 1.0f / LO_SCALE, __uint_as_float(v[i])));
-                } else tmem_ld32(acc_addr + (uint32_t)cb, v);
+                    for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(fmaf(__uint_as_float(c2n[i]), 1.0f / LO_SCALE, __uint_as_float(vn[i])));
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = vn[i];
+                }
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
                     *reinterpret_cast<uint4*>(stg + lane * STG_LD + 4 * j) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                if (cb + 32 < BN) {
+                    tmem_ld32_async(acc_addr + (uint32_t)(cb + 32), vn);
+                    if (X3) tmem_ld32_async(acc_addr + (uint32_t)(BN + cb + 32), c2n);
+                }
                 __syncwarp();
                 float4 O[8];
 #pragma unroll
@@ -461,86 +483,119 @@ __global__ void __launch_bounds__(DIRECT ? 384 : NUM_THREADS, 1) conv_tc_kernel(
         if (tl && tid == 0) { tlo[TC_TL_EPI_WAIT] = tl_a; tlo[TC_TL_EPI_BUSY] = tl_b; tlo[TC_TL_TILES] = lt; tlo[TC_TL_TOTAL] = clock64() - tl_start; }
     } else if (DIRECT && warp < W_LOAD) {
         // ================================================================ activation producers (192 threads)
-        const int pt = tid - 128;
-        bool bad = false;
         // act_split_kernel's mapping: item idx = pt + 192*j -> segment r = idx & 7, 8-channel chunk c = (idx >> 3) & 3, slot
         // q = idx >> 5.  192 = 6 * 32, so the three items of a thread share r and c (one sample, one channel chunk -> ONE
         // set of GroupNorm scale / shift values per k-step) and differ in the slot only: q = pt/32 + 6*j.
+        // The loop is written for instruction count and latency: with one or two producer warps per scheduler every dependent
+        // instruction costs its full latency (ncu: 725 instructions per k-step and thread, issue slots 43 % used, profiles/
+        // r02_summary.md), so everything that does not change per k-step is hoisted to tile / segment changes -- row pointers and
+        // validity per tile, source selection per (tile, source) -- the k-step itself advances three pointers, issues 6 + 4
+        // vector loads and runs ~11 instructions per value (affine, SiLU on ex2.approx / rcp.approx without the denormal
+        // fix-ups of __expf, fp16 hi/lo split, range check).
+        const int pt = tid - 128;
+        bool bad = false;
         const int r = pt & 7, c = (pt >> 3) & 3, q0 = pt >> 5;
-        struct Pre { float4 x[3][2]; float4 a[2], s[2]; uint32_t ok; };
-        // raw rows + scale / shift of k-step ks of work item w; bit j of ok: item j is inside the batch and the sample
-        auto issue = [&](int w, int ks, Pre& P) {
-            const int m_tile = min((w / n_ntiles) * CL + crank, n_mtiles - 1);
-            const bool first = ks < nks0;
+        struct Pre { float4 x[3][2]; float4 a[2], s[2]; };
+        // producer-side cursor over (work item, k-step): `nxt` is what the in-flight loads belong to
+        struct Cur {
+            const float* row[3];     // row pointers of the three items at channel chunk c of the CURRENT k-step's source
+            const float* sc; const float* sh;   // scale / shift at this k-step's channels (null: no affine)
+            uint32_t ok;             // bit j: item j lies inside the batch and the sample (else it is conv zero padding)
+            int silu;
+        };
+        int w = cid, ks = 0;
+        // tile constants (per work item): sample, first position, validity
+        int tb = 0, tile_b = 0; bool segv = false;
+        auto tile_setup = [&](int w_) {
+            const int m_tile = min((w_ / n_ntiles) * CL + crank, n_mtiles - 1);
+            const int g = m_tile * 8 + r;
+            segv = g < p.nsegs16;
+            tile_b = g / spt;
+            tb = (g - tile_b * spt) * 16 - 1 + q0;      // position of item 0; item j: + 6 j
+        };
+        // pointers for k-step ks_ of the current tile (called when the tile, the segment or the concat source changes)
+        auto src_setup = [&](int ks_, Cur& cu) {
+            const bool first = ks_ < nks0;
             const TcSeg& sg = first ? p.seg[0] : p.seg[1];
-            const int kl = first ? ks : ks - nks0;
-            const int g = m_tile * 8 + r, b = g / spt, tb = (g % spt) * 16 - 1, cc = kl * BK + c * 8;
+            const int kl = first ? ks_ : ks_ - nks0;
+            const int cc = kl * BK + c * 8;
             const float* src; int ch, Cs;
             if (cc < sg.C0) { src = sg.src0; ch = cc; Cs = sg.C0; } else { src = sg.src1; ch = cc - sg.C0; Cs = sg.C1; }
-            P.ok = 0;
-            const bool segv = g < p.nsegs16;
+            cu.ok = 0;
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
-                const int t = tb + q0 + 6 * j;
-                P.x[j][0] = P.x[j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (segv && t >= 0 && t < p.Tout) {
-                    const float* row = src + ((size_t)b * sg.Tin + (sg.resample == RS_NEAREST2 ? (t >> 1) : t)) * Cs + ch;
-                    if (!(p.debug & 8)) { P.x[j][0] = ldg4(row); P.x[j][1] = ldg4(row + 4); }   // 8: timing experiment, no row loads
-                    P.ok |= 1u << j;
-                }
+                const int t = tb + 6 * j;
+                const bool v = segv && t >= 0 && t < p.Tout;
+                const int tr = v ? (sg.resample == RS_NEAREST2 ? (t >> 1) : t) : 0;
+                cu.row[j] = src + ((size_t)(v ? tile_b : 0) * sg.Tin + tr) * Cs + ch;   // invalid items: a harmless in-bounds address, never loaded
+                cu.ok |= (v ? 1u : 0u) << j;
             }
             if (sg.scale && segv) {
-                const size_t o = (size_t)b * (sg.C0 + sg.C1) + cc;
-                P.a[0] = ldg4(sg.scale + o); P.a[1] = ldg4(sg.scale + o + 4);
-                P.s[0] = ldg4(sg.shift + o); P.s[1] = ldg4(sg.shift + o + 4);
-            } else {
+                const size_t o = (size_t)tile_b * (sg.C0 + sg.C1) + cc;
+                cu.sc = sg.scale + o; cu.sh = sg.shift + o;
+            } else cu.sc = cu.sh = nullptr;
+            cu.silu = sg.silu;
+        };
+        auto issue = [&](const Cur& cu, Pre& P) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                if ((cu.ok >> j) & 1) { P.x[j][0] = ldg4(cu.row[j]); P.x[j][1] = ldg4(cu.row[j] + 4); }
+                else P.x[j][0] = P.x[j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            if (cu.sc) { P.a[0] = ldg4(cu.sc); P.a[1] = ldg4(cu.sc + 4); P.s[0] = ldg4(cu.sh); P.s[1] = ldg4(cu.sh + 4); }
+            else {
                 P.a[0] = P.a[1] = make_float4(1.f, 1.f, 1.f, 1.f);
                 P.s[0] = P.s[1] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
         };
-        int ia = 0, w = cid, ks = 0;
+        // k-step boundaries at which the pointers must be rebuilt instead of advanced by 32 channels: segment change, and the
+        // switch from src0 to src1 inside a virtual concat (C0 is a multiple of 32, so a k-step never straddles the two)
+        const int sw0 = p.seg[0].src1 ? p.seg[0].C0 / BK : -1;
+        const int sw1 = p.nseg > 1 && p.seg[1].src1 ? nks0 + p.seg[1].C0 / BK : -1;
+        Cur nxt;
         bool have = w < nwork;
         Pre N;
-        if (have) issue(w, 0, N);
+        if (have) { tile_setup(w); src_setup(0, nxt); issue(nxt, N); }
+        int ia = 0;
         while (have) {
             const Pre C = N;
-            const int kc_ = ks;
-            if (++ks == nks) { ks = 0; w += ncl; }
-            have = w < nwork;
-            if (have) issue(w, ks, N);                 // next k-step's loads are in flight while this one is transformed
-            const TcSeg& sg = kc_ < nks0 ? p.seg[0] : p.seg[1];
-            const bool aff = sg.scale != nullptr;
-            const int silu = sg.silu;
+            const uint32_t ok = nxt.ok;
+            const int silu = nxt.silu;
+            // advance the cursor and put the next k-step's loads in flight while this one is transformed
+            if (++ks == nks) { ks = 0; w += ncl; have = w < nwork; if (have) { tile_setup(w); src_setup(0, nxt); } }
+            else if (ks == nks0 || ks == sw0 || ks == sw1) src_setup(ks, nxt);
+            else {
+#pragma unroll
+                for (int j = 0; j < 3; ++j) nxt.row[j] += BK;
+                if (nxt.sc) { nxt.sc += BK; nxt.sh += BK; }
+            }
+            if (have) issue(nxt, N);
             const float a[8] = {C.a[0].x, C.a[0].y, C.a[0].z, C.a[0].w, C.a[1].x, C.a[1].y, C.a[1].z, C.a[1].w};
             const float sh[8] = {C.s[0].x, C.s[0].y, C.s[0].z, C.s[0].w, C.s[1].x, C.s[1].y, C.s[1].z, C.s[1].w};
             const int sa = ia % NA;
             TL_WAIT(tl_a, mbar_wait(barAempty + 8 * sa, ((ia / NA) & 1) ^ 1));
-            uint8_t* img = smem + sa * A_STAGE;
+            uint8_t* img = smem + sa * A_STAGE + c * A_LBO + q0 * A_SBO + r * 16;
+            // (measured: one straight-line block of all 24 values with a select for the padding items is SLOWER than three
+            // 8-value items behind their validity branch -- 13.1 vs 11.1 k cycles per level-0 tile, profiles/r02_summary.md)
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
                 float v[8] = {C.x[j][0].x, C.x[j][0].y, C.x[j][0].z, C.x[j][0].w, C.x[j][1].x, C.x[j][1].y, C.x[j][1].z, C.x[j][1].w};
-                if (((C.ok >> j) & 1) && !(p.debug & 16)) {   // padding / rows past the batch stay exactly zero (16: no transform)
-                    if (aff) {
+                if ((ok >> j) & 1) {                     // padding / rows past the batch stay exactly zero
+                    if (silu) {
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) v[e] = act(v[e], a[e], sh[e], silu);
-                    } else if (silu) {
+                        for (int e = 0; e < 8; ++e) v[e] = silu_ftz(fmaf(a[e], v[e], sh[e]));
+                    } else {
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) v[e] = silu_fast(v[e]);
+                        for (int e = 0; e < 8; ++e) v[e] = fmaf(a[e], v[e], sh[e]);   // no affine: a = 1, s = 0 (exact)
                     }
                 }
-                const uint32_t off = (uint32_t)(c * A_LBO + (q0 + 6 * j) * A_SBO + r * 16);
                 uint4 hi, lo;
-                if (p.debug & 32) {                    // 32: timing experiment, no split
-                    hi = make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
-                    lo = make_uint4(__float_as_uint(v[4]), __float_as_uint(v[5]), __float_as_uint(v[6]), __float_as_uint(v[7]));
-                    if (X3 && !(p.debug & 64)) *reinterpret_cast<uint4*>(img + A_TILE + off) = lo;
-                } else if (X3) {
+                if (X3) {
                     bad |= out_of_f16_range(v);
                     split8_f16(v, hi, lo);
-                    if (!(p.debug & 64)) *reinterpret_cast<uint4*>(img + A_TILE + off) = lo;
+                    *reinterpret_cast<uint4*>(img + j * 6 * A_SBO + A_TILE) = lo;
                 } else round8_bf16(v, hi);
-                if (!(p.debug & 64)) *reinterpret_cast<uint4*>(img + off) = hi;   // 64: timing experiment, no shared-memory stores
-                else if (hi.x == 0x12345678u && lo.y == 0x9abcdef0u) *reinterpret_cast<uint4*>(img + off) = hi;   // keep the math alive
+                *reinterpret_cast<uint4*>(img + j * 6 * A_SBO) = hi;
             }
             fence_proxy_async_smem();                  // generic-proxy stores -> visible to the tensor core's async proxy
             mbar_arrive(barAfull + 8 * sa);
@@ -657,6 +712,18 @@ __global__ void __launch_bounds__(DIRECT ? 384 : NUM_THREADS, 1) conv_tc_kernel(
                         for (int kk = 0; kk < BK / 16; ++kk) {
                             const uint64_t dah = make_desc(a_hi + kk * 2 * A_LBO, A_LBO, A_SBO);
                             const uint64_t dbh = make_desc(b_hi + kk * 2 * B_LBO, B_LBO, B_SBO);
+                            if (CAT && p.cat) {
+                                // N = 128 tiles: the lo weight tile follows the hi tile in the stage with the same 512-byte group
+                                // stride and accumulator 1 follows accumulator 0 in TMEM, so a_hi x [b_hi | b_lo] is ONE N = 256
+                                // MMA into [d0 | d1]: a_hi is read from shared memory once instead of twice (the N = 128 shape is
+                                // bound by shared-memory operand reads: 128 -> 107 B/clk)
+                                const uint64_t dal = make_desc(a_lo + kk * 2 * A_LBO, A_LBO, A_SBO);
+                                if (!skip_mma) {
+                                    umma_bf16(d0, dah, dbh, IDESC_CAT, kk == 0 ? accum : 1u);
+                                    umma_bf16(d1, dal, dbh, IDESC, 1u);
+                                }
+                                continue;
+                            }
                             mma(d0, dah, dbh, kk == 0 ? accum : 1u);
                             if (X3) {
                                 const uint64_t dal = make_desc(a_lo + kk * 2 * A_LBO, A_LBO, A_SBO);
@@ -723,6 +790,7 @@ bool conv_tc_eligible(int Cin0, int Cin1, int Cout, int Tout, int taps, int stri
 int g_conv_tc_cluster = 2;          // CTAs per cluster sharing weight stages by multicast (1, 2 or 4); eegldm_set_conv_cluster
 int g_conv_tc_pair = 0;             // 1: cta_group::2 CTA pairs (M=256 per MMA); 0: single-CTA MMAs (+ multicast clusters)
 int g_conv_tc_bn256_stages = 1;     // minimum weight stages per tile for the N=256 shape
+int g_conv_tc_cat = 1;              // N=128 f16x3 tiles: a_hi x [w_hi | w_lo] as one N=256 MMA
 bool conv_tc_gn_ok(int Cout, int G) {
     if (G <= 0 || Cout % G) return false;
     const int cpg = Cout / G;
@@ -793,8 +861,10 @@ cudaError_t launch_conv_tc_t(const TcConvParams& p, int num_sms, cudaStream_t st
     return cudaLaunchKernelEx(&cfg, conv_tc_kernel<X3, BN, CL, PAIR, DIRECT>, p);
 }
 
-cudaError_t launch_conv_tc(const TcConvParams& p, bool x3, cudaStream_t st) {
-    if (p.nsegs16 <= 0) return cudaSuccess;
+cudaError_t launch_conv_tc(const TcConvParams& p_in, bool x3, cudaStream_t st) {
+    if (p_in.nsegs16 <= 0) return cudaSuccess;
+    TcConvParams p = p_in;
+    p.cat = g_conv_tc_cat;
     static int num_sms = 0;
     if (!num_sms) {
         int dev = 0;

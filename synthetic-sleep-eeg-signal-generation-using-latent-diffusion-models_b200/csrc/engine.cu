@@ -41,6 +41,11 @@ int fail(int code, const std::string& msg) {
     g_err = msg;
     return code;
 }
+}  // namespace
+namespace eegldm {
+void set_last_error(const std::string& msg) { g_err = msg; }
+}
+namespace {
 int cuda_fail(cudaError_t e, const char* what) {
     g_err = std::string(what) + ": " + cudaGetErrorString(e);
     return EEGLDM_ERR_CUDA;
@@ -193,7 +198,7 @@ struct Act {  // channels-last activation [B][T][C]
 using OpFn = std::function<cudaError_t(cudaStream_t)>;
 
 // per-launch bookkeeping for the live profile (eegldm_profile_*): algorithmic FLOPs / HBM bytes
-enum OpKind : int { OP_CONV = 0, OP_GN = 1, OP_ATTN = 2, OP_OTHER = 3, OP_SPLIT = 4, OP_NKIND = 5 };
+enum OpKind : int { OP_CONV = 0, OP_GN = 1, OP_ATTN = 2, OP_OTHER = 3, OP_SPLIT = 4, OP_CONV_SIMT = 5, OP_NKIND = 6 };   // OP_CONV: tcgen05 convs only
 struct OpMeta { int kind; double flops, bytes; };
 
 struct Builder {
@@ -718,7 +723,10 @@ void plan_conv(Builder& bd, ConvParams p, const uint8_t* tw0 = nullptr, const ui
         bd.add([q, x3](cudaStream_t st) { return launch_conv_tc(q, x3, st); }, 1, OP_CONV, flops, bytes);
         return;
     }
-    bd.add([p](cudaStream_t st) { return launch_conv_simt(p, st); }, 1, OP_CONV, flops, bytes);
+    // profile family: the narrow convs (1-channel in / out convs of the UNet, the 2-2-4 autoencoder) are HBM / latency-bound
+    // SIMT launches and are kept apart from the GEMM-shaped ones the roofline is quoted on
+    const bool narrow = p.seg[0].C0 + p.seg[0].C1 < 32 || p.Cout < 32;
+    bd.add([p](cudaStream_t st) { return launch_conv_simt(p, st); }, 1, narrow ? OP_CONV_SIMT : OP_CONV, flops, bytes);
 }
 
 Act plan_res(Builder& bd, const ULayer& l, const Act& x0, const Act* x1, const UNetIO& io) {
@@ -963,6 +971,23 @@ int run_ops(const Builder& bd, cudaStream_t st) {
         if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
         if (prof) { CU(cudaEventRecord(r.e1, st)); g_prof.push_back(r); }
     }
+    return EEGLDM_OK;
+}
+
+// one launch made outside a Builder plan (scheduler step bookkeeping, boundary scaling), recorded in the live profile as "other"
+template <class F>
+int run_profiled(int kind, double bytes, cudaStream_t st, F launch) {
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    const bool prof = g_profile && cudaStreamIsCapturing(st, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone;
+    ProfRec r{};
+    if (prof) {
+        r.m = OpMeta{kind, 0.0, bytes};
+        CU(cudaEventCreate(&r.e0)); CU(cudaEventCreate(&r.e1));
+        CU(cudaEventRecord(r.e0, st));
+    }
+    cudaError_t e = launch();
+    if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
+    if (prof) { CU(cudaEventRecord(r.e1, st)); g_prof.push_back(r); }
     return EEGLDM_OK;
 }
 
@@ -1354,6 +1379,7 @@ int eegldm_set_conv_tuning(int pair, int bn256_min_stages, int fuse_epilogues) {
     g_conv_direct = (fuse_epilogues & 4) != 0;
     g_attn_u_fused = (fuse_epilogues & 8) != 0;
     g_attn_direct = (fuse_epilogues & 16) != 0;
+    g_conv_tc_cat = (fuse_epilogues & 32) ? 0 : 1;   // bit 5 switches the concatenated hi|lo MMA of the N = 128 tiles OFF (A/B timing)
     if (bn256_min_stages < 1) return fail(EEGLDM_ERR_INVALID, "bn256_min_stages must be >= 1");
     g_conv_tc_pair = pair;
     g_conv_tc_bn256_stages = bn256_min_stages;
@@ -1376,7 +1402,7 @@ int eegldm_profile_record(int i, int* kind, double* ms, double* flops, double* b
     return EEGLDM_OK;
 }
 int eegldm_profile_read(int kind, double* ms, double* flops, double* bytes, int64_t* launches) {
-    if (kind < 0 || kind >= OP_NKIND) return fail(EEGLDM_ERR_INVALID, "kind must be 0 (conv), 1 (groupnorm), 2 (attention), 3 (other) or 4 (activation split)");
+    if (kind < 0 || kind >= OP_NKIND) return fail(EEGLDM_ERR_INVALID, "kind must be 0 (conv), 1 (groupnorm), 2 (attention), 3 (other), 4 (activation split) or 5 (narrow fp32 conv)");
     double t = 0, f = 0, b = 0; int64_t n = 0;
     for (auto& r : g_prof) {
         if (r.m.kind != kind) continue;
@@ -1659,8 +1685,9 @@ int eegldm_ddim_sample(eegldm_unet* u, eegldm_aekl* a, const eegldm_sched_cfg* s
     io.x = u->xbuf; io.out = u->xbuf; io.temb = u->temb_step; io.temb_stride = 0;
     io.ddim_x = u->xbuf; io.ddim_coef = u->coef_cur;
     auto emit_step = [&](const Builder& bd, cudaStream_t s) -> int {
-        cudaError_t e = launch_step_advance(u->temb_table, u->emb_total, u->temb_step, u->coef_table, u->coef_cur, u->step_ctr, s);
-        if (e != cudaSuccess) return cuda_fail(e, "step_advance");
+        int rr = run_profiled(OP_OTHER, 8.0 * u->emb_total, s, [&] {
+            return launch_step_advance(u->temb_table, u->emb_total, u->temb_step, u->coef_table, u->coef_cur, u->step_ctr, s); });
+        if (rr) return rr;
         return run_ops(bd, s);
     };
     if (g_graphs_enabled) {
@@ -1724,7 +1751,7 @@ int eegldm_ddim_sample(eegldm_unet* u, eegldm_aekl* a, const eegldm_sched_cfg* s
     }
     // decode_stage_2_outputs(latent / scale_factor)   sample_trials.py:166
     float* zs = u->xtmp;  // NCL staging for the decoder's boundary
-    if (z == 1) CU(launch_scale(u->xbuf, zs, 1.0f / scale_factor, nz, st));
+    if (z == 1) { r = run_profiled(OP_OTHER, 8.0 * nz, st, [&] { return launch_scale(u->xbuf, zs, 1.0f / scale_factor, nz, st); }); if (r) return r; }
     else {
         CU(launch_transpose_nlc_to_ncl(u->xbuf, zs + nz, B, z, T, st));
         CU(launch_scale(zs + nz, zs, 1.0f / scale_factor, nz, st));

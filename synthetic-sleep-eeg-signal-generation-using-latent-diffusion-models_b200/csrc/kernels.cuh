@@ -12,6 +12,8 @@
 
 namespace eegldm {
 
+// message returned by eegldm_last_error() (thread-local, engine.cu); for translation units other than engine.cu
+void set_last_error(const std::string& msg);
 // kernels launched by this library since process start (eegldm_launch_count)
 extern std::atomic<long long> g_launch_count;
 
@@ -115,6 +117,7 @@ struct TcConvParams {
     int direct;         // 1: activation operands produced inside the conv kernel from TcSeg.src0/src1 (no act_split pre-pass)
     int debug;          // timing experiments only (eegldm_bench_conv): 1 = no operand copies, 2 = no MMAs; results are garbage
     int* range_flag;    // optional (fused producer): set to 1 when an operand is outside the f16x3 range (|x| >= 65504 or NaN)
+    int cat;            // f16x3, bn == 128: issue a_hi x [w_hi | w_lo] as one N = 256 MMA (set by launch_conv_tc from g_conv_tc_cat)
     unsigned long long* timeline;   // optional (eegldm_bench_conv_timeline): per-CTA cycle counters, TC_TL_N per CTA
 };
 // per-CTA counters of the conv kernel's warp roles (cycles, summed over the CTA's tiles)
@@ -128,6 +131,7 @@ cudaError_t launch_conv_tc(const TcConvParams& p, bool x3, cudaStream_t st);
 extern int g_conv_tc_cluster;        // CTAs per cluster sharing weight stages (1, 2, 4) when g_conv_tc_pair == 0
 extern int g_conv_tc_pair;           // cta_group::2 CTA pairs (default 1)
 extern int g_conv_tc_bn256_stages;   // N=256 tiles from this many weight stages per tile
+extern int g_conv_tc_cat;            // N=128 f16x3 tiles: hi x [hi | lo] as one N=256 MMA (eegldm_set_conv_tuning bit 5)
 cudaError_t launch_groupnorm(const GnParams& p, cudaStream_t st);
 cudaError_t launch_groupnorm_finalize(const GnParams& p, cudaStream_t st);   // statistics already in p.partial (p.nsplit records)
 int groupnorm_nsplit(int C, int T, int G);

@@ -5,8 +5,7 @@
 // reference's full complex transform; the backward pass is one C2R:
 //   dL/dinput = C2R(H) / sqrt(N),  H_k = -2 (A_t[k] - A_i[k]) * F_i[k] / |F_i[k]|     (F unnormalised, A = |F| / sqrt(N))
 // cuFFT is loaded with dlopen at first use so that libeegldm.so has no link-time dependency on it.
-#include <cufft.h>
-#include <dlfcn.h>
+#include "cufft_api.h"
 
 #include <map>
 #include <mutex>
@@ -18,31 +17,6 @@
 namespace eegldm {
 namespace {
 
-struct CufftApi {
-    void* lib = nullptr;
-    cufftResult (*PlanMany)(cufftHandle*, int, int*, int*, int, int, int*, int, int, cufftType, int) = nullptr;
-    cufftResult (*SetStream)(cufftHandle, cudaStream_t) = nullptr;
-    cufftResult (*ExecR2C)(cufftHandle, cufftReal*, cufftComplex*) = nullptr;
-    cufftResult (*ExecC2R)(cufftHandle, cufftComplex*, cufftReal*) = nullptr;
-    cufftResult (*Destroy)(cufftHandle) = nullptr;
-    std::string err;
-    bool load() {
-        if (lib) return true;
-        for (const char* name : {"libcufft.so.11", "/usr/local/cuda/lib64/libcufft.so.11", "libcufft.so"}) {
-            lib = dlopen(name, RTLD_NOW | RTLD_LOCAL);
-            if (lib) break;
-        }
-        if (!lib) { err = "cannot dlopen libcufft.so.11"; return false; }
-        PlanMany = (decltype(PlanMany))dlsym(lib, "cufftPlanMany");
-        SetStream = (decltype(SetStream))dlsym(lib, "cufftSetStream");
-        ExecR2C = (decltype(ExecR2C))dlsym(lib, "cufftExecR2C");
-        ExecC2R = (decltype(ExecC2R))dlsym(lib, "cufftExecC2R");
-        Destroy = (decltype(Destroy))dlsym(lib, "cufftDestroy");
-        if (!PlanMany || !SetStream || !ExecR2C || !ExecC2R || !Destroy) { err = "libcufft is missing symbols"; return false; }
-        return true;
-    }
-};
-
 // cuFFT plans and their work areas belong to the device they were created on, and a scratch buffer may only be reused by
 // work ordered on the same stream: plans are keyed by (device, stream, N, batch), scratch by (device, stream).  The mutex covers the
 // host-side bookkeeping; launches on different streams use different scratch and do not race.
@@ -51,7 +25,7 @@ struct SpectralScratch {
     float* time = nullptr; size_t time_cap = 0;     // [B][N]
 };
 struct SpectralState {
-    CufftApi api;
+    CufftApi& api = cufft_api();
     std::map<std::tuple<int, cudaStream_t, int, int>, std::pair<cufftHandle, cufftHandle>> plans;   // (device, stream, N, batch) -> (r2c, c2r)
     std::map<std::pair<int, cudaStream_t>, SpectralScratch> scratch;                   // (device, stream)
     std::mutex mu;
@@ -96,6 +70,8 @@ __global__ void scale_store_kernel(const float* __restrict__ src, float* __restr
 }
 
 }  // namespace
+
+CufftApi& cufft_api() { static CufftApi api; return api; }
 
 // loss_dev += loss_weight * reduce(...);  grad_dev (+)= grad_weight * dloss/dinput   (grad_dev may be null)
 // reduction: 0 = sum, 1 = mean.  Returns 0 on success, 1 = cuFFT unavailable / failed (message in *err), else a cudaError_t.

@@ -8,6 +8,7 @@ Re-exposes, on top of the C ABI in ``include/eegldm.h`` (hand-written sm_100a CU
 * ``JukeboxLoss``          <- ``generative.losses.JukeboxLoss`` as used at ``src/train_autoencoderkl.py:158,208``
 * ``AutoencoderKL.train_step`` <- the generator half of the training step ``src/train_autoencoderkl.py:204-220``
 * ``ddim_sample``          <- the sampling loop ``src/sample_trials.py:153-169`` as one fused call
+* ``sample_tail`` / ``compute_psd`` <- the output tail ``src/sample_trials.py:169-197`` (crop, ``.npy``, MNE ``compute_psd``), batched
 
 PyTorch is used for device memory, streams and ``nn.Module`` plumbing only.
 """
@@ -17,6 +18,7 @@ from .aekl import AutoencoderKL  # noqa: F401
 from .schedulers import DDIMScheduler, DDPMScheduler  # noqa: F401
 from .losses import JukeboxLoss  # noqa: F401
 from .sampler import ddim_sample, ddim_sample_host, shard_range, sample_sharded  # noqa: F401
+from .output import compute_psd, crop_to_host, save_npy, save_windows, sample_tail, psd_freqs  # noqa: F401
 from . import synthetic  # noqa: F401
 
 

@@ -43,6 +43,12 @@ class AeklTrainCfg(C.Structure):
                 ("beta2", C.c_float), ("adam_eps", C.c_float)]
 
 
+class PsdCfg(C.Structure):
+    _fields_ = [("method", C.c_int32), ("sfreq", C.c_float), ("fmin", C.c_float), ("fmax", C.c_float), ("bandwidth", C.c_float),
+                ("low_bias", C.c_int32), ("normalization", C.c_int32), ("n_fft", C.c_int32), ("n_overlap", C.c_int32),
+                ("remove_dc", C.c_int32), ("db", C.c_int32)]
+
+
 class SchedCfg(C.Structure):
     _fields_ = [
         ("num_train_timesteps", C.c_int32), ("beta_start", C.c_float), ("beta_end", C.c_float),
@@ -100,6 +106,12 @@ SIGNATURES = {
     "eegldm_sched_ddim_tables": (C.c_int, [C.POINTER(SchedCfg), C.c_int, _I64P, _FP]),
     "eegldm_timestep_embedding": (C.c_int, [_FP, C.c_int, C.c_int, _FP]),
     "eegldm_ddim_sample": (C.c_int, [_P, _P, C.POINTER(SchedCfg), _P, C.c_float, C.c_int, _P, C.c_int, C.c_int, _P]),
+    "eegldm_psd_freqs": (C.c_int, [C.POINTER(PsdCfg), C.c_int, C.POINTER(C.c_int), _FP]),
+    "eegldm_psd": (C.c_int, [C.POINTER(PsdCfg), _P, C.c_int, C.c_int, C.c_int64, _P, _P]),
+    "eegldm_dpss": (C.c_int, [C.c_int, C.c_double, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "eegldm_crop_to_host": (C.c_int, [_P, C.c_int64, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "eegldm_write_npy_f32": (C.c_int, [C.c_char_p, _P, _I64P, C.c_int]),
+    "eegldm_save_windows_npy": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int64, _P, C.c_int, C.c_int, C.c_int]),
     "eegldm_test_conv_gn": (C.c_int, [_P, _P, _P] + [C.c_int] * 6 + [_P, _P, _P, _P]),
     "eegldm_test_qkv_attention": (C.c_int, [_P, _P, _P] + [C.c_int] * 4 + [_P, _P]),
     "eegldm_bench_conv": (C.c_int, [C.c_int] * 9 + [_P, _P]),

@@ -34,7 +34,7 @@ L = eegldm.lib()
 L.eegldm_profile_enable(1)
 m(x, timesteps=t)
 torch.cuda.synchronize()
-names = ["conv", "gn", "attn", "other", "split"]
+names = ["conv", "gn", "attn", "other", "split", "cnarrow"]
 i = 0
 tot = {}
 print(f"{'#':>4} {'kind':6} {'ms':>8} {'GFLOP':>9} {'TFLOP/s':>8} {'GB/s':>8}")
