@@ -196,6 +196,48 @@ int eegldm_aekl_train_export(eegldm_aekl* h, int what, const char* name, float* 
 int eegldm_aekl_train_sync(eegldm_aekl* h);
 
 /* ------------------------------------------------------------------------------------------------
+ * Discriminator: replaces generative.networks.nets.PatchDiscriminator as built at src/train_autoencoderkl.py:135-137 from
+ * config/config_aekl_eeg.yaml:30-40 (spatial_dims 1, norm "BATCH", bias false, LeakyReLU 0.2; kernel_size 3, padding 1).
+ * state_dict keys: initial_conv.conv.{weight,bias}, {l}.conv.weight, {l}.adn.N.{weight,bias,running_mean,running_var,
+ * num_batches_tracked}, final_conv.conv.{weight,bias}. */
+typedef struct {
+    int32_t in_channels;     /* 1 */
+    int32_t out_channels;    /* 1 */
+    int32_t num_channels;    /* 64 */
+    int32_t num_layers_d;    /* 3 */
+    int32_t kernel_size;     /* 3 */
+    int32_t padding;         /* 1 */
+} eegldm_disc_cfg;
+typedef struct eegldm_disc eegldm_disc;
+int eegldm_disc_create(const eegldm_disc_cfg* cfg, eegldm_disc** out);
+void eegldm_disc_destroy(eegldm_disc* h);
+int eegldm_disc_num_params(const eegldm_disc* h);
+/* entries include the BatchNorm buffers (is_buffer = 1; num_batches_tracked has ndim 0 and is carried as a float) */
+int eegldm_disc_param_info(const eegldm_disc* h, int i, const char** name, int64_t shape[4], int* ndim, int* is_buffer);
+int eegldm_disc_load(eegldm_disc* h, const char* name, const float* host, const int64_t* shape, int ndim);
+int eegldm_disc_finalize(eegldm_disc* h);
+/* PatchDiscriminator.forward(x)[-1]: x_dev [B, 1, L] -> logits_dev [B, 1, eegldm_disc_out_len(L)].  training != 0: BatchNorm uses
+ * batch statistics and updates the running ones (the reference never calls discriminator.eval()); else the running statistics. */
+int eegldm_disc_forward(eegldm_disc* h, const float* x_dev, float* logits_dev, int B, int L, int training, void* stream);
+int eegldm_disc_out_len(const eegldm_disc* h, int L);
+/* one state_dict entry in the reference layout: what = 0 value (parameters and buffers), 1 = gradient of the last step */
+int eegldm_disc_export(eegldm_disc* h, int what, const char* name, float* host_out);
+
+/* The FULL autoencoder training step, src/train_autoencoderkl.py:204-234:
+ *   loss_g = L1 + kl_weight * KL + spectral_weight * Jukebox + adv_weight * MSE(lrelu_0.05(D(recon)), 1);  backward;  Adam(lr_g)
+ *   loss_d = adv_weight * 0.5 * (MSE(lrelu_0.05(D(recon.detach())), 0) + MSE(lrelu_0.05(D(x)), 1));      backward;  Adam(lr_d)
+ * (PatchAdversarialLoss(criterion="least_squares"): the logits pass through LeakyReLU(0.05) unless no_activation_leastsq.)
+ * losses_host (nullable; synchronises) receives {l1, kl, spectral, total_g, generator_loss, discriminator_loss}. */
+typedef struct {
+    float kl_weight, spectral_weight, adv_weight;   /* 1e-9, 1e4, 0.01  (config_aekl_eeg.yaml:14-17) */
+    float lr_g, lr_d;                               /* 5e-3, 5e-4       (config_aekl_eeg.yaml:12-13) */
+    float beta1, beta2, adam_eps;
+    int32_t no_activation_leastsq;                  /* 0 (upstream default) */
+} eegldm_aekl_adv_train_cfg;
+int eegldm_aekl_train_step_adv(eegldm_aekl* h, eegldm_disc* disc, const float* x_dev, const float* eps_dev, int B, int L,
+                               const eegldm_aekl_adv_train_cfg* cfg, float* losses_host, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Scheduler + sampling loop: replaces generative.networks.schedulers.DDIMScheduler as used at
  * src/sample_trials.py:136-145 and the loop at src/sample_trials.py:153-166. */
 typedef struct {

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "eegldm", "libeegldm.so")
-SOURCES = ["engine.cu", "kernels_simt.cu", "conv_tc.cu", "attn_tc.cu", "train_kernels.cu", "spectral.cu", "psd.cu"]
+SOURCES = ["engine.cu", "kernels_simt.cu", "conv_tc.cu", "attn_tc.cu", "train_kernels.cu", "spectral.cu", "psd.cu", "disc.cu", "train_tc.cu"]
 OPTIONAL_SOURCES = []
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
 

@@ -72,9 +72,10 @@ constexpr int SPLIT_THREADS = 192;
 static_assert(N_ITEMS % SPLIT_THREADS == 0, "items must divide evenly over the act_split block");
 
 __device__ __forceinline__ float silu_fast(float v) { return __fdividef(v, 1.f + __expf(-v)); }
+// prologue activation after the affine: 0 none, 1 SiLU, 2 LeakyReLU(0.2) (PatchDiscriminator blocks)
 __device__ __forceinline__ float act(float x, float a, float s, int silu) {
     const float v = fmaf(a, x, s);
-    return silu ? silu_fast(v) : v;
+    return silu == 1 ? silu_fast(v) : (silu == 2 ? (v > 0.f ? v : 0.2f * v) : v);
 }
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 // SiLU on the bare special-function instructions: v * rcp(1 + ex2(-v * log2 e)).  ex2.approx.ftz needs none of __expf's
@@ -581,9 +582,12 @@ __global__ void __launch_bounds__(DIRECT ? 384 : NUM_THREADS, 1) conv_tc_kernel(
             for (int j = 0; j < 3; ++j) {
                 float v[8] = {C.x[j][0].x, C.x[j][0].y, C.x[j][0].z, C.x[j][0].w, C.x[j][1].x, C.x[j][1].y, C.x[j][1].z, C.x[j][1].w};
                 if ((ok >> j) & 1) {                     // padding / rows past the batch stay exactly zero
-                    if (silu) {
+                    if (silu == 1) {
 #pragma unroll
                         for (int e = 0; e < 8; ++e) v[e] = silu_ftz(fmaf(a[e], v[e], sh[e]));
+                    } else if (silu == 2) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) { const float u = fmaf(a[e], v[e], sh[e]); v[e] = u > 0.f ? u : 0.2f * u; }
                     } else {
 #pragma unroll
                         for (int e = 0; e < 8; ++e) v[e] = fmaf(a[e], v[e], sh[e]);   // no affine: a = 1, s = 0 (exact)

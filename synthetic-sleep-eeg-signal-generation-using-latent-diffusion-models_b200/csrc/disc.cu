@@ -1,0 +1,449 @@
+// PatchDiscriminator (monai-generative, as built at src/train_autoencoderkl.py:135-137 from config/config_aekl_eeg.yaml:30-40)
+// and the adversarial half of the autoencoder training step (train_autoencoderkl.py:213-234):
+//   generator term      adv_w * MSE(lrelu_0.05(D(recon)), 1)  -> gradient w.r.t. recon through D (BatchNorm in training mode)
+//   discriminator step  loss_d = adv_w * 0.5 * (MSE(act(D(recon.detach())), 0) + MSE(act(D(x)), 1));  backward;  Adam(lr_d)
+// Topology: initial_conv (in -> C, k3 s2 p1, bias, LeakyReLU 0.2) | layers l = 0..n-1 (C 2^l -> C 2^(l+1), s2 except the last,
+// no bias, BatchNorm1d, LeakyReLU 0.2) | final_conv (-> out, k3 s1, bias).
+//
+// Data flow (channels-last [B][T][C] like the rest of the engine): a block's norm + activation is never materialised in the
+// forward pass -- it is the prologue of the next conv (per-channel scale / shift + LeakyReLU), exactly as GroupNorm + SiLU are
+// for the UNet.  Backward: the data gradient of a conv is the forward conv kernel on transformed weights (stride 2: the input's
+// row pairs seen as one row of 2 Cin channels, launch_dgrad_weights), BatchNorm + LeakyReLU backward is two HBM-bound passes.
+// The fake pass is run ONCE and used for both the generator term and the discriminator step (the reference's second forward on
+// recon.detach() sees the same weights and the same input; its extra running-statistics update is applied).
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "disc.h"
+#include "eegldm.h"
+#include "kernels.cuh"
+
+using namespace eegldm;
+
+namespace {
+constexpr float BN_EPS = 1e-5f, BN_MOMENTUM = 0.1f, LEAKY = 0.2f;
+
+int dfail(int code, const std::string& m) { set_last_error(m); return code; }
+int dcuda(cudaError_t e, const char* what) { set_last_error(std::string(what) + ": " + cudaGetErrorString(e)); return EEGLDM_ERR_CUDA; }
+#define DCU(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) return dcuda(e__, #expr); } while (0)
+
+struct DParam { std::string name; std::vector<int64_t> shape; std::vector<float> data; bool loaded = false, buffer = false;
+                size_t numel() const { size_t n = 1; for (auto s : shape) n *= (size_t)s; return n; } };
+struct DLayer { std::string prefix; int cin, cout, stride, pad; bool has_bias, has_norm, has_act;
+                size_t ow = 0, ob = 0, og = 0, obe = 0, orm = 0, orv = 0; };   // offsets into P (parameters) / R (running statistics)
+}  // namespace
+
+struct DiscPass {   // saved tensors of one forward pass (pointers into the workspace)
+    const float* x = nullptr;
+    std::vector<float*> h;        // conv outputs (pre-norm), one per block
+    std::vector<float*> ss;       // [2][B][C] scale / shift of a block's norm (null: no norm)
+    std::vector<float*> mr;       // [2][C] mean / rstd
+    std::vector<int> T;           // output length per block
+    int B = 0, L = 0;
+    bool valid = false;
+};
+
+struct eegldm_disc {
+    eegldm_disc_cfg cfg{};
+    std::vector<DParam> params;
+    std::unordered_map<std::string, int> index;
+    std::vector<DLayer> layers;
+    bool finalized = false;
+    size_t nP = 0, nR = 0;
+    float *P = nullptr, *G = nullptr, *M = nullptr, *V = nullptr, *R = nullptr;   // parameters (SIMT conv images), grads, Adam moments, running stats
+    float* Wd = nullptr; size_t Wd_cap = 0;        // data-gradient weights of the layer being processed
+    double* sums = nullptr;                         // [2 * max C]
+    float* ws = nullptr; size_t ws_cap = 0, ws_off = 0;   // workspace (bump allocator, reset per training step / forward)
+    float* losses = nullptr;                        // device [4]: generator term, d_fake, d_real, spare
+    int step = 0;
+    long long batches_tracked = 0;
+    DiscPass fake, real;
+    ~eegldm_disc() { for (void* p : {(void*)P, (void*)G, (void*)M, (void*)V, (void*)R, (void*)Wd, (void*)sums, (void*)ws, (void*)losses}) if (p) cudaFree(p); }
+    float* alloc(size_t n) { n = (n + 63) & ~size_t(63); float* p = ws ? ws + ws_off : nullptr; ws_off += n; return p; }
+};
+
+namespace {
+
+int build_disc(eegldm_disc* d) {
+    const auto& c = d->cfg;
+    if (c.in_channels < 1 || c.out_channels < 1 || c.num_channels < 1 || c.num_layers_d < 1 || c.num_layers_d > 8)
+        return dfail(EEGLDM_ERR_INVALID, "bad discriminator config");
+    if (c.kernel_size != 3) return dfail(EEGLDM_ERR_INVALID, "PatchDiscriminator: kernel_size must be 3 (config_aekl_eeg.yaml:37)");
+    if (c.padding != 1) return dfail(EEGLDM_ERR_INVALID, "PatchDiscriminator: padding must be 1 (config_aekl_eeg.yaml:40)");
+    auto add = [&](const std::string& n, std::vector<int64_t> shape, bool buffer) {
+        d->index[n] = (int)d->params.size();
+        DParam p; p.name = n; p.shape = std::move(shape); p.buffer = buffer;
+        d->params.push_back(std::move(p));
+    };
+    auto layer = [&](const std::string& prefix, int cin, int cout, int stride, int pad, bool bias, bool norm, bool act) {
+        DLayer l{prefix, cin, cout, stride, pad, bias, norm, act};
+        add(prefix + ".conv.weight", {cout, cin, 3}, false);
+        if (bias) add(prefix + ".conv.bias", {cout}, false);
+        if (norm) {
+            add(prefix + ".adn.N.weight", {cout}, false); add(prefix + ".adn.N.bias", {cout}, false);
+            add(prefix + ".adn.N.running_mean", {cout}, true); add(prefix + ".adn.N.running_var", {cout}, true);
+            add(prefix + ".adn.N.num_batches_tracked", {}, true);
+        }
+        d->layers.push_back(l);
+    };
+    layer("initial_conv", c.in_channels, c.num_channels, 2, c.padding, true, false, true);
+    int cin = c.num_channels, cout = 2 * c.num_channels;
+    for (int l = 0; l < c.num_layers_d; ++l) {
+        layer(std::to_string(l), cin, cout, l == c.num_layers_d - 1 ? 1 : 2, c.padding, false, true, true);
+        cin = cout; cout *= 2;
+    }
+    layer("final_conv", cin, c.out_channels, 1, (c.kernel_size - 1) / 2, true, false, false);
+    return EEGLDM_OK;
+}
+
+const std::vector<float>& pget(const eegldm_disc* d, const std::string& n) { return d->params[d->index.at(n)].data; }
+
+int finalize_disc(eegldm_disc* d) {
+    for (auto& p : d->params) if (!p.loaded) return dfail(EEGLDM_ERR_MISSING, "missing state_dict key: " + p.name);
+    std::vector<float> flat, run;
+    auto push = [](std::vector<float>& dst, const float* src, size_t n) {
+        const size_t off = (dst.size() + 63) & ~size_t(63);
+        dst.resize(off + n);
+        std::memcpy(dst.data() + off, src, n * sizeof(float));
+        return off;
+    };
+    for (auto& l : d->layers) {
+        const auto& w = pget(d, l.prefix + ".conv.weight");
+        std::vector<float> pk((size_t)l.cout * l.cin * 3);
+        for (int co = 0; co < l.cout; ++co)
+            for (int ci = 0; ci < l.cin; ++ci)
+                for (int k = 0; k < 3; ++k) pk[((size_t)ci * 3 + k) * l.cout + co] = w[((size_t)co * l.cin + ci) * 3 + k];
+        l.ow = push(flat, pk.data(), pk.size());
+        if (l.has_bias) { const auto& b = pget(d, l.prefix + ".conv.bias"); l.ob = push(flat, b.data(), b.size()); }
+        if (l.has_norm) {
+            const auto& g = pget(d, l.prefix + ".adn.N.weight"); l.og = push(flat, g.data(), g.size());
+            const auto& b = pget(d, l.prefix + ".adn.N.bias"); l.obe = push(flat, b.data(), b.size());
+            const auto& rm = pget(d, l.prefix + ".adn.N.running_mean"); l.orm = push(run, rm.data(), rm.size());
+            const auto& rv = pget(d, l.prefix + ".adn.N.running_var"); l.orv = push(run, rv.data(), rv.size());
+            d->batches_tracked = (long long)pget(d, l.prefix + ".adn.N.num_batches_tracked")[0];
+        }
+    }
+    d->nP = (flat.size() + 63) & ~size_t(63);
+    flat.resize(d->nP, 0.f);
+    d->nR = std::max<size_t>((run.size() + 63) & ~size_t(63), 64);
+    run.resize(d->nR, 0.f);
+    for (float** p : {&d->P, &d->G, &d->M, &d->V, &d->R}) if (*p) { cudaFree(*p); *p = nullptr; }
+    DCU(cudaMalloc((void**)&d->P, d->nP * sizeof(float)));
+    DCU(cudaMalloc((void**)&d->G, d->nP * sizeof(float)));
+    DCU(cudaMalloc((void**)&d->M, d->nP * sizeof(float)));
+    DCU(cudaMalloc((void**)&d->V, d->nP * sizeof(float)));
+    DCU(cudaMalloc((void**)&d->R, d->nR * sizeof(float)));
+    DCU(cudaMemcpy(d->P, flat.data(), d->nP * sizeof(float), cudaMemcpyHostToDevice));
+    DCU(cudaMemcpy(d->R, run.data(), d->nR * sizeof(float), cudaMemcpyHostToDevice));
+    DCU(cudaMemset(d->G, 0, d->nP * sizeof(float)));
+    DCU(cudaMemset(d->M, 0, d->nP * sizeof(float)));
+    DCU(cudaMemset(d->V, 0, d->nP * sizeof(float)));
+    int maxc = 1;
+    for (auto& l : d->layers) maxc = std::max(maxc, l.cout);
+    if (!d->sums) DCU(cudaMalloc((void**)&d->sums, (size_t)2 * 4096 * sizeof(double)));
+    if (maxc > 4096) return dfail(EEGLDM_ERR_INVALID, "discriminator wider than 4096 channels");
+    if (!d->losses) DCU(cudaMalloc((void**)&d->losses, 4 * sizeof(float)));
+    d->step = 0;
+    d->fake.valid = d->real.valid = false;
+    d->finalized = true;
+    return EEGLDM_OK;
+}
+
+int out_len(int Tin, const DLayer& l) { return (Tin + 2 * l.pad - 3) / l.stride + 1; }
+
+// workspace floats of one forward pass (+ backward temporaries when training)
+size_t pass_floats(const eegldm_disc* d, int B, int L, bool backward) {
+    size_t n = 0, maxact = 0;
+    int T = L;
+    for (auto& l : d->layers) {
+        const size_t in_n = (size_t)B * T * l.cin;
+        T = out_len(T, l);
+        const size_t out_n = (size_t)B * T * l.cout;
+        n += ((out_n + 63) & ~size_t(63)) + ((size_t)2 * B * l.cout + 64) + ((size_t)2 * l.cout + 64);
+        maxact = std::max(maxact, std::max(in_n, out_n));
+    }
+    if (backward) n += 3 * ((maxact + 63) & ~size_t(63)) + 256;   // dh, da, materialised conv input
+    return n + 1024;
+}
+
+int ensure_ws(eegldm_disc* d, size_t floats) {
+    if (floats <= d->ws_cap) return EEGLDM_OK;
+    if (d->ws) { cudaFree(d->ws); d->ws = nullptr; d->ws_cap = 0; }
+    DCU(cudaMalloc((void**)&d->ws, floats * sizeof(float)));
+    d->ws_cap = floats;
+    return EEGLDM_OK;
+}
+
+// D(x): x [B][L][in] channels-last.  training: batch statistics (running statistics updated n_updates times), else running ones.
+int disc_forward(eegldm_disc* d, const float* x, int B, int L, bool training, int n_updates, DiscPass& ps, cudaStream_t st) {
+    ps.x = x; ps.B = B; ps.L = L; ps.h.clear(); ps.ss.clear(); ps.mr.clear(); ps.T.clear();
+    const float* in = x;
+    const float *scale = nullptr, *shift = nullptr;
+    int act = 0, T = L;
+    for (auto& l : d->layers) {
+        const int Tout = out_len(T, l);
+        if (Tout < 1) return dfail(EEGLDM_ERR_SHAPE, "signal too short for the discriminator");
+        float* h = d->alloc((size_t)B * Tout * l.cout);
+        ConvParams p{};
+        p.seg[0] = ConvSeg{in, nullptr, l.cin, 0, scale, shift, act, RS_NONE, T, d->P + l.ow, 3};
+        p.nseg = 1; p.Cout = l.cout; p.Tout = Tout; p.Tc = T; p.stride = l.stride; p.pad_left = l.pad;
+        p.bias = l.has_bias ? d->P + l.ob : nullptr; p.out = h; p.B = B;
+        DCU(launch_conv_simt(p, st));
+        float *ss = nullptr, *mr = nullptr;
+        if (l.has_norm) {
+            ss = d->alloc((size_t)2 * B * l.cout);
+            mr = d->alloc((size_t)2 * l.cout);
+            if (training) {
+                DCU(launch_bn_stats(h, (size_t)B * Tout, l.cout, d->P + l.og, d->P + l.obe, BN_EPS, B, d->sums, ss, ss + (size_t)B * l.cout, mr,
+                                    mr + l.cout, d->R + l.orm, d->R + l.orv, BN_MOMENTUM, n_updates, st));
+            } else {   // eval(): normalise with the running statistics -- a per-channel affine, computed on the host side of the stream
+                std::vector<float> run(2 * (size_t)l.cout), par(2 * (size_t)l.cout), hs((size_t)2 * B * l.cout);
+                DCU(cudaMemcpyAsync(run.data(), d->R + l.orm, l.cout * sizeof(float), cudaMemcpyDeviceToHost, st));
+                DCU(cudaMemcpyAsync(run.data() + l.cout, d->R + l.orv, l.cout * sizeof(float), cudaMemcpyDeviceToHost, st));
+                DCU(cudaMemcpyAsync(par.data(), d->P + l.og, l.cout * sizeof(float), cudaMemcpyDeviceToHost, st));
+                DCU(cudaMemcpyAsync(par.data() + l.cout, d->P + l.obe, l.cout * sizeof(float), cudaMemcpyDeviceToHost, st));
+                DCU(cudaStreamSynchronize(st));
+                for (int c = 0; c < l.cout; ++c) {
+                    const float sc = par[c] / std::sqrt(run[l.cout + c] + BN_EPS), sh = par[l.cout + c] - run[c] * sc;
+                    for (int b = 0; b < B; ++b) { hs[(size_t)b * l.cout + c] = sc; hs[((size_t)B + b) * l.cout + c] = sh; }
+                }
+                DCU(cudaMemcpyAsync(ss, hs.data(), hs.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+                DCU(cudaStreamSynchronize(st));
+            }
+        }
+        ps.h.push_back(h); ps.ss.push_back(ss); ps.mr.push_back(mr); ps.T.push_back(Tout);
+        in = h; T = Tout;
+        scale = ss; shift = ss ? ss + (size_t)B * l.cout : nullptr;
+        act = l.has_act ? 2 : 0;
+    }
+    ps.valid = true;
+    return EEGLDM_OK;
+}
+
+// Backward sweep through a saved pass.  dlogits: gradient w.r.t. the final conv's output (overwritten freely).  wgrad: accumulate the
+// parameter gradients into G.  dx (nullable): receives (accumulate: +=) the gradient w.r.t. the input signal.
+int disc_backward(eegldm_disc* d, const DiscPass& ps, float* dlogits, bool wgrad, float* dx, int dx_accumulate, cudaStream_t st) {
+    const int B = ps.B, nl = (int)d->layers.size();
+    size_t maxact = 0;
+    { int T = ps.L; for (int i = 0; i < nl; ++i) { maxact = std::max(maxact, (size_t)B * T * d->layers[i].cin); T = ps.T[i]; maxact = std::max(maxact, (size_t)B * T * d->layers[i].cout); } }
+    float* buf_a = d->alloc(maxact);    // gradient w.r.t. a conv's input (post-activation)
+    float* buf_h = d->alloc(maxact);    // gradient w.r.t. a conv's output (pre-norm)
+    float* buf_in = wgrad ? d->alloc(maxact) : nullptr;   // materialised conv input for the weight gradient
+    float* dh = dlogits;
+    for (int i = nl - 1; i >= 0; --i) {
+        const DLayer& l = d->layers[i];
+        const int Tin = i ? ps.T[i - 1] : ps.L, Tout = ps.T[i];
+        const float* in_raw = i ? ps.h[i - 1] : ps.x;            // the conv's input before the previous block's norm + activation
+        const DLayer* prev = i ? &d->layers[i - 1] : nullptr;
+        if (wgrad) {
+            const float* a = in_raw;
+            if (prev && (prev->has_norm || prev->has_act)) {
+                DCU(launch_affine_lrelu(in_raw, prev->has_norm ? ps.ss[i - 1] : nullptr, prev->has_norm ? ps.ss[i - 1] + (size_t)B * prev->cout : nullptr,
+                                        prev->cout, prev->has_act ? LEAKY : 1.f, buf_in, (size_t)B * Tin * l.cin, st));
+                a = buf_in;
+            }
+            ConvGradParams g{};
+            g.dy = dh; g.a = a; g.w = d->P + l.ow; g.dw = d->G + l.ow; g.db = l.has_bias ? d->G + l.ob : nullptr;
+            g.Cin = l.cin; g.Cout = l.cout; g.taps = 3; g.stride = l.stride; g.pad = l.pad; g.ups = 0; g.Tin = Tin; g.Tc = Tin; g.Tout = Tout; g.B = B;
+            DCU(launch_conv_bwd_weight(g, st));
+        }
+        const bool need_da = i > 0 || dx != nullptr;
+        if (!need_da) break;
+        // data gradient through the forward conv kernel on transformed weights
+        const bool z2 = l.stride == 2;
+        if (z2 && (Tin & 1)) return dfail(EEGLDM_ERR_SHAPE, "discriminator backward: odd length before a stride-2 conv");
+        const int cod = z2 ? 2 * l.cin : l.cin;
+        const size_t nwd = (size_t)l.cout * 3 * cod;
+        if (nwd > d->Wd_cap) { if (d->Wd) cudaFree(d->Wd); d->Wd = nullptr; d->Wd_cap = 0; DCU(cudaMalloc((void**)&d->Wd, nwd * sizeof(float))); d->Wd_cap = nwd; }
+        DCU(launch_dgrad_weights(d->P + l.ow, l.cin, l.cout, l.stride, d->Wd, st));
+        float* da = (i == 0 && !dx_accumulate) ? dx : buf_a;
+        ConvParams p{};
+        p.seg[0] = ConvSeg{dh, nullptr, l.cout, 0, nullptr, nullptr, 0, RS_NONE, Tout, d->Wd, 3};
+        p.nseg = 1; p.Cout = cod; p.Tout = Tout; p.Tc = Tout; p.stride = 1; p.pad_left = 1; p.out = da; p.B = B;
+        if (!z2 && Tout != Tin) return dfail(EEGLDM_ERR_SHAPE, "discriminator backward: stride-1 conv must keep the length");
+        DCU(launch_conv_simt(p, st));
+        if (i == 0) {
+            if (dx_accumulate) DCU(launch_axpy(buf_a, dx, 1.f, 1, (size_t)B * Tin * l.cin, st));
+            break;
+        }
+        // through the previous block's activation (+ norm): da -> gradient w.r.t. that block's conv output
+        const size_t n = (size_t)B * Tin * prev->cout;
+        if (prev->has_norm)
+            DCU(launch_bn_lrelu_bwd(da, in_raw, ps.mr[i - 1], ps.mr[i - 1] + prev->cout, d->P + prev->og, d->P + prev->obe, (size_t)B * Tin, prev->cout,
+                                    prev->has_act ? LEAKY : 1.f, d->sums, buf_h, wgrad ? d->G + prev->og : nullptr, wgrad ? d->G + prev->obe : nullptr, st));
+        else if (prev->has_act) DCU(launch_lrelu_bwd(da, in_raw, LEAKY, buf_h, n, st));
+        else DCU(cudaMemcpyAsync(buf_h, da, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        dh = buf_h;
+    }
+    return EEGLDM_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ hooks used by the autoencoder step
+namespace eegldm {
+
+int disc_prepare_step(eegldm_disc* d, int B, int L, cudaStream_t st) {
+    if (!d || !d->finalized) return dfail(EEGLDM_ERR_MISSING, "eegldm_disc_finalize has not been called");
+    if (d->cfg.in_channels != 1) return dfail(EEGLDM_ERR_INVALID, "adversarial step: the discriminator must take the 1-channel signal");
+    const size_t need = 2 * pass_floats(d, B, L, false) + pass_floats(d, B, L, true) + (size_t)4 * B * (L / 8 + 8);
+    int r = ensure_ws(d, need);
+    if (r) return r;
+    d->ws_off = 0;
+    d->fake.valid = d->real.valid = false;
+    DCU(cudaMemsetAsync(d->losses, 0, 4 * sizeof(float), st));
+    return EEGLDM_OK;
+}
+
+// generator term: loss_dev[0] += MSE(act(D(recon)), 1) (unweighted, as the reference logs it); drecon += adv_weight * d(that)/d recon
+int disc_generator_term(eegldm_disc* d, const float* recon, int B, int L, float adv_weight, int no_act, float* drecon, cudaStream_t st) {
+    int r = disc_forward(d, recon, B, L, true, /*n_updates=*/2, d->fake, st);
+    if (r) return r;
+    const size_t n = (size_t)B * d->fake.T.back() * d->cfg.out_channels;
+    float* dl = d->alloc(n);
+    DCU(launch_adv_loss(d->fake.h.back(), n, 1.f, no_act ? 1.f : 0.05f, 1.f, d->losses + 0, adv_weight, dl, st));
+    const size_t mark = d->ws_off;
+    r = disc_backward(d, d->fake, dl, /*wgrad=*/false, drecon, /*accumulate=*/1, st);
+    d->ws_off = mark;   // the sweep's temporaries are free again
+    return r;
+}
+
+// discriminator step on the saved fake pass and a fresh real pass; losses[1] = d_fake, losses[2] = d_real (unweighted)
+int disc_step(eegldm_disc* d, const float* x_real, int B, int L, float adv_weight, int no_act, float lr, float b1, float b2, float eps,
+              cudaStream_t st) {
+    if (!d->fake.valid) return dfail(EEGLDM_ERR_INVALID, "discriminator step without a generator term");
+    DCU(cudaMemsetAsync(d->G, 0, d->nP * sizeof(float), st));
+    const float slope = no_act ? 1.f : 0.05f;
+    const size_t n = (size_t)B * d->fake.T.back() * d->cfg.out_channels;
+    float* dl = d->alloc(n);
+    size_t mark = d->ws_off;
+    DCU(launch_adv_loss(d->fake.h.back(), n, 0.f, slope, 1.f, d->losses + 1, 0.5f * adv_weight, dl, st));
+    int r = disc_backward(d, d->fake, dl, true, nullptr, 0, st);
+    if (r) return r;
+    d->ws_off = mark;
+    r = disc_forward(d, x_real, B, L, true, 1, d->real, st);
+    if (r) return r;
+    mark = d->ws_off;
+    DCU(launch_adv_loss(d->real.h.back(), n, 1.f, slope, 1.f, d->losses + 2, 0.5f * adv_weight, dl, st));
+    r = disc_backward(d, d->real, dl, true, nullptr, 0, st);
+    if (r) return r;
+    d->ws_off = mark;
+    if (d->ws_off > d->ws_cap) return dfail(EEGLDM_ERR_NOMEM, "discriminator workspace overflow");
+    d->batches_tracked += 3;
+    if (lr > 0.f) {
+        d->step += 1;
+        DCU(launch_adam(d->P, d->G, d->M, d->V, lr, b1, b2, eps, d->step, d->nP, st));
+    }
+    return EEGLDM_OK;
+}
+
+const float* disc_losses_dev(const eegldm_disc* d) { return d->losses; }
+
+}  // namespace eegldm
+
+// ------------------------------------------------------------------------------------------------ C ABI
+extern "C" {
+
+int eegldm_disc_create(const eegldm_disc_cfg* cfg, eegldm_disc** out) {
+    if (!cfg || !out) return dfail(EEGLDM_ERR_INVALID, "null argument");
+    auto* d = new (std::nothrow) eegldm_disc();
+    if (!d) return dfail(EEGLDM_ERR_NOMEM, "out of host memory");
+    d->cfg = *cfg;
+    int r = build_disc(d);
+    if (r) { delete d; return r; }
+    *out = d;
+    return EEGLDM_OK;
+}
+void eegldm_disc_destroy(eegldm_disc* d) { delete d; }
+int eegldm_disc_num_params(const eegldm_disc* d) { return d ? (int)d->params.size() : 0; }
+int eegldm_disc_param_info(const eegldm_disc* d, int i, const char** name, int64_t shape[4], int* ndim, int* is_buffer) {
+    if (!d || i < 0 || i >= (int)d->params.size()) return dfail(EEGLDM_ERR_INVALID, "bad parameter index");
+    const DParam& p = d->params[i];
+    if (name) *name = p.name.c_str();
+    if (ndim) *ndim = (int)p.shape.size();
+    if (shape) for (size_t k = 0; k < p.shape.size() && k < 4; ++k) shape[k] = p.shape[k];
+    if (is_buffer) *is_buffer = p.buffer ? 1 : 0;
+    return EEGLDM_OK;
+}
+int eegldm_disc_load(eegldm_disc* d, const char* name, const float* host, const int64_t* shape, int ndim) {
+    if (!d || !name || !host || (ndim > 0 && !shape)) return dfail(EEGLDM_ERR_INVALID, "null argument");
+    std::string key(name);
+    if (key.rfind("module.", 0) == 0) key = key.substr(7);
+    auto it = d->index.find(key);
+    if (it == d->index.end()) return dfail(EEGLDM_ERR_MISSING, "unexpected state_dict key: " + key);
+    DParam& p = d->params[it->second];
+    bool ok = (int)p.shape.size() == ndim;
+    for (int i = 0; ok && i < ndim; ++i) ok = p.shape[i] == shape[i];
+    if (!ok) return dfail(EEGLDM_ERR_SHAPE, "shape mismatch for " + key);
+    p.data.assign(host, host + p.numel());
+    p.loaded = true;
+    d->finalized = false;
+    return EEGLDM_OK;
+}
+int eegldm_disc_finalize(eegldm_disc* d) {
+    if (!d) return dfail(EEGLDM_ERR_INVALID, "null handle");
+    return finalize_disc(d);
+}
+
+int eegldm_disc_forward(eegldm_disc* d, const float* x_dev, float* logits_dev, int B, int L, int training, void* stream) {
+    if (!d) return dfail(EEGLDM_ERR_INVALID, "null handle");
+    if (!d->finalized) return dfail(EEGLDM_ERR_MISSING, "eegldm_disc_finalize has not been called");
+    if (d->cfg.in_channels != 1 || d->cfg.out_channels != 1)
+        return dfail(EEGLDM_ERR_INVALID, "discriminator forward: in / out channels must be 1 (config_aekl_eeg.yaml:34-35)");
+    if (B < 0 || L < 8) return dfail(EEGLDM_ERR_SHAPE, "bad input shape");
+    if (B == 0) return EEGLDM_OK;
+    if (!x_dev || !logits_dev) return dfail(EEGLDM_ERR_INVALID, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    int r = ensure_ws(d, pass_floats(d, B, L, false));
+    if (r) return r;
+    d->ws_off = 0;
+    DiscPass ps;
+    r = disc_forward(d, x_dev, B, L, training != 0, 1, ps, st);
+    if (r) return r;
+    if (training) d->batches_tracked += 1;
+    DCU(cudaMemcpyAsync(logits_dev, ps.h.back(), (size_t)B * ps.T.back() * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    d->fake.valid = d->real.valid = false;
+    return EEGLDM_OK;
+}
+
+int eegldm_disc_out_len(const eegldm_disc* d, int L) {
+    if (!d) return -1;
+    int T = L;
+    for (auto& l : d->layers) T = out_len(T, l);
+    return T;
+}
+
+// what: 0 = parameter / buffer value, 1 = gradient of the last discriminator step (parameters only); reference layout
+int eegldm_disc_export(eegldm_disc* d, int what, const char* name, float* host_out) {
+    if (!d || !name || !host_out) return dfail(EEGLDM_ERR_INVALID, "null argument");
+    if (!d->finalized) return dfail(EEGLDM_ERR_MISSING, "eegldm_disc_finalize has not been called");
+    if (what != 0 && what != 1) return dfail(EEGLDM_ERR_INVALID, "what must be 0 (value) or 1 (gradient)");
+    const std::string key(name);
+    DCU(cudaDeviceSynchronize());
+    for (auto& l : d->layers) {
+        const std::string& p = l.prefix;
+        const float* base = what ? d->G : d->P;
+        if (key == p + ".conv.weight") {
+            std::vector<float> pk((size_t)l.cout * l.cin * 3);
+            DCU(cudaMemcpy(pk.data(), base + l.ow, pk.size() * sizeof(float), cudaMemcpyDeviceToHost));
+            for (int co = 0; co < l.cout; ++co)
+                for (int ci = 0; ci < l.cin; ++ci)
+                    for (int k = 0; k < 3; ++k) host_out[((size_t)co * l.cin + ci) * 3 + k] = pk[((size_t)ci * 3 + k) * l.cout + co];
+            return EEGLDM_OK;
+        }
+        if (l.has_bias && key == p + ".conv.bias") { DCU(cudaMemcpy(host_out, base + l.ob, l.cout * sizeof(float), cudaMemcpyDeviceToHost)); return EEGLDM_OK; }
+        if (l.has_norm) {
+            if (key == p + ".adn.N.weight") { DCU(cudaMemcpy(host_out, base + l.og, l.cout * sizeof(float), cudaMemcpyDeviceToHost)); return EEGLDM_OK; }
+            if (key == p + ".adn.N.bias") { DCU(cudaMemcpy(host_out, base + l.obe, l.cout * sizeof(float), cudaMemcpyDeviceToHost)); return EEGLDM_OK; }
+            if (what == 0 && key == p + ".adn.N.running_mean") { DCU(cudaMemcpy(host_out, d->R + l.orm, l.cout * sizeof(float), cudaMemcpyDeviceToHost)); return EEGLDM_OK; }
+            if (what == 0 && key == p + ".adn.N.running_var") { DCU(cudaMemcpy(host_out, d->R + l.orv, l.cout * sizeof(float), cudaMemcpyDeviceToHost)); return EEGLDM_OK; }
+            if (what == 0 && key == p + ".adn.N.num_batches_tracked") { host_out[0] = (float)d->batches_tracked; return EEGLDM_OK; }
+        }
+    }
+    return dfail(EEGLDM_ERR_MISSING, "unknown state_dict key: " + key);
+}
+
+}  // extern "C"

@@ -24,6 +24,7 @@
 #include <unordered_map>
 #include <vector>
 
+#include "disc.h"
 #include "eegldm.h"
 #include "kernels.cuh"
 
@@ -2286,8 +2287,10 @@ int eegldm_jukebox_loss(const float* input_dev, const float* target_dev, int B, 
     return EEGLDM_OK;
 }
 
-int eegldm_aekl_train_step(eegldm_aekl* h, const float* x_dev, const float* eps_dev, int B, int L, const eegldm_aekl_train_cfg* cfg,
-                           float* losses_host, void* stream) {
+// one training step; disc == null: the generator half only (eegldm_aekl_train_step), else the full step of
+// train_autoencoderkl.py:204-234 (eegldm_aekl_train_step_adv).  losses_host: {l1, kl, spectral, total_g[, gen_adv, disc]}
+static int aekl_train_step_impl(eegldm_aekl* h, eegldm_disc* disc, const float* x_dev, const float* eps_dev, int B, int L,
+                                const eegldm_aekl_train_cfg* cfg, float adv_weight, float lr_d, int no_act, float* losses_host, void* stream) {
     if (!h || !cfg) return fail(EEGLDM_ERR_INVALID, "null argument");
     if (h->cfg.in_channels != 1 || h->cfg.out_channels != 1)
         return fail(EEGLDM_ERR_INVALID, "training step supports in/out_channels = 1 (every reference config)");
@@ -2337,22 +2340,52 @@ int eegldm_aekl_train_step(eegldm_aekl* h, const float* x_dev, const float* eps_
         if (sr == 1) return fail(EEGLDM_ERR_CUDA, "cuFFT: " + err);
         if (sr) return cuda_fail((cudaError_t)sr, "spectral loss");
     }
+    if (disc) {   // logits_fake = D(recon)[-1]; generator_loss = adv_loss(logits_fake, real) -- its gradient joins d loss / d recon
+        r = disc_prepare_step(disc, B, L, st);
+        if (r) return r;
+        r = disc_generator_term(disc, recon.p, B, L, adv_weight, no_act, gr.first, st);
+        if (r) return r;
+    }
     tr.backward(cfg->kl_weight);
     if (tr.err != cudaSuccess) return cuda_fail(tr.err, "training backward");
     if (tr.off > t.arena_cap) return fail(EEGLDM_ERR_NOMEM, "training arena overflow");
     CU(launch_axpy(t.losses + 0, t.losses + 3, 1.f, 0, 1, st));
     CU(launch_axpy(t.losses + 1, t.losses + 3, cfg->kl_weight, 1, 1, st));
     CU(launch_axpy(t.losses + 2, t.losses + 3, cfg->spectral_weight, 1, 1, st));
+    if (disc) CU(launch_axpy(disc_losses_dev(disc) + 0, t.losses + 3, adv_weight, 1, 1, st));
     if (cfg->lr > 0.f) {
         t.step += 1;
         CU(launch_adam(t.P, t.G, t.M, t.V, cfg->lr, cfg->beta1, cfg->beta2, cfg->adam_eps, t.step, t.n, st));
         t.dirty = true;
     }
+    if (disc) {   // discriminator part (train_autoencoderkl.py:223-234): recon is the pre-update reconstruction, detached
+        r = disc_step(disc, x_dev, B, L, adv_weight, no_act, lr_d, cfg->beta1, cfg->beta2, cfg->adam_eps, st);
+        if (r) return r;
+    }
     if (losses_host) {
         CU(cudaMemcpyAsync(losses_host, t.losses, 4 * sizeof(float), cudaMemcpyDeviceToHost, st));
+        if (disc) {
+            float dl[4];
+            CU(cudaMemcpyAsync(dl, disc_losses_dev(disc), 4 * sizeof(float), cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            losses_host[4] = dl[0];                      // generator_loss  (train_autoencoderkl.py:214)
+            losses_host[5] = 0.5f * (dl[1] + dl[2]);     // discriminator_loss (:229)
+        }
         CU(cudaStreamSynchronize(st));
     }
     return EEGLDM_OK;
+}
+
+int eegldm_aekl_train_step(eegldm_aekl* h, const float* x_dev, const float* eps_dev, int B, int L, const eegldm_aekl_train_cfg* cfg,
+                           float* losses_host, void* stream) {
+    return aekl_train_step_impl(h, nullptr, x_dev, eps_dev, B, L, cfg, 0.f, 0.f, 0, losses_host, stream);
+}
+
+int eegldm_aekl_train_step_adv(eegldm_aekl* h, eegldm_disc* disc, const float* x_dev, const float* eps_dev, int B, int L,
+                               const eegldm_aekl_adv_train_cfg* cfg, float* losses_host, void* stream) {
+    if (!cfg || !disc) return fail(EEGLDM_ERR_INVALID, "null argument");
+    eegldm_aekl_train_cfg g{cfg->kl_weight, cfg->spectral_weight, cfg->lr_g, cfg->beta1, cfg->beta2, cfg->adam_eps};
+    return aekl_train_step_impl(h, disc, x_dev, eps_dev, B, L, &g, cfg->adv_weight, cfg->lr_d, cfg->no_activation_leastsq, losses_host, stream);
 }
 
 int eegldm_aekl_train_export(eegldm_aekl* h, int what, const char* name, float* host_out) {

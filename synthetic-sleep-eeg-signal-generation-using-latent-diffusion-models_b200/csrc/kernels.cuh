@@ -27,7 +27,7 @@ struct ConvSeg {
     int C0, C1;
     const float* scale;  // [B][C0+C1] GroupNorm scale (gamma*rstd) or null
     const float* shift;  // [B][C0+C1] GroupNorm shift (beta-mean*gamma*rstd)
-    int silu;            // SiLU after the affine
+    int silu;            // activation after the affine: 0 none, 1 SiLU, 2 LeakyReLU(0.2)
     int resample;        // Resample applied AFTER act (unet.py:308-313)
     int Tin;             // source length (before resample)
     const float* w;      // packed [(ci*taps+k)][Cout]
@@ -198,6 +198,32 @@ cudaError_t launch_axpy(const float* src, float* dst, float alpha, int accumulat
 cudaError_t launch_l1_loss(const float* r, const float* x, float* dr, float* loss, float weight, size_t n, cudaStream_t st);
 cudaError_t launch_latent(const float* mu, const float* lv, const float* eps, float* sigma, float* z, const float* dz, float* dmu,
                           float* dlv, float* kl_loss, float kl_weight, int B, size_t n, cudaStream_t st);
+// ---- PatchDiscriminator / adversarial loss (train_kernels.cu): BatchNorm1d in training mode over channels-last rows [N][C]
+cudaError_t launch_bn_stats(const float* h, size_t N, int C, const float* gamma, const float* beta, float eps, int B, double* sums /*[2C]*/,
+                            float* scale /*[B][C]*/, float* shift, float* mean /*[C]*/, float* rstd, float* run_mean, float* run_var,
+                            float momentum, int n_updates, cudaStream_t st);
+cudaError_t launch_bn_lrelu_bwd(const float* da, const float* h, const float* mean, const float* rstd, const float* gamma,
+                                const float* beta, size_t N, int C, float slope, double* sums, float* dh, float* dgamma /*nullable: +=*/,
+                                float* dbeta, cudaStream_t st);
+cudaError_t launch_lrelu_bwd(const float* da, const float* h, float slope, float* dh, size_t n, cudaStream_t st);
+cudaError_t launch_affine_lrelu(const float* h, const float* scale /*[C] or null*/, const float* shift, int C, float slope, float* a,
+                                size_t n, cudaStream_t st);
+cudaError_t launch_adv_loss(const float* logits, size_t n, float target, float act_slope, float loss_weight, float* loss /*+=*/,
+                            float grad_weight, float* dlogits, cudaStream_t st);
+cudaError_t launch_dgrad_weights(const float* w, int Cin, int Cout, int stride, float* wd, cudaStream_t st);
+// ---- tensor-pipe training pieces (train_tc.cu)
+constexpr int WG_CHUNK = 32;   // positions per K chunk of the weight-gradient GEMM
+size_t conv_tc_image_u16(int Cin, int Cout, int k);   // 16-bit elements of a tcgen05 weight image
+cudaError_t launch_pack_conv_tc_dev(const float* w_simt, int Cin, int Cout, int k, uint16_t* out, cudaStream_t st);   // f16x3 image from a SIMT image
+cudaError_t launch_s2z_weights(const float* w, int Cin, int Cout, float* wv, cudaStream_t st);          // stride-2 conv as a conv over row pairs
+cudaError_t launch_s2z_grad_fold(const float* dwv, int Cin, int Cout, float* dw, cudaStream_t st);
+cudaError_t launch_colsum(const float* x, size_t N, int C, float* out /*+=*/, cudaStream_t st);
+bool wgrad_tc_eligible(int Cin, int Cout, int T);
+size_t wgrad_image_bytes(size_t rows_total, int C, int halo);
+cudaError_t launch_wgrad_split(const float* src, const float* scale, const float* shift, int ss_bstride, int act, int B, int T, int C,
+                               int halo, uint8_t* img, cudaStream_t st);
+cudaError_t launch_wgrad_tc(const uint8_t* a_img, const uint8_t* dy_img, float* dw /*[(ci*ktot+tap)][Cout], +=*/, int B, int T, int Cin,
+                            int Cout, int ktot, int tap0, int ntaps, cudaStream_t st);
 cudaError_t launch_adam(float* p, const float* g, float* m, float* v, float lr, float b1, float b2, float eps, int step, size_t n,
                         cudaStream_t st);
 

@@ -19,9 +19,10 @@ constexpr int XP = 2 * BN + 4; // smem pitch of the activation tile (covers the 
 
 __device__ __forceinline__ float silu_f(float v) { return v / (1.f + expf(-v)); }
 
+// prologue activation after the affine: 0 none, 1 SiLU (UNet / autoencoder), 2 LeakyReLU(0.2) (PatchDiscriminator)
 __device__ __forceinline__ float act1(float x, float a, float s, int silu) {
     float v = fmaf(a, x, s);
-    return silu ? silu_f(v) : v;
+    return silu == 1 ? silu_f(v) : (silu == 2 ? (v > 0.f ? v : 0.2f * v) : v);
 }
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }

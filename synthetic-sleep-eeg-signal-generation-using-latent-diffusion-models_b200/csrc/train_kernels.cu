@@ -589,6 +589,131 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 
 unsigned blocks_for(size_t n, int bs = 256) { return (unsigned)((n + bs - 1) / bs); }
 
+// ---- PatchDiscriminator pieces (train_autoencoderkl.py:213-234): BatchNorm1d in training mode over rows h [N = B*T][C]
+// ---- (channels-last), LeakyReLU, the least-squares adversarial loss.  Per-channel sums are accumulated in double (one atomic
+// ---- per channel per block): var = E[x^2] - E[x]^2 is then free of the fp32 cancellation.
+constexpr int BN_ROWS = 64;   // rows per block
+__device__ __forceinline__ float lrelu_grad(float v, float slope) { return v > 0.f ? 1.f : slope; }
+
+__global__ void __launch_bounds__(256) bn_sums_kernel(const float* __restrict__ h, size_t N, int C, double* __restrict__ sums) {
+    const size_t r0 = (size_t)blockIdx.x * BN_ROWS, r1 = min(N, r0 + BN_ROWS);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float s = 0.f, q = 0.f;
+        for (size_t r = r0; r < r1; ++r) { const float v = h[r * C + c]; s += v; q = fmaf(v, v, q); }
+        atomicAdd(sums + c, (double)s);
+        atomicAdd(sums + C + c, (double)q);
+    }
+}
+// mean / rstd [C]; scale = gamma * rstd, shift = beta - mean * scale replicated over the B samples (the conv prologues index
+// [b][c]); running statistics updated n_updates times with momentum (unbiased variance), as nn.BatchNorm1d does per forward call
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, size_t N, int C, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float eps, int B, float* __restrict__ scale, float* __restrict__ shift,
+                                   float* __restrict__ mean_out, float* __restrict__ rstd_out, float* __restrict__ run_mean,
+                                   float* __restrict__ run_var, float momentum, int n_updates) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const double mu = sums[c] / (double)N;
+    double var = sums[C + c] / (double)N - mu * mu;
+    if (var < 0.0) var = 0.0;
+    const float rs = (float)(1.0 / sqrt(var + (double)eps));
+    mean_out[c] = (float)mu; rstd_out[c] = rs;
+    const float sc = gamma[c] * rs, sh = beta[c] - (float)mu * sc;
+    for (int b = 0; b < B; ++b) { scale[(size_t)b * C + c] = sc; shift[(size_t)b * C + c] = sh; }
+    if (run_mean) {
+        const float uv = (float)(N > 1 ? var * (double)N / (double)(N - 1) : var);
+        float rm = run_mean[c], rv = run_var[c];
+        for (int i = 0; i < n_updates; ++i) { rm = (1.f - momentum) * rm + momentum * (float)mu; rv = (1.f - momentum) * rv + momentum * uv; }
+        run_mean[c] = rm; run_var[c] = rv;
+    }
+}
+// backward of a = lrelu(xhat * gamma + beta): pass 1, per-channel sums of dv and dv * xhat (dv = da * lrelu'(v))
+__global__ void __launch_bounds__(256) bn_bwd_sums_kernel(const float* __restrict__ da, const float* __restrict__ h,
+                                                           const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                           const float* __restrict__ gamma, const float* __restrict__ beta, size_t N, int C,
+                                                           float slope, double* __restrict__ sums) {
+    const size_t r0 = (size_t)blockIdx.x * BN_ROWS, r1 = min(N, r0 + BN_ROWS);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const float mu = mean[c], rs = rstd[c], ga = gamma[c], be = beta[c];
+        float s1 = 0.f, s2 = 0.f;
+        for (size_t r = r0; r < r1; ++r) {
+            const float xh = (h[r * C + c] - mu) * rs;
+            const float dv = da[r * C + c] * lrelu_grad(fmaf(xh, ga, be), slope);
+            s1 += dv; s2 = fmaf(dv, xh, s2);
+        }
+        atomicAdd(sums + c, (double)s1);
+        atomicAdd(sums + C + c, (double)s2);
+    }
+}
+// pass 2: dh = gamma * rstd * (dv - mean(dv) - xhat * mean(dv * xhat));  block 0 also adds dgamma = sum dv*xhat, dbeta = sum dv
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restrict__ da, const float* __restrict__ h,
+                                                            const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                            const double* __restrict__ sums, size_t N, int C, float slope,
+                                                            float* __restrict__ dh, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    const size_t r0 = (size_t)blockIdx.x * BN_ROWS, r1 = min(N, r0 + BN_ROWS);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const float mu = mean[c], rs = rstd[c], ga = gamma[c], be = beta[c];
+        const float m1 = (float)(sums[c] / (double)N), m2 = (float)(sums[C + c] / (double)N);
+        for (size_t r = r0; r < r1; ++r) {
+            const float xh = (h[r * C + c] - mu) * rs;
+            const float dv = da[r * C + c] * lrelu_grad(fmaf(xh, ga, be), slope);
+            dh[r * C + c] = ga * rs * (dv - m1 - xh * m2);
+        }
+        if (blockIdx.x == 0 && dgamma) { dgamma[c] += (float)sums[C + c]; dbeta[c] += (float)sums[c]; }
+    }
+}
+// dh = da * lrelu'(h)   (activation without a norm: the discriminator's initial_conv)
+__global__ void lrelu_bwd_kernel(const float* __restrict__ da, const float* __restrict__ h, float slope, float* __restrict__ dh, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dh[i] = da[i] * lrelu_grad(h[i], slope);
+}
+// a = lrelu(scale[c] * h + shift[c])   (materialised conv input for the weight-gradient kernels; scale == null: a = lrelu(h))
+__global__ void affine_lrelu_kernel(const float* __restrict__ h, const float* __restrict__ scale, const float* __restrict__ shift, int C,
+                                    float slope, float* __restrict__ a, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int c = (int)(i % C);
+    const float v = scale ? fmaf(scale[c], h[i], shift[c]) : h[i];
+    a[i] = v > 0.f ? v : slope * v;
+}
+// PatchAdversarialLoss(criterion="least_squares"): y = lrelu_{act_slope}(logit) (act_slope = 1: no activation);
+// loss += loss_weight * mean((y - target)^2);  dlogit = grad_weight * 2 (y - target) / n * lrelu'(logit)
+__global__ void __launch_bounds__(256) adv_loss_kernel(const float* __restrict__ logits, size_t n, float target, float act_slope,
+                                                        float loss_weight, float* __restrict__ loss, float grad_weight,
+                                                        float* __restrict__ dlogits) {
+    __shared__ float red[32];
+    float s[1] = {0.f};
+    const float inv = 1.f / (float)n;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float z = logits[i];
+        const float y = z > 0.f ? z : act_slope * z;
+        const float d = y - target;
+        s[0] = fmaf(d, d, s[0]);
+        if (dlogits) dlogits[i] = grad_weight * 2.f * d * inv * (z > 0.f ? 1.f : act_slope);
+    }
+    block_reduce_sum<1>(s, red);
+    if (threadIdx.x == 0 && loss) atomicAdd(loss, loss_weight * s[0] * inv);
+}
+// Weights of the convolution that computes a conv's input gradient, built from the forward weights (SIMT image
+// [(ci*3 + k)][Cout], k = 3, padding 1) so that the data gradient runs through the forward conv kernels:
+//   stride 1:  da = conv3_same(dy, Wd),  Wd[(co*3 + k)][ci] = W[(ci*3 + 2-k)][co]                       (Cin_d = Cout, Cout_d = Cin)
+//   stride 2:  rows 2t, 2t+1 of the input seen as ONE row of 2 Cin channels (channels-last: the same memory):
+//              dz[t][0:Cin] = W1^T dy[t],  dz[t][Cin:2Cin] = W2^T dy[t] + W0^T dy[t+1]                     (Cin_d = Cout, Cout_d = 2 Cin)
+__global__ void dgrad_weights_kernel(const float* __restrict__ w, int Cin, int Cout, int stride, float* __restrict__ wd) {
+    const int cod = stride == 1 ? Cin : 2 * Cin;
+    const size_t total = (size_t)Cout * 3 * cod;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c2 = (int)(i % cod);
+    const int k = (int)((i / cod) % 3);
+    const int co = (int)(i / ((size_t)cod * 3));
+    float v = 0.f;
+    if (stride == 1) v = w[(size_t)(c2 * 3 + (2 - k)) * Cout + co];
+    else if (k == 1) v = c2 < Cin ? w[(size_t)(c2 * 3 + 1) * Cout + co] : w[(size_t)((c2 - Cin) * 3 + 2) * Cout + co];
+    else if (k == 2) v = c2 >= Cin ? w[(size_t)((c2 - Cin) * 3 + 0) * Cout + co] : 0.f;
+    wd[i] = v;
+}
+
 }  // namespace
 
 cudaError_t launch_norm_act_fwd(const float* x, const float* scale, const float* shift, float* a, int B, int T, int C, int silu,
@@ -712,6 +837,68 @@ cudaError_t launch_adam(float* p, const float* g, float* m, float* v, float lr, 
     if (!n) return cudaSuccess;
     const float bc1 = 1.f - powf(b1, (float)step), bc2 = 1.f - powf(b2, (float)step);
     adam_kernel<<<blocks_for(n), 256, 0, st>>>(p, g, m, v, lr, b1, b2, eps, bc1, sqrtf(bc2), n);
+    g_launch_count += 1;
+    return cudaGetLastError();
+}
+
+}  // namespace eegldm
+
+namespace eegldm {
+
+cudaError_t launch_bn_stats(const float* h, size_t N, int C, const float* gamma, const float* beta, float eps, int B, double* sums,
+                            float* scale, float* shift, float* mean, float* rstd, float* run_mean, float* run_var, float momentum,
+                            int n_updates, cudaStream_t st) {
+    if (!N || C <= 0) return cudaSuccess;
+    cudaError_t e = cudaMemsetAsync(sums, 0, (size_t)2 * C * sizeof(double), st);
+    if (e != cudaSuccess) return e;
+    bn_sums_kernel<<<(unsigned)((N + BN_ROWS - 1) / BN_ROWS), 256, 0, st>>>(h, N, C, sums);
+    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, N, C, gamma, beta, eps, B, scale, shift, mean, rstd, run_mean, run_var, momentum,
+                                                        n_updates);
+    g_launch_count += 2;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_bn_lrelu_bwd(const float* da, const float* h, const float* mean, const float* rstd, const float* gamma,
+                                const float* beta, size_t N, int C, float slope, double* sums, float* dh, float* dgamma, float* dbeta,
+                                cudaStream_t st) {
+    if (!N || C <= 0) return cudaSuccess;
+    cudaError_t e = cudaMemsetAsync(sums, 0, (size_t)2 * C * sizeof(double), st);
+    if (e != cudaSuccess) return e;
+    const unsigned nb = (unsigned)((N + BN_ROWS - 1) / BN_ROWS);
+    bn_bwd_sums_kernel<<<nb, 256, 0, st>>>(da, h, mean, rstd, gamma, beta, N, C, slope, sums);
+    bn_bwd_apply_kernel<<<nb, 256, 0, st>>>(da, h, mean, rstd, gamma, beta, sums, N, C, slope, dh, dgamma, dbeta);
+    g_launch_count += 2;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_lrelu_bwd(const float* da, const float* h, float slope, float* dh, size_t n, cudaStream_t st) {
+    if (!n) return cudaSuccess;
+    lrelu_bwd_kernel<<<blocks_for(n), 256, 0, st>>>(da, h, slope, dh, n);
+    g_launch_count += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_affine_lrelu(const float* h, const float* scale, const float* shift, int C, float slope, float* a, size_t n,
+                                cudaStream_t st) {
+    if (!n) return cudaSuccess;
+    affine_lrelu_kernel<<<blocks_for(n), 256, 0, st>>>(h, scale, shift, C, slope, a, n);
+    g_launch_count += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_adv_loss(const float* logits, size_t n, float target, float act_slope, float loss_weight, float* loss,
+                            float grad_weight, float* dlogits, cudaStream_t st) {
+    if (!n) return cudaSuccess;
+    const unsigned blocks = (unsigned)std::min<size_t>((n + 255) / 256, 148 * 4);
+    adv_loss_kernel<<<blocks, 256, 0, st>>>(logits, n, target, act_slope, loss_weight, loss, grad_weight, dlogits);
+    g_launch_count += 1;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_dgrad_weights(const float* w, int Cin, int Cout, int stride, float* wd, cudaStream_t st) {
+    const size_t total = (size_t)Cout * 3 * (stride == 1 ? Cin : 2 * Cin);
+    if (!total) return cudaSuccess;
+    dgrad_weights_kernel<<<blocks_for(total), 256, 0, st>>>(w, Cin, Cout, stride, wd);
     g_launch_count += 1;
     return cudaGetLastError();
 }

@@ -17,6 +17,7 @@ from .unet import UNetModel  # noqa: F401
 from .aekl import AutoencoderKL  # noqa: F401
 from .schedulers import DDIMScheduler, DDPMScheduler  # noqa: F401
 from .losses import JukeboxLoss  # noqa: F401
+from .discriminator import PatchDiscriminator, PatchAdversarialLoss  # noqa: F401
 from .sampler import ddim_sample, ddim_sample_host, shard_range, sample_sharded  # noqa: F401
 from .output import compute_psd, crop_to_host, save_npy, save_windows, sample_tail, psd_freqs  # noqa: F401
 from . import synthetic  # noqa: F401

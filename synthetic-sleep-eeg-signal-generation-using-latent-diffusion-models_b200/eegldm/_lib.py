@@ -43,6 +43,17 @@ class AeklTrainCfg(C.Structure):
                 ("beta2", C.c_float), ("adam_eps", C.c_float)]
 
 
+class DiscCfg(C.Structure):
+    _fields_ = [("in_channels", C.c_int32), ("out_channels", C.c_int32), ("num_channels", C.c_int32), ("num_layers_d", C.c_int32),
+                ("kernel_size", C.c_int32), ("padding", C.c_int32)]
+
+
+class AeklAdvTrainCfg(C.Structure):
+    _fields_ = [("kl_weight", C.c_float), ("spectral_weight", C.c_float), ("adv_weight", C.c_float), ("lr_g", C.c_float),
+                ("lr_d", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("adam_eps", C.c_float),
+                ("no_activation_leastsq", C.c_int32)]
+
+
 class PsdCfg(C.Structure):
     _fields_ = [("method", C.c_int32), ("sfreq", C.c_float), ("fmin", C.c_float), ("fmax", C.c_float), ("bandwidth", C.c_float),
                 ("low_bias", C.c_int32), ("normalization", C.c_int32), ("n_fft", C.c_int32), ("n_overlap", C.c_int32),
@@ -106,6 +117,16 @@ SIGNATURES = {
     "eegldm_sched_ddim_tables": (C.c_int, [C.POINTER(SchedCfg), C.c_int, _I64P, _FP]),
     "eegldm_timestep_embedding": (C.c_int, [_FP, C.c_int, C.c_int, _FP]),
     "eegldm_ddim_sample": (C.c_int, [_P, _P, C.POINTER(SchedCfg), _P, C.c_float, C.c_int, _P, C.c_int, C.c_int, _P]),
+    "eegldm_disc_create": (C.c_int, [C.POINTER(DiscCfg), C.POINTER(_P)]),
+    "eegldm_disc_destroy": (None, [_P]),
+    "eegldm_disc_num_params": (C.c_int, [_P]),
+    "eegldm_disc_param_info": (C.c_int, [_P, C.c_int, C.POINTER(C.c_char_p), _I64P, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "eegldm_disc_load": (C.c_int, [_P, C.c_char_p, _P, _I64P, C.c_int]),
+    "eegldm_disc_finalize": (C.c_int, [_P]),
+    "eegldm_disc_forward": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
+    "eegldm_disc_out_len": (C.c_int, [_P, C.c_int]),
+    "eegldm_disc_export": (C.c_int, [_P, C.c_int, C.c_char_p, _FP]),
+    "eegldm_aekl_train_step_adv": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.POINTER(AeklAdvTrainCfg), _FP, _P]),
     "eegldm_psd_freqs": (C.c_int, [C.POINTER(PsdCfg), C.c_int, C.POINTER(C.c_int), _FP]),
     "eegldm_psd": (C.c_int, [C.POINTER(PsdCfg), _P, C.c_int, C.c_int, C.c_int64, _P, _P]),
     "eegldm_dpss": (C.c_int, [C.c_int, C.c_double, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),

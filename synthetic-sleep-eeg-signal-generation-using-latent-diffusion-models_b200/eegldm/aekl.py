@@ -106,12 +106,38 @@ class AutoencoderKL(EngineModule):
         return out
 
     # --- training step (generator half of src/train_autoencoderkl.py:204-220) ------------------------
+    def attach_discriminator(self, discriminator=None, seed=None, adv_weight=0.01, lr_d=5e-4, **disc_kwargs):
+        """Make ``train_step`` the FULL step of train_autoencoderkl.py:204-234 by default: keeps ``discriminator`` (or builds
+        the reference's ``PatchDiscriminator(num_layers_d=3, num_channels=64, kernel_size=3)``, config_aekl_eeg.yaml:30-40)."""
+        from .discriminator import PatchDiscriminator
+        if discriminator is None:
+            if seed is not None:
+                torch.manual_seed(seed)
+            kw = dict(spatial_dims=1, num_layers_d=3, num_channels=64, in_channels=1, out_channels=1, kernel_size=3, norm="BATCH",
+                      bias=False, padding=1)
+            kw.update(disc_kwargs)
+            discriminator = PatchDiscriminator(**kw)
+        dev = next(self.parameters()).device
+        object.__setattr__(self, "_disc", discriminator.to(dev))   # not a sub-module: its parameters belong to optimizer_d
+        self._adv_weight, self._lr_d = adv_weight, lr_d
+        return discriminator
+
     def train_step(self, x, eps=None, kl_weight=1e-9, spectral_weight=1e4, lr=5e-3, betas=(0.9, 0.999), adam_eps=1e-8,
-                   return_losses=True):
+                   return_losses=True, discriminator=None, adv_weight=None, lr_d=None, no_activation_leastsq=False):
         """One fused step on the device: forward, L1 + kl_weight*KL + spectral_weight*JukeboxLoss, backward, Adam.
         ``eps`` is the reparameterisation noise (drawn with torch.randn if omitted); ``lr <= 0`` computes losses and
         gradients only.  Parameters are updated inside the engine; call ``sync_trained()`` to copy them back into this
-        module's ``nn.Parameter``s / the inference weights.  Returns {"l1", "kl", "spectral", "total"} (one sync)."""
+        module's ``nn.Parameter``s / the inference weights.  Returns {"l1", "kl", "spectral", "total"} (one sync).
+
+        With ``discriminator`` (an ``eegldm.PatchDiscriminator``, or one attached by ``attach_discriminator``) this is the
+        whole step of train_autoencoderkl.py:204-234: the generator loss gains ``adv_weight * MSE(lrelu(D(recon)), 1)`` and the
+        discriminator takes its own step (``lr_d``) on ``0.5 * (MSE(lrelu(D(recon.detach())), 0) + MSE(lrelu(D(x)), 1))``;
+        the returned dict then also has ``"generator"`` and ``"discriminator"``."""
+        disc = discriminator if discriminator is not None else getattr(self, "_disc", None)
+        if disc is not None:
+            return self._train_step_adv(x, eps, disc, kl_weight, spectral_weight, lr, betas, adam_eps, return_losses,
+                                        getattr(self, "_adv_weight", 0.01) if adv_weight is None else adv_weight,
+                                        getattr(self, "_lr_d", 5e-4) if lr_d is None else lr_d, no_activation_leastsq)
         x = check_cuda_f32(x, "x")
         B, Cin, Lx = x.shape
         T = Lx // self._factor
@@ -128,6 +154,28 @@ class AutoencoderKL(EngineModule):
         self._trained = True
         if return_losses:
             return {"l1": out[0], "kl": out[1], "spectral": out[2], "total": out[3]}
+        return None
+
+    def _train_step_adv(self, x, eps, disc, kl_weight, spectral_weight, lr, betas, adam_eps, return_losses, adv_weight, lr_d, no_act):
+        x = check_cuda_f32(x, "x")
+        B, Cin, Lx = x.shape
+        T = Lx // self._factor
+        if eps is None:
+            eps = torch.randn((B, self.latent_channels, T), device=x.device, dtype=torch.float32)
+        eps = check_cuda_f32(eps, "eps")
+        cfg = _lib.AeklAdvTrainCfg(float(kl_weight), float(spectral_weight), float(adv_weight), float(lr), float(lr_d), float(betas[0]),
+                                   float(betas[1]), float(adam_eps), int(bool(no_act)))
+        out = (C.c_float * 6)()
+        with torch.cuda.device(x.device):
+            self._sync_weights()
+            disc._sync_weights()
+            _lib.check(_lib.lib().eegldm_aekl_train_step_adv(
+                self._h, disc._h, C.c_void_p(x.data_ptr()), C.c_void_p(eps.data_ptr()), int(B), int(Lx), C.byref(cfg),
+                out if return_losses else None, C.c_void_p(_lib.current_stream_ptr(x.device))))
+        self._trained = True
+        disc._trained = True
+        if return_losses:
+            return {"l1": out[0], "kl": out[1], "spectral": out[2], "total": out[3], "generator": out[4], "discriminator": out[5]}
         return None
 
     def _export(self, what: int):

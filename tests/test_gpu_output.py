@@ -77,5 +77,5 @@ def test_sample_tail_end_to_end(built_lib, cuda_device, tmp_path):
     np.testing.assert_allclose(np.load(tmp_path / "psd.npy"), rdb, atol=2e-3)
     assert np.load(tmp_path / "psd_list.npy", allow_pickle=True).shape[0] == 6
     # empty batch
-    p, f = eegldm.compute_psd(torch.zeros(0, 1, 3072, device=cuda_device), fmax=18.0)
+    p, f = eegldm.compute_psd(torch.zeros(0, 1, 3072, device=cuda_device), fmax=18.0, crop=36)
     assert p.shape == (0, 1, 541)
