@@ -226,29 +226,41 @@ def measure_train(args, dev, B=512, with_cpu=True):
                         "note": "autoencoder activations only (6 passes x fp32); with the discriminator the step is conv-FLOP bound, "
                                 "see DESIGN.md section 4.5"}}
     if with_cpu:
-        # CPU baseline: the oracle with torch autograd + Adam, bounded sample (the only use of oracle/ in this function)
-        from oracle import aekl as oa, jukebox as oj
+        # CPU baseline: the oracle with torch autograd + Adam, bounded sample (the only use of oracle/ in this function); with the
+        # discriminator attached it is the same full step (generator and discriminator halves, train_autoencoderkl.py:204-234)
+        from oracle import aekl as oa, jukebox as oj, discriminator as od
         threads = os.cpu_count() or 1
         torch.set_num_threads(threads)
-        Bc = 16
+        Bc, n = (4, 2) if adv else (16, 5)
         params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
         opt = torch.optim.Adam(list(params.values()), lr=5e-3)
         xc, ec = xh[:Bc].clone(), eh[:Bc].clone()
+        if adv:
+            dcfg = od.full_cfg()
+            dp = {k: (v.clone().requires_grad_(True) if not od.is_buffer(k) else v.clone()) for k, v in od.make_disc_state_dict(dcfg, 7).items()}
+            opt_d = torch.optim.Adam([v for k, v in dp.items() if not od.is_buffer(k)], lr=5e-4)
 
         def cpu_step():
             opt.zero_grad(set_to_none=True)
             recon, mu, sigma = oa.forward(cfg, params, xc, ec)
             loss = torch.nn.functional.l1_loss(recon, xc) + 1e-9 * oa.kl_loss(mu, sigma) + 1e4 * oj.jukebox_loss(recon, xc)
+            if adv:
+                loss = loss + 0.01 * od.patch_adversarial_loss(od.forward(dcfg, dp, recon.contiguous())[-1], True, False)
             loss.backward()
             opt.step()
+            if adv:
+                opt_d.zero_grad(set_to_none=True)
+                lf = od.patch_adversarial_loss(od.forward(dcfg, dp, recon.contiguous().detach())[-1], False, True)
+                lr_ = od.patch_adversarial_loss(od.forward(dcfg, dp, xc.contiguous())[-1], True, True)
+                (0.01 * 0.5 * (lf + lr_)).backward()
+                opt_d.step()
         cpu_step()
         t0 = time.perf_counter()
-        n = 5
         for _ in range(n):
             cpu_step()
         out["cpu_baseline"] = {"value": Bc * n / (time.perf_counter() - t0), "unit": "windows/s", "cores": threads, "kind": "port",
-                               "batch": Bc, "sample": f"{Bc} windows x {n} steps, oracle autoencoder forward + torch autograd + Adam "
-                                                      "(generator half only)"}
+                               "batch": Bc, "sample": f"{Bc} windows x {n} steps, oracle autoencoder" + (" + discriminator" if adv else "") +
+                                                      " forward, torch autograd, Adam" + ("" if adv else " (generator half only)")}
     return out
 
 

@@ -220,6 +220,9 @@ int eegldm_disc_finalize(eegldm_disc* h);
  * batch statistics and updates the running ones (the reference never calls discriminator.eval()); else the running statistics. */
 int eegldm_disc_forward(eegldm_disc* h, const float* x_dev, float* logits_dev, int B, int L, int training, void* stream);
 int eegldm_disc_out_len(const eegldm_disc* h, int L);
+/* EEGLDM_MATH_F16X3_TC (default): the 64->128->256->512 convs, their data gradients (the forward kernel on transformed weights) and
+ * their weight gradients (split-K GEMM over the positions) run on tcgen05 in the f16x3 arithmetic; EEGLDM_MATH_FP32_SIMT: fp32 FMA. */
+int eegldm_disc_set_math(eegldm_disc* h, int mode);
 /* one state_dict entry in the reference layout: what = 0 value (parameters and buffers), 1 = gradient of the last step */
 int eegldm_disc_export(eegldm_disc* h, int what, const char* name, float* host_out);
 

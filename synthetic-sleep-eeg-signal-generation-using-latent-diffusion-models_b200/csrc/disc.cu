@@ -33,7 +33,9 @@ int dcuda(cudaError_t e, const char* what) { set_last_error(std::string(what) + 
 struct DParam { std::string name; std::vector<int64_t> shape; std::vector<float> data; bool loaded = false, buffer = false;
                 size_t numel() const { size_t n = 1; for (auto s : shape) n *= (size_t)s; return n; } };
 struct DLayer { std::string prefix; int cin, cout, stride, pad; bool has_bias, has_norm, has_act;
-                size_t ow = 0, ob = 0, og = 0, obe = 0, orm = 0, orv = 0; };   // offsets into P (parameters) / R (running statistics)
+                size_t ow = 0, ob = 0, og = 0, obe = 0, orm = 0, orv = 0;     // offsets into P (parameters) / R (running statistics)
+                // tensor-pipe form (f16x3): the conv runs as a stride-1 conv over cin_v = stride * cin channels (stride 2: row pairs)
+                bool tc = false; int cin_v = 0, cod = 0; size_t o_imgf = 0, o_imgd = 0; };   // offsets (u16) into the image pool
 }  // namespace
 
 struct DiscPass {   // saved tensors of one forward pass (pointers into the workspace)
@@ -42,6 +44,7 @@ struct DiscPass {   // saved tensors of one forward pass (pointers into the work
     std::vector<float*> ss;       // [2][B][C] scale / shift of a block's norm (null: no norm)
     std::vector<float*> mr;       // [2][C] mean / rstd
     std::vector<int> T;           // output length per block
+    std::vector<int> rp;          // copies of scale / shift per sample (2: the consumer reads row pairs)
     int B = 0, L = 0;
     bool valid = false;
 };
@@ -55,13 +58,17 @@ struct eegldm_disc {
     size_t nP = 0, nR = 0;
     float *P = nullptr, *G = nullptr, *M = nullptr, *V = nullptr, *R = nullptr;   // parameters (SIMT conv images), grads, Adam moments, running stats
     float* Wd = nullptr; size_t Wd_cap = 0;        // data-gradient weights of the layer being processed
+    int math = EEGLDM_MATH_F16X3_TC;                // tensor-pipe convs where the shapes allow (eegldm_disc_set_math)
+    uint16_t* img = nullptr; size_t img_n = 0;      // tcgen05 weight images (forward + data-gradient) of the tensor-pipe layers
+    float* wv = nullptr; size_t wv_n = 0;           // scratch: virtual (row-pair / transposed) weights in the SIMT image, and their gradient
+    bool images_dirty = true;
     double* sums = nullptr;                         // [2 * max C]
     float* ws = nullptr; size_t ws_cap = 0, ws_off = 0;   // workspace (bump allocator, reset per training step / forward)
     float* losses = nullptr;                        // device [4]: generator term, d_fake, d_real, spare
     int step = 0;
     long long batches_tracked = 0;
     DiscPass fake, real;
-    ~eegldm_disc() { for (void* p : {(void*)P, (void*)G, (void*)M, (void*)V, (void*)R, (void*)Wd, (void*)sums, (void*)ws, (void*)losses}) if (p) cudaFree(p); }
+    ~eegldm_disc() { for (void* p : {(void*)P, (void*)G, (void*)M, (void*)V, (void*)R, (void*)Wd, (void*)sums, (void*)ws, (void*)losses, (void*)img, (void*)wv}) if (p) cudaFree(p); }
     float* alloc(size_t n) { n = (n + 63) & ~size_t(63); float* p = ws ? ws + ws_off : nullptr; ws_off += n; return p; }
 };
 
@@ -146,6 +153,23 @@ int finalize_disc(eegldm_disc* d) {
     if (!d->sums) DCU(cudaMalloc((void**)&d->sums, (size_t)2 * 4096 * sizeof(double)));
     if (maxc > 4096) return dfail(EEGLDM_ERR_INVALID, "discriminator wider than 4096 channels");
     if (!d->losses) DCU(cudaMalloc((void**)&d->losses, 4 * sizeof(float)));
+    // tensor-pipe layers: stride-1 view with cin_v = stride * cin input channels; forward, data-gradient and weight-gradient
+    // kernels all need channel counts in multiples of 128 (the length conditions are checked per call)
+    size_t img_n = 0, wv_n = 64;
+    for (auto& l : d->layers) {
+        l.cin_v = l.stride * l.cin; l.cod = l.cin_v;
+        l.tc = !l.has_bias && l.cin_v % 128 == 0 && l.cout % 128 == 0;
+        if (!l.tc) continue;
+        l.o_imgf = img_n; img_n += conv_tc_image_u16(l.cin_v, l.cout, 3);
+        l.o_imgd = img_n; img_n += conv_tc_image_u16(l.cout, l.cod, 3);
+        wv_n = std::max(wv_n, (size_t)l.cin_v * 3 * l.cout);
+    }
+    if (d->img) { cudaFree(d->img); d->img = nullptr; }
+    if (d->wv) { cudaFree(d->wv); d->wv = nullptr; }
+    d->img_n = img_n; d->wv_n = wv_n;
+    if (img_n) DCU(cudaMalloc((void**)&d->img, img_n * sizeof(uint16_t)));
+    DCU(cudaMalloc((void**)&d->wv, wv_n * sizeof(float)));
+    d->images_dirty = true;
     d->step = 0;
     d->fake.valid = d->real.valid = false;
     d->finalized = true;
@@ -153,6 +177,41 @@ int finalize_disc(eegldm_disc* d) {
 }
 
 int out_len(int Tin, const DLayer& l) { return (Tin + 2 * l.pad - 3) / l.stride + 1; }
+
+// does layer l run on the tensor pipe for this input length?  (stride 2: the row-pair view needs an even length)
+bool use_tc(const eegldm_disc* d, const DLayer& l, int Tin) {
+    if (d->math != EEGLDM_MATH_F16X3_TC || !l.tc) return false;
+    if (l.stride == 2 && (Tin & 1)) return false;
+    const int Tout = out_len(Tin, l);
+    return Tout == Tin / l.stride && Tout % WG_CHUNK == 0;
+}
+
+// rebuild the tcgen05 weight images from the current parameters (after finalize and after every optimiser step)
+int ensure_images(eegldm_disc* d, cudaStream_t st) {
+    if (!d->images_dirty) return EEGLDM_OK;
+    for (auto& l : d->layers) {
+        if (!l.tc) continue;
+        const float* wf = d->P + l.ow;
+        if (l.stride == 2) { DCU(launch_s2z_weights(d->P + l.ow, l.cin, l.cout, d->wv, st)); wf = d->wv; }
+        DCU(launch_pack_conv_tc_dev(wf, l.cin_v, l.cout, 3, d->img + l.o_imgf, st));
+        DCU(launch_dgrad_weights(d->P + l.ow, l.cin, l.cout, l.stride, d->wv, st));
+        DCU(launch_pack_conv_tc_dev(d->wv, l.cout, l.cod, 3, d->img + l.o_imgd, st));
+    }
+    d->images_dirty = false;
+    return EEGLDM_OK;
+}
+
+// one tcgen05 conv launch (fused producer): out[B][T][Cout] = conv3_same(act(scale * x + shift)), x [B][T][Cin]
+cudaError_t tc_conv(const float* x, const float* scale, const float* shift, int act, const uint16_t* img, int B, int T, int Cin, int Cout,
+                    float* out, cudaStream_t st) {
+    TcConvParams q{};
+    q.nseg = 1; q.Cout = Cout; q.Tout = T; q.nsegs16 = (int)((long long)B * T / 16);
+    q.bn = conv_tc_bn(Cout, Cin / TC_BK * 3);
+    q.direct = 1;
+    q.seg[0] = TcSeg{nullptr, reinterpret_cast<const uint8_t*>(img), 3, Cin / TC_BK, x, nullptr, Cin, 0, scale, shift, act, RS_NONE, T};
+    q.out = out;
+    return launch_conv_tc(q, true, st);
+}
 
 // workspace floats of one forward pass (+ backward temporaries when training)
 size_t pass_floats(const eegldm_disc* d, int B, int L, bool backward) {
@@ -165,7 +224,17 @@ size_t pass_floats(const eegldm_disc* d, int B, int L, bool backward) {
         n += ((out_n + 63) & ~size_t(63)) + ((size_t)2 * B * l.cout + 64) + ((size_t)2 * l.cout + 64);
         maxact = std::max(maxact, std::max(in_n, out_n));
     }
-    if (backward) n += 3 * ((maxact + 63) & ~size_t(63)) + 256;   // dh, da, materialised conv input
+    if (backward) {
+        n += 3 * ((maxact + 63) & ~size_t(63)) + 256;   // dh, da, materialised conv input
+        size_t img = 0;                                // fp16 hi/lo operand images of the weight-gradient GEMM
+        int Tl = L;
+        for (auto& l : d->layers) {
+            const int To = out_len(Tl, l);
+            if (l.tc) img = std::max(img, wgrad_image_bytes((size_t)B * To, l.cin_v, 1) + wgrad_image_bytes((size_t)B * To, l.cout, 0));
+            Tl = To;
+        }
+        n += img / 4 + 256;
+    }
     return n + 1024;
 }
 
@@ -179,28 +248,39 @@ int ensure_ws(eegldm_disc* d, size_t floats) {
 
 // D(x): x [B][L][in] channels-last.  training: batch statistics (running statistics updated n_updates times), else running ones.
 int disc_forward(eegldm_disc* d, const float* x, int B, int L, bool training, int n_updates, DiscPass& ps, cudaStream_t st) {
-    ps.x = x; ps.B = B; ps.L = L; ps.h.clear(); ps.ss.clear(); ps.mr.clear(); ps.T.clear();
+    ps.x = x; ps.B = B; ps.L = L; ps.h.clear(); ps.ss.clear(); ps.mr.clear(); ps.T.clear(); ps.rp.clear();
     const float* in = x;
     const float *scale = nullptr, *shift = nullptr;
     int act = 0, T = L;
-    for (auto& l : d->layers) {
+    int r0 = ensure_images(d, st);
+    if (r0) return r0;
+    for (size_t li = 0; li < d->layers.size(); ++li) {
+        auto& l = d->layers[li];
         const int Tout = out_len(T, l);
         if (Tout < 1) return dfail(EEGLDM_ERR_SHAPE, "signal too short for the discriminator");
         float* h = d->alloc((size_t)B * Tout * l.cout);
-        ConvParams p{};
-        p.seg[0] = ConvSeg{in, nullptr, l.cin, 0, scale, shift, act, RS_NONE, T, d->P + l.ow, 3};
-        p.nseg = 1; p.Cout = l.cout; p.Tout = Tout; p.Tc = T; p.stride = l.stride; p.pad_left = l.pad;
-        p.bias = l.has_bias ? d->P + l.ob : nullptr; p.out = h; p.B = B;
-        DCU(launch_conv_simt(p, st));
+        if (use_tc(d, l, T)) {   // (stride 2: rows 2t, 2t+1 are one row of 2 cin channels; scale / shift were written twice per sample)
+            DCU(tc_conv(in, scale, shift, act, d->img + l.o_imgf, B, Tout, l.cin_v, l.cout, h, st));
+        } else {
+            ConvParams p{};
+            p.seg[0] = ConvSeg{in, nullptr, l.cin, 0, scale, shift, act, RS_NONE, T, d->P + l.ow, 3};
+            p.nseg = 1; p.Cout = l.cout; p.Tout = Tout; p.Tc = T; p.stride = l.stride; p.pad_left = l.pad;
+            p.bias = l.has_bias ? d->P + l.ob : nullptr; p.out = h; p.B = B;
+            DCU(launch_conv_simt(p, st));
+        }
         float *ss = nullptr, *mr = nullptr;
+        // a tensor-pipe stride-2 consumer reads this block's output as rows of 2 cout channels: its prologue then needs the
+        // per-channel scale / shift twice per sample ([B][2][C] is [2B][C])
+        const int rp = (li + 1 < d->layers.size() && d->layers[li + 1].stride == 2 && use_tc(d, d->layers[li + 1], Tout)) ? 2 : 1;
+        const int Brep = B * rp;
         if (l.has_norm) {
-            ss = d->alloc((size_t)2 * B * l.cout);
+            ss = d->alloc((size_t)2 * Brep * l.cout);
             mr = d->alloc((size_t)2 * l.cout);
             if (training) {
-                DCU(launch_bn_stats(h, (size_t)B * Tout, l.cout, d->P + l.og, d->P + l.obe, BN_EPS, B, d->sums, ss, ss + (size_t)B * l.cout, mr,
+                DCU(launch_bn_stats(h, (size_t)B * Tout, l.cout, d->P + l.og, d->P + l.obe, BN_EPS, Brep, d->sums, ss, ss + (size_t)Brep * l.cout, mr,
                                     mr + l.cout, d->R + l.orm, d->R + l.orv, BN_MOMENTUM, n_updates, st));
             } else {   // eval(): normalise with the running statistics -- a per-channel affine, computed on the host side of the stream
-                std::vector<float> run(2 * (size_t)l.cout), par(2 * (size_t)l.cout), hs((size_t)2 * B * l.cout);
+                std::vector<float> run(2 * (size_t)l.cout), par(2 * (size_t)l.cout), hs((size_t)2 * Brep * l.cout);
                 DCU(cudaMemcpyAsync(run.data(), d->R + l.orm, l.cout * sizeof(float), cudaMemcpyDeviceToHost, st));
                 DCU(cudaMemcpyAsync(run.data() + l.cout, d->R + l.orv, l.cout * sizeof(float), cudaMemcpyDeviceToHost, st));
                 DCU(cudaMemcpyAsync(par.data(), d->P + l.og, l.cout * sizeof(float), cudaMemcpyDeviceToHost, st));
@@ -208,15 +288,15 @@ int disc_forward(eegldm_disc* d, const float* x, int B, int L, bool training, in
                 DCU(cudaStreamSynchronize(st));
                 for (int c = 0; c < l.cout; ++c) {
                     const float sc = par[c] / std::sqrt(run[l.cout + c] + BN_EPS), sh = par[l.cout + c] - run[c] * sc;
-                    for (int b = 0; b < B; ++b) { hs[(size_t)b * l.cout + c] = sc; hs[((size_t)B + b) * l.cout + c] = sh; }
+                    for (int b = 0; b < Brep; ++b) { hs[(size_t)b * l.cout + c] = sc; hs[((size_t)Brep + b) * l.cout + c] = sh; }
                 }
                 DCU(cudaMemcpyAsync(ss, hs.data(), hs.size() * sizeof(float), cudaMemcpyHostToDevice, st));
                 DCU(cudaStreamSynchronize(st));
             }
         }
-        ps.h.push_back(h); ps.ss.push_back(ss); ps.mr.push_back(mr); ps.T.push_back(Tout);
+        ps.h.push_back(h); ps.ss.push_back(ss); ps.mr.push_back(mr); ps.T.push_back(Tout); ps.rp.push_back(rp);
         in = h; T = Tout;
-        scale = ss; shift = ss ? ss + (size_t)B * l.cout : nullptr;
+        scale = ss; shift = ss ? ss + (size_t)Brep * l.cout : nullptr;
         act = l.has_act ? 2 : 0;
     }
     ps.valid = true;
@@ -238,10 +318,28 @@ int disc_backward(eegldm_disc* d, const DiscPass& ps, float* dlogits, bool wgrad
         const int Tin = i ? ps.T[i - 1] : ps.L, Tout = ps.T[i];
         const float* in_raw = i ? ps.h[i - 1] : ps.x;            // the conv's input before the previous block's norm + activation
         const DLayer* prev = i ? &d->layers[i - 1] : nullptr;
-        if (wgrad) {
+        const bool tc = use_tc(d, l, Tin);
+        const size_t ss_half = prev && prev->has_norm ? (size_t)B * ps.rp[i - 1] * prev->cout : 0;   // shift follows scale after this many floats
+        if (wgrad && tc) {
+            // weight gradient on the tensor pipe: operands split to fp16 hi/lo once (the conv input with its norm + activation applied,
+            // rows of cin_v channels with a halo; dy plain), then one split-K GEMM per tap
+            const size_t mark = d->ws_off;
+            uint8_t* a_img = reinterpret_cast<uint8_t*>(d->alloc(wgrad_image_bytes((size_t)B * Tout, l.cin_v, 1) / 4 + 64));
+            uint8_t* y_img = reinterpret_cast<uint8_t*>(d->alloc(wgrad_image_bytes((size_t)B * Tout, l.cout, 0) / 4 + 64));
+            const float* sc = prev && prev->has_norm ? ps.ss[i - 1] : nullptr;   // [rp][C] at the front of the buffer = one row of cin_v channels
+            DCU(launch_wgrad_split(in_raw, sc, sc ? sc + ss_half : nullptr, 0, prev && prev->has_act ? 2 : 0, B, Tout, l.cin_v, 1, a_img, st));
+            DCU(launch_wgrad_split(dh, nullptr, nullptr, 0, 0, B, Tout, l.cout, 0, y_img, st));
+            if (l.stride == 1) DCU(launch_wgrad_tc(a_img, y_img, d->G + l.ow, B, Tout, l.cin_v, l.cout, 3, 0, 3, st));
+            else {   // row-pair view: taps (t-1, t) of the virtual weights, folded back onto the three real taps
+                DCU(cudaMemsetAsync(d->wv, 0, (size_t)l.cin_v * 3 * l.cout * sizeof(float), st));
+                DCU(launch_wgrad_tc(a_img, y_img, d->wv, B, Tout, l.cin_v, l.cout, 3, 0, 2, st));
+                DCU(launch_s2z_grad_fold(d->wv, l.cin, l.cout, d->G + l.ow, st));
+            }
+            d->ws_off = mark;
+        } else if (wgrad) {
             const float* a = in_raw;
             if (prev && (prev->has_norm || prev->has_act)) {
-                DCU(launch_affine_lrelu(in_raw, prev->has_norm ? ps.ss[i - 1] : nullptr, prev->has_norm ? ps.ss[i - 1] + (size_t)B * prev->cout : nullptr,
+                DCU(launch_affine_lrelu(in_raw, prev->has_norm ? ps.ss[i - 1] : nullptr, prev->has_norm ? ps.ss[i - 1] + ss_half : nullptr,
                                         prev->cout, prev->has_act ? LEAKY : 1.f, buf_in, (size_t)B * Tin * l.cin, st));
                 a = buf_in;
             }
@@ -258,13 +356,16 @@ int disc_backward(eegldm_disc* d, const DiscPass& ps, float* dlogits, bool wgrad
         const int cod = z2 ? 2 * l.cin : l.cin;
         const size_t nwd = (size_t)l.cout * 3 * cod;
         if (nwd > d->Wd_cap) { if (d->Wd) cudaFree(d->Wd); d->Wd = nullptr; d->Wd_cap = 0; DCU(cudaMalloc((void**)&d->Wd, nwd * sizeof(float))); d->Wd_cap = nwd; }
-        DCU(launch_dgrad_weights(d->P + l.ow, l.cin, l.cout, l.stride, d->Wd, st));
         float* da = (i == 0 && !dx_accumulate) ? dx : buf_a;
-        ConvParams p{};
-        p.seg[0] = ConvSeg{dh, nullptr, l.cout, 0, nullptr, nullptr, 0, RS_NONE, Tout, d->Wd, 3};
-        p.nseg = 1; p.Cout = cod; p.Tout = Tout; p.Tc = Tout; p.stride = 1; p.pad_left = 1; p.out = da; p.B = B;
         if (!z2 && Tout != Tin) return dfail(EEGLDM_ERR_SHAPE, "discriminator backward: stride-1 conv must keep the length");
-        DCU(launch_conv_simt(p, st));
+        if (tc) DCU(tc_conv(dh, nullptr, nullptr, 0, d->img + l.o_imgd, B, Tout, l.cout, cod, da, st));
+        else {
+            DCU(launch_dgrad_weights(d->P + l.ow, l.cin, l.cout, l.stride, d->Wd, st));
+            ConvParams p{};
+            p.seg[0] = ConvSeg{dh, nullptr, l.cout, 0, nullptr, nullptr, 0, RS_NONE, Tout, d->Wd, 3};
+            p.nseg = 1; p.Cout = cod; p.Tout = Tout; p.Tc = Tout; p.stride = 1; p.pad_left = 1; p.out = da; p.B = B;
+            DCU(launch_conv_simt(p, st));
+        }
         if (i == 0) {
             if (dx_accumulate) DCU(launch_axpy(buf_a, dx, 1.f, 1, (size_t)B * Tin * l.cin, st));
             break;
@@ -336,6 +437,7 @@ int disc_step(eegldm_disc* d, const float* x_real, int B, int L, float adv_weigh
     if (lr > 0.f) {
         d->step += 1;
         DCU(launch_adam(d->P, d->G, d->M, d->V, lr, b1, b2, eps, d->step, d->nP, st));
+        d->images_dirty = true;
     }
     return EEGLDM_OK;
 }
@@ -406,6 +508,13 @@ int eegldm_disc_forward(eegldm_disc* d, const float* x_dev, float* logits_dev, i
     if (training) d->batches_tracked += 1;
     DCU(cudaMemcpyAsync(logits_dev, ps.h.back(), (size_t)B * ps.T.back() * sizeof(float), cudaMemcpyDeviceToDevice, st));
     d->fake.valid = d->real.valid = false;
+    return EEGLDM_OK;
+}
+
+int eegldm_disc_set_math(eegldm_disc* d, int mode) {
+    if (!d) return dfail(EEGLDM_ERR_INVALID, "null handle");
+    if (mode != EEGLDM_MATH_FP32_SIMT && mode != EEGLDM_MATH_F16X3_TC) return dfail(EEGLDM_ERR_INVALID, "discriminator math: fp32 SIMT or f16x3");
+    d->math = mode;
     return EEGLDM_OK;
 }
 

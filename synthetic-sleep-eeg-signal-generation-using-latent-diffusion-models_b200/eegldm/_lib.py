@@ -125,6 +125,7 @@ SIGNATURES = {
     "eegldm_disc_finalize": (C.c_int, [_P]),
     "eegldm_disc_forward": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "eegldm_disc_out_len": (C.c_int, [_P, C.c_int]),
+    "eegldm_disc_set_math": (C.c_int, [_P, C.c_int]),
     "eegldm_disc_export": (C.c_int, [_P, C.c_int, C.c_char_p, _FP]),
     "eegldm_aekl_train_step_adv": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.POINTER(AeklAdvTrainCfg), _FP, _P]),
     "eegldm_psd_freqs": (C.c_int, [C.POINTER(PsdCfg), C.c_int, C.POINTER(C.c_int), _FP]),

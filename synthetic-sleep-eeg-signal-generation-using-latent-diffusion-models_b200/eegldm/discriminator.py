@@ -20,7 +20,7 @@ from ._module import EngineModule, check_cuda_f32, _Node
 class PatchDiscriminator(EngineModule):
     def __init__(self, spatial_dims=1, num_channels=64, in_channels=1, out_channels=1, num_layers_d=3, kernel_size=4,
                  activation=("LEAKYRELU", {"negative_slope": 0.2}), norm="BATCH", bias=False, padding=1, dropout=0.0,
-                 last_conv_kernel_size=None):
+                 last_conv_kernel_size=None, math="f16x3"):
         super().__init__()
         if spatial_dims != 1:
             raise NotImplementedError("the reference's discriminator is 1-D (config_aekl_eeg.yaml:32)")
@@ -39,6 +39,7 @@ class PatchDiscriminator(EngineModule):
         _lib.check(L.eegldm_disc_create(C.byref(cfg), C.byref(h)))   # rejects kernel_size != 3 / padding != 1
         self._h = h
         self._trained = False
+        self.set_math(math)
         g = torch.Generator().manual_seed(torch.initial_seed() & 0x7FFFFFFF)
         for i in range(L.eegldm_disc_num_params(h)):
             name, shape, nd, isb = C.c_char_p(), (C.c_int64 * 4)(), C.c_int(), C.c_int()
@@ -76,6 +77,14 @@ class PatchDiscriminator(EngineModule):
             except Exception:
                 pass
             object.__setattr__(self, "_h", None)
+
+    def set_math(self, mode: str) -> "PatchDiscriminator":
+        """``"f16x3"`` (default; tcgen05 for the wide convs and their gradients, fp32-accurate) or ``"fp32"`` (SIMT)."""
+        if mode not in ("fp32", "f16x3"):
+            raise ValueError("math must be 'fp32' or 'f16x3'")
+        _lib.check(_lib.lib().eegldm_disc_set_math(self._h, _lib.MATH_MODES[mode]))
+        self._math = mode
+        return self
 
     def _weights_key(self):
         return tuple((p.data_ptr(), p._version) for p in list(self.parameters()) + list(self.buffers()))

@@ -16,19 +16,22 @@ def _close(a, b, rtol, floor):
     torch.testing.assert_close(a, b, rtol=rtol, atol=floor * max(scale, 1e-30))
 
 
-def _disc(cfg, sd, dev):
+def _disc(cfg, sd, dev, math="f16x3"):
     import eegldm
-    d = eegldm.PatchDiscriminator(**cfg)
+    d = eegldm.PatchDiscriminator(**cfg, math=math)
     d.load_state_dict(sd)
     return d.to(dev)
 
 
+@pytest.mark.parametrize("math", ["fp32", "f16x3"])
 @pytest.mark.parametrize("over,B,L", [({}, 3, 3072), (dict(num_channels=8, num_layers_d=2), 5, 512), (dict(num_channels=16, num_layers_d=4), 2, 1024)])
-def test_discriminator_forward_matches_oracle(built_lib, cuda_device, over, B, L):
+def test_discriminator_forward_matches_oracle(built_lib, cuda_device, over, B, L, math):
+    """The reference configuration takes the tcgen05 path in f16x3 (64 -> 128 -> 256 -> 512 convs; stride 2 as row pairs);
+    the narrow configurations fall back to the fp32 kernels layer by layer."""
     cfg = od.full_cfg(**over)
     sd = od.make_disc_state_dict(cfg, 7, weight_std=0.1)
     x = torch.rand(B, 1, L, generator=torch.Generator().manual_seed(0))
-    d = _disc(cfg, sd, cuda_device)
+    d = _disc(cfg, sd, cuda_device, math)
     run = {}
     ref = od.forward(cfg, sd, x, training=True, update_running=run)[-1]
     y = d(x.to(cuda_device))[-1]
@@ -77,8 +80,9 @@ def _oracle_full_step(acfg, asd, dcfg, dsd, x, eps, kl_w, spec_w, adv_w, lr_g, l
     return losses, g_grads, {k: p.detach() for k, p in gp.items()}, d_grads, {k: p.detach() for k, p in dp.items()}
 
 
+@pytest.mark.parametrize("math", ["fp32", "f16x3"])
 @pytest.mark.parametrize("nc,dover,B,L", [([2, 2, 4], {}, 3, 3072), ([4, 4], dict(num_channels=8, num_layers_d=2), 4, 512)])
-def test_full_training_step_matches_autograd(built_lib, cuda_device, nc, dover, B, L):
+def test_full_training_step_matches_autograd(built_lib, cuda_device, nc, dover, B, L, math):
     import eegldm
     acfg = oa.full_cfg(num_channels=nc, attention_levels=[False] * len(nc))
     asd = oa.make_aekl_state_dict(acfg, 42)
@@ -104,7 +108,7 @@ def test_full_training_step_matches_autograd(built_lib, cuda_device, nc, dover, 
     m = eegldm.AutoencoderKL(**acfg)
     m.load_state_dict(asd)
     m = m.to(cuda_device)
-    d = _disc(dcfg, dsd, cuda_device)
+    d = _disc(dcfg, dsd, cuda_device, math)
     out = m.train_step(x.to(cuda_device), eps.to(cuda_device), kl_weight=kw["kl_w"], spectral_weight=kw["spec_w"], lr=kw["lr_g"],
                        discriminator=d, adv_weight=kw["adv_w"], lr_d=kw["lr_d"])
     for k in ref:
