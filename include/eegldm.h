@@ -277,6 +277,31 @@ int eegldm_ddim_sample_host(eegldm_unet* unet, eegldm_aekl* aekl, const eegldm_s
 int eegldm_set_graphs(int enabled);
 
 /* ------------------------------------------------------------------------------------------------
+ * Latent-diffusion training step: replaces the body of train_epoch_ldm, src/training/training.py:420-443, for one batch
+ * (with the DDPMScheduler of src/train_ldm.py:199-200):
+ *   noisy = scheduler.add_noise(z0, noise, timesteps)                          (training.py:429)
+ *   pred  = model(noisy, timesteps)                                            (training.py:430; UNetModel.forward in training mode)
+ *   target = noise (epsilon) | scheduler.get_velocity(z0, noise, timesteps)    (training.py:432-436, sched->prediction_type)
+ *   loss = F.mse_loss(pred, target);  backward through the whole UNet;  Adam step (train_ldm.py:208)
+ * z0_dev / noise_dev [B, in_channels, T] fp32 (z0 = stage1(images) * scale_factor, the caller's AutoencoderKL.encode + sampling);
+ * timesteps_dev [B] int64 on the device (training.py:420).  in_channels == out_channels is required (the target has the
+ * latent's shape).  Arithmetic: fp32 throughout -- tensor-pipe convolutions (forward, data gradient, weight gradient) in the
+ * f16x3 scheme when the handle's math mode is EEGLDM_MATH_F16X3_TC, fp32 SIMT otherwise; the reference's fp16 autocast +
+ * GradScaler (training.py:423,441-443) is a memory / speed device of its PyTorch path whose loss scaling cancels exactly, so the
+ * fp32 result is the value it approximates.  lr <= 0 computes the loss and the gradients only.  loss_host (nullable;
+ * synchronises) receives the loss.  Parameters, gradients and Adam moments live on the device (created from the loaded
+ * state_dict at the first step); eegldm_unet_train_export returns one state_dict entry (what = 0) or its gradient (what = 1) in
+ * the reference layout; eegldm_unet_train_sync copies the trained parameters back into the inference weights. */
+typedef struct {
+    float lr;                       /* 1e-4  base_lr (config_ldm.yaml:11) */
+    float beta1, beta2, adam_eps;   /* torch.optim.Adam defaults 0.9, 0.999, 1e-8 */
+} eegldm_ldm_train_cfg;
+int eegldm_unet_train_step(eegldm_unet* h, const eegldm_sched_cfg* sched, const float* z0_dev, const float* noise_dev,
+                           const int64_t* timesteps_dev, int B, int T, const eegldm_ldm_train_cfg* cfg, float* loss_host, void* stream);
+int eegldm_unet_train_export(eegldm_unet* h, int what, const char* name, float* host_out);
+int eegldm_unet_train_sync(eegldm_unet* h);
+
+/* ------------------------------------------------------------------------------------------------
  * Output tail of the sampling scripts: replaces, batched over all windows, what src/sample_trials.py:169-197 (and
  * sample_trials_ddpm.py:105-128, util.py:66-112) do per window on the host --
  *   cropped = sample.cpu().numpy()[:, :, 36:-36];  np.save(sample_i.npy, cropped);

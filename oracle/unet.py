@@ -292,10 +292,10 @@ def _run_layer(h, emb, sd, l, cfg):
     raise ValueError(k)
 
 
-@torch.no_grad()
-def unet_forward(cfg: dict, sd: Dict[str, torch.Tensor], x: torch.Tensor, timesteps: torch.Tensor,
-                 taps: dict | None = None) -> torch.Tensor:
-    """UNetModel.forward, unet.py:512-563.  ``timesteps`` has shape [1] or [B]."""
+def unet_forward_train(cfg: dict, sd: Dict[str, torch.Tensor], x: torch.Tensor, timesteps: torch.Tensor,
+                       taps: dict | None = None) -> torch.Tensor:
+    """UNetModel.forward, unet.py:512-563, with autograd enabled (dropout = 0 in every reference config, so training and eval
+    mode compute the same function).  ``timesteps`` has shape [1] or [B]."""
     plan = unet_plan(cfg)
     t_emb = timestep_embedding(timesteps, cfg["model_channels"])
     emb = F.linear(t_emb, sd["time_embed.0.weight"], sd["time_embed.0.bias"])
@@ -320,3 +320,10 @@ def unet_forward(cfg: dict, sd: Dict[str, torch.Tensor], x: torch.Tensor, timest
             taps[f"output_blocks.{bi}"] = h
     h = F.silu(_gn(h, sd, "out.0"))
     return _conv(h, sd, "out.2", 1)
+
+
+@torch.no_grad()
+def unet_forward(cfg: dict, sd: Dict[str, torch.Tensor], x: torch.Tensor, timesteps: torch.Tensor,
+                 taps: dict | None = None) -> torch.Tensor:
+    """UNetModel.forward, unet.py:512-563 (inference).  ``timesteps`` has shape [1] or [B]."""
+    return unet_forward_train(cfg, sd, x, timesteps, taps)

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "eegldm", "libeegldm.so")
-SOURCES = ["engine.cu", "kernels_simt.cu", "conv_tc.cu", "attn_tc.cu", "train_kernels.cu", "spectral.cu", "psd.cu", "disc.cu", "train_tc.cu"]
+SOURCES = ["engine.cu", "kernels_simt.cu", "conv_tc.cu", "attn_tc.cu", "train_kernels.cu", "spectral.cu", "psd.cu", "disc.cu", "train_tc.cu", "unet_train_kernels.cu"]
 OPTIONAL_SOURCES = []
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
 
@@ -28,7 +28,7 @@ def _sources():
 
 def _stamp(srcs):
     h = hashlib.sha256()
-    deps = list(srcs) + [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cuh", ".h"))]
+    deps = list(srcs) + [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cuh", ".h", ".inc"))]
     deps.append(os.path.join(ROOT, "include", "eegldm.h"))
     for p in deps:
         with open(p, "rb") as f:

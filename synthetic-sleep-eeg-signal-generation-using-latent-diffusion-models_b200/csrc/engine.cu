@@ -313,6 +313,9 @@ struct GraphEntry {
 
 }  // namespace
 
+struct UnetTrain;                        // latent-diffusion training state (unet_train.inc)
+void unet_train_free(UnetTrain* t);
+
 struct eegldm_unet {
     eegldm_unet_cfg cfg{};
     ParamSet ps;
@@ -344,8 +347,10 @@ struct eegldm_unet {
     float* host_out = nullptr; size_t host_out_cap = 0;
     std::vector<float> table_key;                          // identifies the cached temb/coef tables
     std::map<std::pair<int, int>, GraphEntry> graphs;      // (B,T) -> one denoise step
+    UnetTrain* train = nullptr;                            // created by the first eegldm_unet_train_step
     ~eegldm_unet() {
         drop_graphs();
+        if (train) unet_train_free(train);
         if (cap_stream) cudaStreamDestroy(cap_stream);
         if (cap_stream2) cudaStreamDestroy(cap_stream2);
         if (ev_fork) cudaEventDestroy(ev_fork);
@@ -2413,3 +2418,5 @@ int eegldm_aekl_train_sync(eegldm_aekl* h) {
 }
 
 }  // extern "C"
+
+#include "unet_train.inc"

@@ -223,8 +223,31 @@ size_t wgrad_image_bytes(size_t rows_total, int C, int halo);
 cudaError_t launch_wgrad_split(const float* src, const float* scale, const float* shift, int ss_bstride, int act, int B, int T, int C,
                                int halo, uint8_t* img, cudaStream_t st);
 cudaError_t launch_wgrad_tc(const uint8_t* a_img, const uint8_t* dy_img, float* dw /*[(ci*ktot+tap)][Cout], +=*/, int B, int T, int Cin,
-                            int Cout, int ktot, int tap0, int ntaps, cudaStream_t st);
+                            int Cout, int ktot, int tap0, int ntaps, cudaStream_t st, int dw_tap_shift = 0);
 cudaError_t launch_adam(float* p, const float* g, float* m, float* v, float lr, float b1, float b2, float eps, int step, size_t n,
                         cudaStream_t st);
+
+// ---- latent-diffusion training step (unet_train_kernels.cu): everything around the convolutions
+struct BGemm {   // C[m][n] (+)= alpha * sum_k A[m][k] B[k][n], element strides; batch index = outer * nb_inner + inner
+    const float* A; const float* B; float* C;
+    int M, N, K;
+    long long a_m, a_k, b_k, b_n, c_m, c_n;
+    int batch, nb_inner;
+    long long a_bo, a_bi, b_bo, b_bi, c_bo, c_bi;
+    float alpha; int accumulate;
+};
+cudaError_t launch_bgemm(const BGemm& g, cudaStream_t st);
+cudaError_t launch_softmax_rows(float* s, size_t rows, int n, cudaStream_t st);                            // in place
+cudaError_t launch_softmax_bwd_rows(const float* p, float* dp, size_t rows, int n, cudaStream_t st);       // dP -> dS in place
+cudaError_t launch_rowsum_bt(const float* x, int B, int T, int C, float* out, int out_stride, int accumulate, cudaStream_t st);
+cudaError_t launch_resample_bwd(const float* dy, float* dx, int B, int Tin, int C, int mode, int accumulate, cudaStream_t st);
+cudaError_t launch_concat(const float* x0, int C0, const float* x1, int C1, float* out, size_t rows, cudaStream_t st);
+cudaError_t launch_split_add(const float* dcat, float* d0, int C0, int acc0, float* d1, int C1, int acc1, size_t rows, cudaStream_t st);
+cudaError_t launch_silu_fwd(const float* x, float* y, size_t n, cudaStream_t st);
+cudaError_t launch_silu_bwd(const float* dy, const float* x, float* dx, size_t n, cudaStream_t st);
+cudaError_t launch_ldm_inputs(const float* z0, const float* eps, const long long* t, const float* acp, int n_train, float* noisy, float* target,
+                              float* t_f, int v_pred, int B, size_t per, cudaStream_t st);
+cudaError_t launch_mse_loss(const float* p, const float* y, float* dp, float* loss, size_t n, cudaStream_t st);
+cudaError_t launch_dgrad_weights_any(const float* w, int Cin, int Cout, int taps, float* wd, cudaStream_t st);
 
 }  // namespace eegldm

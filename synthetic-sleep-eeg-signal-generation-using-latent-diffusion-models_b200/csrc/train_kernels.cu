@@ -76,10 +76,10 @@ __global__ void conv_bwd_data_kernel(const float* __restrict__ dy, const float* 
 }
 
 // Conv1d backward w.r.t. weight and bias; grid (ceil(Tout/P), B), dynamic smem: dy tile [P][Cout] + input tile [P*stride+taps-1][Cin]
-constexpr int WG_P = 64;
+// (P = WG_P positions per block: 64, halved by the launcher until the two tiles fit shared memory)
 __global__ void __launch_bounds__(256) conv_bwd_weight_kernel(const float* __restrict__ dy, const float* __restrict__ a,
                                                                float* __restrict__ dw, float* __restrict__ db, int Cin, int Cout,
-                                                               int taps, int stride, int pad, int ups, int Tin, int Tc, int Tout) {
+                                                               int taps, int stride, int pad, int ups, int Tin, int Tc, int Tout, int WG_P) {
     extern __shared__ float sm[];
     float* dys = sm;                       // [P][Cout]
     float* as = sm + WG_P * Cout;          // [rows][Cin]
@@ -762,8 +762,10 @@ cudaError_t launch_conv_bwd_weight(const ConvGradParams& p, cudaStream_t st) {
         g_launch_count += 1;
         return launch_conv_grad_tiny(p, true, st);
     }
-    const int rows = (WG_P - 1) * p.stride + p.taps;
-    const size_t smem = ((size_t)WG_P * p.Cout + (size_t)rows * p.Cin) * sizeof(float);
+    int WG_P = 64;
+    auto smem_for = [&](int P) { return ((size_t)P * p.Cout + (size_t)((P - 1) * p.stride + p.taps) * p.Cin) * sizeof(float); };
+    while (WG_P > 1 && smem_for(WG_P) > 200 * 1024) WG_P >>= 1;
+    const size_t smem = smem_for(WG_P);
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
     static size_t attr = 0;
     if (smem > 48 * 1024 && smem > attr) {
@@ -772,7 +774,7 @@ cudaError_t launch_conv_bwd_weight(const ConvGradParams& p, cudaStream_t st) {
         attr = 200 * 1024;
     }
     dim3 grid((p.Tout + WG_P - 1) / WG_P, p.B);
-    conv_bwd_weight_kernel<<<grid, 256, smem, st>>>(p.dy, p.a, p.dw, p.db, p.Cin, p.Cout, p.taps, p.stride, p.pad, p.ups, p.Tin, p.Tc, p.Tout);
+    conv_bwd_weight_kernel<<<grid, 256, smem, st>>>(p.dy, p.a, p.dw, p.db, p.Cin, p.Cout, p.taps, p.stride, p.pad, p.ups, p.Tin, p.Tc, p.Tout, WG_P);
     g_launch_count += 1;
     return cudaGetLastError();
 }

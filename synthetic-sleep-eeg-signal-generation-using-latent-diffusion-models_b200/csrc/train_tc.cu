@@ -139,6 +139,7 @@ struct WgradParams {
     float* dw;          // [(ci*ktot + tap)][Cout] fp32, += (split-K reductions)
     int Cin, Cout, ntaps, tap0, ktot;   // taps tap0 .. tap0+ntaps-1 of a ktot-tap weight image (row offset of tap j: j - 1 + ... see below)
     int nchunks, nsplit;
+    int dw_tap_shift;   // tap index in dW = tap - dw_tap_shift (a 1x1 conv reads halo row 1 = "tap 1" and has the single tap 0)
 };
 
 template <int BNW>
@@ -224,7 +225,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const WgradPara
         mbar_wait(barAcc, 0);
         tc_fence_after();
         const int ci = ci_t * 128 + warp * 32 + lane;                    // TMEM lane = input channel
-        float* row = p.dw + ((size_t)ci * p.ktot + tap) * p.Cout + (size_t)co_t * BNW;
+        float* row = p.dw + ((size_t)ci * p.ktot + (tap - p.dw_tap_shift)) * p.Cout + (size_t)co_t * BNW;
         const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
         for (int cb = 0; cb < BNW; cb += 32) {
@@ -286,9 +287,9 @@ cudaError_t launch_wgrad_split(const float* src, const float* scale, const float
 
 // dw[(ci*ktot + tap)][Cout] += sum over positions, taps tap0 .. tap0 + ntaps - 1 (tap j reads position t + j - 1)
 cudaError_t launch_wgrad_tc(const uint8_t* a_img, const uint8_t* dy_img, float* dw, int B, int T, int Cin, int Cout, int ktot, int tap0,
-                            int ntaps, cudaStream_t st) {
+                            int ntaps, cudaStream_t st, int dw_tap_shift) {
     if (!wgrad_tc_eligible(Cin, Cout, T) || ntaps < 1 || tap0 < 0 || tap0 + ntaps > 3) return cudaErrorInvalidValue;
-    WgradParams p{a_img, dy_img, dw, Cin, Cout, ntaps, tap0, ktot, (int)((size_t)B * T / CH), 1};
+    WgradParams p{a_img, dy_img, dw, Cin, Cout, ntaps, tap0, ktot, (int)((size_t)B * T / CH), 1, dw_tap_shift};
     const int bnw = Cout % 256 == 0 ? 256 : 128;
     const int units = ntaps * (Cin / 128) * (Cout / bnw);
     static int num_sms = 0;

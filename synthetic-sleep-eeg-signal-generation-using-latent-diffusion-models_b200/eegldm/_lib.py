@@ -60,6 +60,10 @@ class PsdCfg(C.Structure):
                 ("remove_dc", C.c_int32), ("db", C.c_int32)]
 
 
+class LdmTrainCfg(C.Structure):
+    _fields_ = [("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("adam_eps", C.c_float)]
+
+
 class SchedCfg(C.Structure):
     _fields_ = [
         ("num_train_timesteps", C.c_int32), ("beta_start", C.c_float), ("beta_end", C.c_float),
@@ -113,6 +117,9 @@ SIGNATURES = {
     "eegldm_aekl_train_step": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.POINTER(AeklTrainCfg), _FP, _P]),
     "eegldm_aekl_train_export": (C.c_int, [_P, C.c_int, C.c_char_p, _FP]),
     "eegldm_aekl_train_sync": (C.c_int, [_P]),
+    "eegldm_unet_train_step": (C.c_int, [_P, C.POINTER(SchedCfg), _P, _P, _P, C.c_int, C.c_int, C.POINTER(LdmTrainCfg), _FP, _P]),
+    "eegldm_unet_train_export": (C.c_int, [_P, C.c_int, C.c_char_p, _FP]),
+    "eegldm_unet_train_sync": (C.c_int, [_P]),
     "eegldm_sched_alphas_cumprod": (C.c_int, [C.POINTER(SchedCfg), _FP]),
     "eegldm_sched_ddim_tables": (C.c_int, [C.POINTER(SchedCfg), C.c_int, _I64P, _FP]),
     "eegldm_timestep_embedding": (C.c_int, [_FP, C.c_int, C.c_int, _FP]),

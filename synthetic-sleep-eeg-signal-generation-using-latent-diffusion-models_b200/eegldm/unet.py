@@ -123,6 +123,57 @@ class UNetModel(EngineModule):
                                                  int(ts.numel()), C.c_void_p(out.data_ptr()), int(B), int(T), stream))
         return out
 
+    def train_step(self, z0, noise, timesteps, scheduler, lr=1e-4, betas=(0.9, 0.999), adam_eps=1e-8, return_loss=True):
+        """One latent-diffusion training step on the device (the batch body of train_epoch_ldm, training.py:420-443):
+        ``noisy = scheduler.add_noise(z0, noise, timesteps)``; ``pred = self(noisy, timesteps)``; target = ``noise`` or
+        ``scheduler.get_velocity(z0, noise, timesteps)`` by ``scheduler.prediction_type``; ``F.mse_loss``; backward through the
+        whole UNet; Adam.  ``z0`` is the scaled latent ``stage1(images) * scale_factor`` [B, C, T]; ``timesteps`` int64 [B]
+        (CUDA, as the reference draws them).  ``lr <= 0`` computes the loss and gradients only.  Parameters are updated inside
+        the engine: ``sync_trained()`` copies them back into this module / the inference weights; ``grad_dict()`` returns the
+        last gradients.  fp32 (SIMT) or f16x3 (tensor pipe) by ``set_math``; returns the loss (one sync) if ``return_loss``."""
+        z0 = check_cuda_f32(z0, "z0")
+        noise = check_cuda_f32(noise, "noise")
+        if z0.dim() != 3 or z0.shape[1] != self.in_channels or noise.shape != z0.shape:
+            raise ValueError(f"z0 / noise must be [B, {self.in_channels}, T] and equal in shape")
+        B, _, T = z0.shape
+        ts = torch.as_tensor(timesteps).reshape(-1).to(device=z0.device, dtype=torch.int64).contiguous()
+        if ts.numel() != B:
+            raise ValueError("timesteps must have B entries")
+        cfg = _lib.LdmTrainCfg(float(lr), float(betas[0]), float(betas[1]), float(adam_eps))
+        out = (C.c_float * 1)()
+        with torch.cuda.device(z0.device):
+            self._sync_weights()
+            _lib.check(_lib.lib().eegldm_unet_train_step(
+                self._h, C.byref(scheduler._cfg), C.c_void_p(z0.data_ptr()), C.c_void_p(noise.data_ptr()), C.c_void_p(ts.data_ptr()),
+                int(B), int(T), C.byref(cfg), out if return_loss else None, C.c_void_p(_lib.current_stream_ptr(z0.device))))
+        self._trained = True
+        return float(out[0]) if return_loss else None
+
+    def _export(self, what: int):
+        res = {}
+        L = _lib.lib()
+        for name, p in self.named_parameters():
+            buf = torch.empty(tuple(p.shape), dtype=torch.float32)
+            _lib.check(L.eegldm_unet_train_export(self._h, what, name.encode(), C.cast(C.c_void_p(buf.data_ptr()), C.POINTER(C.c_float))))
+            res[name] = buf
+        return res
+
+    def grad_dict(self):
+        """Gradients of the last train_step, keyed and laid out like ``state_dict()``."""
+        return self._export(1)
+
+    @torch.no_grad()
+    def sync_trained(self):
+        """Copy the engine's trained parameters into this module and into the inference weights."""
+        if not getattr(self, "_trained", False):
+            return self
+        new = self._export(0)
+        for name, p in self.named_parameters():
+            p.copy_(new[name].to(p.device))
+        _lib.check(_lib.lib().eegldm_unet_train_sync(self._h))
+        self._uploaded_key = self._weights_key()   # the engine already holds exactly these values
+        return self
+
     def range_overflow(self) -> bool:
         """f16x3 operand-range guard: True when, since the last call, some activation handed to the tensor pipe had
         |x| >= 65504 or was NaN (that forward's output is invalid: switch to ``set_math("fp32")``).  Synchronises."""
