@@ -341,6 +341,61 @@ def measure_config2(args, dev, unet):
     return out
 
 
+def measure_ldm_train(args, dev, B=64, with_cpu=True):
+    """one latent-diffusion training step (training.py:420-443) of the config_ldm.yaml UNet, batch B x [1,768] latents:
+    add_noise, forward, MSE against the noise, backward, Adam lr 1e-4; tensor-pipe convs in f16x3 (forward, data and weight gradients)."""
+    import torch
+    import eegldm
+    from eegldm import synthetic
+    m = eegldm.UNetModel(**synthetic.LDM_UNET_CFG, math="f16x3")
+    m.load_state_dict(synthetic.seeded_state_dict(m, 0))
+    m = m.to(dev)
+    sched = eegldm.DDPMScheduler(1000, 0.0015, 0.0195, "linear_beta", "epsilon")   # train_ldm.py:199-200
+    g = torch.Generator().manual_seed(0)
+    zh = torch.randn(B, 1, T_LATENT, generator=g).pin_memory()
+    nh = torch.randn(B, 1, T_LATENT, generator=g).pin_memory()
+    th = torch.randint(0, 1000, (B,), generator=g).pin_memory()
+    z, n, t = zh.to(dev), nh.to(dev), th.to(dev)
+    steps, warm = 5, 3
+    l0 = eegldm.launch_count()
+    ms = _events_ms(torch, lambda: m.train_step(z, n, t, sched, return_loss=False), steps, warm)
+    launches = (eegldm.launch_count() - l0) // (steps + warm)
+    t0 = time.perf_counter()
+    for _ in range(steps):   # e2e: latents, noise and timesteps from pinned host memory, the loss read back every step
+        m.train_step(zh.to(dev, non_blocking=True), nh.to(dev, non_blocking=True), th.to(dev, non_blocking=True), sched)
+    torch.cuda.synchronize()
+    ms_e2e = (time.perf_counter() - t0) * 1e3 / steps
+    peaks = _peaks()
+    tf = 3 * UNET_GFLOP_PER_FWD * 1e9 * B / (ms / 1e3) / 1e12   # forward + data gradient + weight gradient
+    out = {"metric": "LDM training-step windows/sec", "value": B / (ms / 1e3), "unit": "windows/s", "ms_per_step": ms,
+           "workload": "8f-2: latent-diffusion training step, config_ldm.yaml UNet (30.5M params), batch %d x [1,768] latents, epsilon target, "
+                       "MSE, backward, Adam lr 1e-4, f16x3" % B,
+           "gpu_launches_per_step": int(launches),
+           "e2e": {"value": B / (ms_e2e / 1e3), "unit": "windows/s", "h2d_bytes_per_step": (zh.numel() + nh.numel()) * 4 + th.numel() * 8,
+                   "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e},
+           "roofline": {"bound": "tensor", "achieved": tf, "peak": peaks["tc_sustained"], "unit": "TFLOP/s", "frac": tf / peaks["tc_sustained"],
+                        "traffic": None, "note": "3 x 13.90 GFLOP algorithmic per window (forward, data gradient, weight gradient) against the "
+                                                 "sustained bf16 peak; f16x3 issues 3 products per MAC"}}
+    if with_cpu:
+        from oracle import ldm_train as ol, unet as ou
+        from oracle.schedulers import DDPMScheduler
+        threads = os.cpu_count() or 1
+        torch.set_num_threads(threads)
+        ucfg = ou.full_cfg()
+        usd = ou.make_unet_state_dict(ucfg, 0)
+        Bc = 4
+        osched = DDPMScheduler(1000, 0.0015, 0.0195, "linear_beta", "epsilon")
+        ol.ldm_train_step(ucfg, usd, zh[:Bc], nh[:Bc], th[:Bc], osched)
+        t0 = time.perf_counter()
+        nrep = 2
+        for _ in range(nrep):
+            ol.ldm_train_step(ucfg, usd, zh[:Bc], nh[:Bc], th[:Bc], osched)
+        dt = (time.perf_counter() - t0) / nrep
+        out["cpu_baseline"] = {"value": Bc / dt, "unit": "windows/s", "cores": threads, "kind": "port", "batch": Bc,
+                               "sample": f"{Bc} windows x {nrep} steps, oracle port (unet.py restated) + torch autograd + Adam, {threads} threads"}
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -508,7 +563,8 @@ def run_ours(args):
         # the other BASELINE.json configurations, measured in the same process (headline numbers stay config 3 / 4 above)
         configs = {"config2_unet_step_b256": measure_config2(args, dev, unet),
                    "config1_aekl_encode_decode_b4": measure_config1(args, dev),
-                   "config5_aekl_train_step_b512": measure_train(args, dev)}
+                   "config5_aekl_train_step_b512": measure_train(args, dev),
+                   "ldm_train_step_b64": measure_ldm_train(args, dev)}
         # fast mode: ONE bf16 product per MAC -- reported apart, never as parity: its error against the parity mode is below
         y16 = eegldm.ddim_sample(unet, sched, noise, DDIM_STEPS, aekl)
         ub = eegldm.UNetModel(**synthetic.LDM_UNET_CFG, math="bf16")
@@ -550,12 +606,15 @@ def run_ours(args):
 
 
 def run_train(args):
-    """--workload train: config 5 alone, as its own bench line."""
+    """--workload train: config 5 alone, as its own bench line; --workload ldm_train: the latent-diffusion training step."""
     import torch
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
     torch.cuda.set_device(dev)
-    B = args.batch if args.batch != 1024 else 512
-    r = measure_train(args, dev, B)
+    if args.workload == "ldm_train":
+        r = measure_ldm_train(args, dev, args.batch if args.batch != 1024 else 64, with_cpu=not args.no_cpu_baseline)
+        r["adversarial"] = False
+    else:
+        r = measure_train(args, dev, args.batch if args.batch != 1024 else 512)
     line = {"metric": r["metric"], "value": r["value"], "unit": r["unit"], "n_gpus": 1, "steps": max(args.steps, 10),
             "warmup": max(args.warmup, 3), "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": {"workload": r["workload"], "adversarial": r["adversarial"]},
@@ -580,10 +639,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the configs / fast_mode objects (configs 1, 2, 5 and the bf16 line)")
     ap.add_argument("--no-adversarial", action="store_true", help="config 5 without the PatchDiscriminator term")
-    ap.add_argument("--workload", default="sample", choices=["sample", "train"],
-                    help="sample = config 3/4 (headline); train = config 5 (AEKL training step)")
+    ap.add_argument("--workload", default="sample", choices=["sample", "train", "ldm_train"],
+                    help="sample = config 3/4 (headline); train = config 5 (AEKL training step); ldm_train = UNet training step (8f-2)")
     args = ap.parse_args()
-    if args.workload == "train":
+    if args.workload in ("train", "ldm_train"):
         run_train(args)
     elif args.impl == "reference":
         run_reference(args)

@@ -73,6 +73,8 @@ int eegldm_set_conv_cluster(int ctas);
  * bit 5 -- (default clear) set to switch OFF the N = 128 tiles' concatenated MMA a_hi x [w_hi | w_lo] (one N = 256 instruction
  *          into both f16x3 accumulators instead of two N = 128 ones; same arithmetic, fewer shared-memory operand reads);
  * bit 1 -- an AttentionBlock's qkv conv writes the attention kernel's fp16 hi/lo operand images instead of fp32 (f16x3; measured no faster than the separate split pass).
+ * bit 6 -- (default clear) set to switch OFF the two-warpgroup conv epilogue (eight warps draining the accumulators in 16-column
+ *          chunks instead of four in 32-column chunks).
  * Call before creating models: plans cache the choices. */
 int eegldm_set_conv_tuning(int pair, int bn256_min_stages, int fuse_epilogues);
 
@@ -194,6 +196,16 @@ int eegldm_aekl_train_step(eegldm_aekl* h, const float* x_dev, const float* eps_
                            float* losses_host, void* stream);
 int eegldm_aekl_train_export(eegldm_aekl* h, int what, const char* name, float* host_out);
 int eegldm_aekl_train_sync(eegldm_aekl* h);
+/* The same autoencoder across an AUTOGRAD boundary, for the reference's unchanged loop (src/train_autoencoderkl.py:204-220:
+ * `reconstruction, z_mu, z_sigma = model(x)`; losses in PyTorch; `loss_g.backward()`; `optimizer_g.step()`):
+ * eegldm_aekl_forward_train = AutoencoderKL.forward(x) in training mode with the sampling noise eps supplied by the caller; the
+ * tensors the backward pass needs stay inside the handle.  eegldm_aekl_backward consumes that recorded pass: d_recon_dev /
+ * d_mu_dev / d_sigma_dev are dL/d(reconstruction), dL/d(z_mu), dL/d(z_sigma) (each nullable = zero); the parameter gradients are
+ * then read with eegldm_aekl_train_export(h, 1, name, ...).  dx_dev must be NULL (the input signal's gradient is not computed). */
+int eegldm_aekl_forward_train(eegldm_aekl* h, const float* x_dev, const float* eps_dev, float* recon_dev, float* z_mu_dev,
+                              float* z_sigma_dev, int B, int L, void* stream);
+int eegldm_aekl_backward(eegldm_aekl* h, const float* d_recon_dev, const float* d_mu_dev, const float* d_sigma_dev, float* dx_dev,
+                         void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Discriminator: replaces generative.networks.nets.PatchDiscriminator as built at src/train_autoencoderkl.py:135-137 from
@@ -220,6 +232,13 @@ int eegldm_disc_finalize(eegldm_disc* h);
  * batch statistics and updates the running ones (the reference never calls discriminator.eval()); else the running statistics. */
 int eegldm_disc_forward(eegldm_disc* h, const float* x_dev, float* logits_dev, int B, int L, int training, void* stream);
 int eegldm_disc_out_len(const eegldm_disc* h, int L);
+/* The discriminator across an AUTOGRAD boundary (the reference's unchanged loop, train_autoencoderkl.py:213-234):
+ * eegldm_disc_forward_train = discriminator(x)[-1] in training mode (batch statistics, running statistics updated once), the pass
+ * recorded in `slot` (0 or 1: two passes may be alive, e.g. the fake and the real batch of the discriminator part);
+ * eegldm_disc_backward consumes it: dlogits_dev [B,1,L_out] -> dx_dev [B,1,L] (nullable), and with want_param_grads the parameter
+ * gradients of this pass (eegldm_disc_export(h, 1, name, ...)). */
+int eegldm_disc_forward_train(eegldm_disc* h, const float* x_dev, float* logits_dev, int B, int L, int slot, void* stream);
+int eegldm_disc_backward(eegldm_disc* h, int slot, const float* dlogits_dev, float* dx_dev, int want_param_grads, void* stream);
 /* EEGLDM_MATH_F16X3_TC (default): the 64->128->256->512 convs, their data gradients (the forward kernel on transformed weights) and
  * their weight gradients (split-K GEMM over the positions) run on tcgen05 in the f16x3 arithmetic; EEGLDM_MATH_FP32_SIMT: fp32 FMA. */
 int eegldm_disc_set_math(eegldm_disc* h, int mode);

@@ -202,12 +202,22 @@ __global__ void __launch_bounds__(SPLIT_THREADS) act_split_kernel(const ActSplit
 // (profiles/r01_producer_bench.txt) switches parts of the producer off: no single part dominates.  Interleaving the 1-tap
 // k-steps of a skip_connection segment with the 3-tap ones (so the ring averages their tensor time) measured 10 % SLOWER on the
 // two-segment layers and was dropped.
-template <bool X3, int BN, int CL, bool PAIR, bool DIRECT>
-__global__ void __launch_bounds__(DIRECT ? 384 : NUM_THREADS, 1) conv_tc_kernel(const TcConvParams p) {
+//
+// EPI8: two epilogue warpgroups instead of one.  With N = 256 in f16x3 the two accumulators fill TMEM, so the epilogue of a tile cannot
+// overlap the next mainloop and its duration is lost tensor time (10-17 k cycles per tile, 20-40 % on the K <= 1536 layers:
+// profiles/r02_summary.md).  One warp per scheduler is latency-bound (every TMEM load -> transpose -> global store chain is exposed);
+// two warps per scheduler, each draining half of the tile's columns in 16-column chunks, halve that time.  Thread t of warp w
+// (lane quarter ew = w & 3, column half eh = w >> 2) owns 4 consecutive positions (ew*4 .. +3) of ONE 16-position segment (lane / 4)
+// x 4 channels per chunk.
+constexpr int conv_tc_threads(bool direct, bool epi8) { return direct ? (epi8 ? 512 : 384) : (epi8 ? 320 : NUM_THREADS); }
+template <bool X3, int BN, int CL, bool PAIR, bool DIRECT, bool EPI8 = false>
+__global__ void __launch_bounds__(conv_tc_threads(DIRECT, EPI8), 1) conv_tc_kernel(const TcConvParams p) {
     static_assert(!PAIR || CL == 2, "a CTA pair is a cluster of 2");
     static_assert(!(PAIR && DIRECT), "the fused producer is implemented for single-CTA MMAs");
-    constexpr int NPROD = DIRECT ? 6 : 0;            // producer warps 4 .. 4+NPROD-1
-    constexpr int W_LOAD = 4 + NPROD, W_MMA = 5 + NPROD;
+    static_assert(!(PAIR && EPI8), "the two-warpgroup epilogue is implemented for single-CTA MMAs");
+    constexpr int NEPI = EPI8 ? 8 : 4;               // epilogue warps 0 .. NEPI-1
+    constexpr int NPROD = DIRECT ? 6 : 0;            // producer warps NEPI .. NEPI+NPROD-1
+    constexpr int W_LOAD = NEPI + NPROD, W_MMA = NEPI + 1 + NPROD;
     constexpr int BNL = PAIR ? BN / 2 : BN;    // weight columns staged in THIS CTA's shared memory
     constexpr int B_HALF = BNL * BK * 2;       // hi (or lo) weight tile of one (tap, k-step): BNL x 32 x 2 B
     constexpr int B_STAGE = 2 * B_HALF;
@@ -239,7 +249,7 @@ __global__ void __launch_bounds__(DIRECT ? 384 : NUM_THREADS, 1) conv_tc_kernel(
         const uint32_t nfull = PAIR && leader ? 2 : 1;   // pair leader: own expect_tx arrive + the peer's relay
         for (int i = 0; i < NA; ++i) { mbar_init(barAfull + 8 * i, DIRECT ? 32 * NPROD : nfull); mbar_init(barAempty + 8 * i, 1); }
         for (int i = 0; i < NB; ++i) { mbar_init(barBfull + 8 * i, nfull); mbar_init(barBempty + 8 * i, PAIR ? 1 : CL); }
-        for (int i = 0; i < 2; ++i) { mbar_init(barAccFull + 8 * i, 1); mbar_init(barAccEmpty + 8 * i, PAIR ? 256 : 128); }
+        for (int i = 0; i < 2; ++i) { mbar_init(barAccFull + 8 * i, 1); mbar_init(barAccEmpty + 8 * i, PAIR ? 256 : 32 * NEPI); }
         fence_mbar_init();
     }
     constexpr uint32_t ACC_COLS = X3 ? 2 * BN : BN;    // X3: accumulator 0 = hi*hi, accumulator 1 = cross terms * 2^11
@@ -264,12 +274,174 @@ __global__ void __launch_bounds__(DIRECT ? 384 : NUM_THREADS, 1) conv_tc_kernel(
     long long tl_a = 0, tl_b = 0, tl_c = 0;
     const long long tl_start = tl ? clock64() : 0;
 #define TL_WAIT(acc, stmt) do { if (tl) { const long long t0__ = clock64(); stmt; acc += clock64() - t0__; } else { stmt; } } while (0)
-    if (DIRECT) {   // warpgroup 0 = epilogue, warpgroups 1-2 = producers + loader + MMA issuer
+    if (DIRECT && !EPI8) {   // warpgroup 0 = epilogue, warpgroups 1-2 = producers + loader + MMA issuer
         if (warp < 4) asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
         else asm volatile("setmaxnreg.dec.sync.aligned.u32 136;");
     }
+    if (DIRECT && EPI8) {    // 512 threads x 128 registers at launch: 256 x 136 (epilogue) + 256 x 120 (producers, loader, MMA issuer)
+        if (warp < 8) asm volatile("setmaxnreg.inc.sync.aligned.u32 136;");
+        else asm volatile("setmaxnreg.dec.sync.aligned.u32 120;");
+    }
 
-    if (warp < 4) {
+    if (EPI8 && warp < NEPI) {
+        // ================================================================ epilogue, two warpgroups (see the kernel comment)
+        const int ew = warp & 3, eh = warp >> 2;
+        constexpr int HC = BN / 2;                                   // columns per warpgroup
+        // per-warp transpose buffer [32 rows][16 columns], 16-byte quads XOR-swizzled by (row >> 1) & 3: conflict-free 128-bit
+        // writes (thread = row) and reads (thread = (segment, quad)) without padding
+        uint32_t* stg = reinterpret_cast<uint32_t*>(smem + STAGING_OFF) + warp * 512;
+        float2* stats = reinterpret_cast<float2*>(smem + STAGING_OFF + STAGING_BYTES);   // [warp][128]: segment * gpt + group
+        const int cpg = p.gn_cpg, gpt = p.gn_partial ? HC / cpg : 0;                        // groups per warpgroup half-tile (<= 16)
+        const int cpg_sh = 31 - __clz(max(cpg, 1));
+        const int seg = lane >> 2, quad = lane & 3, col4 = quad * 4;
+        int lt = 0;
+        for (int w = cid; w < nwork; w += ncl, ++lt) {
+            const int n_tile = w % n_ntiles, m_tile = (w / n_ntiles) * CL + crank;
+            const int as = lt % NSETS, use = lt / NSETS;
+            const int co0 = n_tile * BN + eh * HC;
+            const int g = m_tile * 8 + seg;
+            const int rb = g < p.nsegs16 ? g / spt : -1;             // sample (< 0: segment past the batch)
+            const int rt = (g % spt) * 16 + ew * 4;                  // first of this thread's 4 positions
+            const int bb = max(rb, 0);
+            const size_t obase = ((size_t)bb * p.Tout + rt) * p.Cout + co0 + col4;
+            const int tr = p.res_mode == RS_AVGPOOL2 ? 2 * rt : (p.res_mode == RS_NEAREST2 ? (rt >> 1) : rt);
+            const size_t rbase = ((size_t)bb * p.res_Tin + tr) * p.Cout + co0 + col4;
+            const int rmul = p.res_mode == RS_AVGPOOL2 ? 4 : (p.res_mode == RS_NEAREST2 ? 1 : 2);   // half-rows per position
+#define OOFF(i) (obase + (size_t)(i) * p.Cout)
+#define ROFF(i) (rbase + (size_t)(((i) * rmul) >> 1) * p.Cout)
+            // Prefetched one chunk ahead: plain loads only.  (The pooled residual's second row is loaded where the value is consumed:
+            // an average computed here, even predicated off, makes the warp wait for the loads it has just issued -- ncu showed
+            // that scoreboard wait as 41 % of the epilogue loop's samples, profiles/r02_summary.md.)
+            auto load_res = [&](int cb, float4 (&R)[4]) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) R[i] = ldg4(p.res + ROFF(i) + cb);
+            };
+            float4 Rn[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) Rn[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.res) {
+                if (quad == 0) {   // pull this warp's residual rows into L2 while the mainloop of the tile is still running
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        for (int cb = 0; cb < HC; cb += 32) {
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.res + ROFF(i) + cb));
+                            if (p.res_mode == RS_AVGPOOL2) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.res + ROFF(i) + p.Cout + cb));
+                        }
+                }
+                load_res(0, Rn);
+            }
+            // bias / time-embedding values of a chunk are loaded one chunk ahead as well (the first ones while the mainloop of the tile
+            // still runs): a load consumed in the iteration that issues it costs a full L2 round trip per chunk
+            const float* bias_p = p.bias ? p.bias + co0 + col4 : nullptr;
+            const float* temb_p = p.temb ? p.temb + (size_t)bb * p.temb_stride + co0 + col4 : nullptr;
+            float4 biasn = bias_p ? ldg4(bias_p) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 Tmn = temb_p ? ldg4(temb_p) : make_float4(0.f, 0.f, 0.f, 0.f);
+            TL_WAIT(tl_a, mbar_wait(barAccFull + 8 * as, use & 1));
+            tc_fence_after();
+            const long long tl_e0 = tl ? clock64() : 0;
+            const uint32_t acc_addr = tmem + ((uint32_t)(ew * 32) << 16) + as * ACC_COLS + eh * HC;
+            uint32_t vn[16], c2n[16];
+            tmem_ld16_async(acc_addr, vn);
+            if (X3) tmem_ld16_async(acc_addr + (uint32_t)BN, c2n);
+#pragma unroll 1
+            for (int cb = 0; cb < HC; cb += 16) {
+                float4 R[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) R[i] = Rn[i];
+                if (p.res && p.res_mode == RS_AVGPOOL2) {   // AvgPool1d(2) of the residual (the two down-sampling ResBlocks): second row now
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 x1 = ldg4(p.res + ROFF(i) + p.Cout + cb);
+                        R[i] = make_float4(0.5f * (R[i].x + x1.x), 0.5f * (R[i].y + x1.y), 0.5f * (R[i].z + x1.z), 0.5f * (R[i].w + x1.w));
+                    }
+                }
+                const float4 bias4 = biasn, Tm = Tmn;
+                if (cb + 16 < HC) {
+                    if (p.res) load_res(cb + 16, Rn);
+                    if (bias_p) biasn = ldg4(bias_p + cb + 16);
+                    if (temb_p) Tmn = ldg4(temb_p + cb + 16);
+                }
+                uint32_t v[16];
+                tmem_ld_wait();
+                if (X3) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(fmaf(__uint_as_float(c2n[i]), 1.0f / LO_SCALE, __uint_as_float(vn[i])));
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = vn[i];
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    *reinterpret_cast<uint4*>(stg + lane * 16 + 4 * (j ^ ((lane >> 1) & 3))) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                if (cb + 16 < HC) {
+                    tmem_ld16_async(acc_addr + (uint32_t)(cb + 16), vn);
+                    if (X3) tmem_ld16_async(acc_addr + (uint32_t)(BN + cb + 16), c2n);
+                } else {
+                    tc_fence_before();
+                    mbar_arrive(barAccEmpty + 8 * as);   // every TMEM read of this thread has completed: the set may be overwritten
+                }
+                __syncwarp();
+                float4 O[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int row = 8 * i + seg;
+                    const float4 a = *reinterpret_cast<const float4*>(stg + row * 16 + 4 * (quad ^ ((row >> 1) & 3)));
+                    const float4 o = make_float4(a.x + bias4.x + Tm.x + R[i].x, a.y + bias4.y + Tm.y + R[i].y,
+                                                 a.z + bias4.z + Tm.z + R[i].z, a.w + bias4.w + Tm.w + R[i].w);
+                    if (rb >= 0) *reinterpret_cast<float4*>(p.out + OOFF(i) + cb) = o;
+                    O[i] = o;
+                }
+                if (p.gn_partial) {
+                    // GroupNorm statistics of the tensor being written: 4 positions x 4 channels of one segment per thread, shifted
+                    // one-pass sums, then Chan's equal-count combination over the lanes (quads) that share a group
+                    const float K = O[0].x;
+                    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float d0 = O[j].x - K, d1 = O[j].y - K, d2 = O[j].z - K, d3 = O[j].w - K;
+                        s0 += d0; s1 += d1; s2 += d2; s3 += d3;
+                        q0 = fmaf(d0, d0, q0); q1 = fmaf(d1, d1, q1); q2 = fmaf(d2, d2, q2); q3 = fmaf(d3, d3, q3);
+                    }
+                    const float sd = (s0 + s1) + (s2 + s3);
+                    float mean = fmaf(sd, 1.f / 16.f, K);
+                    float m2 = fmaxf((q0 + q1) + (q2 + q3) - sd * sd * (1.f / 16.f), 0.f);
+                    float n = 16.f;
+                    for (int off = 1; off * 4 < cpg; off <<= 1) {
+                        const float mo = __shfl_xor_sync(0xffffffffu, mean, off), qo = __shfl_xor_sync(0xffffffffu, m2, off);
+                        const float d = mo - mean;
+                        m2 = m2 + qo + d * d * (0.5f * n);
+                        mean = 0.5f * (mean + mo);
+                        n *= 2.f;
+                    }
+                    if ((col4 & (cpg - 1)) == 0) stats[warp * 128 + seg * gpt + ((cb + col4) >> cpg_sh)] = make_float2(mean, m2);
+                }
+                __syncwarp();   // the transpose buffer is reused by the next chunk
+            }
+#undef OOFF
+#undef ROFF
+            if (tl) tl_b += clock64() - tl_e0;
+            if (p.gn_partial) {
+                // the 4 warps of this warpgroup hold the 4 position-quarters of every segment: combine them into one
+                // (count, mean, M2) record per (sample, 16-position segment, group) for gn_finalize
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + eh) : "memory");
+                const float nq = 4.f * cpg;
+                const float2* sw = stats + eh * 512;
+                for (int e = tid & 127; e < 8 * gpt; e += 128) {
+                    const int sg = e / gpt, gi = e - sg * gpt, g16 = m_tile * 8 + sg;
+                    const float2 a = sw[e], b = sw[128 + e], c = sw[256 + e], d = sw[384 + e];
+                    const float mean = 0.25f * ((a.x + b.x) + (c.x + d.x));
+                    const float da = a.x - mean, db = b.x - mean, dc = c.x - mean, dd = d.x - mean;
+                    const float m2 = (a.y + b.y) + (c.y + d.y) + nq * ((da * da + db * db) + (dc * dc + dd * dd));
+                    if (g16 < p.nsegs16) {
+                        float* o = p.gn_partial + ((size_t)g16 * (p.Cout / cpg) + co0 / cpg + gi) * 3;   // [b][segment][group][3]
+                        o[0] = 4.f * nq; o[1] = mean; o[2] = m2;
+                    }
+                }
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + eh) : "memory");   // the stats buffer is rewritten by the next tile
+            }
+        }
+        if (tl && tid == 0) { tlo[TC_TL_EPI_WAIT] = tl_a; tlo[TC_TL_EPI_BUSY] = tl_b; tlo[TC_TL_TILES] = lt; tlo[TC_TL_TOTAL] = clock64() - tl_start; }
+    } else if (!EPI8 && warp < 4) {
         // ================================================================ epilogue
         // TMEM gives each thread one M row (32 columns per load).  The 32x32 block is transposed through a padded
         // per-warp staging buffer so that global loads (residual, time embedding) and stores are 128-byte row segments:
@@ -303,14 +475,10 @@ __global__ void __launch_bounds__(DIRECT ? 384 : NUM_THREADS, 1) conv_tc_kernel(
 #define OOFF(i) (obase[(i) & 1] + (size_t)((i) >> 1) * p.Cout)
 #define ROFF(i) (rbase[(i) & 1] + (size_t)((((i) >> 1) * rmul) >> 1) * p.Cout)
             // residual rows of one 32-column chunk, all 8 loads in flight at once (prefetched one chunk ahead)
+            // plain loads only: the pooled residual's second row is loaded where the value is consumed (see the EPI8 epilogue)
             auto load_res = [&](int cb, float4 (&R)[8]) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    if (p.res_mode == RS_AVGPOOL2) {
-                        const float4 x0 = ldg4(p.res + ROFF(i) + cb), x1 = ldg4(p.res + ROFF(i) + p.Cout + cb);
-                        R[i] = make_float4(0.5f * (x0.x + x1.x), 0.5f * (x0.y + x1.y), 0.5f * (x0.z + x1.z), 0.5f * (x0.w + x1.w));
-                    } else R[i] = ldg4(p.res + ROFF(i) + cb);
-                }
+                for (int i = 0; i < 8; ++i) R[i] = ldg4(p.res + ROFF(i) + cb);
             };
             float4 Rn[8];
 #pragma unroll
@@ -343,6 +511,13 @@ __global__ void __launch_bounds__(DIRECT ? 384 : NUM_THREADS, 1) conv_tc_kernel(
                 float4 R[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) R[i] = Rn[i];
+                if (p.res && p.res_mode == RS_AVGPOOL2) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 x1 = ldg4(p.res + ROFF(i) + p.Cout + cb);
+                        R[i] = make_float4(0.5f * (R[i].x + x1.x), 0.5f * (R[i].y + x1.y), 0.5f * (R[i].z + x1.z), 0.5f * (R[i].w + x1.w));
+                    }
+                }
                 if (p.res && cb + 32 < BN) load_res(cb + 32, Rn);
                 // bias / time-embedding rows of this chunk: issued before the TMEM loads so their latency is covered
                 const int co = co0 + cb + col4;
@@ -493,7 +668,7 @@ __global__ void __launch_bounds__(DIRECT ? 384 : NUM_THREADS, 1) conv_tc_kernel(
         // validity per tile, source selection per (tile, source) -- the k-step itself advances three pointers, issues 6 + 4
         // vector loads and runs ~11 instructions per value (affine, SiLU on ex2.approx / rcp.approx without the denormal
         // fix-ups of __expf, fp16 hi/lo split, range check).
-        const int pt = tid - 128;
+        const int pt = tid - 32 * NEPI;
         bool bad = false;
         const int r = pt & 7, c = (pt >> 3) & 3, q0 = pt >> 5;
         struct Pre { float4 x[3][2]; float4 a[2], s[2]; };
@@ -795,6 +970,7 @@ int g_conv_tc_cluster = 2;          // CTAs per cluster sharing weight stages by
 int g_conv_tc_pair = 0;             // 1: cta_group::2 CTA pairs (M=256 per MMA); 0: single-CTA MMAs (+ multicast clusters)
 int g_conv_tc_bn256_stages = 1;     // minimum weight stages per tile for the N=256 shape
 int g_conv_tc_cat = 1;              // N=128 f16x3 tiles: a_hi x [w_hi | w_lo] as one N=256 MMA
+int g_conv_tc_epi8 = 1;             // two epilogue warpgroups (EPI8); eegldm_set_conv_tuning bit 6 switches it off (A/B timing)
 bool conv_tc_gn_ok(int Cout, int G) {
     if (G <= 0 || Cout % G) return false;
     const int cpg = Cout / G;
@@ -841,11 +1017,11 @@ cudaError_t launch_act_split(const ActSplitParams& p, bool x3, cudaStream_t st) 
     return cudaGetLastError();
 }
 
-template <bool X3, int BN, int CL, bool PAIR, bool DIRECT = false>
+template <bool X3, int BN, int CL, bool PAIR, bool DIRECT = false, bool EPI8 = false>
 cudaError_t launch_conv_tc_t(const TcConvParams& p, int num_sms, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<X3, BN, CL, PAIR, DIRECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(PAIR || DIRECT));
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<X3, BN, CL, PAIR, DIRECT, EPI8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(PAIR || DIRECT));
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
@@ -853,16 +1029,17 @@ cudaError_t launch_conv_tc_t(const TcConvParams& p, int num_sms, cudaStream_t st
     const int nwork = (p.Cout / BN) * ((n_mtiles + CL - 1) / CL);
     int nclusters = num_sms / CL;
     if (nwork < nclusters) nclusters = nwork;
+    if (p.debug & 64) nclusters = 1;   // timing experiment: one cluster alone on the device (no memory-system contention)
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(nclusters * CL);   // persistent: one CTA per SM
-    cfg.blockDim = dim3(DIRECT ? 384 : NUM_THREADS);
+    cfg.blockDim = dim3(conv_tc_threads(DIRECT, EPI8));
     cfg.dynamicSmemBytes = smem_bytes(PAIR || DIRECT);
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, conv_tc_kernel<X3, BN, CL, PAIR, DIRECT>, p);
+    return cudaLaunchKernelEx(&cfg, conv_tc_kernel<X3, BN, CL, PAIR, DIRECT, EPI8>, p);
 }
 
 cudaError_t launch_conv_tc(const TcConvParams& p_in, bool x3, cudaStream_t st) {
@@ -877,6 +1054,23 @@ cudaError_t launch_conv_tc(const TcConvParams& p_in, bool x3, cudaStream_t st) {
     }
     if (p.bn != 128 && p.bn != 256) return cudaErrorInvalidValue;
     cudaError_t e;
+    // two-warpgroup epilogue (EPI8): every single-CTA-MMA launch except the ones whose epilogue writes attention operand images
+    // or 32-channel GroupNorm groups (one-warpgroup epilogue only); cluster sizes 1 and 2
+    const bool epi8 = g_conv_tc_epi8 && !g_conv_tc_pair && !p.qkv16 && !(p.gn_partial && p.gn_cpg == 32) &&
+                      (p.direct || g_conv_tc_cluster == 2 || g_conv_tc_cluster == 1);
+#define EEGLDM_TC8(X3, BN)                                                                               \
+    (p.direct ? (g_conv_tc_cluster == 1 ? launch_conv_tc_t<X3, BN, 1, false, true, true>(p, num_sms, st)   \
+                                        : launch_conv_tc_t<X3, BN, 2, false, true, true>(p, num_sms, st))  \
+     : g_conv_tc_cluster == 2 ? launch_conv_tc_t<X3, BN, 2, false, false, true>(p, num_sms, st)          \
+                              : launch_conv_tc_t<X3, BN, 1, false, false, true>(p, num_sms, st))
+    if (epi8) {
+        if (p.bn == 256) e = x3 ? EEGLDM_TC8(true, 256) : EEGLDM_TC8(false, 256);
+        else e = x3 ? EEGLDM_TC8(true, 128) : EEGLDM_TC8(false, 128);
+        if (e != cudaSuccess) return e;
+        g_launch_count += 1;
+        return cudaGetLastError();
+    }
+#undef EEGLDM_TC8
 #define EEGLDM_TC(X3, BN)                                                                         \
     (p.direct ? (g_conv_tc_cluster == 1 ? launch_conv_tc_t<X3, BN, 1, false, true>(p, num_sms, st)   \
                                         : launch_conv_tc_t<X3, BN, 2, false, true>(p, num_sms, st))  \

@@ -68,6 +68,7 @@ struct eegldm_disc {
     int step = 0;
     long long batches_tracked = 0;
     DiscPass fake, real;
+    size_t pass_end[2] = {0, 0}, slot_floats = 0;   // autograd boundary (eegldm_disc_forward_train): two workspace halves, one per recorded pass
     ~eegldm_disc() { for (void* p : {(void*)P, (void*)G, (void*)M, (void*)V, (void*)R, (void*)Wd, (void*)sums, (void*)ws, (void*)losses, (void*)img, (void*)wv}) if (p) cudaFree(p); }
     float* alloc(size_t n) { n = (n + 63) & ~size_t(63); float* p = ws ? ws + ws_off : nullptr; ws_off += n; return p; }
 };
@@ -508,6 +509,59 @@ int eegldm_disc_forward(eegldm_disc* d, const float* x_dev, float* logits_dev, i
     if (training) d->batches_tracked += 1;
     DCU(cudaMemcpyAsync(logits_dev, ps.h.back(), (size_t)B * ps.T.back() * sizeof(float), cudaMemcpyDeviceToDevice, st));
     d->fake.valid = d->real.valid = false;
+    return EEGLDM_OK;
+}
+
+// PatchDiscriminator.forward(x)[-1] in training mode across an autograd boundary (the reference's own loop,
+// train_autoencoderkl.py:213-234: logits = discriminator(x)[-1]; loss.backward(); optimizer_d.step()).  Up to two recorded passes
+// (slot 0 / 1: the fake and the real batch of the discriminator part) live in the handle; each is consumed by ONE backward call.
+int eegldm_disc_forward_train(eegldm_disc* d, const float* x_dev, float* logits_dev, int B, int L, int slot, void* stream) {
+    if (!d) return dfail(EEGLDM_ERR_INVALID, "null handle");
+    if (!d->finalized) return dfail(EEGLDM_ERR_MISSING, "eegldm_disc_finalize has not been called");
+    if (d->cfg.in_channels != 1 || d->cfg.out_channels != 1)
+        return dfail(EEGLDM_ERR_INVALID, "discriminator forward: in / out channels must be 1 (config_aekl_eeg.yaml:34-35)");
+    if (slot != 0 && slot != 1) return dfail(EEGLDM_ERR_INVALID, "slot must be 0 or 1");
+    if (B <= 0 || L < 8) return dfail(EEGLDM_ERR_SHAPE, "bad input shape");
+    if (!x_dev || !logits_dev) return dfail(EEGLDM_ERR_INVALID, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t half = pass_floats(d, B, L, true) + (size_t)B * L + (size_t)B * (L / 8 + 8) + 1024;
+    if (half != d->slot_floats || 2 * half > d->ws_cap) {   // shape change: both recorded passes are gone
+        float* old = d->ws;
+        int r = ensure_ws(d, 2 * half);
+        if (r) return r;
+        (void)old;
+        d->slot_floats = half;
+        d->fake.valid = d->real.valid = false;
+    }
+    DiscPass& ps = slot ? d->real : d->fake;
+    d->ws_off = (size_t)slot * half;
+    float* xk = d->alloc((size_t)B * L);   // the pass keeps its own copy of the input (read again by the backward sweep)
+    DCU(cudaMemcpyAsync(xk, x_dev, (size_t)B * L * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    int r = disc_forward(d, xk, B, L, true, 1, ps, st);
+    if (r) return r;
+    d->pass_end[slot] = d->ws_off;
+    d->batches_tracked += 1;
+    DCU(cudaMemcpyAsync(logits_dev, ps.h.back(), (size_t)B * ps.T.back() * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return EEGLDM_OK;
+}
+
+// dlogits_dev [B, 1, L_out] -> dx_dev (nullable) [B, 1, L]; want_param_grads: the parameter gradients of THIS pass replace the handle's
+// gradient buffer (eegldm_disc_export(h, 1, ...)).
+int eegldm_disc_backward(eegldm_disc* d, int slot, const float* dlogits_dev, float* dx_dev, int want_param_grads, void* stream) {
+    if (!d || !dlogits_dev) return dfail(EEGLDM_ERR_INVALID, "null argument");
+    if (slot != 0 && slot != 1) return dfail(EEGLDM_ERR_INVALID, "slot must be 0 or 1");
+    DiscPass& ps = slot ? d->real : d->fake;
+    if (!ps.valid || !d->slot_floats) return dfail(EEGLDM_ERR_MISSING, "no recorded forward pass in this slot (eegldm_disc_forward_train)");
+    cudaStream_t st = (cudaStream_t)stream;
+    d->ws_off = d->pass_end[slot];
+    const size_t n = (size_t)ps.B * ps.T.back() * d->cfg.out_channels;
+    float* dl = d->alloc(n);
+    DCU(cudaMemcpyAsync(dl, dlogits_dev, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (want_param_grads) DCU(cudaMemsetAsync(d->G, 0, d->nP * sizeof(float), st));
+    int r = disc_backward(d, ps, dl, want_param_grads != 0, dx_dev, 0, st);
+    ps.valid = false;
+    if (r) return r;
+    if (d->ws_off > (size_t)(slot + 1) * d->slot_floats) return dfail(EEGLDM_ERR_NOMEM, "discriminator workspace overflow");
     return EEGLDM_OK;
 }
 

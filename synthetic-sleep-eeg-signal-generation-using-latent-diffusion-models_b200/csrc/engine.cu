@@ -375,6 +375,7 @@ bool g_conv_qkv_fused = false; // the qkv conv writes attention operand images d
 bool g_attn_direct = false;    // the tcgen05 attention splits fp32 q, k, v itself (eegldm_set_conv_tuning bit 4): measured no faster
 bool g_attn_u_fused = true;    // the tcgen05 attention writes proj_out's operand image instead of fp32 (eegldm_set_conv_tuning bit 3)
 bool g_conv_direct = true;     // tensor-pipe convs produce their activation operands in-kernel (no act_split pre-pass)
+bool g_conv_direct_wide = false;   // fused producer also for 1x1 convs with more than two N tiles (qkv): eegldm_set_conv_tuning bit 7
 bool g_conv_gn_fused = true;   // tensor-pipe convs emit the GroupNorm statistics of their output (eegldm_set_conv_tuning)
 bool g_graphs_enabled = true;
 // Denoise-step graph of eegldm_ddim_sample: 2 = the batch is planned as two independent halves captured on two streams
@@ -684,7 +685,7 @@ void plan_conv(Builder& bd, ConvParams p, const uint8_t* tw0 = nullptr, const ui
         // fused producer: the conv kernel reads the fp32 sources itself (no act_split pass, no U tensors); AvgPool inputs
         // (the two down-sampling ResBlocks) keep the pre-pass
         // and 1x1 convs with many N tiles (qkv: 6) would redo the transform per N tile with only one tap of MMAs to hide it
-        bool direct = g_conv_direct && !qkv && !premade_u0 && !(p.seg[0].taps == 1 && p.Cout / q.bn > 2);
+        bool direct = g_conv_direct && !qkv && !premade_u0 && (g_conv_direct_wide || !(p.seg[0].taps == 1 && p.Cout / q.bn > 2));
         for (int s = 0; direct && s < p.nseg; ++s) direct = p.seg[s].resample == RS_NONE || p.seg[s].resample == RS_NEAREST2;
         q.direct = direct ? 1 : 0;
         for (int s = 0; s < p.nseg; ++s) {
@@ -1103,6 +1104,8 @@ struct ALayer {
 namespace {
 struct TrainOff { size_t w1 = 0, b1 = 0, g1 = 0, be1 = 0, w2 = 0, b2 = 0, g2 = 0, be2 = 0, ws = 0, bs = 0; };
 struct TrainEntry { std::string name; size_t off; std::vector<int64_t> shape; bool conv; };
+struct AeklPending;                      // a recorded forward pass waiting for eegldm_aekl_backward (defined with TrainRun)
+void aekl_pending_free(AeklPending* p);
 struct AeklTrain {
     std::vector<TrainOff> enc, dec;
     TrainOff qmu, qls, pq;
@@ -1112,7 +1115,9 @@ struct AeklTrain {
     size_t arena_cap = 0;
     int step = 0;
     bool dirty = false;   // P has moved away from the host state_dict / inference weights
+    AeklPending* pending = nullptr;
     ~AeklTrain() {
+        if (pending) aekl_pending_free(pending);
         for (float* p : {P, G, M, V, losses, arena}) if (p) cudaFree(p);
     }
 };
@@ -1385,6 +1390,8 @@ int eegldm_set_conv_tuning(int pair, int bn256_min_stages, int fuse_epilogues) {
     g_conv_direct = (fuse_epilogues & 4) != 0;
     g_attn_u_fused = (fuse_epilogues & 8) != 0;
     g_attn_direct = (fuse_epilogues & 16) != 0;
+    g_conv_direct_wide = (fuse_epilogues & 128) != 0;
+    g_conv_tc_epi8 = (fuse_epilogues & 64) ? 0 : 1;  // bit 6 switches the two-warpgroup conv epilogue OFF (A/B timing)
     g_conv_tc_cat = (fuse_epilogues & 32) ? 0 : 1;   // bit 5 switches the concatenated hi|lo MMA of the N = 128 tiles OFF (A/B timing)
     if (bn256_min_stages < 1) return fail(EEGLDM_ERR_INVALID, "bn256_min_stages must be >= 1");
     g_conv_tc_pair = pair;
@@ -1444,6 +1451,7 @@ int eegldm_unet_param_info(const eegldm_unet* h, int i, const char** name, int64
 int eegldm_unet_load(eegldm_unet* h, const char* name, const float* host, const int64_t* shape, int ndim) {
     if (!h) return fail(EEGLDM_ERR_INVALID, "null handle");
     h->finalized = false;
+    if (h->train) { unet_train_free(h->train); h->train = nullptr; }   // new weights: optimiser state starts over
     return h->ps.load(name, host, shape, ndim);
 }
 int eegldm_unet_finalize(eegldm_unet* h) {
@@ -2156,6 +2164,7 @@ struct TrainRun {
     };
     std::vector<Op> tape;
     std::unordered_map<const float*, std::pair<float*, bool>> grads;
+    const float *dmu_ext = nullptr, *dsigma_ext = nullptr;   // gradients at the z_mu / z_sigma outputs (eegldm_aekl_backward)
 
     float* alloc(size_t n) { n = (n + 63) & ~size_t(63); float* p = dry ? nullptr : base + off; off += n; return p; }
     TT tensor(int C, int T) { TT x; x.C = C; x.T = T; x.p = alloc((size_t)B * T * C); return x; }
@@ -2266,16 +2275,99 @@ struct TrainRun {
                 if (dz == grads.end() || !dz->second.second) continue;
                 auto& gm = slot(op.mu); auto& gl = slot(op.lv);
                 ck(launch_latent(op.mu.p, op.lv.p, op.eps, nullptr, nullptr, dz->second.first, gm.first, gl.first, nullptr, kl_weight, B,
-                                 numel(op.mu), st));
+                                 numel(op.mu), st, dmu_ext, dsigma_ext));
                 gm.second = gl.second = true;
             }
         }
     }
 };
 
+struct AeklPending { TrainRun run; TT recon, mu, sigma; int B, L; };
+void aekl_pending_free(AeklPending* p) { delete p; }
+
+// the forward pass of the training step: encoder, reparameterisation with the caller's eps, decoder (tape recorded unless dry)
+TT aekl_train_forward(eegldm_aekl* h, AeklTrain& t, TrainRun& tr, const float* x_dev, const float* eps_dev, int L, TT* mu_out, TT* sigma_out,
+                      cudaStream_t st) {
+    const int z = h->cfg.latent_channels, T = L / h->down_factor();
+    TT x; x.p = const_cast<float*>(x_dev); x.C = 1; x.T = L;
+    TT h3 = tr.blocks(h->enc, t.enc, x, /*first_needs_grad=*/false);
+    TT mu = tr.conv(h3, t.qmu.w1, t.qmu.b1, z, 1, 1, 0, 0, nullptr);
+    TT lv = tr.conv(h3, t.qls.w1, t.qls.b1, z, 1, 1, 0, 0, nullptr);
+    TT sigma = tr.tensor(z, T), zz = tr.tensor(z, T);
+    if (!tr.dry) {
+        tr.ck(launch_latent(mu.p, lv.p, eps_dev, sigma.p, zz.p, nullptr, nullptr, nullptr, t.losses + 1, 0.f, tr.B, tr.numel(mu), st));
+        TrainRun::Op op; op.kind = TrainRun::LATENT; op.out = zz; op.mu = mu; op.lv = lv; op.sigma = sigma; op.eps = eps_dev;
+        tr.tape.push_back(op);
+    }
+    if (mu_out) *mu_out = mu;
+    if (sigma_out) *sigma_out = sigma;
+    TT pq = tr.conv(zz, t.pq.w1, t.pq.b1, z, 1, 1, 0, 0, nullptr);
+    return tr.blocks(h->dec, t.dec, pq, true);
+}
 }  // namespace
 
 extern "C" {
+
+// AutoencoderKL.forward(x) in training mode across an autograd boundary (the reference's own loop, train_autoencoderkl.py:204-220:
+// model(x) -> losses in PyTorch -> loss_g.backward() -> optimizer_g.step()): the forward pass keeps its tape inside the handle ...
+int eegldm_aekl_forward_train(eegldm_aekl* h, const float* x_dev, const float* eps_dev, float* recon_dev, float* z_mu_dev, float* z_sigma_dev,
+                              int B, int L, void* stream) {
+    if (!h || !x_dev || !eps_dev || !recon_dev || !z_mu_dev || !z_sigma_dev) return fail(EEGLDM_ERR_INVALID, "null argument");
+    if (h->cfg.in_channels != 1 || h->cfg.out_channels != 1 || h->cfg.latent_channels != 1)
+        return fail(EEGLDM_ERR_INVALID, "training supports in / out / latent channels = 1 (every reference config)");
+    const int f = h->down_factor();
+    if (B <= 0 || L <= 0 || L % f) return fail(EEGLDM_ERR_SHAPE, "L must be a positive multiple of 2^(levels-1), B > 0");
+    for (int i = 0; i < h->cfg.n_levels; ++i)
+        if (h->cfg.num_channels[i] / h->cfg.norm_num_groups > 256) return fail(EEGLDM_ERR_INVALID, "channels per group > 256 not supported in training");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!h->train) { int r = aekl_train_init(h); if (r) return r; }
+    AeklTrain& t = *h->train;
+    if (t.pending) { aekl_pending_free(t.pending); t.pending = nullptr; }
+    TrainRun sizing{h, &t, B, st, true};
+    aekl_train_forward(h, t, sizing, nullptr, nullptr, L, nullptr, nullptr, st);
+    int r = ensure(t.arena, t.arena_cap, sizing.off * 2 + (size_t)B * (L / f) + (size_t)(1 << 20));
+    if (r) return r;
+    auto* pd = new AeklPending{TrainRun{h, &t, B, st, false}, TT{}, TT{}, TT{}, B, L};
+    pd->run.base = t.arena;
+    // eps is read again by the backward pass: keep a copy in the arena (the caller's tensor may be gone by then)
+    const size_t nz = (size_t)B * (L / f);
+    float* eps_keep = pd->run.alloc(nz);
+    CU(cudaMemcpyAsync(eps_keep, eps_dev, nz * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemsetAsync(t.losses, 0, 4 * sizeof(float), st));
+    pd->recon = aekl_train_forward(h, t, pd->run, x_dev, eps_keep, L, &pd->mu, &pd->sigma, st);
+    if (pd->run.err != cudaSuccess) { cudaError_t e = pd->run.err; delete pd; return cuda_fail(e, "training forward"); }
+    CU(cudaMemcpyAsync(recon_dev, pd->recon.p, (size_t)B * L * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemcpyAsync(z_mu_dev, pd->mu.p, nz * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemcpyAsync(z_sigma_dev, pd->sigma.p, nz * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    t.pending = pd;
+    return EEGLDM_OK;
+}
+
+// ... and the backward pass takes dL/d(reconstruction), dL/d(z_mu), dL/d(z_sigma) (each nullable = zero) and leaves the parameter
+// gradients in the handle (eegldm_aekl_train_export(h, 1, name, ...)); dx_dev (nullable) receives dL/dx.
+int eegldm_aekl_backward(eegldm_aekl* h, const float* d_recon_dev, const float* d_mu_dev, const float* d_sigma_dev, float* dx_dev, void* stream) {
+    if (!h || !h->train || !h->train->pending) return fail(EEGLDM_ERR_MISSING, "no recorded forward pass (eegldm_aekl_forward_train)");
+    if (dx_dev) return fail(EEGLDM_ERR_INVALID, "the gradient with respect to the input signal is not computed (the first conv skips it)");
+    AeklTrain& t = *h->train;
+    AeklPending* pd = t.pending;
+    cudaStream_t st = (cudaStream_t)stream;
+    TrainRun& tr = pd->run;
+    tr.st = st;
+    CU(cudaMemsetAsync(t.G, 0, t.n * sizeof(float), st));
+    auto& gr = tr.slot(pd->recon);
+    if (d_recon_dev) CU(cudaMemcpyAsync(gr.first, d_recon_dev, tr.numel(pd->recon) * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    else CU(cudaMemsetAsync(gr.first, 0, tr.numel(pd->recon) * sizeof(float), st));
+    gr.second = true;
+    tr.dmu_ext = d_mu_dev; tr.dsigma_ext = d_sigma_dev;
+    tr.backward(0.f);
+    const cudaError_t e = tr.err;
+    const bool overflow = tr.off > t.arena_cap;
+    aekl_pending_free(pd);
+    t.pending = nullptr;
+    if (e != cudaSuccess) return cuda_fail(e, "training backward");
+    if (overflow) return fail(EEGLDM_ERR_NOMEM, "training arena overflow");
+    return EEGLDM_OK;
+}
 
 int eegldm_jukebox_loss(const float* input_dev, const float* target_dev, int B, int C, int N, int reduction, float* loss_dev,
                         float* grad_input_dev, void* stream) {
@@ -2308,20 +2400,7 @@ static int aekl_train_step_impl(eegldm_aekl* h, eegldm_disc* disc, const float* 
     if (!h->train) { int r = aekl_train_init(h); if (r) return r; }
     AeklTrain& t = *h->train;
     const int z = h->cfg.latent_channels, T = L / f;
-    auto run = [&](TrainRun& tr) {
-        TT x; x.p = const_cast<float*>(x_dev); x.C = 1; x.T = L;
-        TT h3 = tr.blocks(h->enc, t.enc, x, /*first_needs_grad=*/false);
-        TT mu = tr.conv(h3, t.qmu.w1, t.qmu.b1, z, 1, 1, 0, 0, nullptr);
-        TT lv = tr.conv(h3, t.qls.w1, t.qls.b1, z, 1, 1, 0, 0, nullptr);
-        TT sigma = tr.tensor(z, T), zz = tr.tensor(z, T);
-        if (!tr.dry) {
-            tr.ck(launch_latent(mu.p, lv.p, eps_dev, sigma.p, zz.p, nullptr, nullptr, nullptr, t.losses + 1, 0.f, B, tr.numel(mu), st));
-            TrainRun::Op op; op.kind = TrainRun::LATENT; op.out = zz; op.mu = mu; op.lv = lv; op.sigma = sigma; op.eps = eps_dev;
-            tr.tape.push_back(op);
-        }
-        TT pq = tr.conv(zz, t.pq.w1, t.pq.b1, z, 1, 1, 0, 0, nullptr);
-        return tr.blocks(h->dec, t.dec, pq, true);
-    };
+    auto run = [&](TrainRun& tr) { return aekl_train_forward(h, t, tr, x_dev, eps_dev, L, nullptr, nullptr, st); };
     // eps is given in the reference NCL layout; the engine's latent tensors are channels-last
     if (z != 1) return fail(EEGLDM_ERR_INVALID, "training step supports latent_channels = 1 (config_aekl_eeg_2_2_4_spec.yaml)");
     TrainRun sizing{h, &t, B, st, true};

@@ -131,6 +131,7 @@ cudaError_t launch_conv_tc(const TcConvParams& p, bool x3, cudaStream_t st);
 extern int g_conv_tc_cluster;        // CTAs per cluster sharing weight stages (1, 2, 4) when g_conv_tc_pair == 0
 extern int g_conv_tc_pair;           // cta_group::2 CTA pairs (default 1)
 extern int g_conv_tc_bn256_stages;   // N=256 tiles from this many weight stages per tile
+extern int g_conv_tc_epi8;           // two epilogue warpgroups (eegldm_set_conv_tuning bit 6 = off)
 extern int g_conv_tc_cat;            // N=128 f16x3 tiles: hi x [hi | lo] as one N=256 MMA (eegldm_set_conv_tuning bit 5)
 cudaError_t launch_groupnorm(const GnParams& p, cudaStream_t st);
 cudaError_t launch_groupnorm_finalize(const GnParams& p, cudaStream_t st);   // statistics already in p.partial (p.nsplit records)
@@ -197,7 +198,8 @@ cudaError_t launch_gn_act_fwd(const GnParams& p, float* a, int silu, cudaStream_
 cudaError_t launch_axpy(const float* src, float* dst, float alpha, int accumulate, size_t n, cudaStream_t st);
 cudaError_t launch_l1_loss(const float* r, const float* x, float* dr, float* loss, float weight, size_t n, cudaStream_t st);
 cudaError_t launch_latent(const float* mu, const float* lv, const float* eps, float* sigma, float* z, const float* dz, float* dmu,
-                          float* dlv, float* kl_loss, float kl_weight, int B, size_t n, cudaStream_t st);
+                          float* dlv, float* kl_loss, float kl_weight, int B, size_t n, cudaStream_t st, const float* dmu_ext = nullptr,
+                          const float* dsigma_ext = nullptr);
 // ---- PatchDiscriminator / adversarial loss (train_kernels.cu): BatchNorm1d in training mode over channels-last rows [N][C]
 cudaError_t launch_bn_stats(const float* h, size_t N, int C, const float* gamma, const float* beta, float eps, int B, double* sums /*[2C]*/,
                             float* scale /*[B][C]*/, float* shift, float* mean /*[C]*/, float* rstd, float* run_mean, float* run_var,

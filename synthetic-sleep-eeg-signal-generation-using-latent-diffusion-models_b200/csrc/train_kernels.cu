@@ -79,39 +79,70 @@ __global__ void conv_bwd_data_kernel(const float* __restrict__ dy, const float* 
 // (P = WG_P positions per block: 64, halved by the launcher until the two tiles fit shared memory)
 __global__ void __launch_bounds__(256) conv_bwd_weight_kernel(const float* __restrict__ dy, const float* __restrict__ a,
                                                                float* __restrict__ dw, float* __restrict__ db, int Cin, int Cout,
-                                                               int taps, int stride, int pad, int ups, int Tin, int Tc, int Tout, int WG_P) {
+                                                               int taps, int stride, int pad, int ups, int Tin, int Tc, int Tout, int WG_P,
+                                                               int ntiles_t, int ntiles) {
+    // Persistent over (sample, position tile): narrow convs (Cin * taps * Cout <= 2048: the 1-channel in / out convs of the UNet and
+    // of the discriminator) keep their weight-gradient partial sums in registers across all the block's tiles and issue ONE
+    // atomicAdd per weight per block -- with one atomic per weight per tile the 10^4 tiles of such a layer serialise on a few
+    // hundred addresses.  Wider convs (fp32 fallback only; the tensor-pipe path has wgrad_tc_kernel) add per tile.
     extern __shared__ float sm[];
     float* dys = sm;                       // [P][Cout]
     float* as = sm + WG_P * Cout;          // [rows][Cin]
-    const int b = blockIdx.y, t0 = blockIdx.x * WG_P;
-    const int np = min(WG_P, Tout - t0);
-    const int rows = (WG_P - 1) * stride + taps;
-    const int u0 = t0 * stride - pad;
-    for (int i = threadIdx.x; i < WG_P * Cout; i += blockDim.x) {
-        const int p = i / Cout, co = i % Cout;
-        dys[i] = p < np ? dy[((size_t)b * Tout + t0 + p) * Cout + co] : 0.f;
-    }
-    for (int i = threadIdx.x; i < rows * Cin; i += blockDim.x) {
-        const int r = i / Cin, ci = i % Cin;
-        const int uc = u0 + r;
-        float v = 0.f;
-        if (uc >= 0 && uc < Tc) v = a[((size_t)b * Tin + (ups ? (uc >> 1) : uc)) * Cin + ci];
-        as[i] = v;
-    }
-    __syncthreads();
     const int nw = Cin * taps * Cout;
-    for (int i = threadIdx.x; i < nw; i += blockDim.x) {
-        const int co = i % Cout, ck = i / Cout, k = ck % taps, ci = ck / taps;   // i == packed weight index
-        float acc = 0.f;
-        for (int p = 0; p < np; ++p) acc = fmaf(dys[p * Cout + co], as[(p * stride + k) * Cin + ci], acc);
-        atomicAdd(dw + i, acc);
-    }
-    if (db)
-        for (int co = threadIdx.x; co < Cout; co += blockDim.x) {
-            float acc = 0.f;
-            for (int p = 0; p < np; ++p) acc += dys[p * Cout + co];
-            atomicAdd(db + co, acc);
+    const bool in_regs = nw <= 256 * 8;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, accb = 0.f;
+    const int rows = (WG_P - 1) * stride + taps;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int b = tile / ntiles_t, t0 = (tile - b * ntiles_t) * WG_P;
+        const int np = min(WG_P, Tout - t0);
+        const int u0 = t0 * stride - pad;
+        __syncthreads();   // the previous tile's readers are done
+        for (int i = threadIdx.x; i < WG_P * Cout; i += blockDim.x) {
+            const int p = i / Cout, co = i % Cout;
+            dys[i] = p < np ? dy[((size_t)b * Tout + t0 + p) * Cout + co] : 0.f;
         }
+        for (int i = threadIdx.x; i < rows * Cin; i += blockDim.x) {
+            const int r = i / Cin, ci = i % Cin;
+            const int uc = u0 + r;
+            float v = 0.f;
+            if (uc >= 0 && uc < Tc) v = a[((size_t)b * Tin + (ups ? (uc >> 1) : uc)) * Cin + ci];
+            as[i] = v;
+        }
+        __syncthreads();
+        if (in_regs) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int i = threadIdx.x + 256 * j;
+                if (i < nw) {
+                    const int co = i % Cout, ck = i / Cout, k = ck % taps, ci = ck / taps;   // i == packed weight index
+                    float s = 0.f;
+                    for (int p = 0; p < np; ++p) s = fmaf(dys[p * Cout + co], as[(p * stride + k) * Cin + ci], s);
+                    acc[j] += s;
+                }
+            }
+        } else {
+            for (int i = threadIdx.x; i < nw; i += blockDim.x) {
+                const int co = i % Cout, ck = i / Cout, k = ck % taps, ci = ck / taps;
+                float s = 0.f;
+                for (int p = 0; p < np; ++p) s = fmaf(dys[p * Cout + co], as[(p * stride + k) * Cin + ci], s);
+                atomicAdd(dw + i, s);
+            }
+        }
+        if (db)
+            for (int co = threadIdx.x; co < Cout; co += blockDim.x) {   // Cout <= 256 in the register form: thread co owns db[co]
+                float s = 0.f;
+                for (int p = 0; p < np; ++p) s += dys[p * Cout + co];
+                if (in_regs && Cout <= 256) accb += s; else atomicAdd(db + co, s);
+            }
+    }
+    if (in_regs) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int i = threadIdx.x + 256 * j;
+            if (i < nw) atomicAdd(dw + i, acc[j]);
+        }
+        if (db && Cout <= 256 && (int)threadIdx.x < Cout) atomicAdd(db + threadIdx.x, accb);
+    }
 }
 
 // ---- tiny-channel (1 / 2 / 4) variants for the 2-2-4 autoencoder: rows are vector loads, weights live in shared memory,
@@ -551,7 +582,8 @@ __global__ void __launch_bounds__(256) l1_loss_kernel(const float* __restrict__ 
 __global__ void __launch_bounds__(256) latent_kernel(const float* __restrict__ mu, const float* __restrict__ lv, const float* __restrict__ eps,
                                                       float* __restrict__ sigma, float* __restrict__ z, const float* __restrict__ dz,
                                                       float* __restrict__ dmu, float* __restrict__ dlv, float* __restrict__ kl_loss,
-                                                      float kl_weight, int B, size_t n) {
+                                                      float kl_weight, int B, size_t n, const float* __restrict__ dmu_ext,
+                                                      const float* __restrict__ dsigma_ext) {
     __shared__ float red[32];
     float s[1] = {0.f};
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -564,8 +596,10 @@ __global__ void __launch_bounds__(256) latent_kernel(const float* __restrict__ m
             s[0] += 0.5f * (m * m + sg * sg - logf(sg * sg) - 1.f);
         } else {
             const float m = mu[i];
-            dmu[i] = dz[i] + kl_weight * m / (float)B;
-            const float dsg = dz[i] * eps[i] + kl_weight * (sg - 1.f / sg) / (float)B;
+            // dmu_ext / dsigma_ext: gradients arriving at the z_mu / z_sigma OUTPUTS of AutoencoderKL.forward (autograd boundary,
+            // eegldm_aekl_backward: the caller's own KL term), added to the reparameterisation path
+            dmu[i] = dz[i] + kl_weight * m / (float)B + (dmu_ext ? dmu_ext[i] : 0.f);
+            const float dsg = dz[i] * eps[i] + kl_weight * (sg - 1.f / sg) / (float)B + (dsigma_ext ? dsigma_ext[i] : 0.f);
             dlv[i] = (raw > -30.f && raw < 20.f) ? dsg * sg * 0.5f : 0.f;
         }
     }
@@ -764,6 +798,9 @@ cudaError_t launch_conv_bwd_weight(const ConvGradParams& p, cudaStream_t st) {
     }
     int WG_P = 64;
     auto smem_for = [&](int P) { return ((size_t)P * p.Cout + (size_t)((P - 1) * p.stride + p.taps) * p.Cin) * sizeof(float); };
+    // narrow convs (register form of the kernel): small tiles so that several blocks share an SM -- their loads are latency-bound
+    const size_t smem_cap = (size_t)p.Cin * p.taps * p.Cout <= 2048 ? 40 * 1024 : 200 * 1024;
+    while (WG_P > 8 && smem_for(WG_P) > smem_cap) WG_P >>= 1;
     while (WG_P > 1 && smem_for(WG_P) > 200 * 1024) WG_P >>= 1;
     const size_t smem = smem_for(WG_P);
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
@@ -773,8 +810,12 @@ cudaError_t launch_conv_bwd_weight(const ConvGradParams& p, cudaStream_t st) {
         if (e != cudaSuccess) return e;
         attr = 200 * 1024;
     }
-    dim3 grid((p.Tout + WG_P - 1) / WG_P, p.B);
-    conv_bwd_weight_kernel<<<grid, 256, smem, st>>>(p.dy, p.a, p.dw, p.db, p.Cin, p.Cout, p.taps, p.stride, p.pad, p.ups, p.Tin, p.Tc, p.Tout, WG_P);
+    const int ntiles_t = (p.Tout + WG_P - 1) / WG_P;
+    const long long ntiles = (long long)ntiles_t * p.B;
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / std::max<size_t>(smem, 1)));
+    const unsigned grid = (unsigned)std::min<long long>(ntiles, 148LL * per_sm);
+    conv_bwd_weight_kernel<<<grid, 256, smem, st>>>(p.dy, p.a, p.dw, p.db, p.Cin, p.Cout, p.taps, p.stride, p.pad, p.ups, p.Tin, p.Tc, p.Tout, WG_P,
+                                                    ntiles_t, (int)ntiles);
     g_launch_count += 1;
     return cudaGetLastError();
 }
@@ -826,10 +867,11 @@ cudaError_t launch_l1_loss(const float* r, const float* x, float* dr, float* los
 }
 
 cudaError_t launch_latent(const float* mu, const float* lv, const float* eps, float* sigma, float* z, const float* dz, float* dmu,
-                          float* dlv, float* kl_loss, float kl_weight, int B, size_t n, cudaStream_t st) {
+                          float* dlv, float* kl_loss, float kl_weight, int B, size_t n, cudaStream_t st, const float* dmu_ext,
+                          const float* dsigma_ext) {
     if (!n) return cudaSuccess;
     const unsigned blocks = (unsigned)std::min<size_t>((n + 255) / 256, 148 * 8);
-    latent_kernel<<<blocks, 256, 0, st>>>(mu, lv, eps, sigma, z, dz, dmu, dlv, kl_loss, kl_weight, B, n);
+    latent_kernel<<<blocks, 256, 0, st>>>(mu, lv, eps, sigma, z, dz, dmu, dlv, kl_loss, kl_weight, B, n, dmu_ext, dsigma_ext);
     g_launch_count += 1;
     return cudaGetLastError();
 }

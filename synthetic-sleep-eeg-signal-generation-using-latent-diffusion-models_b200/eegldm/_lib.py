@@ -117,6 +117,10 @@ SIGNATURES = {
     "eegldm_aekl_train_step": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.POINTER(AeklTrainCfg), _FP, _P]),
     "eegldm_aekl_train_export": (C.c_int, [_P, C.c_int, C.c_char_p, _FP]),
     "eegldm_aekl_train_sync": (C.c_int, [_P]),
+    "eegldm_aekl_forward_train": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, _P]),
+    "eegldm_aekl_backward": (C.c_int, [_P, _P, _P, _P, _P, _P]),
+    "eegldm_disc_forward_train": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
+    "eegldm_disc_backward": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, _P]),
     "eegldm_unet_train_step": (C.c_int, [_P, C.POINTER(SchedCfg), _P, _P, _P, C.c_int, C.c_int, C.POINTER(LdmTrainCfg), _FP, _P]),
     "eegldm_unet_train_export": (C.c_int, [_P, C.c_int, C.c_char_p, _FP]),
     "eegldm_unet_train_sync": (C.c_int, [_P]),

@@ -16,6 +16,7 @@ ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--fuse", type=int, default=13)
 ap.add_argument("--bn256", type=int, default=1)
 ap.add_argument("--cluster", type=int, default=2)
+ap.add_argument("--debug", type=int, default=0, help="conv debug bits (64: one cluster alone on the device)")
 a = ap.parse_args()
 torch.cuda.set_device(0)
 torch.zeros(1, device="cuda")
@@ -31,7 +32,7 @@ for (T, ci, co, k, res) in SHAPES:
     fl = 2.0 * ci * co * k * T * a.batch
     m = C.c_float()
     tl = (C.c_double * 16)()
-    _lib.check(L.eegldm_bench_conv_timeline(a.batch, T, ci, co, k, res, 1, 0, a.reps, C.byref(m), tl, None))
+    _lib.check(L.eegldm_bench_conv_timeline(a.batch, T, ci, co, k, res, 1, a.debug, a.reps, C.byref(m), tl, None))
     tiles = max(tl[9], 1.0)
     per = lambda i: tl[i] / tiles          # cycles per tile
     issue = per(0) - per(1) - per(2) - per(3)
