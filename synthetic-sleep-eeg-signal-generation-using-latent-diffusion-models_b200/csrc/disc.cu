@@ -524,7 +524,7 @@ int eegldm_disc_forward_train(eegldm_disc* d, const float* x_dev, float* logits_
     if (B <= 0 || L < 8) return dfail(EEGLDM_ERR_SHAPE, "bad input shape");
     if (!x_dev || !logits_dev) return dfail(EEGLDM_ERR_INVALID, "null argument");
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t half = pass_floats(d, B, L, true) + (size_t)B * L + (size_t)B * (L / 8 + 8) + 1024;
+    const size_t half = (pass_floats(d, B, L, true) + (size_t)B * L + (size_t)B * (L / 8 + 8) + 1024 + 63) & ~size_t(63);   // 256-byte aligned halves
     if (half != d->slot_floats || 2 * half > d->ws_cap) {   // shape change: both recorded passes are gone
         float* old = d->ws;
         int r = ensure_ws(d, 2 * half);

@@ -13,6 +13,45 @@ from . import _lib
 from ._module import EngineModule, check_cuda_f32, default_init, register_tree
 
 
+class _AeklTrainFn(torch.autograd.Function):
+    """``AutoencoderKL.forward`` across the autograd boundary: forward = ``eegldm_aekl_forward_train`` (the tensors the backward pass
+    needs stay in the engine handle), backward = ``eegldm_aekl_backward`` + one gradient per parameter.  The parameters are passed
+    as inputs so that autograd routes their gradients to ``p.grad`` (what the reference's ``optimizer_g.step()`` consumes)."""
+
+    @staticmethod
+    def forward(ctx, mod, x, eps, *params):
+        B, _, Lx = x.shape
+        T = Lx // mod._factor
+        recon = torch.empty((B, mod.out_channels, Lx), device=x.device, dtype=torch.float32)
+        z_mu = torch.empty((B, mod.latent_channels, T), device=x.device, dtype=torch.float32)
+        z_sigma = torch.empty_like(z_mu)
+        with torch.cuda.device(x.device):
+            mod._sync_weights()
+            _lib.check(_lib.lib().eegldm_aekl_forward_train(
+                mod._h, C.c_void_p(x.data_ptr()), C.c_void_p(eps.data_ptr()), C.c_void_p(recon.data_ptr()), C.c_void_p(z_mu.data_ptr()),
+                C.c_void_p(z_sigma.data_ptr()), int(B), int(Lx), C.c_void_p(_lib.current_stream_ptr(x.device))))
+        mod._pass_token = getattr(mod, "_pass_token", 0) + 1
+        ctx.mod, ctx.token, ctx.dev = mod, mod._pass_token, x.device
+        return recon, z_mu, z_sigma
+
+    @staticmethod
+    def backward(ctx, d_recon, d_mu, d_sigma):
+        mod = ctx.mod
+        if ctx.token != mod._pass_token:
+            raise RuntimeError("eegldm.AutoencoderKL: backward through a forward pass that a later forward() has replaced "
+                               "(the engine keeps one recorded pass per model)")
+
+        def ptr(t):
+            return None if t is None else C.c_void_p(t.contiguous().float().data_ptr())
+        keep = [None if t is None else t.contiguous().float() for t in (d_recon, d_mu, d_sigma)]
+        with torch.cuda.device(ctx.dev):
+            _lib.check(_lib.lib().eegldm_aekl_backward(
+                mod._h, *[None if t is None else C.c_void_p(t.data_ptr()) for t in keep], None,
+                C.c_void_p(_lib.current_stream_ptr(ctx.dev))))
+        grads = mod._export(1)
+        return (None, None, None) + tuple(grads[n].to(ctx.dev) for n, _ in mod.named_parameters())
+
+
 class AutoencoderKL(EngineModule):
     def __init__(self, spatial_dims=1, in_channels=1, out_channels=1, num_res_blocks=(2, 2, 2, 2),
                  num_channels=(32, 64, 64, 64), attention_levels=(False, False, True, True), latent_channels=3,
@@ -208,6 +247,17 @@ class AutoencoderKL(EngineModule):
         return self.decode(z_mu)
 
     def forward(self, x):
+        """-> (reconstruction, z_mu, z_sigma), ``generative``'s AutoencoderKL.forward.  Under autograd (grad mode on and a parameter
+        that requires grad) the call is differentiable with respect to the parameters, so the reference's own training loop runs
+        unchanged (train_autoencoderkl.py:204-220: ``model(x)`` -> losses -> ``loss_g.backward()`` -> ``optimizer_g.step()``);
+        ``train_step`` is the fused, much faster form of the same step."""
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            x = check_cuda_f32(x, "x")
+            B, Cin, Lx = x.shape
+            if Cin != self.in_channels or Lx % self._factor:
+                raise ValueError("bad input shape")
+            eps = torch.randn((B, self.latent_channels, Lx // self._factor), device=x.device, dtype=torch.float32)   # sampling()
+            return _AeklTrainFn.apply(self, x.detach(), eps, *self.parameters())
         z_mu, z_sigma = self.encode(x)
         z = self.sampling(z_mu, z_sigma)
         return self.decode(z), z_mu, z_sigma

@@ -17,6 +17,50 @@ from . import _lib
 from ._module import EngineModule, check_cuda_f32, _Node
 
 
+class _DiscTrainFn(torch.autograd.Function):
+    """``discriminator(x)[-1]`` across the autograd boundary (train_autoencoderkl.py:213-234): forward records the pass in one of
+    the engine's two slots, backward returns the gradient with respect to the input signal (the generator's adversarial term)
+    and one gradient per parameter (the discriminator part)."""
+
+    @staticmethod
+    def forward(ctx, mod, x, *params):
+        B, _, Lx = x.shape
+        L = _lib.lib()
+        out = torch.empty((B, 1, L.eegldm_disc_out_len(mod._h, int(Lx))), device=x.device, dtype=torch.float32)
+        slot = mod._next_slot
+        mod._next_slot ^= 1
+        with torch.cuda.device(x.device):
+            mod._sync_weights()
+            _lib.check(L.eegldm_disc_forward_train(mod._h, C.c_void_p(x.data_ptr()), C.c_void_p(out.data_ptr()), int(B), int(Lx), int(slot),
+                                                   C.c_void_p(_lib.current_stream_ptr(x.device))))
+        mod._slot_token[slot] += 1
+        ctx.mod, ctx.slot, ctx.token, ctx.dev, ctx.xshape = mod, slot, mod._slot_token[slot], x.device, tuple(x.shape)
+        mod._trained = True
+        mod._pull_buffers()   # BatchNorm running statistics moved inside the engine: mirror them into the module's buffers
+        return out
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        mod = ctx.mod
+        if ctx.token != mod._slot_token[ctx.slot]:
+            raise RuntimeError("eegldm.PatchDiscriminator: backward through a forward pass that later forward() calls have replaced "
+                               "(the engine keeps two recorded passes per discriminator)")
+        want_dx = ctx.needs_input_grad[1]
+        want_p = any(ctx.needs_input_grad[2:])
+        dl = dlogits.contiguous().float()
+        dx = torch.empty(ctx.xshape, device=ctx.dev, dtype=torch.float32) if want_dx else None
+        with torch.cuda.device(ctx.dev):
+            _lib.check(_lib.lib().eegldm_disc_backward(mod._h, int(ctx.slot), C.c_void_p(dl.data_ptr()),
+                                                       C.c_void_p(dx.data_ptr()) if want_dx else None, int(want_p),
+                                                       C.c_void_p(_lib.current_stream_ptr(ctx.dev))))
+        if want_p:
+            grads = mod._export(1)
+            pg = tuple(grads[n].to(ctx.dev) for n, _ in mod.named_parameters())
+        else:
+            pg = tuple(None for _ in mod.parameters())
+        return (None, dx) + pg
+
+
 class PatchDiscriminator(EngineModule):
     def __init__(self, spatial_dims=1, num_channels=64, in_channels=1, out_channels=1, num_layers_d=3, kernel_size=4,
                  activation=("LEAKYRELU", {"negative_slope": 0.2}), norm="BATCH", bias=False, padding=1, dropout=0.0,
@@ -39,6 +83,7 @@ class PatchDiscriminator(EngineModule):
         _lib.check(L.eegldm_disc_create(C.byref(cfg), C.byref(h)))   # rejects kernel_size != 3 / padding != 1
         self._h = h
         self._trained = False
+        self._next_slot, self._slot_token = 0, [0, 0]
         self.set_math(math)
         g = torch.Generator().manual_seed(torch.initial_seed() & 0x7FFFFFFF)
         for i in range(L.eegldm_disc_num_params(h)):
@@ -95,10 +140,28 @@ class PatchDiscriminator(EngineModule):
         _lib.check(L.eegldm_disc_finalize(self._h))
 
     @torch.no_grad()
+    def _pull_buffers(self):
+        L = _lib.lib()
+        sd = self.state_dict(keep_vars=True)
+        for name, _ in self.named_buffers():
+            buf = torch.empty(tuple(sd[name].shape), dtype=torch.float32)
+            _lib.check(L.eegldm_disc_export(self._h, 0, name.encode(), C.cast(C.c_void_p(buf.data_ptr()), C.POINTER(C.c_float))))
+            sd[name].copy_(buf.to(sd[name].device).to(sd[name].dtype))
+        self._uploaded_key = self._weights_key()
+
     def forward(self, x):
         """-> list whose LAST element is the patch logits ``[B, 1, L_out]`` (the reference takes ``discriminator(x)[-1]``,
         train_autoencoderkl.py:213,226,228).  Upstream also returns every intermediate feature map; they are not
-        materialised here (the list has one element)."""
+        materialised here (the list has one element).  In training mode under autograd (the input or a parameter requires grad)
+        the call is differentiable -- the reference's own loop (train_autoencoderkl.py:213-234) runs unchanged; the fused
+        ``AutoencoderKL.train_step(discriminator=...)`` is the fast form of the same step."""
+        if self.training and torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            xin = check_cuda_f32(x, "x")
+            return [_DiscTrainFn.apply(self, xin, *self.parameters())]
+        return self._forward_nograd(x)
+
+    @torch.no_grad()
+    def _forward_nograd(self, x):
         x = check_cuda_f32(x, "x")
         B, Cin, Lx = x.shape
         L = _lib.lib()
