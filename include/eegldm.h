@@ -319,6 +319,13 @@ int eegldm_unet_train_step(eegldm_unet* h, const eegldm_sched_cfg* sched, const 
                            const int64_t* timesteps_dev, int B, int T, const eegldm_ldm_train_cfg* cfg, float* loss_host, void* stream);
 int eegldm_unet_train_export(eegldm_unet* h, int what, const char* name, float* host_out);
 int eegldm_unet_train_sync(eegldm_unet* h);
+/* The same denoiser across an AUTOGRAD boundary, for the reference's unchanged loop (training.py:420-443: `noise_pred =
+ * model(x=noisy_e, timesteps=timesteps)`; the loss in PyTorch; `scaler.scale(loss).backward()`; `scaler.step(optimizer)`):
+ * eegldm_unet_forward_train = UNetModel.forward in training mode (x_dev [B, in, T], timesteps_dev [B] fp32 on the device, out_dev
+ * [B, out, T]) with the pass recorded inside the handle; eegldm_unet_backward consumes it with d_out_dev = dL/d(output) and leaves the
+ * parameter gradients for eegldm_unet_train_export(h, 1, name, ...). */
+int eegldm_unet_forward_train(eegldm_unet* h, const float* x_dev, const float* timesteps_dev, float* out_dev, int B, int T, void* stream);
+int eegldm_unet_backward(eegldm_unet* h, const float* d_out_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Output tail of the sampling scripts: replaces, batched over all windows, what src/sample_trials.py:169-197 (and

@@ -124,6 +124,8 @@ SIGNATURES = {
     "eegldm_unet_train_step": (C.c_int, [_P, C.POINTER(SchedCfg), _P, _P, _P, C.c_int, C.c_int, C.POINTER(LdmTrainCfg), _FP, _P]),
     "eegldm_unet_train_export": (C.c_int, [_P, C.c_int, C.c_char_p, _FP]),
     "eegldm_unet_train_sync": (C.c_int, [_P]),
+    "eegldm_unet_forward_train": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, _P]),
+    "eegldm_unet_backward": (C.c_int, [_P, _P, _P]),
     "eegldm_sched_alphas_cumprod": (C.c_int, [C.POINTER(SchedCfg), _FP]),
     "eegldm_sched_ddim_tables": (C.c_int, [C.POINTER(SchedCfg), C.c_int, _I64P, _FP]),
     "eegldm_timestep_embedding": (C.c_int, [_FP, C.c_int, C.c_int, _FP]),

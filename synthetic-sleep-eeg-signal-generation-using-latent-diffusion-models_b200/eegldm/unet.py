@@ -19,6 +19,36 @@ def _zero_init(name: str) -> bool:
     return (".out_layers.3." in name) or (".proj_out." in name) or name.startswith("out.2.")
 
 
+class _UNetTrainFn(torch.autograd.Function):
+    """``UNetModel.forward`` across the autograd boundary (training.py:430): forward = ``eegldm_unet_forward_train`` (the pass stays
+    in the engine handle), backward = ``eegldm_unet_backward`` + one gradient per parameter (they are Function inputs so autograd
+    routes them to ``p.grad``).  The input latent gets no gradient (the reference computes it under ``no_grad``)."""
+
+    @staticmethod
+    def forward(ctx, mod, x, ts, *params):
+        B, _, T = x.shape
+        out = torch.empty((B, mod.out_channels, T), device=x.device, dtype=torch.float32)
+        with torch.cuda.device(x.device):
+            mod._sync_weights()
+            _lib.check(_lib.lib().eegldm_unet_forward_train(mod._h, C.c_void_p(x.data_ptr()), C.c_void_p(ts.data_ptr()), C.c_void_p(out.data_ptr()),
+                                                            int(B), int(T), C.c_void_p(_lib.current_stream_ptr(x.device))))
+        mod._pass_token = getattr(mod, "_pass_token", 0) + 1
+        ctx.mod, ctx.token, ctx.dev = mod, mod._pass_token, x.device
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        mod = ctx.mod
+        if ctx.token != mod._pass_token:
+            raise RuntimeError("eegldm.UNetModel: backward through a forward pass that a later forward() has replaced "
+                               "(the engine keeps one recorded pass per model)")
+        d = d_out.contiguous().float()
+        with torch.cuda.device(ctx.dev):
+            _lib.check(_lib.lib().eegldm_unet_backward(mod._h, C.c_void_p(d.data_ptr()), C.c_void_p(_lib.current_stream_ptr(ctx.dev))))
+        grads = mod._export(1)
+        return (None, None, None) + tuple(grads[n].to(ctx.dev) for n, _ in mod.named_parameters())
+
+
 class UNetModel(EngineModule):
     def __init__(self, image_size, in_channels, model_channels, out_channels, num_res_blocks, attention_resolutions,
                  dropout=0, channel_mult=(1, 2, 4, 8), conv_resample=True, num_classes=None, num_heads=1,
@@ -97,10 +127,26 @@ class UNetModel(EngineModule):
         _lib.load_state_dict_into(self._h, L.eegldm_unet_load, state_dict)
         _lib.check(L.eegldm_unet_finalize(self._h))
 
-    @torch.no_grad()
     def forward(self, x, timesteps=None, context=None, y=None, **kwargs):
+        """``UNetModel.forward`` (unet.py:512-563).  In training mode under autograd (grad mode on, a parameter requires grad) the call
+        is differentiable with respect to the parameters, so the reference's own loop runs unchanged (training.py:420-443);
+        ``train_step`` is the fused form of the same step."""
         assert y is None, "must specify y if and only if the model is class-conditional"   # unet.py:521-523
         assert timesteps is not None, "need to implement no-timestep usage"               # unet.py:524
+        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            x = check_cuda_f32(x, "x").detach()
+            if x.dim() != 3 or x.shape[1] != self.in_channels:
+                raise ValueError(f"x must be [B, {self.in_channels}, T], got {tuple(x.shape)}")
+            ts = torch.as_tensor(timesteps).reshape(-1).to(device=x.device, dtype=torch.float32)
+            if ts.numel() == 1:
+                ts = ts.expand(x.shape[0])
+            if ts.numel() != x.shape[0]:
+                raise ValueError("timesteps must have 1 or B entries")
+            return _UNetTrainFn.apply(self, x, ts.contiguous(), *self.parameters())
+        return self._forward_nograd(x, timesteps)
+
+    @torch.no_grad()
+    def _forward_nograd(self, x, timesteps):
         x = check_cuda_f32(x, "x")
         if x.dim() != 3 or x.shape[1] != self.in_channels:
             raise ValueError(f"x must be [B, {self.in_channels}, T], got {tuple(x.shape)}")

@@ -117,3 +117,97 @@ def test_reference_loop_body_verbatim(built_lib, cuda_device, nc, dover, B, L):
         assert bool(torch.isfinite(r2).all())
         mu_ref, _ = oa.encode(acfg, {k: v for k, v in gnew.items()}, x)
         torch.testing.assert_close(r2.cpu(), oa.decode(acfg, gnew, mu_ref), rtol=5e-3, atol=5e-3)
+
+
+@pytest.mark.parametrize("case", ["small_eps", "small_v_convresample"])
+def test_reference_ldm_loop_body_verbatim(built_lib, cuda_device, case):
+    """src/training/training.py:418-443 (train_epoch_ldm's loop body) unchanged: Stage1Wrapper over the drop-in autoencoder, the
+    drop-in scheduler and denoiser under autocast, GradScaler, torch.optim.Adam(lr 1e-4) -- against the oracle's fp32 step on the
+    same latents / noise / timesteps (GradScaler's loss scale cancels in scaler.step)."""
+    import eegldm
+    import torch.nn as nn
+    import torch.nn.functional as F
+    from collections import OrderedDict
+    from torch.cuda.amp import GradScaler, autocast
+    from oracle import ldm_train as ol, unet as ou
+    from oracle.schedulers import DDPMScheduler as ODDPM
+    from train_cases import TRAIN_CASES
+    over, B, T, pred, schedule, (b0, b1) = TRAIN_CASES[case]
+    ucfg = ou.full_cfg(**over)
+    usd = ou.make_unet_state_dict(ucfg, seed=0)
+    acfg = oa.full_cfg(num_channels=[4, 4], attention_levels=[False, False], latent_channels=ucfg["in_channels"])
+    asd = oa.make_aekl_state_dict(acfg, 42)
+    device = cuda_device
+
+    class Stage1Wrapper(nn.Module):   # src/training/training.py:15-26
+        def __init__(self, model: nn.Module) -> None:
+            super().__init__()
+            self.model = model
+
+        def forward(self, x: torch.Tensor) -> torch.Tensor:
+            z_mu, z_sigma = self.model.encode(x)
+            z = self.model.sampling(z_mu, z_sigma)
+            return z
+
+    aekl = eegldm.AutoencoderKL(**acfg)
+    aekl.load_state_dict(asd)
+    stage1 = Stage1Wrapper(aekl.to(device).eval())
+    model = eegldm.UNetModel(**ucfg)
+    model.load_state_dict(usd)
+    model = model.to(device)
+    scheduler = eegldm.DDPMScheduler(num_train_timesteps=1000, beta_schedule=schedule, beta_start=b0, beta_end=b1, prediction_type=pred)
+    optimizer = torch.optim.Adam(model.parameters(), lr=1e-4)
+    scaler = GradScaler(init_scale=1024.0)
+    scale_factor = 0.7
+    x = {"eeg": torch.rand(B, 1, 2 * T, generator=torch.Generator().manual_seed(3))}
+
+    # the random draws of the loop body, reproduced for the oracle: timesteps, the sampling noise of stage1, the diffusion noise
+    torch.manual_seed(77)
+    torch.cuda.manual_seed(77)
+    t_ref = torch.randint(0, scheduler.num_train_timesteps, (B,), device=device).long()
+    with torch.no_grad():
+        e_ref = stage1(x["eeg"].to(device)) * scale_factor
+    n_ref = torch.randn_like(e_ref)
+    osched = ODDPM(1000, b0, b1, schedule, pred)
+    loss_o, grads_o, new_o = ol.ldm_train_step(ucfg, usd, e_ref.cpu(), n_ref.cpu(), t_ref.cpu(), osched, lr=1e-4)
+    torch.manual_seed(77)
+    torch.cuda.manual_seed(77)
+
+    # ---- src/training/training.py:415-443, verbatim ---------------------------------------------------------------------------
+    model.train()
+
+    images = x['eeg'].to(device)
+    timesteps = torch.randint(0, scheduler.num_train_timesteps, (images.shape[0],), device=device).long()
+
+    optimizer.zero_grad(set_to_none=True)
+    with autocast(enabled=True):
+        with torch.no_grad():
+            ##### Replace
+            e = stage1(images) * scale_factor
+
+        noise = torch.randn_like(e).to(device)
+        noisy_e = scheduler.add_noise(original_samples=e, noise=noise, timesteps=timesteps)
+        noise_pred = model(x=noisy_e, timesteps=timesteps)
+
+        if scheduler.prediction_type == "v_prediction":
+            # Use v-prediction parameterization
+            target = scheduler.get_velocity(e, noise, timesteps)
+        elif scheduler.prediction_type == "epsilon":
+            target = noise
+        loss = F.mse_loss(noise_pred.float(), target.float())
+
+    losses = OrderedDict(loss=loss)
+
+    scaler.scale(losses["loss"]).backward()
+    scaler.step(optimizer)
+    scaler.update()
+    # ---------------------------------------------------------------------------------------------------------------------------
+
+    assert torch.equal(timesteps, t_ref) and torch.equal(noise, n_ref)
+    assert abs(loss.item() - loss_o) <= 1e-4 * abs(loss_o)
+    gmax = max(float(v.abs().max()) for v in grads_o.values())
+    for k, p in model.named_parameters():   # p.grad was unscaled in place by scaler.step
+        r = grads_o[k]
+        torch.testing.assert_close(p.grad.cpu(), r, rtol=2e-3, atol=1e-4 * float(r.abs().max()) + 1e-5 * gmax, msg=lambda m: f"{k}: {m}")
+        solid = r.abs() > 1e-4 * gmax
+        torch.testing.assert_close(p.detach().cpu()[solid], new_o[k][solid], rtol=0, atol=2e-6, msg=lambda m: f"{k} (after Adam): {m}")
