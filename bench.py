@@ -632,7 +632,7 @@ def main():
     ap.add_argument("--batch", type=int, default=1024, help="windows per GPU per step (config 3: 1024)")
     ap.add_argument("--math", default=os.environ.get("EEGLDM_BENCH_MATH", "f16x3"), help="fp32 | f16x3 (both parity-green)")
     ap.add_argument("--lanes", type=int, default=1, help="independent batch halves inside the denoise-step graph (1 or 2)")
-    ap.add_argument("--fuse", type=int, default=13, help="eegldm_set_conv_tuning fuse_epilogues bit mask (1 GroupNorm statistics, "
+    ap.add_argument("--fuse", type=int, default=15, help="eegldm_set_conv_tuning fuse_epilogues bit mask (1 GroupNorm statistics, "
                     "2 qkv operand images, 4 in-kernel activation producer, 8 attention -> proj_out operand image, 16 attention splits fp32 q,k,v itself)")
     ap.add_argument("--ref-batch", type=int, default=8, help="windows per CPU-baseline step (bounded sample)")
     ap.add_argument("--profile-batch", type=int, default=1024)

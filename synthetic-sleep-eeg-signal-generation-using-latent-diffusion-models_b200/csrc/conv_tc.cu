@@ -299,6 +299,79 @@ __global__ void __launch_bounds__(conv_tc_threads(DIRECT, EPI8), 1) conv_tc_kern
             const int n_tile = w % n_ntiles, m_tile = (w / n_ntiles) * CL + crank;
             const int as = lt % NSETS, use = lt / NSETS;
             const int co0 = n_tile * BN + eh * HC;
+            if (X3 && p.qkv16) {
+                // qkv conv of an AttentionBlock (unet.py:158): the output's only consumer is attn_tc.cu, so q, k, v go straight into
+                // its fp16 hi/lo operand images (layout: qkv_split_kernel) -- no fp32 tensor, no qkv_split pass.  A TMEM lane is one
+                // position and 16 consecutive columns are two 8-channel image items of 16 bytes each (x hi, lo): no shared-memory
+                // transpose.  The four lanes (l, l+8, l+16, l+24) of one segment hold consecutive positions = 64 contiguous bytes
+                // of a core matrix; one lane permutation (16 shuffles) makes them ADJACENT lanes, so that each quarter-warp phase
+                // of a 128-bit store covers two 64-byte runs instead of eight 16-byte pieces of eight lines (measured: 5.8 k
+                // cycles of stores per tile in the unpermuted form vs 3.9 k for everything else, tools/conv_timeline.py).
+                const int sg = lane >> 2, pos = ew * 4 + (lane & 3);          // (segment, position) this lane STORES
+                const int src_lane = ((lane & 3) << 3) | (lane >> 2);          // the lane whose TMEM row that is
+                const int g = m_tile * 8 + sg;
+                const bool valid = g < p.nsegs16;
+                const int b = valid ? g / spt : 0, t = (g % spt) * 16 + pos;
+                const int ch = p.qkv_ch, T = p.Tout;
+                const int cq = co0 / (3 * ch), rem = co0 - cq * 3 * ch, which = rem / ch, c0 = rem - which * ch;   // head, q|k|v, channel
+                const size_t half = which < 2 ? (size_t)T * 64 : 8192;
+                uint8_t* base = p.qkv16 + (((size_t)b * p.qkv_H + cq) * 3 + which) * ((size_t)4 * ch * T) +
+                                (which < 2 ? (size_t)(t >> 3) * 512 + (t & 7) * 16
+                                           : (size_t)(t >> 5) * 2 * half + ((t & 31) >> 3) * 2048 + (t & 7) * 16);
+                const float* bias_p = p.bias && !(p.debug & 512) ? p.bias + co0 : nullptr;
+                const bool do_store = valid && !(p.debug & 256);   // (debug bits 256 / 512: timing experiments, tools/conv_timeline.py)
+                TL_WAIT(tl_a, mbar_wait(barAccFull + 8 * as, use & 1));
+                tc_fence_after();
+                const long long tl_e0 = tl ? clock64() : 0;
+                const uint32_t acc_addr = tmem + ((uint32_t)(ew * 32) << 16) + as * ACC_COLS + eh * HC;
+                uint32_t vn[16], c2n[16];
+                tmem_ld16_async(acc_addr, vn);
+                tmem_ld16_async(acc_addr + (uint32_t)BN, c2n);
+                bool bad = false;
+#pragma unroll 1
+                for (int cb = 0; cb < HC; cb += 16) {
+                    float4 bi[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) bi[j] = bias_p ? ldg4(bias_p + cb + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    tmem_ld_wait();
+                    float f[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) f[i] = fmaf(__uint_as_float(c2n[i]), 1.0f / LO_SCALE, __uint_as_float(vn[i]));
+                    if (cb + 16 < HC) {
+                        tmem_ld16_async(acc_addr + (uint32_t)(cb + 16), vn);
+                        tmem_ld16_async(acc_addr + (uint32_t)(BN + cb + 16), c2n);
+                    } else {
+                        tc_fence_before();
+                        mbar_arrive(barAccEmpty + 8 * as);
+                    }
+                    const int c = c0 + cb;
+                    uint8_t* dst = base + (which < 2 ? (size_t)(c >> 5) * 2 * half + ((c & 31) >> 3) * 128
+                                                     : (size_t)(c >> 7) * (T >> 5) * 2 * half + ((c & 127) >> 3) * 128);
+                    uint4 pc[4];   // hi item 0, lo item 0, hi item 1, lo item 1 of this lane's TMEM row
+#pragma unroll
+                    for (int it = 0; it < 2; ++it) {
+                        const float v8[8] = {f[8 * it] + bi[2 * it].x,     f[8 * it + 1] + bi[2 * it].y,     f[8 * it + 2] + bi[2 * it].z,
+                                             f[8 * it + 3] + bi[2 * it].w, f[8 * it + 4] + bi[2 * it + 1].x, f[8 * it + 5] + bi[2 * it + 1].y,
+                                             f[8 * it + 6] + bi[2 * it + 1].z, f[8 * it + 7] + bi[2 * it + 1].w};
+                        bad |= out_of_f16_range(v8);
+                        split8_f16(v8, pc[2 * it], pc[2 * it + 1]);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        pc[j].x = __shfl_sync(0xffffffffu, pc[j].x, src_lane); pc[j].y = __shfl_sync(0xffffffffu, pc[j].y, src_lane);
+                        pc[j].z = __shfl_sync(0xffffffffu, pc[j].z, src_lane); pc[j].w = __shfl_sync(0xffffffffu, pc[j].w, src_lane);
+                    }
+                    if (do_store) {
+                        *reinterpret_cast<uint4*>(dst) = pc[0];
+                        *reinterpret_cast<uint4*>(dst + half) = pc[1];
+                        *reinterpret_cast<uint4*>(dst + 128) = pc[2];
+                        *reinterpret_cast<uint4*>(dst + 128 + half) = pc[3];
+                    }
+                }
+                if (bad && p.range_flag) atomicOr(p.range_flag, 1);
+                if (tl) tl_b += clock64() - tl_e0;
+                continue;
+            }
             const int g = m_tile * 8 + seg;
             const int rb = g < p.nsegs16 ? g / spt : -1;             // sample (< 0: segment past the batch)
             const int rt = (g % spt) * 16 + ew * 4;                  // first of this thread's 4 positions
@@ -1054,9 +1127,9 @@ cudaError_t launch_conv_tc(const TcConvParams& p_in, bool x3, cudaStream_t st) {
     }
     if (p.bn != 128 && p.bn != 256) return cudaErrorInvalidValue;
     cudaError_t e;
-    // two-warpgroup epilogue (EPI8): every single-CTA-MMA launch except the ones whose epilogue writes attention operand images
-    // or 32-channel GroupNorm groups (one-warpgroup epilogue only); cluster sizes 1 and 2
-    const bool epi8 = g_conv_tc_epi8 && !g_conv_tc_pair && !p.qkv16 && !(p.gn_partial && p.gn_cpg == 32) &&
+    // two-warpgroup epilogue (EPI8): every single-CTA-MMA launch except the ones whose epilogue emits 32-channel GroupNorm groups
+    // or bf16-mode attention operand images (one-warpgroup epilogue only); cluster sizes 1 and 2
+    const bool epi8 = g_conv_tc_epi8 && !g_conv_tc_pair && !(p.qkv16 && !x3) && !(p.gn_partial && p.gn_cpg == 32) &&
                       (p.direct || g_conv_tc_cluster == 2 || g_conv_tc_cluster == 1);
 #define EEGLDM_TC8(X3, BN)                                                                               \
     (p.direct ? (g_conv_tc_cluster == 1 ? launch_conv_tc_t<X3, BN, 1, false, true, true>(p, num_sms, st)   \

@@ -371,7 +371,7 @@ struct eegldm_unet {
 
 namespace {
 
-bool g_conv_qkv_fused = false; // the qkv conv writes attention operand images directly (f16x3; eegldm_set_conv_tuning): measured no faster
+bool g_conv_qkv_fused = true;  // the qkv conv writes attention operand images directly (f16x3; eegldm_set_conv_tuning bit 1): no qkv_split pass
 bool g_attn_direct = false;    // the tcgen05 attention splits fp32 q, k, v itself (eegldm_set_conv_tuning bit 4): measured no faster
 bool g_attn_u_fused = true;    // the tcgen05 attention writes proj_out's operand image instead of fp32 (eegldm_set_conv_tuning bit 3)
 bool g_conv_direct = true;     // tensor-pipe convs produce their activation operands in-kernel (no act_split pre-pass)
@@ -1969,12 +1969,17 @@ static int bench_conv_impl(int B, int T, int Cin, int Cout, int k, int with_res,
     TcConvParams q{};
     q.nseg = 1; q.Cout = Cout; q.Tout = T; q.nsegs16 = (int)((long long)B * T / 16);
     q.bn = conv_tc_bn(Cout, Cin / TC_BK * k);
+    // with_res == 2: the qkv conv of an AttentionBlock (one head of Cout/3 channels) writing attention operand images (pre-pass form)
+    const bool qkv_mode = with_res == 2 && x3 && Cout % 3 == 0 && attn_tc_eligible(T, Cout / 3);
+    if (with_res == 2 && !qkv_mode) return fail(EEGLDM_ERR_SHAPE, "qkv bench mode needs f16x3 and an attention-eligible shape");
     float *x = nullptr, *out = nullptr, *res = nullptr;
     uint8_t* U = nullptr;
     const size_t nx = (size_t)B * T * Cin, no = (size_t)B * T * Cout;
     cudaError_t ce = cudaMalloc((void**)&x, nx * 4);
     if (ce == cudaSuccess) ce = cudaMalloc((void**)&out, no * 4);
-    if (ce == cudaSuccess && with_res) ce = cudaMalloc((void**)&res, no * 4);
+    uint8_t* q16 = nullptr;
+    if (ce == cudaSuccess && with_res == 1) ce = cudaMalloc((void**)&res, no * 4);
+    if (ce == cudaSuccess && qkv_mode) ce = cudaMalloc((void**)&q16, attn_qkv16_bytes(B, T, 1, Cout / 3));
     if (ce == cudaSuccess) ce = cudaMalloc((void**)&U, act_split_bytes(q.nsegs16, Cin));
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (ce == cudaSuccess) {
@@ -1985,7 +1990,8 @@ static int bench_conv_impl(int B, int T, int Cin, int Cout, int k, int with_res,
     }
     q.seg[0] = TcSeg{U, reinterpret_cast<const uint8_t*>(wp.at(o_t)), k, Cin / TC_BK};
     float* ss = nullptr;
-    if (g_conv_direct) {   // fused producer with a GroupNorm affine + SiLU prologue (the ResBlock conv1 / conv2 shape)
+    if (qkv_mode) { q.qkv16 = q16; q.qkv_H = 1; q.qkv_ch = Cout / 3; }
+    if (g_conv_direct && !qkv_mode) {   // fused producer with a GroupNorm affine + SiLU prologue (the ResBlock conv1 / conv2 shape)
         if (ce == cudaSuccess) ce = cudaMalloc((void**)&ss, (size_t)B * Cin * 2 * 4);
         if (ce == cudaSuccess) { bench_fill_kernel<<<64, 256, 0, st>>>(ss, (size_t)B * Cin * 2, 3u); ce = cudaGetLastError(); }
         q.direct = 1;
@@ -2027,7 +2033,7 @@ static int bench_conv_impl(int B, int T, int Cin, int Cout, int k, int with_res,
         timeline_out[TC_TL_N - 1] = n;
         cudaFree(tl);
     }
-    cudaFree(x); cudaFree(out); cudaFree(res); cudaFree(U); cudaFree(ss);
+    cudaFree(x); cudaFree(out); cudaFree(res); cudaFree(U); cudaFree(ss); cudaFree(q16);
     if (ce != cudaSuccess) return cuda_fail(ce, "conv bench");
     return EEGLDM_OK;
 }

@@ -13,9 +13,10 @@ from eegldm import _lib
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=1024)
 ap.add_argument("--reps", type=int, default=5)
-ap.add_argument("--fuse", type=int, default=13)
+ap.add_argument("--fuse", type=int, default=15)
 ap.add_argument("--bn256", type=int, default=1)
 ap.add_argument("--cluster", type=int, default=2)
+ap.add_argument("--only", type=int, default=-1, help="run one row of SHAPES")
 ap.add_argument("--debug", type=int, default=0, help="conv debug bits (64: one cluster alone on the device)")
 a = ap.parse_args()
 torch.cuda.set_device(0)
@@ -25,10 +26,10 @@ _lib.check(L.eegldm_set_conv_cluster(a.cluster))
 _lib.check(L.eegldm_set_conv_tuning(0, a.bn256, a.fuse))
 # (T, Cin, Cout, k, residual): the UNet's layer shapes (config_ldm.yaml)
 SHAPES = [(768, 128, 128, 3, 0), (768, 128, 128, 3, 1), (768, 256, 128, 3, 0), (384, 256, 256, 3, 1), (384, 768, 256, 3, 0),
-          (192, 512, 512, 3, 0), (192, 512, 512, 3, 1), (192, 1024, 512, 3, 0), (192, 512, 1536, 1, 0), (192, 512, 512, 1, 1)]
+          (192, 512, 512, 3, 0), (192, 512, 512, 3, 1), (192, 1024, 512, 3, 0), (192, 512, 1536, 1, 0), (192, 512, 1536, 1, 2), (192, 512, 512, 1, 1)]
 hdr = ["ms", "TF", "tiles", "total", "mma:acc", "mma:A", "mma:B", "mma:issue", "epi:wait", "epi:busy", "prod:wait", "prod:busy", "load:B"]
 print(f"{'shape':26}" + "".join(f"{h:>10}" for h in hdr))
-for (T, ci, co, k, res) in SHAPES:
+for (T, ci, co, k, res) in (SHAPES if a.only < 0 else [SHAPES[a.only]]):
     fl = 2.0 * ci * co * k * T * a.batch
     m = C.c_float()
     tl = (C.c_double * 16)()

@@ -11,7 +11,7 @@ from eegldm import _lib
 ap = argparse.ArgumentParser()
 ap.add_argument("shape", type=int, nargs=5)
 ap.add_argument("--batch", type=int, default=1024)
-ap.add_argument("--fuse", type=int, default=13)
+ap.add_argument("--fuse", type=int, default=15)
 ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--debug", type=int, default=0)
 a = ap.parse_args()
