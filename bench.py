@@ -419,7 +419,7 @@ def run_ours(args):
 
     # seeded random-init weights of the reference's architecture (no checkpoint ships); product-side helper, no oracle/ here
     _lib.check(eegldm.lib().eegldm_set_sample_lanes(args.lanes))
-    _lib.check(eegldm.lib().eegldm_set_conv_tuning(0, 1, args.fuse))
+    _lib.check(eegldm.lib().eegldm_set_conv_tuning(args.pair, 1, args.fuse))
     unet = eegldm.UNetModel(**synthetic.LDM_UNET_CFG, math=args.math)
     usd = synthetic.seeded_state_dict(unet, 0)
     unet.load_state_dict(usd)
@@ -634,6 +634,7 @@ def main():
     ap.add_argument("--lanes", type=int, default=1, help="independent batch halves inside the denoise-step graph (1 or 2)")
     ap.add_argument("--fuse", type=int, default=15, help="eegldm_set_conv_tuning fuse_epilogues bit mask (1 GroupNorm statistics, "
                     "2 qkv operand images, 4 in-kernel activation producer, 8 attention -> proj_out operand image, 16 attention splits fp32 q,k,v itself)")
+    ap.add_argument("--pair", type=int, default=1, help="eegldm_set_conv_tuning CTA-pair mask (bit 0: 256-wide conv launches, bit 1: 128-wide)")
     ap.add_argument("--ref-batch", type=int, default=8, help="windows per CPU-baseline step (bounded sample)")
     ap.add_argument("--profile-batch", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -184,9 +184,13 @@ __global__ void __launch_bounds__(SPLIT_THREADS) act_split_kernel(const ActSplit
 // tile and only ITS HALF of the weight columns (BN/2), the leader (cluster rank 0) issues every MMA for both, and each
 // CTA drains its own 128 TMEM lanes.  Per MMA an SM then reads 4 KB of A + BN/2 x 32 B of B instead of BN x 32 B, and
 // stages half the weight bytes: the shared-memory operand traffic that bounds the single-CTA shape (profiles/r01_summary.md)
-// drops below the tensor pipe's time.  Synchronisation: loads complete on each CTA's own "full" mbarriers; warp 5 of the
-// peer relays them to the leader's (count 2 = own expect_tx arrive + relay); the leader's tcgen05.commit multicasts the
-// "empty" / "accumulator full" arrivals to both CTAs; both CTAs' epilogue threads arrive on the leader's "accumulator empty".
+// drops below the tensor pipe's time, and N = 128 (two TMEM accumulator sets: overlapped epilogue) costs no more operand
+// bandwidth than the single-CTA N = 256 shape.  Synchronisation without a relay hop: every "full" barrier lives in the LEADER.
+// Both CTAs load with cp.async.bulk.tensor.cta_group::2 (tensor maps over the weight / U images), whose complete_tx reaches the
+// leader's barrier from either CTA (only the leader arrives, with the pair's byte count); the fused producers of both CTAs
+// arrive on the leader's barrier through the cluster (one elected lane per warp after __syncwarp); the leader's tcgen05.commit
+// multicasts the "empty" / "accumulator full" arrivals to both CTAs; both CTAs' epilogue threads arrive on the leader's
+// "accumulator empty".  (Round 1's form relayed the peer's own full barriers through a warp: 25-45 % slower.)
 //
 // DIRECT: no activation pre-pass.  Six producer warps (the act_split thread mapping: 192 threads x 3 sixteen-byte items per
 // k-step) read the fp32 source rows themselves, apply the GroupNorm affine / SiLU / nearest-x2, split to fp16 hi/lo and
@@ -211,10 +215,9 @@ __global__ void __launch_bounds__(SPLIT_THREADS) act_split_kernel(const ActSplit
 // x 4 channels per chunk.
 constexpr int conv_tc_threads(bool direct, bool epi8) { return direct ? (epi8 ? 512 : 384) : (epi8 ? 320 : NUM_THREADS); }
 template <bool X3, int BN, int CL, bool PAIR, bool DIRECT, bool EPI8 = false>
-__global__ void __launch_bounds__(conv_tc_threads(DIRECT, EPI8), 1) conv_tc_kernel(const TcConvParams p) {
+__global__ void __launch_bounds__(conv_tc_threads(DIRECT, EPI8), 1) conv_tc_kernel(const __grid_constant__ TcConvParams p) {
     static_assert(!PAIR || CL == 2, "a CTA pair is a cluster of 2");
-    static_assert(!(PAIR && DIRECT), "the fused producer is implemented for single-CTA MMAs");
-    static_assert(!(PAIR && EPI8), "the two-warpgroup epilogue is implemented for single-CTA MMAs");
+    static_assert(!PAIR || EPI8, "the CTA-pair form uses the two-warpgroup epilogue");
     constexpr int NEPI = EPI8 ? 8 : 4;               // epilogue warps 0 .. NEPI-1
     constexpr int NPROD = DIRECT ? 6 : 0;            // producer warps NEPI .. NEPI+NPROD-1
     constexpr int W_LOAD = NEPI + NPROD, W_MMA = NEPI + 1 + NPROD;
@@ -224,13 +227,13 @@ __global__ void __launch_bounds__(conv_tc_threads(DIRECT, EPI8), 1) conv_tc_kern
     constexpr bool ALT = PAIR || DIRECT;   // ring plan: 5 activation stages + 96 KB of weight stages
     constexpr int NA = ring_na(ALT), BAR_OFF = bar_off(ALT), STAGING_OFF = BAR_OFF + 512;
     constexpr int NB = ring_b_bytes(ALT) / B_STAGE;
-    static_assert(NB <= 16 && NA <= 6, "barrier area sized for at most 6 + 16 stages");
+    static_assert(8 * (3 * NA + 2 * NB + 4) <= 448, "barrier area: 3 NA + 2 NB + 4 mbarriers in front of the TMEM slot");
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t sbase = smem_u32(smem);
     const uint32_t sA = sbase, sB = sbase + NA * A_STAGE;
     const uint32_t bars = sbase + BAR_OFF;             // 8-byte mbarriers
     const uint32_t barAfull = bars, barAempty = bars + 8 * NA, barBfull = bars + 16 * NA, barBempty = barBfull + 8 * NB,
-                   barAccFull = barBempty + 8 * NB, barAccEmpty = barAccFull + 16;
+                   barAccFull = barBempty + 8 * NB, barAccEmpty = barAccFull + 16, barApeer = barAccEmpty + 16;   // barApeer: pair + fused producer
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + BAR_OFF + 448);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -246,10 +249,11 @@ __global__ void __launch_bounds__(conv_tc_threads(DIRECT, EPI8), 1) conv_tc_kern
 
     const bool leader = !PAIR || crank == 0;
     if (tid == 0) {
-        const uint32_t nfull = PAIR && leader ? 2 : 1;   // pair leader: own expect_tx arrive + the peer's relay
-        for (int i = 0; i < NA; ++i) { mbar_init(barAfull + 8 * i, DIRECT ? 32 * NPROD : nfull); mbar_init(barAempty + 8 * i, 1); }
-        for (int i = 0; i < NB; ++i) { mbar_init(barBfull + 8 * i, nfull); mbar_init(barBempty + 8 * i, PAIR ? 1 : CL); }
-        for (int i = 0; i < 2; ++i) { mbar_init(barAccFull + 8 * i, 1); mbar_init(barAccEmpty + 8 * i, PAIR ? 256 : 32 * NEPI); }
+        // pair: the "full" barriers of the async loads that count are the leader's (its one arrive.expect_tx for the pair's bytes);
+        // fused producers arrive on their own CTA's barAfull, the peer's idle issuer warp forwards that to the leader's barApeer
+        for (int i = 0; i < NA; ++i) { mbar_init(barAfull + 8 * i, DIRECT ? 32 * NPROD : 1); mbar_init(barAempty + 8 * i, 1); mbar_init(barApeer + 8 * i, 1); }
+        for (int i = 0; i < NB; ++i) { mbar_init(barBfull + 8 * i, 1); mbar_init(barBempty + 8 * i, PAIR ? 1 : CL); }
+        for (int i = 0; i < 2; ++i) { mbar_init(barAccFull + 8 * i, 1); mbar_init(barAccEmpty + 8 * i, (PAIR ? 2 : 1) * 32 * NEPI); }
         fence_mbar_init();
     }
     constexpr uint32_t ACC_COLS = X3 ? 2 * BN : BN;    // X3: accumulator 0 = hi*hi, accumulator 1 = cross terms * 2^11
@@ -342,7 +346,8 @@ __global__ void __launch_bounds__(conv_tc_threads(DIRECT, EPI8), 1) conv_tc_kern
                         tmem_ld16_async(acc_addr + (uint32_t)(BN + cb + 16), c2n);
                     } else {
                         tc_fence_before();
-                        mbar_arrive(barAccEmpty + 8 * as);
+                        if (PAIR) mbar_arrive_cluster(barAccEmpty + 8 * as, 0);
+                        else mbar_arrive(barAccEmpty + 8 * as);
                     }
                     const int c = c0 + cb;
                     uint8_t* dst = base + (which < 2 ? (size_t)(c >> 5) * 2 * half + ((c & 31) >> 3) * 128
@@ -451,7 +456,10 @@ __global__ void __launch_bounds__(conv_tc_threads(DIRECT, EPI8), 1) conv_tc_kern
                     if (X3) tmem_ld16_async(acc_addr + (uint32_t)(BN + cb + 16), c2n);
                 } else {
                     tc_fence_before();
-                    mbar_arrive(barAccEmpty + 8 * as);   // every TMEM read of this thread has completed: the set may be overwritten
+                    // every TMEM read of this thread has completed: the set may be overwritten (pair: the leader's MMA warp owns both
+                    // CTAs' accumulators)
+                    if (PAIR) mbar_arrive_cluster(barAccEmpty + 8 * as, 0);
+                    else mbar_arrive(barAccEmpty + 8 * as);
                 }
                 __syncwarp();
                 float4 O[4];
@@ -850,7 +858,7 @@ __global__ void __launch_bounds__(conv_tc_threads(DIRECT, EPI8), 1) conv_tc_kern
                 *reinterpret_cast<uint4*>(img + j * 6 * A_SBO) = hi;
             }
             fence_proxy_async_smem();                  // generic-proxy stores -> visible to the tensor core's async proxy
-            mbar_arrive(barAfull + 8 * sa);
+            mbar_arrive(barAfull + 8 * sa);            // (pair: the peer's stage is forwarded to the leader by its issuer warp)
             ++ia;
         }
         if (X3 && bad && p.range_flag) atomicOr(p.range_flag, 1);
@@ -871,8 +879,12 @@ __global__ void __launch_bounds__(conv_tc_threads(DIRECT, EPI8), 1) conv_tc_kern
                     if (!DIRECT) {   // DIRECT: the producer warps fill the activation ring
                         mbar_wait(barAempty + 8 * sa, ((ia / NA) & 1) ^ 1);
                         if (elect_one()) {
-                            if (p.debug & 1) mbar_arrive(barAfull + 8 * sa);   // timing experiment: no operand traffic
-                            else {
+                            if (p.debug & 1) { if (leader) mbar_arrive(barAfull + 8 * sa); }   // timing experiment: no operand traffic
+                            else if (PAIR) {   // U image as rows of 512 B: one stage = 36 (hi + lo) or 18 rows
+                                if (leader) mbar_arrive_expect_tx(barAfull + 8 * sa, 2 * a_bytes);
+                                tma_load_2d_pair(sA + sa * A_STAGE, &p.tmap_u[first ? 0 : 1], 0, (int)(((size_t)m_tile * sg.nks + kl) * (A_STAGE / 512)),
+                                                 barAfull + 8 * sa);
+                            } else {
                                 mbar_arrive_expect_tx(barAfull + 8 * sa, a_bytes);
                                 bulk_copy_g2s(sA + sa * A_STAGE, sg.U + ((size_t)m_tile * sg.nks + kl) * A_STAGE, a_bytes, barAfull + 8 * sa);
                             }
@@ -886,15 +898,20 @@ __global__ void __launch_bounds__(conv_tc_threads(DIRECT, EPI8), 1) conv_tc_kern
                         const int sb = ib % NB;
                         TL_WAIT(tl_a, mbar_wait(barBempty + 8 * sb, ((ib / NB) & 1) ^ 1));   // all consumers of this stage are done
                         if (elect_one()) {
-                          if (p.debug & 1) mbar_arrive(barBfull + 8 * sb);
-                          else {
+                          if (p.debug & 1) { if (leader) mbar_arrive(barBfull + 8 * sb); }
+                          else if (PAIR) {
+                            // this CTA's half of the tile's columns: rows of 8 columns (512 B) of the weight image
+                            // [k-step][tap][hi|lo][Cout/8], box = BNL/8 rows; the leader expects both CTAs' bytes
+                            const uint32_t dst = sB + sb * B_STAGE, bar = barBfull + 8 * sb;
+                            if (leader) mbar_arrive_expect_tx(bar, 2 * b_bytes);
+                            const int row = ((kl * sg.taps + tap) * 2) * (p.Cout >> 3) + ((n_tile * BN + crank * BNL) >> 3);
+                            tma_load_2d_pair(dst, &p.tmap_w[first ? 0 : 1], 0, row, bar);
+                            if (X3) tma_load_2d_pair(dst + B_HALF, &p.tmap_w[first ? 0 : 1], 0, row + (p.Cout >> 3), bar);
+                          } else {
                             mbar_arrive_expect_tx(barBfull + 8 * sb, b_bytes);
                             const uint8_t* hi = wsrc + (size_t)tap * 2 * whalf;
                             const uint32_t dst = sB + sb * B_STAGE, bar = barBfull + 8 * sb;
-                            if (PAIR) {            // this CTA's half of the columns only
-                                bulk_copy_g2s(dst, hi + crank * B_HALF, B_HALF, bar);
-                                if (X3) bulk_copy_g2s(dst + B_HALF, hi + whalf + crank * B_HALF, B_HALF, bar);
-                            } else if (CL > 1) {   // fetch 1/CL of the stage, deliver it to every CTA of the cluster
+                            if (CL > 1) {   // fetch 1/CL of the stage, deliver it to every CTA of the cluster
                                 const uint32_t part = B_HALF / CL, off = crank * part;
                                 bulk_copy_g2s_multicast(dst + off, hi + off, part, bar, CMASK);
                                 if (X3) bulk_copy_g2s_multicast(dst + B_HALF + off, hi + whalf + off, part, bar, CMASK);
@@ -911,22 +928,19 @@ __global__ void __launch_bounds__(conv_tc_threads(DIRECT, EPI8), 1) conv_tc_kern
             if (tl && lane == 0) tlo[TC_TL_LOAD_WAIT_B] = tl_a;
         }
     } else if (PAIR && !leader) {
-        // ================================================================ pair peer: relay "stage landed" to the leader's barriers
-        int ia = 0, ib = 0;
-        for (int w = cid; w < nwork; w += ncl) {
-            for (int ks = 0; ks < nks; ++ks, ++ia) {
-                const int sa = ia % NA;
-                const int taps = ks < nks0 ? p.seg[0].taps : p.seg[1].taps;
-                mbar_wait(barAfull + 8 * sa, (ia / NA) & 1);
-                if (elect_one()) mbar_arrive_cluster(barAfull + 8 * sa, 0);
-                __syncwarp();
-                for (int tap = 0; tap < taps; ++tap, ++ib) {
-                    const int sb = ib % NB;
-                    mbar_wait(barBfull + 8 * sb, (ib / NB) & 1);
-                    if (elect_one()) mbar_arrive_cluster(barBfull + 8 * sb, 0);
+        // ================================================================ pair peer: the leader issues the MMAs of both CTAs
+        // Fused producer: forward "this CTA's activation stage is written" to the leader.  A remote arrive stalls the arriving warp
+        // for the cluster round trip (measured: +330 cycles per k-step when the producer warps did it themselves), this warp has
+        // nothing else to do; the five-stage activation ring hides the extra hop.
+        if (DIRECT) {
+            int ia = 0;
+            for (int w = cid; w < nwork; w += ncl)
+                for (int ks = 0; ks < nks; ++ks, ++ia) {
+                    const int sa = ia % NA;
+                    mbar_wait(barAfull + 8 * sa, (ia / NA) & 1);
+                    if (elect_one()) mbar_arrive_cluster(barApeer + 8 * sa, 0);
                     __syncwarp();
                 }
-            }
         }
     } else {
         // ================================================================ MMA issuer (whole warp runs the loop, one elected lane issues)
@@ -935,8 +949,7 @@ __global__ void __launch_bounds__(conv_tc_threads(DIRECT, EPI8), 1) conv_tc_kern
             for (int w = cid; w < nwork; w += ncl, ++lt) {
                 const int as = lt % NSETS, use = lt / NSETS;
                 const uint32_t d0 = tmem + as * ACC_COLS, d1 = d0 + BN;
-                if (PAIR) mbar_wait_cluster(barAccEmpty + 8 * as, (use & 1) ^ 1);   // both CTAs' epilogues have drained this set
-                else TL_WAIT(tl_a, mbar_wait(barAccEmpty + 8 * as, (use & 1) ^ 1));
+                TL_WAIT(tl_a, mbar_wait(barAccEmpty + 8 * as, (use & 1) ^ 1));   // (pair: both CTAs' epilogues have drained this set)
                 tc_fence_after();
                 uint32_t accum = 0, accum2 = 0;
                 const bool skip_mma = (p.debug & 2) != 0;   // timing experiment: operand traffic only
@@ -948,13 +961,12 @@ __global__ void __launch_bounds__(conv_tc_threads(DIRECT, EPI8), 1) conv_tc_kern
                 for (int ks = 0; ks < nks; ++ks, ++ia) {
                     const int sa = ia % NA;
                     const int taps = ks < nks0 ? p.seg[0].taps : p.seg[1].taps;
-                    if (PAIR) mbar_wait_cluster(barAfull + 8 * sa, (ia / NA) & 1);
-                    else TL_WAIT(tl_b, mbar_wait(barAfull + 8 * sa, (ia / NA) & 1));
+                    TL_WAIT(tl_b, mbar_wait(barAfull + 8 * sa, (ia / NA) & 1));
+                    if (PAIR && DIRECT) TL_WAIT(tl_b, mbar_wait(barApeer + 8 * sa, (ia / NA) & 1));   // the peer's half of the M = 256 rows
                     tc_fence_after();
                     for (int tap = 0; tap < taps; ++tap, ++ib) {
                         const int sb = ib % NB;
-                        if (PAIR) mbar_wait_cluster(barBfull + 8 * sb, (ib / NB) & 1);
-                        else TL_WAIT(tl_c, mbar_wait(barBfull + 8 * sb, (ib / NB) & 1));
+                        TL_WAIT(tl_c, mbar_wait(barBfull + 8 * sb, (ib / NB) & 1));
                         tc_fence_after();
                         const int shift = taps == 3 ? tap : 1;   // slot of the first row: position - 1 + tap
                         const uint32_t a_hi = sA + sa * A_STAGE + shift * A_SBO, a_lo = a_hi + A_TILE;
@@ -1040,7 +1052,7 @@ bool conv_tc_eligible(int Cin0, int Cin1, int Cout, int Tout, int taps, int stri
 // barrier relay doubles the load -> consume -> free round trip (2.7 vs 1.3 us) and the rings that fit in 227 KB no longer
 // cover it: 25-45 % slower on every layer, so they are off by default.
 int g_conv_tc_cluster = 2;          // CTAs per cluster sharing weight stages by multicast (1, 2 or 4); eegldm_set_conv_cluster
-int g_conv_tc_pair = 0;             // 1: cta_group::2 CTA pairs (M=256 per MMA); 0: single-CTA MMAs (+ multicast clusters)
+int g_conv_tc_pair = 1;             // cta_group::2 CTA pairs (M=256 per MMA): bit 0 = the 256-wide launches (default), bit 1 = the 128-wide ones
 int g_conv_tc_bn256_stages = 1;     // minimum weight stages per tile for the N=256 shape
 int g_conv_tc_cat = 1;              // N=128 f16x3 tiles: a_hi x [w_hi | w_lo] as one N=256 MMA
 int g_conv_tc_epi8 = 1;             // two epilogue warpgroups (EPI8); eegldm_set_conv_tuning bit 6 switches it off (A/B timing)
@@ -1115,6 +1127,27 @@ cudaError_t launch_conv_tc_t(const TcConvParams& p, int num_sms, cudaStream_t st
     return cudaLaunchKernelEx(&cfg, conv_tc_kernel<X3, BN, CL, PAIR, DIRECT, EPI8>, p);
 }
 
+// 2-D tensor map over an image of 512-byte rows (256 u16), box = `box_rows` whole rows (CTA-pair loads, see the kernel comment).
+// cuTensorMapEncodeTiled is a pure host-side encoder; it is resolved through the runtime so the library does not link libcuda.
+static cudaError_t encode_rows512(CUtensorMap* tm, const void* base, size_t rows, int box_rows) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn fn = nullptr;
+    if (!fn) {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qr);
+        if (e != cudaSuccess) return e;
+        if (!f || qr != cudaDriverEntryPointSuccess) return cudaErrorNotSupported;
+        fn = (EncodeFn)f;
+    }
+    const cuuint64_t dims[2] = {256, (cuuint64_t)rows}, strides[1] = {512};
+    const cuuint32_t box[2] = {256, (cuuint32_t)box_rows}, es[2] = {1, 1};
+    const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
 cudaError_t launch_conv_tc(const TcConvParams& p_in, bool x3, cudaStream_t st) {
     if (p_in.nsegs16 <= 0) return cudaSuccess;
     TcConvParams p = p_in;
@@ -1127,10 +1160,28 @@ cudaError_t launch_conv_tc(const TcConvParams& p_in, bool x3, cudaStream_t st) {
     }
     if (p.bn != 128 && p.bn != 256) return cudaErrorInvalidValue;
     cudaError_t e;
-    // two-warpgroup epilogue (EPI8): every single-CTA-MMA launch except the ones whose epilogue emits 32-channel GroupNorm groups
-    // or bf16-mode attention operand images (one-warpgroup epilogue only); cluster sizes 1 and 2
-    const bool epi8 = g_conv_tc_epi8 && !g_conv_tc_pair && !(p.qkv16 && !x3) && !(p.gn_partial && p.gn_cpg == 32) &&
-                      (p.direct || g_conv_tc_cluster == 2 || g_conv_tc_cluster == 1);
+    // two-warpgroup epilogue (EPI8): every launch except the ones whose epilogue emits 32-channel GroupNorm groups or bf16-mode
+    // attention operand images (one-warpgroup epilogue only); cluster sizes 1 and 2
+    const bool epi8_ok = !(p.qkv16 && !x3) && !(p.gn_partial && p.gn_cpg == 32);
+    // CTA pairs (cta_group::2): g_conv_tc_pair bit 0 = the N = 256 launches, bit 1 = the N = 128 launches
+    const bool pair = epi8_ok && ((p.bn == 256 && (g_conv_tc_pair & 1)) || (p.bn == 128 && (g_conv_tc_pair & 2)));
+    if (pair) {
+        const int n_mtiles = (p.nsegs16 + 7) / 8;
+        for (int s = 0; s < p.nseg; ++s) {
+            const TcSeg& sg = p.seg[s];
+            e = encode_rows512(&p.tmap_w[s], sg.w, (size_t)sg.nks * sg.taps * 2 * (p.Cout / 8), p.bn / 16);   // BN/2 columns = BN/16 rows
+            if (e == cudaSuccess && !p.direct) e = encode_rows512(&p.tmap_u[s], sg.U, (size_t)n_mtiles * sg.nks * 36, x3 ? 36 : 18);
+            if (e != cudaSuccess) return e;
+        }
+#define EEGLDM_TCP(X3, BN) (p.direct ? launch_conv_tc_t<X3, BN, 2, true, true, true>(p, num_sms, st) : launch_conv_tc_t<X3, BN, 2, true, false, true>(p, num_sms, st))
+        if (p.bn == 256) e = x3 ? EEGLDM_TCP(true, 256) : EEGLDM_TCP(false, 256);
+        else e = x3 ? EEGLDM_TCP(true, 128) : EEGLDM_TCP(false, 128);
+#undef EEGLDM_TCP
+        if (e != cudaSuccess) return e;
+        g_launch_count += 1;
+        return cudaGetLastError();
+    }
+    const bool epi8 = g_conv_tc_epi8 && epi8_ok && (p.direct || g_conv_tc_cluster == 2 || g_conv_tc_cluster == 1);
 #define EEGLDM_TC8(X3, BN)                                                                               \
     (p.direct ? (g_conv_tc_cluster == 1 ? launch_conv_tc_t<X3, BN, 1, false, true, true>(p, num_sms, st)   \
                                         : launch_conv_tc_t<X3, BN, 2, false, true, true>(p, num_sms, st))  \
@@ -1147,7 +1198,6 @@ cudaError_t launch_conv_tc(const TcConvParams& p_in, bool x3, cudaStream_t st) {
 #define EEGLDM_TC(X3, BN)                                                                         \
     (p.direct ? (g_conv_tc_cluster == 1 ? launch_conv_tc_t<X3, BN, 1, false, true>(p, num_sms, st)   \
                                         : launch_conv_tc_t<X3, BN, 2, false, true>(p, num_sms, st))  \
-     : g_conv_tc_pair ? launch_conv_tc_t<X3, BN, 2, true>(p, num_sms, st)                           \
      : g_conv_tc_cluster == 4 ? launch_conv_tc_t<X3, BN, 4, false>(p, num_sms, st)                 \
      : g_conv_tc_cluster == 2 ? launch_conv_tc_t<X3, BN, 2, false>(p, num_sms, st) : launch_conv_tc_t<X3, BN, 1, false>(p, num_sms, st))
     if (p.bn == 256) e = x3 ? EEGLDM_TC(true, 256) : EEGLDM_TC(false, 256);

@@ -685,7 +685,7 @@ void plan_conv(Builder& bd, ConvParams p, const uint8_t* tw0 = nullptr, const ui
         // fused producer: the conv kernel reads the fp32 sources itself (no act_split pass, no U tensors); AvgPool inputs
         // (the two down-sampling ResBlocks) keep the pre-pass
         // and 1x1 convs with many N tiles (qkv: 6) would redo the transform per N tile with only one tap of MMAs to hide it
-        bool direct = g_conv_direct && !qkv && !premade_u0 && (g_conv_direct_wide || !(p.seg[0].taps == 1 && p.Cout / q.bn > 2));
+        bool direct = g_conv_direct && !premade_u0 && (g_conv_direct_wide || !(p.seg[0].taps == 1 && p.Cout / q.bn > 2));
         for (int s = 0; direct && s < p.nseg; ++s) direct = p.seg[s].resample == RS_NONE || p.seg[s].resample == RS_NEAREST2;
         q.direct = direct ? 1 : 0;
         for (int s = 0; s < p.nseg; ++s) {
@@ -1384,7 +1384,7 @@ int eegldm_set_conv_cluster(int ctas) {
 }
 
 int eegldm_set_conv_tuning(int pair, int bn256_min_stages, int fuse_epilogues) {
-    if (pair != 0 && pair != 1) return fail(EEGLDM_ERR_INVALID, "pair must be 0 or 1");
+    if (pair < 0 || pair > 3) return fail(EEGLDM_ERR_INVALID, "pair must be a bit mask in 0..3 (bit 0: 256-wide launches, bit 1: 128-wide launches)");
     g_conv_gn_fused = (fuse_epilogues & 1) != 0;
     g_conv_qkv_fused = (fuse_epilogues & 2) != 0;
     g_conv_direct = (fuse_epilogues & 4) != 0;

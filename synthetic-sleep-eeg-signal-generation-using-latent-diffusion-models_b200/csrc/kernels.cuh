@@ -4,6 +4,7 @@
 // For the 1-channel signals / latents at the API boundary this is bit-identical to the
 // reference's NCL layout; multi-channel latents are transposed once at the boundary.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <atomic>
 #include <cstdint>
@@ -119,6 +120,11 @@ struct TcConvParams {
     int* range_flag;    // optional (fused producer): set to 1 when an operand is outside the f16x3 range (|x| >= 65504 or NaN)
     int cat;            // f16x3, bn == 128: issue a_hi x [w_hi | w_lo] as one N = 256 MMA (set by launch_conv_tc from g_conv_tc_cat)
     unsigned long long* timeline;   // optional (eegldm_bench_conv_timeline): per-CTA cycle counters, TC_TL_N per CTA
+    // CTA-pair form (g_conv_tc_pair; filled by launch_conv_tc): 2-D tensor maps over the weight image ([rows of 256 u16], box = the
+    // BN/2 columns of one CTA) and, in the pre-pass form, over the U image (box = one 18 KB stage) of each segment -- the pair's loads are
+    // cp.async.bulk.tensor.cta_group::2, whose completion can signal the LEADER's mbarrier from either CTA
+    CUtensorMap tmap_w[2];
+    CUtensorMap tmap_u[2];
 };
 // per-CTA counters of the conv kernel's warp roles (cycles, summed over the CTA's tiles)
 enum TcTimeline : int { TC_TL_TOTAL = 0, TC_TL_MMA_WAIT_ACC, TC_TL_MMA_WAIT_A, TC_TL_MMA_WAIT_B, TC_TL_EPI_WAIT, TC_TL_EPI_BUSY,

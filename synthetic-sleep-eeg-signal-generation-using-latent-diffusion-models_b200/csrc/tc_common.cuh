@@ -30,25 +30,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "DONE:\n"
         "}\n" ::"r"(bar), "r"(parity) : "memory");
 }
-// same wait with cluster-scope acquire: pairs with a peer CTA's mbar_arrive_cluster (release.cluster)
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra DONE;\n"
-        "bra LAB_WAIT;\n"
-        "DONE:\n"
-        "}\n" ::"r"(bar), "r"(parity) : "memory");
-}
-// arrive on the mbarrier at the same CTA-relative offset in CTA `cta` of this cluster
+// arrive on the mbarrier at the same CTA-relative offset in CTA `cta` of this cluster.  Default semantics (.release at CTA scope),
+// the form CUTLASS's ClusterBarrier::arrive(cta_id) uses: `.release.cluster` makes ptxas emit MEMBAR.ALL.GPU in front of every
+// arrive, which also waits for the arriving thread's global loads in flight -- measured 2x on the fused producer (r03 timeline).
+// What is handed over here is either shared memory already fenced to the async proxy (fence.proxy.async) or TMEM reads already
+// completed (tcgen05.wait::ld + tcgen05.fence::before_thread_sync); the waiting side uses the plain mbar_wait.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) {
     asm volatile(
         "{\n"
         ".reg .b32 ra;\n"
         "mapa.shared::cluster.u32 ra, %0, %1;\n"
-        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n"
         "}\n" ::"r"(bar), "r"(cta) : "memory");
 }
 __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -63,6 +55,13 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes
 __device__ __forceinline__ void bulk_copy_g2s_multicast(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t cta_mask) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst),
                  "l"(src), "r"(bytes), "r"(bar), "h"(cta_mask) : "memory");
+}
+// 2-D tiled tensor-map copy issued by either CTA of a cta_group::2 pair into ITS OWN shared memory; complete_tx goes to the mbarrier
+// at `bar`'s offset in the pair's LEADER (even cluster rank): the shared::cluster address with the rank bit cleared.  (A non-tensor
+// cp.async.bulk cannot do that -- its complete_tx only reaches a barrier of the destination CTA: tools/probe/remote_tx.cu.)
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const void* tmap, int x, int y, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+                 "l"(tmap), "r"(x), "r"(y), "r"(bar & 0xFEFFFFFFu) : "memory");
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ uint32_t cluster_id_x() { uint32_t r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }

@@ -83,11 +83,10 @@ def test_fused_conv_matches_torch(built_lib, cuda_device, case, math):
         torch.testing.assert_close(y, ref, rtol=1e-4, atol=2e-5)
 
 
-# tile shapes of the tcgen05 kernel: (CTA pair?, minimum weight stages for 256-wide tiles).  The default is (0, 1):
-# single-CTA MMAs, 256-wide tiles wherever Cout % 256 == 0; (x, 10**6) forces 128-wide tiles, pair=1 is cta_group::2.
-SHAPES = [(1, 1), (1, 10 ** 6), (0, 24), (0, 10 ** 6)]
-# third knob = fuse_epilogues bit mask; bit 2 (4) = activation operands produced inside the conv kernel (no act_split pass)
-FUSE = {(1, 1): 3, (1, 10 ** 6): 3, (0, 24): 1, (0, 10 ** 6): 5}
+# tile shapes of the tcgen05 kernel: (CTA-pair mask, minimum weight stages for 256-wide tiles, fuse_epilogues mask).  The default is
+# (1, 1, 15): CTA pairs on the 256-wide tiles (wherever Cout % 256 == 0), single-CTA MMAs on the 128-wide ones; (x, 10**6) forces 128-wide tiles; pair bit 0 / bit 1 =
+# cta_group::2 for the 256- / 128-wide launches; fuse bit 2 (4) = activation operands produced inside the conv kernel (no act_split)
+SHAPES = [(3, 1, 3), (3, 10 ** 6, 3), (3, 1, 15), (3, 10 ** 6, 15), (1, 1, 143), (0, 1, 15), (0, 24, 1), (0, 10 ** 6, 5)]
 BIG_CASES = [
     (40, 768, 128, 128, 3, True, 0, True),     # 240 M tiles: every persistent CTA walks several tiles (ring wrap, both TMEM sets)
     (37, 192, 512, 512, 3, True, 0, True),     # tiles straddle samples, odd tile count (idle slot in the last pair), 2-4 N tiles
@@ -109,18 +108,18 @@ def test_conv_tile_shapes(built_lib, cuda_device, case, shape):
     Tc = {0: Tin, 1: Tin // 2, 2: Tin * 2}[rs]
     res = torch.randn(B, Tc, Cout, generator=g) if has_res else None
     ref = _ref(x, w, bias, scale, shift, aff, rs, res)
-    _lib.check(built_lib.eegldm_set_conv_tuning(*shape, FUSE[tuple(shape)] if tuple(shape) in FUSE else 15))
+    _lib.check(built_lib.eegldm_set_conv_tuning(*shape))
     try:
         y = _run(built_lib, cuda_device, x, w, bias, scale, shift, aff, rs, res, "f16x3")
     finally:
-        _lib.check(built_lib.eegldm_set_conv_tuning(0, 1, 15))
+        _lib.check(built_lib.eegldm_set_conv_tuning(1, 1, 15))
     assert torch.isfinite(y).all()
     torch.testing.assert_close(y, ref, rtol=1e-4, atol=2e-5)
 
 
 @pytest.mark.parametrize("case", BIG_CASES)
 def test_conv_default_shape_big(built_lib, cuda_device, case):
-    test_conv_tile_shapes(built_lib, cuda_device, case, (0, 1))     # default: single-CTA MMAs, 256-wide tiles, fused producer
+    test_conv_tile_shapes(built_lib, cuda_device, case, (1, 1, 15))     # default: CTA pairs on 256-wide tiles, fused producer
 
 
 GN_CASES = [(3, 768, 128, 128, 3), (5, 192, 256, 512, 3), (2, 384, 128, 256, 1), (7, 48, 64, 128, 3), (3, 192, 512, 1024, 1)]
@@ -164,7 +163,7 @@ def test_attention_in_kernel_split(built_lib, cuda_device, case, math):
     try:
         test_attention_matches_torch(built_lib, cuda_device, case, math)
     finally:
-        _lib.check(built_lib.eegldm_set_conv_tuning(0, 1, 15))
+        _lib.check(built_lib.eegldm_set_conv_tuning(1, 1, 15))
 
 
 @pytest.mark.parametrize("math", ["fp32", "f16x3", "bf16"])

@@ -16,6 +16,7 @@ ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--fuse", type=int, default=15)
 ap.add_argument("--bn256", type=int, default=1)
 ap.add_argument("--cluster", type=int, default=2)
+ap.add_argument("--pair", type=int, default=1, help="CTA-pair mask (1: 256-wide launches, 2: 128-wide launches)")
 ap.add_argument("--only", type=int, default=-1, help="run one row of SHAPES")
 ap.add_argument("--debug", type=int, default=0, help="conv debug bits (64: one cluster alone on the device)")
 a = ap.parse_args()
@@ -23,7 +24,7 @@ torch.cuda.set_device(0)
 torch.zeros(1, device="cuda")
 L = eegldm.lib()
 _lib.check(L.eegldm_set_conv_cluster(a.cluster))
-_lib.check(L.eegldm_set_conv_tuning(0, a.bn256, a.fuse))
+_lib.check(L.eegldm_set_conv_tuning(a.pair, a.bn256, a.fuse))
 # (T, Cin, Cout, k, residual): the UNet's layer shapes (config_ldm.yaml)
 SHAPES = [(768, 128, 128, 3, 0), (768, 128, 128, 3, 1), (768, 256, 128, 3, 0), (384, 256, 256, 3, 1), (384, 768, 256, 3, 0),
           (192, 512, 512, 3, 0), (192, 512, 512, 3, 1), (192, 1024, 512, 3, 0), (192, 512, 1536, 1, 0), (192, 512, 1536, 1, 2), (192, 512, 512, 1, 1)]

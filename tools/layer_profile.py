@@ -14,7 +14,7 @@ ap.add_argument("--batch", type=int, default=1024)
 ap.add_argument("--math", default="f16x3")
 ap.add_argument("--cluster", type=int, default=2)
 ap.add_argument("--warmup", type=int, default=2, help="untimed forwards before the profiled one (0 under ncu)")
-ap.add_argument("--pair", type=int, default=0)
+ap.add_argument("--pair", type=int, default=1)
 ap.add_argument("--bn256", type=int, default=1)
 ap.add_argument("--gnfuse", type=int, default=15)
 a = ap.parse_args()
