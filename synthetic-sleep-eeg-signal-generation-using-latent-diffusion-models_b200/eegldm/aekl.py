@@ -251,7 +251,10 @@ class AutoencoderKL(EngineModule):
         that requires grad) the call is differentiable with respect to the parameters, so the reference's own training loop runs
         unchanged (train_autoencoderkl.py:204-220: ``model(x)`` -> losses -> ``loss_g.backward()`` -> ``optimizer_g.step()``);
         ``train_step`` is the fused, much faster form of the same step."""
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+        # (the engine's training kernels cover in / out / latent channels = 1, every reference config; other widths run the
+        # inference path, whose outputs do not require grad -- a .backward() on them fails loudly in PyTorch)
+        trainable = self.in_channels == 1 and self.out_channels == 1 and self.latent_channels == 1
+        if trainable and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             x = check_cuda_f32(x, "x")
             B, Cin, Lx = x.shape
             if Cin != self.in_channels or Lx % self._factor:
