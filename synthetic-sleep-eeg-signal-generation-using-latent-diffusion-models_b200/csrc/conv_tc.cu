@@ -65,7 +65,7 @@ __host__ __device__ constexpr int ring_b_bytes(bool alt) { return (alt ? 96 : 12
 __host__ __device__ constexpr int bar_off(bool alt) { return ring_na(alt) * A_STAGE + ring_b_bytes(alt); }
 constexpr int STG_LD = 36;         // staging row stride in floats: 16-byte aligned rows, conflict-free 128-bit writes and reads
 constexpr int STAGING_BYTES = 4 * 32 * STG_LD * 4;
-constexpr int STATS_BYTES = 4 * 256 * 8;   // per epilogue warp: (mean, M2) of up to 8 segments x 32 groups (GroupNorm statistics)
+constexpr int STATS_BYTES = 8 * 256 * 8;   // per epilogue warp (8 in the two-warpgroup form): (mean, M2) of up to 8 segments x 32 groups
 __host__ __device__ constexpr int smem_bytes(bool alt) { return bar_off(alt) + 512 + STAGING_BYTES + STATS_BYTES; }
 constexpr int NUM_THREADS = 192;
 constexpr int SPLIT_THREADS = 192;
@@ -224,7 +224,8 @@ __global__ void __launch_bounds__(conv_tc_threads(DIRECT, EPI8), 1) conv_tc_kern
     constexpr int BNL = PAIR ? BN / 2 : BN;    // weight columns staged in THIS CTA's shared memory
     constexpr int B_HALF = BNL * BK * 2;       // hi (or lo) weight tile of one (tap, k-step): BNL x 32 x 2 B
     constexpr int B_STAGE = 2 * B_HALF;
-    constexpr bool ALT = PAIR || DIRECT;   // ring plan: 5 activation stages + 96 KB of weight stages
+    constexpr bool ALT = true;   // ring plan of every form: 5 activation stages + 96 KB of weight stages (the 4 + 128 KB plan of the
+                                 // single-CTA pre-pass form no longer fits next to the 16 KB statistics buffer)
     constexpr int NA = ring_na(ALT), BAR_OFF = bar_off(ALT), STAGING_OFF = BAR_OFF + 512;
     constexpr int NB = ring_b_bytes(ALT) / B_STAGE;
     static_assert(8 * (3 * NA + 2 * NB + 4) <= 448, "barrier area: 3 NA + 2 NB + 4 mbarriers in front of the TMEM slot");
@@ -294,8 +295,8 @@ __global__ void __launch_bounds__(conv_tc_threads(DIRECT, EPI8), 1) conv_tc_kern
         // per-warp transpose buffer [32 rows][16 columns], 16-byte quads XOR-swizzled by (row >> 1) & 3: conflict-free 128-bit
         // writes (thread = row) and reads (thread = (segment, quad)) without padding
         uint32_t* stg = reinterpret_cast<uint32_t*>(smem + STAGING_OFF) + warp * 512;
-        float2* stats = reinterpret_cast<float2*>(smem + STAGING_OFF + STAGING_BYTES);   // [warp][128]: segment * gpt + group
-        const int cpg = p.gn_cpg, gpt = p.gn_partial ? HC / cpg : 0;                        // groups per warpgroup half-tile (<= 16)
+        float2* stats = reinterpret_cast<float2*>(smem + STAGING_OFF + STAGING_BYTES);   // [warp][256]: segment * gpt + group
+        const int cpg = p.gn_cpg, gpt = p.gn_partial ? HC / cpg : 0;                        // groups per warpgroup half-tile (<= 32)
         const int cpg_sh = 31 - __clz(max(cpg, 1));
         const int seg = lane >> 2, quad = lane & 3, col4 = quad * 4;
         int lt = 0;
@@ -494,7 +495,7 @@ __global__ void __launch_bounds__(conv_tc_threads(DIRECT, EPI8), 1) conv_tc_kern
                         mean = 0.5f * (mean + mo);
                         n *= 2.f;
                     }
-                    if ((col4 & (cpg - 1)) == 0) stats[warp * 128 + seg * gpt + ((cb + col4) >> cpg_sh)] = make_float2(mean, m2);
+                    if ((col4 & (cpg - 1)) == 0) stats[warp * 256 + seg * gpt + ((cb + col4) >> cpg_sh)] = make_float2(mean, m2);
                 }
                 __syncwarp();   // the transpose buffer is reused by the next chunk
             }
@@ -506,10 +507,10 @@ __global__ void __launch_bounds__(conv_tc_threads(DIRECT, EPI8), 1) conv_tc_kern
                 // (count, mean, M2) record per (sample, 16-position segment, group) for gn_finalize
                 asm volatile("bar.sync %0, 128;" ::"r"(1 + eh) : "memory");
                 const float nq = 4.f * cpg;
-                const float2* sw = stats + eh * 512;
+                const float2* sw = stats + eh * 1024;
                 for (int e = tid & 127; e < 8 * gpt; e += 128) {
                     const int sg = e / gpt, gi = e - sg * gpt, g16 = m_tile * 8 + sg;
-                    const float2 a = sw[e], b = sw[128 + e], c = sw[256 + e], d = sw[384 + e];
+                    const float2 a = sw[e], b = sw[256 + e], c = sw[512 + e], d = sw[768 + e];
                     const float mean = 0.25f * ((a.x + b.x) + (c.x + d.x));
                     const float da = a.x - mean, db = b.x - mean, dc = c.x - mean, dd = d.x - mean;
                     const float m2 = (a.y + b.y) + (c.y + d.y) + nq * ((da * da + db * db) + (dc * dc + dd * dd));
@@ -1059,7 +1060,9 @@ int g_conv_tc_epi8 = 1;             // two epilogue warpgroups (EPI8); eegldm_se
 bool conv_tc_gn_ok(int Cout, int G) {
     if (G <= 0 || Cout % G) return false;
     const int cpg = Cout / G;
-    return (cpg == 4 || cpg == 8 || cpg == 16 || cpg == 32) && Cout % 128 == 0 && (Cout % 256 == 0 ? 256 : 128) / cpg <= 32;
+    // groups per epilogue warpgroup (half a tile in the two-warpgroup form) <= 32; 32-channel groups take the one-warpgroup form
+    const int bn = Cout % 256 == 0 ? 256 : 128;
+    return (cpg == 4 || cpg == 8 || cpg == 16 || cpg == 32) && Cout % 128 == 0 && (g_conv_tc_epi8 && cpg != 32 ? bn / 2 : bn) / cpg <= 32;
 }
 int conv_tc_bn(int Cout, int weight_stages) { return (Cout % 256 == 0 && weight_stages >= g_conv_tc_bn256_stages) ? 256 : 128; }
 
@@ -1106,7 +1109,7 @@ template <bool X3, int BN, int CL, bool PAIR, bool DIRECT = false, bool EPI8 = f
 cudaError_t launch_conv_tc_t(const TcConvParams& p, int num_sms, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<X3, BN, CL, PAIR, DIRECT, EPI8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(PAIR || DIRECT));
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<X3, BN, CL, PAIR, DIRECT, EPI8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(true));
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
@@ -1118,7 +1121,7 @@ cudaError_t launch_conv_tc_t(const TcConvParams& p, int num_sms, cudaStream_t st
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(nclusters * CL);   // persistent: one CTA per SM
     cfg.blockDim = dim3(conv_tc_threads(DIRECT, EPI8));
-    cfg.dynamicSmemBytes = smem_bytes(PAIR || DIRECT);
+    cfg.dynamicSmemBytes = smem_bytes(true);
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;

@@ -246,23 +246,21 @@ ScaleShift plan_gn(Builder& bd, const Act& x0, const Act* x1, int G, const float
     p.scale = bd.ptr(ss.buf);
     p.shift = p.scale + (size_t)bd.B * C;
     ss.scale = p.scale; ss.shift = p.shift;
-    if (!x1 && x0.gn_part && x0.gn_G == G) {   // the producer's epilogue already wrote the statistics: no pass over x0
-        p.nsplit = x0.gn_nsplit;
-        p.partial = bd.ptr(x0.gn_part);
-        bd.add([p](cudaStream_t st) { return launch_groupnorm_finalize(p, st); }, 1, OP_GN, 0.0,
-               4.0 * bd.B * (3.0 * p.nsplit * G + 2.0 * C));
-        return ss;
-    }
-    // virtual concat whose sources both carry epilogue statistics and whose groups are whole numbers of source records
-    // (the 1024 = 512 + 512 inputs of output_blocks.0 / .1: 32-channel groups = two 16-channel records of one source)
-    if (x1 && x0.gn_part && x1->gn_part && x0.gn_nsplit == x1->gn_nsplit && G <= 256) {
-        const int cpg = C / G, r0 = x0.C / x0.gn_G, r1 = x1->C / x1->gn_G;
-        if (x0.C % cpg == 0 && cpg % r0 == 0 && cpg % r1 == 0) {
+    // The producers' epilogues already wrote the statistics as (count, mean, M2) records at THEIR record width (4 or 8 channels,
+    // plan_conv): no pass over the tensor when every group of this norm is a whole number of records -- also for a virtual concat
+    // whose groups straddle the two sources (768 = 512 + 256 in groups of 24, 384 = 256 + 128 in groups of 12).
+    {
+        const int cpg = C / G;
+        const bool have0 = x0.gn_part != nullptr, have1 = !x1 || x1->gn_part != nullptr;
+        const int w0 = have0 ? x0.C / x0.gn_G : 0, w1 = x1 && have1 ? x1->C / x1->gn_G : 0;
+        bool ok = have0 && have1 && G <= 256 && C % G == 0 && cpg % w0 == 0;
+        if (ok && x1) ok = x0.gn_nsplit == x1->gn_nsplit && cpg % w1 == 0 && x0.C % w1 == 0;
+        if (ok) {
             p.nsplit = x0.gn_nsplit;
-            p.partial = bd.ptr(x0.gn_part); p.partial1 = bd.ptr(x1->gn_part);
-            p.rec_G0 = x0.gn_G; p.rec_G1 = x1->gn_G;
+            p.partial = bd.ptr(x0.gn_part); p.rec_G0 = x0.gn_G;
+            if (x1) { p.partial1 = bd.ptr(x1->gn_part); p.rec_G1 = x1->gn_G; }
             bd.add([p](cudaStream_t st) { return launch_groupnorm_finalize(p, st); }, 1, OP_GN, 0.0,
-                   4.0 * bd.B * (3.0 * p.nsplit * (x0.gn_G + x1->gn_G) + 2.0 * C));
+                   4.0 * bd.B * (3.0 * p.nsplit * (x0.gn_G + (x1 ? x1->gn_G : 0)) + 2.0 * C));
             return ss;
         }
     }
@@ -375,6 +373,7 @@ bool g_conv_qkv_fused = true;  // the qkv conv writes attention operand images d
 bool g_attn_direct = false;    // the tcgen05 attention splits fp32 q, k, v itself (eegldm_set_conv_tuning bit 4): measured no faster
 bool g_attn_u_fused = true;    // the tcgen05 attention writes proj_out's operand image instead of fp32 (eegldm_set_conv_tuning bit 3)
 bool g_conv_direct = true;     // tensor-pipe convs produce their activation operands in-kernel (no act_split pre-pass)
+bool g_conv_gn_fine = true;        // epilogue GroupNorm records 4 / 8 channels wide (eegldm_set_conv_tuning bit 8 = the consumer's group width instead)
 bool g_conv_direct_wide = false;   // fused producer also for 1x1 convs with more than two N tiles (qkv): eegldm_set_conv_tuning bit 7
 bool g_conv_gn_fused = true;   // tensor-pipe convs emit the GroupNorm statistics of their output (eegldm_set_conv_tuning)
 bool g_graphs_enabled = true;
@@ -722,6 +721,12 @@ void plan_conv(Builder& bd, ConvParams p, const uint8_t* tw0 = nullptr, const ui
         q.out = p.out;
         q.range_flag = bd.range_flag;
         if (qkv) { q.qkv16 = qkv->dst; q.qkv_H = qkv->H; q.qkv_ch = qkv->ch; }
+        // record width: 4 channels (8 from 512 output channels) instead of the consumer's own group width, so that the same records
+        // also serve the concat norms of the up path, whose groups are 12 / 24 channels wide and straddle the two sources (plan_gn)
+        if (out_act && gn_G > 0 && g_conv_gn_fused && g_conv_gn_fine) {
+            const int rec_G = p.Cout / (p.Cout >= 512 ? 8 : 4);
+            if (rec_G % gn_G == 0 && conv_tc_gn_ok(p.Cout, rec_G)) gn_G = rec_G;
+        }
         if (out_act && g_conv_gn_fused && conv_tc_gn_ok(p.Cout, gn_G)) {
             out_act->gn_nsplit = p.Tout / 16; out_act->gn_G = gn_G;
             out_act->gn_part = bd.scratch((size_t)bd.B * out_act->gn_nsplit * gn_G * 3);
@@ -1391,6 +1396,7 @@ int eegldm_set_conv_tuning(int pair, int bn256_min_stages, int fuse_epilogues) {
     g_attn_u_fused = (fuse_epilogues & 8) != 0;
     g_attn_direct = (fuse_epilogues & 16) != 0;
     g_conv_direct_wide = (fuse_epilogues & 128) != 0;
+    g_conv_gn_fine = (fuse_epilogues & 256) == 0;
     g_conv_tc_epi8 = (fuse_epilogues & 64) ? 0 : 1;  // bit 6 switches the two-warpgroup conv epilogue OFF (A/B timing)
     g_conv_tc_cat = (fuse_epilogues & 32) ? 0 : 1;   // bit 5 switches the concatenated hi|lo MMA of the N = 128 tiles OFF (A/B timing)
     if (bn256_min_stages < 1) return fail(EEGLDM_ERR_INVALID, "bn256_min_stages must be >= 1");

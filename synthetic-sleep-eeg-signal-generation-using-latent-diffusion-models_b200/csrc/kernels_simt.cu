@@ -465,20 +465,33 @@ __global__ void gn_finalize_kernel(const GnParams p) {
         const int g = threadIdx.x % gp, part = threadIdx.x / gp;
         Mom r; r.n = 0.f; r.mean = 0.f; r.m2 = 0.f;
         if (g < p.G) {
-            // where this group's records live: its own column of `partial`, or `nrec` consecutive record groups of one source
-            const float* base = p.partial;
-            int recG = p.G, first = g, nrec = 1;
-            if (p.rec_G0) {
-                const int c0 = g * cpg;                       // first channel of the group in the concatenated tensor
-                if (c0 < p.C0) { recG = p.rec_G0; nrec = cpg / (p.C0 / recG); first = c0 / (p.C0 / recG); }
-                else { base = p.partial1; recG = p.rec_G1; nrec = cpg / (p.C1 / recG); first = (c0 - p.C0) / (p.C1 / recG); }
-            }
-            for (int sp = part; sp < p.nsplit; sp += lanes)
-                for (int k = 0; k < nrec; ++k) {
-                    const float* o = base + (((size_t)b * p.nsplit + sp) * recG + first + k) * 3;
+            // where this group's records live: its own column of `partial`, or whole records of the sources at THEIR record
+            // width -- a group of a virtual concat may take its first channels from source 0 and the rest from source 1
+            // (768 = 512 + 256 channels in 32 groups of 24: group 21 is one 8-channel record of source 0 + four 4-channel
+            // records of source 1)
+            if (!p.rec_G0) {
+                for (int sp = part; sp < p.nsplit; sp += lanes) {
+                    const float* o = p.partial + (((size_t)b * p.nsplit + sp) * p.G + g) * 3;
                     Mom m; m.n = o[0]; m.mean = o[1]; m.m2 = o[2];
                     r = mom_combine(r, m);
                 }
+            } else {
+                const int c0 = g * cpg, c1 = c0 + cpg;    // channel range of the group in the concatenated tensor
+#pragma unroll
+                for (int src = 0; src < 2; ++src) {
+                    const int cb = src ? p.C0 : 0, cs = src ? p.C1 : p.C0, recG = src ? p.rec_G1 : p.rec_G0;
+                    const int lo = max(c0, cb), hi = min(c1, cb + cs);
+                    if (lo >= hi || recG <= 0) continue;
+                    const float* base = src ? p.partial1 : p.partial;
+                    const int w = cs / recG, first = (lo - cb) / w, nrec = (hi - lo) / w;
+                    for (int sp = part; sp < p.nsplit; sp += lanes)
+                        for (int k = 0; k < nrec; ++k) {
+                            const float* o = base + (((size_t)b * p.nsplit + sp) * recG + first + k) * 3;
+                            Mom m; m.n = o[0]; m.mean = o[1]; m.m2 = o[2];
+                            r = mom_combine(r, m);
+                        }
+                }
+            }
         }
         sm[threadIdx.x] = r;
         __syncthreads();
