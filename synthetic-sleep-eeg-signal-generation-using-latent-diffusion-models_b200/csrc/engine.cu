@@ -737,6 +737,12 @@ void plan_conv(Builder& bd, ConvParams p, const uint8_t* tw0 = nullptr, const ui
     }
     // profile family: the narrow convs (1-channel in / out convs of the UNet, the 2-2-4 autoencoder) are HBM / latency-bound
     // SIMT launches and are kept apart from the GEMM-shaped ones the roofline is quoted on
+    // the UNet's input conv (1 -> 128 channels) writes the GroupNorm records of its output like a tensor-pipe conv's epilogue does
+    if (out_act && gn_G > 0 && g_conv_gn_fused && g_conv_gn_fine && conv_narrow_in_gn_ok(p) && (p.Cout / 4) % gn_G == 0) {
+        out_act->gn_nsplit = p.Tout / 16; out_act->gn_G = p.Cout / 4;
+        out_act->gn_part = bd.scratch((size_t)bd.B * out_act->gn_nsplit * out_act->gn_G * 3);
+        p.gn_rec = bd.ptr(out_act->gn_part);
+    }
     const bool narrow = p.seg[0].C0 + p.seg[0].C1 < 32 || p.Cout < 32;
     bd.add([p](cudaStream_t st) { return launch_conv_simt(p, st); }, 1, narrow ? OP_CONV_SIMT : OP_CONV, flops, bytes);
 }
@@ -849,7 +855,7 @@ Act plan_layer(Builder& bd, const ULayer& l, const Act& x0, const Act* x1, const
             p.seg[0] = make_seg(bd, x0, nullptr, nullptr, 0, RS_NONE, l.w1, 3);
             p.nseg = 1; p.Cout = l.cout; p.Tout = x0.T; p.Tc = x0.T; p.stride = 1; p.pad_left = 1;
             p.bias = l.b1; p.out = bd.wptr(y);
-            plan_conv(bd, p);
+            plan_conv(bd, p, nullptr, nullptr, nullptr, &y, 32);
             return y;
         }
         case ULayer::RES: return plan_res(bd, l, x0, x1, io);

@@ -52,7 +52,10 @@ struct ConvParams {
     const float* ddim_x;     // if non-null: out = coef[0]*ddim_x + coef[1]*value   (DDIM step epilogue)
     const float* ddim_coef;  // device [2]
     int B;
+    float* gn_rec;           // optional, narrow-input conv with Cout == 128 and Tout % 16 == 0 only (conv_narrow_in_gn_ok): GroupNorm
+                             // records (64, mean, M2) of the output per (sample, 16-position segment, 4-channel group): [B][Tout/16][32][3]
 };
+bool conv_narrow_in_gn_ok(const ConvParams& p);
 
 struct GnParams {
     const float* src0; const float* src1; int C0, C1;

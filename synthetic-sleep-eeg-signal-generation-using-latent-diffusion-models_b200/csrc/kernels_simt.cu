@@ -276,6 +276,49 @@ __global__ void __launch_bounds__(256) conv_narrow_in_kernel(const float* __rest
     }
 }
 
+// The same conv for Cout = 128 emitting the GroupNorm records of its output (the layout the tcgen05 conv epilogue writes: one
+// (count, mean, M2) per sample, 16-position segment and 4-channel group), so that input_blocks.1's norm and the last output block's
+// concat norm need no pass over the tensor.  One warp = one segment: lane = 4-channel group, 16 positions in sequence (512-byte
+// row stores), shifted one-pass sums per lane -- no cross-lane combination at all.
+__global__ void __launch_bounds__(256) conv_narrow_in_gn_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                                 const float* __restrict__ bias, float* __restrict__ out,
+                                                                 float* __restrict__ rec, int Cin, int T, int nsegs) {
+    constexpr int Cout = 128;
+    extern __shared__ float ws[];   // [Cin*3][Cout] + [Cout]
+    for (int i = threadIdx.x; i < Cin * 3 * Cout; i += blockDim.x) ws[i] = w[i];
+    for (int i = threadIdx.x; i < Cout; i += blockDim.x) ws[Cin * 3 * Cout + i] = bias ? bias[i] : 0.f;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, co = lane * 4;
+    const int wpb = blockDim.x >> 5;
+    const float4 b4 = *reinterpret_cast<const float4*>(ws + Cin * 3 * Cout + co);
+    for (int seg = blockIdx.x * wpb + (threadIdx.x >> 5); seg < nsegs; seg += gridDim.x * wpb) {
+        const size_t bt0 = (size_t)seg * 16;
+        const int t0 = (int)(bt0 % (size_t)T);                 // T % 16 == 0: a segment never straddles samples
+        float K = 0.f, s = 0.f, q = 0.f;
+#pragma unroll 4
+        for (int i = 0; i < 16; ++i) {
+            float4 acc = b4;
+            for (int k = 0; k < 3; ++k) {
+                const int u = t0 + i + k - 1;
+                if (u < 0 || u >= T) continue;
+                const float* xr = x + (bt0 + i + k - 1) * Cin;
+                for (int ci = 0; ci < Cin; ++ci) {
+                    const float xv = __ldg(xr + ci);
+                    const float4 wv = *reinterpret_cast<const float4*>(ws + (ci * 3 + k) * Cout + co);
+                    acc.x = fmaf(xv, wv.x, acc.x); acc.y = fmaf(xv, wv.y, acc.y); acc.z = fmaf(xv, wv.z, acc.z); acc.w = fmaf(xv, wv.w, acc.w);
+                }
+            }
+            *reinterpret_cast<float4*>(out + (bt0 + i) * Cout + co) = acc;
+            if (i == 0) K = acc.x;
+            const float d0 = acc.x - K, d1 = acc.y - K, d2 = acc.z - K, d3 = acc.w - K;
+            s += (d0 + d1) + (d2 + d3);
+            q = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, fmaf(d3, d3, q))));
+        }
+        float* o = rec + ((size_t)seg * 32 + lane) * 3;
+        o[0] = 64.f; o[1] = fmaf(s, 1.f / 64.f, K); o[2] = fmaxf(q - s * s * (1.f / 64.f), 0.f);
+    }
+}
+
 // Narrow-output conv (UNet output head, unet.py:501-505: Conv1d(model_channels -> z, 3, padding=1) on SiLU(GN(h)), z <= 4)
 // with the DDIM update in the epilogue: pure HBM-read bound.  One warp walks a strip of positions; each lane owns 4 of every
 // 128 input channels, applies the GroupNorm affine + SiLU once per element and scatters it into the 3 output rows it feeds;
@@ -908,6 +951,14 @@ __global__ void axpy_sampling_kernel(const float* __restrict__ mu, const float* 
 }  // namespace
 
 // ================================================================================================ launchers
+// can launch_conv_simt emit GroupNorm records for this conv (ConvParams.gn_rec)?  Mirrors the narrow-input branch below.
+bool conv_narrow_in_gn_ok(const ConvParams& p) {
+    const ConvSeg& s0 = p.seg[0];
+    return p.nseg == 1 && s0.taps == 3 && p.stride == 1 && p.pad_left == 1 && !s0.src1 && s0.resample == RS_NONE && !s0.silu && !p.temb &&
+           !p.res && p.Tc == p.Tout && s0.C0 <= 4 && !s0.scale && !p.ddim_x && p.Cout == 128 && p.Tout % 16 == 0 &&
+           (size_t)p.B * p.Tout < (1u << 31);
+}
+
 cudaError_t launch_conv_simt(const ConvParams& p, cudaStream_t st) {
     if (p.B <= 0) return cudaSuccess;
     const ConvSeg& s0 = p.seg[0];
@@ -917,6 +968,14 @@ cudaError_t launch_conv_simt(const ConvParams& p, cudaStream_t st) {
         (size_t)p.B * p.Tout < (1u << 31) && (size_t)(s0.C0 * 3 + 1) * p.Cout * sizeof(float) <= 40 * 1024) {
         const size_t total4 = (size_t)p.B * p.Tout * (p.Cout / 4);
         const size_t smem = ((size_t)s0.C0 * 3 * p.Cout + p.Cout) * sizeof(float);
+        if (p.gn_rec) {
+            if (p.Cout != 128 || p.Tout % 16) return cudaErrorInvalidValue;
+            const int nsegs = (int)((size_t)p.B * p.Tout / 16);
+            const unsigned nb = (unsigned)std::min<size_t>(((size_t)nsegs + 7) / 8, 148 * 16);
+            conv_narrow_in_gn_kernel<<<nb, 256, smem, st>>>(s0.src0, s0.w, p.bias, p.out, p.gn_rec, s0.C0, p.Tout, nsegs);
+            g_launch_count += 1;
+            return cudaGetLastError();
+        }
         const unsigned blocks = (unsigned)std::min<size_t>((total4 + 255) / 256, 148 * 16);
         conv_narrow_in_kernel<<<blocks, 256, smem, st>>>(s0.src0, s0.w, p.bias, p.out, s0.C0, p.Cout, p.Tout, total4);
         g_launch_count += 1;
