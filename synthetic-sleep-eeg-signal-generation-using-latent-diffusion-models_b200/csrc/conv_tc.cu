@@ -78,6 +78,13 @@ __device__ __forceinline__ float act(float x, float a, float s, int silu) {
     return silu == 1 ? silu_fast(v) : (silu == 2 ? (v > 0.f ? v : 0.2f * v) : v);
 }
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+// 8 consecutive floats (32-byte aligned) as ONE 256-bit load (LDG.E.256, sm_100): the fused producer's items are 8 channels wide,
+// and two 128-bit loads per item each fetch half of every 32-byte sector they touch -- twice the LSU wavefronts (ncu: 67 % LSU
+// utilisation, profiles/r02b_ncu_full_conv_pair_512.txt)
+__device__ __forceinline__ void ldg8(const float* p, float4& a, float4& b) {
+    asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+}
 // SiLU on the bare special-function instructions: v * rcp(1 + ex2(-v * log2 e)).  ex2.approx.ftz needs none of __expf's
 // denormal-range fix-ups (3 extra instructions per value): an underflowing exponential is 0 (v large: silu = v), an
 // overflowing one is +inf (v very negative: rcp = 0, silu = -0); both approximations are within 2 ulp, as before.
@@ -797,10 +804,10 @@ __global__ void __launch_bounds__(conv_tc_threads(DIRECT, EPI8), 1) conv_tc_kern
         auto issue = [&](const Cur& cu, Pre& P) {
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
-                if ((cu.ok >> j) & 1) { P.x[j][0] = ldg4(cu.row[j]); P.x[j][1] = ldg4(cu.row[j] + 4); }
+                if ((cu.ok >> j) & 1) ldg8(cu.row[j], P.x[j][0], P.x[j][1]);
                 else P.x[j][0] = P.x[j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            if (cu.sc) { P.a[0] = ldg4(cu.sc); P.a[1] = ldg4(cu.sc + 4); P.s[0] = ldg4(cu.sh); P.s[1] = ldg4(cu.sh + 4); }
+            if (cu.sc) { ldg8(cu.sc, P.a[0], P.a[1]); ldg8(cu.sh, P.s[0], P.s[1]); }
             else {
                 P.a[0] = P.a[1] = make_float4(1.f, 1.f, 1.f, 1.f);
                 P.s[0] = P.s[1] = make_float4(0.f, 0.f, 0.f, 0.f);

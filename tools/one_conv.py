@@ -14,11 +14,12 @@ ap.add_argument("--batch", type=int, default=1024)
 ap.add_argument("--fuse", type=int, default=15)
 ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--debug", type=int, default=0)
+ap.add_argument("--pair", type=int, default=1)
 a = ap.parse_args()
 torch.cuda.set_device(0)
 torch.zeros(1, device="cuda")
 L = eegldm.lib()
-_lib.check(L.eegldm_set_conv_tuning(0, 1, a.fuse))
+_lib.check(L.eegldm_set_conv_tuning(a.pair, 1, a.fuse))
 T, ci, co, k, res = a.shape
 m = C.c_float()
 _lib.check(L.eegldm_bench_conv(a.batch, T, ci, co, k, res, 1, a.debug, a.reps, C.byref(m), None))
