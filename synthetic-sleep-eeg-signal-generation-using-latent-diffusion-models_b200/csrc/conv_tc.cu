@@ -212,7 +212,9 @@ __global__ void __launch_bounds__(SPLIT_THREADS) act_split_kernel(const ActSplit
 // with two items each (512 threads, 232 / 88 registers) measured 6 % slower than six with three.  tools/producer_bench.py
 // (profiles/r01_producer_bench.txt) switches parts of the producer off: no single part dominates.  Interleaving the 1-tap
 // k-steps of a skip_connection segment with the 3-tap ones (so the ring averages their tensor time) measured 10 % SLOWER on the
-// two-segment layers and was dropped.
+// two-segment layers and was dropped.  Pulling the rows of the CTA's NEXT tile into L2 when a tile starts (prefetch.global.L2 per 128-byte line;
+// for the short-K level-0 tiles, whose k-step is shorter than a DRAM round trip) measured 5 % SLOWER on those layers (0.31 vs 0.29 ms):
+// they move 0.8-1.2 GB in 0.29-0.34 ms, i.e. they sit at ~55 % of the HBM peak with mixed reads and writes -- bandwidth, not latency.
 //
 // EPI8: two epilogue warpgroups instead of one.  With N = 256 in f16x3 the two accumulators fill TMEM, so the epilogue of a tile cannot
 // overlap the next mainloop and its duration is lost tensor time (10-17 k cycles per tile, 20-40 % on the K <= 1536 layers:
