@@ -40,7 +40,7 @@ def _peaks():
     return dict(hbm=6650.0, tc_burst=1590.0, tc_sustained=1400.0, src="fallback")   # B200_PROFILING.md fallback
 
 
-NCU_FORWARD_CSVS = ("r02_ncu_forward_b1024.csv", "r01_ncu_forward_b1024.csv")   # newest committed capture wins
+NCU_FORWARD_CSVS = ("r02b_ncu_forward_b1024.csv", "r02_ncu_forward_b1024.csv", "r01_ncu_forward_b1024.csv")   # newest committed capture wins
 
 
 def _ncu_conv_traffic(batch, math):
