@@ -60,21 +60,27 @@ int eegldm_set_sample_lanes(int lanes);
 /* Tuning knob of the tcgen05 conv kernel: CTAs per thread-block cluster that share each weight stage through a
  * multicast bulk copy (1, 2 or 4; default 2).  Changing it invalidates nothing but must not race with launches. */
 int eegldm_set_conv_cluster(int ctas);
-/* Shape selection of the tcgen05 conv kernel.  pair = 1: the two CTAs of a cluster issue one M=256 cta_group::2 MMA over
- * both (each stages half of the weight columns); pair = 0 (default, measured faster): single-CTA MMAs with the multicast
- * cluster of eegldm_set_conv_cluster.  bn256_min_stages (default 1): tiles are 256 output channels wide when Cout % 256 == 0
- * and a tile's mainloop has at least this many weight stages (else 128).  fuse_epilogues (bit mask, default 13):
+/* Shape selection of the tcgen05 conv kernel.  pair (bit mask, default 1): bit 0 -- the launches with 256-wide tiles run as CTA
+ * pairs: the two CTAs of a cluster issue one M=256 cta_group::2 MMA over both, each stages half of the weight columns, loads are
+ * cp.async.bulk.tensor.cta_group::2 completing on the leader's mbarrier; bit 1 -- the same for the 128-wide launches (measured
+ * slower: off); 0: single-CTA MMAs with the multicast cluster of eegldm_set_conv_cluster.
+ * bn256_min_stages (default 1): tiles are 256 output channels wide when Cout % 256 == 0 and a tile's mainloop has at least this
+ * many weight stages (else 128).  fuse_epilogues (bit mask, default 15):
  * bit 0 -- a conv whose output feeds a GroupNorm writes that GroupNorm's statistics from its epilogue (no separate pass);
+ * bit 1 -- an AttentionBlock's qkv conv writes the attention kernel's fp16 hi/lo operand images instead of fp32 (f16x3): no
+ *          qkv_split pass;
  * bit 2 -- the conv kernel's producer warps read the fp32 input and build the fp16 hi/lo operand tiles in shared memory
  *          themselves (GroupNorm apply + SiLU + nearest-x2 + split), replacing the act_split pre-pass and its U tensors;
- * bit 4 -- the tcgen05 attention kernel reads the fp32 qkv tensor and splits q, k, v to fp16 hi/lo in its own producer warps
- *          (no qkv_split pass); T <= 208; measured no faster (the kernel slows down by what the pass cost): off;
  * bit 3 -- the tcgen05 attention kernel writes its result as proj_out's operand image (no fp32 attention output, no pre-pass);
+ * bit 4 -- the tcgen05 attention kernel reads the fp32 qkv tensor and splits q, k, v to fp16 hi/lo in its own producer warps
+ *          (only without bit 1; T <= 208; measured no faster: off);
  * bit 5 -- (default clear) set to switch OFF the N = 128 tiles' concatenated MMA a_hi x [w_hi | w_lo] (one N = 256 instruction
  *          into both f16x3 accumulators instead of two N = 128 ones; same arithmetic, fewer shared-memory operand reads);
- * bit 1 -- an AttentionBlock's qkv conv writes the attention kernel's fp16 hi/lo operand images instead of fp32 (f16x3; measured no faster than the separate split pass).
  * bit 6 -- (default clear) set to switch OFF the two-warpgroup conv epilogue (eight warps draining the accumulators in 16-column
- *          chunks instead of four in 32-column chunks).
+ *          chunks instead of four in 32-column chunks; single-CTA launches only, CTA pairs always use it);
+ * bit 7 -- fused producer also for 1x1 convs with more than two N tiles (the qkv conv; measured slower: off);
+ * bit 8 -- (default clear) set for epilogue GroupNorm records at the consumer's group width instead of 4 / 8 channels (then the
+ *          concat norms with 12- / 24-channel groups need their own pass over the tensor again).
  * Call before creating models: plans cache the choices. */
 int eegldm_set_conv_tuning(int pair, int bn256_min_stages, int fuse_epilogues);
 
