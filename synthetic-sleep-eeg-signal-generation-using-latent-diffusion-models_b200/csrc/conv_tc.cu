@@ -4,12 +4,13 @@
 //     out[b,t,co] = bias[co] + temb[b,co] + res[b,t,co] + sum_seg sum_{k,ci} W_seg[co,ci,k] * u_seg[b, t+k-pad, ci]
 //     u = resample(silu?(scale*x + shift))           (GroupNorm apply + SiLU + AvgPool/nearest)
 // i.e. the same contract as conv_simt_kernel (reference: src/models/unet.py:263,291,302,158,161 + 308-327),
-// in two launches:
+// in one launch (fused-producer form, the default) or two (pre-pass form: AvgPool inputs, the qkv conv):
 //
-//   act_split_kernel   one pass over x: apply the GroupNorm affine / SiLU / resample, split every fp32 value into
+//   act_split_kernel   (pre-pass form only) one pass over x: apply the GroupNorm affine / SiLU / resample, split every fp32 value into
 //                      16-bit parts and write them as ready-made shared-memory tile images ("U" tensors).
-//   conv_tc_kernel     a pure async-copy + tcgen05 GEMM: M = 128 output positions, N = 128 output channels,
-//                      K = taps*Cin per CTA; both operands arrive by cp.async.bulk (UBLKCP), D lives in TMEM.
+//   conv_tc_kernel     tcgen05 GEMM: M = 128 output positions per CTA, N = 128 or 256 output channels, K = taps*Cin; weights arrive by
+//                      cp.async.bulk (single CTA) or cp.async.bulk.tensor (CTA pairs), activations from six producer warps that read
+//                      the fp32 source themselves (or by bulk copy of the U image), D lives in TMEM.
 //
 //   * fp32 parity on a 16-bit tensor pipe ("f16x3"): every fp32 operand is split x = hi + lo/2048 with hi and lo
 //     fp16 (11 + 11 significand bits, lo pre-scaled by 2^11 so it stays in fp16's normal range) and three products
@@ -18,19 +19,19 @@
 //     tools/conv_precision.py), which the separate correction accumulator keeps off the long chain.
 //     EEGLDM_MATH_BF16_TC issues a single bf16 product (fast, NOT a parity mode).
 //   * B operand = weights, pre-split and pre-packed on the host into the exact shared-memory image of one
-//     pipeline stage (K-major, no swizzle, 8x16-byte core matrices): a stage is ONE bulk copy.
+//     pipeline stage (K-major, no swizzle, 8x16-byte core matrices, [k-step][tap][hi|lo][Cout/8]: the columns of any tile
+//     width, or of one CTA of a pair, are one contiguous slice = one copy).
 //   * A operand = activations in a "phase-strided halo" K-major layout: the 128 M rows of a tile are 8 segments of
 //     16 consecutive positions; the 8 rows of one core matrix are the SAME offset in the 8 segments, and each
 //     segment carries its own 2 halo positions (18 slots).  A tap shift of +-1 position is then a whole-core-matrix
 //     shift = +-SBO bytes on the descriptor start address, so the 3 taps of a k=3 conv read ONE staged tile
 //     (12.5 % halo overhead instead of 3 copies).  Segments may belong to different samples; halos at sample
-//     edges are zero (the conv's padding).  U is stored [m_tile][k-step][hi|lo][kc][slot][segment][8 ch], i.e. one
-//     contiguous 18 KB block per (tile, k-step): ONE bulk copy per stage.
-//   * persistent, warp-specialised: one CTA per SM; warps 0-3 epilogue (TMEM -> registers -> global), then (fused-producer
-//     form) six producer warps, one loader warp, one MMA warp.  Tiles are 128 positions x 128 or 256 output channels
-//     (conv_tc_bn); rings: 4 x 18 KB activation + 128 KB of weight stages (pre-pass form) or 5 x 18 KB + 96 KB (fused-producer
-//     and CTA-pair forms), see ring_na / ring_b_bytes.  N = 128: two TMEM accumulator sets, the epilogue of tile i overlaps the
-//     mainloop of tile i+1; N = 256 in f16x3 fills all 512 TMEM columns (one set).
+//     edges are zero (the conv's padding).  Stage image: [hi|lo][kc][slot][segment][8 ch], 18 KB per (tile, k-step).
+//   * persistent, warp-specialised: one CTA per SM; 8 epilogue warps in two warpgroups (TMEM -> registers -> global; 4 in the
+//     one-warpgroup form kept for 32-channel GroupNorm groups), six producer warps (fused-producer form), one loader warp, one
+//     MMA warp.  Rings: 5 x 18 KB activation stages + 96 KB of weight stages (3 x 32 KB ... 12 x 8 KB).  N = 128: two TMEM
+//     accumulator sets, the epilogue of tile i overlaps the mainloop of tile i+1; N = 256 in f16x3 fills all 512 TMEM columns
+//     (one set).  The 256-wide launches run as cta_group::2 CTA pairs (M = 256 per MMA), see the kernel comment.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
