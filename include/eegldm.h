@@ -387,6 +387,10 @@ int eegldm_test_qkv_attention(const float* x_dev, const float* w_host, const flo
  * data of the given shape; debug 0 = real kernel, 1 = operand copies skipped, 2 = MMAs skipped (timing experiments). */
 int eegldm_bench_conv(int B, int T, int Cin, int Cout, int k, int with_res, int math, int debug, int reps, float* ms_out,
                       void* stream);
+/* Timing hook (tools/attn_timeline.py): average milliseconds of `reps` launches of the tcgen05 attention kernel (f16x3, output
+ * written as proj_out's operand image) on synthetic q, k, v; timeline_out (optional, [8]) receives per-CTA cycle averages
+ * {1 S phase, 2 softmax, 3 PV + epilogue, 4 total, 7 number of CTAs}. */
+int eegldm_bench_attention(int B, int T, int H, int ch, int reps, float* ms_out, double* timeline_out, void* stream);
 /* Same, followed by one launch with per-CTA cycle counters: timeline_out[16] receives, averaged over the CTAs that ran,
  * {0 total cycles, 1 MMA warp waiting for a free accumulator, 2 ... for an activation stage, 3 ... for a weight stage,
  *  4 epilogue waiting for a full accumulator, 5 epilogue busy, 6 producer waiting for a free stage, 7 producer busy,

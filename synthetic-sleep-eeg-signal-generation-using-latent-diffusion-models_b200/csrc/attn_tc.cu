@@ -116,6 +116,11 @@ __global__ void __launch_bounds__(DIRECT ? 2 * NUM_THREADS : NUM_THREADS, 1) att
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    // eegldm_bench_attention: per-CTA cycle stamps written by thread 0 (softmax warp 0): [0] start -> barriers ready, [1] -> scores
+    // complete (S phase), [2] -> P written (softmax), [3] -> last output chunk stored (PV + epilogue), [4] total
+    const bool tl = p.timeline != nullptr;
+    const long long tl0 = tl ? clock64() : 0;
+    long long tl1 = 0, tl2 = 0;
 
     if (warp < 4) {
         // ================================================================ softmax, then epilogue
@@ -125,6 +130,7 @@ __global__ void __launch_bounds__(DIRECT ? 2 * NUM_THREADS : NUM_THREADS, 1) att
         const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
         mbar_wait(barS, 0);
         tc_fence_after();
+        if (tl) tl1 = clock64();
         float mx = -INFINITY;
         for (int cb = 0; cb < T; cb += 32) {
             uint32_t v[32];
@@ -169,6 +175,7 @@ __global__ void __launch_bounds__(DIRECT ? 2 * NUM_THREADS : NUM_THREADS, 1) att
         fence_proxy_async_smem();      // P (generic-proxy stores) -> visible to the tensor core's async proxy
         tc_fence_before();             // the TMEM reads above are ordered before the MMAs that reuse the columns
         mbar_arrive(barP);
+        if (tl) tl2 = clock64();
         const float inv = 1.0f / sum;
         float* orow = p.out + ((size_t)b * T + t) * ((size_t)p.H * ch) + (size_t)h * ch;
         for (int c = 0; c < nchunk; ++c) {
@@ -214,6 +221,11 @@ __global__ void __launch_bounds__(DIRECT ? 2 * NUM_THREADS : NUM_THREADS, 1) att
             }
             tc_fence_before();
             mbar_arrive(barOempty + 8 * buf);
+        }
+        if (tl && tid == 0) {
+            unsigned long long* o = p.timeline + ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8;
+            const long long t3 = clock64();
+            o[1] = tl1 - tl0; o[2] = tl2 - tl1; o[3] = t3 - tl2; o[4] = t3 - tl0; o[5] = (unsigned long long)tl0;
         }
     } else if (DIRECT && warp >= 6) {
         // ================================================================ producers (192 threads): fp32 rows -> fp16 hi/lo stage images

@@ -2059,6 +2059,53 @@ int eegldm_bench_conv_timeline(int B, int T, int Cin, int Cout, int k, int with_
     return bench_conv_impl(B, T, Cin, Cout, k, with_res, math, debug, reps, ms_out, timeline_out, stream);
 }
 
+// Timing of the tcgen05 attention kernel on synthetic operand images (tools/attn_timeline.py): `reps` launches bracketed by CUDA
+// events, then one launch with per-CTA cycle stamps; timeline_out[8] = averages over the CTAs {1: S phase (start -> scores complete),
+// 2: softmax, 3: PV + epilogue, 4: total, 7: CTAs}.
+int eegldm_bench_attention(int B, int T, int H, int ch, int reps, float* ms_out, double* timeline_out, void* stream) {
+    if (!ms_out || reps <= 0) return fail(EEGLDM_ERR_INVALID, "bad argument");
+    if (!attn_tc_eligible(T, ch)) return fail(EEGLDM_ERR_SHAPE, "shape not eligible for the tcgen05 attention");
+    cudaStream_t st = (cudaStream_t)stream;
+    float* qkv = nullptr; uint8_t *q16 = nullptr, *ou = nullptr; unsigned long long* tl = nullptr;
+    const size_t nq = (size_t)B * T * H * 3 * ch;
+    const size_t nctas = (size_t)B * H * ((T + 127) / 128);
+    cudaError_t ce = cudaMalloc((void**)&qkv, nq * 4);
+    if (ce == cudaSuccess) ce = cudaMalloc((void**)&q16, attn_qkv16_bytes(B, T, H, ch));
+    if (ce == cudaSuccess) ce = cudaMalloc((void**)&ou, act_split_bytes((int)((long long)B * T / 16), H * ch));
+    if (ce == cudaSuccess) ce = cudaMalloc((void**)&tl, nctas * 8 * sizeof(unsigned long long));
+    if (ce == cudaSuccess) { bench_fill_kernel<<<1024, 256, 0, st>>>(qkv, nq, 7u); ce = launch_qkv_split(qkv, q16, B, T, H, ch, st); }
+    AttnTcParams tp{q16, nullptr, T, H, ch, B, 1.4426950408889634f / sqrtf((float)ch), ou, nullptr, nullptr};
+    if (ce == cudaSuccess) ce = launch_attention_tc(tp, true, st);   // warm-up
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (ce == cudaSuccess) ce = cudaEventCreate(&e0);
+    if (ce == cudaSuccess) ce = cudaEventCreate(&e1);
+    if (ce == cudaSuccess) ce = cudaEventRecord(e0, st);
+    for (int i = 0; i < reps && ce == cudaSuccess; ++i) ce = launch_attention_tc(tp, true, st);
+    if (ce == cudaSuccess) ce = cudaEventRecord(e1, st);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+    float ms = 0.f;
+    if (ce == cudaSuccess) ce = cudaEventElapsedTime(&ms, e0, e1);
+    *ms_out = ms / reps;
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (timeline_out && ce == cudaSuccess) {
+        ce = cudaMemsetAsync(tl, 0, nctas * 8 * sizeof(unsigned long long), st);
+        tp.timeline = tl;
+        if (ce == cudaSuccess) ce = launch_attention_tc(tp, true, st);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+        std::vector<unsigned long long> hst(nctas * 8);
+        if (ce == cudaSuccess) ce = cudaMemcpy(hst.data(), tl, hst.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+        for (int j = 0; j < 8; ++j) timeline_out[j] = 0.0;
+        for (size_t c = 0; c < nctas; ++c)
+            for (int j = 1; j < 5; ++j) timeline_out[j] += (double)hst[c * 8 + j];
+        for (int j = 1; j < 5; ++j) timeline_out[j] /= (double)nctas;
+        timeline_out[7] = (double)nctas;
+    }
+    cudaFree(qkv); cudaFree(q16); cudaFree(ou); cudaFree(tl);
+    if (ce != cudaSuccess) return cuda_fail(ce, "attention bench");
+    return EEGLDM_OK;
+}
+
 // One attention launch (QKVAttentionLegacy.forward) on channels-last qkv [B][T][H*3*ch] -> out [B][T][H*ch].
 int eegldm_test_attention(const float* qkv_dev, int B, int T, int H, int ch, int math, float* out_dev, void* stream) {
     if (!qkv_dev || !out_dev) return fail(EEGLDM_ERR_INVALID, "null argument");

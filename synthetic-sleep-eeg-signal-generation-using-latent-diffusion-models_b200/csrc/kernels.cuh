@@ -156,6 +156,7 @@ struct AttnTcParams {
                             // proj_out conv (conv_tc.cu layout, T % 16 == 0) instead of fp32
     const float* qkv32;     // optional (then `qkv16` is unused): fp32 qkv [B][T][H*3*ch]; q, k, v are split to fp16 hi/lo inside the
                             // kernel (attn_direct_eligible), no launch_qkv_split pass
+    unsigned long long* timeline;   // optional (eegldm_bench_attention): 8 cycle counters per CTA, see attn_tc.cu
 };
 bool attn_tc_eligible(int T, int ch);
 bool attn_direct_eligible(int T, int ch);   // in-kernel fp32 -> fp16 hi/lo split of q, k, v (T <= 208)

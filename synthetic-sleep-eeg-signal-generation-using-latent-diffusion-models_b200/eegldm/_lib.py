@@ -104,6 +104,7 @@ SIGNATURES = {
     "eegldm_unet_forward_devt": (C.c_int, [_P, _P, _P, C.c_int, _P, C.c_int, C.c_int, _P]),
     "eegldm_unet_range_status": (C.c_int, [_P, C.POINTER(C.c_int)]),
     "eegldm_bench_conv_timeline": (C.c_int, [C.c_int] * 9 + [_P, C.POINTER(C.c_double), _P]),
+    "eegldm_bench_attention": (C.c_int, [C.c_int] * 5 + [_P, C.POINTER(C.c_double), _P]),
     "eegldm_aekl_create": (C.c_int, [C.POINTER(AeklCfg), C.POINTER(_P)]),
     "eegldm_aekl_destroy": (None, [_P]),
     "eegldm_aekl_num_params": (C.c_int, [_P]),
