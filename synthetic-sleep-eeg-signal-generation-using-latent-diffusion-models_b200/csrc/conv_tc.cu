@@ -322,17 +322,23 @@ __global__ void __launch_bounds__(conv_tc_threads(DIRECT, EPI8), 1) conv_tc_kern
                 // of a core matrix; one lane permutation (16 shuffles) makes them ADJACENT lanes, so that each quarter-warp phase
                 // of a 128-bit store covers two 64-byte runs instead of eight 16-byte pieces of eight lines (measured: 5.8 k
                 // cycles of stores per tile in the unpermuted form vs 3.9 k for everything else, tools/conv_timeline.py).
-                const int sg = lane >> 2, pos = ew * 4 + (lane & 3);          // (segment, position) this lane STORES
-                const int src_lane = ((lane & 3) << 3) | (lane >> 2);          // the lane whose TMEM row that is
-                const int g = m_tile * 8 + sg;
-                const bool valid = g < p.nsegs16;
-                const int b = valid ? g / spt : 0, t = (g % spt) * 16 + pos;
                 const int ch = p.qkv_ch, T = p.Tout;
                 const int cq = co0 / (3 * ch), rem = co0 - cq * 3 * ch, which = rem / ch, c0 = rem - which * ch;   // head, q|k|v, channel
-                const size_t half = which < 2 ? (size_t)T * 64 : 8192;
-                uint8_t* base = p.qkv16 + (((size_t)b * p.qkv_H + cq) * 3 + which) * ((size_t)4 * ch * T) +
-                                (which < 2 ? (size_t)(t >> 3) * 512 + (t & 7) * 16
-                                           : (size_t)(t >> 5) * 2 * half + ((t & 31) >> 3) * 2048 + (t & 7) * 16);
+                // Q keeps the TMEM lane order (the Q image's rows are phase-strided like this tile: attn_tc.cu): lane = (slot, segment)
+                // with the segment fastest, eight consecutive lanes store one 128-byte core-matrix row set.  K and V lanes are permuted.
+                const bool isq = which == 0;
+                const int sg = isq ? (lane & 7) : (lane >> 2), pos = ew * 4 + (isq ? (lane >> 3) : (lane & 3));   // (segment, position) this lane STORES
+                const int src_lane = ((lane & 3) << 3) | (lane >> 2);          // K, V: the lane whose TMEM row that is
+                const int g = m_tile * 8 + sg;
+                const bool valid = g < p.nsegs16;
+                const int b = valid ? g / spt : 0, s_in = g % spt, t = s_in * 16 + pos;
+                const int Tq = (T + 127) / 128 * 128;
+                const size_t plane = (size_t)4 * ch * T, planeq = (size_t)4 * ch * Tq;
+                const size_t half = isq ? (size_t)Tq * 64 : (which == 1 ? (size_t)T * 64 : 8192);
+                uint8_t* base = p.qkv16 + ((size_t)b * p.qkv_H + cq) * (planeq + 2 * plane) + (isq ? 0 : planeq + (size_t)(which - 1) * plane) +
+                                (isq ? (size_t)((s_in >> 3) * 16 + pos) * 512 + (s_in & 7) * 16
+                                     : (which == 1 ? (size_t)(t >> 3) * 512 + (t & 7) * 16
+                                                   : (size_t)(t >> 5) * 2 * half + ((t & 31) >> 3) * 2048 + (t & 7) * 16));
                 const float* bias_p = p.bias && !(p.debug & 512) ? p.bias + co0 : nullptr;
                 const bool do_store = valid && !(p.debug & 256);   // (debug bits 256 / 512: timing experiments, tools/conv_timeline.py)
                 TL_WAIT(tl_a, mbar_wait(barAccFull + 8 * as, use & 1));
@@ -372,10 +378,12 @@ __global__ void __launch_bounds__(conv_tc_threads(DIRECT, EPI8), 1) conv_tc_kern
                         bad |= out_of_f16_range(v8);
                         split8_f16(v8, pc[2 * it], pc[2 * it + 1]);
                     }
+                    if (!isq) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        pc[j].x = __shfl_sync(0xffffffffu, pc[j].x, src_lane); pc[j].y = __shfl_sync(0xffffffffu, pc[j].y, src_lane);
-                        pc[j].z = __shfl_sync(0xffffffffu, pc[j].z, src_lane); pc[j].w = __shfl_sync(0xffffffffu, pc[j].w, src_lane);
+                        for (int j = 0; j < 4; ++j) {
+                            pc[j].x = __shfl_sync(0xffffffffu, pc[j].x, src_lane); pc[j].y = __shfl_sync(0xffffffffu, pc[j].y, src_lane);
+                            pc[j].z = __shfl_sync(0xffffffffu, pc[j].z, src_lane); pc[j].w = __shfl_sync(0xffffffffu, pc[j].w, src_lane);
+                        }
                     }
                     if (do_store) {
                         *reinterpret_cast<uint4*>(dst) = pc[0];
@@ -643,46 +651,8 @@ __global__ void __launch_bounds__(conv_tc_threads(DIRECT, EPI8), 1) conv_tc_kern
                     const float4 tb = Tm[i & 1];
                     const float4 o = make_float4(a.x + bias4.x + tb.x + R[i].x, a.y + bias4.y + tb.y + R[i].y,
                                                  a.z + bias4.z + tb.z + R[i].z, a.w + bias4.w + tb.w + R[i].w);
-                    if (!p.qkv16 && rb[i & 1] >= 0) *reinterpret_cast<float4*>(p.out + OOFF(i) + cb) = o;
+                    if (rb[i & 1] >= 0) *reinterpret_cast<float4*>(p.out + OOFF(i) + cb) = o;
                     O[i] = o;
-                }
-                if (p.qkv16) {
-                    // qkv conv of an AttentionBlock (unet.py:158): write q, k, v straight into the fp16 hi/lo operand images
-                    // of attn_tc.cu (layout: qkv_split_kernel) instead of fp32 -- the attention kernel's only input.
-                    const int ch = p.qkv_ch, T = p.Tout;
-                    const int cq = co / (3 * ch), rem = co - cq * 3 * ch, which = rem / ch, c = rem - which * ch;   // head, q|k|v, channel
-                    const size_t plane = (size_t)4 * ch * T;
-                    const size_t half = which < 2 ? (size_t)T * 64 : 8192;
-                    const int c8 = c & ~7;                      // the 8-channel item this lane pair (2m, 2m+1) fills together
-                    const size_t cpart = which < 2 ? (size_t)(c8 >> 5) * 2 * half + ((c8 & 31) >> 3) * 128
-                                                   : (size_t)(c8 >> 7) * (T >> 5) * 2 * half + ((c8 & 127) >> 3) * 128;
-                    // Full 32-byte sectors per store instruction (an 8-byte scatter makes L2 read-modify-write every sector):
-                    // the even lane of a pair holds channels 0-3 and the odd lane channels 4-7 of the item, for the same four
-                    // positions.  Per position pair (2pp, 2pp+1) the lanes swap halves, so the even lane owns the whole
-                    // 16-byte item of the even position and the odd lane that of the odd position -- adjacent in the image.
-                    const bool odd = lane & 1;
-#pragma unroll
-                    for (int h = 0; h < 2; ++h)
-#pragma unroll
-                        for (int pp = 0; pp < 2; ++pp) {
-                            uint2 hi0, lo0, hi1, lo1;
-                            split4_f16(O[2 * (2 * pp) + h], hi0, lo0);        // position 2pp     (row i = 2j + h)
-                            split4_f16(O[2 * (2 * pp + 1) + h], hi1, lo1);    // position 2pp + 1
-                            const uint2 sh = odd ? hi0 : hi1, sl = odd ? lo0 : lo1;     // what the partner needs
-                            uint2 rh, rl;
-                            rh.x = __shfl_xor_sync(0xffffffffu, sh.x, 1); rh.y = __shfl_xor_sync(0xffffffffu, sh.y, 1);
-                            rl.x = __shfl_xor_sync(0xffffffffu, sl.x, 1); rl.y = __shfl_xor_sync(0xffffffffu, sl.y, 1);
-                            const uint2 mh = odd ? hi1 : hi0, ml = odd ? lo1 : lo0;
-                            const uint4 ihi = odd ? make_uint4(rh.x, rh.y, mh.x, mh.y) : make_uint4(mh.x, mh.y, rh.x, rh.y);
-                            const uint4 ilo = odd ? make_uint4(rl.x, rl.y, ml.x, ml.y) : make_uint4(ml.x, ml.y, rl.x, rl.y);
-                            if (rb[h] < 0) continue;
-                            const int t = rt[h] + 2 * pp + (odd ? 1 : 0);
-                            const size_t tpart = which < 2 ? (size_t)(t >> 3) * 512 + (t & 7) * 16
-                                                           : (size_t)(t >> 5) * 2 * half + ((t & 31) >> 3) * 2048 + (t & 7) * 16;
-                            uint8_t* dst = p.qkv16 + (((size_t)rb[h] * p.qkv_H + cq) * 3 + which) * plane + cpart + tpart;
-                            *reinterpret_cast<uint4*>(dst) = ihi;
-                            *reinterpret_cast<uint4*>(dst + half) = ilo;
-                        }
                 }
                 if (p.gn_partial) {
                     // GroupNorm statistics of the tensor being written (the consumer's Normalize, unet.py:71-74): this thread
@@ -1175,7 +1145,8 @@ cudaError_t launch_conv_tc(const TcConvParams& p_in, bool x3, cudaStream_t st) {
     cudaError_t e;
     // two-warpgroup epilogue (EPI8): every launch except the ones whose epilogue emits 32-channel GroupNorm groups or bf16-mode
     // attention operand images (one-warpgroup epilogue only); cluster sizes 1 and 2
-    const bool epi8_ok = !(p.qkv16 && !x3) && !(p.gn_partial && p.gn_cpg == 32);
+    if (p.qkv16 && (!x3 || p.gn_partial)) return cudaErrorInvalidValue;   // operand-image output: f16x3, two-warpgroup epilogue only
+    const bool epi8_ok = !(p.gn_partial && p.gn_cpg == 32);
     // CTA pairs (cta_group::2): g_conv_tc_pair bit 0 = the N = 256 launches, bit 1 = the N = 128 launches
     const bool pair = epi8_ok && ((p.bn == 256 && (g_conv_tc_pair & 1)) || (p.bn == 128 && (g_conv_tc_pair & 2)));
     if (pair) {
@@ -1194,7 +1165,7 @@ cudaError_t launch_conv_tc(const TcConvParams& p_in, bool x3, cudaStream_t st) {
         g_launch_count += 1;
         return cudaGetLastError();
     }
-    const bool epi8 = g_conv_tc_epi8 && epi8_ok && (p.direct || g_conv_tc_cluster == 2 || g_conv_tc_cluster == 1);
+    const bool epi8 = (g_conv_tc_epi8 || p.qkv16) && epi8_ok && (p.direct || g_conv_tc_cluster == 2 || g_conv_tc_cluster == 1 || p.qkv16);
 #define EEGLDM_TC8(X3, BN)                                                                               \
     (p.direct ? (g_conv_tc_cluster == 1 ? launch_conv_tc_t<X3, BN, 1, false, true, true>(p, num_sms, st)   \
                                         : launch_conv_tc_t<X3, BN, 2, false, true, true>(p, num_sms, st))  \
