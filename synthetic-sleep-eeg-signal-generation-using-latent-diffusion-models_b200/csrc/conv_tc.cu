@@ -452,7 +452,8 @@ __global__ void __launch_bounds__(conv_tc_threads(DIRECT, EPI8), 1) conv_tc_kern
                         R[i] = make_float4(0.5f * (R[i].x + x1.x), 0.5f * (R[i].y + x1.y), 0.5f * (R[i].z + x1.z), 0.5f * (R[i].w + x1.w));
                     }
                 }
-                const float4 bias4 = biasn, Tm = Tmn;
+                // bias + time embedding once per chunk; the residual add only where there is one (three adds per value -> one or two)
+                const float4 bt = make_float4(biasn.x + Tmn.x, biasn.y + Tmn.y, biasn.z + Tmn.z, biasn.w + Tmn.w);
                 if (cb + 16 < HC) {
                     if (p.res) load_res(cb + 16, Rn);
                     if (bias_p) biasn = ldg4(bias_p + cb + 16);
@@ -486,8 +487,8 @@ __global__ void __launch_bounds__(conv_tc_threads(DIRECT, EPI8), 1) conv_tc_kern
                 for (int i = 0; i < 4; ++i) {
                     const int row = 8 * i + seg;
                     const float4 a = *reinterpret_cast<const float4*>(stg + row * 16 + 4 * (quad ^ ((row >> 1) & 3)));
-                    const float4 o = make_float4(a.x + bias4.x + Tm.x + R[i].x, a.y + bias4.y + Tm.y + R[i].y,
-                                                 a.z + bias4.z + Tm.z + R[i].z, a.w + bias4.w + Tm.w + R[i].w);
+                    float4 o = make_float4(a.x + bt.x, a.y + bt.y, a.z + bt.z, a.w + bt.w);
+                    if (p.res) o = make_float4(o.x + R[i].x, o.y + R[i].y, o.z + R[i].z, o.w + R[i].w);
                     if (rb >= 0) *reinterpret_cast<float4*>(p.out + OOFF(i) + cb) = o;
                     O[i] = o;
                 }
