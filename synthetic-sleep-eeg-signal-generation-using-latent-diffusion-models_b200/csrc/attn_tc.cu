@@ -38,7 +38,7 @@ __host__ __device__ inline int attn_tq(int T) { return (T + 127) / 128 * 128; } 
 __host__ __device__ inline int stage_bytes(int T) { return 2 * Q_HALF + 2 * T * 64; }   // Q hi/lo + K hi/lo of one 32-ch k-step
 __host__ __device__ inline int p_half_bytes(int T) { return (T / 8) * 2048; }           // P hi (or lo): [T/8][16][8][8] fp16
 __host__ __device__ inline int attn_stages(int T) {
-    const int n = (227 * 1024 - 2 * p_half_bytes(T) - 256) / stage_bytes(T);
+    const int n = (227 * 1024 - 2 * p_half_bytes(T) - 256 - 2048) / stage_bytes(T);   // 256 B barriers + 2 KB row max / sum exchange
     return n > 4 ? 4 : n;
 }
 
@@ -100,16 +100,27 @@ __global__ void qkv_split_kernel(const float* __restrict__ qkv, uint8_t* __restr
 // is in flight in registers while the previous one is split.  Lane mapping: S stages -- 4 consecutive lanes cover one row's
 // 32 channels (128 contiguous bytes in, 8 rows x 64 B = 512 contiguous bytes of the image out per warp); PV stages -- a warp
 // covers 8 keys x 4 channel groups, which is conflict-free on the MN-major V image (4 x 128 contiguous bytes).
+// Softmax / epilogue warps: ONE warpgroup leaves every TMEM load -> exp2 / split -> store chain exposed (one warp per scheduler);
+// the pre-split form runs TWO (warps 0-3 and 6-9), each taking half of the score columns in the softmax (row maxima and sums are
+// exchanged through 2 KB of shared memory) and half of every 128-channel output chunk in the epilogue (tools/attn_timeline.py:
+// PV + epilogue 24.9 k -> see profiles/r02b_attn_timeline.txt).  The in-kernel-split form keeps one (warps 6-11 are its producers).
+constexpr int ATTN_THREADS = 320;   // pre-split form: 4 softmax + loader + MMA issuer + 4 softmax
 template <bool X3, bool DIRECT>
-__global__ void __launch_bounds__(DIRECT ? 2 * NUM_THREADS : NUM_THREADS, 1) attn_tc_kernel(const AttnTcParams p) {
+__global__ void __launch_bounds__(DIRECT ? 2 * NUM_THREADS : ATTN_THREADS, 1) attn_tc_kernel(const AttnTcParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int T = p.T, ch = p.ch;
     const int SB = stage_bytes(T), PH = p_half_bytes(T), NST = attn_stages(T);
     const uint32_t sbase = smem_u32(smem);
     const uint32_t sStage = sbase, sP = sbase + NST * SB, bars = sP + 2 * PH;
-    const uint32_t barFull = bars, barEmpty = bars + 8 * NST, barS = bars + 16 * NST, barP = barS + 8, barOfull = barP + 8,
-                   barOempty = barOfull + 16;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + NST * SB + 2 * PH + 16 * NST + 48);
+    // Stage slots.  The S phase streams 40 KB per k-step and is bound by the load round trip; the two P buffers are idle until the
+    // scores are complete, so (pre-split form) the S phase also uses them as stage slots NST .. NSS-1.  The PV phase uses slots
+    // 0 .. NST-1 only and packs VP = 2 of its 16 KB V stages into one slot when the slot is big enough (T >= 128).
+    const int NSS = DIRECT ? NST : NST + (2 * PH) / SB;          // <= NST + 2
+    const int VP = (!DIRECT && SB >= 4 * V_HALF) ? 2 : 1;
+    const uint32_t barFull = bars, barEmpty = bars + 8 * 6, barS = bars + 16 * 6, barP = barS + 8, barOfull = barP + 8,
+                   barOempty = barOfull + 16;                     // (room for 6 stage barriers each: NST <= 4, + 2)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + NST * SB + 2 * PH + 16 * 6 + 48);
+    auto slot_addr = [&](int i) -> uint32_t { return i < NST ? sStage + i * SB : sP + (i - NST) * SB; };
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int mt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -120,10 +131,10 @@ __global__ void __launch_bounds__(DIRECT ? 2 * NUM_THREADS : NUM_THREADS, 1) att
     const uint8_t* gv = gk + plane;
 
     if (tid == 0) {
-        for (int i = 0; i < NST; ++i) { mbar_init(barFull + 8 * i, DIRECT ? NUM_THREADS : 1); mbar_init(barEmpty + 8 * i, 1); }
+        for (int i = 0; i < NSS; ++i) { mbar_init(barFull + 8 * i, DIRECT ? NUM_THREADS : 1); mbar_init(barEmpty + 8 * i, 1); }
         mbar_init(barS, 1);
-        mbar_init(barP, 128);
-        for (int i = 0; i < 2; ++i) { mbar_init(barOfull + 8 * i, 1); mbar_init(barOempty + 8 * i, 128); }
+        mbar_init(barP, DIRECT ? 128 : 256);
+        for (int i = 0; i < 2; ++i) { mbar_init(barOfull + 8 * i, 1); mbar_init(barOempty + 8 * i, DIRECT ? 128 : 256); }
         fence_mbar_init();
     }
     if (warp == 5) tmem_alloc(smem_u32(tmem_slot), 512);
@@ -137,17 +148,24 @@ __global__ void __launch_bounds__(DIRECT ? 2 * NUM_THREADS : NUM_THREADS, 1) att
     const long long tl0 = tl ? clock64() : 0;
     long long tl1 = 0, tl2 = 0;
 
-    if (warp < 4) {
-        // ================================================================ softmax, then epilogue
-        const int row = warp * 32 + lane;                         // MMA row = TMEM lane: (slot = row / 8, segment = row % 8) of the tile
+    if (warp < 4 || (!DIRECT && warp >= 6)) {
+        // ================================================================ softmax, then epilogue (one or two warpgroups)
+        constexpr int NWG = DIRECT ? 1 : 2;
+        const int wg = warp < 4 ? 0 : 1;                            // column half this warpgroup takes
+        const int row = (warp & 3) * 32 + lane;                    // MMA row = TMEM lane (a warp reads the lane quarter warp % 4):
+                                                                   // (slot = row / 8, segment = row % 8) of the tile
         const int t = mt * 128 + (row & 7) * 16 + (row >> 3);     // its position (Q image row order, see the file comment)
         const bool rowv = t < T;
-        const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+        const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+        float* xmax = reinterpret_cast<float*>(smem + NST * SB + 2 * PH + 256);   // [2][128] row maxima, then [2][128] row sums
+        float* xsum = xmax + 256;
+        const int c_mid = NWG == 1 ? nss : (nss + 1) / 2;
+        const int cb0 = (wg == 0 ? 0 : c_mid) * 32, cb1 = (wg == 0 ? c_mid : nss) * 32;   // this warpgroup's score columns
         mbar_wait(barS, 0);
         tc_fence_after();
         if (tl) tl1 = clock64();
         float mx = -INFINITY;
-        for (int cb = 0; cb < T; cb += 32) {
+        for (int cb = cb0; cb < cb1; cb += 32) {
             uint32_t v[32];
             tmem_ld32(lane_addr + cb, v);
             if (X3) {
@@ -159,11 +177,16 @@ __global__ void __launch_bounds__(DIRECT ? 2 * NUM_THREADS : NUM_THREADS, 1) att
 #pragma unroll
             for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
         }
+        if (NWG == 2) {
+            xmax[wg * 128 + row] = mx;
+            asm volatile("bar.sync 2, 256;" ::: "memory");
+            mx = fmaxf(xmax[row], xmax[128 + row]);
+        }
         float sum = 0.f;
         const float sc = p.scale_log2e;               // ch^-1/2 * log2(e): scores are (q.k) * ch^-1/2 (unet.py:119-121)
         const float mxs = mx * sc;
         uint8_t* prow = smem + NST * SB + (row >> 3) * 128 + (row & 7) * 16;
-        for (int cb = 0; cb < T; cb += 32) {
+        for (int cb = cb0; cb < cb1; cb += 32) {
             uint32_t v[32];
             tmem_ld32(lane_addr + cb, v);
             if (X3) {
@@ -190,15 +213,21 @@ __global__ void __launch_bounds__(DIRECT ? 2 * NUM_THREADS : NUM_THREADS, 1) att
         fence_proxy_async_smem();      // P (generic-proxy stores) -> visible to the tensor core's async proxy
         tc_fence_before();             // the TMEM reads above are ordered before the MMAs that reuse the columns
         mbar_arrive(barP);
+        if (NWG == 2) {
+            xsum[wg * 128 + row] = sum;
+            asm volatile("bar.sync 2, 256;" ::: "memory");
+            sum = xsum[row] + xsum[128 + row];
+        }
         if (tl) tl2 = clock64();
         const float inv = 1.0f / sum;
         float* orow = p.out + ((size_t)b * T + t) * ((size_t)p.H * ch) + (size_t)h * ch;
+        const int ob0 = NWG == 1 ? 0 : wg * 64, ob1 = NWG == 1 ? 128 : ob0 + 64;   // this warpgroup's columns of every output chunk
         for (int c = 0; c < nchunk; ++c) {
             const int buf = c & 1;
             mbar_wait(barOfull + 8 * buf, (c >> 1) & 1);
             tc_fence_after();
 #pragma unroll 1
-            for (int cb = 0; cb < 128; cb += 32) {
+            for (int cb = ob0; cb < ob1; cb += 32) {
                 uint32_t v[32];
                 tmem_ld32(lane_addr + buf * 256 + cb, v);
                 if (X3) {
@@ -209,7 +238,8 @@ __global__ void __launch_bounds__(DIRECT ? 2 * NUM_THREADS : NUM_THREADS, 1) att
                 }
                 if (rowv && p.out_u) {
                     // proj_out's operand image (conv_tc.cu U layout, 1x1 conv: halo slots are never read): this row is slot
-                    // t%16 + 1 of 16-position segment b*T/16 + t/16; 8 channels = one 16-byte item per hi / lo half
+                    // t%16 + 1 of 16-position segment b*T/16 + t/16; 8 channels = one 16-byte item per hi / lo half.  Eight
+                    // consecutive lanes are the eight segments of one slot: one whole 128-byte line per store.
                     const int g16 = b * (T >> 4) + (t >> 4);
                     uint8_t* ub = p.out_u + (size_t)(g16 >> 3) * ((size_t)p.H * ch / 32) * (2 * TC_U_HALF_BYTES) +
                                   ((t & 15) + 1) * 128 + (g16 & 7) * 16;
@@ -316,14 +346,15 @@ __global__ void __launch_bounds__(DIRECT ? 2 * NUM_THREADS : NUM_THREADS, 1) att
     } else if (warp == 4) {
         // ================================================================ loader (pre-split images; idle in the DIRECT form)
         if (lane == 0 && !DIRECT) {
-            int it = 0;
+            uint32_t phE = 0;   // bit i: parity of the completed waits on slot i's "empty" barrier
             const uint32_t qb = Q_HALF, kb = (uint32_t)T * 64;   // a whole 128-row Q tile (rows past T: never-written scratch, their
                                                                    // scores and outputs are computed and dropped)
             const size_t qhalf = (size_t)attn_tq(T) * 64;
-            for (int ks = 0; ks < nks; ++ks, ++it) {
-                const int st = it % NST;
-                const uint32_t dst = sStage + st * SB;
-                mbar_wait(barEmpty + 8 * st, ((it / NST) & 1) ^ 1);
+            for (int ks = 0; ks < nks; ++ks) {
+                const int st = ks % NSS;
+                const uint32_t dst = slot_addr(st);
+                mbar_wait(barEmpty + 8 * st, ((phE >> st) & 1) ^ 1);
+                phE ^= 1u << st;
                 mbar_arrive_expect_tx(barFull + 8 * st, X3 ? 2 * (qb + kb) : qb + kb);
                 const uint8_t* qs = gq + ((size_t)ks * 2) * qhalf + (size_t)mt * 16 * 512;
                 const uint8_t* ks_ = gk + ((size_t)ks * 2) * kb;
@@ -334,13 +365,20 @@ __global__ void __launch_bounds__(DIRECT ? 2 * NUM_THREADS : NUM_THREADS, 1) att
                     bulk_copy_g2s(dst + 2 * Q_HALF + kb, ks_ + kb, kb, barFull + 8 * st);
                 }
             }
+            int it = 0;
             for (int c = 0; c < nchunk; ++c)
-                for (int ss = 0; ss < nss; ++ss, ++it) {
-                    const int st = it % NST;
-                    mbar_wait(barEmpty + 8 * st, ((it / NST) & 1) ^ 1);
-                    const uint32_t bytes = X3 ? 2 * V_HALF : V_HALF;
-                    mbar_arrive_expect_tx(barFull + 8 * st, bytes);
-                    bulk_copy_g2s(sStage + st * SB, gv + ((size_t)c * nss + ss) * 2 * V_HALF, bytes, barFull + 8 * st);
+                for (int ss = 0; ss < nss; ss += VP, ++it) {
+                    const int st = it % NST, n = min(VP, nss - ss);
+                    mbar_wait(barEmpty + 8 * st, ((phE >> st) & 1) ^ 1);
+                    phE ^= 1u << st;
+                    const uint8_t* src = gv + ((size_t)c * nss + ss) * 2 * V_HALF;
+                    if (X3) {   // hi and lo of n consecutive 32-key stages are contiguous in the V image: one copy
+                        mbar_arrive_expect_tx(barFull + 8 * st, (uint32_t)n * 2 * V_HALF);
+                        bulk_copy_g2s(slot_addr(st), src, (uint32_t)n * 2 * V_HALF, barFull + 8 * st);
+                    } else {
+                        mbar_arrive_expect_tx(barFull + 8 * st, (uint32_t)n * V_HALF);
+                        for (int u = 0; u < n; ++u) bulk_copy_g2s(slot_addr(st) + u * 2 * V_HALF, src + (size_t)u * 2 * V_HALF, V_HALF, barFull + 8 * st);
+                    }
                 }
         }
     } else {
@@ -348,13 +386,14 @@ __global__ void __launch_bounds__(DIRECT ? 2 * NUM_THREADS : NUM_THREADS, 1) att
         if (lane == 0) {
             const uint32_t idescS = make_idesc(0u, 128u, (uint32_t)T);
             constexpr uint32_t idescO = make_idesc(0u, 128u, 128u, 1u);   // B (= V) is MN-major
-            int it = 0;
+            uint32_t phF = 0;   // bit i: parity of the next wait on slot i's "full" barrier
             uint32_t acc = 0, acc2 = 0;
-            for (int ks = 0; ks < nks; ++ks, ++it) {
-                const int st = it % NST;
-                mbar_wait(barFull + 8 * st, (it / NST) & 1);
+            for (int ks = 0; ks < nks; ++ks) {
+                const int st = ks % NSS;
+                mbar_wait(barFull + 8 * st, (phF >> st) & 1);
+                phF ^= 1u << st;
                 tc_fence_after();
-                const uint32_t q_hi = sStage + st * SB, q_lo = q_hi + Q_HALF, k_hi = q_hi + 2 * Q_HALF, k_lo = k_hi + T * 64;
+                const uint32_t q_hi = slot_addr(st), q_lo = q_hi + Q_HALF, k_hi = q_hi + 2 * Q_HALF, k_lo = k_hi + T * 64;
 #pragma unroll
                 for (int kk = 0; kk < 2; ++kk) {
                     const uint64_t dah = make_desc(q_hi + kk * 256, 128, 512), dbh = make_desc(k_hi + kk * 256, 128, 512);
@@ -372,27 +411,31 @@ __global__ void __launch_bounds__(DIRECT ? 2 * NUM_THREADS : NUM_THREADS, 1) att
             umma_commit(barS);
             mbar_wait(barP, 0);
             tc_fence_after();
+            int it = DIRECT ? nks : 0;   // (in-kernel-split form: its producers walk one slot sequence through both phases)
             for (int c = 0; c < nchunk; ++c) {
                 const int buf = c & 1;
                 mbar_wait(barOempty + 8 * buf, ((c >> 1) & 1) ^ 1);
                 tc_fence_after();
                 uint32_t a0 = 0, a1 = 0;
-                for (int ss = 0; ss < nss; ++ss, ++it) {
-                    const int st = it % NST;
-                    mbar_wait(barFull + 8 * st, (it / NST) & 1);
+                for (int ss = 0; ss < nss; ss += VP, ++it) {
+                    const int st = it % NST, n = min(VP, nss - ss);
+                    mbar_wait(barFull + 8 * st, (phF >> st) & 1);
+                    phF ^= 1u << st;
                     tc_fence_after();
-                    const uint32_t v_hi = sStage + st * SB, v_lo = v_hi + V_HALF;
+                    for (int u = 0; u < n; ++u) {
+                        const uint32_t v_hi = slot_addr(st) + u * 2 * V_HALF, v_lo = v_hi + V_HALF;
 #pragma unroll
-                    for (int kk = 0; kk < 2; ++kk) {
-                        const uint32_t po = (uint32_t)(ss * 4 + kk * 2) * 2048;
-                        const uint64_t dah = make_desc(sP + po, 2048, 128), dbh = make_desc(v_hi + kk * 4096, 2048, 128);
-                        umma_bf16(tmem + buf * 256, dah, dbh, idescO, a0);
-                        a0 = 1;
-                        if (X3) {
-                            const uint64_t dal = make_desc(sP + PH + po, 2048, 128), dbl = make_desc(v_lo + kk * 4096, 2048, 128);
-                            umma_bf16(tmem + buf * 256 + 128, dah, dbl, idescO, a1);
-                            umma_bf16(tmem + buf * 256 + 128, dal, dbh, idescO, 1);
-                            a1 = 1;
+                        for (int kk = 0; kk < 2; ++kk) {
+                            const uint32_t po = (uint32_t)((ss + u) * 4 + kk * 2) * 2048;
+                            const uint64_t dah = make_desc(sP + po, 2048, 128), dbh = make_desc(v_hi + kk * 4096, 2048, 128);
+                            umma_bf16(tmem + buf * 256, dah, dbh, idescO, a0);
+                            a0 = 1;
+                            if (X3) {
+                                const uint64_t dal = make_desc(sP + PH + po, 2048, 128), dbl = make_desc(v_lo + kk * 4096, 2048, 128);
+                                umma_bf16(tmem + buf * 256 + 128, dah, dbl, idescO, a1);
+                                umma_bf16(tmem + buf * 256 + 128, dal, dbh, idescO, 1);
+                                a1 = 1;
+                            }
                         }
                     }
                     umma_commit(barEmpty + 8 * st);
@@ -422,7 +465,7 @@ cudaError_t launch_qkv_split(const float* qkv, uint8_t* dst, int B, int T, int H
 
 cudaError_t launch_attention_tc(const AttnTcParams& p, bool x3, cudaStream_t st) {
     if (p.B <= 0) return cudaSuccess;
-    const int smem = attn_stages(p.T) * stage_bytes(p.T) + 2 * p_half_bytes(p.T) + 256;
+    const int smem = attn_stages(p.T) * stage_bytes(p.T) + 2 * p_half_bytes(p.T) + 256 + 2048;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -437,8 +480,8 @@ cudaError_t launch_attention_tc(const AttnTcParams& p, bool x3, cudaStream_t st)
         if ((128 + p.T) * 4 > 7 * NUM_THREADS) return cudaErrorInvalidValue;   // producer item budget: T <= 208 (attn_direct_eligible)
         if (x3) attn_tc_kernel<true, true><<<grid, 2 * NUM_THREADS, smem, st>>>(p);
         else attn_tc_kernel<false, true><<<grid, 2 * NUM_THREADS, smem, st>>>(p);
-    } else if (x3) attn_tc_kernel<true, false><<<grid, NUM_THREADS, smem, st>>>(p);
-    else attn_tc_kernel<false, false><<<grid, NUM_THREADS, smem, st>>>(p);
+    } else if (x3) attn_tc_kernel<true, false><<<grid, ATTN_THREADS, smem, st>>>(p);
+    else attn_tc_kernel<false, false><<<grid, ATTN_THREADS, smem, st>>>(p);
     g_launch_count += 1;
     return cudaGetLastError();
 }
