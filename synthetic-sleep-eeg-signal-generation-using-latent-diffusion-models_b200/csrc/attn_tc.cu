@@ -5,12 +5,12 @@
 //   qkv_split_kernel   fp32 qkv [B][T][H*3*ch] (legacy head layout, unet.py:116-118) -> fp16 hi/lo images:
 //                        K    : [k-step = ch/32][hi|lo][T/8][4][8 pos][8 ch]   (K-major core matrices; a row range is contiguous)
 //                        Q    : the same with the query rows of each 128-row tile in the conv kernel's phase-strided order:
-//                               row m of tile qt is position qt*128 + (m % 8)*16 + m / 8, i.e. core matrix = one slot of the
-//                               tile's eight 16-position segments ([k-step][hi|lo][ceil(T/128)*16][4][8 seg][8 ch]).  A TMEM
-//                               lane of the qkv conv and of this kernel is then (slot, segment) with the segment fastest, so
-//                               eight consecutive lanes store one whole 128-byte core-matrix row set -- of the Q image in the
-//                               qkv conv's epilogue, of proj_out's operand image in this kernel's epilogue -- instead of
-//                               32 scattered 16-byte pieces (measured: PV + epilogue 26 k -> see profiles/r02b attention timeline)
+//                               a tile holds nseg = min(8, T/16 - 8*tile) segments of 16 positions, and its row m is position
+//                               tile*128 + (m % nseg)*16 + m / nseg (attn_q_row): consecutive rows = the same slot of consecutive
+//                               segments.  A TMEM lane of the qkv conv and of this kernel is then (slot, segment) with the
+//                               segment fastest, so eight consecutive lanes store whole 64- / 128-byte runs -- of the Q image in
+//                               the qkv conv's epilogue, of proj_out's operand image in this kernel's epilogue -- instead of 16-byte
+//                               pieces of 32 different lines
 //                        V    : [ch/128][T/32][hi|lo][4][16][8 key][8 ch]      (MN-major B operand for P.V)
 //   attn_tc_kernel     one CTA per (128-query tile, head, sample):
 //                        S = Q K^T   : M=128, N=T (<=256), K=ch, accumulators in TMEM columns [0,T) and [256,256+T)
@@ -34,7 +34,11 @@ constexpr int Q_HALF = 8192;           // 128 rows x 32 ch x 2 B
 constexpr int V_HALF = 8192;           // 32 keys x 128 ch x 2 B
 constexpr int NUM_THREADS = 192;
 
-__host__ __device__ inline int attn_tq(int T) { return (T + 127) / 128 * 128; }   // query rows of the Q image (whole tiles)
+// row of position t in the Q image: tile t / 128 holds nseg = min(8, T/16 - 8*tile) segments; its rows run over the segments first
+__host__ __device__ inline int attn_q_row(int t, int T) {
+    const int qt = t >> 7, tt = t & 127, nseg = min(8, (T >> 4) - 8 * qt);
+    return qt * 128 + nseg * (tt & 15) + (tt >> 4);
+}
 __host__ __device__ inline int stage_bytes(int T) { return 2 * Q_HALF + 2 * T * 64; }   // Q hi/lo + K hi/lo of one 32-ch k-step
 __host__ __device__ inline int p_half_bytes(int T) { return (T / 8) * 2048; }           // P hi (or lo): [T/8][16][8][8] fp16
 __host__ __device__ inline int attn_stages(int T) {
@@ -66,20 +70,13 @@ __global__ void qkv_split_kernel(const float* __restrict__ qkv, uint8_t* __restr
         if (m >= 0x477FE000u) atomicOr(range_flag, 1);
     }
     split8_f16(v, hi, lo);
-    const size_t plane = (size_t)4 * ch * T;                       // bytes of one of k / v (hi + lo)
-    const int Tq = attn_tq(T);
-    const size_t planeq = (size_t)4 * ch * Tq;                     // q: rows padded to whole 128-row tiles
-    uint8_t* base = dst + ((size_t)b * H + h) * (planeq + 2 * plane) + (which == 0 ? 0 : planeq + (size_t)(which - 1) * plane);
+    const size_t plane = (size_t)4 * ch * T;                       // bytes of one of q / k / v (hi + lo)
+    uint8_t* base = dst + ((size_t)b * H + h) * 3 * plane + (size_t)which * plane;
     size_t ohi, olo;
-    if (which == 0) {  // Q: [ks][hi|lo][Tq/8][4][8][8], tile rows phase-strided: group = tile*16 + slot, row = segment of the tile
+    if (which < 2) {   // Q, K: [ks][hi|lo][T/8][4][8][8]; Q rows in the phase-strided tile order
         const int ks = c / 32, cg = (c % 32) / 8;
-        const int grp = (t >> 7) * 16 + (t & 15), rw = (t & 127) >> 4;
-        const size_t o = (size_t)grp * 512 + cg * 128 + rw * 16;
-        ohi = ((size_t)ks * 2 + 0) * ((size_t)Tq * 64) + o;
-        olo = ((size_t)ks * 2 + 1) * ((size_t)Tq * 64) + o;
-    } else if (which == 1) {   // K: [ks][hi|lo][T/8][4][8][8]
-        const int ks = c / 32, cg = (c % 32) / 8;
-        const size_t o = (size_t)(t / 8) * 512 + cg * 128 + (t % 8) * 16;
+        const int tr = which == 0 ? attn_q_row(t, T) : t;
+        const size_t o = (size_t)(tr / 8) * 512 + cg * 128 + (tr % 8) * 16;
         ohi = ((size_t)ks * 2 + 0) * ((size_t)T * 64) + o;
         olo = ((size_t)ks * 2 + 1) * ((size_t)T * 64) + o;
     } else {           // V: [ch/128][T/32][hi|lo][4][16][8][8]
@@ -125,9 +122,10 @@ __global__ void __launch_bounds__(DIRECT ? 2 * NUM_THREADS : ATTN_THREADS, 1) at
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int mt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
     const int nks = ch / 32, nchunk = ch / 128, nss = T / 32;
-    const size_t plane = (size_t)4 * ch * T, planeq = (size_t)4 * ch * attn_tq(T);
-    const uint8_t* gq = p.qkv16 + ((size_t)b * p.H + h) * (planeq + 2 * plane);
-    const uint8_t* gk = gq + planeq;
+    const int nseg = min(8, (T >> 4) - 8 * mt);   // 16-position segments of this query tile (rows nseg*16 .. 127 of the MMA are unused)
+    const size_t plane = (size_t)4 * ch * T;
+    const uint8_t* gq = p.qkv16 + ((size_t)b * p.H + h) * 3 * plane;
+    const uint8_t* gk = gq + plane;
     const uint8_t* gv = gk + plane;
 
     if (tid == 0) {
@@ -153,9 +151,9 @@ __global__ void __launch_bounds__(DIRECT ? 2 * NUM_THREADS : ATTN_THREADS, 1) at
         constexpr int NWG = DIRECT ? 1 : 2;
         const int wg = warp < 4 ? 0 : 1;                            // column half this warpgroup takes
         const int row = (warp & 3) * 32 + lane;                    // MMA row = TMEM lane (a warp reads the lane quarter warp % 4):
-                                                                   // (slot = row / 8, segment = row % 8) of the tile
-        const int t = mt * 128 + (row & 7) * 16 + (row >> 3);     // its position (Q image row order, see the file comment)
-        const bool rowv = t < T;
+                                                                   // (slot = row / nseg, segment = row % nseg) of the tile
+        const int t = mt * 128 + (row % nseg) * 16 + row / nseg;  // its position (Q image row order, see the file comment)
+        const bool rowv = row < 16 * nseg;
         const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
         float* xmax = reinterpret_cast<float*>(smem + NST * SB + 2 * PH + 256);   // [2][128] row maxima, then [2][128] row sums
         float* xsum = xmax + 256;
@@ -277,7 +275,7 @@ __global__ void __launch_bounds__(DIRECT ? 2 * NUM_THREADS : ATTN_THREADS, 1) at
         const int pt = tid - NUM_THREADS;              // warps 6-11
         const size_t rs = (size_t)p.H * 3 * ch;          // floats per qkv row
         const float* qrow0 = p.qkv32 + (size_t)b * T * rs + (size_t)h * 3 * ch;   // q of position 0; k at +ch, v at +2ch
-        const int rowsQ = 128, nS = (rowsQ + T) * 4, nV = 512;   // all 128 query rows of the tile (rows past T are zero-filled)
+        const int rowsQ = 16 * nseg, nS = (rowsQ + T) * 4, nV = 512;
         const int total = nks + nchunk * nss;
         constexpr int MAXI = 7;                          // items per thread and stage: (128 + 256) * 4 / 192 = 8 would need T = 256: see launcher
         struct Pre { float4 x[MAXI][2]; };
@@ -285,8 +283,8 @@ __global__ void __launch_bounds__(DIRECT ? 2 * NUM_THREADS : ATTN_THREADS, 1) at
             if (it < nks) {
                 const int row = idx >> 2, cg = idx & 3;
                 if (row < rowsQ) {
-                    const int tq = mt * 128 + (row & 7) * 16 + (row >> 3);     // phase-strided query row order
-                    return tq < T ? qrow0 + (size_t)tq * rs + it * 32 + cg * 8 : nullptr;
+                    const int tq = mt * 128 + (row % nseg) * 16 + row / nseg;  // phase-strided query row order
+                    return qrow0 + (size_t)tq * rs + it * 32 + cg * 8;
                 }
                 return qrow0 + ch + (size_t)(row - rowsQ) * rs + it * 32 + cg * 8;
             }
@@ -347,9 +345,8 @@ __global__ void __launch_bounds__(DIRECT ? 2 * NUM_THREADS : ATTN_THREADS, 1) at
         // ================================================================ loader (pre-split images; idle in the DIRECT form)
         if (lane == 0 && !DIRECT) {
             uint32_t phE = 0;   // bit i: parity of the completed waits on slot i's "empty" barrier
-            const uint32_t qb = Q_HALF, kb = (uint32_t)T * 64;   // a whole 128-row Q tile (rows past T: never-written scratch, their
-                                                                   // scores and outputs are computed and dropped)
-            const size_t qhalf = (size_t)attn_tq(T) * 64;
+            const uint32_t qb = (uint32_t)nseg * 1024, kb = (uint32_t)T * 64;   // the tile's 16*nseg query rows
+            const size_t qhalf = kb;
             for (int ks = 0; ks < nks; ++ks) {
                 const int st = ks % NSS;
                 const uint32_t dst = slot_addr(st);
@@ -453,7 +450,7 @@ __global__ void __launch_bounds__(DIRECT ? 2 * NUM_THREADS : ATTN_THREADS, 1) at
 
 bool attn_direct_eligible(int T, int ch) { return attn_tc_eligible(T, ch) && (128 + T) * 4 <= 7 * NUM_THREADS; }
 bool attn_tc_eligible(int T, int ch) { return T >= 32 && T <= 256 && T % 32 == 0 && ch >= 128 && ch % 128 == 0; }
-size_t attn_qkv16_bytes(int B, int T, int H, int ch) { return (size_t)B * H * 4 * ch * ((size_t)attn_tq(T) + 2 * (size_t)T); }
+size_t attn_qkv16_bytes(int B, int T, int H, int ch) { return (size_t)B * H * 12 * ch * T; }
 
 cudaError_t launch_qkv_split(const float* qkv, uint8_t* dst, int B, int T, int H, int ch, cudaStream_t st, int* range_flag) {
     const size_t total = (size_t)B * H * 3 * (ch / 8) * T;

@@ -332,11 +332,12 @@ __global__ void __launch_bounds__(conv_tc_threads(DIRECT, EPI8), 1) conv_tc_kern
                 const int g = m_tile * 8 + sg;
                 const bool valid = g < p.nsegs16;
                 const int b = valid ? g / spt : 0, s_in = g % spt, t = s_in * 16 + pos;
-                const int Tq = (T + 127) / 128 * 128;
-                const size_t plane = (size_t)4 * ch * T, planeq = (size_t)4 * ch * Tq;
-                const size_t half = isq ? (size_t)Tq * 64 : (which == 1 ? (size_t)T * 64 : 8192);
-                uint8_t* base = p.qkv16 + ((size_t)b * p.qkv_H + cq) * (planeq + 2 * plane) + (isq ? 0 : planeq + (size_t)(which - 1) * plane) +
-                                (isq ? (size_t)((s_in >> 3) * 16 + pos) * 512 + (s_in & 7) * 16
+                // Q image row of this position (attn_tc.cu, attn_q_row): tile s_in / 8 holds nseg segments, rows run over them first
+                const int nseg = min(8, spt - (s_in & ~7)), qrow = (s_in >> 3) * 128 + nseg * pos + (s_in & 7);
+                const size_t plane = (size_t)4 * ch * T;
+                const size_t half = which < 2 ? (size_t)T * 64 : 8192;
+                uint8_t* base = p.qkv16 + (((size_t)b * p.qkv_H + cq) * 3 + which) * plane +
+                                (isq ? (size_t)(qrow >> 3) * 512 + (qrow & 7) * 16
                                      : (which == 1 ? (size_t)(t >> 3) * 512 + (t & 7) * 16
                                                    : (size_t)(t >> 5) * 2 * half + ((t & 31) >> 3) * 2048 + (t & 7) * 16));
                 const float* bias_p = p.bias && !(p.debug & 512) ? p.bias + co0 : nullptr;
