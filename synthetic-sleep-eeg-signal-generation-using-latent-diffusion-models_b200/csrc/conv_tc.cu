@@ -215,7 +215,10 @@ __global__ void __launch_bounds__(SPLIT_THREADS) act_split_kernel(const ActSplit
 // k-steps of a skip_connection segment with the 3-tap ones (so the ring averages their tensor time) measured 10 % SLOWER on the
 // two-segment layers and was dropped.  Pulling the rows of the CTA's NEXT tile into L2 when a tile starts (prefetch.global.L2 per 128-byte line;
 // for the short-K level-0 tiles, whose k-step is shorter than a DRAM round trip) measured 5 % SLOWER on those layers (0.31 vs 0.29 ms):
-// they move 0.8-1.2 GB in 0.29-0.34 ms, i.e. they sit at ~55 % of the HBM peak with mixed reads and writes -- bandwidth, not latency.
+// spreading the same prefetches over the k-steps (one 128-byte row piece per k-step, a constant element offset from the current rows)
+// measured no different (+-1 %).  Those tiles are not waiting for DRAM: per tile the MMAs read 480 KB of operands from shared memory
+// (N = 128: 20 KB per K-slice pair), the copies and the producer write 264 KB and the overlapped epilogue stages 128 KB -- 870 KB at
+// 128 B/clk is 6.8 k of the 11.7 k cycles a tile takes; the shared-memory pipe, which the three f16x3 products keep busy, bounds them.
 //
 // EPI8: two epilogue warpgroups instead of one.  With N = 256 in f16x3 the two accumulators fill TMEM, so the epilogue of a tile cannot
 // overlap the next mainloop and its duration is lost tensor time (10-17 k cycles per tile, 20-40 % on the K <= 1536 layers:
