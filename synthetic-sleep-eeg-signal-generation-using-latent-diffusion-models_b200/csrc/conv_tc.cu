@@ -404,11 +404,16 @@ __global__ void __launch_bounds__(conv_tc_threads(DIRECT, EPI8), 1) conv_tc_kern
             const int rb = g < p.nsegs16 ? g / spt : -1;             // sample (< 0: segment past the batch)
             const int rt = (g % spt) * 16 + ew * 4;                  // first of this thread's 4 positions
             const int bb = max(rb, 0);
-            const size_t obase = ((size_t)bb * p.Tout + rt) * p.Cout + co0 + col4;
+            // polyphase up-conv (TcConvParams.poly): this half tile is one output phase; Cr real channels, rows 2t + phase
+            const int Cr = p.poly ? p.Cout >> 1 : p.Cout;
+            const int ph = p.poly && co0 >= Cr ? 1 : 0, cor = co0 - ph * Cr;
+            const size_t ostride = p.poly ? 2 * (size_t)Cr : (size_t)Cr;           // elements between consecutive tile positions
+            const size_t obase = p.poly ? ((size_t)bb * 2 * p.Tout + 2 * rt + ph) * Cr + cor + col4
+                                        : ((size_t)bb * p.Tout + rt) * p.Cout + co0 + col4;
             const int tr = p.res_mode == RS_AVGPOOL2 ? 2 * rt : (p.res_mode == RS_NEAREST2 ? (rt >> 1) : rt);
             const size_t rbase = ((size_t)bb * p.res_Tin + tr) * p.Cout + co0 + col4;
             const int rmul = p.res_mode == RS_AVGPOOL2 ? 4 : (p.res_mode == RS_NEAREST2 ? 1 : 2);   // half-rows per position
-#define OOFF(i) (obase + (size_t)(i) * p.Cout)
+#define OOFF(i) (obase + (size_t)(i) * ostride)
 #define ROFF(i) (rbase + (size_t)(((i) * rmul) >> 1) * p.Cout)
             // Prefetched one chunk ahead: plain loads only.  (The pooled residual's second row is loaded where the value is consumed:
             // an average computed here, even predicated off, makes the warp wait for the loads it has just issued -- ncu showed
@@ -433,8 +438,8 @@ __global__ void __launch_bounds__(conv_tc_threads(DIRECT, EPI8), 1) conv_tc_kern
             }
             // bias / time-embedding values of a chunk are loaded one chunk ahead as well (the first ones while the mainloop of the tile
             // still runs): a load consumed in the iteration that issues it costs a full L2 round trip per chunk
-            const float* bias_p = p.bias ? p.bias + co0 + col4 : nullptr;
-            const float* temb_p = p.temb ? p.temb + (size_t)bb * p.temb_stride + co0 + col4 : nullptr;
+            const float* bias_p = p.bias ? p.bias + cor + col4 : nullptr;
+            const float* temb_p = p.temb ? p.temb + (size_t)bb * p.temb_stride + cor + col4 : nullptr;
             float4 biasn = bias_p ? ldg4(bias_p) : make_float4(0.f, 0.f, 0.f, 0.f);
             float4 Tmn = temb_p ? ldg4(temb_p) : make_float4(0.f, 0.f, 0.f, 0.f);
             TL_WAIT(tl_a, mbar_wait(barAccFull + 8 * as, use & 1));
@@ -538,7 +543,9 @@ __global__ void __launch_bounds__(conv_tc_threads(DIRECT, EPI8), 1) conv_tc_kern
                     const float da = a.x - mean, db = b.x - mean, dc = c.x - mean, dd = d.x - mean;
                     const float m2 = (a.y + b.y) + (c.y + d.y) + nq * ((da * da + db * db) + (dc * dc + dd * dd));
                     if (g16 < p.nsegs16) {
-                        float* o = p.gn_partial + ((size_t)g16 * (p.Cout / cpg) + co0 / cpg + gi) * 3;   // [b][segment][group][3]
+                        // [b][segment][group][3]; polyphase: the 16 even (odd) rows of output segment pair 2 g16, 2 g16 + 1 are
+                        // recorded as "segment" 2 g16 + phase (statistics do not care which 16 rows a record holds)
+                        float* o = p.gn_partial + ((size_t)(p.poly ? 2 * g16 + ph : g16) * (Cr / cpg) + cor / cpg + gi) * 3;
                         o[0] = 4.f * nq; o[1] = mean; o[2] = m2;
                     }
                 }
@@ -880,7 +887,9 @@ __global__ void __launch_bounds__(conv_tc_threads(DIRECT, EPI8), 1) conv_tc_kern
                     // weight image [k-step][tap][hi|lo][Cout/8][4 kc][8][8]: the BN columns of this tile are one contiguous slice
                     const size_t whalf = (size_t)p.Cout * (BK * 2);
                     const uint8_t* wsrc = sg.w + (size_t)kl * sg.taps * 2 * whalf + (size_t)n_tile * BN * (BK * 2);
-                    for (int tap = 0; tap < sg.taps; ++tap, ++ib) {
+                    // polyphase up-conv: the even phase (first half of the columns) has no tap 2, the odd phase no tap 0
+                    const int tap_lo = p.poly && 2 * n_tile * BN >= p.Cout ? 1 : 0, tap_hi = p.poly ? tap_lo + 2 : sg.taps;
+                    for (int tap = tap_lo; tap < tap_hi; ++tap, ++ib) {
                         const int sb = ib % NB;
                         TL_WAIT(tl_a, mbar_wait(barBempty + 8 * sb, ((ib / NB) & 1) ^ 1));   // all consumers of this stage are done
                         if (elect_one()) {
@@ -935,6 +944,7 @@ __global__ void __launch_bounds__(conv_tc_threads(DIRECT, EPI8), 1) conv_tc_kern
             for (int w = cid; w < nwork; w += ncl, ++lt) {
                 const int as = lt % NSETS, use = lt / NSETS;
                 const uint32_t d0 = tmem + as * ACC_COLS, d1 = d0 + BN;
+                const int poly_lo = p.poly && 2 * (w % n_ntiles) * BN >= p.Cout ? 1 : 0;   // polyphase up-conv: first tap of this N tile
                 TL_WAIT(tl_a, mbar_wait(barAccEmpty + 8 * as, (use & 1) ^ 1));   // (pair: both CTAs' epilogues have drained this set)
                 tc_fence_after();
                 uint32_t accum = 0, accum2 = 0;
@@ -947,10 +957,11 @@ __global__ void __launch_bounds__(conv_tc_threads(DIRECT, EPI8), 1) conv_tc_kern
                 for (int ks = 0; ks < nks; ++ks, ++ia) {
                     const int sa = ia % NA;
                     const int taps = ks < nks0 ? p.seg[0].taps : p.seg[1].taps;
+                    const int tap_lo = p.poly ? poly_lo : 0, tap_hi = p.poly ? poly_lo + 2 : taps;
                     TL_WAIT(tl_b, mbar_wait(barAfull + 8 * sa, (ia / NA) & 1));
                     if (PAIR && DIRECT) TL_WAIT(tl_b, mbar_wait(barApeer + 8 * sa, (ia / NA) & 1));   // the peer's half of the M = 256 rows
                     tc_fence_after();
-                    for (int tap = 0; tap < taps; ++tap, ++ib) {
+                    for (int tap = tap_lo; tap < tap_hi; ++tap, ++ib) {
                         const int sb = ib % NB;
                         TL_WAIT(tl_c, mbar_wait(barBfull + 8 * sb, (ib / NB) & 1));
                         tc_fence_after();
@@ -984,13 +995,13 @@ __global__ void __launch_bounds__(conv_tc_threads(DIRECT, EPI8), 1) conv_tc_kern
                         }
                         if (PAIR) {   // one commit per barrier, delivered to the same barrier of both CTAs
                             umma2_commit_multicast(barBempty + 8 * sb, CMASK);
-                            if (tap == taps - 1) umma2_commit_multicast(barAempty + 8 * sa, CMASK);
-                            if (tap == taps - 1 && ks == nks - 1) umma2_commit_multicast(barAccFull + 8 * as, CMASK);
+                            if (tap == tap_hi - 1) umma2_commit_multicast(barAempty + 8 * sa, CMASK);
+                            if (tap == tap_hi - 1 && ks == nks - 1) umma2_commit_multicast(barAccFull + 8 * as, CMASK);
                         } else {
                             if (CL > 1) umma_commit_multicast(barBempty + 8 * sb, CMASK);   // every CTA's loader writes into this stage
                             else umma_commit(barBempty + 8 * sb);                           // weight stage free once these MMAs retire
-                            if (tap == taps - 1) umma_commit(barAempty + 8 * sa);
-                            if (tap == taps - 1 && ks == nks - 1) umma_commit(barAccFull + 8 * as);
+                            if (tap == tap_hi - 1) umma_commit(barAempty + 8 * sa);
+                            if (tap == tap_hi - 1 && ks == nks - 1) umma_commit(barAccFull + 8 * as);
                         }
                         }
                         __syncwarp();
@@ -1079,6 +1090,24 @@ void pack_conv_tc(const float* w, int Cout, int Cin, int k, bool x3, std::vector
         }
 }
 
+// Polyphase image of a 3-tap conv that follows a nearest x2 upsample (TcConvParams.poly): on the low-resolution input u,
+//   out[2t]   = w0 u[t-1] + (w1 + w2) u[t]            (even phase: columns 0 .. Cout-1,      taps (w0, w1+w2, 0))
+//   out[2t+1] = (w0 + w1) u[t] + w2 u[t+1]            (odd phase:  columns Cout .. 2Cout-1,  taps (0, w0+w1, w2))
+// -- the same sums the reference forms on the upsampled signal (unet.py:263-268, 291), with the two coincident taps added in fp32
+// before the 16-bit split.  The zero taps are kept in the image (uniform layout) and skipped by the kernel per N tile.
+void pack_conv_tc_poly(const float* w, int Cout, int Cin, bool x3, std::vector<uint16_t>& out) {
+    std::vector<float> wp((size_t)2 * Cout * Cin * 3);
+    for (int co = 0; co < Cout; ++co)
+        for (int ci = 0; ci < Cin; ++ci) {
+            const float* s = w + ((size_t)co * Cin + ci) * 3;
+            float* e = wp.data() + ((size_t)co * Cin + ci) * 3;
+            float* o = wp.data() + ((size_t)(Cout + co) * Cin + ci) * 3;
+            e[0] = s[0]; e[1] = s[1] + s[2]; e[2] = 0.f;
+            o[0] = 0.f; o[1] = s[0] + s[1]; o[2] = s[2];
+        }
+    pack_conv_tc(wp.data(), 2 * Cout, Cin, 3, x3, out);
+}
+
 size_t act_split_bytes(int nsegs16, int Cin) { return (size_t)((nsegs16 + 7) / 8) * (Cin / TC_BK) * A_STAGE; }
 
 cudaError_t launch_act_split(const ActSplitParams& p, bool x3, cudaStream_t st) {
@@ -1151,6 +1180,10 @@ cudaError_t launch_conv_tc(const TcConvParams& p_in, bool x3, cudaStream_t st) {
     // two-warpgroup epilogue (EPI8): every launch except the ones whose epilogue emits 32-channel GroupNorm groups or bf16-mode
     // attention operand images (one-warpgroup epilogue only); cluster sizes 1 and 2
     if (p.qkv16 && (!x3 || p.gn_partial)) return cudaErrorInvalidValue;   // operand-image output: f16x3, two-warpgroup epilogue only
+    // polyphase up-conv: one segment of 3 taps, whole N tiles per phase, no residual, two-warpgroup epilogue only
+    if (p.poly && (p.nseg != 1 || p.seg[0].taps != 3 || p.bn != 256 || (p.Cout / 2) % 256 || p.res || p.qkv16 ||
+                   (p.gn_partial && p.gn_cpg == 32)))
+        return cudaErrorInvalidValue;
     const bool epi8_ok = !(p.gn_partial && p.gn_cpg == 32);
     // CTA pairs (cta_group::2): g_conv_tc_pair bit 0 = the N = 256 launches, bit 1 = the N = 128 launches
     const bool pair = epi8_ok && ((p.bn == 256 && (g_conv_tc_pair & 1)) || (p.bn == 128 && (g_conv_tc_pair & 2)));
@@ -1170,7 +1203,7 @@ cudaError_t launch_conv_tc(const TcConvParams& p_in, bool x3, cudaStream_t st) {
         g_launch_count += 1;
         return cudaGetLastError();
     }
-    const bool epi8 = (g_conv_tc_epi8 || p.qkv16) && epi8_ok && (p.direct || g_conv_tc_cluster == 2 || g_conv_tc_cluster == 1 || p.qkv16);
+    const bool epi8 = (g_conv_tc_epi8 || p.qkv16 || p.poly) && epi8_ok && (p.direct || g_conv_tc_cluster == 2 || g_conv_tc_cluster == 1 || p.qkv16 || p.poly);
 #define EEGLDM_TC8(X3, BN)                                                                               \
     (p.direct ? (g_conv_tc_cluster == 1 ? launch_conv_tc_t<X3, BN, 1, false, true, true>(p, num_sms, st)   \
                                         : launch_conv_tc_t<X3, BN, 2, false, true, true>(p, num_sms, st))  \

@@ -299,8 +299,9 @@ struct ULayer {
     size_t o_g1, o_be1, o_w1, o_b1, o_g2, o_be2, o_w2, o_b2, o_wskip, o_wqkv, o_bqkv, o_wproj, o_bproj;
     // tcgen05 weight images (null when the layer's channel counts are not tensor-pipe eligible)
     const uint8_t *t_w1 = nullptr, *t_w2 = nullptr, *t_wskip = nullptr, *t_wqkv = nullptr, *t_wproj = nullptr;
-    size_t ot_w1 = 0, ot_w2 = 0, ot_wskip = 0, ot_wqkv = 0, ot_wproj = 0;
-    bool h_w1 = false, h_w2 = false, h_wskip = false, h_wqkv = false, h_wproj = false;
+    const uint8_t* t_w1p = nullptr;   // up-sampling ResBlock: polyphase image of in_layers' conv (pack_conv_tc_poly)
+    size_t ot_w1 = 0, ot_w2 = 0, ot_wskip = 0, ot_wqkv = 0, ot_wproj = 0, ot_w1p = 0;
+    bool h_w1 = false, h_w2 = false, h_wskip = false, h_wqkv = false, h_wproj = false, h_w1p = false;
 };
 
 struct GraphEntry {
@@ -374,6 +375,7 @@ bool g_attn_direct = false;    // the tcgen05 attention splits fp32 q, k, v itse
 bool g_attn_u_fused = true;    // the tcgen05 attention writes proj_out's operand image instead of fp32 (eegldm_set_conv_tuning bit 3)
 bool g_conv_direct = true;     // tensor-pipe convs produce their activation operands in-kernel (no act_split pre-pass)
 bool g_conv_gn_fine = true;        // epilogue GroupNorm records 4 / 8 channels wide (eegldm_set_conv_tuning bit 8 = the consumer's group width instead)
+bool g_conv_poly = true;           // polyphase form of the up-sampling ResBlocks' first conv (eegldm_set_conv_tuning bit 9 = off)
 bool g_conv_direct_wide = false;   // fused producer also for 1x1 convs with more than two N tiles (qkv): eegldm_set_conv_tuning bit 7
 bool g_conv_gn_fused = true;   // tensor-pipe convs emit the GroupNorm statistics of their output (eegldm_set_conv_tuning)
 bool g_graphs_enabled = true;
@@ -546,6 +548,12 @@ int finalize_unet(eegldm_unet* h) {
                 // weight stages per tile = sum over K segments of (Cin/32)*taps; conv2 and its skip segment share one tile shape
                 const int st1 = l.cin / TC_BK * 3, st2 = l.cout / TC_BK * 3 + (l.cin != l.cout ? l.cin / TC_BK : 0);
                 tc_pack(p + ".in_layers.2.weight", l.cout, l.cin, 3, st1, l.ot_w1, l.h_w1);
+                if (l.h_w1 && l.mode == RS_NEAREST2 && l.cout % 256 == 0) {   // up-sampling ResBlock: polyphase image as well
+                    std::vector<uint16_t> img;
+                    pack_conv_tc_poly(ps.get(p + ".in_layers.2.weight").data(), l.cout, l.cin, h->math == EEGLDM_MATH_F16X3_TC, img);
+                    l.ot_w1p = wp.push_u16(img);
+                    l.h_w1p = true;
+                }
                 tc_pack(p + ".out_layers.3.weight", l.cout, l.cout, 3, st2, l.ot_w2, l.h_w2);
                 if (l.cin != l.cout) tc_pack(p + ".skip_connection.weight", l.cout, l.cin, 1, st2, l.ot_wskip, l.h_wskip);
                 break;
@@ -608,6 +616,7 @@ int finalize_unet(eegldm_unet* h) {
     for_each_layer(h, [&](ULayer& l) {
         auto tcp = [&](bool has, size_t off) { return has ? reinterpret_cast<const uint8_t*>(wp.at(off)) : nullptr; };
         l.t_w1 = tcp(l.h_w1, l.ot_w1); l.t_w2 = tcp(l.h_w2, l.ot_w2); l.t_wskip = tcp(l.h_wskip, l.ot_wskip);
+        l.t_w1p = tcp(l.h_w1p, l.ot_w1p);
         l.t_wqkv = tcp(l.h_wqkv, l.ot_wqkv); l.t_wproj = tcp(l.h_wproj, l.ot_wproj);
         switch (l.kind) {
             case ULayer::CONV_IN: l.w1 = wp.at(l.o_w1); l.b1 = wp.at(l.o_b1); break;
@@ -658,7 +667,8 @@ struct TcShare {
 struct QkvOut { uint8_t* dst; int H, ch; };
 // premade_u0: segment 0's operand image already exists (written by the attention kernel's epilogue): no pre-pass, no producer.
 void plan_conv(Builder& bd, ConvParams p, const uint8_t* tw0 = nullptr, const uint8_t* tw1 = nullptr, TcShare* share = nullptr,
-               Act* out_act = nullptr, int gn_G = 0, const QkvOut* qkv = nullptr, const uint8_t* premade_u0 = nullptr) {
+               Act* out_act = nullptr, int gn_G = 0, const QkvOut* qkv = nullptr, const uint8_t* premade_u0 = nullptr,
+               const uint8_t* tw0_poly = nullptr) {
     p.B = bd.B;
     double flops = 0, bytes = 4.0 * p.B * (double)p.Tout * p.Cout;   // output write
     for (int s = 0; s < p.nseg; ++s) {
@@ -680,6 +690,16 @@ void plan_conv(Builder& bd, ConvParams p, const uint8_t* tw0 = nullptr, const ui
         int stages = 0;
         for (int s = 0; s < p.nseg; ++s) stages += (p.seg[s].C0 + p.seg[s].C1) / TC_BK * p.seg[s].taps;
         q.bn = conv_tc_bn(p.Cout, stages);   // tile width is a launch-time choice: the weight image is width-agnostic
+        // "nearest x2 -> 3-tap conv" (in_layers of an up-sampling ResBlock) in polyphase form: the conv runs on the low-resolution
+        // input with [even | odd] output phases as 2 Cout columns and two taps of MMAs per phase instead of three (TcConvParams.poly)
+        const bool poly = tw0_poly && g_conv_poly && g_conv_gn_fine && p.nseg == 1 && p.seg[0].taps == 3 &&
+                          p.seg[0].resample == RS_NEAREST2 && 2 * p.seg[0].Tin == p.Tout && p.seg[0].Tin % 16 == 0 && !p.res && !qkv &&
+                          !premade_u0 && !(share && share->want_raw) && p.Cout % 256 == 0 && q.bn == 256;
+        if (poly) {
+            q.poly = 1; q.Cout = 2 * p.Cout; q.Tout = p.seg[0].Tin; q.nsegs16 = (int)((long long)p.B * q.Tout / 16);
+            p.seg[0].resample = RS_NONE;   // (p is this function's copy: the tensor path below sees the low-resolution input as it is)
+            tw0 = tw0_poly;
+        }
         std::shared_ptr<Buf> ubuf[2];
         // fused producer: the conv kernel reads the fp32 sources itself (no act_split pass, no U tensors); AvgPool inputs
         // (the two down-sampling ResBlocks) keep the pre-pass
@@ -711,7 +731,7 @@ void plan_conv(Builder& bd, ConvParams p, const uint8_t* tw0 = nullptr, const ui
                 share->raw = bd.scratch((ub + 3) / 4);
                 uraw = reinterpret_cast<uint8_t*>(bd.ptr(share->raw));
             }
-            ActSplitParams sp{a.src0, a.src1, a.C0, a.C1, a.scale, a.shift, a.silu, a.resample, a.Tin, p.Tout, q.nsegs16, cin / TC_BK,
+            ActSplitParams sp{a.src0, a.src1, a.C0, a.C1, a.scale, a.shift, a.silu, a.resample, a.Tin, q.Tout, q.nsegs16, cin / TC_BK,
                               reinterpret_cast<uint8_t*>(bd.ptr(ubuf[s])), uraw, bd.range_flag};
             bd.add([sp, x3](cudaStream_t st) { return launch_act_split(sp, x3, st); }, 1, OP_SPLIT, 0.0,
                    4.0 * p.B * (double)a.Tin * cin + (double)ub * (x3 ? 1.0 : 0.5) * (uraw ? 2.0 : 1.0));
@@ -761,7 +781,7 @@ Act plan_res(Builder& bd, const ULayer& l, const Act& x0, const Act* x1, const U
         p.nseg = 1; p.Cout = l.cout; p.Tout = Tc; p.Tc = Tc; p.stride = 1; p.pad_left = 1;
         p.bias = l.b1; p.temb = io.temb + l.emb_off; p.temb_stride = io.temb_stride;
         p.out = bd.wptr(h1);
-        plan_conv(bd, p, l.t_w1, nullptr, &share, &h1, 32);
+        plan_conv(bd, p, l.t_w1, nullptr, &share, &h1, 32, nullptr, nullptr, l.t_w1p);
     }
     Act y = bd.act(l.cout, Tc);
     {
@@ -1403,6 +1423,7 @@ int eegldm_set_conv_tuning(int pair, int bn256_min_stages, int fuse_epilogues) {
     g_attn_direct = (fuse_epilogues & 16) != 0;
     g_conv_direct_wide = (fuse_epilogues & 128) != 0;
     g_conv_gn_fine = (fuse_epilogues & 256) == 0;
+    g_conv_poly = (fuse_epilogues & 512) == 0;
     g_conv_tc_epi8 = (fuse_epilogues & 64) ? 0 : 1;  // bit 6 switches the two-warpgroup conv epilogue OFF (A/B timing)
     g_conv_tc_cat = (fuse_epilogues & 32) ? 0 : 1;   // bit 5 switches the concatenated hi|lo MMA of the N = 128 tiles OFF (A/B timing)
     if (bn256_min_stages < 1) return fail(EEGLDM_ERR_INVALID, "bn256_min_stages must be >= 1");
@@ -1833,10 +1854,14 @@ int eegldm_test_conv(const float* x_dev, const float* scale_dev, const float* sh
     size_t o_b = 0, o_t = 0;
     if (bias_host) o_b = wp.push(bias_host, Cout);
     const bool tc = math != EEGLDM_MATH_FP32_SIMT;
+    // the polyphase form plan_conv picks for "nearest x2 -> 3-tap conv" (up-sampling ResBlocks)
+    const bool poly = tc && g_conv_poly && resample == RS_NEAREST2 && k == 3 && !res_dev && Cout % 256 == 0 && Tin % 16 == 0 &&
+                      conv_tc_bn(Cout, Cin / TC_BK * k) == 256;
     if (tc) {
         if (!conv_tc_eligible(Cin, 0, Cout, Tc, k, 1)) return fail(EEGLDM_ERR_SHAPE, "shape not eligible for the tcgen05 path");
         std::vector<uint16_t> img;
-        pack_conv_tc(w.data(), Cout, Cin, k, math == EEGLDM_MATH_F16X3_TC, img);
+        if (poly) pack_conv_tc_poly(w.data(), Cout, Cin, math == EEGLDM_MATH_F16X3_TC, img);
+        else pack_conv_tc(w.data(), Cout, Cin, k, math == EEGLDM_MATH_F16X3_TC, img);
         o_t = wp.push_u16(img);
     }
     int r = wp.upload();
@@ -1854,6 +1879,7 @@ int eegldm_test_conv(const float* x_dev, const float* scale_dev, const float* sh
         TcConvParams q{};
         q.nseg = 1; q.Cout = Cout; q.Tout = Tc; q.nsegs16 = (int)((long long)B * Tc / 16);
         q.bn = conv_tc_bn(Cout, Cin / TC_BK * k);
+        if (poly) { q.poly = 1; q.Cout = 2 * Cout; q.Tout = Tin; q.nsegs16 = (int)((long long)B * Tin / 16); resample = RS_NONE; }
         if (g_conv_direct && (resample == RS_NONE || resample == RS_NEAREST2)) {   // fused producer: no pre-pass
             q.direct = 1;
             q.seg[0] = TcSeg{nullptr, reinterpret_cast<const uint8_t*>(wp.at(o_t)), k, Cin / TC_BK, x_dev, nullptr, Cin, 0, scale_dev, shift_dev,
@@ -1861,7 +1887,7 @@ int eegldm_test_conv(const float* x_dev, const float* scale_dev, const float* sh
             ce = cudaSuccess;
         } else {
             CU(cudaMalloc((void**)&U, act_split_bytes(q.nsegs16, Cin)));
-            ActSplitParams sp{x_dev, nullptr, Cin, 0, scale_dev, shift_dev, silu, resample, Tin, Tc, q.nsegs16, Cin / TC_BK, U, nullptr};
+            ActSplitParams sp{x_dev, nullptr, Cin, 0, scale_dev, shift_dev, silu, resample, Tin, q.Tout, q.nsegs16, Cin / TC_BK, U, nullptr};
             ce = launch_act_split(sp, x3, st);
             q.seg[0] = TcSeg{U, reinterpret_cast<const uint8_t*>(wp.at(o_t)), k, Cin / TC_BK};
         }

@@ -122,6 +122,12 @@ struct TcConvParams {
     int debug;          // timing experiments only (eegldm_bench_conv): 1 = no operand copies, 2 = no MMAs; results are garbage
     int* range_flag;    // optional (fused producer): set to 1 when an operand is outside the f16x3 range (|x| >= 65504 or NaN)
     int cat;            // f16x3, bn == 128: issue a_hi x [w_hi | w_lo] as one N = 256 MMA (set by launch_conv_tc from g_conv_tc_cat)
+    int poly;           // 1: polyphase form of "nearest x2 upsample -> 3-tap conv" (ResBlock(up=True).in_layers, unet.py:263-268): the conv
+                        //    runs on the LOW-resolution input; Cout = 2 x the real channel count = [even-output phase | odd-output phase],
+                        //    weights (w0, w1+w2, 0) | (0, w0+w1, w2) (pack_conv_tc_poly): an N tile lies in one phase and skips that
+                        //    phase's zero tap (2 taps of MMAs instead of 3); output position t of phase ph is row 2t + ph of
+                        //    out [B][2 Tout][Cout/2]; bias / temb / GroupNorm records are indexed with the real channel.  No residual,
+                        //    two-warpgroup epilogue only, bn == 256, (Cout/2) % 256 == 0.
     unsigned long long* timeline;   // optional (eegldm_bench_conv_timeline): per-CTA cycle counters, TC_TL_N per CTA
     // CTA-pair form (g_conv_tc_pair; filled by launch_conv_tc): 2-D tensor maps over the weight image ([rows of 256 u16], box = the
     // BN/2 columns of one CTA) and, in the pre-pass form, over the U image (box = one 18 KB stage) of each segment -- the pair's loads are
@@ -136,6 +142,7 @@ bool conv_tc_eligible(int Cin0, int Cin1, int Cout, int Tout, int taps, int stri
 bool conv_tc_gn_ok(int Cout, int G);         // can the conv epilogue emit the GroupNorm(G) statistics of its output?
 int conv_tc_bn(int Cout, int weight_stages);   // weight_stages = sum over segments of (Cin/32)*taps
 void pack_conv_tc(const float* w, int Cout, int Cin, int k, bool x3, std::vector<uint16_t>& out);
+void pack_conv_tc_poly(const float* w, int Cout, int Cin, bool x3, std::vector<uint16_t>& out);   // TcConvParams.poly image (2 Cout columns)
 cudaError_t launch_conv_tc(const TcConvParams& p, bool x3, cudaStream_t st);
 extern int g_conv_tc_cluster;        // CTAs per cluster sharing weight stages (1, 2, 4) when g_conv_tc_pair == 0
 extern int g_conv_tc_pair;           // cta_group::2 CTA pairs (default 1)

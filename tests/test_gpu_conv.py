@@ -53,6 +53,8 @@ CASES = [
     (3, 48, 64, 256, 3, True, 0, False),       # partial last tile (9 segments), several samples per tile
     (2, 64, 256, 128, 3, True, 1, False),      # AvgPool1d(2,2) folded into the load
     (2, 32, 128, 384, 3, True, 2, True),       # nearest x2 folded into the load
+    (3, 48, 256, 256, 3, True, 2, False),      # nearest x2 -> 3-tap conv in polyphase form (up-sampling ResBlock, 256-wide tiles)
+    (2, 96, 512, 512, 3, True, 2, False),      # the same with two N tiles per phase; tiles straddle samples
     (5, 16, 512, 512, 1, False, 0, True),
     (2, 768, 384, 128, 3, True, 0, False),
     (2, 64, 512, 256, 3, True, 0, True),       # long K -> 256-channel tiles (single TMEM accumulator set)
