@@ -353,10 +353,18 @@ __global__ void __launch_bounds__(256) conv_narrow_out_kernel(const ConvParams p
 #pragma unroll
                 for (int c = 0; c < CO; ++c) hw[e][k][c] = c < p.Cout ? __ldg(sg.w + (size_t)((lane * 4 + e) * 3 + k) * p.Cout + c) : 0.f;
     }
+    // (hoisted form: four rows of loads in flight ahead of the row being reduced -- the loop is a chain of load -> SiLU -> 5-step
+    // shuffle reduction per row otherwise, 0.28 ms for a 403 MB read at B = 1024)
+    auto ldrow = [&](int rr) -> float4 {
+        return hoist && rr >= 0 && rr < T && rr <= t1 ? ld4(hb + (size_t)rr * Cin + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    float4 pf0 = ldrow(t0 - 1), pf1 = ldrow(t0), pf2 = ldrow(t0 + 1), pf3 = ldrow(t0 + 2);
     for (int r = t0 - 1; r <= t1; ++r) {   // input rows feeding outputs t0..t1-1
+        const float4 hv_pf = pf0;
+        pf0 = pf1; pf1 = pf2; pf2 = pf3; pf3 = ldrow(r + 4);
         if (r >= 0 && r < T) {
             if (hoist) {
-                const float4 hv = ld4(hb + (size_t)r * Cin + lane * 4);
+                const float4 hv = hv_pf;
                 float v[4] = {hv.x, hv.y, hv.z, hv.w};
                 if (sg.scale) {
                     v[0] = act1(v[0], ha.x, hs.x, sg.silu); v[1] = act1(v[1], ha.y, hs.y, sg.silu);
