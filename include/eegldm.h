@@ -81,6 +81,8 @@ int eegldm_set_conv_cluster(int ctas);
  * bit 7 -- fused producer also for 1x1 convs with more than two N tiles (the qkv conv; measured slower: off);
  * bit 8 -- (default clear) set for epilogue GroupNorm records at the consumer's group width instead of 4 / 8 channels (then the
  *          concat norms with 12- / 24-channel groups need their own pass over the tensor again).
+ * bit 10 -- (default clear) set for one GroupNorm record per 16-position segment everywhere (default: one per 128-row tile where the
+ *          length is a multiple of 128, so that a tile never straddles samples).
  * bit 9 -- (default clear) set to switch OFF the polyphase form of the up-sampling ResBlocks' first conv (nearest x2 -> 3-tap conv
  *          computed on the low-resolution input as an even and an odd output phase with two taps each: a third fewer MMAs).
  * Call before creating models: plans cache the choices. */

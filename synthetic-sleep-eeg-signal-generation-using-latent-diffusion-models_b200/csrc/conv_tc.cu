@@ -536,6 +536,24 @@ __global__ void __launch_bounds__(conv_tc_threads(DIRECT, EPI8), 1) conv_tc_kern
                 asm volatile("bar.sync %0, 128;" ::"r"(1 + eh) : "memory");
                 const float nq = 4.f * cpg;
                 const float2* sw = stats + eh * 1024;
+                if (p.gn_tile) {
+                    // Tout % 128 == 0: the tile's eight segments are one sample's -- ONE record per (tile, group): the 32 equal-count
+                    // moments (8 segments x 4 position quarters) combined by Chan's formula
+                    for (int gi = tid & 127; gi < gpt; gi += 128) {
+                        float msum = 0.f;
+                        for (int i = 0; i < 32; ++i) msum += sw[(i >> 3) * 256 + (i & 7) * gpt + gi].x;
+                        const float mean = msum * (1.f / 32.f);
+                        float m2 = 0.f, dd = 0.f;
+                        for (int i = 0; i < 32; ++i) {
+                            const float2 v = sw[(i >> 3) * 256 + (i & 7) * gpt + gi];
+                            m2 += v.y; dd = fmaf(v.x - mean, v.x - mean, dd);
+                        }
+                        if (m_tile < n_mtiles) {
+                            float* o = p.gn_partial + ((size_t)(p.poly ? 2 * m_tile + ph : m_tile) * (Cr / cpg) + cor / cpg + gi) * 3;
+                            o[0] = 32.f * nq; o[1] = mean; o[2] = fmaf(nq, dd, m2);
+                        }
+                    }
+                } else
                 for (int e = tid & 127; e < 8 * gpt; e += 128) {
                     const int sg = e / gpt, gi = e - sg * gpt, g16 = m_tile * 8 + sg;
                     const float2 a = sw[e], b = sw[256 + e], c = sw[512 + e], d = sw[768 + e];
@@ -1181,6 +1199,7 @@ cudaError_t launch_conv_tc(const TcConvParams& p_in, bool x3, cudaStream_t st) {
     // attention operand images (one-warpgroup epilogue only); cluster sizes 1 and 2
     if (p.qkv16 && (!x3 || p.gn_partial)) return cudaErrorInvalidValue;   // operand-image output: f16x3, two-warpgroup epilogue only
     // polyphase up-conv: one segment of 3 taps, whole N tiles per phase, no residual, two-warpgroup epilogue only
+    if (p.gn_tile && (!p.gn_partial || p.Tout % 128 || p.gn_cpg == 32)) return cudaErrorInvalidValue;   // tile records: two-warpgroup epilogue
     if (p.poly && (p.nseg != 1 || p.seg[0].taps != 3 || p.bn != 256 || (p.Cout / 2) % 256 || p.res || p.qkv16 ||
                    (p.gn_partial && p.gn_cpg == 32)))
         return cudaErrorInvalidValue;
@@ -1203,7 +1222,7 @@ cudaError_t launch_conv_tc(const TcConvParams& p_in, bool x3, cudaStream_t st) {
         g_launch_count += 1;
         return cudaGetLastError();
     }
-    const bool epi8 = (g_conv_tc_epi8 || p.qkv16 || p.poly) && epi8_ok && (p.direct || g_conv_tc_cluster == 2 || g_conv_tc_cluster == 1 || p.qkv16 || p.poly);
+    const bool epi8 = (g_conv_tc_epi8 || p.qkv16 || p.poly || p.gn_tile) && epi8_ok && (p.direct || g_conv_tc_cluster == 2 || g_conv_tc_cluster == 1 || p.qkv16 || p.poly || p.gn_tile);
 #define EEGLDM_TC8(X3, BN)                                                                               \
     (p.direct ? (g_conv_tc_cluster == 1 ? launch_conv_tc_t<X3, BN, 1, false, true, true>(p, num_sms, st)   \
                                         : launch_conv_tc_t<X3, BN, 2, false, true, true>(p, num_sms, st))  \

@@ -254,9 +254,9 @@ ScaleShift plan_gn(Builder& bd, const Act& x0, const Act* x1, int G, const float
         const bool have0 = x0.gn_part != nullptr, have1 = !x1 || x1->gn_part != nullptr;
         const int w0 = have0 ? x0.C / x0.gn_G : 0, w1 = x1 && have1 ? x1->C / x1->gn_G : 0;
         bool ok = have0 && have1 && G <= 256 && C % G == 0 && cpg % w0 == 0;
-        if (ok && x1) ok = x0.gn_nsplit == x1->gn_nsplit && cpg % w1 == 0 && x0.C % w1 == 0;
+        if (ok && x1) ok = cpg % w1 == 0 && x0.C % w1 == 0;
         if (ok) {
-            p.nsplit = x0.gn_nsplit;
+            p.nsplit = x0.gn_nsplit; p.nsplit1 = x1 ? x1->gn_nsplit : 0;
             p.partial = bd.ptr(x0.gn_part); p.rec_G0 = x0.gn_G;
             if (x1) { p.partial1 = bd.ptr(x1->gn_part); p.rec_G1 = x1->gn_G; }
             bd.add([p](cudaStream_t st) { return launch_groupnorm_finalize(p, st); }, 1, OP_GN, 0.0,
@@ -375,6 +375,7 @@ bool g_attn_direct = false;    // the tcgen05 attention splits fp32 q, k, v itse
 bool g_attn_u_fused = true;    // the tcgen05 attention writes proj_out's operand image instead of fp32 (eegldm_set_conv_tuning bit 3)
 bool g_conv_direct = true;     // tensor-pipe convs produce their activation operands in-kernel (no act_split pre-pass)
 bool g_conv_gn_fine = true;        // epilogue GroupNorm records 4 / 8 channels wide (eegldm_set_conv_tuning bit 8 = the consumer's group width instead)
+bool g_conv_gn_tile = true;        // epilogue GroupNorm records per 128-row tile where tiles never straddle samples (eegldm_set_conv_tuning bit 10 = off)
 bool g_conv_poly = true;           // polyphase form of the up-sampling ResBlocks' first conv (eegldm_set_conv_tuning bit 9 = off)
 bool g_conv_direct_wide = false;   // fused producer also for 1x1 convs with more than two N tiles (qkv): eegldm_set_conv_tuning bit 7
 bool g_conv_gn_fused = true;   // tensor-pipe convs emit the GroupNorm statistics of their output (eegldm_set_conv_tuning)
@@ -748,7 +749,9 @@ void plan_conv(Builder& bd, ConvParams p, const uint8_t* tw0 = nullptr, const ui
             if (rec_G % gn_G == 0 && conv_tc_gn_ok(p.Cout, rec_G)) gn_G = rec_G;
         }
         if (out_act && g_conv_gn_fused && conv_tc_gn_ok(p.Cout, gn_G)) {
-            out_act->gn_nsplit = p.Tout / 16; out_act->gn_G = gn_G;
+            // one record per 128-row tile where a tile never straddles samples (kernel-side length % 128 == 0), else per segment
+            q.gn_tile = g_conv_gn_tile && g_conv_tc_epi8 && q.Tout % 128 == 0 && p.Cout / gn_G != 32 ? 1 : 0;
+            out_act->gn_nsplit = q.gn_tile ? p.Tout / 128 : p.Tout / 16; out_act->gn_G = gn_G;
             out_act->gn_part = bd.scratch((size_t)bd.B * out_act->gn_nsplit * gn_G * 3);
             q.gn_partial = bd.ptr(out_act->gn_part); q.gn_cpg = p.Cout / gn_G;
         }
@@ -759,7 +762,8 @@ void plan_conv(Builder& bd, ConvParams p, const uint8_t* tw0 = nullptr, const ui
     // SIMT launches and are kept apart from the GEMM-shaped ones the roofline is quoted on
     // the UNet's input conv (1 -> 128 channels) writes the GroupNorm records of its output like a tensor-pipe conv's epilogue does
     if (out_act && gn_G > 0 && g_conv_gn_fused && g_conv_gn_fine && conv_narrow_in_gn_ok(p) && (p.Cout / 4) % gn_G == 0) {
-        out_act->gn_nsplit = p.Tout / 16; out_act->gn_G = p.Cout / 4;
+        p.gn_rec_tile = g_conv_gn_tile && p.Tout % 128 == 0 ? 1 : 0;
+        out_act->gn_nsplit = p.gn_rec_tile ? p.Tout / 128 : p.Tout / 16; out_act->gn_G = p.Cout / 4;
         out_act->gn_part = bd.scratch((size_t)bd.B * out_act->gn_nsplit * out_act->gn_G * 3);
         p.gn_rec = bd.ptr(out_act->gn_part);
     }
@@ -1424,6 +1428,7 @@ int eegldm_set_conv_tuning(int pair, int bn256_min_stages, int fuse_epilogues) {
     g_conv_direct_wide = (fuse_epilogues & 128) != 0;
     g_conv_gn_fine = (fuse_epilogues & 256) == 0;
     g_conv_poly = (fuse_epilogues & 512) == 0;
+    g_conv_gn_tile = (fuse_epilogues & 1024) == 0;
     g_conv_tc_epi8 = (fuse_epilogues & 64) ? 0 : 1;  // bit 6 switches the two-warpgroup conv epilogue OFF (A/B timing)
     g_conv_tc_cat = (fuse_epilogues & 32) ? 0 : 1;   // bit 5 switches the concatenated hi|lo MMA of the N = 128 tiles OFF (A/B timing)
     if (bn256_min_stages < 1) return fail(EEGLDM_ERR_INVALID, "bn256_min_stages must be >= 1");

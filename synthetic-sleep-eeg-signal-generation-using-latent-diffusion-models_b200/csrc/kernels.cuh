@@ -54,6 +54,7 @@ struct ConvParams {
     int B;
     float* gn_rec;           // optional, narrow-input conv with Cout == 128 and Tout % 16 == 0 only (conv_narrow_in_gn_ok): GroupNorm
                              // records (64, mean, M2) of the output per (sample, 16-position segment, 4-channel group): [B][Tout/16][32][3]
+    int gn_rec_tile;         // 1 (Tout % 128 == 0): one record (512, mean, M2) per 128 positions instead: [B][Tout/128][32][3]
 };
 bool conv_narrow_in_gn_ok(const ConvParams& p);
 
@@ -72,6 +73,7 @@ struct GnParams {
     // norm's G, single source).  Every group of this norm must be a whole number of records of ONE source.
     const float* partial1;
     int rec_G0, rec_G1;
+    int nsplit1;                  // records per sample of source 1 (0: the same as `nsplit`)
 };
 
 struct AttnParams {
@@ -118,6 +120,9 @@ struct TcConvParams {
     int qkv_H, qkv_ch;  //   q/k/v operand images of attn_tc.cu (layout of launch_qkv_split) for qkv_H heads of qkv_ch channels; f16x3 only
     float* gn_partial;  // optional: GroupNorm statistics of `out`, one (count, mean, M2) record per (sample, 16-position segment, group):
     int gn_cpg;         //   [B][Tout/16][Cout/gn_cpg][3]; gn_cpg = channels per group in {4, 8, 16, 32} (conv_tc_gn_ok)
+    int gn_tile;        // 1 (needs Tout % 128 == 0: a 128-row tile never straddles samples; two-warpgroup epilogue): ONE record per
+                        //   (tile, group) instead of eight per-segment ones -- [B][Tout/128][Cout/gn_cpg][3]: an eighth of the record
+                        //   traffic and of gn_finalize's loop
     int direct;         // 1: activation operands produced inside the conv kernel from TcSeg.src0/src1 (no act_split pre-pass)
     int debug;          // timing experiments only (eegldm_bench_conv): 1 = no operand copies, 2 = no MMAs; results are garbage
     int* range_flag;    // optional (fused producer): set to 1 when an operand is outside the f16x3 range (|x| >= 65504 or NaN)

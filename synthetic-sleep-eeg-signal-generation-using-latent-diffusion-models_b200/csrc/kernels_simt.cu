@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(256) conv_narrow_in_kernel(const float* __rest
 // row stores), shifted one-pass sums per lane -- no cross-lane combination at all.
 __global__ void __launch_bounds__(256) conv_narrow_in_gn_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                                  const float* __restrict__ bias, float* __restrict__ out,
-                                                                 float* __restrict__ rec, int Cin, int T, int nsegs) {
+                                                                 float* __restrict__ rec, int Cin, int T, int nsegs, int per) {
     constexpr int Cout = 128;
     extern __shared__ float ws[];   // [Cin*3][Cout] + [Cout]
     for (int i = threadIdx.x; i < Cin * 3 * Cout; i += blockDim.x) ws[i] = w[i];
@@ -291,12 +291,13 @@ __global__ void __launch_bounds__(256) conv_narrow_in_gn_kernel(const float* __r
     const int lane = threadIdx.x & 31, co = lane * 4;
     const int wpb = blockDim.x >> 5;
     const float4 b4 = *reinterpret_cast<const float4*>(ws + Cin * 3 * Cout + co);
+    // per = 16 (a record per 16-position segment) or 128 (T % 128 == 0: a record per 128 positions); nsegs counts records
     for (int seg = blockIdx.x * wpb + (threadIdx.x >> 5); seg < nsegs; seg += gridDim.x * wpb) {
-        const size_t bt0 = (size_t)seg * 16;
-        const int t0 = (int)(bt0 % (size_t)T);                 // T % 16 == 0: a segment never straddles samples
+        const size_t bt0 = (size_t)seg * per;
+        const int t0 = (int)(bt0 % (size_t)T);                 // T % per == 0: a record never straddles samples
         float K = 0.f, s = 0.f, q = 0.f;
 #pragma unroll 4
-        for (int i = 0; i < 16; ++i) {
+        for (int i = 0; i < per; ++i) {
             float4 acc = b4;
             for (int k = 0; k < 3; ++k) {
                 const int u = t0 + i + k - 1;
@@ -315,7 +316,8 @@ __global__ void __launch_bounds__(256) conv_narrow_in_gn_kernel(const float* __r
             q = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, fmaf(d3, d3, q))));
         }
         float* o = rec + ((size_t)seg * 32 + lane) * 3;
-        o[0] = 64.f; o[1] = fmaf(s, 1.f / 64.f, K); o[2] = fmaxf(q - s * s * (1.f / 64.f), 0.f);
+        const float cnt = 4.f * per, icnt = 1.f / cnt;
+        o[0] = cnt; o[1] = fmaf(s, icnt, K); o[2] = fmaxf(q - s * s * icnt, 0.f);
     }
 }
 
@@ -535,9 +537,10 @@ __global__ void gn_finalize_kernel(const GnParams p) {
                     if (lo >= hi || recG <= 0) continue;
                     const float* base = src ? p.partial1 : p.partial;
                     const int w = cs / recG, first = (lo - cb) / w, nrec = (hi - lo) / w;
-                    for (int sp = part; sp < p.nsplit; sp += lanes)
+                    const int ns = src && p.nsplit1 ? p.nsplit1 : p.nsplit;     // records per sample of this source
+                    for (int sp = part; sp < ns; sp += lanes)
                         for (int k = 0; k < nrec; ++k) {
-                            const float* o = base + (((size_t)b * p.nsplit + sp) * recG + first + k) * 3;
+                            const float* o = base + (((size_t)b * ns + sp) * recG + first + k) * 3;
                             Mom m; m.n = o[0]; m.mean = o[1]; m.m2 = o[2];
                             r = mom_combine(r, m);
                         }
@@ -978,9 +981,11 @@ cudaError_t launch_conv_simt(const ConvParams& p, cudaStream_t st) {
         const size_t smem = ((size_t)s0.C0 * 3 * p.Cout + p.Cout) * sizeof(float);
         if (p.gn_rec) {
             if (p.Cout != 128 || p.Tout % 16) return cudaErrorInvalidValue;
-            const int nsegs = (int)((size_t)p.B * p.Tout / 16);
+            const int per = p.gn_rec_tile ? 128 : 16;
+            if (p.Tout % per) return cudaErrorInvalidValue;
+            const int nsegs = (int)((size_t)p.B * p.Tout / per);
             const unsigned nb = (unsigned)std::min<size_t>(((size_t)nsegs + 7) / 8, 148 * 16);
-            conv_narrow_in_gn_kernel<<<nb, 256, smem, st>>>(s0.src0, s0.w, p.bias, p.out, p.gn_rec, s0.C0, p.Tout, nsegs);
+            conv_narrow_in_gn_kernel<<<nb, 256, smem, st>>>(s0.src0, s0.w, p.bias, p.out, p.gn_rec, s0.C0, p.Tout, nsegs, per);
             g_launch_count += 1;
             return cudaGetLastError();
         }
