@@ -48,6 +48,31 @@ def test_unet_forward_matches_reference_golden(built_lib, cuda_device, name, mat
     torch.testing.assert_close(y, torch.from_numpy(g[name + "/y"]), rtol=RTOL, atol=ATOL)
 
 
+# (CTA-pair mask, fuse_epilogues mask) of eegldm_set_conv_tuning: every switch off in turn next to the default (1, 15) -- pairs, operand-image
+# qkv epilogue (2), fused producer (4), attention -> proj_out image (8), wide GroupNorm records (256), polyphase up-conv (512),
+# per-segment records everywhere (1024), two-warpgroup conv epilogue (64), fused producer for the qkv conv (128), pairs on 128-wide tiles
+TUNINGS = [(1, 15), (0, 15), (3, 15), (1, 13), (1, 11), (1, 7), (1, 15 + 256), (1, 15 + 512), (1, 15 + 1024), (1, 15 + 64), (1, 15 + 128)]
+
+
+@pytest.mark.parametrize("tuning", TUNINGS)
+def test_unet_tuning_switches_match_reference_golden(built_lib, cuda_device, tuning):
+    """The full config_ldm.yaml UNet against the reference's own output under every tuning switch: the switches choose kernels and
+    data paths (CTA pairs, epilogue forms, record widths, polyphase up-conv), never results beyond the parity tolerance."""
+    from eegldm import _lib
+    over, B, T, ts = CASES["ldm_per_sample_t"]
+    cfg = ou.full_cfg(**over)
+    sd = ou.make_unet_state_dict(cfg, seed=0)
+    g = np.load(os.path.join(GOLDEN, "unet_golden.npz"))
+    x = torch.from_numpy(g["ldm_per_sample_t/x"]).to(cuda_device)
+    t = torch.from_numpy(g["ldm_per_sample_t/t"])
+    _lib.check(built_lib.eegldm_set_conv_tuning(tuning[0], 1, tuning[1]))
+    try:
+        y = _unet(cfg, sd, cuda_device, "f16x3")(x, timesteps=t).cpu()
+    finally:
+        _lib.check(built_lib.eegldm_set_conv_tuning(1, 1, 15))
+    torch.testing.assert_close(y, torch.from_numpy(g["ldm_per_sample_t/y"]), rtol=RTOL, atol=ATOL)
+
+
 @pytest.mark.parametrize("math", MATH)
 def test_unet_forward_matches_oracle_config2_slice(built_lib, cuda_device, math):
     """Config 2 (one denoise step, config_ldm.yaml) on a B=8 slice, per-sample and shared timesteps."""
