@@ -46,6 +46,25 @@ __global__ void norm_act_fwd_kernel(const float* __restrict__ x, const float* __
     a[i] = v;
 }
 
+// the same, four channels per thread (C % 4 == 0: the UNet's tensors) -- identical per-element arithmetic, a quarter of the index
+// divisions and 128-bit accesses
+__global__ void norm_act_fwd4_kernel(const float* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
+                                     float* __restrict__ a, int C, int T, int silu, size_t total4) {
+    const size_t i4 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i4 >= total4) return;
+    const size_t i = i4 * 4;
+    const int c = (int)(i % C);
+    const size_t b = i / ((size_t)C * T);
+    const float4 xv = *reinterpret_cast<const float4*>(x + i);
+    const float4 sc = *reinterpret_cast<const float4*>(scale + b * C + c), sh = *reinterpret_cast<const float4*>(shift + b * C + c);
+    float v[4] = {fmaf(sc.x, xv.x, sh.x), fmaf(sc.y, xv.y, sh.y), fmaf(sc.z, xv.z, sh.z), fmaf(sc.w, xv.w, sh.w)};
+    if (silu) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[e] = v[e] * sigmoid_f(v[e]);
+    }
+    *reinterpret_cast<float4*>(a + i) = make_float4(v[0], v[1], v[2], v[3]);
+}
+
 // Conv1d backward w.r.t. its input.  The conv consumed u = upsample?(a) with length Tc, stride s, left pad p:
 //   y[t][co] = sum_{k,ci} W[ci][k][co] * u[t*s + k - p][ci]        da[b][i][ci] (+)= sum over the conv-input rows that read a[i]
 __global__ void conv_bwd_data_kernel(const float* __restrict__ dy, const float* __restrict__ w, float* __restrict__ da, int Cin,
@@ -557,6 +576,39 @@ __global__ void norm_act_bwd_apply_kernel(const float* __restrict__ da, const fl
     dx[i] = accumulate ? dx[i] + r : r;
 }
 
+// the same, four channels per thread (C % 4 == 0 and (C/G) % 4 == 0: the four channels share a group)
+__global__ void norm_act_bwd_apply4_kernel(const float* __restrict__ da, const float* __restrict__ x, const float* __restrict__ mean,
+                                           const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                           const float* __restrict__ beta, const float* __restrict__ m12, float* __restrict__ dx, int C,
+                                           int T, int G, int silu, int accumulate, size_t total4) {
+    const size_t i4 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i4 >= total4) return;
+    const size_t i = i4 * 4;
+    const int c = (int)(i % C);
+    const size_t b = i / ((size_t)C * T);
+    const int g = c / (C / G);
+    const float mu = mean[b * G + g], rs = rstd[b * G + g], m1 = m12[(b * G + g) * 2], m2 = m12[(b * G + g) * 2 + 1];
+    const float4 xv = *reinterpret_cast<const float4*>(x + i), dv4 = *reinterpret_cast<const float4*>(da + i);
+    const float4 ga4 = *reinterpret_cast<const float4*>(gamma + c), be4 = *reinterpret_cast<const float4*>(beta + c);
+    const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, ds[4] = {dv4.x, dv4.y, dv4.z, dv4.w};
+    const float gs[4] = {ga4.x, ga4.y, ga4.z, ga4.w}, bs[4] = {be4.x, be4.y, be4.z, be4.w};
+    float r[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const float xh = (xs[e] - mu) * rs;
+        const float v = fmaf(xh, gs[e], bs[e]);
+        float dv = ds[e];
+        if (silu) { const float sg = sigmoid_f(v); dv *= sg * (1.f + v * (1.f - sg)); }
+        r[e] = rs * (dv * gs[e] - m1 - xh * m2);
+    }
+    float4 o = make_float4(r[0], r[1], r[2], r[3]);
+    if (accumulate) {
+        const float4 p = *reinterpret_cast<const float4*>(dx + i);
+        o = make_float4(p.x + o.x, p.y + o.y, p.z + o.z, p.w + o.w);
+    }
+    *reinterpret_cast<float4*>(dx + i) = o;
+}
+
 __global__ void axpy_kernel(const float* __restrict__ src, float* __restrict__ dst, float alpha, int accumulate, size_t n) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = accumulate ? dst[i] + alpha * src[i] : alpha * src[i];
@@ -754,7 +806,10 @@ cudaError_t launch_norm_act_fwd(const float* x, const float* scale, const float*
                                 cudaStream_t st) {
     const size_t total = (size_t)B * T * C;
     if (!total) return cudaSuccess;
-    norm_act_fwd_kernel<<<blocks_for(total), 256, 0, st>>>(x, scale, shift, a, C, T, silu, total);
+    const bool al16 = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(scale) |
+                        reinterpret_cast<uintptr_t>(shift)) & 15) == 0;
+    if (C % 4 == 0 && al16) norm_act_fwd4_kernel<<<blocks_for(total / 4), 256, 0, st>>>(x, scale, shift, a, C, T, silu, total / 4);
+    else norm_act_fwd_kernel<<<blocks_for(total), 256, 0, st>>>(x, scale, shift, a, C, T, silu, total);
     g_launch_count += 1;
     return cudaGetLastError();
 }
@@ -831,8 +886,14 @@ cudaError_t launch_norm_act_bwd(const NormGradParams& p, cudaStream_t st) {
     dim3 grid(p.G, p.B);
     norm_act_bwd_reduce_kernel<<<grid, 256, 0, st>>>(p.da, p.x, p.mean, p.rstd, p.gamma, p.beta, p.m12, p.dgamma, p.dbeta, p.C, p.T, p.G, p.silu);
     const size_t total = (size_t)p.B * p.T * p.C;
-    norm_act_bwd_apply_kernel<<<blocks_for(total), 256, 0, st>>>(p.da, p.x, p.mean, p.rstd, p.gamma, p.beta, p.m12, p.dx, p.C, p.T, p.G, p.silu,
-                                                                p.accumulate, total);
+    const bool al16 = ((reinterpret_cast<uintptr_t>(p.da) | reinterpret_cast<uintptr_t>(p.x) | reinterpret_cast<uintptr_t>(p.dx) |
+                        reinterpret_cast<uintptr_t>(p.gamma) | reinterpret_cast<uintptr_t>(p.beta)) & 15) == 0;
+    if (p.C % 4 == 0 && (p.C / p.G) % 4 == 0 && al16)
+        norm_act_bwd_apply4_kernel<<<blocks_for(total / 4), 256, 0, st>>>(p.da, p.x, p.mean, p.rstd, p.gamma, p.beta, p.m12, p.dx, p.C, p.T, p.G,
+                                                                          p.silu, p.accumulate, total / 4);
+    else
+        norm_act_bwd_apply_kernel<<<blocks_for(total), 256, 0, st>>>(p.da, p.x, p.mean, p.rstd, p.gamma, p.beta, p.m12, p.dx, p.C, p.T, p.G, p.silu,
+                                                                    p.accumulate, total);
     g_launch_count += 2;
     return cudaGetLastError();
 }
