@@ -106,7 +106,8 @@ template <bool X3, bool DIRECT>
 __global__ void __launch_bounds__(DIRECT ? 2 * NUM_THREADS : ATTN_THREADS, 1) attn_tc_kernel(const AttnTcParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int T = p.T, ch = p.ch;
-    const int SB = stage_bytes(T), PH = p_half_bytes(T), NST = attn_stages(T);
+    const int Tk = p.Tk ? p.Tk : T, nkb = T / Tk;   // keys of this CTA's block; nkb > 1: partial outputs, merged by attn_merge_kernel
+    const int SB = stage_bytes(Tk), PH = p_half_bytes(Tk), NST = attn_stages(Tk);
     const uint32_t sbase = smem_u32(smem);
     const uint32_t sStage = sbase, sP = sbase + NST * SB, bars = sP + 2 * PH;
     // Stage slots.  The S phase streams 40 KB per k-step and is bound by the load round trip; the two P buffers are idle until the
@@ -120,8 +121,8 @@ __global__ void __launch_bounds__(DIRECT ? 2 * NUM_THREADS : ATTN_THREADS, 1) at
     auto slot_addr = [&](int i) -> uint32_t { return i < NST ? sStage + i * SB : sP + (i - NST) * SB; };
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int mt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-    const int nks = ch / 32, nchunk = ch / 128, nss = T / 32;
+    const int mt = blockIdx.x / nkb, kblk = blockIdx.x - mt * nkb, key0 = kblk * Tk, h = blockIdx.y, b = blockIdx.z;
+    const int nks = ch / 32, nchunk = ch / 128, nss = Tk / 32;
     const int nseg = min(8, (T >> 4) - 8 * mt);   // 16-position segments of this query tile (rows nseg*16 .. 127 of the MMA are unused)
     const size_t plane = (size_t)4 * ch * T;
     const uint8_t* gq = p.qkv16 + ((size_t)b * p.H + h) * 3 * plane;
@@ -218,7 +219,9 @@ __global__ void __launch_bounds__(DIRECT ? 2 * NUM_THREADS : ATTN_THREADS, 1) at
         }
         if (tl) tl2 = clock64();
         const float inv = 1.0f / sum;
-        float* orow = p.out + ((size_t)b * T + t) * ((size_t)p.H * ch) + (size_t)h * ch;
+        if (nkb > 1 && wg == 0 && rowv) p.part_ml[(((size_t)kblk * p.B + b) * p.H + h) * T + t] = make_float2(mxs, sum);
+        float* orow = (nkb > 1 ? p.part_out + (size_t)kblk * p.B * T * ((size_t)p.H * ch) : p.out) + ((size_t)b * T + t) * ((size_t)p.H * ch) +
+                      (size_t)h * ch;
         const int ob0 = NWG == 1 ? 0 : wg * 64, ob1 = NWG == 1 ? 128 : ob0 + 64;   // this warpgroup's columns of every output chunk
         for (int c = 0; c < nchunk; ++c) {
             const int buf = c & 1;
@@ -345,8 +348,8 @@ __global__ void __launch_bounds__(DIRECT ? 2 * NUM_THREADS : ATTN_THREADS, 1) at
         // ================================================================ loader (pre-split images; idle in the DIRECT form)
         if (lane == 0 && !DIRECT) {
             uint32_t phE = 0;   // bit i: parity of the completed waits on slot i's "empty" barrier
-            const uint32_t qb = (uint32_t)nseg * 1024, kb = (uint32_t)T * 64;   // the tile's 16*nseg query rows
-            const size_t qhalf = kb;
+            const uint32_t qb = (uint32_t)nseg * 1024, kb = (uint32_t)Tk * 64;   // the tile's 16*nseg query rows; this block's keys
+            const size_t qhalf = (size_t)T * 64;                                  // bytes of one (k-step, hi | lo) plane of Q and of K
             for (int ks = 0; ks < nks; ++ks) {
                 const int st = ks % NSS;
                 const uint32_t dst = slot_addr(st);
@@ -354,12 +357,12 @@ __global__ void __launch_bounds__(DIRECT ? 2 * NUM_THREADS : ATTN_THREADS, 1) at
                 phE ^= 1u << st;
                 mbar_arrive_expect_tx(barFull + 8 * st, X3 ? 2 * (qb + kb) : qb + kb);
                 const uint8_t* qs = gq + ((size_t)ks * 2) * qhalf + (size_t)mt * 16 * 512;
-                const uint8_t* ks_ = gk + ((size_t)ks * 2) * kb;
+                const uint8_t* ks_ = gk + ((size_t)ks * 2) * qhalf + (size_t)key0 * 64;
                 bulk_copy_g2s(dst, qs, qb, barFull + 8 * st);
                 bulk_copy_g2s(dst + 2 * Q_HALF, ks_, kb, barFull + 8 * st);
                 if (X3) {
                     bulk_copy_g2s(dst + Q_HALF, qs + qhalf, qb, barFull + 8 * st);
-                    bulk_copy_g2s(dst + 2 * Q_HALF + kb, ks_ + kb, kb, barFull + 8 * st);
+                    bulk_copy_g2s(dst + 2 * Q_HALF + kb, ks_ + qhalf, kb, barFull + 8 * st);
                 }
             }
             int it = 0;
@@ -368,7 +371,7 @@ __global__ void __launch_bounds__(DIRECT ? 2 * NUM_THREADS : ATTN_THREADS, 1) at
                     const int st = it % NST, n = min(VP, nss - ss);
                     mbar_wait(barEmpty + 8 * st, ((phE >> st) & 1) ^ 1);
                     phE ^= 1u << st;
-                    const uint8_t* src = gv + ((size_t)c * nss + ss) * 2 * V_HALF;
+                    const uint8_t* src = gv + ((size_t)c * (T >> 5) + (key0 >> 5) + ss) * 2 * V_HALF;
                     if (X3) {   // hi and lo of n consecutive 32-key stages are contiguous in the V image: one copy
                         mbar_arrive_expect_tx(barFull + 8 * st, (uint32_t)n * 2 * V_HALF);
                         bulk_copy_g2s(slot_addr(st), src, (uint32_t)n * 2 * V_HALF, barFull + 8 * st);
@@ -381,7 +384,7 @@ __global__ void __launch_bounds__(DIRECT ? 2 * NUM_THREADS : ATTN_THREADS, 1) at
     } else {
         // ================================================================ MMA issuer
         if (lane == 0) {
-            const uint32_t idescS = make_idesc(0u, 128u, (uint32_t)T);
+            const uint32_t idescS = make_idesc(0u, 128u, (uint32_t)Tk);
             constexpr uint32_t idescO = make_idesc(0u, 128u, 128u, 1u);   // B (= V) is MN-major
             uint32_t phF = 0;   // bit i: parity of the next wait on slot i's "full" barrier
             uint32_t acc = 0, acc2 = 0;
@@ -390,7 +393,7 @@ __global__ void __launch_bounds__(DIRECT ? 2 * NUM_THREADS : ATTN_THREADS, 1) at
                 mbar_wait(barFull + 8 * st, (phF >> st) & 1);
                 phF ^= 1u << st;
                 tc_fence_after();
-                const uint32_t q_hi = slot_addr(st), q_lo = q_hi + Q_HALF, k_hi = q_hi + 2 * Q_HALF, k_lo = k_hi + T * 64;
+                const uint32_t q_hi = slot_addr(st), q_lo = q_hi + Q_HALF, k_hi = q_hi + 2 * Q_HALF, k_lo = k_hi + Tk * 64;
 #pragma unroll
                 for (int kk = 0; kk < 2; ++kk) {
                     const uint64_t dah = make_desc(q_hi + kk * 256, 128, 512), dbh = make_desc(k_hi + kk * 256, 128, 512);
@@ -448,8 +451,50 @@ __global__ void __launch_bounds__(DIRECT ? 2 * NUM_THREADS : ATTN_THREADS, 1) at
 
 }  // namespace
 
+// out[b][t][h*ch + c] = sum_kb w_kb O_kb / sum_kb w_kb,  w_kb = exp2(m_kb - max_kb m_kb) * l_kb  (the key blocks' partial softmaxes merged)
+__global__ void attn_merge_kernel(const float* __restrict__ part, const float2* __restrict__ ml, float* __restrict__ out, int nkb, int B, int T,
+                                  int H, int ch, size_t total4) {
+    const size_t i4 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i4 >= total4) return;
+    const size_t i = i4 * 4, C = (size_t)H * ch;
+    const int c = (int)(i % C), h = c / ch;
+    const size_t bt = i / C;
+    const int t = (int)(bt % T);
+    const size_t b = bt / T;
+    float m = -INFINITY, w[8];
+    for (int kb = 0; kb < nkb; ++kb) m = fmaxf(m, ml[(((size_t)kb * B + b) * H + h) * T + t].x);
+    float W = 0.f;
+    for (int kb = 0; kb < nkb; ++kb) {
+        const float2 v = ml[(((size_t)kb * B + b) * H + h) * T + t];
+        w[kb] = exp2f(v.x - m) * v.y;
+        W += w[kb];
+    }
+    const float iW = 1.0f / W;
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int kb = 0; kb < nkb; ++kb) {
+        const float4 pv = *reinterpret_cast<const float4*>(part + (size_t)kb * B * T * C + i);
+        const float f = w[kb] * iW;
+        o.x = fmaf(f, pv.x, o.x); o.y = fmaf(f, pv.y, o.y); o.z = fmaf(f, pv.z, o.z); o.w = fmaf(f, pv.w, o.w);
+    }
+    *reinterpret_cast<float4*>(out + i) = o;
+}
+
 bool attn_direct_eligible(int T, int ch) { return attn_tc_eligible(T, ch) && (128 + T) * 4 <= 7 * NUM_THREADS; }
-bool attn_tc_eligible(int T, int ch) { return T >= 32 && T <= 256 && T % 32 == 0 && ch >= 128 && ch % 128 == 0; }
+// keys per CTA: the whole sequence up to 256 (one score tile in TMEM); longer sequences in blocks merged afterwards
+int attn_tc_key_block(int T) {
+    if (T <= 256) return T;
+    for (int tk : {256, 192, 128}) if (T % tk == 0 && T / tk <= 8) return tk;
+    return 0;
+}
+bool attn_tc_eligible(int T, int ch) {
+    return T >= 32 && T % 32 == 0 && ch >= 128 && ch % 128 == 0 && attn_tc_key_block(T) > 0 && (T <= 256 || T % 16 == 0);
+}
+size_t attn_tc_scratch_bytes(int B, int T, int H, int ch) {
+    const int tk = attn_tc_key_block(T);
+    if (tk <= 0 || tk == T) return 0;
+    const size_t nkb = (size_t)(T / tk);
+    return nkb * B * T * ((size_t)H * ch * sizeof(float) + (size_t)H * sizeof(float2));
+}
 size_t attn_qkv16_bytes(int B, int T, int H, int ch) { return (size_t)B * H * 12 * ch * T; }
 
 cudaError_t launch_qkv_split(const float* qkv, uint8_t* dst, int B, int T, int H, int ch, cudaStream_t st, int* range_flag) {
@@ -460,9 +505,18 @@ cudaError_t launch_qkv_split(const float* qkv, uint8_t* dst, int B, int T, int H
     return cudaGetLastError();
 }
 
-cudaError_t launch_attention_tc(const AttnTcParams& p, bool x3, cudaStream_t st) {
-    if (p.B <= 0) return cudaSuccess;
-    const int smem = attn_stages(p.T) * stage_bytes(p.T) + 2 * p_half_bytes(p.T) + 256 + 2048;
+cudaError_t launch_attention_tc(const AttnTcParams& p_in, bool x3, cudaStream_t st) {
+    if (p_in.B <= 0) return cudaSuccess;
+    AttnTcParams p = p_in;
+    const int Tk = attn_tc_key_block(p.T);
+    if (Tk <= 0) return cudaErrorInvalidValue;
+    const int nkb = p.T / Tk;
+    if (nkb > 1) {   // key blocks + merge: fp32 output only, pre-split operand images, scratch from attn_tc_scratch_bytes
+        if (!p.part_out || !p.out || p.out_u || p.qkv32) return cudaErrorInvalidValue;
+        p.Tk = Tk;
+        p.part_ml = reinterpret_cast<float2*>(p.part_out + (size_t)nkb * p.B * p.T * ((size_t)p.H * p.ch));
+    } else p.Tk = 0;
+    const int smem = attn_stages(Tk) * stage_bytes(Tk) + 2 * p_half_bytes(Tk) + 256 + 2048;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -472,7 +526,7 @@ cudaError_t launch_attention_tc(const AttnTcParams& p, bool x3, cudaStream_t st)
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    dim3 grid((p.T + 127) / 128, p.H, p.B);
+    dim3 grid((unsigned)((p.T + 127) / 128 * nkb), p.H, p.B);
     if (p.qkv32) {
         if ((128 + p.T) * 4 > 7 * NUM_THREADS) return cudaErrorInvalidValue;   // producer item budget: T <= 208 (attn_direct_eligible)
         if (x3) attn_tc_kernel<true, true><<<grid, 2 * NUM_THREADS, smem, st>>>(p);
@@ -480,6 +534,11 @@ cudaError_t launch_attention_tc(const AttnTcParams& p, bool x3, cudaStream_t st)
     } else if (x3) attn_tc_kernel<true, false><<<grid, ATTN_THREADS, smem, st>>>(p);
     else attn_tc_kernel<false, false><<<grid, ATTN_THREADS, smem, st>>>(p);
     g_launch_count += 1;
+    if (nkb > 1) {
+        const size_t total4 = (size_t)p.B * p.T * p.H * p.ch / 4;
+        attn_merge_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(p.part_out, p.part_ml, p.out, nkb, p.B, p.T, p.H, p.ch, total4);
+        g_launch_count += 1;
+    }
     return cudaGetLastError();
 }
 

@@ -830,7 +830,9 @@ Act plan_attn(Builder& bd, const ULayer& l, const Act& x) {
     }
     // tensor-pipe attention followed by a tensor-pipe proj_out: the attention epilogue writes proj_out's fp16 hi/lo operand
     // image directly (no fp32 attention output, no pre-pass / producer for the 1x1 conv)
-    const bool fuse_proj = attn_tc && g_attn_u_fused && l.t_wproj && x.T % 16 == 0 && conv_tc_eligible(l.ch, 0, l.ch, x.T, 1, 1);
+    // (sequences longer than one 256-key score tile run as key blocks merged into an fp32 output: no operand-image epilogue there)
+    const bool attn_split = attn_tc && attn_tc_key_block(x.T) != x.T;
+    const bool fuse_proj = attn_tc && !attn_split && g_attn_u_fused && l.t_wproj && x.T % 16 == 0 && conv_tc_eligible(l.ch, 0, l.ch, x.T, 1, 1);
     std::shared_ptr<Buf> au;
     Act a;
     if (fuse_proj) au = bd.scratch((act_split_bytes((int)((long long)bd.B * x.T / 16), l.ch) + 3) / 4);
@@ -848,7 +850,12 @@ Act plan_attn(Builder& bd, const ULayer& l, const Act& x) {
         }
         AttnTcParams tp{qdst, fuse_proj ? nullptr : bd.wptr(a), T, H, hch, B, 1.4426950408889634f / sqrtf((float)hch),
                         fuse_proj ? reinterpret_cast<uint8_t*>(bd.ptr(au)) : nullptr, attn_direct ? bd.ptr(qkv) : nullptr};
-        bd.add([tp, x3](cudaStream_t st) { return launch_attention_tc(tp, x3, st); }, 1, OP_ATTN,
+        std::shared_ptr<Buf> part;
+        if (attn_split) {   // partial outputs + (max, sum) per key block
+            part = bd.scratch((attn_tc_scratch_bytes(B, T, H, hch) + 3) / 4);
+            tp.part_out = bd.ptr(part);
+        }
+        bd.add([tp, x3](cudaStream_t st) { return launch_attention_tc(tp, x3, st); }, attn_split ? 2 : 1, OP_ATTN,
                4.0 * B * (double)T * T * l.ch, 4.0 * B * (double)T * l.ch * 4.0);
     } else {
         AttnParams ap{};
@@ -2143,6 +2150,7 @@ int eegldm_test_attention(const float* qkv_dev, int B, int T, int H, int ch, int
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t ce;
     uint8_t* q16 = nullptr;
+    float* part = nullptr;
     if (math != EEGLDM_MATH_FP32_SIMT) {
         if (!attn_tc_eligible(T, ch)) return fail(EEGLDM_ERR_SHAPE, "shape not eligible for the tcgen05 attention");
         if (g_attn_direct && attn_direct_eligible(T, ch)) {   // q, k, v split inside the kernel
@@ -2152,6 +2160,9 @@ int eegldm_test_attention(const float* qkv_dev, int B, int T, int H, int ch, int
             CU(cudaMalloc((void**)&q16, attn_qkv16_bytes(B, T, H, ch)));
             ce = launch_qkv_split(qkv_dev, q16, B, T, H, ch, st);
             AttnTcParams tp{q16, out_dev, T, H, ch, B, 1.4426950408889634f / sqrtf((float)ch)};
+            const size_t sb = attn_tc_scratch_bytes(B, T, H, ch);   // T > 256: key blocks + merge
+            if (ce == cudaSuccess && sb) ce = cudaMalloc((void**)&part, sb);
+            tp.part_out = part;
             if (ce == cudaSuccess) ce = launch_attention_tc(tp, math == EEGLDM_MATH_F16X3_TC, st);
         }
     } else {
@@ -2160,6 +2171,7 @@ int eegldm_test_attention(const float* qkv_dev, int B, int T, int H, int ch, int
     }
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
     if (q16) cudaFree(q16);
+    if (part) cudaFree(part);
     if (ce != cudaSuccess) return cuda_fail(ce, "attention launch");
     return EEGLDM_OK;
 }

@@ -169,8 +169,16 @@ struct AttnTcParams {
     const float* qkv32;     // optional (then `qkv16` is unused): fp32 qkv [B][T][H*3*ch]; q, k, v are split to fp16 hi/lo inside the
                             // kernel (attn_direct_eligible), no launch_qkv_split pass
     unsigned long long* timeline;   // optional (eegldm_bench_attention): 8 cycle counters per CTA, see attn_tc.cu
+    // long sequences (T > 256: the raw-signal DM variant, sample_trials_ddpm.py, T = 768): keys are processed in blocks of Tk
+    // (attn_tc_key_block) by separate CTAs; each writes its softmax-normalised partial output and the row's (max, sum) of its block,
+    // launch_attention_tc then merges the blocks (flash-decoding style split over the keys).  Set by launch_attention_tc.
+    int Tk;                 // keys per CTA (0 / T: all of them, no merge)
+    float* part_out;        // [T/Tk][B][T][H*ch] fp32
+    float2* part_ml;        // [T/Tk][B][H][T]: (row max in log2 units, row sum) of the block
 };
 bool attn_tc_eligible(int T, int ch);
+int attn_tc_key_block(int T);                               // keys per CTA: T for T <= 256, else the largest of 256 / 192 / 128 dividing T
+size_t attn_tc_scratch_bytes(int B, int T, int H, int ch);  // part_out + part_ml for T > 256 (0 otherwise); pass as AttnTcParams.part_out
 bool attn_direct_eligible(int T, int ch);   // in-kernel fp32 -> fp16 hi/lo split of q, k, v (T <= 208)
 size_t attn_qkv16_bytes(int B, int T, int H, int ch);
 cudaError_t launch_qkv_split(const float* qkv, uint8_t* dst, int B, int T, int H, int ch, cudaStream_t st, int* range_flag = nullptr);

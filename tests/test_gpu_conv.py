@@ -152,7 +152,9 @@ def test_conv_epilogue_groupnorm_statistics(built_lib, cuda_device, case):
     torch.testing.assert_close(rstd.cpu().double(), 1.0 / torch.sqrt(ref_var + 1e-6), rtol=2e-5, atol=1e-6)
 
 
-ATTN_CASES = [(2, 192, 1, 512), (1, 128, 1, 128), (3, 64, 2, 128), (2, 256, 1, 256), (1, 32, 4, 128)]
+ATTN_CASES = [(2, 192, 1, 512), (1, 128, 1, 128), (3, 64, 2, 128), (2, 256, 1, 256), (1, 32, 4, 128),
+              # longer than one 256-key score tile: key blocks of 256 / 192 / 256 merged afterwards (the raw-signal DM variant's T = 768)
+              (2, 768, 1, 512), (1, 384, 2, 128), (3, 512, 1, 256)]
 
 
 @pytest.mark.parametrize("case", ATTN_CASES)

@@ -17,6 +17,7 @@ ap.add_argument("--warmup", type=int, default=2, help="untimed forwards before t
 ap.add_argument("--pair", type=int, default=1)
 ap.add_argument("--bn256", type=int, default=1)
 ap.add_argument("--gnfuse", type=int, default=15)
+ap.add_argument("--length", type=int, default=768, help="input length (3072: the raw-signal DM variant, attention at T = 768)")
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 _lib.check(eegldm.lib().eegldm_set_conv_cluster(a.cluster))
@@ -25,7 +26,7 @@ cfg = ou.full_cfg()
 m = eegldm.UNetModel(**cfg, math=a.math)
 m.load_state_dict(ou.make_unet_state_dict(cfg, 0))
 m = m.to(dev).eval()
-x = torch.randn(a.batch, 1, 768, device=dev)
+x = torch.randn(a.batch, 1, a.length, device=dev)
 t = torch.tensor([500])
 for _ in range(a.warmup):
     m(x, timesteps=t)
