@@ -341,6 +341,25 @@ def measure_config2(args, dev, unet):
     return out
 
 
+def measure_dm_variant(args, dev, unet):
+    """one denoise step of the raw-signal DM variant (sample_trials_ddpm.py:83-102): the same UNet on [B,1,3072], attention at
+    T = 768 (tcgen05 attention split over three key blocks).  No CPU leg (the oracle needs minutes per window at this length)."""
+    import torch
+    B = 64
+    x = torch.randn(B, 1, 4 * T_LATENT, generator=torch.Generator().manual_seed(0)).to(dev)
+    t = torch.randint(0, 1000, (B,), generator=torch.Generator().manual_seed(1)).to(dev)
+    ms = _events_ms(torch, lambda: unet(x, timesteps=t), 5, 3)
+    peaks = _peaks()
+    # 4 x the latent forward (convs scale with the length) + the attention's extra share: six blocks of 4 T^2 C FLOPs at T = 768 are 7.25
+    # GFLOP, of which 4 x 0.453 are already in the first term
+    gflop = 4 * UNET_GFLOP_PER_FWD + 5.44
+    tf = B * gflop * 1e9 / (ms / 1e3) / 1e12
+    return {"workload": "8f-4: one UNet denoise step of the raw-signal DM variant, batch 64 x [1,3072], attention at T = 768",
+            "value": B / (ms / 1e3), "unit": "UNet evaluations/s", "ms_per_step": ms,
+            "roofline": {"bound": "tensor", "achieved": tf, "peak": peaks["tc_sustained"], "unit": "TFLOP/s", "frac": tf / peaks["tc_sustained"],
+                         "traffic": None, "note": "whole forward (%.1f GFLOP algorithmic per sample) against the sustained bf16 peak" % gflop}}
+
+
 def measure_ldm_train(args, dev, B=64, with_cpu=True):
     """one latent-diffusion training step (training.py:420-443) of the config_ldm.yaml UNet, batch B x [1,768] latents:
     add_noise, forward, MSE against the noise, backward, Adam lr 1e-4; tensor-pipe convs in f16x3 (forward, data and weight gradients)."""
@@ -564,7 +583,8 @@ def run_ours(args):
         configs = {"config2_unet_step_b256": measure_config2(args, dev, unet),
                    "config1_aekl_encode_decode_b4": measure_config1(args, dev),
                    "config5_aekl_train_step_b512": measure_train(args, dev),
-                   "ldm_train_step_b64": measure_ldm_train(args, dev)}
+                   "ldm_train_step_b64": measure_ldm_train(args, dev),
+                   "dm_variant_unet_step_b64": measure_dm_variant(args, dev, unet)}
         # fast mode: ONE bf16 product per MAC -- reported apart, never as parity: its error against the parity mode is below
         y16 = eegldm.ddim_sample(unet, sched, noise, DDIM_STEPS, aekl)
         ub = eegldm.UNetModel(**synthetic.LDM_UNET_CFG, math="bf16")
