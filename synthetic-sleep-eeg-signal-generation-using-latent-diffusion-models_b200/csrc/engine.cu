@@ -2106,13 +2106,19 @@ int eegldm_bench_attention(int B, int T, int H, int ch, int reps, float* ms_out,
     cudaStream_t st = (cudaStream_t)stream;
     float* qkv = nullptr; uint8_t *q16 = nullptr, *ou = nullptr; unsigned long long* tl = nullptr;
     const size_t nq = (size_t)B * T * H * 3 * ch;
-    const size_t nctas = (size_t)B * H * ((T + 127) / 128);
+    const size_t nctas = (size_t)B * H * ((T + 127) / 128) * (T / std::max(attn_tc_key_block(T), 1));
     cudaError_t ce = cudaMalloc((void**)&qkv, nq * 4);
     if (ce == cudaSuccess) ce = cudaMalloc((void**)&q16, attn_qkv16_bytes(B, T, H, ch));
     if (ce == cudaSuccess) ce = cudaMalloc((void**)&ou, act_split_bytes((int)((long long)B * T / 16), H * ch));
     if (ce == cudaSuccess) ce = cudaMalloc((void**)&tl, nctas * 8 * sizeof(unsigned long long));
     if (ce == cudaSuccess) { bench_fill_kernel<<<1024, 256, 0, st>>>(qkv, nq, 7u); ce = launch_qkv_split(qkv, q16, B, T, H, ch, st); }
     AttnTcParams tp{q16, nullptr, T, H, ch, B, 1.4426950408889634f / sqrtf((float)ch), ou, nullptr, nullptr};
+    float *part = nullptr, *out32 = nullptr;
+    if (const size_t sb = attn_tc_scratch_bytes(B, T, H, ch)) {   // T > 256: key blocks merged into an fp32 output
+        if (ce == cudaSuccess) ce = cudaMalloc((void**)&part, sb);
+        if (ce == cudaSuccess) ce = cudaMalloc((void**)&out32, (size_t)B * T * H * ch * sizeof(float));
+        tp.out = out32; tp.out_u = nullptr; tp.part_out = part;
+    }
     if (ce == cudaSuccess) ce = launch_attention_tc(tp, true, st);   // warm-up
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (ce == cudaSuccess) ce = cudaEventCreate(&e0);
@@ -2139,7 +2145,7 @@ int eegldm_bench_attention(int B, int T, int H, int ch, int reps, float* ms_out,
         for (int j = 1; j < 5; ++j) timeline_out[j] /= (double)nctas;
         timeline_out[7] = (double)nctas;
     }
-    cudaFree(qkv); cudaFree(q16); cudaFree(ou); cudaFree(tl);
+    cudaFree(qkv); cudaFree(q16); cudaFree(ou); cudaFree(tl); cudaFree(part); cudaFree(out32);
     if (ce != cudaSuccess) return cuda_fail(ce, "attention bench");
     return EEGLDM_OK;
 }

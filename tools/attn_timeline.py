@@ -16,9 +16,9 @@ torch.cuda.set_device(0)
 torch.zeros(1, device="cuda")
 L = eegldm.lib()
 print(f"{'shape':22}{'ms':>8}{'TF':>9}{'CTAs':>8}{'S phase':>10}{'softmax':>10}{'PV+epi':>10}{'total':>10}")
-for (T, H, ch) in [(192, 1, 512), (128, 1, 512), (256, 1, 512), (192, 4, 128)]:
+for (T, H, ch) in [(192, 1, 512), (128, 1, 512), (256, 1, 512), (192, 4, 128), (768, 1, 512)]:
     m = C.c_float()
     tl = (C.c_double * 8)()
-    _lib.check(L.eegldm_bench_attention(a.batch, T, H, ch, a.reps, C.byref(m), tl, None))
-    fl = 4.0 * a.batch * T * T * H * ch
+    _lib.check(L.eegldm_bench_attention(a.batch if T <= 256 else max(a.batch // 8, 1), T, H, ch, a.reps, C.byref(m), tl, None))
+    fl = 4.0 * (a.batch if T <= 256 else max(a.batch // 8, 1)) * T * T * H * ch
     print(f"T{T} H{H} ch{ch}".ljust(22) + f"{m.value:8.3f}{fl / m.value / 1e9:9.1f}{tl[7]:8.0f}{tl[1]:10.0f}{tl[2]:10.0f}{tl[3]:10.0f}{tl[4]:10.0f}", flush=True)
