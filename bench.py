@@ -567,6 +567,11 @@ def run_ours(args):
                 "launch_set": "profile family 'conv' = the tcgen05 conv launches only (narrow fp32 convs: family 'conv_narrow'); "
                               "flops, bytes, time and the ncu traffic are all averaged over this one set",
                 # whole-step view against both ceilings (13.90 GFLOP, 25.2 MB per forward per sample)
+                # cross-check against the timed (graph-replayed) region: the profiled leg launches eagerly with events around every
+                # kernel, so its clock state is not the timed legs'; `profile_over_timed_step` = profiled kernel time per denoise step /
+                # timed time per denoise step, and `achieved_scaled_to_timed_step` is `achieved` at the timed region's speed
+                "profile_over_timed_step": (tot / psteps) / (ms / args.steps / DDIM_STEPS),
+                "achieved_scaled_to_timed_step": ach * (tot / psteps) / (ms / args.steps / DDIM_STEPS),
                 "step_tensor_frac": value / world * DDIM_STEPS * UNET_GFLOP_PER_FWD * 1e9 / (peak_tc * 1e12),
                 "step_hbm_frac": value / world * DDIM_STEPS * UNET_MB_PER_FWD * 1e6 / (peaks["hbm"] * 1e9)}
         prof = {k: {"ms": round(v["ms"], 3), "share": round(v["ms"] / tot, 4), "launches": v["launches"],
