@@ -4,7 +4,8 @@
 //
 //   qkv_split_kernel   fp32 qkv [B][T][H*3*ch] (legacy head layout, unet.py:116-118) -> fp16 hi/lo images:
 //                        K    : [k-step = ch/32][hi|lo][T/8][4][8 pos][8 ch]   (K-major core matrices; a row range is contiguous)
-//                        Q    : the same with the query rows of each 128-row tile in the conv kernel's phase-strided order:
+//                        All three images hold their rows (queries; keys of K and V alike -- the key order is free as long as K and V
+//                        agree) in the conv kernel's phase-strided order, per 128-row tile:
 //                               a tile holds nseg = min(8, T/16 - 8*tile) segments of 16 positions, and its row m is position
 //                               tile*128 + (m % nseg)*16 + m / nseg (attn_q_row): consecutive rows = the same slot of consecutive
 //                               segments.  A TMEM lane of the qkv conv and of this kernel is then (slot, segment) with the
@@ -73,15 +74,15 @@ __global__ void qkv_split_kernel(const float* __restrict__ qkv, uint8_t* __restr
     const size_t plane = (size_t)4 * ch * T;                       // bytes of one of q / k / v (hi + lo)
     uint8_t* base = dst + ((size_t)b * H + h) * 3 * plane + (size_t)which * plane;
     size_t ohi, olo;
-    if (which < 2) {   // Q, K: [ks][hi|lo][T/8][4][8][8]; Q rows in the phase-strided tile order
+    const int tr = attn_q_row(t, T);   // image row of position t: queries and keys in the phase-strided tile order
+    if (which < 2) {   // Q, K: [ks][hi|lo][T/8][4][8][8]
         const int ks = c / 32, cg = (c % 32) / 8;
-        const int tr = which == 0 ? attn_q_row(t, T) : t;
         const size_t o = (size_t)(tr / 8) * 512 + cg * 128 + (tr % 8) * 16;
         ohi = ((size_t)ks * 2 + 0) * ((size_t)T * 64) + o;
         olo = ((size_t)ks * 2 + 1) * ((size_t)T * 64) + o;
     } else {           // V: [ch/128][T/32][hi|lo][4][16][8][8]
-        const size_t blk = (size_t)(c / 128) * (T / 32) + t / 32;
-        const size_t o = (size_t)((t % 32) / 8) * 2048 + ((c % 128) / 8) * 128 + (t % 8) * 16;
+        const size_t blk = (size_t)(c / 128) * (T / 32) + tr / 32;
+        const size_t o = (size_t)((tr % 32) / 8) * 2048 + ((c % 128) / 8) * 128 + (tr % 8) * 16;
         ohi = (blk * 2 + 0) * V_HALF + o;
         olo = (blk * 2 + 1) * V_HALF + o;
     }

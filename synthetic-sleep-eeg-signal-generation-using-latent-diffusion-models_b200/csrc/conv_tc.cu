@@ -321,28 +321,24 @@ __global__ void __launch_bounds__(conv_tc_threads(DIRECT, EPI8), 1) conv_tc_kern
                 // qkv conv of an AttentionBlock (unet.py:158): the output's only consumer is attn_tc.cu, so q, k, v go straight into
                 // its fp16 hi/lo operand images (layout: qkv_split_kernel) -- no fp32 tensor, no qkv_split pass.  A TMEM lane is one
                 // position and 16 consecutive columns are two 8-channel image items of 16 bytes each (x hi, lo): no shared-memory
-                // transpose.  The four lanes (l, l+8, l+16, l+24) of one segment hold consecutive positions = 64 contiguous bytes
-                // of a core matrix; one lane permutation (16 shuffles) makes them ADJACENT lanes, so that each quarter-warp phase
-                // of a 128-bit store covers two 64-byte runs instead of eight 16-byte pieces of eight lines (measured: 5.8 k
-                // cycles of stores per tile in the unpermuted form vs 3.9 k for everything else, tools/conv_timeline.py).
+                // transpose.  The rows of all three images are in this tile's phase-strided order (attn_tc.cu, attn_q_row: queries AND
+                // keys -- the attention only needs K and V to agree on the key order), so lane = (slot, segment) with the segment
+                // fastest and eight consecutive lanes store one 128-byte core-matrix row set.  (In position order the four lanes
+                // l, l+8, l+16, l+24 of a segment hold consecutive rows: 16-byte pieces of eight lines per store cost 5.8 k cycles per
+                // tile, a 16-shuffle lane permutation to 64-byte runs 0.9 k + 1.2 k, this order 0.9 k: tools/conv_timeline.py.)
                 const int ch = p.qkv_ch, T = p.Tout;
                 const int cq = co0 / (3 * ch), rem = co0 - cq * 3 * ch, which = rem / ch, c0 = rem - which * ch;   // head, q|k|v, channel
-                // Q keeps the TMEM lane order (the Q image's rows are phase-strided like this tile: attn_tc.cu): lane = (slot, segment)
-                // with the segment fastest, eight consecutive lanes store one 128-byte core-matrix row set.  K and V lanes are permuted.
-                const bool isq = which == 0;
-                const int sg = isq ? (lane & 7) : (lane >> 2), pos = ew * 4 + (isq ? (lane >> 3) : (lane & 3));   // (segment, position) this lane STORES
-                const int src_lane = ((lane & 3) << 3) | (lane >> 2);          // K, V: the lane whose TMEM row that is
+                const int sg = lane & 7, pos = ew * 4 + (lane >> 3);   // (segment, position) of this lane's TMEM row
                 const int g = m_tile * 8 + sg;
                 const bool valid = g < p.nsegs16;
-                const int b = valid ? g / spt : 0, s_in = g % spt, t = s_in * 16 + pos;
-                // Q image row of this position (attn_tc.cu, attn_q_row): tile s_in / 8 holds nseg segments, rows run over them first
-                const int nseg = min(8, spt - (s_in & ~7)), qrow = (s_in >> 3) * 128 + nseg * pos + (s_in & 7);
+                const int b = valid ? g / spt : 0, s_in = g % spt;
+                // image row of this position (attn_tc.cu, attn_q_row): tile s_in / 8 holds nseg segments, rows run over them first
+                const int nseg = min(8, spt - (s_in & ~7)), t = (s_in >> 3) * 128 + nseg * pos + (s_in & 7);
                 const size_t plane = (size_t)4 * ch * T;
                 const size_t half = which < 2 ? (size_t)T * 64 : 8192;
                 uint8_t* base = p.qkv16 + (((size_t)b * p.qkv_H + cq) * 3 + which) * plane +
-                                (isq ? (size_t)(qrow >> 3) * 512 + (qrow & 7) * 16
-                                     : (which == 1 ? (size_t)(t >> 3) * 512 + (t & 7) * 16
-                                                   : (size_t)(t >> 5) * 2 * half + ((t & 31) >> 3) * 2048 + (t & 7) * 16));
+                                (which < 2 ? (size_t)(t >> 3) * 512 + (t & 7) * 16
+                                           : (size_t)(t >> 5) * 2 * half + ((t & 31) >> 3) * 2048 + (t & 7) * 16);
                 const float* bias_p = p.bias && !(p.debug & 512) ? p.bias + co0 : nullptr;
                 const bool do_store = valid && !(p.debug & 256);   // (debug bits 256 / 512: timing experiments, tools/conv_timeline.py)
                 TL_WAIT(tl_a, mbar_wait(barAccFull + 8 * as, use & 1));
@@ -381,13 +377,6 @@ __global__ void __launch_bounds__(conv_tc_threads(DIRECT, EPI8), 1) conv_tc_kern
                                              f[8 * it + 6] + bi[2 * it + 1].z, f[8 * it + 7] + bi[2 * it + 1].w};
                         bad |= out_of_f16_range(v8);
                         split8_f16(v8, pc[2 * it], pc[2 * it + 1]);
-                    }
-                    if (!isq) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            pc[j].x = __shfl_sync(0xffffffffu, pc[j].x, src_lane); pc[j].y = __shfl_sync(0xffffffffu, pc[j].y, src_lane);
-                            pc[j].z = __shfl_sync(0xffffffffu, pc[j].z, src_lane); pc[j].w = __shfl_sync(0xffffffffu, pc[j].w, src_lane);
-                        }
                     }
                     if (do_store) {
                         *reinterpret_cast<uint4*>(dst) = pc[0];
